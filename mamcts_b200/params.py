@@ -1,0 +1,59 @@
+"""Python-side constructors of the parameter structs, mirroring the reference defaults.
+
+mcts_default_parameters()                 : reference mcts/mcts_parameters.h:97-135
+default_crossing_state_parameters<int>()  : reference environments/crossing_state_parameters.h:36-59
+SimpleState constants                     : reference test/uct/simple_state.h:16
+"""
+from __future__ import annotations
+
+from ._abi import CrossingParams, Params, SimpleParams
+
+
+def default_params(**over) -> Params:
+    p = Params()
+    p.discount_factor = 0.9
+    p.random_seed = 1000
+    p.max_number_of_iterations = 10000
+    p.max_number_of_nodes = 10000
+    p.max_search_depth = 1000
+    p.use_bound_estimation = 1
+    p.num_parallel_mcts = 1
+    p.rh_max_number_of_iterations = 1000
+    p.uct_lower_bound = -1000.0
+    p.uct_upper_bound = 100.0
+    p.uct_exploration_constant = 0.7
+    p.uct_pw_k = 4.0
+    p.uct_pw_alpha = 0.25
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def default_crossing_params(**over) -> CrossingParams:
+    c = CrossingParams()
+    c.num_other_agents = 2
+    c.cost_only_collision = 0
+    c.max_velocity_other = 3
+    c.min_velocity_other = -3
+    c.max_velocity_ego = 2
+    c.min_velocity_ego = -1
+    c.chain_length = 21
+    c.ego_goal_pos = 12
+    c.num_other_actions = 7
+    c.reward_collision = -1000.0
+    c.reward_goal_reached = 100.0
+    c.reward_step = 0.0
+    for k, v in over.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def default_simple_params() -> SimpleParams:
+    s = SimpleParams()
+    s.winning_state_length = 10
+    s.loosing_state_length = -1
+    return s

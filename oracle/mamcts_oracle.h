@@ -1,0 +1,145 @@
+/*
+ * oracle/mamcts_oracle.h - CPU restatement (plain C) of the MA-MCTS rollout-and-backup hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY. Nothing under mamcts_b200/ may include, link or call this; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it,
+ * and only as the checker. Each function cites the reference (juloberno/mamcts) file:line it
+ * restates. Parity status: PINNED - validated against the unmodified reference compiled into
+ * oracle/_ref/libmamcts_ref.so (tests/test_oracle_vs_reference.py) and against the golden
+ * vectors in tests/golden/ generated from it (tests/golden/make_golden.py).
+ */
+#ifndef MAMCTS_ORACLE_H_
+#define MAMCTS_ORACLE_H_
+
+#include <stdint.h>
+#include "mamcts_b200.h" /* parameter structs only (the public C ABI header) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_AGENTS MAMCTS_MAX_AGENTS
+#define ORC_MAX_ACTIONS MAMCTS_MAX_ACTIONS
+
+/* ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3",
+ * SC'11; the Random123 reference constants). The PHILOX action source is NOT in the reference
+ * (its rollouts are deterministic); the stream layout is specified in DESIGN.md §5. */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* Unbiased draw in [0, n) from 16-bit lane `pos` of stream (stream_hi, stream_lo). */
+uint32_t orc_philox_draw(uint64_t seed, uint32_t stream_hi, uint32_t stream_lo, uint32_t pos,
+                         uint32_t n);
+
+/* ---- environments ------------------------------------------------------------------------ */
+
+typedef struct orc_state {
+  int32_t x[ORC_MAX_AGENTS];    /* Crossing: x_pos per agent (ego first); Simple: x[0] = length */
+  int32_t last[ORC_MAX_AGENTS]; /* Crossing: last_action */
+  uint8_t terminal, goal, collided, pad;
+} orc_state;
+
+/* CrossingState<int>::execute (environments/crossing_state.h:115-163).
+ * action[0] = ego action index; action[1..] = the int the reference bit-casts out of the
+ * other agent's ActionIdx (crossing_state_common.h:19-27). Writes the ego reward and cost[0]. */
+void orc_crossing_execute(const mamcts_crossing_params* cp, const orc_state* s,
+                          const int32_t* action, orc_state* next, double* ego_reward,
+                          double* cost0);
+/* SimpleState::execute (test/uct/simple_state.h:26-54). rewards[2]. */
+void orc_simple_execute(const mamcts_simple_params* sp, const orc_state* s, const int32_t* action,
+                        orc_state* next, double* rewards);
+
+/* ---- rollout: RandomHeuristic::rollout (mcts/heuristics/random_heuristic.h:27-104) -------- */
+
+typedef struct orc_env {
+  int32_t env;                       /* MAMCTS_ENV_* */
+  uint32_t num_agents;               /* A */
+  uint32_t num_actions[ORC_MAX_AGENTS];
+  mamcts_crossing_params crossing;
+  mamcts_simple_params simple;
+} orc_env;
+
+void orc_env_crossing(orc_env* env, const mamcts_crossing_params* cp);
+void orc_env_simple(orc_env* env, const mamcts_simple_params* sp);
+
+typedef struct orc_rollout_result {
+  double ego_return;
+  double other_return[ORC_MAX_AGENTS];   /* index j = other j (position j+1) */
+  double cost0;
+  double step_length;
+  uint32_t steps;
+  orc_state final_state;
+} orc_rollout_result;
+
+/* One rollout. Action source as in mamcts_action_source but for ONE rollout:
+ *   kind REPLAY: replay[step*A + agent] (int8), replay_steps steps available;
+ *   kind REFERENCE_CONST: const_actions[agent]; kind PHILOX: (seed, stream_hi, stream_lo).
+ * reward_trace (optional) receives the ego step rewards, up to trace_cap entries. */
+void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* start,
+                 uint32_t start_depth, int32_t kind, const int8_t* replay, uint32_t replay_steps,
+                 const uint32_t* const_actions, uint64_t seed, uint32_t stream_hi,
+                 uint32_t stream_lo, orc_rollout_result* out, double* reward_trace,
+                 uint32_t trace_cap);
+
+/* The K-rollout mean of one leaf in the engine's fixed reduction order.
+ * vals[k], k < K. K in {1,2,4,8,16} or a multiple of 32 (<=256) or a multiple of 256. */
+double orc_reduce_mean(const double* vals, uint32_t K);
+
+/* ---- backup: UctStatistic (mcts/statistics/uct_statistic.h) -------------------------------- */
+
+typedef struct orc_stat {
+  double value;                       /* value_ */
+  double latest_return;               /* latest_return_ */
+  uint32_t total_visits;              /* total_node_visits_ */
+  uint32_t num_actions;
+  uint32_t num_expanded;
+  uint8_t expanded[ORC_MAX_ACTIONS];  /* action present in ucb_statistics_ */
+  uint32_t n[ORC_MAX_ACTIONS];        /* action_count_ */
+  double q[ORC_MAX_ACTIONS];          /* action_value_ */
+  uint32_t collected_action;          /* collected_reward_.first (node_statistic.h:115-121) */
+  double collected_reward;            /* collected_reward_.second */
+} orc_stat;
+
+void orc_stat_init(orc_stat* s, uint32_t num_actions);
+/* UctStatistic::update_from_heuristic (uct_statistic.h:100-110). */
+void orc_stat_update_from_heuristic(orc_stat* s, double h);
+/* UctStatistic::update_statistics_from_backpropagated (uct_statistic.h:134-144). */
+void orc_stat_backprop(orc_stat* s, double gamma, double child_latest_return);
+/* UctStatistic::choose_next_action (uct_statistic.h:61-76, 223-244, 256-262, 122-132);
+ * expand_order = the statistic's deterministic widening order (mamcts_reference_expand_order). */
+uint32_t orc_stat_choose_next_action(orc_stat* s, const mamcts_params* mp,
+                                     const uint32_t* expand_order);
+/* UctStatistic::get_best_action (uct_statistic.h:78-89). */
+uint32_t orc_stat_best_action(const orc_stat* s);
+/* UctStatistic::merge_node_statistics (uct_statistic.h:165-184) over n ego root statistics. */
+void orc_stat_merge(const orc_stat* const* stats, uint32_t n, orc_stat* merged);
+
+/* ---- whole search: Mcts::search / iterate (mcts/mcts.h:166-186,294-333) + StageNode
+ * (mcts/stage_node.h:167-271) on an arena tree --------------------------------------------- */
+
+typedef struct orc_tree orc_tree;
+
+typedef struct orc_search_config {
+  orc_env env;
+  mamcts_params mcts;
+  int32_t action_source;       /* REFERENCE_CONST or PHILOX */
+  uint32_t rollouts_per_leaf;  /* K */
+  uint64_t philox_seed;
+  uint32_t tree_id;            /* global tree id = Philox stream_hi */
+  /* per-agent widening order, [A][ORC_MAX_ACTIONS] (mamcts_reference_expand_order) */
+  uint32_t expand_order[ORC_MAX_AGENTS][ORC_MAX_ACTIONS];
+} orc_search_config;
+
+orc_tree* orc_tree_create(const orc_search_config* cfg, const orc_state* root);
+void orc_tree_destroy(orc_tree* t);
+/* Runs `iterations` MCTS iterations. */
+void orc_tree_run(orc_tree* t, uint32_t iterations);
+uint32_t orc_tree_num_nodes(const orc_tree* t);
+uint64_t orc_tree_rollout_steps(const orc_tree* t);
+const orc_stat* orc_tree_root_stat(const orc_tree* t, uint32_t agent);
+/* Canonical dump, same record format as mamcts_search_dump_tree. Returns number of records. */
+uint32_t orc_tree_dump(const orc_tree* t, double* records, uint32_t capacity_records,
+                       uint32_t max_actions);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

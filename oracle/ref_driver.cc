@@ -1,0 +1,639 @@
+// oracle/ref_driver.cc - drives the UNMODIFIED reference (juloberno/mamcts headers, included from
+// where they lie under $MAMCTS_REFERENCE, default /root/reference) behind a small C interface so
+// that tests can pin oracle/mamcts_oracle.c and the CUDA engine against the real thing, and so
+// that bench.py can time the reference's own CPU path.
+//
+// TEST INFRASTRUCTURE ONLY. Built by oracle/Makefile into oracle/_ref/libmamcts_ref.so (git-ignored,
+// travels to the GPU box). No reference source is copied into this repository: this file only
+// instantiates the reference's templates and reads their results.
+//
+// Wall-clock cut-offs (MAX_SEARCH_TIME, random_heuristic.MAX_SEARCH_TIME) are set huge so the
+// reference is deterministic.
+
+#define UNIT_TESTING  // mcts/common.h:16-20: MCTS_TEST -> `friend class UctTest`
+#include <chrono>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <sstream>
+#include <thread>
+#include <vector>
+
+#include "mcts/mcts.h"
+#include "mcts/heuristics/random_heuristic.h"
+#include "mcts/statistics/uct_statistic.h"
+#include "environments/crossing_state.h"
+#include "test/uct/simple_state.h"
+
+#include "mamcts_b200.h"
+#include "mamcts_oracle.h"
+
+using namespace mcts;
+
+namespace {
+
+MctsParameters to_ref_params(const mamcts_params& p) {
+  MctsParameters r = mcts_default_parameters();
+  r.DISCOUNT_FACTOR = p.discount_factor;
+  r.RANDOM_SEED = p.random_seed;
+  r.MAX_NUMBER_OF_ITERATIONS = p.max_number_of_iterations;
+  r.MAX_SEARCH_TIME = 1000000000u;  // F2
+  r.MAX_SEARCH_DEPTH = p.max_search_depth;
+  r.MAX_NUMBER_OF_NODES = p.max_number_of_nodes;
+  r.USE_BOUND_ESTIMATION = p.use_bound_estimation != 0;
+  r.NUM_PARALLEL_MCTS = p.num_parallel_mcts ? p.num_parallel_mcts : 1;
+  r.USE_MULTI_THREADING = false;
+  r.random_heuristic.MAX_SEARCH_TIME = 1e9;  // F2
+  r.random_heuristic.MAX_NUMBER_OF_ITERATIONS = p.rh_max_number_of_iterations;
+  r.uct_statistic.LOWER_BOUND = p.uct_lower_bound;
+  r.uct_statistic.UPPER_BOUND = p.uct_upper_bound;
+  r.uct_statistic.EXPLORATION_CONSTANT = p.uct_exploration_constant;
+  r.uct_statistic.PROGRESSIVE_WIDENING_K = p.uct_pw_k;
+  r.uct_statistic.PROGRESSIVE_WIDENING_ALPHA = p.uct_pw_alpha;
+  return r;
+}
+
+CrossingStateParameters<int> to_ref_crossing(const mamcts_crossing_params& c) {
+  CrossingStateParameters<int> r = default_crossing_state_parameters<int>();
+  r.NUM_OTHER_AGENTS = c.num_other_agents;
+  r.COST_ONLY_COLLISION = c.cost_only_collision != 0;
+  r.MAX_VELOCITY_OTHER = c.max_velocity_other;
+  r.MIN_VELOCITY_OTHER = c.min_velocity_other;
+  r.NUM_OTHER_ACTIONS = c.num_other_actions;
+  r.MAX_VELOCITY_EGO = c.max_velocity_ego;
+  r.MIN_VELOCITY_EGO = c.min_velocity_ego;
+  r.CHAIN_LENGTH = c.chain_length;
+  r.EGO_GOAL_POS = c.ego_goal_pos;
+  r.REWARD_COLLISION = c.reward_collision;
+  r.REWARD_GOAL_REACHED = c.reward_goal_reached;
+  r.REWARD_STEP = c.reward_step;
+  return r;
+}
+
+// ---- recording -----------------------------------------------------------------------------
+struct StepRecord {
+  std::vector<long long> action;  // JointAction entries reinterpreted as signed
+  std::vector<double> rewards;
+  std::vector<double> cost;
+  bool terminal_after;
+};
+struct Recorder {
+  std::vector<StepRecord> steps;
+};
+thread_local Recorder* g_recorder = nullptr;
+
+// A State that forwards every concept call to the wrapped reference state and logs execute().
+// RandomHeuristic::rollout only touches the state through these methods
+// (mcts/heuristics/random_heuristic.h:36-91).
+template <class Inner>
+class RecState : public StateInterface<RecState<Inner>> {
+ public:
+  explicit RecState(std::shared_ptr<Inner> inner) : inner_(std::move(inner)) {}
+  std::shared_ptr<RecState> clone() const { return std::make_shared<RecState>(inner_->clone()); }
+  std::shared_ptr<RecState> execute(const JointAction& ja, std::vector<Reward>& rewards,
+                                    EgoCosts& cost) const {
+    auto next = inner_->execute(ja, rewards, cost);
+    if (g_recorder) {
+      StepRecord rec;
+      for (auto a : ja) rec.action.push_back(static_cast<long long>(a));
+      rec.rewards = rewards;
+      rec.cost = cost;
+      rec.terminal_after = next->is_terminal();
+      g_recorder->steps.push_back(rec);
+    }
+    return std::make_shared<RecState>(next);
+  }
+  ActionIdx get_num_actions(AgentIdx a) const { return inner_->get_num_actions(a); }
+  bool is_terminal() const { return inner_->is_terminal(); }
+  const std::vector<AgentIdx> get_other_agent_idx() const { return inner_->get_other_agent_idx(); }
+  const AgentIdx get_ego_agent_idx() const { return inner_->get_ego_agent_idx(); }
+  const std::size_t get_num_costs() const { return inner_->get_num_costs(); }
+  double get_execution_step_length() const { return inner_->get_execution_step_length(); }
+  void choose_random_seed(const unsigned& s) { inner_->choose_random_seed(s); }
+  std::string sprintf() const { return inner_->sprintf(); }
+  const Inner& inner() const { return *inner_; }
+
+ private:
+  std::shared_ptr<Inner> inner_;
+};
+
+// Long-lived pieces a CrossingState<int> keeps references to (crossing_state.h:320, hypothesis_state.h:42).
+struct CrossingWorld {
+  CrossingStateParameters<int> params;
+  std::unordered_map<AgentIdx, HypothesisId> hypothesis_map;
+  explicit CrossingWorld(const mamcts_crossing_params& c) : params(to_ref_crossing(c)) {
+    for (AgentIdx i = 1; i <= c.num_other_agents; ++i) hypothesis_map[i] = 0;
+  }
+  std::shared_ptr<CrossingState<int>> make(const int32_t* x, const int32_t* last, bool terminal) {
+    std::vector<AgentState<int>> others;
+    for (unsigned i = 0; i < params.NUM_OTHER_AGENTS; ++i)
+      others.emplace_back(x[i + 1], last ? last[i + 1] : 2);
+    AgentState<int> ego(x[0], last ? last[0] : 2);
+    return std::make_shared<CrossingState<int>>(hypothesis_map, params, others, ego, terminal,
+                                                false, false,
+                                                std::vector<AgentPolicyCrossingState<int>>());
+  }
+};
+
+// ---- stochastic twin: the reference's Mcts/StageNode/UctStatistic with a Philox heuristic -----
+struct PhiloxCtx {
+  orc_env env;
+  mamcts_params mp;
+  uint64_t seed;
+  uint32_t tree_id;
+  uint32_t K;
+  uint64_t rollout_steps;
+};
+thread_local PhiloxCtx g_philox;
+
+void pack_state(const CrossingState<int>& s, orc_state* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->x[0] = s.get_ego_state().x_pos;
+  o->last[0] = s.get_ego_state().last_action;
+  const auto& oth = s.get_agent_states();
+  for (size_t i = 0; i < oth.size(); ++i) {
+    o->x[i + 1] = oth[i].x_pos;
+    o->last[i + 1] = oth[i].last_action;
+  }
+  o->terminal = s.is_terminal();
+  o->goal = s.ego_goal_reached();
+  o->collided = s.ego_collided();
+}
+void pack_state(const SimpleState& s, orc_state* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->x[0] = s.get_state_length();
+  o->terminal = s.is_terminal();
+}
+
+// Heuristic concept (mcts/heuristic.h:24-41) whose rollout body is oracle/mamcts_oracle.c's
+// orc_rollout in PHILOX mode, stream (tree_id, node_index*K + k); node_index = number of
+// heuristic calls so far (== creation index of the node being evaluated).
+class PhiloxHeuristic : public mcts::Heuristic<PhiloxHeuristic> {
+ public:
+  explicit PhiloxHeuristic(const MctsParameters& p) : mcts::Heuristic<PhiloxHeuristic>(p), calls_(0) {}
+  template <class S, class SE, class SO, class H>
+  std::pair<SE, std::unordered_map<AgentIdx, SO>> calculate_heuristic_values(
+      const std::shared_ptr<StageNode<S, SE, SO, H>>& node) {
+    ++calls_;
+    PhiloxCtx& c = g_philox;
+    orc_state st;
+    pack_state(*node->get_state(), &st);
+    const uint32_t A = c.env.num_agents;
+    std::vector<double> ego(c.K), oth(static_cast<size_t>(c.K) * ORC_MAX_AGENTS);
+    for (uint32_t k = 0; k < c.K; ++k) {
+      orc_rollout_result rr;
+      orc_rollout(&c.env, &c.mp, &st, node->get_depth(), MAMCTS_SRC_PHILOX, nullptr, 0, nullptr,
+                  c.seed, c.tree_id, calls_ * c.K + k, &rr, nullptr, 0);
+      c.rollout_steps += rr.steps;
+      ego[k] = rr.ego_return;
+      for (uint32_t j = 0; j + 1 < A; ++j) oth[static_cast<size_t>(j) * c.K + k] = rr.other_return[j];
+    }
+    SE ego_h(0, node->get_state()->get_ego_agent_idx(), mcts_parameters_);
+    ego_h.set_heuristic_estimate(orc_reduce_mean(ego.data(), c.K), EgoCosts());
+    std::unordered_map<AgentIdx, SO> others;
+    uint32_t j = 0;
+    for (auto ai : node->get_state()->get_other_agent_idx()) {
+      SO st_o(0, ai, mcts_parameters_);
+      st_o.set_heuristic_estimate(orc_reduce_mean(oth.data() + static_cast<size_t>(j) * c.K, c.K),
+                                  EgoCosts());
+      others.insert(std::pair<AgentIdx, SO>(ai, st_o));
+      ++j;
+    }
+    return std::pair<SE, std::unordered_map<AgentIdx, SO>>(ego_h, others);
+  }
+  std::string sprintf() const { return "PhiloxHeuristic"; }
+
+ private:
+  uint32_t calls_;
+};
+
+}  // namespace
+
+// White-box reader: the reference grants `friend class UctTest` under UNIT_TESTING.
+class mcts::UctTest {
+ public:
+  static void read_stat(const UctStatistic& s, double* value, double* latest, uint32_t* visits,
+                        double* q, int64_t* n, uint32_t max_actions) {
+    *value = s.value_;
+    *latest = s.latest_return_;
+    *visits = s.total_node_visits_;
+    for (uint32_t a = 0; a < max_actions; ++a) { q[a] = 0.0; n[a] = -1; }
+    for (const auto& kv : s.ucb_statistics_) {
+      if (kv.first < max_actions) {
+        q[kv.first] = kv.second.action_value_;
+        n[kv.first] = kv.second.action_count_;
+      }
+    }
+  }
+  static void force_visits(UctStatistic& s, unsigned v) { s.total_node_visits_ = v; }
+
+  template <class S, class H>
+  static uint32_t dump(const std::shared_ptr<StageNode<S, UctStatistic, UctStatistic, H>>& node,
+                       double* rec, uint32_t cap, uint32_t count, uint32_t max_actions) {
+    const uint32_t A = node->state_->get_num_agents();
+    const uint32_t stride = 4 + A * (3 + 2 * max_actions);
+    auto code_of = [&](const JointAction& ja) {
+      double code = 0.0, mul = 1.0;
+      for (uint32_t a = 0; a < A; ++a) { code += mul * static_cast<double>(ja[a]); mul *= max_actions; }
+      return code;
+    };
+    if (count < cap) {
+      double* r = rec + static_cast<size_t>(count) * stride;
+      r[0] = node->depth_;
+      r[1] = node->is_root() ? -1.0 : code_of(node->joint_action_);
+      r[2] = node->visit_count_;
+      r[3] = static_cast<double>(node->children_.size());
+      auto emit = [&](const UctStatistic& st, uint32_t a) {
+        double* s = r + 4 + a * (3 + 2 * max_actions);
+        double v, l; uint32_t nv;
+        std::vector<double> q(max_actions);
+        std::vector<int64_t> n(max_actions);
+        read_stat(st, &v, &l, &nv, q.data(), n.data(), max_actions);
+        s[0] = nv; s[1] = v; s[2] = l;
+        for (uint32_t k = 0; k < max_actions; ++k) {
+          s[3 + k] = static_cast<double>(n[k]);
+          s[3 + max_actions + k] = q[k];
+        }
+      };
+      emit(node->ego_int_node_, 0);
+      for (uint32_t j = 0; j < node->other_int_nodes_.size(); ++j) emit(node->other_int_nodes_[j], j + 1);
+    }
+    ++count;
+    std::map<double, std::shared_ptr<StageNode<S, UctStatistic, UctStatistic, H>>> sorted;
+    for (const auto& kv : node->children_) sorted[code_of(kv.first)] = kv.second;
+    for (const auto& kv : sorted) count = dump<S, H>(kv.second, rec, cap, count, max_actions);
+    return count;
+  }
+
+  template <class S, class H>
+  static std::shared_ptr<StageNode<S, UctStatistic, UctStatistic, H>> root_of(
+      Mcts<S, UctStatistic, UctStatistic, H>& m) {
+    return m.root_;
+  }
+};
+
+namespace {
+
+struct SearchOut {
+  uint32_t num_nodes;
+  uint32_t num_iterations;
+  uint32_t best_action;
+};
+
+template <class S, class H>
+void run_search_and_dump(const S& state, const MctsParameters& rp, uint32_t num_agents,
+                         uint32_t max_actions, double* root_value, double* root_latest,
+                         uint32_t* root_visits, double* root_q, int64_t* root_n,
+                         uint32_t* counters /*[3]: nodes, iterations, best*/, double* tree_records,
+                         uint32_t tree_capacity, uint32_t* tree_count) {
+  Mcts<S, UctStatistic, UctStatistic, H> mcts(rp);
+  mcts.search(state);
+  const auto& root = mcts.get_root();
+  UctTest::read_stat(root.get_ego_int_node(), &root_value[0], &root_latest[0], &root_visits[0],
+                     root_q, root_n, max_actions);
+  for (uint32_t j = 0; j + 1 < num_agents; ++j) {
+    UctTest::read_stat(root.get_other_int_nodes()[j], &root_value[j + 1], &root_latest[j + 1],
+                       &root_visits[j + 1], root_q + (j + 1) * max_actions,
+                       root_n + (j + 1) * max_actions, max_actions);
+  }
+  counters[0] = mcts.numNodes();
+  counters[1] = mcts.numIterations();
+  counters[2] = static_cast<uint32_t>(mcts.returnBestAction());
+  if (tree_records && tree_count && rp.NUM_PARALLEL_MCTS <= 1) {
+    *tree_count = UctTest::dump<S, H>(UctTest::root_of<S, H>(mcts), tree_records, tree_capacity, 0,
+                                      max_actions);
+  } else if (tree_count) {
+    *tree_count = 0;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// The widening order of a real UctStatistic with `num_actions` actions
+// (mcts/statistics/uct_statistic.h:61-69): total_node_visits_ is forced high so that
+// require_progressive_widening_total() stays true until every action is expanded.
+int ref_uct_expand_order(const mamcts_params* mp, uint32_t num_actions, uint32_t* order) {
+  MctsParameters rp = to_ref_params(*mp);
+  UctStatistic stat(num_actions, 0, rp);
+  UctTest::force_visits(stat, 1000000000u);
+  rp.uct_statistic.PROGRESSIVE_WIDENING_K = 1e9;
+  UctStatistic wide(num_actions, 0, rp);
+  UctTest::force_visits(wide, 1000000000u);
+  SimpleState dummy(0);
+  for (uint32_t k = 0; k < num_actions; ++k) order[k] = static_cast<uint32_t>(wide.choose_next_action(dummy));
+  return 0;
+}
+
+// RandomHeuristic::rollout<RecState<CrossingState<int>>, UctStatistic, UctStatistic, RandomHeuristic>
+// from n start states (SoA x[a*n+i]); records every execute().
+//   rec_actions: int8 [n][rec_stride][A] (ego index, other bit-cast value), rec_rewards [n][rec_stride],
+//   rec_steps[n].
+int ref_rollout_crossing(const mamcts_params* mp, const mamcts_crossing_params* cp, uint32_t n,
+                         const int32_t* x, const int32_t* last, const uint8_t* flags,
+                         const uint32_t* depth, double* ego_ret, double* other_ret, double* cost0,
+                         double* step_len, uint32_t* steps, int32_t* final_x, int32_t* final_last,
+                         uint8_t* final_flags, int8_t* rec_actions, double* rec_rewards,
+                         uint32_t rec_stride) {
+  const MctsParameters rp = to_ref_params(*mp);
+  CrossingWorld world(*cp);
+  const uint32_t A = cp->num_other_agents + 1;
+  using RS = RecState<CrossingState<int>>;
+  for (uint32_t i = 0; i < n; ++i) {
+    std::vector<int32_t> xi(A), li(A);
+    for (uint32_t a = 0; a < A; ++a) { xi[a] = x[a * n + i]; li[a] = last ? last[a * n + i] : 2; }
+    auto inner = world.make(xi.data(), li.data(), flags ? (flags[i] & 1) : false);
+    auto start = std::make_shared<RS>(inner);
+    Recorder rec;
+    g_recorder = &rec;
+    auto result = RandomHeuristic::rollout<RS, UctStatistic, UctStatistic, RandomHeuristic>(
+        start, rp, depth ? depth[i] : 0);
+    g_recorder = nullptr;
+    ego_ret[i] = std::get<0>(result);
+    const auto& others = std::get<1>(result);
+    for (uint32_t j = 0; j + 1 < A; ++j) other_ret[j * n + i] = others.at(j + 1);
+    const auto& costs = std::get<2>(result);
+    cost0[i] = costs.empty() ? 0.0 : costs[0];
+    step_len[i] = std::get<3>(result);
+    steps[i] = static_cast<uint32_t>(rec.steps.size());
+    // replay the recorded actions on the plain reference state to obtain the final state
+    std::shared_ptr<CrossingState<int>> cur = inner;
+    for (size_t s = 0; s < rec.steps.size(); ++s) {
+      JointAction ja(A);
+      for (uint32_t a = 0; a < A; ++a) ja[a] = static_cast<ActionIdx>(rec.steps[s].action[a]);
+      std::vector<Reward> r; EgoCosts c;
+      cur = cur->execute(ja, r, c);
+      if (s < rec_stride) {
+        if (rec_actions) {
+          rec_actions[(static_cast<size_t>(i) * rec_stride + s) * A + 0] = static_cast<int8_t>(ja[0]);
+          for (uint32_t a = 1; a < A; ++a)
+            rec_actions[(static_cast<size_t>(i) * rec_stride + s) * A + a] =
+                static_cast<int8_t>(aconv<int>(ja[a]));
+        }
+        if (rec_rewards) rec_rewards[static_cast<size_t>(i) * rec_stride + s] = rec.steps[s].rewards[0];
+      }
+    }
+    orc_state fs;
+    pack_state(*cur, &fs);
+    for (uint32_t a = 0; a < A; ++a) {
+      if (final_x) final_x[a * n + i] = fs.x[a];
+      if (final_last) final_last[a * n + i] = fs.last[a];
+    }
+    if (final_flags) final_flags[i] = (fs.terminal ? 1 : 0) | (fs.goal ? 2 : 0) | (fs.collided ? 4 : 0);
+  }
+  return 0;
+}
+
+// Same for SimpleState (agents 4 and 5 -> positions 0 and 1).
+int ref_rollout_simple(const mamcts_params* mp, uint32_t n, const int32_t* len,
+                       const uint32_t* depth, double* ego_ret, double* other_ret,
+                       double* step_len, uint32_t* steps, int32_t* final_len,
+                       int8_t* rec_actions, double* rec_rewards, uint32_t rec_stride) {
+  const MctsParameters rp = to_ref_params(*mp);
+  using RS = RecState<SimpleState>;
+  for (uint32_t i = 0; i < n; ++i) {
+    auto inner = std::make_shared<SimpleState>(len[i]);
+    auto start = std::make_shared<RS>(inner);
+    Recorder rec;
+    g_recorder = &rec;
+    auto result = RandomHeuristic::rollout<RS, UctStatistic, UctStatistic, RandomHeuristic>(
+        start, rp, depth ? depth[i] : 0);
+    g_recorder = nullptr;
+    ego_ret[i] = std::get<0>(result);
+    other_ret[i] = std::get<1>(result).at(5);
+    step_len[i] = std::get<3>(result);
+    steps[i] = static_cast<uint32_t>(rec.steps.size());
+    std::shared_ptr<SimpleState> cur = inner;
+    for (size_t s = 0; s < rec.steps.size(); ++s) {
+      JointAction ja(2);
+      ja[0] = rec.steps[s].action[0]; ja[1] = rec.steps[s].action[1];
+      std::vector<Reward> r; EgoCosts c;
+      cur = cur->execute(ja, r, c);
+      if (s < rec_stride) {
+        if (rec_actions) {
+          rec_actions[(static_cast<size_t>(i) * rec_stride + s) * 2 + 0] = static_cast<int8_t>(ja[0]);
+          rec_actions[(static_cast<size_t>(i) * rec_stride + s) * 2 + 1] = static_cast<int8_t>(ja[1]);
+        }
+        if (rec_rewards) rec_rewards[static_cast<size_t>(i) * rec_stride + s] = rec.steps[s].rewards[0];
+      }
+    }
+    if (final_len) final_len[i] = cur->get_state_length();
+  }
+  return 0;
+}
+
+// One CrossingState<int>::execute on arbitrary states/actions (ego index, other bit-cast value).
+int ref_crossing_execute(const mamcts_crossing_params* cp, uint32_t n, const int32_t* x,
+                         const int32_t* last, const int32_t* action, int32_t* next_x,
+                         int32_t* next_last, uint8_t* next_flags, double* ego_reward,
+                         double* cost0) {
+  CrossingWorld world(*cp);
+  const uint32_t A = cp->num_other_agents + 1;
+  for (uint32_t i = 0; i < n; ++i) {
+    std::vector<int32_t> xi(A), li(A);
+    for (uint32_t a = 0; a < A; ++a) { xi[a] = x[a * n + i]; li[a] = last ? last[a * n + i] : 2; }
+    auto st = world.make(xi.data(), li.data(), false);
+    JointAction ja(A);
+    ja[0] = static_cast<ActionIdx>(action[0 * n + i]);
+    for (uint32_t a = 1; a < A; ++a) ja[a] = aconv<int>(action[a * n + i]);
+    std::vector<Reward> r; EgoCosts c;
+    auto nx = st->execute(ja, r, c);
+    orc_state fs;
+    pack_state(*nx, &fs);
+    for (uint32_t a = 0; a < A; ++a) { next_x[a * n + i] = fs.x[a]; next_last[a * n + i] = fs.last[a]; }
+    next_flags[i] = (fs.terminal ? 1 : 0) | (fs.goal ? 2 : 0) | (fs.collided ? 4 : 0);
+    ego_reward[i] = r[0];
+    cost0[i] = c[0];
+  }
+  return 0;
+}
+
+// Mcts<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic>::search (mcts/mcts.h:133-141).
+// Root statistics per agent position: value/latest/visits [A], q/n [A*max_actions] (n = -1: unexpanded).
+int ref_search_crossing(const mamcts_params* mp, const mamcts_crossing_params* cp,
+                        const int32_t* root_x, const int32_t* root_last, uint32_t max_actions,
+                        double* root_value, double* root_latest, uint32_t* root_visits,
+                        double* root_q, int64_t* root_n, uint32_t* counters, double* tree_records,
+                        uint32_t tree_capacity, uint32_t* tree_count) {
+  const MctsParameters rp = to_ref_params(*mp);
+  CrossingWorld world(*cp);
+  auto state = world.make(root_x, root_last, false);
+  run_search_and_dump<CrossingState<int>, RandomHeuristic>(
+      *state, rp, cp->num_other_agents + 1, max_actions, root_value, root_latest, root_visits,
+      root_q, root_n, counters, tree_records, tree_capacity, tree_count);
+  return 0;
+}
+
+int ref_search_simple(const mamcts_params* mp, int32_t state_length, uint32_t max_actions,
+                      double* root_value, double* root_latest, uint32_t* root_visits,
+                      double* root_q, int64_t* root_n, uint32_t* counters, double* tree_records,
+                      uint32_t tree_capacity, uint32_t* tree_count) {
+  const MctsParameters rp = to_ref_params(*mp);
+  SimpleState state(state_length);
+  run_search_and_dump<SimpleState, RandomHeuristic>(state, rp, 2, max_actions, root_value,
+                                                    root_latest, root_visits, root_q, root_n,
+                                                    counters, tree_records, tree_capacity,
+                                                    tree_count);
+  return 0;
+}
+
+// Stochastic twin: the reference's own tree code with the Philox heuristic.
+// env: MAMCTS_ENV_*; tree_id = Philox stream_hi; K rollouts per leaf.
+int ref_search_philox(int32_t env, const mamcts_params* mp, const mamcts_crossing_params* cp,
+                      const mamcts_simple_params* sp, const int32_t* root_x,
+                      const int32_t* root_last, uint64_t seed, uint32_t tree_id, uint32_t K,
+                      uint32_t max_actions, double* root_value, double* root_latest,
+                      uint32_t* root_visits, double* root_q, int64_t* root_n, uint32_t* counters,
+                      uint64_t* rollout_steps, double* tree_records, uint32_t tree_capacity,
+                      uint32_t* tree_count) {
+  MctsParameters rp = to_ref_params(*mp);
+  rp.NUM_PARALLEL_MCTS = 1;
+  PhiloxCtx& c = g_philox;
+  c.mp = *mp;
+  c.seed = seed;
+  c.tree_id = tree_id;
+  c.K = K;
+  c.rollout_steps = 0;
+  if (env == MAMCTS_ENV_CROSSING_I32) {
+    orc_env_crossing(&c.env, cp);
+    CrossingWorld world(*cp);
+    auto state = world.make(root_x, root_last, false);
+    run_search_and_dump<CrossingState<int>, PhiloxHeuristic>(
+        *state, rp, cp->num_other_agents + 1, max_actions, root_value, root_latest, root_visits,
+        root_q, root_n, counters, tree_records, tree_capacity, tree_count);
+  } else {
+    orc_env_simple(&c.env, sp);
+    SimpleState state(root_x[0]);
+    run_search_and_dump<SimpleState, PhiloxHeuristic>(state, rp, 2, max_actions, root_value,
+                                                      root_latest, root_visits, root_q, root_n,
+                                                      counters, tree_records, tree_capacity,
+                                                      tree_count);
+  }
+  if (rollout_steps) *rollout_steps = c.rollout_steps;
+  return 0;
+}
+
+// UctStatistic::merge_node_statistics (uct_statistic.h:165-184) on `n` ego root statistics given as
+// arrays (q/cnt [n*max_actions], cnt = -1: action absent; visits[n]).
+int ref_merge_uct(const mamcts_params* mp, uint32_t n, uint32_t num_actions, uint32_t max_actions,
+                  const double* q, const int64_t* cnt, const uint32_t* visits, double* merged_q,
+                  int64_t* merged_n, uint32_t* merged_visits, double* merged_value,
+                  uint32_t* best_action) {
+  const MctsParameters rp = to_ref_params(*mp);
+  std::vector<UctStatistic> stats;
+  for (uint32_t t = 0; t < n; ++t) {
+    UctStatistic s(num_actions, 0, rp);
+    UctStatistic::UcbStatistics ucb;
+    for (uint32_t a = 0; a < num_actions; ++a) {
+      if (cnt[t * max_actions + a] >= 0)
+        ucb[a] = UctStatistic::UcbPair(static_cast<unsigned>(cnt[t * max_actions + a]),
+                                       q[t * max_actions + a], 0.0);
+    }
+    s.SetUcbStatistics(ucb);
+    UctTest::force_visits(s, visits[t]);
+    stats.push_back(s);
+  }
+  UctStatistic merged(num_actions, 0, rp);
+  merged.merge_node_statistics(stats);
+  double latest;
+  UctTest::read_stat(merged, merged_value, &latest, merged_visits, merged_q, merged_n, max_actions);
+  *best_action = static_cast<uint32_t>(merged.get_best_action());
+  return 0;
+}
+
+// ---- timing of the reference's own CPU path (bench.py --impl reference / cpu_baseline) ---------
+
+// `threads` independent loops of RandomHeuristic::rollout from the default start state for about
+// `seconds` s; returns env-steps/s (execute() calls / wall time) and rollouts/s.
+int ref_time_rollouts(const mamcts_params* mp, const mamcts_crossing_params* cp, uint32_t threads,
+                      double seconds, double* env_steps_per_s, double* rollouts_per_s) {
+  const MctsParameters rp = to_ref_params(*mp);
+  std::vector<uint64_t> steps(threads, 0), rollouts(threads, 0);
+  const auto t0 = std::chrono::steady_clock::now();
+  auto body = [&](uint32_t tid) {
+    CrossingWorld world(*cp);
+    const uint32_t A = cp->num_other_agents + 1;
+    std::vector<int32_t> x(A, 5), last(A, 2);
+    auto start = world.make(x.data(), last.data(), false);
+    for (;;) {
+      for (int rep = 0; rep < 64; ++rep) {
+        auto r = RandomHeuristic::rollout<CrossingState<int>, UctStatistic, UctStatistic,
+                                          RandomHeuristic>(start, rp, 0);
+        steps[tid] += static_cast<uint64_t>(std::get<3>(r));
+        rollouts[tid] += 1;
+      }
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (el >= seconds) break;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (uint32_t t = 0; t < threads; ++t) pool.emplace_back(body, t);
+  for (auto& th : pool) th.join();
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  uint64_t s = 0, r = 0;
+  for (uint32_t t = 0; t < threads; ++t) { s += steps[t]; r += rollouts[t]; }
+  *env_steps_per_s = s / el;
+  *rollouts_per_s = r / el;
+  return 0;
+}
+
+// `threads` independent Mcts::search calls (single_search, mcts/mcts.h:166-186), `repeats` each;
+// returns iterations/s and the env-steps/s of the rollouts inside them (execute() calls counted
+// with the recording wrapper would perturb timing, so steps are derived from one untimed recorded
+// search and scaled).
+int ref_time_search(const mamcts_params* mp, const mamcts_crossing_params* cp, uint32_t threads,
+                    uint32_t repeats, double* iterations_per_s, double* seconds_out) {
+  const MctsParameters rp = to_ref_params(*mp);
+  std::vector<uint64_t> iters(threads, 0);
+  const auto t0 = std::chrono::steady_clock::now();
+  auto body = [&](uint32_t tid) {
+    CrossingWorld world(*cp);
+    const uint32_t A = cp->num_other_agents + 1;
+    std::vector<int32_t> x(A, 5), last(A, 2);
+    auto start = world.make(x.data(), last.data(), false);
+    for (uint32_t r = 0; r < repeats; ++r) {
+      Mcts<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic> mcts(rp);
+      mcts.search(*start);
+      iters[tid] += mcts.numIterations();
+    }
+  };
+  std::vector<std::thread> pool;
+  for (uint32_t t = 0; t < threads; ++t) pool.emplace_back(body, t);
+  for (auto& th : pool) th.join();
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  uint64_t it = 0;
+  for (uint32_t t = 0; t < threads; ++t) it += iters[t];
+  *iterations_per_s = it / el;
+  *seconds_out = el;
+  return 0;
+}
+
+// The reference's own root-parallel path: Mcts::parallel_search with USE_MULTI_THREADING
+// (mcts/mcts.h:188-221) - the runnable stand-in for test/parallel_mcts (needs OR-tools).
+int ref_time_parallel_search(const mamcts_params* mp, const mamcts_crossing_params* cp,
+                             uint32_t num_parallel, double* iterations_per_s, double* seconds_out,
+                             double* root_q, int64_t* root_n, uint32_t max_actions) {
+  MctsParameters rp = to_ref_params(*mp);
+  rp.NUM_PARALLEL_MCTS = num_parallel;
+  rp.USE_MULTI_THREADING = true;
+  CrossingWorld world(*cp);
+  const uint32_t A = cp->num_other_agents + 1;
+  std::vector<int32_t> x(A, 5), last(A, 2);
+  auto start = world.make(x.data(), last.data(), false);
+  const auto t0 = std::chrono::steady_clock::now();
+  Mcts<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic> mcts(rp);
+  mcts.search(*start);
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  *iterations_per_s = static_cast<double>(num_parallel) * rp.MAX_NUMBER_OF_ITERATIONS / el;
+  *seconds_out = el;
+  if (root_q && root_n) {
+    double v, l; uint32_t nv;
+    UctTest::read_stat(mcts.get_root().get_ego_int_node(), &v, &l, &nv, root_q, root_n, max_actions);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,496 @@
+"""ctypes access to the CPU checker (oracle/) for tests, smoke() and bench.py's CPU legs.
+
+  Oracle   : oracle/_build/libmamcts_oracle.so - the plain-C restatement (always available;
+             built on demand with gcc).
+  Reference: oracle/_ref/libmamcts_ref.so      - the UNMODIFIED reference compiled from
+             /root/reference (built where the reference checkout exists; the prebuilt .so
+             travels to the GPU box). `reference_available()` says whether it can be used.
+
+TEST INFRASTRUCTURE ONLY: nothing under mamcts_b200/ imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mamcts_b200._abi import (MAX_ACTIONS, MAX_AGENTS, SRC_PHILOX, SRC_REFERENCE_CONST,
+                              SRC_REPLAY, ENV_CROSSING_I32, ENV_SIMPLE, CrossingParams, Params,
+                              SimpleParams)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libmamcts_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libmamcts_ref.so")
+REFERENCE_SRC = os.environ.get("MAMCTS_REFERENCE", "/root/reference")
+
+
+def _ptr(a, ty=None):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OrcState(C.Structure):
+    _fields_ = [("x", C.c_int32 * MAX_AGENTS), ("last", C.c_int32 * MAX_AGENTS),
+                ("terminal", C.c_uint8), ("goal", C.c_uint8), ("collided", C.c_uint8),
+                ("pad", C.c_uint8)]
+
+
+class OrcEnv(C.Structure):
+    _fields_ = [("env", C.c_int32), ("num_agents", C.c_uint32),
+                ("num_actions", C.c_uint32 * MAX_AGENTS), ("crossing", CrossingParams),
+                ("simple", SimpleParams)]
+
+
+class OrcRolloutResult(C.Structure):
+    _fields_ = [("ego_return", C.c_double), ("other_return", C.c_double * MAX_AGENTS),
+                ("cost0", C.c_double), ("step_length", C.c_double), ("steps", C.c_uint32),
+                ("final_state", OrcState)]
+
+
+class OrcStat(C.Structure):
+    _fields_ = [("value", C.c_double), ("latest_return", C.c_double),
+                ("total_visits", C.c_uint32), ("num_actions", C.c_uint32),
+                ("num_expanded", C.c_uint32), ("expanded", C.c_uint8 * MAX_ACTIONS),
+                ("n", C.c_uint32 * MAX_ACTIONS), ("q", C.c_double * MAX_ACTIONS),
+                ("collected_action", C.c_uint32), ("collected_reward", C.c_double)]
+
+
+class OrcSearchConfig(C.Structure):
+    _fields_ = [("env", OrcEnv), ("mcts", Params), ("action_source", C.c_int32),
+                ("rollouts_per_leaf", C.c_uint32), ("philox_seed", C.c_uint64),
+                ("tree_id", C.c_uint32),
+                ("expand_order", (C.c_uint32 * MAX_ACTIONS) * MAX_AGENTS)]
+
+
+def build_oracle(force: bool = False) -> str:
+    src = os.path.join(ORACLE_DIR, "mamcts_oracle.c")
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(ORACLE_DIR, "mamcts_oracle.h"))):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+    return ORACLE_SO
+
+
+def build_reference(force: bool = False) -> str | None:
+    """(Re)builds oracle/_ref when the reference checkout is present; otherwise uses a prebuilt one."""
+    if os.path.isdir(os.path.join(REFERENCE_SRC, "mcts")):
+        srcs = [os.path.join(ORACLE_DIR, f) for f in ("ref_driver.cc", "mamcts_oracle.c",
+                                                       "mamcts_oracle.h")]
+        if force or not os.path.exists(REF_SO) or os.path.getmtime(REF_SO) < max(
+                os.path.getmtime(s) for s in srcs):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref", f"REF={REFERENCE_SRC}"])
+    return REF_SO if os.path.exists(REF_SO) else None
+
+
+def reference_available() -> bool:
+    return build_reference() is not None
+
+
+_oracle = None
+_ref = None
+
+
+def oracle() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(build_oracle())
+        lib.orc_philox_draw.restype = C.c_uint32
+        lib.orc_philox_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        lib.orc_reduce_mean.restype = C.c_double
+        lib.orc_reduce_mean.argtypes = [C.c_void_p, C.c_uint32]
+        lib.orc_tree_create.restype = C.c_void_p
+        lib.orc_tree_create.argtypes = [C.POINTER(OrcSearchConfig), C.POINTER(OrcState)]
+        lib.orc_tree_destroy.argtypes = [C.c_void_p]
+        lib.orc_tree_run.argtypes = [C.c_void_p, C.c_uint32]
+        lib.orc_tree_num_nodes.restype = C.c_uint32
+        lib.orc_tree_num_nodes.argtypes = [C.c_void_p]
+        lib.orc_tree_rollout_steps.restype = C.c_uint64
+        lib.orc_tree_rollout_steps.argtypes = [C.c_void_p]
+        lib.orc_tree_root_stat.restype = C.POINTER(OrcStat)
+        lib.orc_tree_root_stat.argtypes = [C.c_void_p, C.c_uint32]
+        lib.orc_tree_dump.restype = C.c_uint32
+        lib.orc_tree_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.orc_stat_choose_next_action.restype = C.c_uint32
+        lib.orc_stat_best_action.restype = C.c_uint32
+        _oracle = lib
+    return _oracle
+
+
+def reference() -> C.CDLL:
+    global _ref
+    if _ref is None:
+        path = build_reference()
+        if path is None:
+            raise RuntimeError("oracle/_ref/libmamcts_ref.so not built and no reference checkout")
+        _ref = C.CDLL(path)
+    return _ref
+
+
+# ------------------------------------------------------------------------------------------------
+# environments
+# ------------------------------------------------------------------------------------------------
+
+def make_env(cp: CrossingParams | None = None, sp: SimpleParams | None = None) -> OrcEnv:
+    env = OrcEnv()
+    if cp is not None:
+        oracle().orc_env_crossing(C.byref(env), C.byref(cp))
+    else:
+        oracle().orc_env_simple(C.byref(env), C.byref(sp))
+    return env
+
+
+def make_state(x, last=None, terminal=False) -> OrcState:
+    s = OrcState()
+    for i, v in enumerate(x):
+        s.x[i] = int(v)
+        s.last[i] = int(last[i]) if last is not None else 2
+    s.terminal = 1 if terminal else 0
+    return s
+
+
+def philox4x32_10(ctr, key):
+    out = (C.c_uint32 * 4)()
+    oracle().orc_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+    return list(out)
+
+
+def philox_draw(seed, hi, lo, pos, n) -> int:
+    return int(oracle().orc_philox_draw(seed, hi, lo, pos, n))
+
+
+def reduce_mean(vals) -> float:
+    v = np.ascontiguousarray(vals, dtype=np.float64)
+    return float(oracle().orc_reduce_mean(_ptr(v), len(v)))
+
+
+def crossing_execute(cp: CrossingParams, x, last, action):
+    """Oracle CrossingState<int>::execute on one state. action[0]: ego index; [1:]: other values."""
+    s = make_state(x, last)
+    nxt = OrcState()
+    r = C.c_double()
+    c0 = C.c_double()
+    act = (C.c_int32 * MAX_AGENTS)(*[int(a) for a in action])
+    oracle().orc_crossing_execute(C.byref(cp), C.byref(s), act, C.byref(nxt), C.byref(r),
+                                  C.byref(c0))
+    A = cp.num_other_agents + 1
+    flags = (1 if nxt.terminal else 0) | (2 if nxt.goal else 0) | (4 if nxt.collided else 0)
+    return list(nxt.x[:A]), list(nxt.last[:A]), flags, r.value, c0.value
+
+
+def rollout(env: OrcEnv, mp: Params, x, last=None, terminal=False, depth=0, kind=SRC_PHILOX,
+            replay=None, const_actions=None, seed=0, stream_hi=0, stream_lo=0, trace_cap=0):
+    """One oracle rollout; returns a dict."""
+    st = make_state(x, last, terminal)
+    res = OrcRolloutResult()
+    rp = None
+    nrep = 0
+    if replay is not None:
+        rep = np.ascontiguousarray(replay, dtype=np.int8)
+        nrep = rep.shape[0]
+        rp = _ptr(rep)
+    ca = (C.c_uint32 * MAX_AGENTS)(*(const_actions or []))
+    trace = np.zeros(max(trace_cap, 1), dtype=np.float64)
+    oracle().orc_rollout(C.byref(env), C.byref(mp), C.byref(st), C.c_uint32(depth),
+                         C.c_int32(kind), rp, C.c_uint32(nrep), ca, C.c_uint64(seed),
+                         C.c_uint32(stream_hi), C.c_uint32(stream_lo), C.byref(res),
+                         _ptr(trace) if trace_cap else None, C.c_uint32(trace_cap))
+    A = env.num_agents
+    fs = res.final_state
+    return dict(ego_return=res.ego_return, other_return=list(res.other_return[:A - 1]),
+                cost0=res.cost0, step_length=res.step_length, steps=res.steps,
+                final_x=list(fs.x[:A]), final_last=list(fs.last[:A]),
+                final_flags=(1 if fs.terminal else 0) | (2 if fs.goal else 0) |
+                (4 if fs.collided else 0),
+                reward_trace=trace[:min(trace_cap, res.steps)].copy())
+
+
+def rollout_batch(env: OrcEnv, mp: Params, x, last=None, flags=None, depth=None, K=1,
+                  kind=SRC_PHILOX, replay=None, replay_steps=None, const_actions=None, seed=0,
+                  stream_hi=None, stream_hi_base=0, stream_lo_base=0, trace_stride=0):
+    """Oracle counterpart of mamcts_rollout_* over n leaves x K rollouts (same output layout)."""
+    x = np.asarray(x, dtype=np.int32)
+    A = env.num_agents
+    n = x.shape[1]
+    out = dict(ego_return=np.zeros(n), other_return=np.zeros((max(A - 1, 0), n)),
+               ego_cost=np.zeros(n), step_length=np.zeros(n), total_steps=0,
+               steps=np.zeros(n * K, dtype=np.uint32), final_x=np.zeros((A, n * K), dtype=np.int32),
+               final_last_action=np.zeros((A, n * K), dtype=np.int32),
+               final_flags=np.zeros(n * K, dtype=np.uint8),
+               rollout_ego_return=np.zeros(n * K),
+               reward_trace=np.zeros((n * K, max(trace_stride, 1))))
+    for i in range(n):
+        ego, cost, sl = np.zeros(K), np.zeros(K), np.zeros(K)
+        oth = np.zeros((max(A - 1, 1), K))
+        for k in range(K):
+            hi = int(stream_hi[i]) if stream_hi is not None else stream_hi_base
+            lo = (stream_lo_base + i * K + k) & 0xFFFFFFFF
+            rep = None
+            if kind == SRC_REPLAY:
+                rep = np.asarray(replay[i][:int(replay_steps[i])], dtype=np.int8).reshape(-1, A)
+            r = rollout(env, mp, x[:, i], None if last is None else np.asarray(last)[:, i],
+                        bool(flags[i] & 1) if flags is not None else False,
+                        int(depth[i]) if depth is not None else 0, kind, rep, const_actions, seed,
+                        hi, lo, trace_stride)
+            idx = i * K + k
+            ego[k], cost[k], sl[k] = r["ego_return"], r["cost0"], r["step_length"]
+            for j in range(A - 1):
+                oth[j, k] = r["other_return"][j]
+            out["steps"][idx] = r["steps"]
+            out["final_x"][:, idx] = r["final_x"]
+            out["final_last_action"][:, idx] = r["final_last"]
+            out["final_flags"][idx] = r["final_flags"]
+            out["rollout_ego_return"][idx] = r["ego_return"]
+            out["total_steps"] += r["steps"]
+            if trace_stride:
+                out["reward_trace"][idx, :len(r["reward_trace"])] = r["reward_trace"]
+        out["ego_return"][i] = reduce_mean(ego)
+        out["ego_cost"][i] = reduce_mean(cost)
+        out["step_length"][i] = reduce_mean(sl)
+        for j in range(A - 1):
+            out["other_return"][j, i] = reduce_mean(oth[j])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# search (oracle restatement)
+# ------------------------------------------------------------------------------------------------
+
+def expand_order_libstdcxx(seed: int, n: int):
+    """The widening order the product computes on the host (same libstdc++ algorithm); used by the
+    oracle so that it does not depend on the product: asks the reference when available, else the
+    golden table in tests/golden/expand_order.json."""
+    if reference_available():
+        from mamcts_b200.params import default_params
+        mp = default_params(random_seed=seed)
+        order = (C.c_uint32 * n)()
+        reference().ref_uct_expand_order(C.byref(mp), C.c_uint32(n), order)
+        return list(order)
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "expand_order.json")) as f:
+        table = json.load(f)
+    return table[str(seed)][str(n)]
+
+
+class OracleTree:
+    def __init__(self, env: OrcEnv, mp: Params, root_x, root_last=None, action_source=SRC_PHILOX,
+                 K=1, seed=0, tree_id=0, expand_orders=None):
+        cfg = OrcSearchConfig()
+        cfg.env = env
+        cfg.mcts = mp
+        cfg.action_source = action_source
+        cfg.rollouts_per_leaf = K
+        cfg.philox_seed = seed
+        cfg.tree_id = tree_id
+        self.env = env
+        for a in range(env.num_agents):
+            nA = env.num_actions[a]
+            order = (expand_orders[a] if expand_orders is not None
+                     else expand_order_libstdcxx(mp.random_seed, nA))
+            for k in range(nA):
+                cfg.expand_order[a][k] = order[k]
+        st = make_state(root_x, root_last)
+        self.cfg = cfg
+        self.h = oracle().orc_tree_create(C.byref(cfg), C.byref(st))
+
+    def run(self, iterations: int):
+        oracle().orc_tree_run(self.h, iterations)
+
+    @property
+    def num_nodes(self) -> int:
+        return int(oracle().orc_tree_num_nodes(self.h))
+
+    @property
+    def rollout_steps(self) -> int:
+        return int(oracle().orc_tree_rollout_steps(self.h))
+
+    def root_stat(self, agent: int):
+        s = oracle().orc_tree_root_stat(self.h, agent).contents
+        nA = s.num_actions
+        return dict(value=s.value, latest=s.latest_return, visits=s.total_visits,
+                    n=[int(s.n[a]) if s.expanded[a] else -1 for a in range(nA)],
+                    q=[s.q[a] if s.expanded[a] else 0.0 for a in range(nA)])
+
+    def dump(self, max_actions: int, capacity: int | None = None):
+        cap = capacity or self.num_nodes
+        stride = 4 + self.env.num_agents * (3 + 2 * max_actions)
+        rec = np.zeros((cap, stride))
+        cnt = oracle().orc_tree_dump(self.h, _ptr(rec), cap, max_actions)
+        return rec[:min(cnt, cap)]
+
+    def close(self):
+        if self.h:
+            oracle().orc_tree_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# the compiled reference
+# ------------------------------------------------------------------------------------------------
+
+def ref_expand_order(mp: Params, n: int):
+    order = (C.c_uint32 * n)()
+    reference().ref_uct_expand_order(C.byref(mp), C.c_uint32(n), order)
+    return list(order)
+
+
+def ref_rollout_crossing(mp: Params, cp: CrossingParams, x, last=None, flags=None, depth=None,
+                         rec_stride=64):
+    x = np.ascontiguousarray(x, dtype=np.int32)
+    A, n = x.shape
+    last_a = None if last is None else np.ascontiguousarray(last, dtype=np.int32)
+    flags_a = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+    depth_a = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+    out = dict(ego_return=np.zeros(n), other_return=np.zeros((A - 1, n)), ego_cost=np.zeros(n),
+               step_length=np.zeros(n), steps=np.zeros(n, dtype=np.uint32),
+               final_x=np.zeros((A, n), dtype=np.int32),
+               final_last_action=np.zeros((A, n), dtype=np.int32),
+               final_flags=np.zeros(n, dtype=np.uint8),
+               rec_actions=np.zeros((n, rec_stride, A), dtype=np.int8),
+               rec_rewards=np.zeros((n, rec_stride)))
+    reference().ref_rollout_crossing(
+        C.byref(mp), C.byref(cp), C.c_uint32(n), _ptr(x), _ptr(last_a), _ptr(flags_a),
+        _ptr(depth_a), _ptr(out["ego_return"]), _ptr(out["other_return"]), _ptr(out["ego_cost"]),
+        _ptr(out["step_length"]), _ptr(out["steps"]), _ptr(out["final_x"]),
+        _ptr(out["final_last_action"]), _ptr(out["final_flags"]), _ptr(out["rec_actions"]),
+        _ptr(out["rec_rewards"]), C.c_uint32(rec_stride))
+    return out
+
+
+def ref_rollout_simple(mp: Params, length, depth=None, rec_stride=64):
+    length = np.ascontiguousarray(length, dtype=np.int32)
+    n = length.shape[0]
+    depth_a = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+    out = dict(ego_return=np.zeros(n), other_return=np.zeros((1, n)), step_length=np.zeros(n),
+               steps=np.zeros(n, dtype=np.uint32), final_len=np.zeros(n, dtype=np.int32),
+               rec_actions=np.zeros((n, rec_stride, 2), dtype=np.int8),
+               rec_rewards=np.zeros((n, rec_stride)))
+    reference().ref_rollout_simple(
+        C.byref(mp), C.c_uint32(n), _ptr(length), _ptr(depth_a), _ptr(out["ego_return"]),
+        _ptr(out["other_return"]), _ptr(out["step_length"]), _ptr(out["steps"]),
+        _ptr(out["final_len"]), _ptr(out["rec_actions"]), _ptr(out["rec_rewards"]),
+        C.c_uint32(rec_stride))
+    return out
+
+
+def ref_crossing_execute(cp: CrossingParams, x, last, action):
+    x = np.ascontiguousarray(x, dtype=np.int32)
+    A, n = x.shape
+    last = np.ascontiguousarray(last, dtype=np.int32)
+    action = np.ascontiguousarray(action, dtype=np.int32)
+    nx = np.zeros((A, n), dtype=np.int32)
+    nl = np.zeros((A, n), dtype=np.int32)
+    fl = np.zeros(n, dtype=np.uint8)
+    r = np.zeros(n)
+    c0 = np.zeros(n)
+    reference().ref_crossing_execute(C.byref(cp), C.c_uint32(n), _ptr(x), _ptr(last), _ptr(action),
+                                     _ptr(nx), _ptr(nl), _ptr(fl), _ptr(r), _ptr(c0))
+    return nx, nl, fl, r, c0
+
+
+def _search_outputs(A, max_actions, tree_capacity):
+    return dict(value=np.zeros(A), latest=np.zeros(A), visits=np.zeros(A, dtype=np.uint32),
+                q=np.zeros((A, max_actions)), n=np.zeros((A, max_actions), dtype=np.int64),
+                counters=np.zeros(3, dtype=np.uint32),
+                tree=np.zeros((max(tree_capacity, 1), 4 + A * (3 + 2 * max_actions))),
+                tree_count=C.c_uint32(0))
+
+
+def _finish_search(o, tree_capacity):
+    cnt = o.pop("tree_count").value
+    o["tree"] = o["tree"][:min(cnt, tree_capacity)]
+    o["tree_count"] = cnt
+    o["num_nodes"], o["num_iterations"], o["best_action"] = (int(v) for v in o.pop("counters"))
+    return o
+
+
+def ref_search_crossing(mp: Params, cp: CrossingParams, root_x=None, root_last=None,
+                        max_actions=7, tree_capacity=0):
+    A = cp.num_other_agents + 1
+    rx = np.ascontiguousarray(root_x if root_x is not None else [5] * A, dtype=np.int32)
+    rl = np.ascontiguousarray(root_last if root_last is not None else [2] * A, dtype=np.int32)
+    o = _search_outputs(A, max_actions, tree_capacity)
+    reference().ref_search_crossing(
+        C.byref(mp), C.byref(cp), _ptr(rx), _ptr(rl), C.c_uint32(max_actions), _ptr(o["value"]),
+        _ptr(o["latest"]), _ptr(o["visits"]), _ptr(o["q"]), _ptr(o["n"]), _ptr(o["counters"]),
+        _ptr(o["tree"]) if tree_capacity else None, C.c_uint32(tree_capacity),
+        C.byref(o["tree_count"]))
+    return _finish_search(o, tree_capacity)
+
+
+def ref_search_simple(mp: Params, state_length=4, max_actions=2, tree_capacity=0):
+    o = _search_outputs(2, max_actions, tree_capacity)
+    reference().ref_search_simple(
+        C.byref(mp), C.c_int32(state_length), C.c_uint32(max_actions), _ptr(o["value"]),
+        _ptr(o["latest"]), _ptr(o["visits"]), _ptr(o["q"]), _ptr(o["n"]), _ptr(o["counters"]),
+        _ptr(o["tree"]) if tree_capacity else None, C.c_uint32(tree_capacity),
+        C.byref(o["tree_count"]))
+    return _finish_search(o, tree_capacity)
+
+
+def ref_search_philox(env_kind, mp: Params, cp=None, sp=None, root_x=None, root_last=None, seed=0,
+                      tree_id=0, K=1, max_actions=7, tree_capacity=0):
+    A = (cp.num_other_agents + 1) if env_kind == ENV_CROSSING_I32 else 2
+    rx = np.ascontiguousarray(root_x if root_x is not None else [5] * A, dtype=np.int32)
+    rl = np.ascontiguousarray(root_last if root_last is not None else [2] * A, dtype=np.int32)
+    o = _search_outputs(A, max_actions, tree_capacity)
+    steps = C.c_uint64(0)
+    reference().ref_search_philox(
+        C.c_int32(env_kind), C.byref(mp), C.byref(cp) if cp is not None else None,
+        C.byref(sp) if sp is not None else None, _ptr(rx), _ptr(rl), C.c_uint64(seed),
+        C.c_uint32(tree_id), C.c_uint32(K), C.c_uint32(max_actions), _ptr(o["value"]),
+        _ptr(o["latest"]), _ptr(o["visits"]), _ptr(o["q"]), _ptr(o["n"]), _ptr(o["counters"]),
+        C.byref(steps), _ptr(o["tree"]) if tree_capacity else None, C.c_uint32(tree_capacity),
+        C.byref(o["tree_count"]))
+    o = _finish_search(o, tree_capacity)
+    o["rollout_steps"] = steps.value
+    return o
+
+
+def ref_merge_uct(mp: Params, q, cnt, visits, num_actions):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    cnt = np.ascontiguousarray(cnt, dtype=np.int64)
+    visits = np.ascontiguousarray(visits, dtype=np.uint32)
+    n, max_actions = q.shape
+    mq = np.zeros(max_actions)
+    mn = np.zeros(max_actions, dtype=np.int64)
+    mv = C.c_uint32(0)
+    val = C.c_double(0)
+    best = C.c_uint32(0)
+    reference().ref_merge_uct(C.byref(mp), C.c_uint32(n), C.c_uint32(num_actions),
+                              C.c_uint32(max_actions), _ptr(q), _ptr(cnt), _ptr(visits), _ptr(mq),
+                              _ptr(mn), C.byref(mv), C.byref(val), C.byref(best))
+    return dict(q=mq, n=mn, visits=mv.value, value=val.value, best=best.value)
+
+
+def ref_time_rollouts(mp: Params, cp: CrossingParams, threads: int, seconds: float):
+    s, r = C.c_double(0), C.c_double(0)
+    reference().ref_time_rollouts(C.byref(mp), C.byref(cp), C.c_uint32(threads),
+                                  C.c_double(seconds), C.byref(s), C.byref(r))
+    return s.value, r.value
+
+
+def ref_time_search(mp: Params, cp: CrossingParams, threads: int, repeats: int):
+    it, sec = C.c_double(0), C.c_double(0)
+    reference().ref_time_search(C.byref(mp), C.byref(cp), C.c_uint32(threads), C.c_uint32(repeats),
+                                C.byref(it), C.byref(sec))
+    return it.value, sec.value
+
+
+def ref_time_parallel_search(mp: Params, cp: CrossingParams, num_parallel: int, max_actions=7):
+    it, sec = C.c_double(0), C.c_double(0)
+    q = np.zeros(max_actions)
+    n = np.zeros(max_actions, dtype=np.int64)
+    reference().ref_time_parallel_search(C.byref(mp), C.byref(cp), C.c_uint32(num_parallel),
+                                         C.byref(it), C.byref(sec), _ptr(q), _ptr(n),
+                                         C.c_uint32(max_actions))
+    return it.value, sec.value, q, n
