@@ -1,0 +1,300 @@
+// backup.cu - batched UctStatistic back-propagation and the root-parallel merge.
+//
+// backup_uct_kernel : one lane per (path, agent); every agent's statistic is an independent
+//   sequential recurrence along the path (reference mcts/mcts.h:309-329,
+//   mcts/statistics/uct_statistic.h:100-110,134-144), so A adjacent lanes walk one path together
+//   and read the edge records coalesced.
+// root_merge_kernel : fixed-order block reduction of the local trees' ego root statistics into
+//   {sum_q[a], sum_n[a], occ[a], sum_visits} (reference uct_statistic.h:165-184); one
+//   ncclAllReduce of those 3*nA+1 doubles when a communicator is attached; root_finish_kernel
+//   divides and picks the best action (uct_statistic.h:78-89).
+#include <algorithm>
+#include <cstring>
+
+#include "engine.h"
+#include "staging.h"
+#include "root_merge.h"
+
+namespace mamcts {
+
+struct BackupParams {
+  uint32_t n_paths, A, max_actions;
+  double gamma;
+  const uint32_t* leaf_node;
+  const uint8_t* leaf_has_heuristic;
+  const double* ego_return;
+  const double* other_return;  // [(A-1)*n_paths]
+  const uint32_t* path_offset;
+  const uint32_t* path_len;
+  const uint32_t* edge_node;
+  const uint8_t* edge_action;
+  const double* edge_reward;
+  double* value;
+  double* latest;
+  uint32_t* visits;
+  double* q;
+  uint32_t* n;
+};
+
+__global__ void __launch_bounds__(256) backup_uct_kernel(const __grid_constant__ BackupParams p) {
+  const uint64_t total = (uint64_t)p.n_paths * p.A;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t path = (uint32_t)(t / p.A);
+    const uint32_t a = (uint32_t)(t % p.A);
+    const uint32_t leaf = p.leaf_node[path];
+    const size_t leaf_slot = (size_t)leaf * p.A + a;
+    double G;
+    if (p.leaf_has_heuristic[path]) {
+      // UctStatistic::update_from_heuristic, uct_statistic.h:100-110
+      const double h = (a == 0) ? p.ego_return[path] : p.other_return[(size_t)(a - 1) * p.n_paths + path];
+      p.value[leaf_slot] = h;
+      p.latest[leaf_slot] = h;
+      p.visits[leaf_slot] += 1;
+      G = h;
+    } else {
+      G = p.latest[leaf_slot];  // re-visited terminal node: no update (stage_node.h:183-187)
+    }
+    const uint32_t off = p.path_offset[path];
+    const uint32_t len = p.path_len[path];
+    for (uint32_t e = 0; e < len; ++e) {
+      const size_t idx = (size_t)off + e;
+      const size_t slot = (size_t)p.edge_node[idx] * p.A + a;
+      const uint32_t act = p.edge_action[idx * p.A + a];
+      const double r = p.edge_reward[idx * p.A + a];
+      // UctStatistic::update_statistics_from_backpropagated, uct_statistic.h:134-144
+      G = __dadd_rn(r, __dmul_rn(p.gamma, G));
+      const size_t qa = slot * p.max_actions + act;
+      const uint32_t cnt = p.n[qa] + 1;
+      p.n[qa] = cnt;
+      const double qv = p.q[qa];
+      p.q[qa] = __dadd_rn(qv, __ddiv_rn(__dsub_rn(G, qv), (double)cnt));
+      const uint32_t nv = p.visits[slot] + 1;
+      p.visits[slot] = nv;
+      const double v = p.value[slot];
+      p.value[slot] = __dadd_rn(v, __ddiv_rn(__dsub_rn(G, v), (double)nv));
+      p.latest[slot] = G;
+    }
+  }
+}
+
+// ---- root merge -------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(1024)
+root_merge_kernel(RootGather g, uint32_t n_trees, uint32_t nA, double* __restrict__ acc) {
+  extern __shared__ double sm[];  // [blockDim.x]
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t comp = 0; comp < 3 * nA + 1; ++comp) {
+    double part = 0.0;
+    for (uint32_t t = tid; t < n_trees; t += blockDim.x) {
+      size_t qbase, nbase, vbase;
+      if (g.root_slot) {
+        qbase = nbase = (size_t)g.root_slot[t] * g.max_actions;
+        vbase = g.root_slot[t];
+      } else {
+        qbase = (size_t)t * g.stride_q;
+        nbase = (size_t)t * g.stride_n;
+        vbase = (size_t)t * g.stride_v;
+      }
+      double v;
+      if (comp < nA) {
+        v = g.n[nbase + comp] ? g.q[qbase + comp] : 0.0;
+      } else if (comp < 2 * nA) {
+        v = (double)g.n[nbase + comp - nA];
+      } else if (comp < 3 * nA) {
+        v = g.n[nbase + comp - 2 * nA] ? 1.0 : 0.0;
+      } else {
+        v = (double)g.visits[vbase];
+      }
+      part = __dadd_rn(part, v);
+    }
+    sm[tid] = part;
+    __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+      if (tid < s) sm[tid] = __dadd_rn(sm[tid], sm[tid + s]);
+      __syncthreads();
+    }
+    if (tid == 0) acc[comp] = sm[0];
+    __syncthreads();
+  }
+}
+
+// out (doubles): [0,nA) merged q, [nA,2nA) merged n, [2nA,3nA) occurrences, [3nA] visits,
+// [3nA+1] value, [3nA+2] best action.  Reference uct_statistic.h:173-183 and :78-89.
+__global__ void root_finish_kernel(const double* __restrict__ acc, uint32_t nA, double* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double value = 0.0;
+  uint32_t present = 0;
+  double best_q = 0.0;
+  uint32_t best = 0;
+  bool first = true;
+  for (uint32_t a = 0; a < nA; ++a) {
+    const double occ = acc[2 * nA + a];
+    double q = 0.0;
+    if (occ > 0.0) {
+      q = acc[a] / occ;
+      value = __dadd_rn(value, q);
+      present += 1;
+      if (first) { best_q = q; best = a; first = false; }
+      else if (q > best_q) { best_q = q; best = a; }
+    }
+    out[a] = q;
+    out[nA + a] = acc[nA + a];
+    out[2 * nA + a] = occ;
+  }
+  out[3 * nA] = acc[3 * nA];
+  out[3 * nA + 1] = present ? value / (double)present : 0.0;
+  out[3 * nA + 2] = (double)best;
+}
+
+// Shared by mamcts_root_merge and mamcts_search_merge_roots (search.cu).
+int root_merge_device(mamcts_engine* e, const RootGather& g, uint32_t n_trees, uint32_t nA,
+                      double* merged_q, uint64_t* merged_n, uint32_t* merged_occ,
+                      uint64_t* merged_total_visits, double* merged_value, uint32_t* best_action) {
+  if (nA == 0 || nA > MAMCTS_MAX_ACTIONS) return fail(e, MAMCTS_ERR_INVALID, "root merge: bad num_actions");
+  const size_t nacc = 3 * (size_t)nA + 1, nout = 3 * (size_t)nA + 3;
+  int rc = ensure_scratch(e, sizeof(double) * (nacc + nout));
+  if (rc != MAMCTS_OK) return rc;
+  double* acc = static_cast<double*>(e->scratch);
+  double* out = acc + nacc;
+  const int threads = n_trees >= 1024 ? 1024 : (n_trees > 32 ? 256 : 32);
+  root_merge_kernel<<<1, threads, threads * sizeof(double), e->stream>>>(g, n_trees, nA, acc);
+  e->launches++;
+  MAMCTS_CUDA(e, cudaGetLastError());
+  if (e->nccl_comm) {
+    rc = mamcts_allreduce_f64(e, acc, nacc);  // one all-reduce per decision
+    if (rc != MAMCTS_OK) return rc;
+  }
+  root_finish_kernel<<<1, 32, 0, e->stream>>>(acc, nA, out);
+  e->launches++;
+  MAMCTS_CUDA(e, cudaGetLastError());
+  double host[3 * MAMCTS_MAX_ACTIONS + 3];
+  MAMCTS_CUDA(e, cudaMemcpyAsync(host, out, sizeof(double) * nout, cudaMemcpyDeviceToHost, e->stream));
+  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  for (uint32_t a = 0; a < nA; ++a) {
+    if (merged_q) merged_q[a] = host[a];
+    if (merged_n) merged_n[a] = (uint64_t)host[nA + a];
+    if (merged_occ) merged_occ[a] = (uint32_t)host[2 * nA + a];
+  }
+  if (merged_total_visits) *merged_total_visits = (uint64_t)host[3 * nA];
+  if (merged_value) *merged_value = host[3 * nA + 1];
+  if (best_action) *best_action = (uint32_t)host[3 * nA + 2];
+  return MAMCTS_OK;
+}
+
+}  // namespace mamcts
+
+using namespace mamcts;
+
+extern "C" {
+
+int mamcts_backup_uct(mamcts_engine* e, const mamcts_params* mp, uint32_t num_agents,
+                      uint32_t n_paths, int32_t mem, const uint32_t* leaf_node,
+                      const uint8_t* leaf_has_heuristic, const double* ego_return,
+                      const double* other_return, const uint32_t* path_offset,
+                      const uint32_t* path_len, const uint32_t* edge_node,
+                      const uint8_t* edge_action, const double* edge_reward,
+                      mamcts_uct_stats* stats) {
+  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_backup_uct: null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!mp || !stats || !leaf_node || !leaf_has_heuristic || !ego_return || !path_offset ||
+      !path_len || (num_agents > 1 && !other_return))
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_backup_uct: null argument");
+  if (num_agents == 0 || num_agents > MAMCTS_MAX_AGENTS || stats->max_actions == 0 ||
+      stats->max_actions > MAMCTS_MAX_ACTIONS || stats->num_slots % num_agents != 0)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_backup_uct: bad agent / action / slot counts");
+  if (n_paths == 0) return MAMCTS_OK;
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  // total number of edges: needs the host view of offsets/lengths when they are host arrays;
+  // for device arrays the caller guarantees edge arrays cover max(offset+len).
+  size_t n_edges = 0;
+  if (mem == MAMCTS_MEM_HOST) {
+    for (uint32_t i = 0; i < n_paths; ++i) n_edges = std::max<size_t>(n_edges, (size_t)path_offset[i] + path_len[i]);
+    for (uint32_t i = 0; i < n_paths; ++i)
+      if ((size_t)leaf_node[i] * num_agents >= stats->num_slots)
+        return fail(e, MAMCTS_ERR_INVALID, "mamcts_backup_uct: leaf node out of range");
+  }
+  if (mem == MAMCTS_MEM_HOST && n_edges > 0 && (!edge_node || !edge_action || !edge_reward))
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_backup_uct: null edge arrays");
+  const size_t A = num_agents, S = stats->num_slots, MA = stats->max_actions;
+  ArgStager stg(e);
+  const int t_leaf = stg.plan(leaf_node, sizeof(uint32_t) * n_paths, mem, false);
+  const int t_has = stg.plan(leaf_has_heuristic, n_paths, mem, false);
+  const int t_ego = stg.plan(ego_return, sizeof(double) * n_paths, mem, false);
+  const int t_oth = stg.plan(other_return, sizeof(double) * (A - 1) * n_paths, mem, false);
+  const int t_off = stg.plan(path_offset, sizeof(uint32_t) * n_paths, mem, false);
+  const int t_len = stg.plan(path_len, sizeof(uint32_t) * n_paths, mem, false);
+  const int t_en = stg.plan(n_edges || mem == MAMCTS_MEM_DEVICE ? edge_node : nullptr, sizeof(uint32_t) * n_edges, mem, false);
+  const int t_ea = stg.plan(n_edges || mem == MAMCTS_MEM_DEVICE ? edge_action : nullptr, n_edges * A, mem, false);
+  const int t_er = stg.plan(n_edges || mem == MAMCTS_MEM_DEVICE ? edge_reward : nullptr, sizeof(double) * n_edges * A, mem, false);
+  // statistics are in/out: staged in as inputs, copied back explicitly below
+  const int s_val = stg.plan(stats->value, sizeof(double) * S, stats->mem, false);
+  const int s_lat = stg.plan(stats->latest_return, sizeof(double) * S, stats->mem, false);
+  const int s_vis = stg.plan(stats->total_visits, sizeof(uint32_t) * S, stats->mem, false);
+  const int s_q = stg.plan(stats->q, sizeof(double) * S * MA, stats->mem, false);
+  const int s_n = stg.plan(stats->n, sizeof(uint32_t) * S * MA, stats->mem, false);
+  int rc = stg.commit();
+  if (rc != MAMCTS_OK) return rc;
+
+  BackupParams p;
+  p.n_paths = n_paths; p.A = num_agents; p.max_actions = stats->max_actions;
+  p.gamma = mp->discount_factor;
+  p.leaf_node = stg.dev<const uint32_t>(t_leaf);
+  p.leaf_has_heuristic = stg.dev<const uint8_t>(t_has);
+  p.ego_return = stg.dev<const double>(t_ego);
+  p.other_return = stg.dev<const double>(t_oth);
+  p.path_offset = stg.dev<const uint32_t>(t_off);
+  p.path_len = stg.dev<const uint32_t>(t_len);
+  p.edge_node = stg.dev<const uint32_t>(t_en);
+  p.edge_action = stg.dev<const uint8_t>(t_ea);
+  p.edge_reward = stg.dev<const double>(t_er);
+  p.value = stg.dev<double>(s_val);
+  p.latest = stg.dev<double>(s_lat);
+  p.visits = stg.dev<uint32_t>(s_vis);
+  p.q = stg.dev<double>(s_q);
+  p.n = stg.dev<uint32_t>(s_n);
+  const uint64_t total = (uint64_t)n_paths * num_agents;
+  const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, (uint64_t)e->num_sms * 8));
+  backup_uct_kernel<<<grid, 256, 0, e->stream>>>(p);
+  e->launches++;
+  MAMCTS_CUDA(e, cudaGetLastError());
+  if (stats->mem == MAMCTS_MEM_HOST) {
+    MAMCTS_CUDA(e, cudaMemcpyAsync(stats->value, p.value, sizeof(double) * S, cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaMemcpyAsync(stats->latest_return, p.latest, sizeof(double) * S, cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaMemcpyAsync(stats->total_visits, p.visits, sizeof(uint32_t) * S, cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaMemcpyAsync(stats->q, p.q, sizeof(double) * S * MA, cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaMemcpyAsync(stats->n, p.n, sizeof(uint32_t) * S * MA, cudaMemcpyDeviceToHost, e->stream));
+  }
+  return stg.finish();
+}
+
+int mamcts_root_merge(mamcts_engine* e, const mamcts_uct_stats* stats, uint32_t n_trees,
+                      int32_t mem, const uint32_t* root_slot, uint32_t num_actions,
+                      double* merged_q, uint64_t* merged_n, uint32_t* merged_occurrences,
+                      uint64_t* merged_total_visits, double* merged_value,
+                      uint32_t* best_action) {
+  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_root_merge: null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!stats || !root_slot || n_trees == 0) return fail(e, MAMCTS_ERR_INVALID, "mamcts_root_merge: null argument");
+  if (num_actions > stats->max_actions) return fail(e, MAMCTS_ERR_INVALID, "mamcts_root_merge: num_actions > max_actions");
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  const size_t S = stats->num_slots, MA = stats->max_actions;
+  ArgStager stg(e);
+  const int t_slot = stg.plan(root_slot, sizeof(uint32_t) * n_trees, mem, false);
+  const int s_vis = stg.plan(stats->total_visits, sizeof(uint32_t) * S, stats->mem, false);
+  const int s_q = stg.plan(stats->q, sizeof(double) * S * MA, stats->mem, false);
+  const int s_n = stg.plan(stats->n, sizeof(uint32_t) * S * MA, stats->mem, false);
+  int rc = stg.commit();
+  if (rc != MAMCTS_OK) return rc;
+  RootGather g;
+  std::memset(&g, 0, sizeof(g));
+  g.q = stg.dev<const double>(s_q);
+  g.n = stg.dev<const uint32_t>(s_n);
+  g.visits = stg.dev<const uint32_t>(s_vis);
+  g.root_slot = stg.dev<const uint32_t>(t_slot);
+  g.max_actions = stats->max_actions;
+  return root_merge_device(e, g, n_trees, num_actions, merged_q, merged_n, merged_occurrences,
+                           merged_total_visits, merged_value, best_action);
+}
+
+}  // extern "C"

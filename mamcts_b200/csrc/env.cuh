@@ -1,0 +1,110 @@
+// env.cuh - device restatement of the two environments' execute(), one lane per episode, state in
+// registers. All floating point is IEEE binary64 in the reference's operation order; the library
+// is compiled with -fmad=false so no multiply-add is contracted.
+#pragma once
+#include <stdint.h>
+
+namespace mamcts {
+
+// Everything execute() reads that is constant over a launch.
+struct EnvParams {
+  // CrossingState<int> (reference environments/crossing_state_parameters.h:15-33)
+  double r_goal, r_coll, r_step;
+  int32_t min_v_ego;
+  int32_t crossing_point;   // CROSSING_POINT() = (CHAIN_LENGTH-1)/2+1, :28
+  int32_t goal_pos;
+  int32_t cost_only_collision;
+  uint32_t n_ego_actions;   // NUM_EGO_ACTIONS(), :25
+  uint32_t n_other_actions;
+  // SimpleState (reference test/uct/simple_state.h:16)
+  int32_t win_len, lose_len;
+};
+
+// CrossingState<int> with NO other agents. Positions / last actions live in registers.
+template <int NO>
+struct CrossingEnv {
+  static constexpr int A = NO + 1;
+  static constexpr int kStateInts = A;     // x_pos per agent
+  static constexpr bool kHasCost = true;   // get_num_costs() == 1, crossing_state.h:101-103
+  struct State {
+    int32_t x[A];
+    int32_t last[A];
+    uint32_t flags;  // bit0 terminal, bit1 goal, bit2 collided
+  };
+
+  __device__ __forceinline__ static uint32_t num_actions(const EnvParams& p, int agent) {
+    return agent == 0 ? p.n_ego_actions : p.n_other_actions;
+  }
+  __device__ __forceinline__ static bool terminal(const EnvParams&, const State& s) { return s.flags & 1u; }
+
+  // act[0] = ego action index; act[i>0] = the Domain value of other i (for index-valued sources the
+  // reference's bit-cast of the raw index, i.e. +index).
+  // Restates CrossingState<int>::execute, reference environments/crossing_state.h:115-163.
+  __device__ __forceinline__ static void step(const EnvParams& p, State& s, const int32_t (&act)[A],
+                                              double& r_ego, double& r_other, double& cost) {
+    const int32_t old_x = s.x[0];
+    const int32_t v_ego = act[0] + p.min_v_ego;            // :306-309
+    const int32_t new_x = old_x + v_ego;                   // :119 (ego not clamped)
+    const bool oob = new_x < 0;                            // :121-123
+    const bool ego_encloses = (new_x >= p.crossing_point) & (old_x <= p.crossing_point);
+    bool coll = false;
+#pragma unroll
+    for (int i = 1; i < A; ++i) {
+      const int32_t ox = s.x[i];
+      const int32_t nx = max(ox + act[i], 0);              // :130-131
+      coll |= ego_encloses & (nx >= p.crossing_point) & (ox <= p.crossing_point);  // :135-139
+      s.x[i] = nx;
+      s.last[i] = act[i];
+    }
+    s.x[0] = new_x;
+    s.last[0] = v_ego;
+    const bool goal = (new_x >= p.goal_pos) & !coll;       // :142
+    s.flags = (uint32_t)(goal | coll | oob) | ((uint32_t)goal << 1) | ((uint32_t)coll << 2);  // :144
+    // :146-148 evaluated left to right in double (bool -> double products keep signed zeros)
+    double r = __dadd_rn(__dmul_rn((double)(int)goal, p.r_goal), __dmul_rn((double)(int)coll, p.r_coll));
+    r = __dadd_rn(r, __dmul_rn(p.r_coll, (double)(int)oob));
+    r = __dadd_rn(r, p.r_step);
+    r_ego = r;
+    r_other = 0.0;                                         // rewards[1..] stay 0 (:145 resize)
+    cost = p.cost_only_collision ? (double)(int)coll : -r; // :149-153
+  }
+};
+
+// SimpleState: one int32 of state, 2 agents x 2 actions (reference test/uct/simple_state.h).
+struct SimpleEnv {
+  static constexpr int A = 2;
+  static constexpr int kStateInts = 1;     // state_length_
+  static constexpr bool kHasCost = false;  // get_num_costs() == 0, :60-62
+  struct State {
+    int32_t x[A];     // x[0] = state_length_, x[1] unused (kept for a uniform interface)
+    int32_t last[A];  // unused
+    uint32_t flags;   // bit0 terminal
+  };
+  __device__ __forceinline__ static uint32_t num_actions(const EnvParams&, int) { return 2; }
+  __device__ __forceinline__ static bool terminal(const EnvParams& p, const State& s) {
+    return (s.x[0] >= p.win_len) | (s.x[0] <= p.lose_len);  // is_terminal :72-74
+  }
+  // Restates SimpleState::execute, reference test/uct/simple_state.h:26-54.
+  __device__ __forceinline__ static void step(const EnvParams& p, State& s, const int32_t (&act)[A],
+                                              double& r_ego, double& r_other, double& cost) {
+    r_ego = 0.0;
+    r_other = 0.0;
+    cost = 0.0;
+    if (act[0] != act[1]) {                                // :35
+      int32_t nl = s.x[0] + 1;
+      r_ego = 1.0;
+      r_other = 1.0;
+      if (nl >= p.win_len) {                               // :43-46
+        r_ego = 5.0;
+        r_other = 10.0;
+        nl = p.win_len;
+      }
+      s.x[0] = nl;
+    }
+    s.last[0] = act[0];
+    s.last[1] = act[1];
+    s.flags = (uint32_t)terminal(p, s);
+  }
+};
+
+}  // namespace mamcts

@@ -1,0 +1,62 @@
+// philox.cuh - counter-based Philox4x32-10 (Salmon et al., SC'11) and the engine's action-draw
+// stream layout. Device-only; the CPU checker has its own independent copy.
+#pragma once
+#include <stdint.h>
+
+namespace mamcts {
+
+struct Philox4 {
+  uint32_t w[4];
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0);
+    const uint32_t lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2);
+    const uint32_t lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  Philox4 out;
+  out.w[0] = c0; out.w[1] = c1; out.w[2] = c2; out.w[3] = c3;
+  return out;
+}
+
+// 16-bit lane h (0..7) of a block. h is a compile-time constant at every call site.
+__device__ __forceinline__ uint32_t philox_half(const Philox4& b, int h) {
+  return (h & 1) ? (b.w[h >> 1] >> 16) : (b.w[h >> 1] & 0xFFFFu);
+}
+
+// Exactly-uniform draw in [0, n) from the 16-bit word x of stream position `pos` (Lemire's
+// multiply-shift with rejection). The r-th retry reads lane ((r) & 7) of
+// philox({pos, lo, hi, 0x10000 + (r >> 3)}); taken with probability (65536 mod n) / 65536.
+__device__ __forceinline__ uint32_t philox_bounded(uint32_t x, uint32_t n, uint32_t pos,
+                                                   uint32_t stream_lo, uint32_t stream_hi,
+                                                   uint32_t k0, uint32_t k1) {
+  uint32_t m = x * n;
+  uint32_t l = m & 0xFFFFu;
+  if (l < n) {
+    const uint32_t t = 65536u % n;
+    uint32_t r = 0;
+    while (l < t) {
+      const Philox4 b = philox4x32_10(pos, stream_lo, stream_hi, 0x10000u + (r >> 3), k0, k1);
+      const uint32_t hh = r & 7u;
+      const uint32_t word = b.w[0] * (uint32_t)((hh >> 1) == 0) + b.w[1] * (uint32_t)((hh >> 1) == 1) +
+                            b.w[2] * (uint32_t)((hh >> 1) == 2) + b.w[3] * (uint32_t)((hh >> 1) == 3);
+      x = (hh & 1u) ? (word >> 16) : (word & 0xFFFFu);
+      m = x * n;
+      l = m & 0xFFFFu;
+      ++r;
+    }
+  }
+  return m >> 16;
+}
+
+}  // namespace mamcts

@@ -1,0 +1,456 @@
+// rollout.cu - the batched random-heuristic rollout (reference
+// mcts/heuristics/random_heuristic.h:27-104) as a persistent CUDA kernel for sm_100a.
+//
+// Mapping: one lane = one episode, state in registers; a warp keeps 32 episodes in flight and
+// refills finished lanes from the grid-strided work list in a warp-uniform "service" step, so the
+// environment step always runs converged. PHILOX draws are laid out so that one Philox4x32-10 block
+// feeds S = 8/A consecutive steps and all lanes of a warp regenerate their block at the same loop
+// iteration. K > 1 rollouts per leaf go through a per-rollout scratch and a fixed-
+// order warp-shuffle segmented reduction (reduce.cu), so the means are deterministic.
+#include <algorithm>
+#include <cstring>
+#include <type_traits>
+
+#include "engine.h"
+#include "env.cuh"
+#include "philox.cuh"
+#include "staging.h"
+
+namespace mamcts {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int kRolloutThreads = 256;
+constexpr int kServiceThreshold = 8;  // finished lanes that trigger a refill while others still run
+
+struct RolloutParams {
+  uint32_t n_leaves, K, total;
+  // inputs (device)
+  const int32_t* x;
+  const int32_t* last;
+  const uint8_t* flags;
+  const uint32_t* depth;
+  // action source
+  const int8_t* replay;
+  const uint32_t* replay_steps;
+  uint32_t replay_stride;
+  uint32_t const_actions[MAMCTS_MAX_AGENTS];
+  uint32_t key0, key1;
+  const uint32_t* stream_hi;
+  uint32_t stream_hi_base, stream_lo_base;
+  // mcts
+  double gamma;
+  uint32_t rh_cap, max_depth;
+  EnvParams env;
+  // per-rollout outputs (device); index r = leaf*K + k; other_ret / final_* are SoA with stride total
+  double* ego_ret;
+  double* other_ret;
+  double* cost;
+  double* step_len;
+  uint32_t* steps;
+  int32_t* final_x;
+  int32_t* final_last;
+  uint8_t* final_flags;
+  double* trace;
+  uint32_t trace_stride;
+  unsigned long long* total_steps;
+};
+
+template <class Env, int KIND>
+struct StepsPerBlock {
+  static constexpr int value = (KIND == MAMCTS_SRC_PHILOX && Env::A <= 8) ? 8 / Env::A : 1;
+};
+
+template <class Env, int KIND, bool PARITY>
+__global__ void __launch_bounds__(kRolloutThreads)
+rollout_kernel(const __grid_constant__ RolloutParams p) {
+  constexpr int A = Env::A;
+  constexpr int S = StepsPerBlock<Env, KIND>::value;
+  constexpr bool kSimple = std::is_same<Env, SimpleEnv>::value;
+  constexpr int XR = kSimple ? 1 : A;  // rows of the x arrays (SimpleState: only state_length_)
+  const uint32_t G = gridDim.x * blockDim.x;
+  uint32_t rid = blockIdx.x * blockDim.x + threadIdx.x;
+
+  typename Env::State st;
+  double m = 0.0, ego = 0.0, other = 0.0, cost = 0.0, prob = 1.0;
+  uint32_t it = 0, depth = 0, cap = 0, leaf = 0, s_lo = 0, s_hi = 0;
+  bool has = false, fin = true;
+  unsigned long long lane_steps = 0;
+  const double inv_n_ego = 1.0 / (double)Env::num_actions(p.env, 0);  // random_heuristic.h:88
+
+  auto load = [&]() {
+    has = rid < p.total;
+    if (!has) return;
+    leaf = (p.K == 1) ? rid : rid / p.K;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      st.x[a] = (a < XR) ? __ldg(p.x + (size_t)a * p.n_leaves + leaf) : 0;
+      st.last[a] = (p.last && !kSimple) ? __ldg(p.last + (size_t)a * p.n_leaves + leaf) : 2;
+    }
+    st.flags = p.flags ? (uint32_t)(__ldg(p.flags + leaf) & 1u) : 0u;
+    depth = p.depth ? __ldg(p.depth + leaf) : 0u;
+    cap = p.rh_cap;
+    if (KIND == MAMCTS_SRC_REPLAY) cap = min(cap, __ldg(p.replay_steps + leaf));
+    if (KIND == MAMCTS_SRC_PHILOX) {
+      s_hi = p.stream_hi ? __ldg(p.stream_hi + leaf) : p.stream_hi_base;
+      s_lo = p.stream_lo_base + rid;
+    }
+    m = p.gamma;   // random_heuristic.h:46
+    ego = 0.0; other = 0.0; cost = 0.0; prob = 1.0; it = 0;
+    fin = Env::terminal(p.env, st) | (it >= cap) | (depth >= p.max_depth);  // :51-54
+  };
+
+  auto finalize = [&]() {
+    // random_heuristic.h:95-101
+    const double ego_out = __dmul_rn(ego, prob);
+    const double cost_out = Env::kHasCost ? __dmul_rn(cost, prob) : 0.0;
+    if (p.ego_ret) p.ego_ret[rid] = ego_out;
+    if (p.other_ret) {
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) p.other_ret[(size_t)j * p.total + rid] = other;
+    }
+    if (p.cost) p.cost[rid] = cost_out;
+    if (p.step_len) p.step_len[rid] = (double)it;
+    lane_steps += it;
+    if (PARITY) {
+      if (p.steps) p.steps[rid] = it;
+      if (p.final_x) {
+#pragma unroll
+        for (int a = 0; a < XR; ++a) p.final_x[(size_t)a * p.total + rid] = st.x[a];
+      }
+      if (p.final_last) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) p.final_last[(size_t)a * p.total + rid] = st.last[a];
+      }
+      if (p.final_flags) p.final_flags[rid] = (uint8_t)((st.flags & ~1u) | (uint32_t)Env::terminal(p.env, st));
+    }
+  };
+
+  load();
+
+  while (true) {
+    const unsigned need = __ballot_sync(FULL, has && fin);
+    const unsigned running = __ballot_sync(FULL, has && !fin);
+    if (need != 0 && (running == 0 || __popc(need) >= kServiceThreshold)) {
+      if (has && fin) {
+        finalize();
+        rid += G;
+        load();
+      }
+      continue;
+    }
+    if (running == 0) break;
+
+    const bool active0 = has && !fin;
+    Philox4 blk[(A + 7) / 8];
+    if (KIND == MAMCTS_SRC_PHILOX && active0) {
+      if (A <= 8) {
+        blk[0] = philox4x32_10(it / S, s_lo, s_hi, 0u, p.key0, p.key1);
+      } else {
+#pragma unroll
+        for (int b = 0; b < (A + 7) / 8; ++b)
+          blk[b] = philox4x32_10(it * ((A + 7) / 8) + b, s_lo, s_hi, 0u, p.key0, p.key1);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (has && !fin) {
+        int32_t act[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          if (KIND == MAMCTS_SRC_REPLAY) {
+            act[a] = (int32_t)p.replay[((size_t)leaf * p.replay_stride + it) * A + a];
+          } else if (KIND == MAMCTS_SRC_REFERENCE_CONST) {
+            act[a] = (int32_t)p.const_actions[a];
+          } else {
+            const uint32_t h = (A <= 8) ? philox_half(blk[0], s * A + a) : philox_half(blk[a / 8], a % 8);
+            act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi,
+                                             p.key0, p.key1);
+          }
+        }
+        double r_ego, r_other, c;
+        Env::step(p.env, st, act, r_ego, r_other, c);
+        if (PARITY && p.trace && it < p.trace_stride) p.trace[(size_t)rid * p.trace_stride + it] = r_ego;
+        m = __dmul_rn(p.gamma, m);                 // :71
+        ego = __dadd_rn(ego, __dmul_rn(m, r_ego)); // :72
+        other = __dmul_rn(m, r_other);             // :73-77 (assigned, not accumulated)
+        if (Env::kHasCost) cost = __dadd_rn(cost, c);  // :79-84
+        m = __dmul_rn(m, p.gamma);                 // :85
+        prob = __dmul_rn(prob, inv_n_ego);         // :88
+        it += 1;                                   // :89
+        depth += 1;                                // :90
+        fin = Env::terminal(p.env, st) | (it >= cap) | (depth >= p.max_depth);
+      }
+    }
+  }
+
+  // env-steps counter: one atomic per warp
+  if (p.total_steps) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) lane_steps += __shfl_xor_sync(FULL, lane_steps, off);
+    if ((threadIdx.x & 31) == 0 && lane_steps) atomicAdd(p.total_steps, lane_steps);
+  }
+}
+
+// K-rollout mean per leaf in the fixed order of DESIGN.md §6 (oracle: orc_reduce_mean).
+//   K < 32 : K-lane segments, xor-butterfly K/2..1, mean = total / K
+//   K >= 32: one warp per leaf; lane l sums vals[c*32R + j*32 + l], j < R = min(K/32, 8), then a
+//            32-lane xor-butterfly; chunk partials are added in chunk order.
+// blockIdx.y selects the array (src + y*src_stride -> dst + y*dst_stride).
+__global__ void __launch_bounds__(256)
+reduce_mean_kernel(const double* __restrict__ src, double* __restrict__ dst, uint32_t n, uint32_t K,
+                   size_t src_stride, size_t dst_stride) {
+  src += (size_t)blockIdx.y * src_stride;
+  dst += (size_t)blockIdx.y * dst_stride;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  if (K < 32) {
+    const uint32_t per_warp = 32 / K;
+    const uint32_t groups = (n + per_warp - 1) / per_warp;
+    for (uint32_t g = warp; g < groups; g += num_warps) {
+      const uint32_t leaf = g * per_warp + lane / K;
+      double v = leaf < n ? src[(size_t)leaf * K + (lane % K)] : 0.0;
+      for (uint32_t off = K / 2; off >= 1; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, off));
+      if (leaf < n && (lane % K) == 0) dst[leaf] = v / (double)K;
+    }
+  } else {
+    const uint32_t R = min(K / 32, 8u);
+    const uint32_t chunk = 32 * R;
+    const uint32_t nchunks = K / chunk;
+    for (uint32_t leaf = warp; leaf < n; leaf += num_warps) {
+      double total = 0.0;
+      for (uint32_t c = 0; c < nchunks; ++c) {
+        double acc = 0.0;
+        for (uint32_t j = 0; j < R; ++j)
+          acc = __dadd_rn(acc, src[(size_t)leaf * K + (size_t)c * chunk + j * 32 + lane]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, off));
+        total = __dadd_rn(total, acc);
+      }
+      if (lane == 0) dst[leaf] = total / (double)K;
+    }
+  }
+}
+
+static bool valid_k(uint32_t K) {
+  if (K == 1 || K == 2 || K == 4 || K == 8 || K == 16) return true;
+  if (K >= 32 && K <= 256 && K % 32 == 0) return true;
+  return K > 256 && K % 256 == 0;
+}
+
+// Persistent grid: as many blocks as stay resident (occupancy x SM count), never more than the work.
+template <class Kernel>
+static int launch_persistent(mamcts_engine* e, Kernel kernel, const RolloutParams& p) {
+  int per_sm = 0;
+  MAMCTS_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRolloutThreads, 0));
+  const int max_blocks = e->num_sms * std::max(per_sm, 1);
+  const int need_blocks = (int)(((uint64_t)p.total + kRolloutThreads - 1) / kRolloutThreads);
+  const int grid = std::max(1, std::min(max_blocks, need_blocks));
+  kernel<<<dim3(grid), dim3(kRolloutThreads), 0, e->stream>>>(p);
+  return MAMCTS_OK;
+}
+
+template <class Env>
+static int launch_rollout(mamcts_engine* e, const RolloutParams& p, int kind, bool parity) {
+#define MAMCTS_LAUNCH(KIND)                                                                   \
+  do {                                                                                        \
+    int rc__ = parity ? launch_persistent(e, rollout_kernel<Env, KIND, true>, p)              \
+                      : launch_persistent(e, rollout_kernel<Env, KIND, false>, p);            \
+    if (rc__ != MAMCTS_OK) return rc__;                                                       \
+  } while (0)
+  if (kind == MAMCTS_SRC_REPLAY) MAMCTS_LAUNCH(MAMCTS_SRC_REPLAY);
+  else if (kind == MAMCTS_SRC_REFERENCE_CONST) MAMCTS_LAUNCH(MAMCTS_SRC_REFERENCE_CONST);
+  else MAMCTS_LAUNCH(MAMCTS_SRC_PHILOX);
+#undef MAMCTS_LAUNCH
+  e->launches += 1;
+  MAMCTS_CUDA(e, cudaGetLastError());
+  return MAMCTS_OK;
+}
+
+static int dispatch_crossing(mamcts_engine* e, const RolloutParams& p, int num_others, int kind,
+                             bool parity) {
+  switch (num_others) {
+    case 1: return launch_rollout<CrossingEnv<1>>(e, p, kind, parity);
+    case 2: return launch_rollout<CrossingEnv<2>>(e, p, kind, parity);
+    case 3: return launch_rollout<CrossingEnv<3>>(e, p, kind, parity);
+    case 4: return launch_rollout<CrossingEnv<4>>(e, p, kind, parity);
+    case 5: return launch_rollout<CrossingEnv<5>>(e, p, kind, parity);
+    case 6: return launch_rollout<CrossingEnv<6>>(e, p, kind, parity);
+    case 7: return launch_rollout<CrossingEnv<7>>(e, p, kind, parity);
+    case 11: return launch_rollout<CrossingEnv<11>>(e, p, kind, parity);
+    case 15: return launch_rollout<CrossingEnv<15>>(e, p, kind, parity);
+    default:
+      return fail(e, MAMCTS_ERR_UNSUPPORTED,
+                  "rollout: compiled for 1..7, 11 or 15 other agents (CrossingState)");
+  }
+}
+
+// Shared body of the two entry points. A = number of agents; x_rows = rows of the state array.
+static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* mp, const EnvParams& ep,
+                          uint32_t A, uint32_t n, uint32_t K, int32_t mem, const int32_t* state_x,
+                          const int32_t* state_last, const uint8_t* state_flags,
+                          const uint32_t* start_depth, const mamcts_action_source* src,
+                          mamcts_rollout_out* out) {
+  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "rollout: null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!mp || !src || !out || !state_x) return fail(e, MAMCTS_ERR_INVALID, "rollout: null argument");
+  if (n == 0) return MAMCTS_OK;
+  if (!valid_k(K))
+    return fail(e, MAMCTS_ERR_INVALID,
+                "rollout: rollouts_per_leaf must be 1,2,4,8,16, a multiple of 32 up to 256, or a multiple of 256");
+  if ((uint64_t)n * K > 0xF0000000ull) return fail(e, MAMCTS_ERR_INVALID, "rollout: n_leaves * K too large for one call");
+  if (src->kind == MAMCTS_SRC_REPLAY && (K != 1 || !src->replay_actions || !src->replay_steps))
+    return fail(e, MAMCTS_ERR_INVALID, "rollout: REPLAY needs K == 1 and replay buffers");
+  if (src->kind < MAMCTS_SRC_REPLAY || src->kind > MAMCTS_SRC_PHILOX)
+    return fail(e, MAMCTS_ERR_INVALID, "rollout: unknown action source");
+  if (src->kind == MAMCTS_SRC_REFERENCE_CONST) {
+    for (uint32_t a = 0; a < A; ++a) {
+      const uint32_t na = (env_kind == MAMCTS_ENV_SIMPLE) ? 2u : (a == 0 ? ep.n_ego_actions : ep.n_other_actions);
+      if (src->const_actions[a] >= na) return fail(e, MAMCTS_ERR_INVALID, "rollout: const action out of range");
+    }
+  }
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  const uint32_t total = n * K;
+  const uint32_t x_rows = (env_kind == MAMCTS_ENV_SIMPLE) ? 1 : A;
+
+  ArgStager stg(e);
+  const int t_x = stg.plan(state_x, sizeof(int32_t) * x_rows * n, mem, false);
+  const int t_last = stg.plan(state_last, sizeof(int32_t) * x_rows * n, mem, false);
+  const int t_flags = stg.plan(state_flags, n, mem, false);
+  const int t_depth = stg.plan(start_depth, sizeof(uint32_t) * n, mem, false);
+  const int t_rep = stg.plan(src->kind == MAMCTS_SRC_REPLAY ? src->replay_actions : nullptr,
+                             (size_t)n * src->replay_stride * A, src->mem, false);
+  const int t_reps = stg.plan(src->kind == MAMCTS_SRC_REPLAY ? src->replay_steps : nullptr,
+                              sizeof(uint32_t) * n, src->mem, false);
+  const int t_shi = stg.plan(src->kind == MAMCTS_SRC_PHILOX ? src->stream_hi : nullptr,
+                             sizeof(uint32_t) * n, src->mem, false);
+  const int o_ego = stg.plan(out->ego_return, sizeof(double) * n, out->mem, true);
+  const int o_oth = stg.plan(out->other_return, sizeof(double) * (A - 1) * n, out->mem, true);
+  const int o_cost = stg.plan(out->ego_cost, sizeof(double) * n, out->mem, true);
+  const int o_len = stg.plan(out->step_length, sizeof(double) * n, out->mem, true);
+  const int o_tot = stg.plan(out->total_steps, sizeof(uint64_t), out->mem, true);
+  const int o_steps = stg.plan(out->steps, sizeof(uint32_t) * total, out->mem, true);
+  const int o_fx = stg.plan(out->final_x, sizeof(int32_t) * x_rows * total, out->mem, true);
+  const int o_fl = stg.plan(out->final_last_action, sizeof(int32_t) * A * total, out->mem, true);
+  const int o_ff = stg.plan(out->final_flags, total, out->mem, true);
+  const int o_tr = stg.plan(out->reward_trace, sizeof(double) * (size_t)total * out->trace_stride, out->mem, true);
+  int rc = stg.commit();
+  if (rc != MAMCTS_OK) return rc;
+
+  RolloutParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n_leaves = n; p.K = K; p.total = total;
+  p.x = stg.dev<const int32_t>(t_x);
+  p.last = stg.dev<const int32_t>(t_last);
+  p.flags = stg.dev<const uint8_t>(t_flags);
+  p.depth = stg.dev<const uint32_t>(t_depth);
+  p.replay = stg.dev<const int8_t>(t_rep);
+  p.replay_steps = stg.dev<const uint32_t>(t_reps);
+  p.replay_stride = src->replay_stride;
+  for (int a = 0; a < MAMCTS_MAX_AGENTS; ++a) p.const_actions[a] = src->const_actions[a];
+  p.key0 = (uint32_t)src->philox_seed;
+  p.key1 = (uint32_t)(src->philox_seed >> 32);
+  p.stream_hi = stg.dev<const uint32_t>(t_shi);
+  p.stream_hi_base = src->stream_hi_base;
+  p.stream_lo_base = src->stream_lo_base;
+  p.gamma = mp->discount_factor;
+  p.rh_cap = mp->rh_max_number_of_iterations;
+  p.max_depth = mp->max_search_depth;
+  p.env = ep;
+  p.steps = stg.dev<uint32_t>(o_steps);
+  p.final_x = stg.dev<int32_t>(o_fx);
+  p.final_last = stg.dev<int32_t>(o_fl);
+  p.final_flags = stg.dev<uint8_t>(o_ff);
+  p.trace = stg.dev<double>(o_tr);
+  p.trace_stride = out->trace_stride;
+  p.total_steps = reinterpret_cast<unsigned long long*>(stg.dev<uint64_t>(o_tot));
+  if (p.total_steps) MAMCTS_CUDA(e, cudaMemsetAsync(p.total_steps, 0, sizeof(uint64_t), e->stream));
+  if (p.trace) MAMCTS_CUDA(e, cudaMemsetAsync(p.trace, 0, sizeof(double) * (size_t)total * out->trace_stride, e->stream));
+
+  double* d_ego = stg.dev<double>(o_ego);
+  double* d_oth = stg.dev<double>(o_oth);
+  double* d_cost = stg.dev<double>(o_cost);
+  double* d_len = stg.dev<double>(o_len);
+  const uint32_t n_arrays = A + 2;  // ego, A-1 others, cost, step_len
+  if (K == 1) {
+    p.ego_ret = d_ego; p.other_ret = d_oth; p.cost = d_cost; p.step_len = d_len;
+  } else {
+    rc = ensure_scratch(e, sizeof(double) * (size_t)n_arrays * total);
+    if (rc != MAMCTS_OK) return rc;
+    double* s = static_cast<double*>(e->scratch);
+    p.ego_ret = s;
+    p.other_ret = s + (size_t)total;
+    p.cost = s + (size_t)A * total;
+    p.step_len = s + (size_t)(A + 1) * total;
+  }
+  const bool parity = p.steps || p.final_x || p.final_last || p.final_flags || p.trace;
+
+  if (env_kind == MAMCTS_ENV_SIMPLE) rc = launch_rollout<SimpleEnv>(e, p, src->kind, parity);
+  else rc = dispatch_crossing(e, p, (int)A - 1, src->kind, parity);
+  if (rc != MAMCTS_OK) return rc;
+
+  if (K > 1) {
+    const double* s = static_cast<const double*>(e->scratch);
+    const int rgrid = std::max(1, std::min(grid_for(e, 4), (int)((n + 7) / 8)));
+    if (d_ego) { reduce_mean_kernel<<<dim3(rgrid, 1), 256, 0, e->stream>>>(s, d_ego, n, K, 0, 0); e->launches++; }
+    if (d_oth && A > 1) {
+      reduce_mean_kernel<<<dim3(rgrid, A - 1), 256, 0, e->stream>>>(s + (size_t)total, d_oth, n, K, total, n);
+      e->launches++;
+    }
+    if (d_cost) { reduce_mean_kernel<<<dim3(rgrid, 1), 256, 0, e->stream>>>(s + (size_t)A * total, d_cost, n, K, 0, 0); e->launches++; }
+    if (d_len) { reduce_mean_kernel<<<dim3(rgrid, 1), 256, 0, e->stream>>>(s + (size_t)(A + 1) * total, d_len, n, K, 0, 0); e->launches++; }
+    MAMCTS_CUDA(e, cudaGetLastError());
+  }
+  return stg.finish();
+}
+
+}  // namespace mamcts
+
+using namespace mamcts;
+
+extern "C" {
+
+int mamcts_rollout_crossing_i32(mamcts_engine* e, const mamcts_params* mp,
+                                const mamcts_crossing_params* cp, uint32_t n_leaves,
+                                uint32_t rollouts_per_leaf, int32_t mem, const int32_t* state_x,
+                                const int32_t* state_last_action, const uint8_t* state_flags,
+                                const uint32_t* start_depth, const mamcts_action_source* src,
+                                mamcts_rollout_out* out) {
+  if (!cp) return fail(e, MAMCTS_ERR_INVALID, "mamcts_rollout_crossing_i32: null crossing params");
+  if (cp->num_other_agents + 1 > MAMCTS_MAX_AGENTS || cp->num_other_agents == 0)
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_rollout_crossing_i32: 1..15 other agents supported");
+  EnvParams ep;
+  std::memset(&ep, 0, sizeof(ep));
+  ep.r_goal = cp->reward_goal_reached;
+  ep.r_coll = cp->reward_collision;
+  ep.r_step = cp->reward_step;
+  ep.min_v_ego = cp->min_velocity_ego;
+  ep.crossing_point = (cp->chain_length - 1) / 2 + 1;
+  ep.goal_pos = cp->ego_goal_pos;
+  ep.cost_only_collision = cp->cost_only_collision;
+  ep.n_ego_actions = (uint32_t)(cp->max_velocity_ego - cp->min_velocity_ego + 1);
+  ep.n_other_actions = cp->num_other_actions;
+  if (ep.n_ego_actions == 0 || ep.n_ego_actions > MAMCTS_MAX_ACTIONS || ep.n_other_actions == 0 ||
+      ep.n_other_actions > MAMCTS_MAX_ACTIONS)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_rollout_crossing_i32: action counts out of range");
+  return rollout_common(e, MAMCTS_ENV_CROSSING_I32, mp, ep, cp->num_other_agents + 1, n_leaves,
+                        rollouts_per_leaf, mem, state_x, state_last_action, state_flags, start_depth,
+                        src, out);
+}
+
+int mamcts_rollout_simple(mamcts_engine* e, const mamcts_params* mp, const mamcts_simple_params* sp,
+                          uint32_t n_leaves, uint32_t rollouts_per_leaf, int32_t mem,
+                          const int32_t* state_len, const uint32_t* start_depth,
+                          const mamcts_action_source* src, mamcts_rollout_out* out) {
+  if (!sp) return fail(e, MAMCTS_ERR_INVALID, "mamcts_rollout_simple: null simple params");
+  EnvParams ep;
+  std::memset(&ep, 0, sizeof(ep));
+  ep.win_len = sp->winning_state_length;
+  ep.lose_len = sp->loosing_state_length;
+  ep.n_ego_actions = 2;
+  ep.n_other_actions = 2;
+  return rollout_common(e, MAMCTS_ENV_SIMPLE, mp, ep, 2, n_leaves, rollouts_per_leaf, mem, state_len,
+                        nullptr, nullptr, start_depth, src, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+"""Thin Python host over the C ABI (include/mamcts_b200.h): numpy in / numpy out for HOST buffers,
+raw device pointers (e.g. torch tensors' data_ptr()) for DEVICE buffers.
+
+Mirrors the reference surfaces that sit on the hot path:
+  Engine.rollout_crossing / rollout_simple  <- RandomHeuristic::rollout
+                                               (reference mcts/heuristics/random_heuristic.h:27-104)
+  Engine.backup_uct                         <- the backprop loop, mcts/mcts.h:309-329
+  Engine.root_merge                         <- UctStatistic::merge_node_statistics, uct_statistic.h:165-184
+  Search                                    <- Mcts<S,UctStatistic,UctStatistic,RandomHeuristic>::search
+                                               for T root-parallel trees, mcts/mcts.h:133-221
+There is no CPU path here: every compute call goes to libmamcts_b200.so and raises on error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import (ENV_CROSSING_I32, ENV_SIMPLE, MAX_ACTIONS, MEM_DEVICE, MEM_HOST, SRC_PHILOX,
+                   SRC_REFERENCE_CONST, SRC_REPLAY, ActionSource, Config, CrossingParams, Params,
+                   RolloutOut, SearchConfig, SimpleParams, UctStats)
+
+
+class MamctsError(RuntimeError):
+    pass
+
+
+def _vp(a):
+    """void* of a numpy array (host) / int device pointer / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+def reference_expand_order(seed: int, num_actions: int):
+    """UctStatistic's deterministic widening order (reference uct_statistic.h:61-69)."""
+    lib = _abi.load()
+    out = (C.c_uint32 * num_actions)()
+    rc = lib.mamcts_reference_expand_order(seed, num_actions, out)
+    if rc != 0:
+        raise MamctsError(lib.mamcts_last_error(None).decode())
+    return list(out)
+
+
+class Engine:
+    """One CUDA device + stream (mamcts_engine)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _abi.load()
+        self.h = C.c_void_p()
+        cfg = Config(device=device, flags=0)
+        rc = self.lib.mamcts_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise MamctsError(f"mamcts_create failed ({rc}): {self.lib.mamcts_last_error(None).decode()}")
+        self.device = device
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise MamctsError(f"{what} failed ({rc}): {self.lib.mamcts_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.mamcts_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.mamcts_sync(self.h), "mamcts_sync")
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.mamcts_set_stream(self.h, C.c_void_p(cuda_stream)), "mamcts_set_stream")
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.mamcts_get_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mamcts_launch_count(self.h))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.mamcts_device_alloc(self.h, nbytes, C.byref(p)), "mamcts_device_alloc")
+        return int(p.value)
+
+    def device_free(self, ptr: int):
+        self._check(self.lib.mamcts_device_free(self.h, C.c_void_p(ptr)), "mamcts_device_free")
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        self._check(self.lib.mamcts_memcpy_h2d(self.h, C.c_void_p(dptr), _vp(arr), arr.nbytes), "h2d")
+
+    def d2h(self, arr: np.ndarray, dptr: int):
+        self._check(self.lib.mamcts_memcpy_d2h(self.h, _vp(arr), C.c_void_p(dptr), arr.nbytes), "d2h")
+
+    # -- NCCL ---------------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * _abi.NCCL_UNIQUE_ID_BYTES)()
+        self._check(self.lib.mamcts_comm_get_unique_id(self.h, buf), "mamcts_comm_get_unique_id")
+        return bytes(buf)
+
+    def comm_init_rank(self, unique_id: bytes, world_size: int, rank: int):
+        buf = (C.c_uint8 * _abi.NCCL_UNIQUE_ID_BYTES)(*unique_id)
+        self._check(self.lib.mamcts_comm_init_rank(self.h, buf, world_size, rank), "mamcts_comm_init_rank")
+
+    def comm_destroy(self):
+        self._check(self.lib.mamcts_comm_destroy(self.h), "mamcts_comm_destroy")
+
+    # -- rollouts -----------------------------------------------------------------------------
+    @staticmethod
+    def _source(kind, A, replay_actions=None, replay_steps=None, const_actions=None, seed=0,
+                stream_hi=None, stream_hi_base=0, stream_lo_base=0, mem=MEM_HOST):
+        src = ActionSource()
+        src.kind = kind
+        src.mem = mem
+        keep = []
+        if kind == SRC_REPLAY:
+            if mem == MEM_HOST:
+                ra = np.ascontiguousarray(replay_actions, dtype=np.int8)
+                rs = np.ascontiguousarray(replay_steps, dtype=np.uint32)
+                keep += [ra, rs]
+                src.replay_stride = ra.shape[1]
+                src.replay_actions = ra.ctypes.data
+                src.replay_steps = rs.ctypes.data
+            else:  # device pointers; replay_actions = (ptr, stride)
+                src.replay_actions, src.replay_stride = int(replay_actions[0]), int(replay_actions[1])
+                src.replay_steps = int(replay_steps)
+        elif kind == SRC_REFERENCE_CONST:
+            for a in range(A):
+                src.const_actions[a] = int(const_actions[a])
+        else:
+            src.philox_seed = seed
+            src.stream_hi_base = stream_hi_base
+            src.stream_lo_base = stream_lo_base
+            if stream_hi is not None:
+                if mem == MEM_HOST:
+                    sh = np.ascontiguousarray(stream_hi, dtype=np.uint32)
+                    keep.append(sh)
+                    src.stream_hi = sh.ctypes.data
+                else:
+                    src.stream_hi = int(stream_hi)
+        return src, keep
+
+    def _rollout_host(self, env, mp, envp, A, x, last, flags, depth, K, src_kw, want_parity,
+                      trace_stride):
+        x = np.ascontiguousarray(x, dtype=np.int32)
+        if env == ENV_SIMPLE:
+            x = x.reshape(1, -1)
+        n = x.shape[1]
+        total = n * K
+        last_a = None if last is None else np.ascontiguousarray(last, dtype=np.int32)
+        flags_a = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        depth_a = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+        src, keep = self._source(A=A, **src_kw)
+        res = dict(ego_return=np.zeros(n), other_return=np.zeros((A - 1, n)), ego_cost=np.zeros(n),
+                   step_length=np.zeros(n), total_steps=np.zeros(1, dtype=np.uint64))
+        out = RolloutOut()
+        out.mem = MEM_HOST
+        out.ego_return = res["ego_return"].ctypes.data
+        out.other_return = res["other_return"].ctypes.data
+        out.ego_cost = res["ego_cost"].ctypes.data
+        out.step_length = res["step_length"].ctypes.data
+        out.total_steps = res["total_steps"].ctypes.data
+        if want_parity:
+            xr = 1 if env == ENV_SIMPLE else A
+            res.update(steps=np.zeros(total, dtype=np.uint32),
+                       final_x=np.zeros((xr, total), dtype=np.int32),
+                       final_last_action=np.zeros((A, total), dtype=np.int32),
+                       final_flags=np.zeros(total, dtype=np.uint8))
+            out.steps = res["steps"].ctypes.data
+            out.final_x = res["final_x"].ctypes.data
+            out.final_last_action = res["final_last_action"].ctypes.data
+            out.final_flags = res["final_flags"].ctypes.data
+            if trace_stride:
+                res["reward_trace"] = np.zeros((total, trace_stride))
+                out.reward_trace = res["reward_trace"].ctypes.data
+                out.trace_stride = trace_stride
+        if env == ENV_CROSSING_I32:
+            rc = self.lib.mamcts_rollout_crossing_i32(
+                self.h, C.byref(mp), C.byref(envp), n, K, MEM_HOST, _vp(x), _vp(last_a), _vp(flags_a),
+                _vp(depth_a), C.byref(src), C.byref(out))
+            self._check(rc, "mamcts_rollout_crossing_i32")
+        else:
+            rc = self.lib.mamcts_rollout_simple(self.h, C.byref(mp), C.byref(envp), n, K, MEM_HOST,
+                                                _vp(x), _vp(depth_a), C.byref(src), C.byref(out))
+            self._check(rc, "mamcts_rollout_simple")
+        res["total_steps"] = int(res["total_steps"][0])
+        del keep
+        return res
+
+    def rollout_crossing(self, mp: Params, cp: CrossingParams, x, last=None, flags=None, depth=None,
+                         K: int = 1, kind: int = SRC_PHILOX, parity: bool = False,
+                         trace_stride: int = 0, **src_kw):
+        """HOST-buffer batched rollout through CrossingState<int>::execute. x: [A, n] int32."""
+        return self._rollout_host(ENV_CROSSING_I32, mp, cp, cp.num_other_agents + 1, x, last, flags,
+                                  depth, K, dict(kind=kind, **src_kw), parity, trace_stride)
+
+    def rollout_simple(self, mp: Params, sp: SimpleParams, length, depth=None, K: int = 1,
+                       kind: int = SRC_PHILOX, parity: bool = False, trace_stride: int = 0, **src_kw):
+        """HOST-buffer batched rollout through SimpleState::execute. length: [n] int32."""
+        return self._rollout_host(ENV_SIMPLE, mp, sp, 2, length, None, None, depth, K,
+                                  dict(kind=kind, **src_kw), parity, trace_stride)
+
+    def rollout_crossing_device(self, mp: Params, cp: CrossingParams, n: int, K: int, d_x: int,
+                                d_ego: int, d_other: int = 0, d_cost: int = 0, d_len: int = 0,
+                                d_total_steps: int = 0, d_last: int = 0, d_flags: int = 0,
+                                d_depth: int = 0, kind: int = SRC_PHILOX, **src_kw):
+        """DEVICE-buffer variant: raw device pointers, fully asynchronous on the engine stream."""
+        src, keep = self._source(A=cp.num_other_agents + 1, kind=kind, mem=MEM_DEVICE, **src_kw)
+        out = RolloutOut()
+        out.mem = MEM_DEVICE
+        out.ego_return = d_ego or None
+        out.other_return = d_other or None
+        out.ego_cost = d_cost or None
+        out.step_length = d_len or None
+        out.total_steps = d_total_steps or None
+        rc = self.lib.mamcts_rollout_crossing_i32(
+            self.h, C.byref(mp), C.byref(cp), n, K, MEM_DEVICE, C.c_void_p(d_x),
+            C.c_void_p(d_last) if d_last else None, C.c_void_p(d_flags) if d_flags else None,
+            C.c_void_p(d_depth) if d_depth else None, C.byref(src), C.byref(out))
+        self._check(rc, "mamcts_rollout_crossing_i32")
+        del keep
+
+    # -- backup -------------------------------------------------------------------------------
+    def backup_uct(self, mp: Params, num_agents: int, leaf_node, leaf_has_heuristic, ego_return,
+                   other_return, path_offset, path_len, edge_node, edge_action, edge_reward,
+                   stats: dict):
+        """HOST-buffer batched backup; `stats` holds numpy arrays value/latest_return/total_visits
+        [slots], q/n [slots, max_actions] and is updated in place."""
+        leaf_node = np.ascontiguousarray(leaf_node, dtype=np.uint32)
+        n_paths = leaf_node.shape[0]
+        has = np.ascontiguousarray(leaf_has_heuristic, dtype=np.uint8)
+        ego = np.ascontiguousarray(ego_return, dtype=np.float64)
+        oth = np.ascontiguousarray(other_return, dtype=np.float64)
+        off = np.ascontiguousarray(path_offset, dtype=np.uint32)
+        ln = np.ascontiguousarray(path_len, dtype=np.uint32)
+        en = np.ascontiguousarray(edge_node, dtype=np.uint32)
+        ea = np.ascontiguousarray(edge_action, dtype=np.uint8)
+        er = np.ascontiguousarray(edge_reward, dtype=np.float64)
+        st = self._stats_struct(stats)
+        rc = self.lib.mamcts_backup_uct(self.h, C.byref(mp), num_agents, n_paths, MEM_HOST,
+                                        _vp(leaf_node), _vp(has), _vp(ego), _vp(oth), _vp(off),
+                                        _vp(ln), _vp(en), _vp(ea), _vp(er), C.byref(st))
+        self._check(rc, "mamcts_backup_uct")
+
+    @staticmethod
+    def _stats_struct(stats: dict) -> UctStats:
+        st = UctStats()
+        st.mem = MEM_HOST
+        st.num_slots = stats["value"].shape[0]
+        st.max_actions = stats["q"].shape[1]
+        for k, dt in (("value", np.float64), ("latest_return", np.float64),
+                      ("total_visits", np.uint32), ("q", np.float64), ("n", np.uint32)):
+            a = stats[k]
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"], k
+        st.value = stats["value"].ctypes.data
+        st.latest_return = stats["latest_return"].ctypes.data
+        st.total_visits = stats["total_visits"].ctypes.data
+        st.q = stats["q"].ctypes.data
+        st.n = stats["n"].ctypes.data
+        return st
+
+    def root_merge(self, stats: dict, root_slot, num_actions: int):
+        st = self._stats_struct(stats)
+        slots = np.ascontiguousarray(root_slot, dtype=np.uint32)
+        return self._merge_call(
+            lambda *o: self.lib.mamcts_root_merge(self.h, C.byref(st), slots.shape[0], MEM_HOST,
+                                                  _vp(slots), num_actions, *o),
+            num_actions, "mamcts_root_merge")
+
+    def _merge_call(self, fn, num_actions, what):
+        q = (C.c_double * MAX_ACTIONS)()
+        n = (C.c_uint64 * MAX_ACTIONS)()
+        occ = (C.c_uint32 * MAX_ACTIONS)()
+        vis = C.c_uint64(0)
+        val = C.c_double(0)
+        best = C.c_uint32(0)
+        self._check(fn(q, n, occ, C.byref(vis), C.byref(val), C.byref(best)), what)
+        return dict(q=np.array(q[:num_actions]), n=np.array(n[:num_actions], dtype=np.uint64),
+                    occurrences=np.array(occ[:num_actions], dtype=np.uint32), visits=vis.value,
+                    value=val.value, best=best.value)
+
+
+class Search:
+    """T device-resident root-parallel trees (mamcts_search)."""
+
+    def __init__(self, engine: Engine, env: int, mp: Params, num_trees: int, cp: CrossingParams = None,
+                 sp: SimpleParams = None, root_x=None, action_source: int = SRC_PHILOX,
+                 philox_seed: int = 0, first_tree_id: int = 0, rollouts_per_leaf: int = 1,
+                 max_nodes_per_tree: int = 0):
+        self.engine = engine
+        self.lib = engine.lib
+        cfg = SearchConfig()
+        cfg.env = env
+        cfg.action_source = action_source
+        cfg.num_trees = num_trees
+        cfg.first_tree_id = first_tree_id
+        cfg.rollouts_per_leaf = rollouts_per_leaf
+        cfg.max_nodes_per_tree = max_nodes_per_tree
+        cfg.philox_seed = philox_seed
+        cfg.mcts = mp
+        if cp is not None:
+            cfg.crossing = cp
+        if sp is not None:
+            cfg.simple = sp
+        self.cfg = cfg
+        if env == ENV_CROSSING_I32:
+            self.A = cp.num_other_agents + 1
+            self.num_actions = [cp.num_ego_actions] + [cp.num_other_actions] * (self.A - 1)
+            default_root = [5] * self.A
+        else:
+            self.A = 2
+            self.num_actions = [2, 2]
+            default_root = [4]
+        rx = np.zeros(_abi.MAX_AGENTS, dtype=np.int32)
+        root = default_root if root_x is None else list(root_x)
+        rx[:len(root)] = root
+        self.h = C.c_void_p()
+        rc = self.lib.mamcts_search_create(engine.h, C.byref(cfg), rx.ctypes.data_as(_abi.c_i32_p), None,
+                                           C.byref(self.h))
+        engine._check(rc, "mamcts_search_create")
+
+    def close(self):
+        if self.h:
+            self.lib.mamcts_search_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, root_x):
+        rx = np.zeros(_abi.MAX_AGENTS, dtype=np.int32)
+        rx[:len(root_x)] = root_x
+        self.engine._check(self.lib.mamcts_search_reset(self.h, rx.ctypes.data_as(_abi.c_i32_p), None),
+                           "mamcts_search_reset")
+
+    def run(self, iterations: int):
+        self.engine._check(self.lib.mamcts_search_run(self.h, iterations), "mamcts_search_run")
+
+    def counters(self):
+        v = [C.c_uint64(0) for _ in range(4)]
+        self.engine._check(self.lib.mamcts_search_counters(self.h, *[C.byref(x) for x in v]),
+                           "mamcts_search_counters")
+        return dict(iterations=v[0].value, rollout_steps=v[1].value, expand_steps=v[2].value,
+                    nodes=v[3].value)
+
+    def root_stats(self, tree: int, agent: int):
+        nA = self.num_actions[agent]
+        q = (C.c_double * MAX_ACTIONS)()
+        n = (C.c_uint32 * MAX_ACTIONS)()
+        val = C.c_double(0)
+        vis = C.c_uint32(0)
+        mask = C.c_uint32(0)
+        nn = C.c_uint32(0)
+        self.engine._check(self.lib.mamcts_search_root_stats(self.h, tree, agent, C.byref(val),
+                                                             C.byref(vis), q, n, C.byref(mask),
+                                                             C.byref(nn)), "mamcts_search_root_stats")
+        return dict(value=val.value, visits=vis.value, num_nodes=nn.value,
+                    q=[q[a] if (mask.value >> a) & 1 else 0.0 for a in range(nA)],
+                    n=[int(n[a]) if (mask.value >> a) & 1 else -1 for a in range(nA)])
+
+    def merge_roots(self):
+        return self.engine._merge_call(
+            lambda *o: self.lib.mamcts_search_merge_roots(self.h, *o), self.num_actions[0],
+            "mamcts_search_merge_roots")
+
+    def dump_tree(self, tree: int, capacity: int):
+        max_actions = max(self.num_actions)
+        stride = 4 + self.A * (3 + 2 * max_actions)
+        rec = np.zeros((capacity, stride))
+        cnt = C.c_uint32(0)
+        self.engine._check(self.lib.mamcts_search_dump_tree(self.h, tree, rec.ctypes.data_as(_abi.c_double_p),
+                                                            capacity, C.byref(cnt)),
+                           "mamcts_search_dump_tree")
+        return rec[:min(cnt.value, capacity)]

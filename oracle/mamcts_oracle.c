@@ -31,17 +31,32 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* Stream layout: position pos of stream (hi, lo) is 16-bit lane (pos & 7) of the
- * block philox(ctr = {pos >> 3, lo, hi, 0}, key = seed). Lemire's multiply-shift on 16 bits with
- * rejection makes the draw exactly uniform; the r-th retry (r >= 1) of position pos reads lane
- * ((r-1) & 7) of philox(ctr = {pos, lo, hi, 0x10000 + ((r-1) >> 3)}). */
-uint32_t orc_philox_draw(uint64_t seed, uint32_t stream_hi, uint32_t stream_lo, uint32_t pos,
-                         uint32_t n) {
+/* Stream layout. The draw of agent `agent` at rollout step `step` with A agents:
+ *   A <= 8: S = 8 / A steps share one block; block = step / S, lane = (step % S) * A + agent;
+ *   A  > 8: B = ceil(A / 8) blocks per step; block = step * B + agent / 8, lane = agent % 8.
+ * The 16-bit word is lane `lane` of philox(ctr = {block, lo, hi, 0}, key = seed). Lemire's
+ * multiply-shift on 16 bits with rejection makes the draw exactly uniform; the r-th retry
+ * (r = 0, 1, ...) reads lane (r & 7) of philox(ctr = {step * A + agent, lo, hi, 0x10000 + (r >> 3)}). */
+void orc_draw_position(uint32_t A, uint32_t step, uint32_t agent, uint32_t* block, uint32_t* lane) {
+  if (A <= 8) {
+    const uint32_t S = 8 / A;
+    *block = step / S;
+    *lane = (step % S) * A + agent;
+  } else {
+    const uint32_t B = (A + 7) / 8;
+    *block = step * B + agent / 8;
+    *lane = agent % 8;
+  }
+}
+
+uint32_t orc_philox_draw(uint64_t seed, uint32_t stream_hi, uint32_t stream_lo, uint32_t A,
+                         uint32_t step, uint32_t agent, uint32_t n) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-  uint32_t ctr[4] = {pos >> 3, stream_lo, stream_hi, 0u};
+  uint32_t block, h;
+  orc_draw_position(A, step, agent, &block, &h);
+  uint32_t ctr[4] = {block, stream_lo, stream_hi, 0u};
   uint32_t w[4];
   orc_philox4x32_10(ctr, key, w);
-  uint32_t h = pos & 7u;
   uint32_t x = (w[h >> 1] >> (16u * (h & 1u))) & 0xFFFFu;
   uint32_t m = x * n;
   uint32_t l = m & 0xFFFFu;
@@ -49,7 +64,7 @@ uint32_t orc_philox_draw(uint64_t seed, uint32_t stream_hi, uint32_t stream_lo, 
     uint32_t t = 65536u % n;
     uint32_t r = 0;
     while (l < t) {
-      uint32_t rc[4] = {pos, stream_lo, stream_hi, 0x10000u + (r >> 3)};
+      uint32_t rc[4] = {step * A + agent, stream_lo, stream_hi, 0x10000u + (r >> 3)};
       orc_philox4x32_10(rc, key, w);
       uint32_t hh = r & 7u;
       x = (w[hh >> 1] >> (16u * (hh & 1u))) & 0xFFFFu;
@@ -203,7 +218,7 @@ void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* s
       } else if (kind == MAMCTS_SRC_REFERENCE_CONST) {
         act[a] = (int32_t)const_actions[a];
       } else {
-        act[a] = (int32_t)orc_philox_draw(seed, stream_hi, stream_lo, it * A + a,
+        act[a] = (int32_t)orc_philox_draw(seed, stream_hi, stream_lo, A, it, a,
                                           env->num_actions[a]);
       }
     }

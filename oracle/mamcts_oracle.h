@@ -25,9 +25,11 @@ extern "C" {
  * SC'11; the Random123 reference constants). The PHILOX action source is NOT in the reference
  * (its rollouts are deterministic); the stream layout is specified in DESIGN.md §5. */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* Unbiased draw in [0, n) from 16-bit lane `pos` of stream (stream_hi, stream_lo). */
-uint32_t orc_philox_draw(uint64_t seed, uint32_t stream_hi, uint32_t stream_lo, uint32_t pos,
-                         uint32_t n);
+/* Where the draw of (step, agent) with A agents sits in its stream: block index and 16-bit lane. */
+void orc_draw_position(uint32_t A, uint32_t step, uint32_t agent, uint32_t* block, uint32_t* lane);
+/* Exactly-uniform draw in [0, n) for (step, agent) of stream (stream_hi, stream_lo). */
+uint32_t orc_philox_draw(uint64_t seed, uint32_t stream_hi, uint32_t stream_lo, uint32_t A,
+                         uint32_t step, uint32_t agent, uint32_t n);
 
 /* ---- environments ------------------------------------------------------------------------ */
 

@@ -1,0 +1,168 @@
+"""Generates tests/golden/*.json from the UNMODIFIED reference (oracle/_ref/libmamcts_ref.so, built
+from /root/reference by oracle/Makefile). Run in the container that has the reference checkout:
+
+    python tests/golden/make_golden.py
+
+The vectors pin (a) CrossingState<int>::execute, (b) RandomHeuristic::rollout incl. the recorded
+action / reward sequences used for REPLAY, (c) whole Mcts::search root statistics and a digest of
+every node statistic of the tree, (d) UctStatistic::merge_node_statistics, (e) the libstdc++
+widening orders. Floats are stored as hex so nothing is lost in JSON.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle_api as O  # noqa: E402
+from mamcts_b200 import default_crossing_params, default_params  # noqa: E402
+
+
+def fhex(a):
+    return [float(v).hex() for v in np.asarray(a, dtype=np.float64).ravel()]
+
+
+def tree_digest(tree: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(tree, dtype=np.float64).tobytes()).hexdigest()
+
+
+def dump(name, obj):
+    with open(os.path.join(HERE, name), "w") as f:
+        json.dump(obj, f, separators=(",", ":"))
+    print("wrote", name)
+
+
+def gen_expand_order():
+    table = {}
+    for seed in (1000, 7, 42, 1, 2024):
+        mp = default_params(random_seed=seed)
+        table[str(seed)] = {str(n): O.ref_expand_order(mp, n) for n in (2, 3, 4, 5, 7, 8, 30)}
+    dump("expand_order.json", table)
+
+
+def gen_execute():
+    rng = np.random.default_rng(12345)
+    cases = []
+    for num_others, chain, goal in ((1, 21, 12), (2, 21, 12), (3, 41, 26), (7, 21, 12)):
+        for cost_only in (0, 1):
+            cp = default_crossing_params(num_other_agents=num_others, chain_length=chain,
+                                         ego_goal_pos=goal, cost_only_collision=cost_only)
+            A = num_others + 1
+            n = 64
+            cpt = cp.crossing_point
+            x = rng.integers(-1, cpt + 8, size=(A, n)).astype(np.int32)
+            x[1:] = np.maximum(x[1:], 0)
+            last = rng.integers(-3, 7, size=(A, n)).astype(np.int32)
+            act = np.zeros((A, n), dtype=np.int32)
+            act[0] = rng.integers(0, cp.num_ego_actions, size=n)
+            act[1:] = rng.integers(-3, 7, size=(A - 1, n))
+            nx, nl, fl, r, c0 = O.ref_crossing_execute(cp, x, last, act)
+            cases.append(dict(num_others=num_others, chain_length=chain, ego_goal_pos=goal,
+                              cost_only_collision=cost_only, x=x.tolist(), last=last.tolist(),
+                              action=act.tolist(), next_x=nx.tolist(), next_last=nl.tolist(),
+                              flags=fl.tolist(), reward=fhex(r), cost0=fhex(c0)))
+    dump("crossing_execute.json", cases)
+
+
+def gen_rollouts():
+    rng = np.random.default_rng(777)
+    cases = []
+    for seed in (1000, 7, 42):
+        for num_others in (1, 2, 7):
+            for reward_step in (0.0, -1.5):
+                mp = default_params(random_seed=seed, rh_max_number_of_iterations=50)
+                cp = default_crossing_params(num_other_agents=num_others, reward_step=reward_step)
+                A = num_others + 1
+                n = 24
+                x = rng.integers(0, 12, size=(A, n)).astype(np.int32)
+                x[:, 0] = 5  # the reference's default start state
+                depth = rng.integers(0, 4, size=n).astype(np.uint32)
+                depth[1] = 999   # one step before MAX_SEARCH_DEPTH (1000)
+                depth[2] = 1000  # at the cap: loop never runs
+                flags = np.zeros(n, dtype=np.uint8)
+                flags[3] = 1     # terminal start state
+                r = O.ref_rollout_crossing(mp, cp, x, None, flags, depth, rec_stride=50)
+                cases.append(dict(seed=seed, num_others=num_others, reward_step=reward_step,
+                                  x=x.tolist(), depth=depth.tolist(), flags=flags.tolist(),
+                                  ego_return=fhex(r["ego_return"]), other_return=fhex(r["other_return"]),
+                                  ego_cost=fhex(r["ego_cost"]), step_length=fhex(r["step_length"]),
+                                  steps=r["steps"].tolist(), final_x=r["final_x"].tolist(),
+                                  final_last_action=r["final_last_action"].tolist(),
+                                  final_flags=r["final_flags"].tolist(),
+                                  rec_actions=r["rec_actions"].tolist(),
+                                  rec_rewards=fhex(r["rec_rewards"])))
+    dump("rollout_crossing.json", cases)
+    # SimpleState: rollouts from every length, default cap 1000 would never end (F1): cap at 40.
+    scases = []
+    for seed in (1000, 7):
+        mp = default_params(random_seed=seed, rh_max_number_of_iterations=40)
+        length = np.arange(-1, 11, dtype=np.int32)
+        r = O.ref_rollout_simple(mp, length, None, rec_stride=40)
+        scases.append(dict(seed=seed, length=length.tolist(), ego_return=fhex(r["ego_return"]),
+                           other_return=fhex(r["other_return"]), step_length=fhex(r["step_length"]),
+                           steps=r["steps"].tolist(), final_len=r["final_len"].tolist(),
+                           rec_actions=r["rec_actions"].tolist(), rec_rewards=fhex(r["rec_rewards"])))
+    dump("rollout_simple.json", scases)
+
+
+def gen_search():
+    cases = []
+    # C1: SimpleState(4), 20 iterations (reference test/uct/uct_test.cc:22-40 parameters)
+    for iters, nodes in ((20, 100), (200, 100), (2000, 100000)):
+        mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=nodes)
+        s = O.ref_search_simple(mp, 4, max_actions=2, tree_capacity=iters + 1)
+        cases.append(dict(env="simple", iterations=iters, max_nodes=nodes, seed=1000, state_length=4,
+                          value=fhex(s["value"]), visits=s["visits"].tolist(), q=fhex(s["q"]),
+                          n=s["n"].tolist(), num_nodes=s["num_nodes"], best=s["best_action"],
+                          tree_count=s["tree_count"], tree_sha256=tree_digest(s["tree"])))
+    # C2: CrossingState, 1 other, 10 000 iterations; plus A = 3, 4, 8 and other seeds
+    for seed, num_others, iters, chain, goal in ((1000, 1, 10000, 21, 12), (1000, 2, 3000, 21, 12),
+                                                 (7, 1, 3000, 21, 12), (42, 2, 2000, 21, 12),
+                                                 (1000, 3, 2000, 41, 26), (1000, 7, 1500, 21, 12)):
+        mp = default_params(random_seed=seed, max_number_of_iterations=iters,
+                            max_number_of_nodes=100000000, rh_max_number_of_iterations=50)
+        cp = default_crossing_params(num_other_agents=num_others, chain_length=chain,
+                                     ego_goal_pos=goal)
+        s = O.ref_search_crossing(mp, cp, max_actions=7, tree_capacity=iters + 1)
+        cases.append(dict(env="crossing", iterations=iters, seed=seed, num_others=num_others,
+                          chain_length=chain, ego_goal_pos=goal, value=fhex(s["value"]),
+                          visits=s["visits"].tolist(), q=fhex(s["q"]), n=s["n"].tolist(),
+                          num_nodes=s["num_nodes"], best=s["best_action"],
+                          tree_count=s["tree_count"], tree_sha256=tree_digest(s["tree"])))
+    dump("search.json", cases)
+
+
+def gen_merge():
+    rng = np.random.default_rng(99)
+    cases = []
+    mp = default_params()
+    for n_trees, nA in ((2, 4), (8, 4), (5, 7), (64, 4)):
+        q = rng.normal(size=(n_trees, nA)) * 10
+        cnt = rng.integers(1, 500, size=(n_trees, nA)).astype(np.int64)
+        absent = rng.random(size=(n_trees, nA)) < 0.25
+        absent[0, 0] = False
+        cnt[absent] = -1
+        q[absent] = 0.0
+        visits = np.array([max(1, int(c[c > 0].sum())) for c in cnt], dtype=np.uint32)
+        m = O.ref_merge_uct(mp, q, cnt, visits, nA)
+        cases.append(dict(num_actions=nA, q=fhex(q), cnt=cnt.tolist(), visits=visits.tolist(),
+                          merged_q=fhex(m["q"]), merged_n=m["n"].tolist(), merged_visits=m["visits"],
+                          merged_value=float(m["value"]).hex(), best=m["best"]))
+    dump("merge.json", cases)
+
+
+if __name__ == "__main__":
+    assert O.reference_available(), "needs /root/reference (or a prebuilt oracle/_ref)"
+    gen_expand_order()
+    gen_execute()
+    gen_rollouts()
+    gen_search()
+    gen_merge()

@@ -99,7 +99,8 @@ def oracle() -> C.CDLL:
     if _oracle is None:
         lib = C.CDLL(build_oracle())
         lib.orc_philox_draw.restype = C.c_uint32
-        lib.orc_philox_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        lib.orc_philox_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        C.c_uint32, C.c_uint32]
         lib.orc_reduce_mean.restype = C.c_double
         lib.orc_reduce_mean.argtypes = [C.c_void_p, C.c_uint32]
         lib.orc_tree_create.restype = C.c_void_p
@@ -158,8 +159,8 @@ def philox4x32_10(ctr, key):
     return list(out)
 
 
-def philox_draw(seed, hi, lo, pos, n) -> int:
-    return int(oracle().orc_philox_draw(seed, hi, lo, pos, n))
+def philox_draw(seed, hi, lo, A, step, agent, n) -> int:
+    return int(oracle().orc_philox_draw(seed, hi, lo, A, step, agent, n))
 
 
 def reduce_mean(vals) -> float:

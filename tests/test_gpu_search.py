@@ -1,0 +1,278 @@
+"""GPU parity tests for the backup kernel, the root merge and the device-resident search, through
+the C ABI. REFERENCE_CONST searches must reproduce the reference's tree bit for bit (golden digests
+from the unmodified reference); PHILOX searches must equal the CPU oracle's tree driven by the same
+streams, and the reference's own Mcts/StageNode/UctStatistic when oracle/_ref is on the box."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import oracle_api as O
+from helpers import assert_bit_equal, golden, rel_close, tree_digest, unhex
+from mamcts_b200 import default_crossing_params, default_params, default_simple_params
+from mamcts_b200._abi import ENV_CROSSING_I32, ENV_SIMPLE, SRC_PHILOX, SRC_REFERENCE_CONST
+from mamcts_b200.engine import MamctsError, Search, reference_expand_order
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- backup kernel ------------------------------------------------------------------------------
+
+def _oracle_backup(mp, A, MA, n_nodes, paths):
+    """CPU statement of the same batch of path backups with orc_stat_* (oracle)."""
+    import ctypes as C
+    lib = O.oracle()
+    lib.orc_stat_backprop.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.orc_stat_update_from_heuristic.argtypes = [C.c_void_p, C.c_double]
+    stats = [[O.OrcStat() for _ in range(A)] for _ in range(n_nodes)]
+    for nd in stats:
+        for s in nd:
+            s.num_actions = MA
+    return stats, lib
+
+
+def test_backup_matches_oracle(engine):
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    A, MA = 3, 7
+    mp = default_params(discount_factor=0.9)
+    n_paths, L = 500, 9
+    n_nodes = n_paths * (L + 1)
+    stats = dict(value=np.zeros(n_nodes * A), latest_return=np.zeros(n_nodes * A),
+                 total_visits=np.zeros(n_nodes * A, dtype=np.uint32), q=np.zeros((n_nodes * A, MA)),
+                 n=np.zeros((n_nodes * A, MA), dtype=np.uint32))
+    ostats, lib = _oracle_backup(mp, A, MA, n_nodes, None)
+    # three rounds over the same trees so that running means are exercised beyond the first visit
+    for rnd in range(3):
+        leaf = np.arange(n_paths, dtype=np.uint32) * (L + 1) + L
+        has = (rng.random(n_paths) < 0.8).astype(np.uint8)
+        ego = rng.normal(size=n_paths)
+        oth = rng.normal(size=(A - 1, n_paths))
+        plen = rng.integers(0, L + 1, size=n_paths).astype(np.uint32)
+        off = np.concatenate([[0], np.cumsum(plen)[:-1]]).astype(np.uint32)
+        ne = int(plen.sum())
+        enode = np.zeros(ne, dtype=np.uint32)
+        eact = rng.integers(0, MA, size=(ne, A)).astype(np.uint8)
+        erew = rng.choice([0.0, -1000.0, 100.0, 1.0], size=(ne, A))
+        for p in range(n_paths):
+            for e in range(plen[p]):
+                enode[off[p] + e] = p * (L + 1) + (L - 1 - e)
+        engine.backup_uct(mp, A, leaf, has, ego, oth, off, plen, enode, eact, erew, stats)
+        for p in range(n_paths):
+            for a in range(A):
+                ls = ostats[leaf[p]][a]
+                if has[p]:
+                    lib.orc_stat_update_from_heuristic(C.byref(ls), ego[p] if a == 0 else oth[a - 1, p])
+                G = ls.latest_return
+                for e in range(plen[p]):
+                    s = ostats[enode[off[p] + e]][a]
+                    s.collected_action = int(eact[off[p] + e, a])
+                    s.collected_reward = float(erew[off[p] + e, a])
+                    lib.orc_stat_backprop(C.byref(s), mp.discount_factor, G)
+                    G = s.latest_return
+    exp_v = np.array([ostats[i][a].value for i in range(n_nodes) for a in range(A)])
+    exp_g = np.array([ostats[i][a].latest_return for i in range(n_nodes) for a in range(A)])
+    exp_N = np.array([ostats[i][a].total_visits for i in range(n_nodes) for a in range(A)])
+    exp_q = np.array([[ostats[i][a].q[k] for k in range(MA)] for i in range(n_nodes) for a in range(A)])
+    exp_n = np.array([[ostats[i][a].n[k] for k in range(MA)] for i in range(n_nodes) for a in range(A)])
+    assert_bit_equal(stats["value"], exp_v, "value")
+    assert_bit_equal(stats["latest_return"], exp_g, "latest")
+    assert stats["total_visits"].tolist() == exp_N.tolist()
+    assert_bit_equal(stats["q"], exp_q, "q")
+    assert stats["n"].tolist() == exp_n.tolist()
+
+
+def test_root_merge_matches_golden(engine):
+    for case in golden("merge.json"):
+        nA = case["num_actions"]
+        cnt = np.array(case["cnt"])
+        T = cnt.shape[0]
+        q = unhex(case["q"], cnt.shape)
+        stats = dict(value=np.zeros(T), latest_return=np.zeros(T),
+                     total_visits=np.array(case["visits"], dtype=np.uint32),
+                     q=np.ascontiguousarray(q), n=np.maximum(cnt, 0).astype(np.uint32))
+        m = engine.root_merge(stats, np.arange(T, dtype=np.uint32), nA)
+        mq = unhex(case["merged_q"])
+        present = np.array(case["merged_n"]) >= 0
+        assert rel_close(m["q"][present], mq[present], 1e-12)
+        assert m["n"][present].tolist() == np.array(case["merged_n"])[present].tolist()
+        assert m["visits"] == case["merged_visits"]
+        assert rel_close(m["value"], float.fromhex(case["merged_value"]), 1e-12)
+        assert m["best"] == case["best"]
+
+
+# ---- device-resident search ---------------------------------------------------------------------
+
+def _golden_search(engine, case, num_trees=3):
+    if case["env"] == "simple":
+        mp = default_params(random_seed=case["seed"], max_number_of_iterations=case["iterations"],
+                            max_number_of_nodes=case["max_nodes"])
+        s = Search(engine, ENV_SIMPLE, mp, num_trees, sp=default_simple_params(),
+                   root_x=[case["state_length"]], action_source=SRC_REFERENCE_CONST)
+        nacts, ma = [2, 2], 2
+    else:
+        mp = default_params(random_seed=case["seed"], max_number_of_iterations=case["iterations"],
+                            max_number_of_nodes=100000000, rh_max_number_of_iterations=50)
+        cp = default_crossing_params(num_other_agents=case["num_others"],
+                                     chain_length=case["chain_length"], ego_goal_pos=case["ego_goal_pos"])
+        s = Search(engine, ENV_CROSSING_I32, mp, num_trees, cp=cp, action_source=SRC_REFERENCE_CONST)
+        nacts, ma = [4] + [7] * case["num_others"], 7
+    return s, nacts, ma
+
+
+def test_expand_order_matches_golden():
+    for seed, per_n in golden("expand_order.json").items():
+        for n, order in per_n.items():
+            assert reference_expand_order(int(seed), int(n)) == order
+
+
+def test_reference_const_search_reproduces_reference_tree(engine):
+    """Whole Mcts::search: every statistic of every node equals the reference's, bit for bit."""
+    for case in golden("search.json"):
+        s, nacts, ma = _golden_search(engine, case)
+        # in two launches: the trees must carry on exactly where they stopped
+        first = case["iterations"] // 3
+        s.run(first)
+        s.run(case["iterations"] - first)
+        A = len(nacts)
+        gq = unhex(case["q"], (A, ma))
+        for tree in (0, 2):  # the reference's parallel trees are identical
+            for a in range(A):
+                st = s.root_stats(tree, a)
+                assert st["num_nodes"] == case["num_nodes"]
+                assert st["visits"] == case["visits"][a]
+                assert st["n"] == case["n"][a][:nacts[a]]
+                assert_bit_equal(st["q"], gq[a, :nacts[a]], f"root q agent {a}")
+                assert_bit_equal(st["value"], unhex(case["value"])[a], "root value")
+            assert tree_digest(s.dump_tree(tree, case["tree_count"])) == case["tree_sha256"]
+        c = s.counters()
+        assert c["iterations"] == 3 * case["iterations"]
+        assert c["nodes"] == 3 * case["num_nodes"]
+        m = s.merge_roots()
+        assert m["best"] == case["best"]
+        present = np.array(case["n"][0][:nacts[0]]) >= 0
+        assert rel_close(m["q"][present], gq[0, :nacts[0]][present], 1e-12)
+        assert m["n"][present].tolist() == (3 * np.array(case["n"][0][:nacts[0]])[present]).tolist()
+        s.close()
+
+
+@pytest.mark.parametrize("num_others", [1, 2, 3, 7])
+def test_philox_search_equals_oracle_tree(engine, num_others):
+    iters = 600
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=num_others)
+    T, first = 70, 1000
+    s = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=SRC_PHILOX, philox_seed=4242,
+               first_tree_id=first)
+    s.run(iters)
+    env = O.make_env(cp=cp)
+    total_steps = 0
+    for tree in (0, 1, 33, 69):
+        t = O.OracleTree(env, mp, [5] * (num_others + 1), action_source=SRC_PHILOX, seed=4242,
+                         tree_id=first + tree)
+        t.run(iters)
+        assert s.root_stats(tree, 0)["num_nodes"] == t.num_nodes
+        got = s.dump_tree(tree, t.num_nodes)
+        assert np.array_equal(got, t.dump(7)), f"tree {tree} differs from the oracle"
+        t.close()
+    # trees with different ids are different trees (unlike the reference's identical ones)
+    assert not np.array_equal(s.dump_tree(0, iters + 1), s.dump_tree(1, iters + 1))
+    c = s.counters()
+    assert c["iterations"] == T * iters
+    s.close()
+
+
+def test_philox_search_simple_equals_oracle_tree(engine):
+    iters = 300
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100,
+                        rh_max_number_of_iterations=30)
+    sp = default_simple_params()
+    s = Search(engine, ENV_SIMPLE, mp, 40, sp=sp, root_x=[4], action_source=SRC_PHILOX, philox_seed=1)
+    s.run(iters)
+    for tree in (0, 39):
+        t = O.OracleTree(O.make_env(sp=sp), mp, [4], action_source=SRC_PHILOX, seed=1, tree_id=tree)
+        t.run(iters)
+        assert np.array_equal(s.dump_tree(tree, t.num_nodes), t.dump(2))
+        assert s.root_stats(tree, 0)["num_nodes"] == t.num_nodes == 101  # MAX_NUMBER_OF_NODES + 1
+        t.close()
+    s.close()
+
+
+@pytest.mark.skipif(not O.reference_available(), reason="compiled reference not on this box")
+def test_philox_search_equals_reference_twin(engine):
+    """The reference's own Mcts<>/StageNode/UctStatistic code with the Philox heuristic."""
+    iters = 500
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=2)
+    s = Search(engine, ENV_CROSSING_I32, mp, 8, cp=cp, action_source=SRC_PHILOX, philox_seed=99)
+    s.run(iters)
+    steps = 0
+    for tree in range(8):
+        ref = O.ref_search_philox(ENV_CROSSING_I32, mp, cp, None, root_x=[5, 5, 5], seed=99,
+                                  tree_id=tree, K=1, max_actions=7, tree_capacity=iters + 1)
+        assert np.array_equal(s.dump_tree(tree, iters + 1), ref["tree"])
+        steps += ref["rollout_steps"]
+    assert s.counters()["rollout_steps"] == steps
+    # root-parallel merge == UctStatistic::merge_node_statistics over the 8 reference roots
+    q = np.zeros((8, 7)); cnt = np.full((8, 7), -1, dtype=np.int64); vis = np.zeros(8, dtype=np.uint32)
+    for tree in range(8):
+        st = s.root_stats(tree, 0)
+        q[tree, :4], cnt[tree, :4], vis[tree] = st["q"], st["n"], st["visits"]
+    exp = O.ref_merge_uct(mp, q, cnt, vis, 4)
+    m = s.merge_roots()
+    assert rel_close(m["q"], exp["q"][:4], 1e-6)
+    assert m["n"].tolist() == exp["n"][:4].tolist()
+    assert m["visits"] == exp["visits"] and m["best"] == exp["best"]
+    assert rel_close(m["value"], exp["value"], 1e-6)
+    s.close()
+
+
+def test_search_reset_and_limits(engine):
+    mp = default_params(max_number_of_iterations=100, rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    s = Search(engine, ENV_CROSSING_I32, mp, 33, cp=cp, action_source=SRC_PHILOX, philox_seed=3)
+    s.run(100)
+    a = s.dump_tree(5, 101)
+    with pytest.raises(MamctsError, match="MAX_NUMBER_OF_ITERATIONS"):
+        s.run(1)
+    s.reset([5, 5])
+    assert s.counters()["iterations"] == 0
+    s.run(100)
+    assert np.array_equal(s.dump_tree(5, 101), a)   # idempotent after reset
+    s.reset([11, 9])                                # a different decision state
+    s.run(50)
+    assert s.root_stats(0, 0)["visits"] == 50
+    s.close()
+    with pytest.raises(MamctsError, match="compiled for"):
+        Search(engine, ENV_CROSSING_I32, mp, 1, cp=default_crossing_params(num_other_agents=5))
+
+
+def test_root_policy_statistically_matches_cpu_twin(engine):
+    """Root action-selection frequencies over many independent trees: GPU trees [0, T) against CPU
+    oracle trees [T, 2T) (disjoint Philox streams, same distribution). Stated tolerance: total
+    variation distance of the pooled root visit distribution <= 0.02, best action equal."""
+    iters, T = 400, 256
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    s = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=SRC_PHILOX, philox_seed=1000)
+    s.run(iters)
+    m = s.merge_roots()
+    gpu_freq = m["n"].astype(np.float64) / m["n"].sum()
+    cpu_n = np.zeros(4)
+    cpu_q = np.zeros(4)
+    env = O.make_env(cp=cp)
+    for tree in range(T, 2 * T):
+        t = O.OracleTree(env, mp, [5, 5], action_source=SRC_PHILOX, seed=1000, tree_id=tree)
+        t.run(iters)
+        st = t.root_stat(0)
+        cpu_n += np.maximum(st["n"], 0)
+        cpu_q += st["q"]
+        t.close()
+    cpu_freq = cpu_n / cpu_n.sum()
+    tv = 0.5 * np.abs(gpu_freq - cpu_freq).sum()
+    assert tv <= 0.02, (tv, gpu_freq, cpu_freq)
+    assert int(np.argmax(cpu_q)) == m["best"]
+    s.close()
