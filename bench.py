@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the MA-MCTS rollout-and-backup hot path on B200.
+
+Workload (BASELINE.json configs[1], "C2"): CrossingState<int>, 2 agents (ego 4 actions, other 7),
+UctStatistic for ego and other, 10 000 MCTS iterations per tree, rollout depth cap 50, on T
+root-parallel trees per GPU that live in HBM. One bench "step" = one decision: every tree is
+re-rooted at the start state and searched for 10 000 iterations (select/expand -> rollout -> backup,
+all on the device). Metric: env-steps/s = CrossingState::execute() calls (rollout + expansion) per
+second over all GPUs; MCTS iterations/s is reported beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           # this repository's CUDA engine
+  python bench.py --impl reference [...]                        # the reference's own CPU search
+
+Prints ONE JSON line (rank 0). See DESIGN.md §8 for how every field is derived.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # oracle_api: ONLY for the cpu_baseline / reference legs
+
+METRIC = "crossingstate_env_steps_per_s"
+UNIT = "env-steps/s"
+ITERATIONS = 10000        # C2: 10k iterations per tree
+DEPTH_CAP = 50            # random_heuristic.MAX_NUMBER_OF_ITERATIONS
+NUM_OTHERS = 1            # C2: 2 agents
+
+
+def _params():
+    from mamcts_b200 import default_crossing_params, default_params
+    mp = default_params(max_number_of_iterations=ITERATIONS, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=DEPTH_CAP)
+    cp = default_crossing_params(num_other_agents=NUM_OTHERS)
+    return mp, cp
+
+
+def _config(trees_per_gpu, n_gpus, action_source):
+    return {
+        "workload": "C2: CrossingState<int> 2 agents (ego 4 / other 7 actions), UctStatistic ego+other, "
+                    f"{ITERATIONS} iterations per tree, rollout depth cap {DEPTH_CAP}, "
+                    f"{trees_per_gpu} root-parallel trees per GPU (one decision per step)",
+        "trees_per_gpu": trees_per_gpu, "trees_total": trees_per_gpu * n_gpus,
+        "iterations_per_tree": ITERATIONS, "rollout_depth_cap": DEPTH_CAP, "agents": NUM_OTHERS + 1,
+        "action_source": action_source,
+        "cache": "inputs larger than L2: tree arenas are tens of GB, no flush needed",
+        "parallelism": f"root-parallel x{n_gpus} (trees sharded by global id, one NCCL all-reduce of "
+                       "root statistics per decision)",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        self.index = index
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [names[i] for i in range(4) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own CPU path (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference_search(threads: int, repeats: int):
+    """`threads` independent Mcts<CrossingState<int>,UctStatistic,UctStatistic,RandomHeuristic>::search
+    calls of the C2 configuration on the host cores (oracle/_ref = the unmodified reference)."""
+    import oracle_api as O
+    mp, cp = _params()
+    if O.reference_available():
+        calls, iters, _nodes = O.ref_search_count_steps(mp, cp)   # deterministic: exact step count
+        it_per_s, seconds = O.ref_time_search(mp, cp, threads, repeats)
+        steps_per_s = it_per_s * calls / iters
+        return dict(kind="reference", env_steps_per_s=steps_per_s, iterations_per_s=it_per_s,
+                    seconds=seconds, searches=threads * repeats,
+                    env_steps_per_search=calls)
+    # oracle port (scalar C restatement) when the compiled reference did not travel
+    from mamcts_b200._abi import SRC_REFERENCE_CONST
+    t0 = time.time()
+    steps = 0
+    for _ in range(repeats):
+        t = O.OracleTree(O.make_env(cp=cp), mp, [5] * (NUM_OTHERS + 1), action_source=SRC_REFERENCE_CONST)
+        t.run(ITERATIONS)
+        steps += t.rollout_steps + t.num_nodes - 1
+        t.close()
+    el = time.time() - t0
+    return dict(kind="port", env_steps_per_s=steps / el, iterations_per_s=repeats * ITERATIONS / el,
+                seconds=el, searches=repeats, env_steps_per_search=steps / repeats)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    total_steps = args.warmup + args.steps
+    # each bench step = every host thread runs `rep` whole searches; sized to ~1 s per step
+    rep = 1
+    cpu_reference_search(threads, 1) if args.warmup else None
+    results = [cpu_reference_search(threads, rep) for _ in range(args.steps)]
+    steps_per_s = sum(r["env_steps_per_s"] * r["seconds"] for r in results) / sum(r["seconds"] for r in results)
+    its_per_s = sum(r["iterations_per_s"] * r["seconds"] for r in results) / sum(r["seconds"] for r in results)
+    ms = 1e3 * sum(r["seconds"] for r in results) / len(results)
+    kind = results[0]["kind"]
+    sample = (f"{threads} host threads x {rep} independent single_search of the C2 configuration per step "
+              f"({ITERATIONS} iterations each, deterministic reference rollouts, "
+              f"{results[0]['env_steps_per_search']:.0f} execute() calls per search)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": _config(args.trees, args.gpus, "philox4x32-10 uniform joint actions"),
+        "reference_action_source": "the reference's stock RandomHeuristic (mt19937 first-draw constant "
+                                   "actions, SURVEY.md F1); it has no other rollout policy",
+        "iterations_per_s": its_per_s,
+        "cpu_baseline": {"value": steps_per_s, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": steps_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    del total_steps
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# this repository's engine
+# ---------------------------------------------------------------------------------------------
+
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mamcts_b200._abi import ENV_CROSSING_I32, SRC_PHILOX, lib_path
+    from mamcts_b200.engine import Engine, Search
+
+    if not os.path.exists(lib_path()):
+        import __graft_entry__
+        __graft_entry__.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the mamcts_b200 engine has no CPU fallback")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    engine = Engine(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    engine.set_stream(stream.cuda_stream)
+    if world > 1:
+        # the engine's own NCCL communicator; the unique id travels over torch.distributed
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.tensor(list(engine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        engine.comm_init_rank(bytes(uid.cpu().tolist()), world, rank)
+
+    mp, cp = _params()
+    T = args.trees
+    search = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=SRC_PHILOX,
+                    philox_seed=1000, first_tree_id=rank * T)
+    root = np.full(NUM_OTHERS + 1, 5, dtype=np.int32)
+    root_pinned = torch.from_numpy(root.copy()).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        search.reset(None)          # root state already resident in HBM
+        search.run(ITERATIONS)
+
+    def e2e_step():
+        # the call a user makes: host root state in, merged root statistics / best action out
+        search.reset(root_pinned.numpy())     # host -> device copy of the decision state
+        search.run(ITERATIONS)
+        return search.merge_roots()           # local reduce (+ NCCL all-reduce) + device -> host read
+
+    # ---- value: device-resident, CUDA events on the engine stream --------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = engine.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    ev0.record(stream)
+    for _ in range(args.steps):
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        search.reset(None)
+        ka.record(stream)
+        search.run(ITERATIONS)
+        kb.record(stream)
+        kern_ms.append((ka, kb))
+    ev1.record(stream)
+    barrier()
+    launches = engine.launch_count - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    search_kernel_ms = sum(a.elapsed_time(b) for a, b in kern_ms) / len(kern_ms)
+    c = search.counters()  # counters of the LAST step (reset zeroes them)
+    t_ms = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([c["rollout_steps"] + c["expand_steps"], c["iterations"], c["backup_levels"],
+                        c["rollout_steps"], c["nodes"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t_ms.item())
+    env_steps_per_step, iters_per_step, levels_per_step, rollout_steps, nodes = (float(v) for v in cnt.tolist())
+    value = env_steps_per_step * args.steps / (elapsed_ms * 1e-3)
+    its = iters_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: through the public API with host buffers, wall clock around the whole call -------
+    for _ in range(min(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        merged = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = env_steps_per_step * args.steps / float(t_e2e.item())
+    nA = 4
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (search_kernel), rank 0's launch -------------------
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            with open(peaks_path) as f:
+                peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        A = NUM_OTHERS + 1
+        it_local = c["iterations"]
+        mean_depth = c["backup_levels"] / max(it_local, 1)
+        # algorithmic bytes per iteration: rollout 16A+8C+8, backup 80*A*L,
+        # selection reads (12*nA+12) per agent per level = 60 (ego) + 96 (other)
+        bytes_per_it = (16 * A + 8 + 8) + 80 * A * mean_depth + (60 + 96 * (A - 1)) * (mean_depth + 1)
+        algo_bytes = bytes_per_it * it_local
+        achieved = algo_bytes / (search_kernel_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "search_kernel<CrossingEnv<1>,4,7,PHILOX>",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src, "traffic": None,
+                    "algorithmic_bytes_per_iteration": bytes_per_it, "mean_leaf_depth": mean_depth,
+                    "kernel_ms": search_kernel_ms,
+                    "note": "latency/issue-bound pointer chasing; see DESIGN.md §7 and profiles/"}
+        # ---- cpu baseline: the reference's own search on the host cores, bounded sample -----------
+        threads = os.cpu_count() or 1
+        cb = cpu_reference_search(threads, max(1, args.cpu_repeats))
+        cpu_baseline = {"value": cb["env_steps_per_s"], "unit": UNIT, "cores": threads, "kind": cb["kind"],
+                        "iterations_per_s": cb["iterations_per_s"],
+                        "sample": f"{cb['searches']} whole C2 searches ({ITERATIONS} iterations each) on "
+                                  f"{threads} host threads, {cb['seconds']:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config(T, world, "philox4x32-10 uniform joint actions"),
+            "iterations_per_s": its,
+            "env_steps_per_decision": env_steps_per_step, "rollout_steps_per_decision": rollout_steps,
+            "nodes_per_decision": nodes,
+            "clocks": clock_info,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64,  # the int32[16] root-state vector mamcts_search_reset copies
+                    "d2h_bytes_per_step": 8 * (3 * nA + 3),
+                    "api": "Search.reset(host root) + Search.run + Search.merge_roots -> best action",
+                    "best_action": int(merged["best"])},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    search.close()
+    if world > 1:
+        engine.comm_destroy()
+        dist.barrier()
+        dist.destroy_process_group()
+    engine.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--trees", type=int, default=16384, help="root-parallel trees per GPU")
+    ap.add_argument("--cpu-repeats", type=int, default=24, help="whole searches per host thread for cpu_baseline")
+    ap.add_argument("--iterations", type=int, default=ITERATIONS,
+                    help="iterations per tree (C2 = 10000; smaller values only for profiling runs)")
+    args = ap.parse_args()
+    globals()["ITERATIONS"] = args.iterations
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

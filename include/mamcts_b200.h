@@ -288,14 +288,16 @@ typedef struct mamcts_search mamcts_search;
 int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, const int32_t* root_x,
                          const int32_t* root_last_action, mamcts_search** out);
 int mamcts_search_destroy(mamcts_search* s);
-/* Re-roots every tree (new decision) without reallocating. */
+/* Re-roots every tree (new decision) without reallocating. root_x == NULL keeps the root state
+ * already resident on the device (no host->device copy). */
 int mamcts_search_reset(mamcts_search* s, const int32_t* root_x, const int32_t* root_last_action);
 /* Runs `iterations` more MCTS iterations on every tree (select/expand, rollout, backup),
  * asynchronously on the engine stream. */
 int mamcts_search_run(mamcts_search* s, uint32_t iterations);
-/* Totals since the last reset: iterations done, execute() calls in rollouts, in expansions, nodes. */
+/* Totals since the last reset: iterations done, execute() calls in rollouts, in expansions, nodes,
+ * and statistic levels walked by the backups (sum of leaf depths). Any pointer may be NULL. */
 int mamcts_search_counters(mamcts_search* s, uint64_t* iterations, uint64_t* rollout_steps,
-                           uint64_t* expand_steps, uint64_t* nodes);
+                           uint64_t* expand_steps, uint64_t* nodes, uint64_t* backup_levels);
 /* Root statistics of local tree t, agent position a: HOST outputs, arrays of max_actions. */
 int mamcts_search_root_stats(mamcts_search* s, uint32_t tree, uint32_t agent, double* value,
                              uint32_t* total_visits, double* q, uint32_t* n, uint32_t* expanded_mask,

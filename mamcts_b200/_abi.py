@@ -216,7 +216,7 @@ def load() -> C.CDLL:
         "mamcts_search_destroy": (i32, [vp]),
         "mamcts_search_reset": (i32, [vp, c_i32_p, c_i32_p]),
         "mamcts_search_run": (i32, [vp, u32]),
-        "mamcts_search_counters": (i32, [vp, c_u64_p, c_u64_p, c_u64_p, c_u64_p]),
+        "mamcts_search_counters": (i32, [vp, c_u64_p, c_u64_p, c_u64_p, c_u64_p, c_u64_p]),
         "mamcts_search_root_stats": (
             i32, [vp, u32, u32, c_double_p, c_u32_p, c_double_p, c_u32_p, c_u32_p, c_u32_p]),
         "mamcts_search_merge_roots": (

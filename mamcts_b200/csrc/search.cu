@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
   Node* nodes = static_cast<Node*>(p.nodes) + (size_t)tree * p.max_nodes;
   uint32_t* hash = p.hash + (size_t)tree * (p.hash_mask + 1);
   uint32_t num_nodes = p.tree_nodes[tree];
-  unsigned long long rollout_steps = 0, expand_steps = 0;
+  unsigned long long rollout_steps = 0, expand_steps = 0, backup_levels = 0;
   const uint32_t nodes_before = num_nodes;
   uint8_t const_act[A];
 #pragma unroll
@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
       G[0] = backprop_stat<NE>(&pn->ego, cn->ja[0], r0, p.gamma, G[0]);
 #pragma unroll
       for (int j = 0; j < A - 1; ++j) G[j + 1] = backprop_stat<NA>(&pn->oth[j], cn->ja[j + 1], r1, p.gamma, G[j + 1]);
+      backup_levels += 1;
       child = par;
     }
   }
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
   atomicAdd(p.counters + 1, rollout_steps);
   atomicAdd(p.counters + 2, expand_steps);
   atomicAdd(p.counters + 3, (unsigned long long)(num_nodes - nodes_before));
+  atomicAdd(p.counters + 4, backup_levels);
 }
 
 template <class Env, int NE, int NA>
@@ -396,7 +398,7 @@ struct SearchT final : public mamcts_search {
   int launch_reset() override {
     const uint32_t T = cfg.num_trees;
     MAMCTS_CUDA(e, cudaMemsetAsync(d_hash, 0, sizeof(uint32_t) * (size_t)T * (p.hash_mask + 1), e->stream));
-    MAMCTS_CUDA(e, cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 4, e->stream));
+    MAMCTS_CUDA(e, cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
     search_reset_kernel<Env, NE, NA><<<(T + 255) / 256, 256, 0, e->stream>>>(
         d_nodes, d_tree_nodes, d_tree_iters, T, p.max_nodes, d_root_x, p.env);
     e->launches++;
@@ -582,7 +584,7 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   alloc((void**)&s->d_tree_iters, sizeof(uint32_t) * T);
   alloc((void**)&s->d_tab, sizeof(SearchTables));
   alloc((void**)&s->d_log, sizeof(double) * logs.size());
-  alloc((void**)&s->d_counters, sizeof(unsigned long long) * 4);
+  alloc((void**)&s->d_counters, sizeof(unsigned long long) * 8);
   alloc((void**)&s->d_root_x, sizeof(int32_t) * MAMCTS_MAX_AGENTS);
   if (err != cudaSuccess) {
     free_search(s);
@@ -624,14 +626,16 @@ int mamcts_search_destroy(mamcts_search* s) {
 
 int mamcts_search_reset(mamcts_search* s, const int32_t* root_x, const int32_t* root_last_action) {
   (void)root_last_action;
-  if (!s || !root_x) return fail(s ? s->e : nullptr, MAMCTS_ERR_INVALID, "mamcts_search_reset: null argument");
+  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_reset: null handle");
   mamcts_engine* e = s->e;
   std::lock_guard<std::mutex> lock(e->mu);
   MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  int32_t rx[MAMCTS_MAX_AGENTS] = {0};
-  for (uint32_t i = 0; i < s->state_ints; ++i) rx[i] = root_x[i];
-  MAMCTS_CUDA(e, cudaMemcpyAsync(s->d_root_x, rx, sizeof(rx), cudaMemcpyHostToDevice, e->stream));
-  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (root_x) {  // NULL: re-root at the state already resident on the device (no copy)
+    int32_t rx[MAMCTS_MAX_AGENTS] = {0};
+    for (uint32_t i = 0; i < s->state_ints; ++i) rx[i] = root_x[i];
+    MAMCTS_CUDA(e, cudaMemcpyAsync(s->d_root_x, rx, sizeof(rx), cudaMemcpyHostToDevice, e->stream));
+    MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  }
   return s->launch_reset();
 }
 
@@ -649,18 +653,19 @@ int mamcts_search_run(mamcts_search* s, uint32_t iterations) {
 }
 
 int mamcts_search_counters(mamcts_search* s, uint64_t* iterations, uint64_t* rollout_steps,
-                           uint64_t* expand_steps, uint64_t* nodes) {
+                           uint64_t* expand_steps, uint64_t* nodes, uint64_t* backup_levels) {
   if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_counters: null handle");
   mamcts_engine* e = s->e;
   std::lock_guard<std::mutex> lock(e->mu);
   MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  unsigned long long h[4];
+  unsigned long long h[8];
   MAMCTS_CUDA(e, cudaMemcpyAsync(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
   MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
   if (iterations) *iterations = h[0];
   if (rollout_steps) *rollout_steps = h[1];
   if (expand_steps) *expand_steps = h[2];
   if (nodes) *nodes = h[3] + s->cfg.num_trees;  // + the roots
+  if (backup_levels) *backup_levels = h[4];
   return MAMCTS_OK;
 }
 

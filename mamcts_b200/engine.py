@@ -341,21 +341,24 @@ class Search:
         except Exception:
             pass
 
-    def reset(self, root_x):
-        rx = np.zeros(_abi.MAX_AGENTS, dtype=np.int32)
-        rx[:len(root_x)] = root_x
-        self.engine._check(self.lib.mamcts_search_reset(self.h, rx.ctypes.data_as(_abi.c_i32_p), None),
-                           "mamcts_search_reset")
+    def reset(self, root_x=None):
+        """New decision from root_x (host); None = keep the root already on the device."""
+        ptr = None
+        if root_x is not None:
+            rx = np.zeros(_abi.MAX_AGENTS, dtype=np.int32)
+            rx[:len(root_x)] = root_x
+            ptr = rx.ctypes.data_as(_abi.c_i32_p)
+        self.engine._check(self.lib.mamcts_search_reset(self.h, ptr, None), "mamcts_search_reset")
 
     def run(self, iterations: int):
         self.engine._check(self.lib.mamcts_search_run(self.h, iterations), "mamcts_search_run")
 
     def counters(self):
-        v = [C.c_uint64(0) for _ in range(4)]
+        v = [C.c_uint64(0) for _ in range(5)]
         self.engine._check(self.lib.mamcts_search_counters(self.h, *[C.byref(x) for x in v]),
                            "mamcts_search_counters")
         return dict(iterations=v[0].value, rollout_steps=v[1].value, expand_steps=v[2].value,
-                    nodes=v[3].value)
+                    nodes=v[3].value, backup_levels=v[4].value)
 
     def root_stats(self, tree: int, agent: int):
         nA = self.num_actions[agent]

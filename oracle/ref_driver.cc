@@ -611,6 +611,28 @@ int ref_time_search(const mamcts_params* mp, const mamcts_crossing_params* cp, u
   return 0;
 }
 
+// One untimed Mcts::search with the recording state as S: counts every execute() call (expansion
+// + rollout steps) and the iterations, so timed runs can be converted to env-steps/s exactly (the
+// search is deterministic).
+int ref_search_count_steps(const mamcts_params* mp, const mamcts_crossing_params* cp,
+                           uint64_t* execute_calls, uint32_t* iterations, uint32_t* nodes) {
+  const MctsParameters rp = to_ref_params(*mp);
+  CrossingWorld world(*cp);
+  const uint32_t A = cp->num_other_agents + 1;
+  std::vector<int32_t> x(A, 5), last(A, 2);
+  using RS = RecState<CrossingState<int>>;
+  RS start(world.make(x.data(), last.data(), false));
+  Recorder rec;
+  g_recorder = &rec;
+  Mcts<RS, UctStatistic, UctStatistic, RandomHeuristic> mcts(rp);
+  mcts.search(start);
+  g_recorder = nullptr;
+  *execute_calls = rec.steps.size();
+  *iterations = mcts.numIterations();
+  *nodes = mcts.numNodes();
+  return 0;
+}
+
 // The reference's own root-parallel path: Mcts::parallel_search with USE_MULTI_THREADING
 // (mcts/mcts.h:188-221) - the runnable stand-in for test/parallel_mcts (needs OR-tools).
 int ref_time_parallel_search(const mamcts_params* mp, const mamcts_crossing_params* cp,

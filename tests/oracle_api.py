@@ -487,6 +487,14 @@ def ref_time_search(mp: Params, cp: CrossingParams, threads: int, repeats: int):
     return it.value, sec.value
 
 
+def ref_search_count_steps(mp: Params, cp: CrossingParams):
+    """(execute() calls, iterations, nodes) of one deterministic reference search."""
+    calls, it, nodes = C.c_uint64(0), C.c_uint32(0), C.c_uint32(0)
+    reference().ref_search_count_steps(C.byref(mp), C.byref(cp), C.byref(calls), C.byref(it),
+                                       C.byref(nodes))
+    return calls.value, it.value, nodes.value
+
+
 def ref_time_parallel_search(mp: Params, cp: CrossingParams, num_parallel: int, max_actions=7):
     it, sec = C.c_double(0), C.c_double(0)
     q = np.zeros(max_actions)
