@@ -111,6 +111,49 @@ __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const Search
   }
   const double log2N = __dmul_rn(2.0, __ldg(p.log_table + N));  // 2 * log(total_node_visits_)
   const double range = __dsub_rn(hi, lo);
+
+  // FP32 screen. The FP64 UCB values cost two divisions and a square root per action; the arg-max
+  // almost never needs that precision. Scores are first evaluated in FP32 (every operation IEEE
+  // rounded: error <= 2e-7 * (|score| + 1) per score); when the first maximum beats every action
+  // with different inputs by more than `delta` (>= 5x the worst-case error of two scores), the
+  // exact arg-max is provably the same and is returned. Actions with bit-identical (Q, n) have
+  // identical exact scores, so the strict-> first-max rule picks the same one either way. Anything
+  // else falls through to the exact FP64 evaluation below, so the selected action is ALWAYS the
+  // reference's.
+  {
+    const float rangef = (float)range, Lf = (float)log2N, c2f = (float)p.two_c;
+    float sc[NACT];
+    float best_sc = -1.0f;
+    int bi = -1;
+    bool ok = isfinite(rangef) && rangef != 0.0f;
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) {
+      sc[a] = -2.0f;
+      if ((mask >> a) & 1u) {
+        const float normf = (float)__dsub_rn(q[a], lo) / rangef;
+        sc[a] = fmaf(c2f, sqrtf(Lf / (float)cnt[a]), normf);
+        ok &= (cnt[a] != 0u) & isfinite(sc[a]);
+        if (sc[a] > best_sc) { best_sc = sc[a]; bi = a; }
+      }
+    }
+    // best_sc must be safely above DBL_MIN's role as the initial maximum (:225)
+    ok &= (bi >= 0) & (best_sc > 1e-3f);
+    if (ok) {
+      const float delta = 4e-6f * (best_sc + 1.0f);
+      double qb = 0.0;
+      uint32_t nb = 0;
+#pragma unroll
+      for (int a = 0; a < NACT; ++a) if (a == bi) { qb = q[a]; nb = cnt[a]; }
+#pragma unroll
+      for (int a = 0; a < NACT; ++a) {
+        if (((mask >> a) & 1u) && a != bi && sc[a] >= best_sc - delta)
+          ok &= (q[a] == qb) & (cnt[a] == nb);
+      }
+      if (ok) return (uint32_t)bi;
+    }
+  }
+
+  // exact evaluation, calculate_ucb_and_max_action :223-244
   uint32_t best = 0;
   double max_value = DBL_MIN;  // std::numeric_limits<double>::min(), :225
 #pragma unroll
@@ -131,12 +174,17 @@ __device__ __forceinline__ double backprop_stat(StatRec<NACT>* s, uint32_t act, 
   const double G = __dadd_rn(r, __dmul_rn(gamma, child_G));
   const uint32_t cnt = s->n[act] + 1;
   s->n[act] = cnt;
+  // x + (d / k) with d == +-0 is x + d for any k > 0 (the quotient keeps d's signed zero), so the
+  // division is skipped when the running mean already equals the return - always the case for the
+  // reward-free other agents of CrossingState.
   const double q = s->Q[act];
-  s->Q[act] = __dadd_rn(q, __ddiv_rn(__dsub_rn(G, q), (double)cnt));
+  const double dq = __dsub_rn(G, q);
+  s->Q[act] = (dq == 0.0) ? __dadd_rn(q, dq) : __dadd_rn(q, __ddiv_rn(dq, (double)cnt));
   const uint32_t nv = s->N + 1;
   s->N = nv;
   const double v = s->V;
-  s->V = __dadd_rn(v, __ddiv_rn(__dsub_rn(G, v), (double)nv));
+  const double dv = __dsub_rn(G, v);
+  s->V = (dv == 0.0) ? __dadd_rn(v, dv) : __dadd_rn(v, __ddiv_rn(dv, (double)nv));
   s->G = G;
   return G;
 }
