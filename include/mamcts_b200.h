@@ -298,6 +298,9 @@ int mamcts_search_run(mamcts_search* s, uint32_t iterations);
  * and statistic levels walked by the backups (sum of leaf depths). Any pointer may be NULL. */
 int mamcts_search_counters(mamcts_search* s, uint64_t* iterations, uint64_t* rollout_steps,
                            uint64_t* expand_steps, uint64_t* nodes, uint64_t* backup_levels);
+/* Diagnostic: how many UCB arg-max selections since the last reset needed the exact FP64 evaluation
+ * after the FP32 screen could not prove the winner (selection results are exact either way). */
+int mamcts_search_exact_ucb_evaluations(mamcts_search* s, uint64_t* count);
 /* Root statistics of local tree t, agent position a: HOST outputs, arrays of max_actions. */
 int mamcts_search_root_stats(mamcts_search* s, uint32_t tree, uint32_t agent, double* value,
                              uint32_t* total_visits, double* q, uint32_t* n, uint32_t* expanded_mask,

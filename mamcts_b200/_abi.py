@@ -217,6 +217,7 @@ def load() -> C.CDLL:
         "mamcts_search_reset": (i32, [vp, c_i32_p, c_i32_p]),
         "mamcts_search_run": (i32, [vp, u32]),
         "mamcts_search_counters": (i32, [vp, c_u64_p, c_u64_p, c_u64_p, c_u64_p, c_u64_p]),
+        "mamcts_search_exact_ucb_evaluations": (i32, [vp, c_u64_p]),
         "mamcts_search_root_stats": (
             i32, [vp, u32, u32, c_double_p, c_u32_p, c_double_p, c_u32_p, c_u32_p, c_u32_p]),
         "mamcts_search_merge_roots": (
@@ -240,6 +241,6 @@ EXPORTED_SYMBOLS = [
     "mamcts_backup_uct", "mamcts_root_merge", "mamcts_comm_get_unique_id",
     "mamcts_comm_init_rank", "mamcts_comm_destroy", "mamcts_allreduce_f64",
     "mamcts_search_create", "mamcts_search_destroy", "mamcts_search_reset", "mamcts_search_run",
-    "mamcts_search_counters", "mamcts_search_root_stats", "mamcts_search_merge_roots",
+    "mamcts_search_counters", "mamcts_search_exact_ucb_evaluations", "mamcts_search_root_stats", "mamcts_search_merge_roots",
     "mamcts_search_dump_tree",
 ]

@@ -5,408 +5,24 @@
 // (mcts/stage_node.h:167-271) and UctStatistic (mcts/statistics/uct_statistic.h).
 //
 // HBM layout: per tree a contiguous arena of fixed-size node records (AoS: a lane
-// that touches a node uses every byte of the lines it pulls) and an open-addressing child table
-// (uint32 child index per slot, keyed by hash(parent, joint action), verified against the child's
-// own header). Statistics are FP64 and are updated in the reference's operation order; log(N) comes
-// from a host-computed table and the widening thresholds from host libm, so a REFERENCE_CONST
-// search reproduces the reference's tree bit for bit.
+// that touches a node uses every byte of the lines it pulls). Children are found through a direct
+// per-node table when the joint-action space is small (2 agents) and otherwise through a per-tree
+// open-addressing table (uint32 child index per slot, keyed by hash(parent, joint action), verified
+// against the child's own header). Statistics are FP64 and are updated in the reference's operation
+// order; log(N) comes from a host-computed table and the widening thresholds from host libm, so a
+// REFERENCE_CONST search reproduces the reference's tree bit for bit.
 #include <algorithm>
-#include <cfloat>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 #include <vector>
 
 #include "engine.h"
-#include "env.cuh"
-#include "philox.cuh"
 #include "root_merge.h"
+#include "search_kernel.cuh"
 
-namespace mamcts {
-
-constexpr uint32_t kNoParent = 0xFFFFFFFFu;
-constexpr int kSearchThreads = 128;
-
-template <int NACT>
-struct alignas(8) StatRec {
-  double V;        // value_
-  double G;        // latest_return_
-  uint32_t N;      // total_node_visits_
-  uint32_t nexp;   // ucb_statistics_.size(): the first nexp entries of the widening order
-  double Q[NACT];  // action_value_
-  uint32_t n[NACT + (NACT & 1)];  // action_count_
-};
-
-template <class Env, int NE, int NA>
-struct alignas(8) NodeRec {
-  static constexpr int A = Env::A;
-  uint32_t parent;
-  uint32_t visit_count;              // StageNode::visit_count_
-  uint32_t depth;
-  uint8_t flags;                     // bit0 terminal, bit1 goal, bit2 collided
-  uint8_t ja[(A + 1 + 3) / 4 * 4 - 1];  // joint action leading here (pads the header to 4 bytes)
-  int32_t x[Env::kStateInts + (Env::kStateInts & 1)];
-  double r_in[2];                    // reward collected on the incoming edge: ego / every other
-  StatRec<NE> ego;
-  StatRec<NA> oth[A - 1];
-};
-
-struct SearchTables {
-  // class 0 = ego, class 1 = others
-  uint8_t order[2][MAMCTS_MAX_ACTIONS];        // widening order (mamcts_reference_expand_order)
-  uint32_t exp_mask[2][MAMCTS_MAX_ACTIONS + 1];// bitmask of the first k actions of the order
-  uint32_t pw_min_visits[2][MAMCTS_MAX_ACTIONS];// smallest N with k <= pw_k * pow(N, pw_alpha)
-};
-
-struct SearchParams {
-  void* nodes;
-  uint32_t* hash;
-  uint32_t* tree_nodes;   // [T] nodes in use (num_nodes_ of the tree)
-  uint32_t* tree_iters;   // [T] iterations done
-  const SearchTables* tab;
-  const double* log_table;  // log((double)N), host libm
-  unsigned long long* counters;  // iterations, rollout steps, expand steps, nodes created
-  uint32_t T, max_nodes, hash_mask, iterations, first_tree_id;
-  uint32_t n_ego, n_oth;
-  uint32_t use_bound_est, max_depth, node_budget, rh_cap;
-  uint32_t key0, key1;
-  double gamma, two_c, lb, ub;
-  EnvParams env;
-};
-
-// UctStatistic::choose_next_action, reference uct_statistic.h:61-76 (+ :122-132, :223-244, :256-262).
-template <int NACT>
-__device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const SearchParams& p, int cls,
-                                                  uint32_t nact) {
-  const uint32_t N = s->N;
-  const uint32_t nexp = s->nexp;
-  if (nexp < nact && N >= p.tab->pw_min_visits[cls][nexp]) {  // require_progressive_widening_total
-    const uint32_t a = p.tab->order[cls][nexp];               // :64-68 (deterministic order, F2)
-    s->nexp = nexp + 1;
-    s->Q[a] = 0.0;                                            // ucb_statistics_[a] = UcbPair()
-    s->n[a] = 0;
-    return a;
-  }
-  const uint32_t mask = p.tab->exp_mask[cls][nexp];
-  double q[NACT];
-  uint32_t cnt[NACT];
-#pragma unroll
-  for (int a = 0; a < NACT; ++a) {
-    const bool ex = (mask >> a) & 1u;
-    q[a] = ex ? s->Q[a] : 0.0;
-    cnt[a] = ex ? s->n[a] : 1u;
-  }
-  double lo = p.lb, hi = p.ub;
-  if (p.use_bound_est) {  // calculate_bounds_based_on_stat :122-132
-    double mn = 0.0, mx = 0.0;
-    bool first = true;
-#pragma unroll
-    for (int a = 0; a < NACT; ++a) {
-      if ((mask >> a) & 1u) {
-        if (first) { mn = q[a]; mx = q[a]; first = false; }
-        else { mn = q[a] < mn ? q[a] : mn; mx = q[a] < mx ? mx : q[a]; }
-      }
-    }
-    if (mn == mx) { lo = 0.0; hi = (mx != 0.0) ? mx : 1.0; }
-    else { lo = mn; hi = mx; }
-  }
-  const double log2N = __dmul_rn(2.0, __ldg(p.log_table + N));  // 2 * log(total_node_visits_)
-  const double range = __dsub_rn(hi, lo);
-
-  // FP32 screen. The FP64 UCB values cost two divisions and a square root per action; the arg-max
-  // almost never needs that precision. Scores are first evaluated in FP32 (every operation IEEE
-  // rounded: error <= 2e-7 * (|score| + 1) per score); when the first maximum beats every action
-  // with different inputs by more than `delta` (>= 5x the worst-case error of two scores), the
-  // exact arg-max is provably the same and is returned. Actions with bit-identical (Q, n) have
-  // identical exact scores, so the strict-> first-max rule picks the same one either way. Anything
-  // else falls through to the exact FP64 evaluation below, so the selected action is ALWAYS the
-  // reference's.
-  {
-    const float rangef = (float)range, Lf = (float)log2N, c2f = (float)p.two_c;
-    float sc[NACT];
-    float best_sc = -1.0f;
-    int bi = -1;
-    bool ok = isfinite(rangef) && rangef != 0.0f;
-#pragma unroll
-    for (int a = 0; a < NACT; ++a) {
-      sc[a] = -2.0f;
-      if ((mask >> a) & 1u) {
-        const float normf = (float)__dsub_rn(q[a], lo) / rangef;
-        sc[a] = fmaf(c2f, sqrtf(Lf / (float)cnt[a]), normf);
-        ok &= (cnt[a] != 0u) & isfinite(sc[a]);
-        if (sc[a] > best_sc) { best_sc = sc[a]; bi = a; }
-      }
-    }
-    // best_sc must be safely above DBL_MIN's role as the initial maximum (:225)
-    ok &= (bi >= 0) & (best_sc > 1e-3f);
-    if (ok) {
-      const float delta = 4e-6f * (best_sc + 1.0f);
-      double qb = 0.0;
-      uint32_t nb = 0;
-#pragma unroll
-      for (int a = 0; a < NACT; ++a) if (a == bi) { qb = q[a]; nb = cnt[a]; }
-#pragma unroll
-      for (int a = 0; a < NACT; ++a) {
-        if (((mask >> a) & 1u) && a != bi && sc[a] >= best_sc - delta)
-          ok &= (q[a] == qb) & (cnt[a] == nb);
-      }
-      if (ok) return (uint32_t)bi;
-    }
-  }
-
-  // exact evaluation, calculate_ucb_and_max_action :223-244
-  uint32_t best = 0;
-  double max_value = DBL_MIN;  // std::numeric_limits<double>::min(), :225
-#pragma unroll
-  for (int a = 0; a < NACT; ++a) {
-    if ((mask >> a) & 1u) {
-      const double norm = __ddiv_rn(__dsub_rn(q[a], lo), range);
-      const double v = __dadd_rn(norm, __dmul_rn(p.two_c, __dsqrt_rn(__ddiv_rn(log2N, (double)cnt[a]))));
-      if (v > max_value) { max_value = v; best = a; }
-    }
-  }
-  return best;
-}
-
-// UctStatistic::update_statistics_from_backpropagated, reference uct_statistic.h:134-144.
-template <int NACT>
-__device__ __forceinline__ double backprop_stat(StatRec<NACT>* s, uint32_t act, double r, double gamma,
-                                                double child_G) {
-  const double G = __dadd_rn(r, __dmul_rn(gamma, child_G));
-  const uint32_t cnt = s->n[act] + 1;
-  s->n[act] = cnt;
-  // x + (d / k) with d == +-0 is x + d for any k > 0 (the quotient keeps d's signed zero), so the
-  // division is skipped when the running mean already equals the return - always the case for the
-  // reward-free other agents of CrossingState.
-  const double q = s->Q[act];
-  const double dq = __dsub_rn(G, q);
-  s->Q[act] = (dq == 0.0) ? __dadd_rn(q, dq) : __dadd_rn(q, __ddiv_rn(dq, (double)cnt));
-  const uint32_t nv = s->N + 1;
-  s->N = nv;
-  const double v = s->V;
-  const double dv = __dsub_rn(G, v);
-  s->V = (dv == 0.0) ? __dadd_rn(v, dv) : __dadd_rn(v, __ddiv_rn(dv, (double)nv));
-  s->G = G;
-  return G;
-}
-
-template <int A>
-__device__ __forceinline__ uint32_t hash_ja(uint32_t parent, const uint8_t (&ja)[A]) {
-  uint32_t h = parent * 0x9E3779B1u;
-#pragma unroll
-  for (int a = 0; a < A; ++a) h = (h ^ ja[a]) * 0x01000193u;
-  h ^= h >> 15;
-  h *= 0x2C1B3C6Du;
-  h ^= h >> 12;
-  return h;
-}
-
-// RandomHeuristic::rollout for one lane (reference random_heuristic.h:27-104); same arithmetic as
-// rollout_kernel. Returns the ego return; `other` = the (shared) other-agent return.
-template <class Env, int KIND>
-__device__ __forceinline__ double lane_rollout(const SearchParams& p, typename Env::State st,
-                                               uint32_t depth, uint32_t s_hi, uint32_t s_lo,
-                                               const uint8_t* const_act, double& other,
-                                               uint32_t& steps) {
-  constexpr int A = Env::A;
-  constexpr int S = (KIND == MAMCTS_SRC_PHILOX && A <= 8) ? 8 / A : 1;
-  const double inv_n_ego = 1.0 / (double)Env::num_actions(p.env, 0);
-  double m = p.gamma, ego = 0.0, prob = 1.0;
-  other = 0.0;
-  uint32_t it = 0;
-  bool fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
-  while (!fin) {
-    Philox4 blk[(A + 7) / 8];
-    if (KIND == MAMCTS_SRC_PHILOX) {
-      if (A <= 8) {
-        blk[0] = philox4x32_10(it / S, s_lo, s_hi, 0u, p.key0, p.key1);
-      } else {
-#pragma unroll
-        for (int b = 0; b < (A + 7) / 8; ++b)
-          blk[b] = philox4x32_10(it * ((A + 7) / 8) + b, s_lo, s_hi, 0u, p.key0, p.key1);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      if (!fin) {
-        int32_t act[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-          if (KIND == MAMCTS_SRC_PHILOX) {
-            const uint32_t h = (A <= 8) ? philox_half(blk[0], s * A + a) : philox_half(blk[a / 8], a % 8);
-            act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi,
-                                             p.key0, p.key1);
-          } else {
-            act[a] = (int32_t)const_act[a];
-          }
-        }
-        double r_ego, r_other, c;
-        Env::step(p.env, st, act, r_ego, r_other, c);
-        m = __dmul_rn(p.gamma, m);
-        ego = __dadd_rn(ego, __dmul_rn(m, r_ego));
-        other = __dmul_rn(m, r_other);
-        m = __dmul_rn(m, p.gamma);
-        prob = __dmul_rn(prob, inv_n_ego);
-        it += 1;
-        depth += 1;
-        fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
-      }
-    }
-  }
-  steps = it;
-  return __dmul_rn(ego, prob);
-}
-
-template <class Env, int NE, int NA, int KIND>
-__global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_constant__ SearchParams p) {
-  using Node = NodeRec<Env, NE, NA>;
-  constexpr int A = Env::A;
-  const uint32_t tree = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tree >= p.T) return;
-  Node* nodes = static_cast<Node*>(p.nodes) + (size_t)tree * p.max_nodes;
-  uint32_t* hash = p.hash + (size_t)tree * (p.hash_mask + 1);
-  uint32_t num_nodes = p.tree_nodes[tree];
-  unsigned long long rollout_steps = 0, expand_steps = 0, backup_levels = 0;
-  const uint32_t nodes_before = num_nodes;
-  uint8_t const_act[A];
-#pragma unroll
-  for (int a = 0; a < A; ++a) const_act[a] = p.tab->order[a == 0 ? 0 : 1][0];  // F1: first draw
-
-  for (uint32_t iter = 0; iter < p.iterations; ++iter) {
-    uint32_t node = 0;
-    bool do_rollout = false;
-    typename Env::State st;
-    uint32_t depth = 0;
-    // ---- select & expand: mcts.h:300-305, stage_node.h:167-232 --------------------------------
-    while (true) {
-      Node* nd = nodes + node;
-      nd->visit_count += 1;                                              // :180
-      depth = nd->depth;
-#pragma unroll
-      for (int i = 0; i < A; ++i) { st.x[i] = (i < Env::kStateInts) ? nd->x[i] : 0; st.last[i] = 0; }
-      st.flags = nd->flags;
-      if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) break;  // :183-187
-      uint8_t ja[A];
-      ja[0] = (uint8_t)choose_action<NE>(&nd->ego, p, 0, p.n_ego);       // :190-195
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) ja[j + 1] = (uint8_t)choose_action<NA>(&nd->oth[j], p, 1, p.n_oth);
-      // child lookup, :198
-      uint32_t h = hash_ja<A>(node, ja) & p.hash_mask;
-      uint32_t child = 0;
-      while (true) {
-        const uint32_t c = hash[h];
-        if (c == 0) break;
-        const Node* cn = nodes + c;
-        bool same = cn->parent == node;
-#pragma unroll
-        for (int a = 0; a < A; ++a) same &= cn->ja[a] == ja[a];
-        if (same) { child = c; break; }
-        h = (h + 1) & p.hash_mask;
-      }
-      if (child) { node = child; continue; }                             // :199-206
-      // expand, :207-231
-      int32_t act[A];
-#pragma unroll
-      for (int a = 0; a < A; ++a) act[a] = ja[a];  // index-valued: others move by +index (F5)
-      double r_ego, r_other, c0;
-      Env::step(p.env, st, act, r_ego, r_other, c0);
-      expand_steps += 1;
-      child = num_nodes++;
-      Node* cn = nodes + child;
-      cn->parent = node;
-      cn->visit_count = 0;
-      cn->depth = depth + 1;
-      cn->flags = (uint8_t)((st.flags & ~1u) | (uint32_t)Env::terminal(p.env, st));
-#pragma unroll
-      for (int a = 0; a < A; ++a) cn->ja[a] = ja[a];
-#pragma unroll
-      for (int i = 0; i < Env::kStateInts; ++i) cn->x[i] = st.x[i];
-      cn->r_in[0] = r_ego;
-      cn->r_in[1] = r_other;
-      cn->ego.V = 0.0; cn->ego.G = 0.0; cn->ego.N = 0; cn->ego.nexp = 0;
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) { cn->oth[j].V = 0.0; cn->oth[j].G = 0.0; cn->oth[j].N = 0; cn->oth[j].nexp = 0; }
-      hash[h] = child;
-      node = child;
-      depth += 1;
-      st.flags = cn->flags;
-      do_rollout = true;
-      break;
-    }
-    // ---- heuristic: mcts.h:309-312, random_heuristic.h:106-134, uct_statistic.h:100-110 --------
-    Node* leaf = nodes + node;
-    double G[A];
-    if (do_rollout) {
-      double other = 0.0;
-      uint32_t steps = 0;
-      const double ego = lane_rollout<Env, KIND>(p, st, depth, p.first_tree_id + tree, node, const_act,
-                                                 other, steps);
-      rollout_steps += steps;
-      leaf->ego.V = ego; leaf->ego.G = ego; leaf->ego.N += 1;
-      G[0] = ego;
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) {
-        leaf->oth[j].V = other; leaf->oth[j].G = other; leaf->oth[j].N += 1;
-        G[j + 1] = other;
-      }
-    } else {
-      G[0] = leaf->ego.G;
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) G[j + 1] = leaf->oth[j].G;
-    }
-    // ---- backpropagation: mcts.h:314-329, stage_node.h:259-271 ---------------------------------
-    uint32_t child = node;
-    while (true) {
-      const Node* cn = nodes + child;
-      const uint32_t par = cn->parent;
-      if (par == kNoParent) break;
-      Node* pn = nodes + par;
-      const double r0 = cn->r_in[0], r1 = cn->r_in[1];
-      G[0] = backprop_stat<NE>(&pn->ego, cn->ja[0], r0, p.gamma, G[0]);
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) G[j + 1] = backprop_stat<NA>(&pn->oth[j], cn->ja[j + 1], r1, p.gamma, G[j + 1]);
-      backup_levels += 1;
-      child = par;
-    }
-  }
-  p.tree_nodes[tree] = num_nodes;
-  p.tree_iters[tree] += p.iterations;
-  atomicAdd(p.counters + 0, (unsigned long long)p.iterations);
-  atomicAdd(p.counters + 1, rollout_steps);
-  atomicAdd(p.counters + 2, expand_steps);
-  atomicAdd(p.counters + 3, (unsigned long long)(num_nodes - nodes_before));
-  atomicAdd(p.counters + 4, backup_levels);
-}
-
-template <class Env, int NE, int NA>
-__global__ void search_reset_kernel(void* nodes_v, uint32_t* tree_nodes, uint32_t* tree_iters, uint32_t T,
-                                    uint32_t max_nodes, const int32_t* root_x, EnvParams env) {
-  using Node = NodeRec<Env, NE, NA>;
-  const uint32_t tree = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tree >= T) return;
-  Node* root = static_cast<Node*>(nodes_v) + (size_t)tree * max_nodes;
-  root->parent = kNoParent;
-  root->visit_count = 0;
-  root->depth = 0;
-  typename Env::State st;
-  for (int i = 0; i < Env::A; ++i) { st.x[i] = (i < Env::kStateInts) ? root_x[i] : 0; st.last[i] = 0; }
-  st.flags = 0;
-  root->flags = (uint8_t)Env::terminal(env, st);
-  for (int a = 0; a < Env::A; ++a) root->ja[a] = 0;
-  for (int i = 0; i < Env::kStateInts; ++i) root->x[i] = root_x[i];
-  root->r_in[0] = 0.0;
-  root->r_in[1] = 0.0;
-  root->ego.V = 0.0; root->ego.G = 0.0; root->ego.N = 0; root->ego.nexp = 0;
-  for (int j = 0; j < Env::A - 1; ++j) { root->oth[j].V = 0.0; root->oth[j].G = 0.0; root->oth[j].N = 0; root->oth[j].nexp = 0; }
-  tree_nodes[tree] = 1;
-  tree_iters[tree] = 0;
-}
-
-// ---- host side ---------------------------------------------------------------------------------
-
-}  // namespace mamcts
-
-// Type-erased handle behind the C ABI; one concrete SearchT per compiled (environment, action-count)
-// combination.
+// Type-erased handle behind the C ABI; one concrete SearchT per compiled (environment, action-count,
+// child-index) combination.
 struct mamcts_search {
   mamcts_engine* e = nullptr;
   mamcts_search_config cfg;
@@ -425,6 +41,7 @@ struct mamcts_search {
 
   virtual ~mamcts_search() {}
   virtual size_t node_bytes() const = 0;
+  virtual bool uses_hash() const = 0;
   virtual int launch_reset() = 0;
   virtual int launch_run(uint32_t iterations) = 0;
   // host-side views of a node record copied back from the device
@@ -437,17 +54,19 @@ struct mamcts_search {
 
 namespace mamcts {
 
-template <class Env, int NE, int NA>
+template <class Env, int NE, int NA, int NCHILD, class CIDX>
 struct SearchT final : public mamcts_search {
-  using Node = NodeRec<Env, NE, NA>;
+  using Node = NodeRec<Env, NE, NA, NCHILD, CIDX>;
 
   size_t node_bytes() const override { return sizeof(Node); }
+  bool uses_hash() const override { return NCHILD == 0; }
 
   int launch_reset() override {
     const uint32_t T = cfg.num_trees;
-    MAMCTS_CUDA(e, cudaMemsetAsync(d_hash, 0, sizeof(uint32_t) * (size_t)T * (p.hash_mask + 1), e->stream));
+    if (NCHILD == 0)
+      MAMCTS_CUDA(e, cudaMemsetAsync(d_hash, 0, sizeof(uint32_t) * (size_t)T * (p.hash_mask + 1), e->stream));
     MAMCTS_CUDA(e, cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
-    search_reset_kernel<Env, NE, NA><<<(T + 255) / 256, 256, 0, e->stream>>>(
+    search_reset_kernel<Env, NE, NA, NCHILD, CIDX><<<(T + 255) / 256, 256, 0, e->stream>>>(
         d_nodes, d_tree_nodes, d_tree_iters, T, p.max_nodes, d_root_x, p.env);
     e->launches++;
     MAMCTS_CUDA(e, cudaGetLastError());
@@ -461,9 +80,9 @@ struct SearchT final : public mamcts_search {
     const uint32_t T = cfg.num_trees;
     const int grid = (int)((T + kSearchThreads - 1) / kSearchThreads);
     if (cfg.action_source == MAMCTS_SRC_PHILOX)
-      search_kernel<Env, NE, NA, MAMCTS_SRC_PHILOX><<<grid, kSearchThreads, 0, e->stream>>>(q);
+      search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_PHILOX><<<grid, kSearchThreads, 0, e->stream>>>(q);
     else
-      search_kernel<Env, NE, NA, MAMCTS_SRC_REFERENCE_CONST><<<grid, kSearchThreads, 0, e->stream>>>(q);
+      search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_REFERENCE_CONST><<<grid, kSearchThreads, 0, e->stream>>>(q);
     e->launches++;
     MAMCTS_CUDA(e, cudaGetLastError());
     return MAMCTS_OK;
@@ -509,14 +128,21 @@ struct SearchT final : public mamcts_search {
   }
 };
 
-static mamcts_search* make_search(const mamcts_search_config& cfg, uint32_t n_ego, uint32_t n_oth) {
-  if (cfg.env == MAMCTS_ENV_SIMPLE) return new SearchT<SimpleEnv, 2, 2>();
+template <class Env, int NE, int NA, int NCHILD>
+static mamcts_search* make_search_cidx(uint32_t max_nodes) {
+  if (NCHILD > 0 && max_nodes <= 65535) return new SearchT<Env, NE, NA, NCHILD, uint16_t>();
+  return new SearchT<Env, NE, NA, NCHILD, uint32_t>();
+}
+
+static mamcts_search* make_search(const mamcts_search_config& cfg, uint32_t n_ego, uint32_t n_oth,
+                                  uint32_t max_nodes) {
+  if (cfg.env == MAMCTS_ENV_SIMPLE) return make_search_cidx<SimpleEnv, 2, 2, 4>(max_nodes);
   if (n_ego == 4 && n_oth == 7) {
     switch (cfg.crossing.num_other_agents) {
-      case 1: return new SearchT<CrossingEnv<1>, 4, 7>();
-      case 2: return new SearchT<CrossingEnv<2>, 4, 7>();
-      case 3: return new SearchT<CrossingEnv<3>, 4, 7>();
-      case 7: return new SearchT<CrossingEnv<7>, 4, 7>();
+      case 1: return make_search_cidx<CrossingEnv<1>, 4, 7, 28>(max_nodes);
+      case 2: return make_search_cidx<CrossingEnv<2>, 4, 7, 0>(max_nodes);
+      case 3: return make_search_cidx<CrossingEnv<3>, 4, 7, 0>(max_nodes);
+      case 7: return make_search_cidx<CrossingEnv<7>, 4, 7, 0>(max_nodes);
       default: return nullptr;
     }
   }
@@ -575,7 +201,14 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   } else {
     return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: unknown environment");
   }
-  mamcts_search* s = make_search(*cfg, n_ego, n_oth);
+  const uint32_t max_iter = mp.max_number_of_iterations;
+  uint32_t max_nodes = cfg->max_nodes_per_tree;
+  const uint64_t needed = std::min<uint64_t>((uint64_t)mp.max_number_of_nodes + 1, (uint64_t)max_iter + 1);
+  if (max_nodes == 0) max_nodes = (uint32_t)needed;
+  if (max_nodes < needed)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: max_nodes_per_tree below min(MAX_NUMBER_OF_NODES, iterations) + 1");
+
+  mamcts_search* s = make_search(*cfg, n_ego, n_oth, max_nodes);
   if (!s)
     return fail(e, MAMCTS_ERR_UNSUPPORTED,
                 "mamcts_search_create: compiled for SimpleState and CrossingState<int> with 4 ego / 7 other "
@@ -589,7 +222,6 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   SearchTables& tab = s->tab;
   std::memset(&tab, 0, sizeof(tab));
   const uint32_t nact[2] = {n_ego, n_oth};
-  const uint32_t max_iter = mp.max_number_of_iterations;
   for (int cls = 0; cls < 2; ++cls) {
     uint32_t order[MAMCTS_MAX_ACTIONS];
     int rc = mamcts_reference_expand_order(mp.random_seed, nact[cls], order);
@@ -613,21 +245,14 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   std::vector<double> logs((size_t)max_iter + 2);
   for (size_t N = 0; N < logs.size(); ++N) logs[N] = std::log((double)N);  // log(total_node_visits_)
 
-  uint32_t max_nodes = cfg->max_nodes_per_tree;
-  const uint64_t needed = std::min<uint64_t>((uint64_t)mp.max_number_of_nodes + 1, (uint64_t)max_iter + 1);
-  if (max_nodes == 0) max_nodes = (uint32_t)needed;
-  if (max_nodes < needed) {
-    delete s;
-    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: max_nodes_per_tree below min(MAX_NUMBER_OF_NODES, iterations) + 1");
-  }
   uint32_t hcap = 16;
-  while (hcap < 2 * max_nodes) hcap <<= 1;
+  if (s->uses_hash()) while (hcap < 2 * max_nodes) hcap <<= 1;
 
   const uint32_t T = cfg->num_trees;
   cudaError_t err = cudaSuccess;
   auto alloc = [&](void** ptr, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(ptr, bytes); };
   alloc(&s->d_nodes, s->node_bytes() * (size_t)T * max_nodes);
-  alloc((void**)&s->d_hash, sizeof(uint32_t) * (size_t)T * hcap);
+  alloc((void**)&s->d_hash, s->uses_hash() ? sizeof(uint32_t) * (size_t)T * hcap : 256);
   alloc((void**)&s->d_tree_nodes, sizeof(uint32_t) * T);
   alloc((void**)&s->d_tree_iters, sizeof(uint32_t) * T);
   alloc((void**)&s->d_tab, sizeof(SearchTables));
@@ -714,6 +339,18 @@ int mamcts_search_counters(mamcts_search* s, uint64_t* iterations, uint64_t* rol
   if (expand_steps) *expand_steps = h[2];
   if (nodes) *nodes = h[3] + s->cfg.num_trees;  // + the roots
   if (backup_levels) *backup_levels = h[4];
+  return MAMCTS_OK;
+}
+
+int mamcts_search_exact_ucb_evaluations(mamcts_search* s, uint64_t* count) {
+  if (!s || !count) return fail(s ? s->e : nullptr, MAMCTS_ERR_INVALID, "mamcts_search_exact_ucb_evaluations: null argument");
+  mamcts_engine* e = s->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  unsigned long long h = 0;
+  MAMCTS_CUDA(e, cudaMemcpyAsync(&h, s->d_counters + 5, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  *count = h;
   return MAMCTS_OK;
 }
 

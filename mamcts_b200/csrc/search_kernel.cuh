@@ -1,0 +1,493 @@
+// search_kernel.cuh - device side of the device-resident root-parallel MCTS (see search.cu).
+//
+// One lane owns one tree and runs whole iterations without returning to the host:
+//   select/expand  mcts.h:300-305, stage_node.h:167-232, uct_statistic.h:61-76,122-132,223-262
+//   rollout        random_heuristic.h:27-104 (+ leaf update uct_statistic.h:100-110)
+//   backup         mcts.h:314-329, stage_node.h:259-271, uct_statistic.h:134-144
+//
+// Latency design (the kernel is bound by the dependent memory round trips of one tree, not by
+// bandwidth): every level of the descent costs ONE round trip - all fields of a node record are
+// loaded together into registers, the child index comes from a direct per-node child table when
+// the joint-action space is small (2 agents) or from a hash probe whose target node is prefetched;
+// the descent records its path so that the backup needs no pointer chasing and its statistic lines
+// are prefetched in one batch.
+#pragma once
+#include <cfloat>
+#include <stdint.h>
+
+#include "env.cuh"
+#include "mamcts_b200.h"
+#include "philox.cuh"
+
+namespace mamcts {
+
+constexpr uint32_t kNoParent = 0xFFFFFFFFu;
+constexpr int kSearchThreads = 64;
+constexpr int kPathMax = 32;  // recorded path levels; deeper leaves fall back to parent pointers
+
+template <int NACT>
+struct alignas(8) StatRec {
+  double V;        // value_
+  double G;        // latest_return_
+  uint32_t N;      // total_node_visits_
+  uint32_t nexp;   // ucb_statistics_.size(): the first nexp entries of the widening order
+  double Q[NACT];  // action_value_
+  uint32_t n[NACT + (NACT & 1)];  // action_count_
+};
+
+// NCHILD > 0: direct child table indexed by the joint-action code (ego * NA + other), CIDX-typed
+// node indices (0 = absent). NCHILD == 0: children are found through the per-tree hash table.
+template <class Env, int NE, int NA, int NCHILD, class CIDX>
+struct alignas(32) NodeRec {
+  static constexpr int A = Env::A;
+  uint32_t parent;
+  uint32_t visit_count;              // StageNode::visit_count_
+  uint32_t depth;
+  uint8_t flags;                     // bit0 terminal, bit1 goal, bit2 collided
+  uint8_t ja[(A + 1 + 3) / 4 * 4 - 1];  // joint action leading here (pads the header to 4 bytes)
+  int32_t x[Env::kStateInts + (Env::kStateInts & 1)];
+  double r_in[2];                    // reward collected on the incoming edge: ego / every other
+  StatRec<NE> ego;
+  StatRec<NA> oth[A - 1];
+  CIDX child[NCHILD > 0 ? NCHILD : 1];
+};
+
+struct SearchTables {
+  // class 0 = ego, class 1 = others
+  uint8_t order[2][MAMCTS_MAX_ACTIONS];         // widening order (mamcts_reference_expand_order)
+  uint32_t exp_mask[2][MAMCTS_MAX_ACTIONS + 1]; // bitmask of the first k actions of the order
+  uint32_t pw_min_visits[2][MAMCTS_MAX_ACTIONS];// smallest N with k <= pw_k * pow(N, pw_alpha)
+};
+
+struct SearchParams {
+  void* nodes;
+  uint32_t* hash;
+  uint32_t* tree_nodes;   // [T] nodes in use (num_nodes_ of the tree)
+  uint32_t* tree_iters;   // [T] iterations done
+  const SearchTables* tab;
+  const double* log_table;  // log((double)N), host libm
+  unsigned long long* counters;  // iterations, rollout steps, expand steps, nodes, backup levels, exact UCB
+  uint32_t T, max_nodes, hash_mask, iterations, first_tree_id;
+  uint32_t n_ego, n_oth;
+  uint32_t use_bound_est, max_depth, node_budget, rh_cap;
+  uint32_t key0, key1;
+  double gamma, two_c, lb, ub;
+  EnvParams env;
+};
+
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+
+// Register image of the part of a statistic the selection reads. All loads are unconditional and
+// independent of each other, so one node costs one memory round trip.
+template <int NACT>
+struct StatRegs {
+  uint32_t N, nexp;
+  double Q[NACT];
+  uint32_t n[NACT];
+};
+
+template <int NACT>
+__device__ __forceinline__ StatRegs<NACT> load_stat(const StatRec<NACT>* s) {
+  StatRegs<NACT> r;
+  r.N = s->N;
+  r.nexp = s->nexp;
+#pragma unroll
+  for (int a = 0; a < NACT; ++a) { r.Q[a] = s->Q[a]; r.n[a] = s->n[a]; }
+  return r;
+}
+
+// UctStatistic::choose_next_action, reference uct_statistic.h:61-76 (+ :122-132, :223-244, :256-262).
+template <int NACT>
+__device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRegs<NACT>& r,
+                                                  const SearchParams& p, int cls, uint32_t nact,
+                                                  unsigned long long& exact_evals) {
+  const uint32_t N = r.N;
+  const uint32_t nexp = r.nexp;
+  if (nexp < nact && N >= p.tab->pw_min_visits[cls][nexp]) {  // require_progressive_widening_total
+    const uint32_t a = p.tab->order[cls][nexp];               // :64-68 (deterministic order, F2)
+    s->nexp = nexp + 1;
+    s->Q[a] = 0.0;                                            // ucb_statistics_[a] = UcbPair()
+    s->n[a] = 0;
+    return a;
+  }
+  const uint32_t mask = p.tab->exp_mask[cls][nexp];
+  double q[NACT];
+  uint32_t cnt[NACT];
+#pragma unroll
+  for (int a = 0; a < NACT; ++a) {
+    const bool ex = (mask >> a) & 1u;
+    q[a] = ex ? r.Q[a] : 0.0;
+    cnt[a] = ex ? r.n[a] : 1u;
+  }
+  double lo = p.lb, hi = p.ub;
+  if (p.use_bound_est) {  // calculate_bounds_based_on_stat :122-132
+    double mn = 0.0, mx = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) {
+      if ((mask >> a) & 1u) {
+        if (first) { mn = q[a]; mx = q[a]; first = false; }
+        else { mn = q[a] < mn ? q[a] : mn; mx = q[a] < mx ? mx : q[a]; }
+      }
+    }
+    if (mn == mx) { lo = 0.0; hi = (mx != 0.0) ? mx : 1.0; }
+    else { lo = mn; hi = mx; }
+  }
+  const double log2N = __dmul_rn(2.0, __ldg(p.log_table + N));  // 2 * log(total_node_visits_)
+  const double range = __dsub_rn(hi, lo);
+
+  // FP32 screen. The FP64 UCB values cost two divisions and a square root per action; the arg-max
+  // almost never needs that precision. Scores are first evaluated in FP32 (every operation IEEE
+  // rounded: error <= 2e-7 * (|score| + 1) per score); when the first maximum beats every action
+  // with different inputs by more than `delta` (>= 5x the worst-case error of two scores), the
+  // exact arg-max is provably the same and is returned. Actions with bit-identical (Q, n) have
+  // identical exact scores, so the strict-> first-max rule picks the same one either way. Anything
+  // else falls through to the exact FP64 evaluation below, so the selected action is ALWAYS the
+  // reference's.
+  {
+    const float rangef = (float)range, Lf = (float)log2N, c2f = (float)p.two_c;
+    float sc[NACT];
+    float best_sc = -1.0f;
+    int bi = -1;
+    bool ok = isfinite(rangef) && rangef != 0.0f;
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) {
+      sc[a] = -2.0f;
+      if ((mask >> a) & 1u) {
+        const float normf = (float)__dsub_rn(q[a], lo) / rangef;
+        sc[a] = fmaf(c2f, sqrtf(Lf / (float)cnt[a]), normf);
+        ok &= (cnt[a] != 0u) & isfinite(sc[a]);
+        if (sc[a] > best_sc) { best_sc = sc[a]; bi = a; }
+      }
+    }
+    // best_sc must be safely above DBL_MIN's role as the initial maximum (:225)
+    ok &= (bi >= 0) & (best_sc > 1e-3f);
+    if (ok) {
+      const float delta = 4e-6f * (best_sc + 1.0f);
+      double qb = 0.0;
+      uint32_t nb = 0;
+#pragma unroll
+      for (int a = 0; a < NACT; ++a) if (a == bi) { qb = q[a]; nb = cnt[a]; }
+#pragma unroll
+      for (int a = 0; a < NACT; ++a) {
+        if (((mask >> a) & 1u) && a != bi && sc[a] >= best_sc - delta)
+          ok &= (q[a] == qb) & (cnt[a] == nb);
+      }
+      if (ok) return (uint32_t)bi;
+    }
+  }
+
+  // exact evaluation, calculate_ucb_and_max_action :223-244
+  exact_evals += 1;
+  uint32_t best = 0;
+  double max_value = DBL_MIN;  // std::numeric_limits<double>::min(), :225
+#pragma unroll
+  for (int a = 0; a < NACT; ++a) {
+    if ((mask >> a) & 1u) {
+      const double norm = __ddiv_rn(__dsub_rn(q[a], lo), range);
+      const double v = __dadd_rn(norm, __dmul_rn(p.two_c, __dsqrt_rn(__ddiv_rn(log2N, (double)cnt[a]))));
+      if (v > max_value) { max_value = v; best = a; }
+    }
+  }
+  return best;
+}
+
+// UctStatistic::update_statistics_from_backpropagated, reference uct_statistic.h:134-144.
+template <int NACT>
+__device__ __forceinline__ double backprop_stat(StatRec<NACT>* s, uint32_t act, double r, double gamma,
+                                                double child_G) {
+  const double G = __dadd_rn(r, __dmul_rn(gamma, child_G));
+  const uint32_t cnt = s->n[act] + 1;
+  s->n[act] = cnt;
+  // x + (d / k) with d == +-0 is x + d for any k > 0 (the quotient keeps d's signed zero), so the
+  // division is skipped when the running mean already equals the return - always the case for the
+  // reward-free other agents of CrossingState.
+  const double q = s->Q[act];
+  const double dq = __dsub_rn(G, q);
+  s->Q[act] = (dq == 0.0) ? __dadd_rn(q, dq) : __dadd_rn(q, __ddiv_rn(dq, (double)cnt));
+  const uint32_t nv = s->N + 1;
+  s->N = nv;
+  const double v = s->V;
+  const double dv = __dsub_rn(G, v);
+  s->V = (dv == 0.0) ? __dadd_rn(v, dv) : __dadd_rn(v, __ddiv_rn(dv, (double)nv));
+  s->G = G;
+  return G;
+}
+
+template <int A>
+__device__ __forceinline__ uint32_t hash_ja(uint32_t parent, const uint8_t (&ja)[A]) {
+  uint32_t h = parent * 0x9E3779B1u;
+#pragma unroll
+  for (int a = 0; a < A; ++a) h = (h ^ ja[a]) * 0x01000193u;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return h;
+}
+
+// RandomHeuristic::rollout for one lane (reference random_heuristic.h:27-104); same arithmetic as
+// rollout_kernel. Returns the ego return; `other` = the (shared) other-agent return.
+template <class Env, int KIND>
+__device__ __forceinline__ double lane_rollout(const SearchParams& p, typename Env::State st,
+                                               uint32_t depth, uint32_t s_hi, uint32_t s_lo,
+                                               const uint8_t* const_act, double& other,
+                                               uint32_t& steps) {
+  constexpr int A = Env::A;
+  constexpr int S = (KIND == MAMCTS_SRC_PHILOX && A <= 8) ? 8 / A : 1;
+  const double inv_n_ego = 1.0 / (double)Env::num_actions(p.env, 0);
+  double m = p.gamma, ego = 0.0, prob = 1.0;
+  other = 0.0;
+  uint32_t it = 0;
+  bool fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
+  while (!fin) {
+    Philox4 blk[(A + 7) / 8];
+    if (KIND == MAMCTS_SRC_PHILOX) {
+      if (A <= 8) {
+        blk[0] = philox4x32_10(it / S, s_lo, s_hi, 0u, p.key0, p.key1);
+      } else {
+#pragma unroll
+        for (int b = 0; b < (A + 7) / 8; ++b)
+          blk[b] = philox4x32_10(it * ((A + 7) / 8) + b, s_lo, s_hi, 0u, p.key0, p.key1);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      if (!fin) {
+        int32_t act[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          if (KIND == MAMCTS_SRC_PHILOX) {
+            const uint32_t h = (A <= 8) ? philox_half(blk[0], s * A + a) : philox_half(blk[a / 8], a % 8);
+            act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi,
+                                             p.key0, p.key1);
+          } else {
+            act[a] = (int32_t)const_act[a];
+          }
+        }
+        double r_ego, r_other, c;
+        Env::step(p.env, st, act, r_ego, r_other, c);
+        m = __dmul_rn(p.gamma, m);
+        ego = __dadd_rn(ego, __dmul_rn(m, r_ego));
+        other = __dmul_rn(m, r_other);
+        m = __dmul_rn(m, p.gamma);
+        prob = __dmul_rn(prob, inv_n_ego);
+        it += 1;
+        depth += 1;
+        fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
+      }
+    }
+  }
+  steps = it;
+  return __dmul_rn(ego, prob);
+}
+
+template <class Env, int NE, int NA, int NCHILD, class CIDX, int KIND>
+__global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_constant__ SearchParams p) {
+  using Node = NodeRec<Env, NE, NA, NCHILD, CIDX>;
+  constexpr int A = Env::A;
+  constexpr bool kDirect = NCHILD > 0;
+  const uint32_t tree = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tree >= p.T) return;
+  Node* nodes = static_cast<Node*>(p.nodes) + (size_t)tree * p.max_nodes;
+  uint32_t* hash = kDirect ? nullptr : p.hash + (size_t)tree * (p.hash_mask + 1);
+  uint32_t num_nodes = p.tree_nodes[tree];
+  unsigned long long rollout_steps = 0, expand_steps = 0, backup_levels = 0, exact_evals = 0;
+  const uint32_t nodes_before = num_nodes;
+  uint8_t const_act[A];
+#pragma unroll
+  for (int a = 0; a < A; ++a) const_act[a] = p.tab->order[a == 0 ? 0 : 1][0];  // F1: first draw
+
+  // the path of the current iteration (collect(), node_statistic.h:115-121): per edge the parent
+  // node, the joint action taken and the rewards collected on it
+  uint32_t path_node[kPathMax];
+  uint8_t path_ja[kPathMax][A];
+  double path_r0[kPathMax], path_r1[kPathMax];
+
+  for (uint32_t iter = 0; iter < p.iterations; ++iter) {
+    uint32_t node = 0;
+    uint32_t depth = 0;
+    bool do_rollout = false;
+    typename Env::State st;
+    // ---- select & expand: mcts.h:300-305, stage_node.h:167-232 --------------------------------
+    while (true) {
+      Node* nd = nodes + node;
+      // one round trip: everything the level needs is requested before anything is used
+      const uint32_t vc = nd->visit_count;
+      const uint32_t flags = nd->flags;
+      const StatRegs<NE> ego = load_stat<NE>(&nd->ego);
+      StatRegs<NA> oth[A - 1];
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) oth[j] = load_stat<NA>(&nd->oth[j]);
+      if (kDirect) prefetch_l1(&nd->child[0]);
+      double r_in0 = 0.0, r_in1 = 0.0;
+      if (depth > 0) { r_in0 = nd->r_in[0]; r_in1 = nd->r_in[1]; }
+      nd->visit_count = vc + 1;                                          // :180
+      if (depth > 0 && depth <= kPathMax) { path_r0[depth - 1] = r_in0; path_r1[depth - 1] = r_in1; }
+      st.flags = flags;
+      if (Env::kStateInts == 1) st.x[0] = nd->x[0];  // SimpleState: terminal() reads the state
+      if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) break;  // :183-187
+      uint8_t ja[A];
+      ja[0] = (uint8_t)choose_action<NE>(&nd->ego, ego, p, 0, p.n_ego, exact_evals);  // :190-195
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j)
+        ja[j + 1] = (uint8_t)choose_action<NA>(&nd->oth[j], oth[j], p, 1, p.n_oth, exact_evals);
+      if (depth < kPathMax) {
+        path_node[depth] = node;
+#pragma unroll
+        for (int a = 0; a < A; ++a) path_ja[depth][a] = ja[a];
+      }
+      // child lookup, :198
+      uint32_t child = 0;
+      uint32_t slot = 0;
+      if (kDirect) {
+        slot = (uint32_t)ja[0] * NA + (A > 1 ? (uint32_t)ja[A > 1 ? 1 : 0] : 0u);
+        child = nd->child[slot];
+      } else {
+        slot = hash_ja<A>(node, ja) & p.hash_mask;
+        while (true) {
+          const uint32_t c = hash[slot];
+          if (c == 0) break;
+          const Node* cn = nodes + c;
+          // the candidate is almost always the child: start pulling its record now
+          prefetch_l1(&cn->ego);
+          prefetch_l1(&cn->oth[A - 2]);
+          bool same = cn->parent == node;
+#pragma unroll
+          for (int a = 0; a < A; ++a) same &= cn->ja[a] == ja[a];
+          if (same) { child = c; break; }
+          slot = (slot + 1) & p.hash_mask;
+        }
+      }
+      if (child) { node = child; depth += 1; continue; }                 // :199-206
+      // expand, :207-231
+#pragma unroll
+      for (int i = 0; i < A; ++i) { st.x[i] = (i < Env::kStateInts) ? nd->x[i] : 0; st.last[i] = 0; }
+      int32_t act[A];
+#pragma unroll
+      for (int a = 0; a < A; ++a) act[a] = ja[a];  // index-valued: others move by +index (F5)
+      double r_ego, r_other, c0;
+      Env::step(p.env, st, act, r_ego, r_other, c0);
+      expand_steps += 1;
+      child = num_nodes++;
+      Node* cn = nodes + child;
+      cn->parent = node;
+      cn->visit_count = 0;
+      cn->depth = depth + 1;
+      st.flags = (st.flags & ~1u) | (uint32_t)Env::terminal(p.env, st);
+      cn->flags = (uint8_t)st.flags;
+#pragma unroll
+      for (int a = 0; a < A; ++a) cn->ja[a] = ja[a];
+#pragma unroll
+      for (int i = 0; i < Env::kStateInts; ++i) cn->x[i] = st.x[i];
+      cn->r_in[0] = r_ego;
+      cn->r_in[1] = r_other;
+      cn->ego.V = 0.0; cn->ego.G = 0.0; cn->ego.N = 0; cn->ego.nexp = 0;
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) { cn->oth[j].V = 0.0; cn->oth[j].G = 0.0; cn->oth[j].N = 0; cn->oth[j].nexp = 0; }
+      if (kDirect) {
+#pragma unroll
+        for (int k = 0; k < (NCHILD > 0 ? NCHILD : 1); ++k) cn->child[k] = 0;
+        nd->child[slot] = (CIDX)child;
+      } else {
+        hash[slot] = child;
+      }
+      if (depth < kPathMax) { path_r0[depth] = r_ego; path_r1[depth] = r_other; }
+      node = child;
+      depth += 1;
+      do_rollout = true;
+      break;
+    }
+    // ---- heuristic: mcts.h:309-312, random_heuristic.h:106-134, uct_statistic.h:100-110 --------
+    Node* leaf = nodes + node;
+    // the backup will touch every statistic on the path: start pulling those lines now so that the
+    // whole backup costs one round trip (they are usually still in L1/L2 from the descent)
+    {
+      const uint32_t lv = depth < (uint32_t)kPathMax ? depth : (uint32_t)kPathMax;
+      for (uint32_t e = 0; e < lv; ++e) {
+        const Node* pn = nodes + path_node[e];
+        prefetch_l1(&pn->ego);
+        prefetch_l1(&pn->oth[A - 2]);
+      }
+    }
+    double G[A];
+    if (do_rollout) {
+      double other = 0.0;
+      uint32_t steps = 0;
+      const double ego = lane_rollout<Env, KIND>(p, st, depth, p.first_tree_id + tree, node, const_act,
+                                                 other, steps);
+      rollout_steps += steps;
+      leaf->ego.V = ego; leaf->ego.G = ego; leaf->ego.N = 1;   // fresh node: 0 + 1
+      G[0] = ego;
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) {
+        leaf->oth[j].V = other; leaf->oth[j].G = other; leaf->oth[j].N = 1;
+        G[j + 1] = other;
+      }
+    } else {
+      G[0] = leaf->ego.G;
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) G[j + 1] = leaf->oth[j].G;
+    }
+    // ---- backpropagation: mcts.h:314-329, stage_node.h:259-271 ---------------------------------
+    uint32_t level = depth;  // number of edges between the root and the leaf
+    uint32_t child = node;
+    while (level > (uint32_t)kPathMax) {  // deeper than the recorded path: follow parent pointers
+      const Node* cn = nodes + child;
+      const uint32_t par = cn->parent;
+      Node* pn = nodes + par;
+      const double r0 = cn->r_in[0], r1 = cn->r_in[1];
+      G[0] = backprop_stat<NE>(&pn->ego, cn->ja[0], r0, p.gamma, G[0]);
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) G[j + 1] = backprop_stat<NA>(&pn->oth[j], cn->ja[j + 1], r1, p.gamma, G[j + 1]);
+      child = par;
+      level -= 1;
+    }
+    backup_levels += depth;
+    while (level > 0) {
+      level -= 1;
+      Node* pn = nodes + path_node[level];
+      const double r0 = path_r0[level], r1 = path_r1[level];
+      G[0] = backprop_stat<NE>(&pn->ego, path_ja[level][0], r0, p.gamma, G[0]);
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j)
+        G[j + 1] = backprop_stat<NA>(&pn->oth[j], path_ja[level][j + 1], r1, p.gamma, G[j + 1]);
+    }
+  }
+  p.tree_nodes[tree] = num_nodes;
+  p.tree_iters[tree] += p.iterations;
+  atomicAdd(p.counters + 0, (unsigned long long)p.iterations);
+  atomicAdd(p.counters + 1, rollout_steps);
+  atomicAdd(p.counters + 2, expand_steps);
+  atomicAdd(p.counters + 3, (unsigned long long)(num_nodes - nodes_before));
+  atomicAdd(p.counters + 4, backup_levels);
+  atomicAdd(p.counters + 5, exact_evals);
+}
+
+template <class Env, int NE, int NA, int NCHILD, class CIDX>
+__global__ void search_reset_kernel(void* nodes_v, uint32_t* tree_nodes, uint32_t* tree_iters, uint32_t T,
+                                    uint32_t max_nodes, const int32_t* root_x, EnvParams env) {
+  using Node = NodeRec<Env, NE, NA, NCHILD, CIDX>;
+  const uint32_t tree = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tree >= T) return;
+  Node* root = static_cast<Node*>(nodes_v) + (size_t)tree * max_nodes;
+  root->parent = kNoParent;
+  root->visit_count = 0;
+  root->depth = 0;
+  typename Env::State st;
+  for (int i = 0; i < Env::A; ++i) { st.x[i] = (i < Env::kStateInts) ? root_x[i] : 0; st.last[i] = 0; }
+  st.flags = 0;
+  root->flags = (uint8_t)Env::terminal(env, st);
+  for (int a = 0; a < Env::A; ++a) root->ja[a] = 0;
+  for (int i = 0; i < Env::kStateInts; ++i) root->x[i] = root_x[i];
+  root->r_in[0] = 0.0;
+  root->r_in[1] = 0.0;
+  root->ego.V = 0.0; root->ego.G = 0.0; root->ego.N = 0; root->ego.nexp = 0;
+  for (int j = 0; j < Env::A - 1; ++j) { root->oth[j].V = 0.0; root->oth[j].G = 0.0; root->oth[j].N = 0; root->oth[j].nexp = 0; }
+  for (int k = 0; k < (NCHILD > 0 ? NCHILD : 1); ++k) root->child[k] = 0;
+  tree_nodes[tree] = 1;
+  tree_iters[tree] = 0;
+}
+
+}  // namespace mamcts

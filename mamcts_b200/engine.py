@@ -360,6 +360,12 @@ class Search:
         return dict(iterations=v[0].value, rollout_steps=v[1].value, expand_steps=v[2].value,
                     nodes=v[3].value, backup_levels=v[4].value)
 
+    def exact_ucb_evaluations(self) -> int:
+        v = C.c_uint64(0)
+        self.engine._check(self.lib.mamcts_search_exact_ucb_evaluations(self.h, C.byref(v)),
+                           "mamcts_search_exact_ucb_evaluations")
+        return v.value
+
     def root_stats(self, tree: int, agent: int):
         nA = self.num_actions[agent]
         q = (C.c_double * MAX_ACTIONS)()
