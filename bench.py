@@ -338,7 +338,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--trees", type=int, default=16384, help="root-parallel trees per GPU")
+    ap.add_argument("--trees", type=int, default=32768,
+                    help="root-parallel trees per GPU (32768 trees x 10001 nodes x 288 B = 94 GB of HBM)")
     ap.add_argument("--cpu-repeats", type=int, default=24, help="whole searches per host thread for cpu_baseline")
     ap.add_argument("--iterations", type=int, default=ITERATIONS,
                     help="iterations per tree (C2 = 10000; smaller values only for profiling runs)")

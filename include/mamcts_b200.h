@@ -115,9 +115,11 @@ typedef struct mamcts_action_source {
   /* REFERENCE_CONST: the one joint action every rollout step applies (F1), as action indices. */
   uint32_t const_actions[MAMCTS_MAX_AGENTS];
   /* PHILOX: key = philox_seed; the stream of rollout k of leaf i is
-   * (stream_hi[i] if given else stream_hi_base, stream_lo_base + i*K + k). */
+   * (stream_hi[i] if given else stream_hi_base,
+   *  stream_lo[i] + k if given else stream_lo_base + i*K + k), modulo 2^32. */
   uint64_t philox_seed;
   const uint32_t* stream_hi;        /* optional per-leaf, may be NULL */
+  const uint32_t* stream_lo;        /* optional per-leaf, may be NULL */
   uint32_t stream_hi_base;
   uint32_t stream_lo_base;
 } mamcts_action_source;

@@ -99,6 +99,7 @@ class ActionSource(C.Structure):
         ("const_actions", C.c_uint32 * MAX_AGENTS),
         ("philox_seed", C.c_uint64),
         ("stream_hi", C.c_void_p),
+        ("stream_lo", C.c_void_p),
         ("stream_hi_base", C.c_uint32),
         ("stream_lo_base", C.c_uint32),
     ]

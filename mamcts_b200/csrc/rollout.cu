@@ -36,6 +36,7 @@ struct RolloutParams {
   uint32_t const_actions[MAMCTS_MAX_AGENTS];
   uint32_t key0, key1;
   const uint32_t* stream_hi;
+  const uint32_t* stream_lo;
   uint32_t stream_hi_base, stream_lo_base;
   // mcts
   double gamma;
@@ -92,7 +93,7 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
     if (KIND == MAMCTS_SRC_REPLAY) cap = min(cap, __ldg(p.replay_steps + leaf));
     if (KIND == MAMCTS_SRC_PHILOX) {
       s_hi = p.stream_hi ? __ldg(p.stream_hi + leaf) : p.stream_hi_base;
-      s_lo = p.stream_lo_base + rid;
+      s_lo = p.stream_lo ? __ldg(p.stream_lo + leaf) + (rid - leaf * p.K) : p.stream_lo_base + rid;
     }
     m = p.gamma;   // random_heuristic.h:46
     ego = 0.0; other = 0.0; cost = 0.0; prob = 1.0; it = 0;
@@ -324,6 +325,8 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
                               sizeof(uint32_t) * n, src->mem, false);
   const int t_shi = stg.plan(src->kind == MAMCTS_SRC_PHILOX ? src->stream_hi : nullptr,
                              sizeof(uint32_t) * n, src->mem, false);
+  const int t_slo = stg.plan(src->kind == MAMCTS_SRC_PHILOX ? src->stream_lo : nullptr,
+                             sizeof(uint32_t) * n, src->mem, false);
   const int o_ego = stg.plan(out->ego_return, sizeof(double) * n, out->mem, true);
   const int o_oth = stg.plan(out->other_return, sizeof(double) * (A - 1) * n, out->mem, true);
   const int o_cost = stg.plan(out->ego_cost, sizeof(double) * n, out->mem, true);
@@ -351,6 +354,7 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   p.key0 = (uint32_t)src->philox_seed;
   p.key1 = (uint32_t)(src->philox_seed >> 32);
   p.stream_hi = stg.dev<const uint32_t>(t_shi);
+  p.stream_lo = stg.dev<const uint32_t>(t_slo);
   p.stream_hi_base = src->stream_hi_base;
   p.stream_lo_base = src->stream_lo_base;
   p.gamma = mp->discount_factor;

@@ -194,24 +194,42 @@ __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRe
   return best;
 }
 
+// The four values a backup level reads from one statistic; loaded for all agents (and one level
+// ahead) before anything is stored, so the loads of a level overlap instead of serialising.
+struct BackRegs {
+  uint32_t cnt0, nv0;
+  double q, v;
+};
+
+template <int NACT>
+__device__ __forceinline__ BackRegs back_load(const StatRec<NACT>* s, uint32_t act) {
+  BackRegs b;
+  b.cnt0 = s->n[act];
+  b.q = s->Q[act];
+  b.nv0 = s->N;
+  b.v = s->V;
+  return b;
+}
+
 // UctStatistic::update_statistics_from_backpropagated, reference uct_statistic.h:134-144.
 template <int NACT>
-__device__ __forceinline__ double backprop_stat(StatRec<NACT>* s, uint32_t act, double r, double gamma,
-                                                double child_G) {
+__device__ __forceinline__ double back_apply(StatRec<NACT>* s, uint32_t act, const BackRegs& b, double r,
+                                             double gamma, double child_G) {
+  const uint32_t cnt0 = b.cnt0, nv0 = b.nv0;
+  const double q = b.q, v = b.v;
   const double G = __dadd_rn(r, __dmul_rn(gamma, child_G));
-  const uint32_t cnt = s->n[act] + 1;
-  s->n[act] = cnt;
+  const uint32_t cnt = cnt0 + 1, nv = nv0 + 1;
   // x + (d / k) with d == +-0 is x + d for any k > 0 (the quotient keeps d's signed zero), so the
   // division is skipped when the running mean already equals the return - always the case for the
   // reward-free other agents of CrossingState.
-  const double q = s->Q[act];
   const double dq = __dsub_rn(G, q);
-  s->Q[act] = (dq == 0.0) ? __dadd_rn(q, dq) : __dadd_rn(q, __ddiv_rn(dq, (double)cnt));
-  const uint32_t nv = s->N + 1;
-  s->N = nv;
-  const double v = s->V;
   const double dv = __dsub_rn(G, v);
-  s->V = (dv == 0.0) ? __dadd_rn(v, dv) : __dadd_rn(v, __ddiv_rn(dv, (double)nv));
+  const double qn = (dq == 0.0) ? __dadd_rn(q, dq) : __dadd_rn(q, __ddiv_rn(dq, (double)cnt));
+  const double vn = (dv == 0.0) ? __dadd_rn(v, dv) : __dadd_rn(v, __ddiv_rn(dv, (double)nv));
+  s->n[act] = cnt;
+  s->Q[act] = qn;
+  s->N = nv;
+  s->V = vn;
   s->G = G;
   return G;
 }
@@ -438,21 +456,53 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
       const uint32_t par = cn->parent;
       Node* pn = nodes + par;
       const double r0 = cn->r_in[0], r1 = cn->r_in[1];
-      G[0] = backprop_stat<NE>(&pn->ego, cn->ja[0], r0, p.gamma, G[0]);
+      uint8_t cja[A];
 #pragma unroll
-      for (int j = 0; j < A - 1; ++j) G[j + 1] = backprop_stat<NA>(&pn->oth[j], cn->ja[j + 1], r1, p.gamma, G[j + 1]);
+      for (int a = 0; a < A; ++a) cja[a] = cn->ja[a];
+      const BackRegs be = back_load<NE>(&pn->ego, cja[0]);
+      BackRegs bo[A - 1];
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) bo[j] = back_load<NA>(&pn->oth[j], cja[j + 1]);
+      G[0] = back_apply<NE>(&pn->ego, cja[0], be, r0, p.gamma, G[0]);
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) G[j + 1] = back_apply<NA>(&pn->oth[j], cja[j + 1], bo[j], r1, p.gamma, G[j + 1]);
       child = par;
       level -= 1;
     }
     backup_levels += depth;
-    while (level > 0) {
-      level -= 1;
-      Node* pn = nodes + path_node[level];
-      const double r0 = path_r0[level], r1 = path_r1[level];
-      G[0] = backprop_stat<NE>(&pn->ego, path_ja[level][0], r0, p.gamma, G[0]);
+    // recorded path, software-pipelined: the loads of level k-1 are in flight while level k is applied
+    if (level > 0) {
+      uint8_t cja[A], nja[A];
+      BackRegs be, bo[A - 1], ne, no[A - 1];
+      Node* pn = nodes + path_node[level - 1];
 #pragma unroll
-      for (int j = 0; j < A - 1; ++j)
-        G[j + 1] = backprop_stat<NA>(&pn->oth[j], path_ja[level][j + 1], r1, p.gamma, G[j + 1]);
+      for (int a = 0; a < A; ++a) cja[a] = path_ja[level - 1][a];
+      be = back_load<NE>(&pn->ego, cja[0]);
+#pragma unroll
+      for (int j = 0; j < A - 1; ++j) bo[j] = back_load<NA>(&pn->oth[j], cja[j + 1]);
+      while (level > 0) {
+        level -= 1;
+        Node* nn = pn;
+        if (level > 0) {
+          nn = nodes + path_node[level - 1];
+#pragma unroll
+          for (int a = 0; a < A; ++a) nja[a] = path_ja[level - 1][a];
+          ne = back_load<NE>(&nn->ego, nja[0]);
+#pragma unroll
+          for (int j = 0; j < A - 1; ++j) no[j] = back_load<NA>(&nn->oth[j], nja[j + 1]);
+        }
+        const double r0 = path_r0[level], r1 = path_r1[level];
+        G[0] = back_apply<NE>(&pn->ego, cja[0], be, r0, p.gamma, G[0]);
+#pragma unroll
+        for (int j = 0; j < A - 1; ++j)
+          G[j + 1] = back_apply<NA>(&pn->oth[j], cja[j + 1], bo[j], r1, p.gamma, G[j + 1]);
+        pn = nn;
+        be = ne;
+#pragma unroll
+        for (int j = 0; j < A - 1; ++j) bo[j] = no[j];
+#pragma unroll
+        for (int a = 0; a < A; ++a) cja[a] = nja[a];
+      }
     }
   }
   p.tree_nodes[tree] = num_nodes;

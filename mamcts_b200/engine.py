@@ -119,7 +119,7 @@ class Engine:
     # -- rollouts -----------------------------------------------------------------------------
     @staticmethod
     def _source(kind, A, replay_actions=None, replay_steps=None, const_actions=None, seed=0,
-                stream_hi=None, stream_hi_base=0, stream_lo_base=0, mem=MEM_HOST):
+                stream_hi=None, stream_hi_base=0, stream_lo_base=0, stream_lo=None, mem=MEM_HOST):
         src = ActionSource()
         src.kind = kind
         src.mem = mem
@@ -149,6 +149,13 @@ class Engine:
                     src.stream_hi = sh.ctypes.data
                 else:
                     src.stream_hi = int(stream_hi)
+            if stream_lo is not None:
+                if mem == MEM_HOST:
+                    sl = np.ascontiguousarray(stream_lo, dtype=np.uint32)
+                    keep.append(sl)
+                    src.stream_lo = sl.ctypes.data
+                else:
+                    src.stream_lo = int(stream_lo)
         return src, keep
 
     def _rollout_host(self, env, mp, envp, A, x, last, flags, depth, K, src_kw, want_parity,

@@ -1,0 +1,88 @@
+// cuda_state.h - CudaState<S>: how a reference State is packed into the engine's positional POD
+// layout (include/mamcts_b200.h). Compiled against the reference's headers (juloberno/mamcts):
+// add this repository's mamcts_b200/host and include/ to the include path of the host program.
+//
+//   State concept      : mcts/state.h:99-136
+//   CrossingState<int> : environments/crossing_state.h (accessors :261-271, :173-185)
+//   SimpleState        : test/uct/simple_state.h
+//
+// Agents are positional on the device (ego = 0, others in get_other_agent_idx() order); agent ids
+// (4 / 5 in SimpleState) stay a host concept (SURVEY.md §7 "agent identity").
+#ifndef MAMCTS_B200_HOST_CUDA_STATE_H_
+#define MAMCTS_B200_HOST_CUDA_STATE_H_
+
+#include <cstdint>
+#include <stdexcept>
+#include <vector>
+
+#include "mamcts_b200.h"
+#include "mcts/state.h"
+
+namespace mcts {
+
+template <class S, class Enable = void>
+struct CudaState;  // specialise per environment
+
+// ---- CrossingState<int> -----------------------------------------------------------------------
+#ifdef CROSSING_STATE_H
+template <>
+struct CudaState<CrossingState<int>> {
+  static constexpr int kEnv = MAMCTS_ENV_CROSSING_I32;
+  // CrossingState keeps its parameters private (crossing_state.h:320); the host registers the same
+  // CrossingStateParameters<int> object it built its states from, once per process.
+  static mamcts_crossing_params& params() {
+    static mamcts_crossing_params p = [] { mamcts_crossing_params d; mamcts_default_crossing_params(&d); return d; }();
+    return p;
+  }
+  static void set_parameters(const CrossingStateParameters<int>& c) {
+    mamcts_crossing_params& p = params();
+    p.num_other_agents = c.NUM_OTHER_AGENTS;
+    p.num_other_actions = c.NUM_OTHER_ACTIONS;
+    p.cost_only_collision = c.COST_ONLY_COLLISION ? 1 : 0;
+    p.min_velocity_ego = c.MIN_VELOCITY_EGO;
+    p.max_velocity_ego = c.MAX_VELOCITY_EGO;
+    p.min_velocity_other = c.MIN_VELOCITY_OTHER;
+    p.max_velocity_other = c.MAX_VELOCITY_OTHER;
+    p.chain_length = c.CHAIN_LENGTH;
+    p.ego_goal_pos = c.EGO_GOAL_POS;
+    p.reward_collision = c.REWARD_COLLISION;
+    p.reward_goal_reached = c.REWARD_GOAL_REACHED;
+    p.reward_step = c.REWARD_STEP;
+  }
+  static uint32_t num_agents(const CrossingState<int>& s) { return s.get_num_agents(); }
+  // x / last: [A] positional; flags bit0 = terminal
+  static void pack(const CrossingState<int>& s, int32_t* x, int32_t* last, uint8_t* flags) {
+    if (s.get_agent_states().size() != params().num_other_agents)
+      throw std::logic_error("CudaState<CrossingState<int>>: set_parameters() does not match the state");
+    x[0] = s.get_ego_state().x_pos;
+    last[0] = s.get_ego_state().last_action;
+    const auto& others = s.get_agent_states();
+    for (size_t i = 0; i < others.size(); ++i) {
+      x[i + 1] = others[i].x_pos;
+      last[i + 1] = others[i].last_action;
+    }
+    *flags = s.is_terminal() ? 1 : 0;
+  }
+};
+#endif
+
+// ---- SimpleState --------------------------------------------------------------------------------
+#ifdef SIMPLESTATE_H
+template <>
+struct CudaState<SimpleState> {
+  static constexpr int kEnv = MAMCTS_ENV_SIMPLE;
+  static mamcts_simple_params& params() {
+    static mamcts_simple_params p = [] { mamcts_simple_params d; mamcts_default_simple_params(&d); return d; }();
+    return p;
+  }
+  static uint32_t num_agents(const SimpleState&) { return 2; }
+  static void pack(const SimpleState& s, int32_t* x, int32_t* last, uint8_t* flags) {
+    x[0] = s.get_state_length();
+    last[0] = 0;
+    *flags = s.is_terminal() ? 1 : 0;
+  }
+};
+#endif
+
+}  // namespace mcts
+#endif

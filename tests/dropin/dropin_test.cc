@@ -1,0 +1,246 @@
+// tests/dropin/dropin_test.cc - the drop-in check: the reference's OWN host code
+// (Mcts<S,SE,SO,H>::search, StageNode, parallel_search; juloberno/mamcts headers, unmodified) is
+// instantiated with this repository's CudaRandomHeuristic / CudaUctStatistic and compared with the
+// stock RandomHeuristic / UctStatistic instantiation in the same binary, tree by tree, bit by bit.
+//
+// Built by oracle/Makefile (target dropin) where the reference checkout exists; the binary travels
+// to the GPU box and is run by tests/test_gpu_dropin.py. Exit code = number of failed checks.
+#define UNIT_TESTING  // MCTS_TEST -> friend class UctTest (mcts/common.h:16-20)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <sstream>
+#include <vector>
+
+#include "mcts/mcts.h"
+#include "mcts/heuristics/random_heuristic.h"
+#include "mcts/statistics/uct_statistic.h"
+#include "environments/crossing_state.h"
+#include "test/uct/simple_state.h"
+
+#include "batched_mcts.h"
+#include "cuda_random_heuristic.h"
+#include "cuda_state.h"
+#include "cuda_uct_statistic.h"
+#include "mamcts_oracle.h"  // CPU checker for the PHILOX cases (test infrastructure)
+
+using namespace mcts;
+
+static int g_failures = 0;
+#define CHECK_MSG(cond, name)                                        \
+  do {                                                               \
+    if (cond) { std::printf("PASS %s\n", name); }                    \
+    else { std::printf("FAIL %s\n", name); ++g_failures; }           \
+  } while (0)
+
+// statistic readers: UctStatistic keeps its members protected (friend UctTest), CudaUctStatistic has
+// public accessors.
+class mcts::UctTest {
+ public:
+  static void read(const UctStatistic& s, double* v, double* g, unsigned* n, std::map<ActionIdx, std::pair<unsigned, double>>* ucb) {
+    *v = s.value_; *g = s.latest_return_; *n = s.total_node_visits_;
+    for (const auto& kv : s.ucb_statistics_) (*ucb)[kv.first] = {kv.second.action_count_, kv.second.action_value_};
+  }
+  static void read(const CudaUctStatistic& s, double* v, double* g, unsigned* n, std::map<ActionIdx, std::pair<unsigned, double>>* ucb) {
+    *v = s.get_value(); *g = s.get_latest_return(); *n = s.get_total_node_visits();
+    for (const auto& kv : s.get_ucb_statistics()) (*ucb)[kv.first] = {kv.second.action_count_, kv.second.action_value_};
+  }
+  template <class M>
+  static auto root_of(M& m) { return m.root_; }
+};
+
+// canonical dump (same record as mamcts_search_dump_tree / orc_tree_dump)
+template <class NodePtr>
+static void dump_tree(const NodePtr& node, uint32_t max_actions, std::vector<double>* out) {
+  const uint32_t A = node->get_state()->get_num_agents();
+  auto code_of = [&](const JointAction& ja) {
+    double c = 0.0, mul = 1.0;
+    for (uint32_t a = 0; a < A; ++a) { c += mul * (double)ja[a]; mul *= max_actions; }
+    return c;
+  };
+  auto children = node->get_children();
+  std::map<double, typename decltype(children)::mapped_type> sorted;
+  for (auto& kv : children) sorted[code_of(kv.first)] = kv.second;
+  out->push_back(node->get_depth());
+  out->push_back(-2.0);  // joint-action code is written by the parent below
+  const size_t code_pos = out->size() - 1;
+  (void)code_pos;
+  out->push_back(node->get_visit_count());
+  out->push_back((double)children.size());
+  auto emit = [&](const auto& stat) {
+    double v, g; unsigned n;
+    std::map<ActionIdx, std::pair<unsigned, double>> ucb;
+    UctTest::read(stat, &v, &g, &n, &ucb);
+    out->push_back(n); out->push_back(v); out->push_back(g);
+    for (uint32_t k = 0; k < max_actions; ++k) out->push_back(ucb.count(k) ? (double)ucb[k].first : -1.0);
+    for (uint32_t k = 0; k < max_actions; ++k) out->push_back(ucb.count(k) ? ucb[k].second : 0.0);
+  };
+  emit(node->get_ego_int_node());
+  for (const auto& o : node->get_other_int_nodes()) emit(o);
+  for (auto& kv : sorted) {
+    const size_t pos = out->size();
+    dump_tree(kv.second, max_actions, out);
+    (*out)[pos + 1] = kv.first;
+  }
+}
+
+template <class NodePtr>
+static std::vector<double> dump_root(const NodePtr& root, uint32_t max_actions) {
+  std::vector<double> out;
+  dump_tree(root, max_actions, &out);
+  out[1] = -1.0;
+  return out;
+}
+
+static bool bit_equal(const std::vector<double>& a, const std::vector<double>& b) {
+  return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(double)) == 0);
+}
+
+static MctsParameters test_params(unsigned iterations, unsigned seed = 1000) {
+  MctsParameters p = mcts_default_parameters();
+  p.RANDOM_SEED = seed;
+  p.MAX_NUMBER_OF_ITERATIONS = iterations;
+  p.MAX_NUMBER_OF_NODES = 100000000;
+  p.MAX_SEARCH_TIME = 1000000000;          // no wall-clock cut-offs
+  p.random_heuristic.MAX_SEARCH_TIME = 1e9;
+  p.random_heuristic.MAX_NUMBER_OF_ITERATIONS = 50;
+  return p;
+}
+
+struct CrossingFixture {
+  CrossingStateParameters<int> params;
+  std::unordered_map<AgentIdx, HypothesisId> hyp;
+  explicit CrossingFixture(unsigned others) : params(default_crossing_state_parameters<int>()) {
+    params.NUM_OTHER_AGENTS = others;
+    for (AgentIdx i = 1; i <= others; ++i) hyp[i] = 0;
+    CudaState<CrossingState<int>>::set_parameters(params);
+  }
+  CrossingState<int> state() { return CrossingState<int>(hyp, params); }
+};
+
+template <class S, class SE, class SO, class H>
+static std::vector<double> search_and_dump(const S& state, const MctsParameters& p, uint32_t max_actions,
+                                           ActionIdx* best = nullptr) {
+  Mcts<S, SE, SO, H> mcts(p);
+  mcts.search(state);
+  if (best) *best = mcts.returnBestAction();
+  return dump_root(UctTest::root_of(mcts), max_actions);
+}
+
+static std::vector<double> oracle_dump(const orc_env& env, const mamcts_params& mp, const int32_t* root_x,
+                                       uint32_t iterations, uint64_t seed, uint32_t tree_id, uint32_t max_actions) {
+  orc_search_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.env = env;
+  cfg.mcts = mp;
+  cfg.action_source = MAMCTS_SRC_PHILOX;
+  cfg.rollouts_per_leaf = 1;
+  cfg.philox_seed = seed;
+  cfg.tree_id = tree_id;
+  for (uint32_t a = 0; a < env.num_agents; ++a) mamcts_reference_expand_order(mp.random_seed, env.num_actions[a], cfg.expand_order[a]);
+  orc_state root;
+  std::memset(&root, 0, sizeof(root));
+  for (uint32_t a = 0; a < env.num_agents; ++a) { root.x[a] = root_x[a]; root.last[a] = 2; }
+  orc_tree* t = orc_tree_create(&cfg, &root);
+  orc_tree_run(t, iterations);
+  const uint32_t nn = orc_tree_num_nodes(t);
+  std::vector<double> rec((size_t)nn * (4 + env.num_agents * (3 + 2 * max_actions)));
+  orc_tree_dump(t, rec.data(), nn, max_actions);
+  orc_tree_destroy(t);
+  return rec;
+}
+
+int main() {
+  // 1. CudaRandomHeuristic (REFERENCE_CONST) under the reference's Mcts reproduces the stock tree.
+  for (unsigned others : {1u, 2u}) {
+    CrossingFixture fx(others);
+    const MctsParameters p = test_params(others == 1 ? 1500 : 700);
+    CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();
+    auto state = fx.state();
+    auto ref = search_and_dump<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic>(state, p, 7);
+    auto gpu = search_and_dump<CrossingState<int>, UctStatistic, UctStatistic, CudaRandomHeuristic>(state, p, 7);
+    CHECK_MSG(bit_equal(ref, gpu), others == 1 ? "crossing2_cuda_heuristic_tree_bit_equal" : "crossing3_cuda_heuristic_tree_bit_equal");
+    // 2. ... and with CudaUctStatistic as SE and SO (backup through mamcts_backup_uct).
+    ActionIdx best_ref = 0, best_gpu = 0;
+    auto ref2 = search_and_dump<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic>(state, p, 7, &best_ref);
+    auto gpu2 = search_and_dump<CrossingState<int>, CudaUctStatistic, CudaUctStatistic, CudaRandomHeuristic>(state, p, 7, &best_gpu);
+    CHECK_MSG(bit_equal(ref2, gpu2) && best_ref == best_gpu,
+              others == 1 ? "crossing2_cuda_statistic_tree_bit_equal" : "crossing3_cuda_statistic_tree_bit_equal");
+  }
+  {  // SimpleState (config 1: test/uct/uct_test.cc parameters, 20 and 300 iterations, 100 nodes)
+    for (unsigned iters : {20u, 300u}) {
+      MctsParameters p = test_params(iters);
+      p.MAX_NUMBER_OF_NODES = 100;
+      p.random_heuristic.MAX_NUMBER_OF_ITERATIONS = 40;
+      SimpleState state(4);
+      auto ref = search_and_dump<SimpleState, UctStatistic, UctStatistic, RandomHeuristic>(state, p, 2);
+      auto gpu = search_and_dump<SimpleState, CudaUctStatistic, CudaUctStatistic, CudaRandomHeuristic>(state, p, 2);
+      CHECK_MSG(bit_equal(ref, gpu), iters == 20 ? "simple_20_iterations_tree_bit_equal" : "simple_300_iterations_tree_bit_equal");
+    }
+  }
+  {  // 3. static rollout<> keeps RandomHeuristic's tuple (used by ActionValueRandomHeuristic, :61)
+    CrossingFixture fx(2);
+    const MctsParameters p = test_params(10);
+    auto st = std::make_shared<CrossingState<int>>(fx.state());
+    auto a = RandomHeuristic::rollout<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic>(st, p, 0);
+    auto b = CudaRandomHeuristic::rollout<CrossingState<int>, UctStatistic, UctStatistic, CudaRandomHeuristic>(st, p, 0);
+    bool same = std::get<0>(a) == std::get<0>(b) && std::get<2>(a) == std::get<2>(b) && std::get<3>(a) == std::get<3>(b) &&
+                std::get<1>(a) == std::get<1>(b);
+    CHECK_MSG(same && std::get<0>(b) == 0.0013962886019873665 && std::get<3>(b) == 7.0, "static_rollout_tuple_equal");
+  }
+  {  // 4. parallel_search (threads) + merge_node_statistics through mamcts_root_merge
+    CrossingFixture fx(1);
+    MctsParameters p = test_params(400);
+    p.NUM_PARALLEL_MCTS = 4;
+    p.USE_MULTI_THREADING = true;
+    auto state = fx.state();
+    Mcts<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic> ref(p);
+    ref.search(state);
+    Mcts<CrossingState<int>, CudaUctStatistic, CudaUctStatistic, CudaRandomHeuristic> gpu(p);
+    gpu.search(state);
+    double v, g, v2, g2; unsigned n, n2;
+    std::map<ActionIdx, std::pair<unsigned, double>> a, b;
+    UctTest::read(ref.get_root().get_ego_int_node(), &v, &g, &n, &a);
+    UctTest::read(gpu.get_root().get_ego_int_node(), &v2, &g2, &n2, &b);
+    bool ok = n == n2 && a.size() == b.size() && std::fabs(v - v2) <= 1e-12 * std::fabs(v) &&
+              ref.returnBestAction() == gpu.returnBestAction();
+    for (auto& kv : a) ok = ok && b.count(kv.first) && b[kv.first].first == kv.second.first &&
+                            std::fabs(b[kv.first].second - kv.second.second) <= 1e-12 * std::fabs(kv.second.second) + 1e-300;
+    CHECK_MSG(ok, "parallel_search_merge_matches");
+  }
+  // 5. leaf-parallel batcher over host trees: one rollout launch (and one backup launch) per wave.
+  for (int variant = 0; variant < 2; ++variant) {
+    CrossingFixture fx(1);
+    const MctsParameters p = test_params(300);
+    const unsigned T = 24, first = 500;
+    const uint64_t seed = 4242;
+    auto state = fx.state();
+    orc_env env;
+    orc_env_crossing(&env, &CudaState<CrossingState<int>>::params());
+    const mamcts_params mp = to_mamcts_params(p);
+    const int32_t root_x[2] = {5, 5};
+    bool ok = true;
+    uint64_t steps = 0;
+    ActionIdx best = 99;
+    std::vector<std::vector<double>> dumps;
+    if (variant == 0) {
+      BatchedRootParallelMcts<CrossingState<int>, UctStatistic, UctStatistic> b(p, T, seed, first);
+      b.search(state);
+      for (unsigned t = 0; t < T; ++t) dumps.push_back(dump_root(b.get_root_ptr(t), 7));
+      steps = b.rolloutSteps();
+      best = b.returnBestAction();
+    } else {
+      BatchedRootParallelMcts<CrossingState<int>, CudaUctStatistic, CudaUctStatistic> b(p, T, seed, first);
+      b.search(state);
+      for (unsigned t = 0; t < T; ++t) dumps.push_back(dump_root(b.get_root_ptr(t), 7));
+      steps = b.rolloutSteps();
+      best = b.returnBestAction();
+    }
+    for (unsigned t = 0; t < T; ++t) ok = ok && bit_equal(dumps[t], oracle_dump(env, mp, root_x, 300, seed, first + t, 7));
+    CHECK_MSG(ok && steps > 0 && best < 4, variant == 0 ? "batched_host_trees_equal_oracle" : "batched_host_trees_cuda_statistic_equal_oracle");
+  }
+  std::printf("%s (%d failed)\n", g_failures ? "DROPIN FAILED" : "DROPIN OK", g_failures);
+  return g_failures;
+}

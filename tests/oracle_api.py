@@ -211,7 +211,7 @@ def rollout(env: OrcEnv, mp: Params, x, last=None, terminal=False, depth=0, kind
 
 def rollout_batch(env: OrcEnv, mp: Params, x, last=None, flags=None, depth=None, K=1,
                   kind=SRC_PHILOX, replay=None, replay_steps=None, const_actions=None, seed=0,
-                  stream_hi=None, stream_hi_base=0, stream_lo_base=0, trace_stride=0):
+                  stream_hi=None, stream_hi_base=0, stream_lo_base=0, stream_lo=None, trace_stride=0):
     """Oracle counterpart of mamcts_rollout_* over n leaves x K rollouts (same output layout)."""
     x = np.asarray(x, dtype=np.int32)
     A = env.num_agents
@@ -228,7 +228,8 @@ def rollout_batch(env: OrcEnv, mp: Params, x, last=None, flags=None, depth=None,
         oth = np.zeros((max(A - 1, 1), K))
         for k in range(K):
             hi = int(stream_hi[i]) if stream_hi is not None else stream_hi_base
-            lo = (stream_lo_base + i * K + k) & 0xFFFFFFFF
+            lo = ((int(stream_lo[i]) + k) if stream_lo is not None
+                  else (stream_lo_base + i * K + k)) & 0xFFFFFFFF
             rep = None
             if kind == SRC_REPLAY:
                 rep = np.asarray(replay[i][:int(replay_steps[i])], dtype=np.int8).reshape(-1, A)

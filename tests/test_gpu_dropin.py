@@ -1,0 +1,54 @@
+"""GPU drop-in tests: the reference's OWN host code (Mcts<S,SE,SO,H>::search, StageNode,
+parallel_search, UctTest::verify_uct - compiled unmodified from the reference checkout into
+oracle/_ref/ by `make -C oracle dropin`) instantiated with this repository's CudaRandomHeuristic /
+CudaUctStatistic / BatchedRootParallelMcts (mamcts_b200/host/*.h), which reach the kernels through
+the C ABI. The binaries are prebuilt where the reference exists and travel to the GPU box; nothing
+here reads /root/reference at run time.
+
+  dropin_test        - tests/dropin/dropin_test.cc: stock vs CUDA instantiation, tree by tree, bit by bit
+  dropin_verify_uct  - tests/dropin/dropin_verify_uct.cc: reference test/uct/uct_test_class.h:23-215
+                       (the back-propagation invariant) on trees whose rollouts came from the GPU
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _run(name: str, timeout: int = 600) -> str:
+    exe = os.path.join(REF_DIR, name)
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} is missing: run `python __graft_entry__.py` where the reference checkout exists "
+                    f"(the binary travels to the GPU box with the snapshot)")
+    pr = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
+    out = pr.stdout + pr.stderr
+    assert pr.returncode == 0, f"{name} exited {pr.returncode}:\n{out[-4000:]}"
+    return out
+
+
+def test_reference_mcts_with_cuda_heuristic_and_statistic_is_bit_equal():
+    out = _run("dropin_test")
+    assert "DROPIN OK" in out
+    assert "FAIL" not in out
+    # every named check ran
+    for name in ("crossing2_cuda_heuristic_tree_bit_equal", "crossing3_cuda_heuristic_tree_bit_equal",
+                 "crossing2_cuda_statistic_tree_bit_equal", "crossing3_cuda_statistic_tree_bit_equal",
+                 "simple_20_iterations_tree_bit_equal", "simple_300_iterations_tree_bit_equal",
+                 "static_rollout_tuple_equal", "parallel_search_merge_matches",
+                 "batched_host_trees_equal_oracle", "batched_host_trees_cuda_statistic_equal_oracle"):
+        assert f"PASS {name}" in out, f"{name} did not pass:\n{out[-4000:]}"
+
+
+def test_reference_verify_uct_on_gpu_rollouts():
+    out = _run("dropin_verify_uct")
+    assert "FAIL" not in out and " 0 failures" in out, out[-4000:]
+    for name in ("dropin_mcts.verify_uct_simple_state_philox_rollouts",
+                 "dropin_mcts.verify_uct_crossing_state_philox_rollouts"):
+        assert f"PASS {name}" in out, out[-4000:]
