@@ -204,10 +204,12 @@ def run_native(args):
         dist.broadcast(uid, 0)
         engine.comm_init_rank(bytes(uid.cpu().tolist()), world, rank)
 
+    from mamcts_b200 import sharding
     mp, cp = _params()
     T = args.trees
-    search = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=SRC_PHILOX,
-                    philox_seed=1000, first_tree_id=rank * T)
+    shard = sharding.weak_shard(T, world, rank)   # fixed trees per GPU, global ids rank*T ...
+    search = Search(engine, ENV_CROSSING_I32, mp, shard.num_trees, cp=cp, action_source=SRC_PHILOX,
+                    philox_seed=1000, first_tree_id=shard.first_tree_id)
     root = np.full(NUM_OTHERS + 1, 5, dtype=np.int32)
     root_pinned = torch.from_numpy(root.copy()).pin_memory()
 

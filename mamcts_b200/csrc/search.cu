@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -38,6 +39,7 @@ struct mamcts_search {
   unsigned long long* d_counters = nullptr;
   int32_t* d_root_x = nullptr;
   uint32_t iters_done = 0;
+  int block_threads = mamcts::kSearchThreads;
 
   virtual ~mamcts_search() {}
   virtual size_t node_bytes() const = 0;
@@ -78,11 +80,12 @@ struct SearchT final : public mamcts_search {
     SearchParams q = p;
     q.iterations = iterations;
     const uint32_t T = cfg.num_trees;
-    const int grid = (int)((T + kSearchThreads - 1) / kSearchThreads);
+    const uint32_t trees_per_block = (uint32_t)(block_threads / 32) * q.lanes_per_warp;
+    const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
     if (cfg.action_source == MAMCTS_SRC_PHILOX)
-      search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_PHILOX><<<grid, kSearchThreads, 0, e->stream>>>(q);
+      search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_PHILOX><<<grid, block_threads, 0, e->stream>>>(q);
     else
-      search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_REFERENCE_CONST><<<grid, kSearchThreads, 0, e->stream>>>(q);
+      search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_REFERENCE_CONST><<<grid, block_threads, 0, e->stream>>>(q);
     e->launches++;
     MAMCTS_CUDA(e, cudaGetLastError());
     return MAMCTS_OK;
@@ -276,6 +279,15 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   p.gamma = mp.discount_factor; p.two_c = 2 * mp.uct_exploration_constant;
   p.lb = mp.uct_lower_bound; p.ub = mp.uct_upper_bound;
   p.env = ep;
+  p.lanes_per_warp = 32;
+  if (const char* v = std::getenv("MAMCTS_SEARCH_LPW")) {
+    const int l = std::atoi(v);
+    if (l >= 1 && l <= 32) p.lanes_per_warp = (uint32_t)l;
+  }
+  if (const char* v = std::getenv("MAMCTS_SEARCH_THREADS")) {
+    const int t = std::atoi(v);
+    if (t >= 32 && t <= kSearchThreads && t % 32 == 0) s->block_threads = t;
+  }
   s->state_ints = (cfg->env == MAMCTS_ENV_SIMPLE) ? 1 : A;
   int32_t rx[MAMCTS_MAX_AGENTS] = {0};
   for (uint32_t i = 0; i < s->state_ints; ++i) rx[i] = root_x[i];

@@ -68,6 +68,7 @@ struct SearchParams {
   const double* log_table;  // log((double)N), host libm
   unsigned long long* counters;  // iterations, rollout steps, expand steps, nodes, backup levels, exact UCB
   uint32_t T, max_nodes, hash_mask, iterations, first_tree_id;
+  uint32_t lanes_per_warp;  // trees per warp: lanes >= this exit at once (see search.cu: divergence)
   uint32_t n_ego, n_oth;
   uint32_t use_bound_est, max_depth, node_budget, rh_cap;
   uint32_t key0, key1;
@@ -306,7 +307,9 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
   using Node = NodeRec<Env, NE, NA, NCHILD, CIDX>;
   constexpr int A = Env::A;
   constexpr bool kDirect = NCHILD > 0;
-  const uint32_t tree = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (lane >= p.lanes_per_warp) return;
+  const uint32_t tree = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * p.lanes_per_warp + lane;
   if (tree >= p.T) return;
   Node* nodes = static_cast<Node*>(p.nodes) + (size_t)tree * p.max_nodes;
   uint32_t* hash = kDirect ? nullptr : p.hash + (size_t)tree * (p.hash_mask + 1);

@@ -5,7 +5,7 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it,
  * and only as the checker. Each function cites the reference (juloberno/mamcts) file:line it
  * restates. Parity status: PINNED - validated against the unmodified reference compiled into
- * oracle/_ref/libmamcts_ref.so (tests/test_oracle_vs_reference.py) and against the golden
+ * oracle/_ref/libmamcts_ref.so (tests/test_oracle_cpu.py::test_oracle_*_equal_reference*) and against the golden
  * vectors in tests/golden/ generated from it (tests/golden/make_golden.py).
  */
 #ifndef MAMCTS_ORACLE_H_

@@ -1,0 +1,37 @@
+"""Sweep of the device-resident search over (lanes per warp, block threads, trees); prints one line per
+point. Profiling helper, not part of the product or the tests.
+   python scripts/sweep_search.py "lpw,threads,trees,iterations;..." """
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from mamcts_b200 import default_crossing_params, default_params
+from mamcts_b200._abi import ENV_CROSSING_I32, SRC_PHILOX
+from mamcts_b200.engine import Engine, Search
+
+def main():
+    pts = [tuple(int(x) for x in p.split(",")) for p in sys.argv[1].split(";") if p]
+    others = int(os.environ.get("SWEEP_OTHERS", "1"))
+    e = Engine(0)
+    for pt in pts:
+        lpw, threads, trees, iters = pt[:4]
+        maxn = pt[4] if len(pt) > 4 else 0
+        os.environ["MAMCTS_SEARCH_LPW"] = str(lpw)
+        os.environ["MAMCTS_SEARCH_THREADS"] = str(threads)
+        mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000, rh_max_number_of_iterations=50)
+        cp = default_crossing_params(num_other_agents=others)
+        s = Search(e, ENV_CROSSING_I32, mp, trees, cp=cp, action_source=SRC_PHILOX, philox_seed=1000,
+                   max_nodes_per_tree=maxn)
+        s.run(iters); e.sync()
+        best = 1e9
+        for _ in range(2):
+            s.reset(None); e.sync()
+            t0 = time.perf_counter(); s.run(iters); e.sync(); dt = time.perf_counter() - t0
+            best = min(best, dt)
+        c = s.counters()
+        steps = c["rollout_steps"] + c["expand_steps"]
+        print(f"lpw={lpw} threads={threads} trees={trees} iters={iters} maxn={maxn} ms={best*1e3:.1f} "
+              f"env_steps/s={steps/best:.4g} it/s={c['iterations']/best:.4g}", flush=True)
+        s.close()
+    e.close()
+main()

@@ -152,6 +152,77 @@ static std::vector<double> oracle_dump(const orc_env& env, const mamcts_params& 
   return rec;
 }
 
+// Check 6: the back-propagation invariant of the reference's verify_uct (test/uct/uct_test_class.h),
+// stated positionally so that it also holds on PHILOX trees (non-diagonal joint actions, terminal
+// children that are re-visited: stage_node.h:183-187 returns without a rollout but mcts.h:314-329
+// still back-propagates the child's latest return):
+//   n_a(parent) = sum over children c with ja_c[p] == a of (1 + visit_count_c)
+//   Q_a(parent) = sum over those children of (1 + visit_count_c) (r_c[p] + gamma V_c) / n_a(parent)
+//   N(parent)   = sum_a n_a(parent) + (parent is not the root: 1 for its own heuristic update)
+template <class NodePtr>
+static void check_invariant(const NodePtr& node, double gamma, long* nodes_checked, long* bad) {
+  auto children = node->get_children();
+  if (children.empty()) return;
+  const auto* st = node->get_state();
+  const unsigned A = st->get_num_agents();
+  auto read_pos = [](const auto& nd, unsigned p, double* v, unsigned* n, std::map<ActionIdx, std::pair<unsigned, double>>* ucb) {
+    double g;
+    if (p == 0) UctTest::read(nd->get_ego_int_node(), v, &g, n, ucb);
+    else UctTest::read(nd->get_other_int_nodes()[p - 1], v, &g, n, ucb);
+  };
+  for (unsigned p = 0; p < A; ++p) {
+    double pv; unsigned pn;
+    std::map<ActionIdx, std::pair<unsigned, double>> pucb;
+    read_pos(node, p, &pv, &pn, &pucb);
+    std::map<ActionIdx, double> exp_n, exp_q;
+    for (const auto& kv : children) {
+      const JointAction& ja = kv.first;
+      std::vector<Reward> rewards;
+      EgoCosts cost;
+      st->execute(ja, rewards, cost);
+      double cv; unsigned cn;
+      std::map<ActionIdx, std::pair<unsigned, double>> cucb;
+      read_pos(kv.second, p, &cv, &cn, &cucb);
+      const double w = 1.0 + kv.second->get_visit_count();
+      exp_n[ja[p]] += w;
+      exp_q[ja[p]] += w * (rewards[p] + gamma * cv);
+    }
+    double sum_n = 0.0;
+    for (const auto& kv : exp_n) {
+      const ActionIdx a = kv.first;
+      const bool have = pucb.count(a) == 1;
+      const double q = exp_q[a] / kv.second;
+      if (!have || (double)pucb[a].first != kv.second ||
+          std::fabs(pucb[a].second - q) > 1e-9 * (1.0 + std::fabs(q))) {
+        if (*bad < 5) std::printf("  invariant violated: depth %u agent position %u action %zu: n %u vs %.0f, q %.17g vs %.17g\n",
+                                  node->get_depth(), p, (size_t)a, have ? pucb[a].first : 0u, kv.second, have ? pucb[a].second : 0.0, q);
+        ++*bad;
+      }
+      sum_n += kv.second;
+    }
+    if ((double)pn != sum_n + (node->is_root() ? 0.0 : 1.0)) {
+      if (*bad < 5) std::printf("  invariant violated: depth %u agent position %u: N %u vs %.0f\n", node->get_depth(), p, pn, sum_n);
+      ++*bad;
+    }
+  }
+  *nodes_checked += 1;
+  for (const auto& kv : children) check_invariant(kv.second, gamma, nodes_checked, bad);
+}
+
+template <class S, class SE, class SO>
+static bool philox_tree_satisfies_invariant(const S& state, const MctsParameters& p, long min_nodes) {
+  CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();
+  CudaRandomHeuristic::options().action_source = MAMCTS_SRC_PHILOX;
+  CudaRandomHeuristic::options().philox_seed = 77;
+  Mcts<S, SE, SO, CudaRandomHeuristic> mcts(p);
+  mcts.search(state);
+  long nodes = 0, bad = 0;
+  check_invariant(UctTest::root_of(mcts), p.DISCOUNT_FACTOR, &nodes, &bad);
+  CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();
+  std::printf("  %ld inner nodes checked, %ld violations\n", nodes, bad);
+  return bad == 0 && nodes >= min_nodes;
+}
+
 int main() {
   // 1. CudaRandomHeuristic (REFERENCE_CONST) under the reference's Mcts reproduces the stock tree.
   for (unsigned others : {1u, 2u}) {
@@ -240,6 +311,22 @@ int main() {
     }
     for (unsigned t = 0; t < T; ++t) ok = ok && bit_equal(dumps[t], oracle_dump(env, mp, root_x, 300, seed, first + t, 7));
     CHECK_MSG(ok && steps > 0 && best < 4, variant == 0 ? "batched_host_trees_equal_oracle" : "batched_host_trees_cuda_statistic_equal_oracle");
+  }
+  {  // 6. positional back-propagation invariant on PHILOX trees (stock and CUDA statistics)
+    CrossingFixture fx(2);
+    MctsParameters p = test_params(1500);
+    auto cs = fx.state();
+    CHECK_MSG((philox_tree_satisfies_invariant<CrossingState<int>, UctStatistic, UctStatistic>(cs, p, 50)),
+              "philox_crossing_tree_backprop_invariant");
+    CHECK_MSG((philox_tree_satisfies_invariant<CrossingState<int>, CudaUctStatistic, CudaUctStatistic>(cs, p, 50)),
+              "philox_crossing_tree_backprop_invariant_cuda_statistic");
+    MctsParameters ps = test_params(1500);
+    ps.random_heuristic.MAX_NUMBER_OF_ITERATIONS = 40;
+    SimpleState ss(4);
+    CHECK_MSG((philox_tree_satisfies_invariant<SimpleState, UctStatistic, UctStatistic>(ss, ps, 50)),
+              "philox_simple_tree_backprop_invariant");
+    CHECK_MSG((philox_tree_satisfies_invariant<SimpleState, CudaUctStatistic, CudaUctStatistic>(ss, ps, 50)),
+              "philox_simple_tree_backprop_invariant_cuda_statistic");
   }
   std::printf("%s (%d failed)\n", g_failures ? "DROPIN FAILED" : "DROPIN OK", g_failures);
   return g_failures;

@@ -1,8 +1,16 @@
-// tests/dropin/dropin_verify_uct.cc - runs the REFERENCE'S OWN back-propagation invariant checker
-// (UctTest::verify_uct, reference test/uct/uct_test_class.h:23-215: for every node, recompute the
-// expected visit counts and Q(s,a) = sum_child n_child (r + gamma V_child) / n_a from the children)
-// on trees whose rollouts came from the CUDA engine through CudaRandomHeuristic. Mirrors the
-// reference's test/uct/uct_test.cc:42-52. Built by oracle/Makefile (target dropin).
+// tests/dropin/dropin_verify_uct.cc - the reference's back-propagation invariant on trees whose
+// rollouts came from the CUDA engine.
+//
+// 1. The reference's OWN checker UctTest::verify_uct (reference test/uct/uct_test_class.h:23-215)
+//    run exactly as the reference's test does (test/uct/uct_test.cc:22-52: SimpleState(4), 10 000
+//    iterations, 100 nodes) with CudaRandomHeuristic plugged into Mcts<>.
+//    verify_uct is only sound on the trees that test produces: it looks actions up with
+//    std::find over the WHOLE joint action (uct_test_class.h:44-47) and indexes other agents'
+//    actions by their position among the others, i.e. one slot too low (:96-101, :160), which is
+//    harmless only while every child has a "diagonal" joint action (a, a) - the case under the
+//    reference's deterministic rollouts. So it runs with the REFERENCE_CONST source.
+//    The same invariant stated positionally, for PHILOX trees, is check 6 of dropin_test.cc.
+// Built by oracle/Makefile (target dropin); run on the GPU box by tests/test_gpu_dropin.py.
 #include "gtest/gtest.h"
 
 #define UNIT_TESTING
@@ -23,7 +31,7 @@ MctsParameters default_uct_params() {
   MctsParameters parameters(mcts_default_parameters());
   parameters.DISCOUNT_FACTOR = 0.9;
   parameters.RANDOM_SEED = 1000;
-  parameters.MAX_NUMBER_OF_ITERATIONS = 2000;
+  parameters.MAX_NUMBER_OF_ITERATIONS = 10000;
   parameters.MAX_SEARCH_TIME = 1000000000;
   parameters.MAX_SEARCH_DEPTH = 1000;
   parameters.MAX_NUMBER_OF_NODES = 100;
@@ -36,31 +44,27 @@ MctsParameters default_uct_params() {
   return parameters;
 }
 
-TEST(dropin_mcts, verify_uct_simple_state_philox_rollouts) {
-  CudaRandomHeuristic::options().action_source = MAMCTS_SRC_PHILOX;
-  CudaRandomHeuristic::options().rollouts_per_leaf = 4;
+// ---- 1. the reference's own test with the CUDA heuristic -----------------------------------------
+TEST(dropin_mcts, reference_verify_uct_simple_state_cuda_heuristic) {
+  CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();  // REFERENCE_CONST
   Mcts<SimpleState, UctStatistic, UctStatistic, CudaRandomHeuristic> mcts(default_uct_params());
   SimpleState state(4);
   mcts.search(state);
+  EXPECT_EQ(mcts.numIterations(), 10000u);
   UctTest test;
   test.verify_uct(mcts, 1000);
 }
 
-TEST(dropin_mcts, verify_uct_crossing_state_philox_rollouts) {
-  CudaRandomHeuristic::options().action_source = MAMCTS_SRC_PHILOX;
-  CudaRandomHeuristic::options().rollouts_per_leaf = 1;
-  auto cparams = default_crossing_state_parameters<int>();
-  cparams.NUM_OTHER_AGENTS = 2;
-  CudaState<CrossingState<int>>::set_parameters(cparams);
-  std::unordered_map<AgentIdx, HypothesisId> hyp{{1, 0}, {2, 0}};
+// small_search_depth (test/uct/uct_test.cc:54-64) with the CUDA heuristic
+TEST(dropin_mcts, reference_small_search_depth_cuda_heuristic) {
+  CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();
   auto params = default_uct_params();
-  params.MAX_NUMBER_OF_NODES = 100000;
-  params.MAX_NUMBER_OF_ITERATIONS = 1500;
-  Mcts<CrossingState<int>, UctStatistic, UctStatistic, CudaRandomHeuristic> mcts(params);
-  CrossingState<int> state(hyp, cparams);
+  params.MAX_SEARCH_DEPTH = 2;
+  Mcts<SimpleState, UctStatistic, UctStatistic, CudaRandomHeuristic> mcts(params);
+  SimpleState state(4);
   mcts.search(state);
-  UctTest test;
-  test.verify_uct(mcts, 1000);
+  EXPECT_EQ(mcts.numIterations(), 10000u);
+  UctTest test;  // as in the reference: the depth-limited search only has to run
 }
 
 int main(int argc, char** argv) {

@@ -6,8 +6,8 @@ the C ABI. The binaries are prebuilt where the reference exists and travel to th
 here reads /root/reference at run time.
 
   dropin_test        - tests/dropin/dropin_test.cc: stock vs CUDA instantiation, tree by tree, bit by bit
-  dropin_verify_uct  - tests/dropin/dropin_verify_uct.cc: reference test/uct/uct_test_class.h:23-215
-                       (the back-propagation invariant) on trees whose rollouts came from the GPU
+  dropin_verify_uct  - tests/dropin/dropin_verify_uct.cc: the reference's own test/uct/uct_test.cc:42-64
+                       (verify_uct, test/uct/uct_test_class.h:23-215) with the CUDA heuristic plugged in
 """
 from __future__ import annotations
 
@@ -42,13 +42,15 @@ def test_reference_mcts_with_cuda_heuristic_and_statistic_is_bit_equal():
                  "crossing2_cuda_statistic_tree_bit_equal", "crossing3_cuda_statistic_tree_bit_equal",
                  "simple_20_iterations_tree_bit_equal", "simple_300_iterations_tree_bit_equal",
                  "static_rollout_tuple_equal", "parallel_search_merge_matches",
-                 "batched_host_trees_equal_oracle", "batched_host_trees_cuda_statistic_equal_oracle"):
+                 "batched_host_trees_equal_oracle", "batched_host_trees_cuda_statistic_equal_oracle",
+                 "philox_crossing_tree_backprop_invariant", "philox_crossing_tree_backprop_invariant_cuda_statistic",
+                 "philox_simple_tree_backprop_invariant", "philox_simple_tree_backprop_invariant_cuda_statistic"):
         assert f"PASS {name}" in out, f"{name} did not pass:\n{out[-4000:]}"
 
 
 def test_reference_verify_uct_on_gpu_rollouts():
     out = _run("dropin_verify_uct")
     assert "FAIL" not in out and " 0 failures" in out, out[-4000:]
-    for name in ("dropin_mcts.verify_uct_simple_state_philox_rollouts",
-                 "dropin_mcts.verify_uct_crossing_state_philox_rollouts"):
+    for name in ("dropin_mcts.reference_verify_uct_simple_state_cuda_heuristic",
+                 "dropin_mcts.reference_small_search_depth_cuda_heuristic"):
         assert f"PASS {name}" in out, out[-4000:]
