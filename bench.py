@@ -170,6 +170,89 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# C3: the batched rollout kernel alone (BASELINE.json configs[2])
+# ---------------------------------------------------------------------------------------------
+
+C3_OTHERS = 7            # 8 agents
+C3_ROLLOUTS = 1 << 20    # 1M rollouts per decision
+
+
+def measure_rollout_c3(engine, stream, steps=5, warmup=3):
+    """CrossingState<int>, 8 agents, 2^20 Philox rollouts per decision (4096 start states x 256
+    rollouts each, depth cap 50), device-resident inputs; returns env-steps/s from the kernel's own
+    step counter, timed with CUDA events on the engine stream, plus the HBM roofline of
+    rollout_kernel (algorithmic bytes 16A+8C+8 per rollout)."""
+    import numpy as np
+    import torch
+    from mamcts_b200 import default_crossing_params, default_params
+    from mamcts_b200._abi import SRC_PHILOX
+    mp = default_params(rh_max_number_of_iterations=DEPTH_CAP)
+    cp = default_crossing_params(num_other_agents=C3_OTHERS)
+    A = C3_OTHERS + 1
+    n, K = 4096, C3_ROLLOUTS // 4096
+    dev = torch.device("cuda", engine.device)
+    with torch.cuda.stream(stream):
+        # the decision state (all agents at x = 5, reference crossing_state_common.h:31) in every slot
+        x = torch.full((A, n), 5, dtype=torch.int32, device=dev)
+        ego = torch.zeros(n, dtype=torch.float64, device=dev)
+        oth = torch.zeros((A - 1, n), dtype=torch.float64, device=dev)
+        cost = torch.zeros(n, dtype=torch.float64, device=dev)
+        ln = torch.zeros(n, dtype=torch.float64, device=dev)
+        tot = torch.zeros(1, dtype=torch.int64, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
+
+    def one(i):
+        engine.rollout_crossing_device(mp, cp, n, K, x.data_ptr(), ego.data_ptr(), oth.data_ptr(),
+                                       cost.data_ptr(), ln.data_ptr(), tot.data_ptr(), kind=SRC_PHILOX,
+                                       seed=1000, stream_hi_base=i, stream_lo_base=0)
+
+    for i in range(warmup):
+        one(i)
+    stream.synchronize()
+    times, total_steps = [], 0
+    launches0 = engine.launch_count
+    for i in range(steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(i & 0xFF)                     # flush L2 between timed iterations
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        one(warmup + i)
+        b.record(stream)
+        stream.synchronize()
+        times.append(a.elapsed_time(b))
+        total_steps += int(tot.item())
+    launches = engine.launch_count - launches0
+    ms = sum(times) / len(times)
+    steps_per_s = total_steps / (sum(times) * 1e-3)
+    # e2e: host buffers through the public call (pinned numpy in, numpy out)
+    xh = np.full((A, n), 5, dtype=np.int32)
+    engine.rollout_crossing(mp, cp, xh, K=K, kind=SRC_PHILOX, seed=1000, stream_hi_base=99)
+    t0 = time.perf_counter()
+    e2e_steps = 0
+    for i in range(steps):
+        r = engine.rollout_crossing(mp, cp, xh, K=K, kind=SRC_PHILOX, seed=1000, stream_hi_base=100 + i)
+        e2e_steps += r["total_steps"]
+    e2e_s = time.perf_counter() - t0
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    bytes_per_rollout = 16 * A + 8 * 1 + 8
+    achieved = bytes_per_rollout * C3_ROLLOUTS / (ms * 1e-3) / 1e9
+    return {
+        "workload": f"C3: CrossingState<int> {A} agents, {C3_ROLLOUTS} Philox rollouts per decision "
+                    f"({n} leaves x {K}), depth cap {DEPTH_CAP}, L2 flushed between decisions",
+        "env_steps_per_s": steps_per_s, "rollouts_per_s": C3_ROLLOUTS / (ms * 1e-3), "ms_per_decision": ms,
+        "mean_steps_per_rollout": total_steps / (steps * C3_ROLLOUTS), "gpu_launches": int(launches),
+        "e2e_env_steps_per_s": e2e_steps / e2e_s,
+        "e2e_h2d_bytes": int(xh.nbytes), "e2e_d2h_bytes": int(8 * n * (A + 2) + 8),
+        "roofline": {"bound": "hbm", "kernel": "rollout_kernel<CrossingEnv<7>,PHILOX>", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "algorithmic_bytes_per_rollout": bytes_per_rollout,
+                     "note": "state lives in registers for the whole episode: issue-bound, see "
+                             "profiles/ for smsp__issue_active and instructions per env-step"},
+    }
+
+
+# ---------------------------------------------------------------------------------------------
 # this repository's engine
 # ---------------------------------------------------------------------------------------------
 
@@ -205,6 +288,12 @@ def run_native(args):
         engine.comm_init_rank(bytes(uid.cpu().tolist()), world, rank)
 
     from mamcts_b200 import sharding
+    if args.workload == "c3":
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": 1,
+                              **measure_rollout_c3(engine, stream, args.steps, args.warmup)}))
+        engine.close()
+        return
     mp, cp = _params()
     T = args.trees
     shard = sharding.weak_shard(T, world, rank)   # fixed trees per GPU, global ids rank*T ...
@@ -265,7 +354,7 @@ def run_native(args):
     its = iters_per_step * args.steps / (elapsed_ms * 1e-3)
 
     # ---- e2e: through the public API with host buffers, wall clock around the whole call -------
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(min(args.warmup, 1)):  # e2e warm-up
         e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -325,8 +414,11 @@ def run_native(args):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
     search.close()
+    if rank == 0:
+        # the batched rollout kernel on its own (C3), after the trees are freed
+        line["rollout_c3"] = measure_rollout_c3(engine, stream)
+        print(json.dumps(line))
     if world > 1:
         engine.comm_destroy()
         dist.barrier()
@@ -343,6 +435,9 @@ def main():
     ap.add_argument("--trees", type=int, default=32768,
                     help="root-parallel trees per GPU (32768 trees x 10001 nodes x 288 B = 94 GB of HBM)")
     ap.add_argument("--cpu-repeats", type=int, default=24, help="whole searches per host thread for cpu_baseline")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 = the headline search benchmark (default, includes a C3 rollout-kernel section); "
+                         "c3 = only the batched rollout kernel (profiling)")
     ap.add_argument("--iterations", type=int, default=ITERATIONS,
                     help="iterations per tree (C2 = 10000; smaller values only for profiling runs)")
     args = ap.parse_args()

@@ -34,27 +34,34 @@ __device__ __forceinline__ uint32_t philox_half(const Philox4& b, int h) {
   return (h & 1) ? (b.w[h >> 1] >> 16) : (b.w[h >> 1] & 0xFFFFu);
 }
 
+// Rejection branch of philox_bounded: taken with probability (65536 mod n) / 65536 (1e-4 for n = 7),
+// so it is kept out of line - every call site would otherwise carry its own ten Philox rounds.
+static __device__ __noinline__ uint32_t philox_bounded_retry(uint32_t n, uint32_t t, uint32_t pos, uint32_t stream_lo,
+                                                      uint32_t stream_hi, uint32_t k0, uint32_t k1) {
+  uint32_t r = 0, m, l;
+  do {
+    const Philox4 b = philox4x32_10(pos, stream_lo, stream_hi, 0x10000u + (r >> 3), k0, k1);
+    const uint32_t hh = r & 7u;
+    const uint32_t word = (hh >> 1) == 0 ? b.w[0] : (hh >> 1) == 1 ? b.w[1] : (hh >> 1) == 2 ? b.w[2] : b.w[3];
+    const uint32_t x = (hh & 1u) ? (word >> 16) : (word & 0xFFFFu);
+    m = x * n;
+    l = m & 0xFFFFu;
+    ++r;
+  } while (l < t);
+  return m;
+}
+
 // Exactly-uniform draw in [0, n) from the 16-bit word x of stream position `pos` (Lemire's
 // multiply-shift with rejection). The r-th retry reads lane ((r) & 7) of
-// philox({pos, lo, hi, 0x10000 + (r >> 3)}); taken with probability (65536 mod n) / 65536.
+// philox({pos, lo, hi, 0x10000 + (r >> 3)}).
 __device__ __forceinline__ uint32_t philox_bounded(uint32_t x, uint32_t n, uint32_t pos,
                                                    uint32_t stream_lo, uint32_t stream_hi,
                                                    uint32_t k0, uint32_t k1) {
   uint32_t m = x * n;
-  uint32_t l = m & 0xFFFFu;
+  const uint32_t l = m & 0xFFFFu;
   if (l < n) {
     const uint32_t t = 65536u % n;
-    uint32_t r = 0;
-    while (l < t) {
-      const Philox4 b = philox4x32_10(pos, stream_lo, stream_hi, 0x10000u + (r >> 3), k0, k1);
-      const uint32_t hh = r & 7u;
-      const uint32_t word = b.w[0] * (uint32_t)((hh >> 1) == 0) + b.w[1] * (uint32_t)((hh >> 1) == 1) +
-                            b.w[2] * (uint32_t)((hh >> 1) == 2) + b.w[3] * (uint32_t)((hh >> 1) == 3);
-      x = (hh & 1u) ? (word >> 16) : (word & 0xFFFFu);
-      m = x * n;
-      l = m & 0xFFFFu;
-      ++r;
-    }
+    if (l < t) m = philox_bounded_retry(n, t, pos, stream_lo, stream_hi, k0, k1);
   }
   return m >> 16;
 }

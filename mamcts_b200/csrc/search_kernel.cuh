@@ -85,8 +85,17 @@ __device__ __forceinline__ void prefetch_l1(const void* ptr) {
 template <int NACT>
 struct StatRegs {
   uint32_t N, nexp;
+  double V;
   double Q[NACT];
   uint32_t n[NACT];
+};
+
+// What one backup level needs from a statistic. The descent has all four values in registers (a tree
+// is touched by one lane only, so they are still current when the backup reaches the level); they are
+// recorded with the path and the backup does no loads at all.
+struct BackRegs {
+  double q, v;
+  uint32_t cnt0, nv0;
 };
 
 template <int NACT>
@@ -94,23 +103,48 @@ __device__ __forceinline__ StatRegs<NACT> load_stat(const StatRec<NACT>* s) {
   StatRegs<NACT> r;
   r.N = s->N;
   r.nexp = s->nexp;
+  r.V = s->V;
 #pragma unroll
   for (int a = 0; a < NACT; ++a) { r.Q[a] = s->Q[a]; r.n[a] = s->n[a]; }
   return r;
 }
 
+// Exact UCB arg-max, calculate_ucb_and_max_action (reference uct_statistic.h:223-244). Cold: only
+// reached when the FP32 screen of choose_action cannot prove the winner, so it is kept out of line
+// (the hot loop must stay small enough for the instruction cache).
+template <int NACT>
+__device__ __noinline__ uint32_t exact_ucb_argmax(StatRegs<NACT> r, uint32_t mask, double lo, double range,
+                                                  double log2N, double two_c) {
+  uint32_t best = 0;
+  double max_value = DBL_MIN;  // std::numeric_limits<double>::min(), :225
+#pragma unroll 1
+  for (int a = 0; a < NACT; ++a) {
+    if ((mask >> a) & 1u) {
+      const double norm = __ddiv_rn(__dsub_rn(r.Q[a], lo), range);
+      const double v = __dadd_rn(norm, __dmul_rn(two_c, __dsqrt_rn(__ddiv_rn(log2N, (double)r.n[a]))));
+      if (v > max_value) { max_value = v; best = a; }
+    }
+  }
+  return best;
+}
+
 // UctStatistic::choose_next_action, reference uct_statistic.h:61-76 (+ :122-132, :223-244, :256-262).
+// Also returns (in `back`) the values the backup of this level will need for the chosen action.
 template <int NACT>
 __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRegs<NACT>& r,
                                                   const SearchParams& p, int cls, uint32_t nact,
-                                                  unsigned long long& exact_evals) {
+                                                  unsigned long long& exact_evals, BackRegs& back) {
   const uint32_t N = r.N;
   const uint32_t nexp = r.nexp;
+  back.nv0 = N;
+  back.v = r.V;
   if (nexp < nact && N >= p.tab->pw_min_visits[cls][nexp]) {  // require_progressive_widening_total
     const uint32_t a = p.tab->order[cls][nexp];               // :64-68 (deterministic order, F2)
     s->nexp = nexp + 1;
     s->Q[a] = 0.0;                                            // ucb_statistics_[a] = UcbPair()
     s->n[a] = 0;
+    back.cnt0 = 0;
+    back.q = 0.0;
     return a;
   }
   const uint32_t mask = p.tab->exp_mask[cls][nexp];
@@ -145,14 +179,15 @@ __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRe
   // with different inputs by more than `delta` (>= 5x the worst-case error of two scores), the
   // exact arg-max is provably the same and is returned. Actions with bit-identical (Q, n) have
   // identical exact scores, so the strict-> first-max rule picks the same one either way. Anything
-  // else falls through to the exact FP64 evaluation below, so the selected action is ALWAYS the
+  // else falls through to the exact FP64 evaluation, so the selected action is ALWAYS the
   // reference's.
+  int bi = -1;
+  bool ok;
   {
     const float rangef = (float)range, Lf = (float)log2N, c2f = (float)p.two_c;
     float sc[NACT];
     float best_sc = -1.0f;
-    int bi = -1;
-    bool ok = isfinite(rangef) && rangef != 0.0f;
+    ok = isfinite(rangef) && rangef != 0.0f;
 #pragma unroll
     for (int a = 0; a < NACT; ++a) {
       sc[a] = -2.0f;
@@ -165,43 +200,31 @@ __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRe
     }
     // best_sc must be safely above DBL_MIN's role as the initial maximum (:225)
     ok &= (bi >= 0) & (best_sc > 1e-3f);
+    double qb = 0.0;
+    uint32_t nb = 0;
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) if (a == bi) { qb = q[a]; nb = cnt[a]; }
     if (ok) {
       const float delta = 4e-6f * (best_sc + 1.0f);
-      double qb = 0.0;
-      uint32_t nb = 0;
-#pragma unroll
-      for (int a = 0; a < NACT; ++a) if (a == bi) { qb = q[a]; nb = cnt[a]; }
 #pragma unroll
       for (int a = 0; a < NACT; ++a) {
         if (((mask >> a) & 1u) && a != bi && sc[a] >= best_sc - delta)
           ok &= (q[a] == qb) & (cnt[a] == nb);
       }
-      if (ok) return (uint32_t)bi;
     }
+    back.q = qb;
+    back.cnt0 = nb;
   }
+  if (ok) return (uint32_t)bi;
 
-  // exact evaluation, calculate_ucb_and_max_action :223-244
   exact_evals += 1;
-  uint32_t best = 0;
-  double max_value = DBL_MIN;  // std::numeric_limits<double>::min(), :225
+  const uint32_t best = exact_ucb_argmax<NACT>(r, mask, lo, range, log2N, p.two_c);
 #pragma unroll
-  for (int a = 0; a < NACT; ++a) {
-    if ((mask >> a) & 1u) {
-      const double norm = __ddiv_rn(__dsub_rn(q[a], lo), range);
-      const double v = __dadd_rn(norm, __dmul_rn(p.two_c, __dsqrt_rn(__ddiv_rn(log2N, (double)cnt[a]))));
-      if (v > max_value) { max_value = v; best = a; }
-    }
-  }
+  for (int a = 0; a < NACT; ++a) if ((uint32_t)a == best) { back.q = r.Q[a]; back.cnt0 = r.n[a]; }
   return best;
 }
 
-// The four values a backup level reads from one statistic; loaded for all agents (and one level
-// ahead) before anything is stored, so the loads of a level overlap instead of serialising.
-struct BackRegs {
-  uint32_t cnt0, nv0;
-  double q, v;
-};
-
+// Loads the backup inputs of one statistic (only used below the recorded path, see deep_backup).
 template <int NACT>
 __device__ __forceinline__ BackRegs back_load(const StatRec<NACT>* s, uint32_t act) {
   BackRegs b;
@@ -246,8 +269,11 @@ __device__ __forceinline__ uint32_t hash_ja(uint32_t parent, const uint8_t (&ja)
   return h;
 }
 
-// RandomHeuristic::rollout for one lane (reference random_heuristic.h:27-104); same arithmetic as
-// rollout_kernel. Returns the ego return; `other` = the (shared) other-agent return.
+// RandomHeuristic::rollout for one lane (reference random_heuristic.h:27-104); same arithmetic and
+// the same Philox stream positions as rollout_kernel. Returns the ego return; `other` = the (shared)
+// other-agent return. The step loop is NOT unrolled over the S steps a Philox block feeds: all lanes
+// of a warp start their rollout together, so `it % S` is uniform among the active lanes and the
+// 16-bit lane is picked with a short select chain; the body stays a few hundred bytes of code.
 template <class Env, int KIND>
 __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename Env::State st,
                                                uint32_t depth, uint32_t s_hi, uint32_t s_lo,
@@ -255,51 +281,80 @@ __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename E
                                                uint32_t& steps) {
   constexpr int A = Env::A;
   constexpr int S = (KIND == MAMCTS_SRC_PHILOX && A <= 8) ? 8 / A : 1;
+  constexpr int NB = (A + 7) / 8;
   const double inv_n_ego = 1.0 / (double)Env::num_actions(p.env, 0);
   double m = p.gamma, ego = 0.0, prob = 1.0;
   other = 0.0;
   uint32_t it = 0;
   bool fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
+  Philox4 blk[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) blk[b].w[0] = blk[b].w[1] = blk[b].w[2] = blk[b].w[3] = 0u;
+#pragma unroll 1
   while (!fin) {
-    Philox4 blk[(A + 7) / 8];
+    const uint32_t sub = (S > 1) ? it % S : 0u;
     if (KIND == MAMCTS_SRC_PHILOX) {
       if (A <= 8) {
-        blk[0] = philox4x32_10(it / S, s_lo, s_hi, 0u, p.key0, p.key1);
+        if (sub == 0) blk[0] = philox4x32_10(it / S, s_lo, s_hi, 0u, p.key0, p.key1);
       } else {
 #pragma unroll
-        for (int b = 0; b < (A + 7) / 8; ++b)
-          blk[b] = philox4x32_10(it * ((A + 7) / 8) + b, s_lo, s_hi, 0u, p.key0, p.key1);
+        for (int b = 0; b < NB; ++b) blk[b] = philox4x32_10(it * NB + b, s_lo, s_hi, 0u, p.key0, p.key1);
       }
     }
+    int32_t act[A];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      if (!fin) {
-        int32_t act[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-          if (KIND == MAMCTS_SRC_PHILOX) {
-            const uint32_t h = (A <= 8) ? philox_half(blk[0], s * A + a) : philox_half(blk[a / 8], a % 8);
-            act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi,
-                                             p.key0, p.key1);
-          } else {
-            act[a] = (int32_t)const_act[a];
-          }
+    for (int a = 0; a < A; ++a) {
+      if (KIND == MAMCTS_SRC_PHILOX) {
+        uint32_t h;
+        if (A <= 8) {
+          const uint32_t lane16 = sub * A + a;   // 16-bit lane of the block, DESIGN.md section 5
+          const uint32_t wi = lane16 >> 1;
+          const uint32_t word = (S == 1) ? blk[0].w[(a >> 1) & 3]
+                                         : (wi == 0 ? blk[0].w[0] : wi == 1 ? blk[0].w[1] : wi == 2 ? blk[0].w[2] : blk[0].w[3]);
+          h = (lane16 & 1u) ? (word >> 16) : (word & 0xFFFFu);
+        } else {
+          h = philox_half(blk[a / 8], a % 8);
         }
-        double r_ego, r_other, c;
-        Env::step(p.env, st, act, r_ego, r_other, c);
-        m = __dmul_rn(p.gamma, m);
-        ego = __dadd_rn(ego, __dmul_rn(m, r_ego));
-        other = __dmul_rn(m, r_other);
-        m = __dmul_rn(m, p.gamma);
-        prob = __dmul_rn(prob, inv_n_ego);
-        it += 1;
-        depth += 1;
-        fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
+        act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi, p.key0, p.key1);
+      } else {
+        act[a] = (int32_t)const_act[a];
       }
     }
+    double r_ego, r_other, c;
+    Env::step(p.env, st, act, r_ego, r_other, c);
+    m = __dmul_rn(p.gamma, m);
+    ego = __dadd_rn(ego, __dmul_rn(m, r_ego));
+    other = __dmul_rn(m, r_other);
+    m = __dmul_rn(m, p.gamma);
+    prob = __dmul_rn(prob, inv_n_ego);
+    it += 1;
+    depth += 1;
+    fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
   }
   steps = it;
   return __dmul_rn(ego, prob);
+}
+
+// Backup below the recorded path (leaves deeper than kPathMax): follows parent pointers and loads the
+// statistics. Cold for every configuration of the reference; kept out of line.
+template <class Node, int NE, int NA, int A>
+__device__ __noinline__ uint32_t deep_backup(Node* nodes, uint32_t child, uint32_t level, double gamma, double* G) {
+  while (level > (uint32_t)kPathMax) {
+    const Node* cn = nodes + child;
+    const uint32_t par = cn->parent;
+    Node* pn = nodes + par;
+    const double r0 = cn->r_in[0], r1 = cn->r_in[1];
+    const BackRegs be = back_load<NE>(&pn->ego, cn->ja[0]);
+    G[0] = back_apply<NE>(&pn->ego, cn->ja[0], be, r0, gamma, G[0]);
+#pragma unroll 1
+    for (int j = 0; j < A - 1; ++j) {
+      const BackRegs bo = back_load<NA>(&pn->oth[j], cn->ja[j + 1]);
+      G[j + 1] = back_apply<NA>(&pn->oth[j], cn->ja[j + 1], bo, r1, gamma, G[j + 1]);
+    }
+    child = par;
+    level -= 1;
+  }
+  return child;
 }
 
 template <class Env, int NE, int NA, int NCHILD, class CIDX, int KIND>
@@ -321,26 +376,33 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
   for (int a = 0; a < A; ++a) const_act[a] = p.tab->order[a == 0 ? 0 : 1][0];  // F1: first draw
 
   // the path of the current iteration (collect(), node_statistic.h:115-121): per edge the parent
-  // node, the joint action taken and the rewards collected on it
+  // node, the joint action taken, the rewards collected on it and, per agent, the four statistic
+  // values the backup of that level reads (already in registers during the descent)
   uint32_t path_node[kPathMax];
   uint8_t path_ja[kPathMax][A];
   double path_r0[kPathMax], path_r1[kPathMax];
+  BackRegs path_back[kPathMax][A];
 
+#pragma unroll 1
   for (uint32_t iter = 0; iter < p.iterations; ++iter) {
     uint32_t node = 0;
     uint32_t depth = 0;
     bool do_rollout = false;
     typename Env::State st;
     // ---- select & expand: mcts.h:300-305, stage_node.h:167-232 --------------------------------
+#pragma unroll 1
     while (true) {
       Node* nd = nodes + node;
       // one round trip: everything the level needs is requested before anything is used
       const uint32_t vc = nd->visit_count;
       const uint32_t flags = nd->flags;
       const StatRegs<NE> ego = load_stat<NE>(&nd->ego);
-      StatRegs<NA> oth[A - 1];
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) oth[j] = load_stat<NA>(&nd->oth[j]);
+      StatRegs<NA> oth0;
+      if (A > 1) oth0 = load_stat<NA>(&nd->oth[0]);
+      if (A > 2) {
+#pragma unroll 1
+        for (int j = 1; j < A - 1; ++j) { prefetch_l1(&nd->oth[j]); prefetch_l1(&nd->oth[j].Q[NA - 1]); }
+      }
       if (kDirect) prefetch_l1(&nd->child[0]);
       double r_in0 = 0.0, r_in1 = 0.0;
       if (depth > 0) { r_in0 = nd->r_in[0]; r_in1 = nd->r_in[1]; }
@@ -350,14 +412,23 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
       if (Env::kStateInts == 1) st.x[0] = nd->x[0];  // SimpleState: terminal() reads the state
       if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) break;  // :183-187
       uint8_t ja[A];
-      ja[0] = (uint8_t)choose_action<NE>(&nd->ego, ego, p, 0, p.n_ego, exact_evals);  // :190-195
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j)
-        ja[j + 1] = (uint8_t)choose_action<NA>(&nd->oth[j], oth[j], p, 1, p.n_oth, exact_evals);
+      BackRegs back[A];
+      ja[0] = (uint8_t)choose_action<NE>(&nd->ego, ego, p, 0, p.n_ego, exact_evals, back[0]);  // :190-195
+      if (A > 1) ja[1] = (uint8_t)choose_action<NA>(&nd->oth[0], oth0, p, 1, p.n_oth, exact_evals, back[1]);
+      if (A > 2) {
+        // further other agents: one copy of the selection code, statistics come from L1 (prefetched)
+#pragma unroll 1
+        for (int j = 1; j < A - 1; ++j) {
+          const StatRegs<NA> o = load_stat<NA>(&nd->oth[j]);
+          BackRegs b;
+          ja[j + 1] = (uint8_t)choose_action<NA>(&nd->oth[j], o, p, 1, p.n_oth, exact_evals, b);
+          back[j + 1] = b;
+        }
+      }
       if (depth < kPathMax) {
         path_node[depth] = node;
 #pragma unroll
-        for (int a = 0; a < A; ++a) path_ja[depth][a] = ja[a];
+        for (int a = 0; a < A; ++a) { path_ja[depth][a] = ja[a]; path_back[depth][a] = back[a]; }
       }
       // child lookup, :198
       uint32_t child = 0;
@@ -373,7 +444,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
           const Node* cn = nodes + c;
           // the candidate is almost always the child: start pulling its record now
           prefetch_l1(&cn->ego);
-          prefetch_l1(&cn->oth[A - 2]);
+          prefetch_l1(&cn->oth[0]);
           bool same = cn->parent == node;
 #pragma unroll
           for (int a = 0; a < A; ++a) same &= cn->ja[a] == ja[a];
@@ -404,9 +475,9 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
       for (int i = 0; i < Env::kStateInts; ++i) cn->x[i] = st.x[i];
       cn->r_in[0] = r_ego;
       cn->r_in[1] = r_other;
-      cn->ego.V = 0.0; cn->ego.G = 0.0; cn->ego.N = 0; cn->ego.nexp = 0;
+      cn->ego.nexp = 0;
 #pragma unroll
-      for (int j = 0; j < A - 1; ++j) { cn->oth[j].V = 0.0; cn->oth[j].G = 0.0; cn->oth[j].N = 0; cn->oth[j].nexp = 0; }
+      for (int j = 0; j < A - 1; ++j) cn->oth[j].nexp = 0;
       if (kDirect) {
 #pragma unroll
         for (int k = 0; k < (NCHILD > 0 ? NCHILD : 1); ++k) cn->child[k] = 0;
@@ -422,16 +493,6 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
     }
     // ---- heuristic: mcts.h:309-312, random_heuristic.h:106-134, uct_statistic.h:100-110 --------
     Node* leaf = nodes + node;
-    // the backup will touch every statistic on the path: start pulling those lines now so that the
-    // whole backup costs one round trip (they are usually still in L1/L2 from the descent)
-    {
-      const uint32_t lv = depth < (uint32_t)kPathMax ? depth : (uint32_t)kPathMax;
-      for (uint32_t e = 0; e < lv; ++e) {
-        const Node* pn = nodes + path_node[e];
-        prefetch_l1(&pn->ego);
-        prefetch_l1(&pn->oth[A - 2]);
-      }
-    }
     double G[A];
     if (do_rollout) {
       double other = 0.0;
@@ -453,59 +514,21 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
     }
     // ---- backpropagation: mcts.h:314-329, stage_node.h:259-271 ---------------------------------
     uint32_t level = depth;  // number of edges between the root and the leaf
-    uint32_t child = node;
-    while (level > (uint32_t)kPathMax) {  // deeper than the recorded path: follow parent pointers
-      const Node* cn = nodes + child;
-      const uint32_t par = cn->parent;
-      Node* pn = nodes + par;
-      const double r0 = cn->r_in[0], r1 = cn->r_in[1];
-      uint8_t cja[A];
-#pragma unroll
-      for (int a = 0; a < A; ++a) cja[a] = cn->ja[a];
-      const BackRegs be = back_load<NE>(&pn->ego, cja[0]);
-      BackRegs bo[A - 1];
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) bo[j] = back_load<NA>(&pn->oth[j], cja[j + 1]);
-      G[0] = back_apply<NE>(&pn->ego, cja[0], be, r0, p.gamma, G[0]);
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) G[j + 1] = back_apply<NA>(&pn->oth[j], cja[j + 1], bo[j], r1, p.gamma, G[j + 1]);
-      child = par;
-      level -= 1;
-    }
     backup_levels += depth;
-    // recorded path, software-pipelined: the loads of level k-1 are in flight while level k is applied
-    if (level > 0) {
-      uint8_t cja[A], nja[A];
-      BackRegs be, bo[A - 1], ne, no[A - 1];
-      Node* pn = nodes + path_node[level - 1];
+    if (level > (uint32_t)kPathMax) {
+      deep_backup<Node, NE, NA, A>(nodes, node, level, p.gamma, G);
+      level = kPathMax;
+    }
+    // recorded path: no loads, only the arithmetic and the stores
+#pragma unroll 1
+    while (level > 0) {
+      level -= 1;
+      Node* pn = nodes + path_node[level];
+      const double r0 = path_r0[level], r1 = path_r1[level];
+      G[0] = back_apply<NE>(&pn->ego, path_ja[level][0], path_back[level][0], r0, p.gamma, G[0]);
 #pragma unroll
-      for (int a = 0; a < A; ++a) cja[a] = path_ja[level - 1][a];
-      be = back_load<NE>(&pn->ego, cja[0]);
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) bo[j] = back_load<NA>(&pn->oth[j], cja[j + 1]);
-      while (level > 0) {
-        level -= 1;
-        Node* nn = pn;
-        if (level > 0) {
-          nn = nodes + path_node[level - 1];
-#pragma unroll
-          for (int a = 0; a < A; ++a) nja[a] = path_ja[level - 1][a];
-          ne = back_load<NE>(&nn->ego, nja[0]);
-#pragma unroll
-          for (int j = 0; j < A - 1; ++j) no[j] = back_load<NA>(&nn->oth[j], nja[j + 1]);
-        }
-        const double r0 = path_r0[level], r1 = path_r1[level];
-        G[0] = back_apply<NE>(&pn->ego, cja[0], be, r0, p.gamma, G[0]);
-#pragma unroll
-        for (int j = 0; j < A - 1; ++j)
-          G[j + 1] = back_apply<NA>(&pn->oth[j], cja[j + 1], bo[j], r1, p.gamma, G[j + 1]);
-        pn = nn;
-        be = ne;
-#pragma unroll
-        for (int j = 0; j < A - 1; ++j) bo[j] = no[j];
-#pragma unroll
-        for (int a = 0; a < A; ++a) cja[a] = nja[a];
-      }
+      for (int j = 0; j < A - 1; ++j)
+        G[j + 1] = back_apply<NA>(&pn->oth[j], path_ja[level][j + 1], path_back[level][j + 1], r1, p.gamma, G[j + 1]);
     }
   }
   p.tree_nodes[tree] = num_nodes;
