@@ -298,7 +298,8 @@ def run_native(args):
     T = args.trees
     shard = sharding.weak_shard(T, world, rank)   # fixed trees per GPU, global ids rank*T ...
     search = Search(engine, ENV_CROSSING_I32, mp, shard.num_trees, cp=cp, action_source=SRC_PHILOX,
-                    philox_seed=1000, first_tree_id=shard.first_tree_id)
+                    philox_seed=1000, first_tree_id=shard.first_tree_id, layout=args.layout,
+                    max_inner_nodes_per_tree=args.max_inner)
     root = np.full(NUM_OTHERS + 1, 5, dtype=np.int32)
     root_pinned = torch.from_numpy(root.copy()).pin_memory()
 
@@ -435,6 +436,9 @@ def main():
     ap.add_argument("--trees", type=int, default=32768,
                     help="root-parallel trees per GPU (32768 trees x 10001 nodes x 288 B = 94 GB of HBM)")
     ap.add_argument("--cpu-repeats", type=int, default=24, help="whole searches per host thread for cpu_baseline")
+    ap.add_argument("--layout", type=int, default=0, help="tree layout: 0 auto, 1 classic, 2 compact")
+    ap.add_argument("--max-inner", type=int, default=0,
+                    help="compact layout: inner records per tree (0 = one per node)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2 = the headline search benchmark (default, includes a C3 rollout-kernel section); "
                          "c3 = only the batched rollout kernel (profiling)")

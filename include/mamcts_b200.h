@@ -269,6 +269,16 @@ int mamcts_allreduce_f64(mamcts_engine* e, double* dptr, size_t count);
 /* Replaces Mcts<S, UctStatistic, UctStatistic, RandomHeuristic>::search for T independent trees
  * (mcts/mcts.h:133-141,166-221,294-333; mcts/stage_node.h:167-271). See mamcts_search_* below. */
 
+/* Tree storage of the device-resident search.
+ * CLASSIC: one fixed-size record per node (any number of agents, any depth).
+ * COMPACT: nodes that were never selected again keep only their heuristic values (16 B for 2
+ *          agents) and are promoted to a full record on their second selection; needs a direct child
+ *          table (2 agents) and trees no deeper than 64 levels. Same results, a third of the memory.
+ * AUTO   : COMPACT where possible, else CLASSIC. */
+#define MAMCTS_LAYOUT_AUTO 0
+#define MAMCTS_LAYOUT_CLASSIC 1
+#define MAMCTS_LAYOUT_COMPACT 2
+
 typedef struct mamcts_search_config {
   int32_t env;                 /* MAMCTS_ENV_* */
   int32_t action_source;       /* MAMCTS_SRC_REFERENCE_CONST or MAMCTS_SRC_PHILOX */
@@ -277,6 +287,11 @@ typedef struct mamcts_search_config {
   uint32_t rollouts_per_leaf;  /* K >= 1 (K > 1 only with PHILOX) */
   uint32_t max_nodes_per_tree; /* arena size; iterations stop expanding past it like
                                   MAX_NUMBER_OF_NODES (mcts/stage_node.h:184) */
+  uint32_t layout;             /* MAMCTS_LAYOUT_*: how a tree is stored in HBM */
+  uint32_t max_inner_nodes_per_tree; /* compact layout: records for nodes visited more than once;
+                                  0 = max_nodes_per_tree (always enough). A 10 000-iteration C2 tree
+                                  needs about 2 500 (max 2 734 over 120 trees). A tree that runs out
+                                  makes every later read-back fail with MAMCTS_ERR_NOMEM. */
   uint64_t philox_seed;
   mamcts_params mcts;
   mamcts_crossing_params crossing;

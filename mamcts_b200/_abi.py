@@ -138,6 +138,9 @@ class UctStats(C.Structure):
     ]
 
 
+LAYOUT_AUTO, LAYOUT_CLASSIC, LAYOUT_COMPACT = 0, 1, 2
+
+
 class SearchConfig(C.Structure):
     _fields_ = [
         ("env", C.c_int32),
@@ -146,6 +149,8 @@ class SearchConfig(C.Structure):
         ("first_tree_id", C.c_uint32),
         ("rollouts_per_leaf", C.c_uint32),
         ("max_nodes_per_tree", C.c_uint32),
+        ("layout", C.c_uint32),
+        ("max_inner_nodes_per_tree", C.c_uint32),
         ("philox_seed", C.c_uint64),
         ("mcts", Params),
         ("crossing", CrossingParams),

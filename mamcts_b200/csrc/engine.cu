@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -48,6 +49,50 @@ int ensure_scratch(mamcts_engine* e, size_t bytes) { return grow(e, &e->scratch,
 int ensure_staging(mamcts_engine* e, size_t bytes) { return grow(e, &e->staging, &e->staging_bytes, bytes, false); }
 int ensure_pinned(mamcts_engine* e, size_t bytes) { return grow(e, &e->pinned, &e->pinned_bytes, bytes, true); }
 
+// One thread: the sequence is a chain of dependent, individually rounded multiplications
+// (reference random_heuristic.h:46,71,85,88), a few microseconds for the default cap of 1000.
+__global__ void discount_table_kernel(double gamma, double inv_n_ego, uint32_t len, double* tab) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double m = gamma, prob = 1.0;      // :46, :48
+  for (uint32_t k = 0; k < len; ++k) {
+    const double m1 = __dmul_rn(gamma, m);   // :71
+    tab[k] = m1;
+    tab[len + k] = prob;                     // prob after k steps
+    m = __dmul_rn(m1, gamma);                // :85
+    prob = __dmul_rn(prob, inv_n_ego);       // :88
+  }
+}
+
+int fill_discount_table(mamcts_engine* e, double gamma, double inv_n_ego, uint32_t max_steps, double* dst) {
+  discount_table_kernel<<<1, 32, 0, e->stream>>>(gamma, inv_n_ego, max_steps + 1, dst);
+  e->launches++;
+  MAMCTS_CUDA(e, cudaGetLastError());
+  return MAMCTS_OK;
+}
+
+int ensure_discount_table(mamcts_engine* e, double gamma, double inv_n_ego, uint32_t max_steps,
+                          const double** tab, uint32_t* len) {
+  const uint32_t need = max_steps + 1;
+  const bool same = e->disc && e->disc_len == need &&
+                    std::memcmp(&e->disc_gamma, &gamma, sizeof(double)) == 0 &&
+                    std::memcmp(&e->disc_inv, &inv_n_ego, sizeof(double)) == 0;
+  if (!same) {
+    if (e->disc_len < need || !e->disc) {
+      // the old table may still be read by kernels in flight on the stream
+      if (e->disc) { MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream)); MAMCTS_CUDA(e, cudaFree(e->disc)); e->disc = nullptr; }
+      MAMCTS_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&e->disc), sizeof(double) * 2 * (size_t)need));
+    }
+    int rc = fill_discount_table(e, gamma, inv_n_ego, max_steps, e->disc);
+    if (rc != MAMCTS_OK) return rc;
+    e->disc_len = need;
+    e->disc_gamma = gamma;
+    e->disc_inv = inv_n_ego;
+  }
+  *tab = e->disc;
+  *len = need;
+  return MAMCTS_OK;
+}
+
 }  // namespace mamcts
 
 using namespace mamcts;
@@ -73,6 +118,10 @@ int mamcts_create(const mamcts_config* cfg, mamcts_engine** out) {
   cudaDeviceProp prop;
   MAMCTS_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
   e->num_sms = prop.multiProcessorCount;
+  if (const char* g = std::getenv("MAMCTS_L2_FETCH_GRANULARITY")) {   // experiment knob (profiles/)
+    const int v = std::atoi(g);
+    if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+  }
   if (prop.major < 10) {
     std::string msg = "mamcts_create: device " + std::string(prop.name) +
                       " is not sm_100-class; this library is compiled for sm_100a only";
@@ -94,6 +143,7 @@ void mamcts_destroy(mamcts_engine* e) {
   if (e->scratch) cudaFree(e->scratch);
   if (e->staging) cudaFree(e->staging);
   if (e->pinned) cudaFreeHost(e->pinned);
+  if (e->disc) cudaFree(e->disc);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }

@@ -23,6 +23,10 @@ struct mamcts_engine {
   size_t staging_bytes = 0;
   void* pinned = nullptr;   // pinned host staging
   size_t pinned_bytes = 0;
+  // discount / probability tables of the rollout (see ensure_discount_table)
+  double* disc = nullptr;
+  uint32_t disc_len = 0;
+  double disc_gamma = 0.0, disc_inv = 0.0;
   // NCCL (loaded lazily with dlopen; see comm.cu)
   void* nccl_comm = nullptr;
   int world_size = 1;
@@ -54,6 +58,18 @@ struct Stager {
   explicit Stager(mamcts_engine* eng) : e(eng) {}
   static size_t align(size_t n) { return (n + 255) & ~size_t(255); }
 };
+
+// The rollout's discount sequence depends only on (gamma, 1/nA_ego, step index): m1[k] = the weight
+// the k-th step's reward is multiplied with (random_heuristic.h:71-72,85) and prob[k] = (1/nA_ego)^k
+// (:88), both produced by the reference's own chain of individually rounded multiplications. They are
+// tabulated once per parameter set by a one-thread kernel, so that the step loops do no FP64 work
+// unless a reward is non-zero. Layout: tab[0, len) = m1, tab[len, 2 len) = prob; len = max steps + 1.
+// Writes the device pointer to *tab (owned by the engine, valid until the next call with other
+// parameters on the same engine stream).
+int ensure_discount_table(mamcts_engine* e, double gamma, double inv_n_ego, uint32_t max_steps,
+                          const double** tab, uint32_t* len);
+// Same table into caller-owned device memory of 2 * (max_steps + 1) doubles.
+int fill_discount_table(mamcts_engine* e, double gamma, double inv_n_ego, uint32_t max_steps, double* dst);
 
 inline int grid_for(const mamcts_engine* e, int blocks_per_sm) { return e->num_sms * blocks_per_sm; }
 

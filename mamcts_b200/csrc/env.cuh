@@ -4,6 +4,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "mamcts_b200.h"
+
 namespace mamcts {
 
 // Everything execute() reads that is constant over a launch.
@@ -18,7 +20,37 @@ struct EnvParams {
   uint32_t n_other_actions;
   // SimpleState (reference test/uct/simple_state.h:16)
   int32_t win_len, lose_len;
+  // CrossingState: the ego reward and cost of a step only depend on (goal, collision, out_of_map);
+  // the 8 possible values are evaluated once on the host in the reference's operation order
+  // (crossing_state.h:146-153) and looked up with index goal | collision << 1 | out_of_map << 2.
+  double r_tab[8], c_tab[8];
 };
+
+// Fills every CrossingState field of EnvParams from the public parameter struct.
+inline void make_crossing_env(const mamcts_crossing_params& cp, EnvParams& ep) {
+  ep.r_goal = cp.reward_goal_reached;
+  ep.r_coll = cp.reward_collision;
+  ep.r_step = cp.reward_step;
+  ep.min_v_ego = cp.min_velocity_ego;
+  ep.crossing_point = (cp.chain_length - 1) / 2 + 1;   // CROSSING_POINT(), crossing_state_parameters.h:28
+  ep.goal_pos = cp.ego_goal_pos;
+  ep.cost_only_collision = cp.cost_only_collision;
+  ep.n_ego_actions = (uint32_t)(cp.max_velocity_ego - cp.min_velocity_ego + 1);
+  ep.n_other_actions = cp.num_other_actions;
+  for (int f = 0; f < 8; ++f) {
+    const bool goal = f & 1, coll = f & 2, oob = f & 4;
+    // :146-148 evaluated left to right in double; volatile keeps every product and sum individually
+    // rounded whatever the host compiler's contraction setting
+    volatile double t0 = (double)(int)goal * ep.r_goal;
+    volatile double t1 = (double)(int)coll * ep.r_coll;
+    volatile double r = t0 + t1;
+    volatile double t2 = ep.r_coll * (double)(int)oob;
+    r = r + t2;
+    r = r + ep.r_step;
+    ep.r_tab[f] = r;
+    ep.c_tab[f] = cp.cost_only_collision ? (double)(int)coll : -r;   // :149-153
+  }
+}
 
 // CrossingState<int> with NO other agents. Positions / last actions live in registers.
 template <int NO>
@@ -60,13 +92,11 @@ struct CrossingEnv {
     s.last[0] = v_ego;
     const bool goal = (new_x >= p.goal_pos) & !coll;       // :142
     s.flags = (uint32_t)(goal | coll | oob) | ((uint32_t)goal << 1) | ((uint32_t)coll << 2);  // :144
-    // :146-148 evaluated left to right in double (bool -> double products keep signed zeros)
-    double r = __dadd_rn(__dmul_rn((double)(int)goal, p.r_goal), __dmul_rn((double)(int)coll, p.r_coll));
-    r = __dadd_rn(r, __dmul_rn(p.r_coll, (double)(int)oob));
-    r = __dadd_rn(r, p.r_step);
-    r_ego = r;
+    // :146-153: one of 8 host-evaluated values (see EnvParams::r_tab)
+    const uint32_t f = (uint32_t)goal | ((uint32_t)coll << 1) | ((uint32_t)oob << 2);
+    r_ego = p.r_tab[f];
     r_other = 0.0;                                         // rewards[1..] stay 0 (:145 resize)
-    cost = p.cost_only_collision ? (double)(int)coll : -r; // :149-153
+    cost = p.c_tab[f];
   }
 };
 

@@ -39,7 +39,8 @@ struct RolloutParams {
   const uint32_t* stream_lo;
   uint32_t stream_hi_base, stream_lo_base;
   // mcts
-  double gamma;
+  const double* disc;      // [0, disc_len): reward weight of step k; [disc_len, 2 disc_len): (1/nA_ego)^k
+  uint32_t disc_len;
   uint32_t rh_cap, max_depth;
   EnvParams env;
   // per-rollout outputs (device); index r = leaf*K + k; other_ret / final_* are SoA with stride total
@@ -72,11 +73,14 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
   uint32_t rid = blockIdx.x * blockDim.x + threadIdx.x;
 
   typename Env::State st;
-  double m = 0.0, ego = 0.0, other = 0.0, cost = 0.0, prob = 1.0;
+  // Return accumulation (random_heuristic.h:71-88) without per-step FP64 work: the weight of step k
+  // and (1/nA_ego)^k come from the table (engine.h: ensure_discount_table), and adding a zero reward
+  // or cost is the identity on an accumulator that started at +0.0 (it can never hold -0.0), so those
+  // additions are skipped; other agents' returns are ASSIGNED (:75), so only the last step matters.
+  double ego = 0.0, cost = 0.0, r_other_last = 0.0;
   uint32_t it = 0, depth = 0, cap = 0, leaf = 0, s_lo = 0, s_hi = 0;
   bool has = false, fin = true;
   unsigned long long lane_steps = 0;
-  const double inv_n_ego = 1.0 / (double)Env::num_actions(p.env, 0);  // random_heuristic.h:88
 
   auto load = [&]() {
     has = rid < p.total;
@@ -95,13 +99,14 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
       s_hi = p.stream_hi ? __ldg(p.stream_hi + leaf) : p.stream_hi_base;
       s_lo = p.stream_lo ? __ldg(p.stream_lo + leaf) + (rid - leaf * p.K) : p.stream_lo_base + rid;
     }
-    m = p.gamma;   // random_heuristic.h:46
-    ego = 0.0; other = 0.0; cost = 0.0; prob = 1.0; it = 0;
+    ego = 0.0; cost = 0.0; r_other_last = 0.0; it = 0;   // random_heuristic.h:36-49
     fin = Env::terminal(p.env, st) | (it >= cap) | (depth >= p.max_depth);  // :51-54
   };
 
   auto finalize = [&]() {
     // random_heuristic.h:95-101
+    const double prob = __ldg(p.disc + p.disc_len + it);
+    const double other = it ? __dmul_rn(__ldg(p.disc + it - 1), r_other_last) : 0.0;  // :73-77
     const double ego_out = __dmul_rn(ego, prob);
     const double cost_out = Env::kHasCost ? __dmul_rn(cost, prob) : 0.0;
     if (p.ego_ret) p.ego_ret[rid] = ego_out;
@@ -171,12 +176,9 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
         double r_ego, r_other, c;
         Env::step(p.env, st, act, r_ego, r_other, c);
         if (PARITY && p.trace && it < p.trace_stride) p.trace[(size_t)rid * p.trace_stride + it] = r_ego;
-        m = __dmul_rn(p.gamma, m);                 // :71
-        ego = __dadd_rn(ego, __dmul_rn(m, r_ego)); // :72
-        other = __dmul_rn(m, r_other);             // :73-77 (assigned, not accumulated)
-        if (Env::kHasCost) cost = __dadd_rn(cost, c);  // :79-84
-        m = __dmul_rn(m, p.gamma);                 // :85
-        prob = __dmul_rn(prob, inv_n_ego);         // :88
+        if (r_ego != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it), r_ego));  // :71-72
+        r_other_last = r_other;                                                        // :73-77
+        if (Env::kHasCost && c != 0.0) cost = __dadd_rn(cost, c);                      // :79-84
         it += 1;                                   // :89
         depth += 1;                                // :90
         fin = Env::terminal(p.env, st) | (it >= cap) | (depth >= p.max_depth);
@@ -357,7 +359,14 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   p.stream_lo = stg.dev<const uint32_t>(t_slo);
   p.stream_hi_base = src->stream_hi_base;
   p.stream_lo_base = src->stream_lo_base;
-  p.gamma = mp->discount_factor;
+  {
+    const uint32_t n_ego = (env_kind == MAMCTS_ENV_SIMPLE) ? 2u : ep.n_ego_actions;
+    const uint32_t max_steps = std::min(mp->rh_max_number_of_iterations, mp->max_search_depth);
+    if (max_steps > (1u << 24))
+      return fail(e, MAMCTS_ERR_UNSUPPORTED, "rollout: min(random_heuristic.MAX_NUMBER_OF_ITERATIONS, MAX_SEARCH_DEPTH) above 2^24");
+    rc = ensure_discount_table(e, mp->discount_factor, 1.0 / (double)n_ego, max_steps, &p.disc, &p.disc_len);
+    if (rc != MAMCTS_OK) return rc;
+  }
   p.rh_cap = mp->rh_max_number_of_iterations;
   p.max_depth = mp->max_search_depth;
   p.env = ep;
@@ -425,15 +434,7 @@ int mamcts_rollout_crossing_i32(mamcts_engine* e, const mamcts_params* mp,
     return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_rollout_crossing_i32: 1..15 other agents supported");
   EnvParams ep;
   std::memset(&ep, 0, sizeof(ep));
-  ep.r_goal = cp->reward_goal_reached;
-  ep.r_coll = cp->reward_collision;
-  ep.r_step = cp->reward_step;
-  ep.min_v_ego = cp->min_velocity_ego;
-  ep.crossing_point = (cp->chain_length - 1) / 2 + 1;
-  ep.goal_pos = cp->ego_goal_pos;
-  ep.cost_only_collision = cp->cost_only_collision;
-  ep.n_ego_actions = (uint32_t)(cp->max_velocity_ego - cp->min_velocity_ego + 1);
-  ep.n_other_actions = cp->num_other_actions;
+  make_crossing_env(*cp, ep);
   if (ep.n_ego_actions == 0 || ep.n_ego_actions > MAMCTS_MAX_ACTIONS || ep.n_other_actions == 0 ||
       ep.n_other_actions > MAMCTS_MAX_ACTIONS)
     return fail(e, MAMCTS_ERR_INVALID, "mamcts_rollout_crossing_i32: action counts out of range");

@@ -20,6 +20,7 @@
 
 #include "engine.h"
 #include "root_merge.h"
+#include "search_compact.cuh"
 #include "search_kernel.cuh"
 
 // Type-erased handle behind the C ABI; one concrete SearchT per compiled (environment, action-count,
@@ -36,14 +37,29 @@ struct mamcts_search {
   uint32_t* d_tree_iters = nullptr;
   mamcts::SearchTables* d_tab = nullptr;
   double* d_log = nullptr;
+  double* d_disc = nullptr;
   unsigned long long* d_counters = nullptr;
   int32_t* d_root_x = nullptr;
+  // compact (two-tier) layout, search_compact.cuh
+  void* d_inner = nullptr;
+  void* d_leaves = nullptr;
+  uint32_t* d_tree_inner = nullptr;
+  uint32_t* d_tree_leaves = nullptr;
+  uint32_t max_inner = 0;
   uint32_t iters_done = 0;
   int block_threads = mamcts::kSearchThreads;
 
   virtual ~mamcts_search() {}
-  virtual size_t node_bytes() const = 0;
+  virtual size_t node_bytes() const = 0;     // bytes of the record that carries the statistics
+  virtual size_t leaf_bytes() const { return 0; }
   virtual bool uses_hash() const = 0;
+  virtual bool is_compact() const { return false; }
+  // first record (the root) of a tree and the distance between consecutive trees' roots
+  virtual const char* root_record(uint32_t tree) const {
+    return static_cast<const char*>(d_nodes) + node_bytes() * (size_t)tree * p.max_nodes;
+  }
+  // canonical depth-first export of one tree (mamcts_search_dump_tree)
+  virtual int dump(uint32_t tree, double* records, uint32_t capacity_records, uint32_t* num_records) = 0;
   virtual int launch_reset() = 0;
   virtual int launch_run(uint32_t iterations) = 0;
   // host-side views of a node record copied back from the device
@@ -56,8 +72,14 @@ struct mamcts_search {
 
 namespace mamcts {
 
+static int dump_classic(mamcts_search* s, uint32_t tree, double* records, uint32_t capacity_records,
+                        uint32_t* num_records);
+
 template <class Env, int NE, int NA, int NCHILD, class CIDX>
 struct SearchT final : public mamcts_search {
+  int dump(uint32_t tree, double* records, uint32_t capacity_records, uint32_t* num_records) override {
+    return dump_classic(this, tree, records, capacity_records, num_records);
+  }
   using Node = NodeRec<Env, NE, NA, NCHILD, CIDX>;
 
   size_t node_bytes() const override { return sizeof(Node); }
@@ -131,21 +153,193 @@ struct SearchT final : public mamcts_search {
   }
 };
 
+// Compact (two-tier) layout: search_compact.cuh.
+template <class Env, int NE, int NA, int NCHILD, class CIDX>
+struct SearchC final : public mamcts_search {
+  using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX>;
+  using Leaf = LeafRec<Env::A>;
+
+  size_t node_bytes() const override { return sizeof(Inner); }
+  size_t leaf_bytes() const override { return sizeof(Leaf); }
+  bool uses_hash() const override { return false; }
+  bool is_compact() const override { return true; }
+  const char* root_record(uint32_t tree) const override {
+    return static_cast<const char*>(d_inner) + sizeof(Inner) * (size_t)tree * max_inner;
+  }
+
+  int launch_reset() override {
+    const uint32_t T = cfg.num_trees;
+    MAMCTS_CUDA(e, cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
+    search_compact_reset_kernel<Env, NE, NA, NCHILD, CIDX><<<(T + 255) / 256, 256, 0, e->stream>>>(
+        d_inner, d_tree_nodes, d_tree_iters, d_tree_inner, d_tree_leaves, T, max_inner);
+    e->launches++;
+    MAMCTS_CUDA(e, cudaGetLastError());
+    iters_done = 0;
+    return MAMCTS_OK;
+  }
+
+  int launch_run(uint32_t iterations) override {
+    SearchParams q = p;
+    q.iterations = iterations;
+    CompactParams c;
+    c.inner = d_inner; c.leaves = d_leaves; c.tree_inner = d_tree_inner; c.tree_leaves = d_tree_leaves;
+    c.max_inner = max_inner; c.root_x = d_root_x;
+    const uint32_t T = cfg.num_trees;
+    const uint32_t trees_per_block = (uint32_t)(block_threads / 32) * q.lanes_per_warp;
+    const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
+    if (cfg.action_source == MAMCTS_SRC_PHILOX)
+      search_compact_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_PHILOX><<<grid, block_threads, 0, e->stream>>>(q, c);
+    else
+      search_compact_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_REFERENCE_CONST><<<grid, block_threads, 0, e->stream>>>(q, c);
+    e->launches++;
+    MAMCTS_CUDA(e, cudaGetLastError());
+    return MAMCTS_OK;
+  }
+
+  void read_header(const void* node, uint32_t* parent, uint32_t* depth, uint32_t* visits,
+                   uint8_t* ja) const override {
+    const Inner* nd = static_cast<const Inner*>(node);
+    *parent = nd->parent;
+    *depth = 0;  // not stored: the export derives it
+    *visits = nd->visit_count;
+    for (int a = 0; a < Env::A; ++a) ja[a] = nd->ja[a];
+  }
+
+  void read_stat(const void* node, uint32_t agent, double* value, double* latest, uint32_t* visits,
+                 uint32_t* nexp, double* q, uint32_t* n) const override {
+    const Inner* nd = static_cast<const Inner*>(node);
+    if (agent == 0) SearchT<Env, NE, NA, NCHILD, CIDX>::template read_stat_rec<NE>(nd->ego, value, latest, visits, nexp, q, n);
+    else SearchT<Env, NE, NA, NCHILD, CIDX>::template read_stat_rec<NA>(nd->oth[agent - 1], value, latest, visits, nexp, q, n);
+  }
+
+  void root_gather(RootGather* g) const override {
+    const char* base = static_cast<const char*>(d_inner);
+    const size_t tree_bytes = sizeof(Inner) * (size_t)max_inner;
+    g->q = reinterpret_cast<const double*>(base + offsetof(Inner, ego) + offsetof(StatRec<NE>, Q));
+    g->n = reinterpret_cast<const uint32_t*>(base + offsetof(Inner, ego) + offsetof(StatRec<NE>, n));
+    g->visits = reinterpret_cast<const uint32_t*>(base + offsetof(Inner, ego) + offsetof(StatRec<NE>, N));
+    g->root_slot = nullptr;
+    g->stride_q = tree_bytes / sizeof(double);
+    g->stride_n = tree_bytes / sizeof(uint32_t);
+    g->stride_v = tree_bytes / sizeof(uint32_t);
+    g->max_actions = NE;
+  }
+
+  // Export (like StageNode::printTree, reference stage_node.h:322-391): depth-first from the root through
+  // the child tables, children in ascending joint-action code; a leaf record is written out as the
+  // node the reference would hold for it (visit_count 0, N = 1, V = G = h, nothing expanded).
+  int dump(uint32_t tree, double* records, uint32_t capacity_records, uint32_t* num_records) override {
+    uint32_t ni = 0, nl = 0;
+    MAMCTS_CUDA(e, cudaMemcpyAsync(&ni, d_tree_inner + tree, sizeof(ni), cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaMemcpyAsync(&nl, d_tree_leaves + tree, sizeof(nl), cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+    std::vector<Inner> in(ni);
+    std::vector<Leaf> lf(nl ? nl : 1);
+    MAMCTS_CUDA(e, cudaMemcpyAsync(in.data(), root_record(tree), sizeof(Inner) * ni, cudaMemcpyDeviceToHost, e->stream));
+    if (nl)
+      MAMCTS_CUDA(e, cudaMemcpyAsync(lf.data(), static_cast<const char*>(d_leaves) + sizeof(Leaf) * (size_t)tree * p.max_nodes,
+                                     sizeof(Leaf) * nl, cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+    constexpr uint32_t A = Env::A;
+    const uint32_t max_actions = std::max(p.n_ego, p.n_oth);
+    const uint32_t stride = 4 + A * (3 + 2 * max_actions);
+    uint32_t count = 0;
+    auto code_of = [&](uint32_t slot) {   // slot = ja[0] * NA + ja[1]  ->  sum_a ja[a] * max_actions^a
+      const uint32_t j0 = slot / NA, j1 = slot % NA;
+      return (double)j0 + (double)max_actions * (double)j1;
+    };
+    struct Kid { double code; uint32_t entry; };
+    auto kids_of = [&](const Inner& nd) {
+      std::vector<Kid> k;
+      for (int sl = 0; sl < NCHILD; ++sl) if (nd.child[sl]) k.push_back({code_of((uint32_t)sl), (uint32_t)nd.child[sl]});
+      std::sort(k.begin(), k.end(), [](const Kid& a, const Kid& b) { return a.code < b.code; });
+      return k;
+    };
+    auto emit_inner = [&](uint32_t i, uint32_t depth, double code, size_t nkids) {
+      if (count < capacity_records) {
+        double* r = records + (size_t)count * stride;
+        r[0] = depth; r[1] = code; r[2] = in[i].visit_count; r[3] = (double)nkids;
+        for (uint32_t a = 0; a < A; ++a) {
+          double* o = r + 4 + a * (3 + 2 * max_actions);
+          double v, l, qq[MAMCTS_MAX_ACTIONS];
+          uint32_t vis, nexp, cnt[MAMCTS_MAX_ACTIONS + 1];
+          read_stat(&in[i], a, &v, &l, &vis, &nexp, qq, cnt);
+          const uint32_t nact = a == 0 ? p.n_ego : p.n_oth;
+          const uint32_t mask = tab.exp_mask[a == 0 ? 0 : 1][std::min(nexp, nact)];
+          o[0] = vis; o[1] = v; o[2] = l;
+          for (uint32_t k = 0; k < max_actions; ++k) {
+            const bool ex = k < nact && ((mask >> k) & 1u);
+            o[3 + k] = ex ? (double)cnt[k] : -1.0;
+            o[3 + max_actions + k] = ex ? qq[k] : 0.0;
+          }
+        }
+      }
+      ++count;
+    };
+    auto emit_leaf = [&](uint32_t l, uint32_t depth, double code) {
+      if (count < capacity_records) {
+        double* r = records + (size_t)count * stride;
+        r[0] = depth; r[1] = code; r[2] = 0.0; r[3] = 0.0;
+        for (uint32_t a = 0; a < A; ++a) {
+          double* o = r + 4 + a * (3 + 2 * max_actions);
+          o[0] = 1.0; o[1] = lf[l].h[a]; o[2] = lf[l].h[a];
+          for (uint32_t k = 0; k < max_actions; ++k) { o[3 + k] = -1.0; o[3 + max_actions + k] = 0.0; }
+        }
+      }
+      ++count;
+    };
+    struct Frame { std::vector<Kid> kids; size_t next; uint32_t depth; };
+    std::vector<Frame> stack;
+    {
+      auto k = kids_of(in[0]);
+      emit_inner(0, 0, -1.0, k.size());
+      stack.push_back({std::move(k), 0, 0});
+    }
+    while (!stack.empty()) {
+      Frame& top = stack.back();
+      if (top.next >= top.kids.size()) { stack.pop_back(); continue; }
+      const Kid kid = top.kids[top.next++];
+      const uint32_t d = top.depth + 1;
+      if (kid.entry & 1u) {
+        const uint32_t i = kid.entry >> 1;
+        if (i >= ni) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: corrupt child table");
+        auto k = kids_of(in[i]);
+        emit_inner(i, d, kid.code, k.size());
+        stack.push_back({std::move(k), 0, d});
+      } else {
+        const uint32_t l = (kid.entry >> 1) - 1u;
+        if (l >= nl) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: corrupt child table");
+        emit_leaf(l, d, kid.code);
+      }
+    }
+    *num_records = count;
+    return MAMCTS_OK;
+  }
+};
+
 template <class Env, int NE, int NA, int NCHILD>
-static mamcts_search* make_search_cidx(uint32_t max_nodes) {
+static mamcts_search* make_search_cidx(uint32_t max_nodes, bool compact) {
+  if (NCHILD > 0 && compact) {
+    if constexpr (NCHILD > 0) {
+      if (max_nodes + 1 < 32768) return new SearchC<Env, NE, NA, NCHILD, uint16_t>();
+      return new SearchC<Env, NE, NA, NCHILD, uint32_t>();
+    }
+  }
   if (NCHILD > 0 && max_nodes <= 65535) return new SearchT<Env, NE, NA, NCHILD, uint16_t>();
   return new SearchT<Env, NE, NA, NCHILD, uint32_t>();
 }
 
 static mamcts_search* make_search(const mamcts_search_config& cfg, uint32_t n_ego, uint32_t n_oth,
                                   uint32_t max_nodes) {
-  if (cfg.env == MAMCTS_ENV_SIMPLE) return make_search_cidx<SimpleEnv, 2, 2, 4>(max_nodes);
+  // layout: 0 = automatic (compact wherever a direct child table exists), 1 = classic, 2 = compact
+  const bool compact = cfg.layout != MAMCTS_LAYOUT_CLASSIC;
+  if (cfg.env == MAMCTS_ENV_SIMPLE) return make_search_cidx<SimpleEnv, 2, 2, 4>(max_nodes, compact);
   if (n_ego == 4 && n_oth == 7) {
     switch (cfg.crossing.num_other_agents) {
-      case 1: return make_search_cidx<CrossingEnv<1>, 4, 7, 28>(max_nodes);
-      case 2: return make_search_cidx<CrossingEnv<2>, 4, 7, 0>(max_nodes);
-      case 3: return make_search_cidx<CrossingEnv<3>, 4, 7, 0>(max_nodes);
-      case 7: return make_search_cidx<CrossingEnv<7>, 4, 7, 0>(max_nodes);
+      case 1: return make_search_cidx<CrossingEnv<1>, 4, 7, 28>(max_nodes, compact);
+      case 2: return make_search_cidx<CrossingEnv<2>, 4, 7, 0>(max_nodes, false);
+      case 3: return make_search_cidx<CrossingEnv<3>, 4, 7, 0>(max_nodes, false);
+      case 7: return make_search_cidx<CrossingEnv<7>, 4, 7, 0>(max_nodes, false);
       default: return nullptr;
     }
   }
@@ -156,269 +350,35 @@ static void free_search(mamcts_search* s) {
   if (!s) return;
   cudaSetDevice(s->e->device);
   cudaStreamSynchronize(s->e->stream);
+  cudaFree(s->d_inner); cudaFree(s->d_leaves); cudaFree(s->d_tree_inner); cudaFree(s->d_tree_leaves);
   cudaFree(s->d_nodes); cudaFree(s->d_hash); cudaFree(s->d_tree_nodes); cudaFree(s->d_tree_iters);
-  cudaFree(s->d_tab); cudaFree(s->d_log); cudaFree(s->d_counters); cudaFree(s->d_root_x);
+  cudaFree(s->d_tab); cudaFree(s->d_log); cudaFree(s->d_disc); cudaFree(s->d_counters); cudaFree(s->d_root_x);
   delete s;
+}
+
+// Device-side failures of the compact layout are counted (search_compact.cuh); every read-back
+// reports them instead of returning statistics of an unfinished search.
+static int check_search_health(mamcts_search* s) {
+  if (!s->is_compact()) return MAMCTS_OK;
+  mamcts_engine* e = s->e;
+  unsigned long long h[2] = {0, 0};
+  MAMCTS_CUDA(e, cudaMemcpyAsync(h, s->d_counters + 6, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (h[0])
+    return fail(e, MAMCTS_ERR_NOMEM, "mamcts_search: " + std::to_string(h[0]) + " tree(s) ran out of inner node records; "
+                "raise mamcts_search_config.max_inner_nodes_per_tree (0 = one per node, always enough)");
+  if (h[1])
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search: " + std::to_string(h[1]) + " tree(s) grew deeper than 64 levels; "
+                "use layout = MAMCTS_LAYOUT_CLASSIC for such searches");
+  return MAMCTS_OK;
 }
 
 }  // namespace mamcts
 
-using namespace mamcts;
-
-extern "C" {
-
-int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, const int32_t* root_x,
-                         const int32_t* root_last_action, mamcts_search** out) {
-  (void)root_last_action;  // last_action does not influence UctStatistic searches (no hypothesis policy)
-  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_create: null engine");
-  std::lock_guard<std::mutex> lock(e->mu);
-  if (!cfg || !root_x || !out) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: null argument");
-  if (cfg->num_trees == 0) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: num_trees == 0");
-  if (cfg->action_source != MAMCTS_SRC_PHILOX && cfg->action_source != MAMCTS_SRC_REFERENCE_CONST)
-    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: action source must be REFERENCE_CONST or PHILOX");
-  if (cfg->rollouts_per_leaf != 1)
-    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: rollouts_per_leaf must be 1 in this build");
-  const mamcts_params& mp = cfg->mcts;
-  if (!(mp.uct_pw_k >= 0.0) || !(mp.uct_pw_alpha >= 0.0))
-    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: progressive widening k, alpha must be >= 0");
-  if (mp.max_number_of_iterations == 0) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: zero iterations");
-  uint32_t n_ego, n_oth, A;
-  EnvParams ep;
-  std::memset(&ep, 0, sizeof(ep));
-  if (cfg->env == MAMCTS_ENV_SIMPLE) {
-    n_ego = n_oth = 2; A = 2;
-    ep.win_len = cfg->simple.winning_state_length;
-    ep.lose_len = cfg->simple.loosing_state_length;
-    ep.n_ego_actions = ep.n_other_actions = 2;
-  } else if (cfg->env == MAMCTS_ENV_CROSSING_I32) {
-    const mamcts_crossing_params& cp = cfg->crossing;
-    n_ego = (uint32_t)(cp.max_velocity_ego - cp.min_velocity_ego + 1);
-    n_oth = cp.num_other_actions;
-    A = cp.num_other_agents + 1;
-    ep.r_goal = cp.reward_goal_reached; ep.r_coll = cp.reward_collision; ep.r_step = cp.reward_step;
-    ep.min_v_ego = cp.min_velocity_ego;
-    ep.crossing_point = (cp.chain_length - 1) / 2 + 1;
-    ep.goal_pos = cp.ego_goal_pos;
-    ep.cost_only_collision = cp.cost_only_collision;
-    ep.n_ego_actions = n_ego; ep.n_other_actions = n_oth;
-  } else {
-    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: unknown environment");
-  }
-  const uint32_t max_iter = mp.max_number_of_iterations;
-  uint32_t max_nodes = cfg->max_nodes_per_tree;
-  const uint64_t needed = std::min<uint64_t>((uint64_t)mp.max_number_of_nodes + 1, (uint64_t)max_iter + 1);
-  if (max_nodes == 0) max_nodes = (uint32_t)needed;
-  if (max_nodes < needed)
-    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: max_nodes_per_tree below min(MAX_NUMBER_OF_NODES, iterations) + 1");
-
-  mamcts_search* s = make_search(*cfg, n_ego, n_oth, max_nodes);
-  if (!s)
-    return fail(e, MAMCTS_ERR_UNSUPPORTED,
-                "mamcts_search_create: compiled for SimpleState and CrossingState<int> with 4 ego / 7 other "
-                "actions and 1, 2, 3 or 7 other agents");
-  s->e = e;
-  s->cfg = *cfg;
-  s->A = A;
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
-
-  // host tables: widening order (libstdc++), expanded masks, widening thresholds (libm pow), log table
-  SearchTables& tab = s->tab;
-  std::memset(&tab, 0, sizeof(tab));
-  const uint32_t nact[2] = {n_ego, n_oth};
-  for (int cls = 0; cls < 2; ++cls) {
-    uint32_t order[MAMCTS_MAX_ACTIONS];
-    int rc = mamcts_reference_expand_order(mp.random_seed, nact[cls], order);
-    if (rc != MAMCTS_OK) { delete s; return rc; }
-    uint32_t mask = 0;
-    tab.exp_mask[cls][0] = 0;
-    for (uint32_t k = 0; k < nact[cls]; ++k) {
-      tab.order[cls][k] = (uint8_t)order[k];
-      mask |= 1u << order[k];
-      tab.exp_mask[cls][k + 1] = mask;
-      // require_progressive_widening_total (uct_statistic.h:256-262): k <= pw_k * pow(N, pw_alpha);
-      // non-decreasing in N for k, alpha >= 0, so the first N that satisfies it is a threshold.
-      uint32_t thr = 0xFFFFFFFFu;
-      for (uint32_t N = 0; N <= max_iter + 1; ++N) {
-        const double term = mp.uct_pw_k * std::pow((double)N, mp.uct_pw_alpha);
-        if ((double)k <= term) { thr = N; break; }
-      }
-      tab.pw_min_visits[cls][k] = thr;
-    }
-  }
-  std::vector<double> logs((size_t)max_iter + 2);
-  for (size_t N = 0; N < logs.size(); ++N) logs[N] = std::log((double)N);  // log(total_node_visits_)
-
-  uint32_t hcap = 16;
-  if (s->uses_hash()) while (hcap < 2 * max_nodes) hcap <<= 1;
-
-  const uint32_t T = cfg->num_trees;
-  cudaError_t err = cudaSuccess;
-  auto alloc = [&](void** ptr, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(ptr, bytes); };
-  alloc(&s->d_nodes, s->node_bytes() * (size_t)T * max_nodes);
-  alloc((void**)&s->d_hash, s->uses_hash() ? sizeof(uint32_t) * (size_t)T * hcap : 256);
-  alloc((void**)&s->d_tree_nodes, sizeof(uint32_t) * T);
-  alloc((void**)&s->d_tree_iters, sizeof(uint32_t) * T);
-  alloc((void**)&s->d_tab, sizeof(SearchTables));
-  alloc((void**)&s->d_log, sizeof(double) * logs.size());
-  alloc((void**)&s->d_counters, sizeof(unsigned long long) * 8);
-  alloc((void**)&s->d_root_x, sizeof(int32_t) * MAMCTS_MAX_AGENTS);
-  if (err != cudaSuccess) {
-    free_search(s);
-    cudaGetLastError();
-    return fail(e, MAMCTS_ERR_NOMEM, std::string("mamcts_search_create: device allocation failed: ") + cudaGetErrorString(err));
-  }
-  SearchParams& p = s->p;
-  std::memset(&p, 0, sizeof(p));
-  p.nodes = s->d_nodes; p.hash = s->d_hash; p.tree_nodes = s->d_tree_nodes; p.tree_iters = s->d_tree_iters;
-  p.tab = s->d_tab; p.log_table = s->d_log; p.counters = s->d_counters;
-  p.T = T; p.max_nodes = max_nodes; p.hash_mask = hcap - 1; p.first_tree_id = cfg->first_tree_id;
-  p.n_ego = n_ego; p.n_oth = n_oth;
-  p.use_bound_est = mp.use_bound_estimation; p.max_depth = mp.max_search_depth;
-  p.node_budget = mp.max_number_of_nodes; p.rh_cap = mp.rh_max_number_of_iterations;
-  p.key0 = (uint32_t)cfg->philox_seed; p.key1 = (uint32_t)(cfg->philox_seed >> 32);
-  p.gamma = mp.discount_factor; p.two_c = 2 * mp.uct_exploration_constant;
-  p.lb = mp.uct_lower_bound; p.ub = mp.uct_upper_bound;
-  p.env = ep;
-  p.lanes_per_warp = 32;
-  if (const char* v = std::getenv("MAMCTS_SEARCH_LPW")) {
-    const int l = std::atoi(v);
-    if (l >= 1 && l <= 32) p.lanes_per_warp = (uint32_t)l;
-  }
-  if (const char* v = std::getenv("MAMCTS_SEARCH_THREADS")) {
-    const int t = std::atoi(v);
-    if (t >= 32 && t <= kSearchThreads && t % 32 == 0) s->block_threads = t;
-  }
-  s->state_ints = (cfg->env == MAMCTS_ENV_SIMPLE) ? 1 : A;
-  int32_t rx[MAMCTS_MAX_AGENTS] = {0};
-  for (uint32_t i = 0; i < s->state_ints; ++i) rx[i] = root_x[i];
-  err = cudaMemcpyAsync(s->d_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(s->d_log, logs.data(), sizeof(double) * logs.size(), cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(s->d_root_x, rx, sizeof(rx), cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);  // host sources go out of scope
-  if (err != cudaSuccess) { free_search(s); return cuda_fail(e, err, "mamcts_search_create uploads"); }
-  int rc = s->launch_reset();
-  if (rc != MAMCTS_OK) { free_search(s); return rc; }
-  *out = s;
-  return MAMCTS_OK;
-}
-
-int mamcts_search_destroy(mamcts_search* s) {
-  if (!s) return MAMCTS_OK;
-  std::lock_guard<std::mutex> lock(s->e->mu);
-  free_search(s);
-  return MAMCTS_OK;
-}
-
-int mamcts_search_reset(mamcts_search* s, const int32_t* root_x, const int32_t* root_last_action) {
-  (void)root_last_action;
-  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_reset: null handle");
+namespace mamcts {
+static int dump_classic(mamcts_search* s, uint32_t tree, double* records, uint32_t capacity_records,
+                        uint32_t* num_records) {
   mamcts_engine* e = s->e;
-  std::lock_guard<std::mutex> lock(e->mu);
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  if (root_x) {  // NULL: re-root at the state already resident on the device (no copy)
-    int32_t rx[MAMCTS_MAX_AGENTS] = {0};
-    for (uint32_t i = 0; i < s->state_ints; ++i) rx[i] = root_x[i];
-    MAMCTS_CUDA(e, cudaMemcpyAsync(s->d_root_x, rx, sizeof(rx), cudaMemcpyHostToDevice, e->stream));
-    MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
-  }
-  return s->launch_reset();
-}
-
-int mamcts_search_run(mamcts_search* s, uint32_t iterations) {
-  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_run: null handle");
-  mamcts_engine* e = s->e;
-  std::lock_guard<std::mutex> lock(e->mu);
-  if ((uint64_t)s->iters_done + iterations > s->cfg.mcts.max_number_of_iterations)
-    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_run: exceeds MAX_NUMBER_OF_ITERATIONS of the configuration");
-  if (iterations == 0) return MAMCTS_OK;
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  int rc = s->launch_run(iterations);
-  if (rc == MAMCTS_OK) s->iters_done += iterations;
-  return rc;
-}
-
-int mamcts_search_counters(mamcts_search* s, uint64_t* iterations, uint64_t* rollout_steps,
-                           uint64_t* expand_steps, uint64_t* nodes, uint64_t* backup_levels) {
-  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_counters: null handle");
-  mamcts_engine* e = s->e;
-  std::lock_guard<std::mutex> lock(e->mu);
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  unsigned long long h[8];
-  MAMCTS_CUDA(e, cudaMemcpyAsync(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
-  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
-  if (iterations) *iterations = h[0];
-  if (rollout_steps) *rollout_steps = h[1];
-  if (expand_steps) *expand_steps = h[2];
-  if (nodes) *nodes = h[3] + s->cfg.num_trees;  // + the roots
-  if (backup_levels) *backup_levels = h[4];
-  return MAMCTS_OK;
-}
-
-int mamcts_search_exact_ucb_evaluations(mamcts_search* s, uint64_t* count) {
-  if (!s || !count) return fail(s ? s->e : nullptr, MAMCTS_ERR_INVALID, "mamcts_search_exact_ucb_evaluations: null argument");
-  mamcts_engine* e = s->e;
-  std::lock_guard<std::mutex> lock(e->mu);
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  unsigned long long h = 0;
-  MAMCTS_CUDA(e, cudaMemcpyAsync(&h, s->d_counters + 5, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
-  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
-  *count = h;
-  return MAMCTS_OK;
-}
-
-int mamcts_search_root_stats(mamcts_search* s, uint32_t tree, uint32_t agent, double* value,
-                             uint32_t* total_visits, double* q, uint32_t* n, uint32_t* expanded_mask,
-                             uint32_t* num_nodes) {
-  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_root_stats: null handle");
-  mamcts_engine* e = s->e;
-  std::lock_guard<std::mutex> lock(e->mu);
-  if (tree >= s->cfg.num_trees || agent >= s->A) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_root_stats: index out of range");
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  std::vector<char> node(s->node_bytes());
-  const char* src = static_cast<const char*>(s->d_nodes) + s->node_bytes() * (size_t)tree * s->p.max_nodes;
-  MAMCTS_CUDA(e, cudaMemcpyAsync(node.data(), src, node.size(), cudaMemcpyDeviceToHost, e->stream));
-  uint32_t nn = 0;
-  MAMCTS_CUDA(e, cudaMemcpyAsync(&nn, s->d_tree_nodes + tree, sizeof(nn), cudaMemcpyDeviceToHost, e->stream));
-  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
-  double v, l, qq[MAMCTS_MAX_ACTIONS];
-  uint32_t vis, nexp, nn_a[MAMCTS_MAX_ACTIONS + 1];
-  s->read_stat(node.data(), agent, &v, &l, &vis, &nexp, qq, nn_a);
-  const int cls = agent == 0 ? 0 : 1;
-  const uint32_t nact = agent == 0 ? s->p.n_ego : s->p.n_oth;
-  const uint32_t mask = s->tab.exp_mask[cls][std::min(nexp, nact)];
-  if (value) *value = v;
-  if (total_visits) *total_visits = vis;
-  for (uint32_t a = 0; a < nact; ++a) {
-    const bool ex = (mask >> a) & 1u;
-    if (q) q[a] = ex ? qq[a] : 0.0;
-    if (n) n[a] = ex ? nn_a[a] : 0u;
-  }
-  if (expanded_mask) *expanded_mask = mask;
-  if (num_nodes) *num_nodes = nn;
-  return MAMCTS_OK;
-}
-
-int mamcts_search_merge_roots(mamcts_search* s, double* merged_q, uint64_t* merged_n,
-                              uint32_t* merged_occurrences, uint64_t* merged_total_visits,
-                              double* merged_value, uint32_t* best_action) {
-  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_merge_roots: null handle");
-  mamcts_engine* e = s->e;
-  std::lock_guard<std::mutex> lock(e->mu);
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  RootGather g;
-  std::memset(&g, 0, sizeof(g));
-  s->root_gather(&g);
-  return root_merge_device(e, g, s->cfg.num_trees, s->p.n_ego, merged_q, merged_n, merged_occurrences,
-                           merged_total_visits, merged_value, best_action);
-}
-
-int mamcts_search_dump_tree(mamcts_search* s, uint32_t tree, double* records,
-                            uint32_t capacity_records, uint32_t* num_records) {
-  if (!s || !records || !num_records) return fail(s ? s->e : nullptr, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: null argument");
-  mamcts_engine* e = s->e;
-  std::lock_guard<std::mutex> lock(e->mu);
-  if (tree >= s->cfg.num_trees) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: tree out of range");
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
   uint32_t nn = 0;
   MAMCTS_CUDA(e, cudaMemcpyAsync(&nn, s->d_tree_nodes + tree, sizeof(nn), cudaMemcpyDeviceToHost, e->stream));
   MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -484,6 +444,287 @@ int mamcts_search_dump_tree(mamcts_search* s, uint32_t tree, double* records,
   }
   *num_records = count;
   return MAMCTS_OK;
+}
+}  // namespace mamcts
+
+using namespace mamcts;
+
+extern "C" {
+
+int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, const int32_t* root_x,
+                         const int32_t* root_last_action, mamcts_search** out) {
+  (void)root_last_action;  // last_action does not influence UctStatistic searches (no hypothesis policy)
+  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_create: null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!cfg || !root_x || !out) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: null argument");
+  if (cfg->num_trees == 0) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: num_trees == 0");
+  if (cfg->action_source != MAMCTS_SRC_PHILOX && cfg->action_source != MAMCTS_SRC_REFERENCE_CONST)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: action source must be REFERENCE_CONST or PHILOX");
+  if (cfg->layout > MAMCTS_LAYOUT_COMPACT)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: unknown layout");
+  if (cfg->rollouts_per_leaf != 1)
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: rollouts_per_leaf must be 1 in this build");
+  const mamcts_params& mp = cfg->mcts;
+  if (!(mp.uct_pw_k >= 0.0) || !(mp.uct_pw_alpha >= 0.0))
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: progressive widening k, alpha must be >= 0");
+  if (mp.max_number_of_iterations == 0) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: zero iterations");
+  uint32_t n_ego, n_oth, A;
+  EnvParams ep;
+  std::memset(&ep, 0, sizeof(ep));
+  if (cfg->env == MAMCTS_ENV_SIMPLE) {
+    n_ego = n_oth = 2; A = 2;
+    ep.win_len = cfg->simple.winning_state_length;
+    ep.lose_len = cfg->simple.loosing_state_length;
+    ep.n_ego_actions = ep.n_other_actions = 2;
+  } else if (cfg->env == MAMCTS_ENV_CROSSING_I32) {
+    const mamcts_crossing_params& cp = cfg->crossing;
+    n_ego = (uint32_t)(cp.max_velocity_ego - cp.min_velocity_ego + 1);
+    n_oth = cp.num_other_actions;
+    A = cp.num_other_agents + 1;
+    make_crossing_env(cp, ep);
+  } else {
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: unknown environment");
+  }
+  const uint32_t max_iter = mp.max_number_of_iterations;
+  uint32_t max_nodes = cfg->max_nodes_per_tree;
+  const uint64_t needed = std::min<uint64_t>((uint64_t)mp.max_number_of_nodes + 1, (uint64_t)max_iter + 1);
+  if (max_nodes == 0) max_nodes = (uint32_t)needed;
+  if (max_nodes < needed)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: max_nodes_per_tree below min(MAX_NUMBER_OF_NODES, iterations) + 1");
+
+  mamcts_search* s = make_search(*cfg, n_ego, n_oth, max_nodes);
+  if (!s)
+    return fail(e, MAMCTS_ERR_UNSUPPORTED,
+                "mamcts_search_create: compiled for SimpleState and CrossingState<int> with 4 ego / 7 other "
+                "actions and 1, 2, 3 or 7 other agents");
+  if (cfg->layout == MAMCTS_LAYOUT_COMPACT && !s->is_compact()) {
+    delete s;
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: the compact layout needs a direct child table (2 agents)");
+  }
+  s->e = e;
+  s->cfg = *cfg;
+  s->A = A;
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+
+  // host tables: widening order (libstdc++), expanded masks, widening thresholds (libm pow), log table
+  SearchTables& tab = s->tab;
+  std::memset(&tab, 0, sizeof(tab));
+  const uint32_t nact[2] = {n_ego, n_oth};
+  for (int cls = 0; cls < 2; ++cls) {
+    uint32_t order[MAMCTS_MAX_ACTIONS];
+    int rc = mamcts_reference_expand_order(mp.random_seed, nact[cls], order);
+    if (rc != MAMCTS_OK) { delete s; return rc; }
+    uint32_t mask = 0;
+    tab.exp_mask[cls][0] = 0;
+    for (uint32_t k = 0; k < nact[cls]; ++k) {
+      tab.order[cls][k] = (uint8_t)order[k];
+      mask |= 1u << order[k];
+      tab.exp_mask[cls][k + 1] = mask;
+      // require_progressive_widening_total (uct_statistic.h:256-262): k <= pw_k * pow(N, pw_alpha);
+      // non-decreasing in N for k, alpha >= 0, so the first N that satisfies it is a threshold.
+      uint32_t thr = 0xFFFFFFFFu;
+      for (uint32_t N = 0; N <= max_iter + 1; ++N) {
+        const double term = mp.uct_pw_k * std::pow((double)N, mp.uct_pw_alpha);
+        if ((double)k <= term) { thr = N; break; }
+      }
+      tab.pw_min_visits[cls][k] = thr;
+    }
+  }
+  std::vector<double> logs((size_t)max_iter + 2);
+  for (size_t N = 0; N < logs.size(); ++N) logs[N] = std::log((double)N);  // log(total_node_visits_)
+
+  uint32_t hcap = 16;
+  if (s->uses_hash()) while (hcap < 2 * max_nodes) hcap <<= 1;
+
+  const uint32_t T = cfg->num_trees;
+  cudaError_t err = cudaSuccess;
+  auto alloc = [&](void** ptr, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(ptr, bytes); };
+  if (s->is_compact()) {
+    s->max_inner = cfg->max_inner_nodes_per_tree ? std::min(cfg->max_inner_nodes_per_tree, max_nodes) : max_nodes;
+    alloc(&s->d_inner, s->node_bytes() * (size_t)T * s->max_inner);
+    alloc(&s->d_leaves, s->leaf_bytes() * (size_t)T * max_nodes);
+    alloc((void**)&s->d_tree_inner, sizeof(uint32_t) * T);
+    alloc((void**)&s->d_tree_leaves, sizeof(uint32_t) * T);
+  } else {
+    alloc(&s->d_nodes, s->node_bytes() * (size_t)T * max_nodes);
+  }
+  alloc((void**)&s->d_hash, s->uses_hash() ? sizeof(uint32_t) * (size_t)T * hcap : 256);
+  alloc((void**)&s->d_tree_nodes, sizeof(uint32_t) * T);
+  alloc((void**)&s->d_tree_iters, sizeof(uint32_t) * T);
+  alloc((void**)&s->d_tab, sizeof(SearchTables));
+  alloc((void**)&s->d_log, sizeof(double) * logs.size());
+  const uint32_t max_steps = std::min(mp.rh_max_number_of_iterations, mp.max_search_depth);
+  alloc((void**)&s->d_disc, sizeof(double) * 2 * ((size_t)std::min(max_steps, 1u << 24) + 1));
+  alloc((void**)&s->d_counters, sizeof(unsigned long long) * 8);
+  alloc((void**)&s->d_root_x, sizeof(int32_t) * MAMCTS_MAX_AGENTS);
+  if (err == cudaSuccess && max_steps > (1u << 24)) {
+    free_search(s);
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: min(random_heuristic.MAX_NUMBER_OF_ITERATIONS, MAX_SEARCH_DEPTH) above 2^24");
+  }
+  if (err != cudaSuccess) {
+    free_search(s);
+    cudaGetLastError();
+    return fail(e, MAMCTS_ERR_NOMEM, std::string("mamcts_search_create: device allocation failed: ") + cudaGetErrorString(err));
+  }
+  SearchParams& p = s->p;
+  std::memset(&p, 0, sizeof(p));
+  p.nodes = s->d_nodes; p.hash = s->d_hash; p.tree_nodes = s->d_tree_nodes; p.tree_iters = s->d_tree_iters;
+  p.tab = s->d_tab; p.log_table = s->d_log; p.counters = s->d_counters;
+  p.disc = s->d_disc; p.disc_len = max_steps + 1;
+  p.T = T; p.max_nodes = max_nodes; p.hash_mask = hcap - 1; p.first_tree_id = cfg->first_tree_id;
+  p.n_ego = n_ego; p.n_oth = n_oth;
+  p.use_bound_est = mp.use_bound_estimation; p.max_depth = mp.max_search_depth;
+  p.node_budget = mp.max_number_of_nodes; p.rh_cap = mp.rh_max_number_of_iterations;
+  p.key0 = (uint32_t)cfg->philox_seed; p.key1 = (uint32_t)(cfg->philox_seed >> 32);
+  p.gamma = mp.discount_factor; p.two_c = 2 * mp.uct_exploration_constant;
+  p.lb = mp.uct_lower_bound; p.ub = mp.uct_upper_bound;
+  p.env = ep;
+  p.lanes_per_warp = 32;
+  if (const char* v = std::getenv("MAMCTS_SEARCH_LPW")) {
+    const int l = std::atoi(v);
+    if (l >= 1 && l <= 32) p.lanes_per_warp = (uint32_t)l;
+  }
+  if (const char* v = std::getenv("MAMCTS_SEARCH_THREADS")) {
+    const int t = std::atoi(v);
+    if (t >= 32 && t <= kSearchThreads && t % 32 == 0) s->block_threads = t;
+  }
+  s->state_ints = (cfg->env == MAMCTS_ENV_SIMPLE) ? 1 : A;
+  int32_t rx[MAMCTS_MAX_AGENTS] = {0};
+  for (uint32_t i = 0; i < s->state_ints; ++i) rx[i] = root_x[i];
+  err = cudaMemcpyAsync(s->d_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(s->d_log, logs.data(), sizeof(double) * logs.size(), cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(s->d_root_x, rx, sizeof(rx), cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);  // host sources go out of scope
+  if (err != cudaSuccess) { free_search(s); return cuda_fail(e, err, "mamcts_search_create uploads"); }
+  int rc = fill_discount_table(e, mp.discount_factor, 1.0 / (double)n_ego, max_steps, s->d_disc);
+  if (rc == MAMCTS_OK) rc = s->launch_reset();
+  if (rc != MAMCTS_OK) { free_search(s); return rc; }
+  *out = s;
+  return MAMCTS_OK;
+}
+
+int mamcts_search_destroy(mamcts_search* s) {
+  if (!s) return MAMCTS_OK;
+  std::lock_guard<std::mutex> lock(s->e->mu);
+  free_search(s);
+  return MAMCTS_OK;
+}
+
+int mamcts_search_reset(mamcts_search* s, const int32_t* root_x, const int32_t* root_last_action) {
+  (void)root_last_action;
+  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_reset: null handle");
+  mamcts_engine* e = s->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  if (root_x) {  // NULL: re-root at the state already resident on the device (no copy)
+    int32_t rx[MAMCTS_MAX_AGENTS] = {0};
+    for (uint32_t i = 0; i < s->state_ints; ++i) rx[i] = root_x[i];
+    MAMCTS_CUDA(e, cudaMemcpyAsync(s->d_root_x, rx, sizeof(rx), cudaMemcpyHostToDevice, e->stream));
+    MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  }
+  return s->launch_reset();
+}
+
+int mamcts_search_run(mamcts_search* s, uint32_t iterations) {
+  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_run: null handle");
+  mamcts_engine* e = s->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if ((uint64_t)s->iters_done + iterations > s->cfg.mcts.max_number_of_iterations)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_run: exceeds MAX_NUMBER_OF_ITERATIONS of the configuration");
+  if (iterations == 0) return MAMCTS_OK;
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  int rc = s->launch_run(iterations);
+  if (rc == MAMCTS_OK) s->iters_done += iterations;
+  return rc;
+}
+
+int mamcts_search_counters(mamcts_search* s, uint64_t* iterations, uint64_t* rollout_steps,
+                           uint64_t* expand_steps, uint64_t* nodes, uint64_t* backup_levels) {
+  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_counters: null handle");
+  mamcts_engine* e = s->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  unsigned long long h[8];
+  MAMCTS_CUDA(e, cudaMemcpyAsync(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  { int rc = check_search_health(s); if (rc != MAMCTS_OK) return rc; }
+  if (iterations) *iterations = h[0];
+  if (rollout_steps) *rollout_steps = h[1];
+  if (expand_steps) *expand_steps = h[2];
+  if (nodes) *nodes = h[3] + s->cfg.num_trees;  // + the roots
+  if (backup_levels) *backup_levels = h[4];
+  return MAMCTS_OK;
+}
+
+int mamcts_search_exact_ucb_evaluations(mamcts_search* s, uint64_t* count) {
+  if (!s || !count) return fail(s ? s->e : nullptr, MAMCTS_ERR_INVALID, "mamcts_search_exact_ucb_evaluations: null argument");
+  mamcts_engine* e = s->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  unsigned long long h = 0;
+  MAMCTS_CUDA(e, cudaMemcpyAsync(&h, s->d_counters + 5, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  *count = h;
+  return MAMCTS_OK;
+}
+
+int mamcts_search_root_stats(mamcts_search* s, uint32_t tree, uint32_t agent, double* value,
+                             uint32_t* total_visits, double* q, uint32_t* n, uint32_t* expanded_mask,
+                             uint32_t* num_nodes) {
+  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_root_stats: null handle");
+  mamcts_engine* e = s->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (tree >= s->cfg.num_trees || agent >= s->A) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_root_stats: index out of range");
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  { int rc = check_search_health(s); if (rc != MAMCTS_OK) return rc; }
+  std::vector<char> node(s->node_bytes());
+  const char* src = s->root_record(tree);
+  MAMCTS_CUDA(e, cudaMemcpyAsync(node.data(), src, node.size(), cudaMemcpyDeviceToHost, e->stream));
+  uint32_t nn = 0;
+  MAMCTS_CUDA(e, cudaMemcpyAsync(&nn, s->d_tree_nodes + tree, sizeof(nn), cudaMemcpyDeviceToHost, e->stream));
+  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  double v, l, qq[MAMCTS_MAX_ACTIONS];
+  uint32_t vis, nexp, nn_a[MAMCTS_MAX_ACTIONS + 1];
+  s->read_stat(node.data(), agent, &v, &l, &vis, &nexp, qq, nn_a);
+  const int cls = agent == 0 ? 0 : 1;
+  const uint32_t nact = agent == 0 ? s->p.n_ego : s->p.n_oth;
+  const uint32_t mask = s->tab.exp_mask[cls][std::min(nexp, nact)];
+  if (value) *value = v;
+  if (total_visits) *total_visits = vis;
+  for (uint32_t a = 0; a < nact; ++a) {
+    const bool ex = (mask >> a) & 1u;
+    if (q) q[a] = ex ? qq[a] : 0.0;
+    if (n) n[a] = ex ? nn_a[a] : 0u;
+  }
+  if (expanded_mask) *expanded_mask = mask;
+  if (num_nodes) *num_nodes = nn;
+  return MAMCTS_OK;
+}
+
+int mamcts_search_merge_roots(mamcts_search* s, double* merged_q, uint64_t* merged_n,
+                              uint32_t* merged_occurrences, uint64_t* merged_total_visits,
+                              double* merged_value, uint32_t* best_action) {
+  if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_merge_roots: null handle");
+  mamcts_engine* e = s->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  { int rc = check_search_health(s); if (rc != MAMCTS_OK) return rc; }
+  RootGather g;
+  std::memset(&g, 0, sizeof(g));
+  s->root_gather(&g);
+  return root_merge_device(e, g, s->cfg.num_trees, s->p.n_ego, merged_q, merged_n, merged_occurrences,
+                           merged_total_visits, merged_value, best_action);
+}
+
+int mamcts_search_dump_tree(mamcts_search* s, uint32_t tree, double* records,
+                            uint32_t capacity_records, uint32_t* num_records) {
+  if (!s || !records || !num_records) return fail(s ? s->e : nullptr, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: null argument");
+  mamcts_engine* e = s->e;
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (tree >= s->cfg.num_trees) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: tree out of range");
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  { int rc = check_search_health(s); if (rc != MAMCTS_OK) return rc; }
+  return s->dump(tree, records, capacity_records, num_records);
 }
 
 }  // extern "C"

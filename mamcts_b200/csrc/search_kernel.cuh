@@ -66,6 +66,8 @@ struct SearchParams {
   uint32_t* tree_iters;   // [T] iterations done
   const SearchTables* tab;
   const double* log_table;  // log((double)N), host libm
+  const double* disc;       // rollout discount / probability table (engine.h: ensure_discount_table)
+  uint32_t disc_len;
   unsigned long long* counters;  // iterations, rollout steps, expand steps, nodes, backup levels, exact UCB
   uint32_t T, max_nodes, hash_mask, iterations, first_tree_id;
   uint32_t lanes_per_warp;  // trees per warp: lanes >= this exit at once (see search.cu: divergence)
@@ -174,17 +176,23 @@ __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRe
   const double range = __dsub_rn(hi, lo);
 
   // FP32 screen. The FP64 UCB values cost two divisions and a square root per action; the arg-max
-  // almost never needs that precision. Scores are first evaluated in FP32 (every operation IEEE
-  // rounded: error <= 2e-7 * (|score| + 1) per score); when the first maximum beats every action
-  // with different inputs by more than `delta` (>= 5x the worst-case error of two scores), the
-  // exact arg-max is provably the same and is returned. Actions with bit-identical (Q, n) have
-  // identical exact scores, so the strict-> first-max rule picks the same one either way. Anything
-  // else falls through to the exact FP64 evaluation, so the selected action is ALWAYS the
-  // reference's.
+  // almost never needs that precision. Scores are first evaluated in FP32 with one correctly
+  // rounded reciprocal and square root per statistic and one MUFU.RSQ (<= 2 ulp) per action:
+  //   norm  = float(q - lo) * rcp(float(range))                     |error| <= 4 u          (u = 2^-24)
+  //   bonus = (float(2c) * sqrt(float(2 ln N))) * rsqrt(float(n))   |error| <= 8.5 u * bonus
+  //   score = fma(...)                                              |error| <= 9.5 u * (score + 1)
+  // so two scores compare wrongly only if they are closer than 1.2e-6 * (score + 1). When the first
+  // maximum beats every action with different inputs by more than `delta` = 6e-6 * (score + 1)
+  // (5x that bound), the exact arg-max is provably the same and is returned. Actions with
+  // bit-identical (Q, n) have identical exact scores, so the strict-> first-max rule picks the same
+  // one either way. Anything else (including non-finite intermediates) falls through to the exact
+  // FP64 evaluation, so the selected action is ALWAYS the reference's.
   int bi = -1;
   bool ok;
   {
-    const float rangef = (float)range, Lf = (float)log2N, c2f = (float)p.two_c;
+    const float rangef = (float)range;
+    const float inv_range = __frcp_rn(rangef);
+    const float csl = (float)p.two_c * __fsqrt_rn((float)log2N);
     float sc[NACT];
     float best_sc = -1.0f;
     ok = isfinite(rangef) && rangef != 0.0f;
@@ -192,8 +200,8 @@ __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRe
     for (int a = 0; a < NACT; ++a) {
       sc[a] = -2.0f;
       if ((mask >> a) & 1u) {
-        const float normf = (float)__dsub_rn(q[a], lo) / rangef;
-        sc[a] = fmaf(c2f, sqrtf(Lf / (float)cnt[a]), normf);
+        const float normf = (float)__dsub_rn(q[a], lo) * inv_range;
+        sc[a] = fmaf(csl, rsqrtf((float)cnt[a]), normf);
         ok &= (cnt[a] != 0u) & isfinite(sc[a]);
         if (sc[a] > best_sc) { best_sc = sc[a]; bi = a; }
       }
@@ -205,7 +213,7 @@ __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRe
 #pragma unroll
     for (int a = 0; a < NACT; ++a) if (a == bi) { qb = q[a]; nb = cnt[a]; }
     if (ok) {
-      const float delta = 4e-6f * (best_sc + 1.0f);
+      const float delta = 6e-6f * (best_sc + 1.0f);
 #pragma unroll
       for (int a = 0; a < NACT; ++a) {
         if (((mask >> a) & 1u) && a != bi && sc[a] >= best_sc - delta)
@@ -282,9 +290,8 @@ __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename E
   constexpr int A = Env::A;
   constexpr int S = (KIND == MAMCTS_SRC_PHILOX && A <= 8) ? 8 / A : 1;
   constexpr int NB = (A + 7) / 8;
-  const double inv_n_ego = 1.0 / (double)Env::num_actions(p.env, 0);
-  double m = p.gamma, ego = 0.0, prob = 1.0;
-  other = 0.0;
+  // accumulation without per-step FP64 work: see rollout_kernel (rollout.cu)
+  double ego = 0.0, r_other_last = 0.0;
   uint32_t it = 0;
   bool fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
   Philox4 blk[NB];
@@ -322,17 +329,15 @@ __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename E
     }
     double r_ego, r_other, c;
     Env::step(p.env, st, act, r_ego, r_other, c);
-    m = __dmul_rn(p.gamma, m);
-    ego = __dadd_rn(ego, __dmul_rn(m, r_ego));
-    other = __dmul_rn(m, r_other);
-    m = __dmul_rn(m, p.gamma);
-    prob = __dmul_rn(prob, inv_n_ego);
+    if (r_ego != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it), r_ego));
+    r_other_last = r_other;
     it += 1;
     depth += 1;
     fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
   }
   steps = it;
-  return __dmul_rn(ego, prob);
+  other = it ? __dmul_rn(__ldg(p.disc + it - 1), r_other_last) : 0.0;
+  return __dmul_rn(ego, __ldg(p.disc + p.disc_len + it));
 }
 
 // Backup below the recorded path (leaves deeper than kPathMax): follows parent pointers and loads the

@@ -304,7 +304,7 @@ class Search:
     def __init__(self, engine: Engine, env: int, mp: Params, num_trees: int, cp: CrossingParams = None,
                  sp: SimpleParams = None, root_x=None, action_source: int = SRC_PHILOX,
                  philox_seed: int = 0, first_tree_id: int = 0, rollouts_per_leaf: int = 1,
-                 max_nodes_per_tree: int = 0):
+                 max_nodes_per_tree: int = 0, layout: int = 0, max_inner_nodes_per_tree: int = 0):
         self.engine = engine
         self.lib = engine.lib
         cfg = SearchConfig()
@@ -314,6 +314,8 @@ class Search:
         cfg.first_tree_id = first_tree_id
         cfg.rollouts_per_leaf = rollouts_per_leaf
         cfg.max_nodes_per_tree = max_nodes_per_tree
+        cfg.layout = layout
+        cfg.max_inner_nodes_per_tree = max_inner_nodes_per_tree
         cfg.philox_seed = philox_seed
         cfg.mcts = mp
         if cp is not None:

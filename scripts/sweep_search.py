@@ -16,12 +16,14 @@ def main():
     for pt in pts:
         lpw, threads, trees, iters = pt[:4]
         maxn = pt[4] if len(pt) > 4 else 0
+        layout = pt[5] if len(pt) > 5 else 0
+        inner = pt[6] if len(pt) > 6 else 0
         os.environ["MAMCTS_SEARCH_LPW"] = str(lpw)
         os.environ["MAMCTS_SEARCH_THREADS"] = str(threads)
         mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000, rh_max_number_of_iterations=50)
         cp = default_crossing_params(num_other_agents=others)
         s = Search(e, ENV_CROSSING_I32, mp, trees, cp=cp, action_source=SRC_PHILOX, philox_seed=1000,
-                   max_nodes_per_tree=maxn)
+                   max_nodes_per_tree=maxn, layout=layout, max_inner_nodes_per_tree=inner)
         s.run(iters); e.sync()
         best = 1e9
         for _ in range(2):
@@ -30,7 +32,7 @@ def main():
             best = min(best, dt)
         c = s.counters()
         steps = c["rollout_steps"] + c["expand_steps"]
-        print(f"lpw={lpw} threads={threads} trees={trees} iters={iters} maxn={maxn} ms={best*1e3:.1f} "
+        print(f"lpw={lpw} threads={threads} trees={trees} iters={iters} maxn={maxn} layout={layout} inner={inner} ms={best*1e3:.1f} "
               f"env_steps/s={steps/best:.4g} it/s={c['iterations']/best:.4g}", flush=True)
         s.close()
     e.close()

@@ -10,7 +10,8 @@ import pytest
 import oracle_api as O
 from helpers import assert_bit_equal, golden, rel_close, tree_digest, unhex
 from mamcts_b200 import default_crossing_params, default_params, default_simple_params
-from mamcts_b200._abi import ENV_CROSSING_I32, ENV_SIMPLE, SRC_PHILOX, SRC_REFERENCE_CONST
+from mamcts_b200._abi import (ENV_CROSSING_I32, ENV_SIMPLE, LAYOUT_AUTO, LAYOUT_CLASSIC, LAYOUT_COMPACT,
+                              SRC_PHILOX, SRC_REFERENCE_CONST)
 from mamcts_b200.engine import MamctsError, Search, reference_expand_order
 
 pytestmark = pytest.mark.gpu
@@ -103,19 +104,19 @@ def test_root_merge_matches_golden(engine):
 
 # ---- device-resident search ---------------------------------------------------------------------
 
-def _golden_search(engine, case, num_trees=3):
+def _golden_search(engine, case, num_trees=3, layout=LAYOUT_AUTO):
     if case["env"] == "simple":
         mp = default_params(random_seed=case["seed"], max_number_of_iterations=case["iterations"],
                             max_number_of_nodes=case["max_nodes"])
         s = Search(engine, ENV_SIMPLE, mp, num_trees, sp=default_simple_params(),
-                   root_x=[case["state_length"]], action_source=SRC_REFERENCE_CONST)
+                   root_x=[case["state_length"]], action_source=SRC_REFERENCE_CONST, layout=layout)
         nacts, ma = [2, 2], 2
     else:
         mp = default_params(random_seed=case["seed"], max_number_of_iterations=case["iterations"],
                             max_number_of_nodes=100000000, rh_max_number_of_iterations=50)
         cp = default_crossing_params(num_other_agents=case["num_others"],
                                      chain_length=case["chain_length"], ego_goal_pos=case["ego_goal_pos"])
-        s = Search(engine, ENV_CROSSING_I32, mp, num_trees, cp=cp, action_source=SRC_REFERENCE_CONST)
+        s = Search(engine, ENV_CROSSING_I32, mp, num_trees, cp=cp, action_source=SRC_REFERENCE_CONST, layout=layout)
         nacts, ma = [4] + [7] * case["num_others"], 7
     return s, nacts, ma
 
@@ -126,10 +127,12 @@ def test_expand_order_matches_golden():
             assert reference_expand_order(int(seed), int(n)) == order
 
 
-def test_reference_const_search_reproduces_reference_tree(engine):
-    """Whole Mcts::search: every statistic of every node equals the reference's, bit for bit."""
+@pytest.mark.parametrize("layout", [LAYOUT_CLASSIC, LAYOUT_AUTO])
+def test_reference_const_search_reproduces_reference_tree(engine, layout):
+    """Whole Mcts::search: every statistic of every node equals the reference's, bit for bit
+    (classic layout, and the compact one wherever AUTO selects it: 2 agents, SimpleState)."""
     for case in golden("search.json"):
-        s, nacts, ma = _golden_search(engine, case)
+        s, nacts, ma = _golden_search(engine, case, layout=layout)
         # in two launches: the trees must carry on exactly where they stopped
         first = case["iterations"] // 3
         s.run(first)
@@ -156,16 +159,18 @@ def test_reference_const_search_reproduces_reference_tree(engine):
         s.close()
 
 
-@pytest.mark.parametrize("num_others", [1, 2, 3, 7])
-def test_philox_search_equals_oracle_tree(engine, num_others):
+@pytest.mark.parametrize("num_others,layout", [(1, LAYOUT_CLASSIC), (1, LAYOUT_COMPACT), (2, LAYOUT_AUTO),
+                                               (3, LAYOUT_AUTO), (7, LAYOUT_AUTO)])
+def test_philox_search_equals_oracle_tree(engine, num_others, layout):
     iters = 600
     mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
                         rh_max_number_of_iterations=50)
     cp = default_crossing_params(num_other_agents=num_others)
     T, first = 70, 1000
     s = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=SRC_PHILOX, philox_seed=4242,
-               first_tree_id=first)
-    s.run(iters)
+               first_tree_id=first, layout=layout)
+    s.run(iters // 2)       # two launches: the trees carry on exactly where they stopped
+    s.run(iters - iters // 2)
     env = O.make_env(cp=cp)
     total_steps = 0
     for tree in (0, 1, 33, 69):
@@ -183,12 +188,14 @@ def test_philox_search_equals_oracle_tree(engine, num_others):
     s.close()
 
 
-def test_philox_search_simple_equals_oracle_tree(engine):
+@pytest.mark.parametrize("layout", [LAYOUT_CLASSIC, LAYOUT_COMPACT])
+def test_philox_search_simple_equals_oracle_tree(engine, layout):
     iters = 300
     mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100,
                         rh_max_number_of_iterations=30)
     sp = default_simple_params()
-    s = Search(engine, ENV_SIMPLE, mp, 40, sp=sp, root_x=[4], action_source=SRC_PHILOX, philox_seed=1)
+    s = Search(engine, ENV_SIMPLE, mp, 40, sp=sp, root_x=[4], action_source=SRC_PHILOX, philox_seed=1,
+               layout=layout)
     s.run(iters)
     for tree in (0, 39):
         t = O.OracleTree(O.make_env(sp=sp), mp, [4], action_source=SRC_PHILOX, seed=1, tree_id=tree)
@@ -229,10 +236,56 @@ def test_philox_search_equals_reference_twin(engine):
     s.close()
 
 
-def test_search_reset_and_limits(engine):
+def test_compact_and_classic_layouts_agree_on_large_trees(engine):
+    """The two tree layouts are two storages of the same search: every node statistic of every tree is
+    bit-identical, at the benchmark's tree size (10 000 iterations), and the merged roots agree."""
+    iters = 10000
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    dumps, merged, counters = [], [], []
+    for layout, inner in ((LAYOUT_CLASSIC, 0), (LAYOUT_COMPACT, 3200)):
+        s = Search(engine, ENV_CROSSING_I32, mp, 96, cp=cp, action_source=SRC_PHILOX, philox_seed=1000,
+                   first_tree_id=7, layout=layout, max_inner_nodes_per_tree=inner)
+        s.run(iters)
+        dumps.append([s.dump_tree(t, iters + 1) for t in (0, 31, 95)])
+        merged.append(s.merge_roots())
+        counters.append(s.counters())
+        s.close()
+    for a, b in zip(*dumps):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert counters[0] == counters[1]
+    assert merged[0]["n"].tolist() == merged[1]["n"].tolist() and merged[0]["best"] == merged[1]["best"]
+    assert_bit_equal(merged[0]["q"], merged[1]["q"], "merged q")
+    # ... and against the CPU oracle for one of them
+    t = O.OracleTree(O.make_env(cp=cp), mp, [5, 5], action_source=SRC_PHILOX, seed=1000, tree_id=7 + 31)
+    t.run(iters)
+    assert np.array_equal(dumps[1][1], t.dump(7))
+    t.close()
+
+
+def test_compact_layout_reports_exhausted_inner_records(engine):
+    mp = default_params(max_number_of_iterations=2000, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    s = Search(engine, ENV_CROSSING_I32, mp, 8, cp=cp, action_source=SRC_PHILOX, philox_seed=5,
+               layout=LAYOUT_COMPACT, max_inner_nodes_per_tree=50)
+    s.run(2000)
+    with pytest.raises(MamctsError, match="inner node records"):
+        s.merge_roots()
+    with pytest.raises(MamctsError, match="inner node records"):
+        s.counters()
+    s.close()
+    with pytest.raises(MamctsError, match="direct child table"):
+        Search(engine, ENV_CROSSING_I32, mp, 1, cp=default_crossing_params(num_other_agents=2),
+               layout=LAYOUT_COMPACT)
+
+
+@pytest.mark.parametrize("layout", [LAYOUT_CLASSIC, LAYOUT_COMPACT])
+def test_search_reset_and_limits(engine, layout):
     mp = default_params(max_number_of_iterations=100, rh_max_number_of_iterations=50)
     cp = default_crossing_params(num_other_agents=1)
-    s = Search(engine, ENV_CROSSING_I32, mp, 33, cp=cp, action_source=SRC_PHILOX, philox_seed=3)
+    s = Search(engine, ENV_CROSSING_I32, mp, 33, cp=cp, action_source=SRC_PHILOX, philox_seed=3, layout=layout)
     s.run(100)
     a = s.dump_tree(5, 101)
     with pytest.raises(MamctsError, match="MAX_NUMBER_OF_ITERATIONS"):
