@@ -42,7 +42,7 @@ def _params():
     return mp, cp
 
 
-def _config(trees_per_gpu, n_gpus, action_source):
+def _config(trees_per_gpu, n_gpus, action_source, layout="compact (16-B leaf + 256-B inner records)"):
     return {
         "workload": "C2: CrossingState<int> 2 agents (ego 4 / other 7 actions), UctStatistic ego+other, "
                     f"{ITERATIONS} iterations per tree, rollout depth cap {DEPTH_CAP}, "
@@ -50,10 +50,24 @@ def _config(trees_per_gpu, n_gpus, action_source):
         "trees_per_gpu": trees_per_gpu, "trees_total": trees_per_gpu * n_gpus,
         "iterations_per_tree": ITERATIONS, "rollout_depth_cap": DEPTH_CAP, "agents": NUM_OTHERS + 1,
         "action_source": action_source,
+        "tree_layout": layout,
         "cache": "inputs larger than L2: tree arenas are tens of GB, no flush needed",
         "parallelism": f"root-parallel x{n_gpus} (trees sharded by global id, one NCCL all-reduce of "
                        "root statistics per decision)",
     }
+
+
+def _measured_traffic(layout, trees, iterations):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact
+    configuration (profiles/r01_traffic.json), else None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        for e in json.load(f)["entries"]:
+            if (e["layout"], e["trees"], e["iterations"]) == (layout if layout else 2, trees, iterations):
+                return e["dram_bytes_per_launch"]
+    return None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -157,7 +171,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _config(args.trees, args.gpus, "philox4x32-10 uniform joint actions"),
+        "config": _config(args.trees, args.gpus, "philox4x32-10 uniform joint actions",
+                          "n/a for this arm (the reference keeps each tree in shared_ptr / std::map nodes on the host)"),
         "reference_action_source": "the reference's stock RandomHeuristic (mt19937 first-draw constant "
                                    "actions, SURVEY.md F1); it has no other rollout policy",
         "iterations_per_s": its_per_s,
@@ -385,12 +400,17 @@ def run_native(args):
         bytes_per_it = (16 * A + 8 + 8) + 80 * A * mean_depth + (60 + 96 * (A - 1)) * (mean_depth + 1)
         algo_bytes = bytes_per_it * it_local
         achieved = algo_bytes / (search_kernel_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "search_kernel<CrossingEnv<1>,4,7,PHILOX>",
+        roofline = {"bound": "hbm", "kernel": ("search_kernel" if args.layout == 1 else "search_compact_kernel") +
+                                              "<CrossingEnv<1>,4,7,PHILOX>",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": None,
+                    "peak_source": peak_src, "traffic": _measured_traffic(args.layout, T, ITERATIONS),
                     "algorithmic_bytes_per_iteration": bytes_per_it, "mean_leaf_depth": mean_depth,
                     "kernel_ms": search_kernel_ms,
-                    "note": "latency/issue-bound pointer chasing; see DESIGN.md §7 and profiles/"}
+                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                    "profiles/r01_traffic.json; null when this configuration was not captured)",
+                    "note": "one lane per tree, one randomly placed 256-B record per level: bound by HBM random-record "
+                            "access (about 2.8 TB/s of DRAM traffic at this size, profiles/r01_randrec_microbench.txt), "
+                            "not by streaming bandwidth; see DESIGN.md section 7"}
         # ---- cpu baseline: the reference's own search on the host cores, bounded sample -----------
         threads = os.cpu_count() or 1
         cb = cpu_reference_search(threads, max(1, args.cpu_repeats))
@@ -402,7 +422,9 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": _config(T, world, "philox4x32-10 uniform joint actions"),
+            "config": _config(T, world, "philox4x32-10 uniform joint actions",
+                              "classic (288-B node records)" if args.layout == 1 else
+                              f"compact (16-B leaf + 256-B inner records, {args.max_inner} inner per tree)"),
             "iterations_per_s": its,
             "env_steps_per_decision": env_steps_per_step, "rollout_steps_per_decision": rollout_steps,
             "nodes_per_decision": nodes,
@@ -433,12 +455,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--trees", type=int, default=32768,
-                    help="root-parallel trees per GPU (32768 trees x 10001 nodes x 288 B = 94 GB of HBM)")
+    ap.add_argument("--trees", type=int, default=65536,
+                    help="root-parallel trees per GPU (compact layout: 65536 trees x (3200 x 256 B inner + "
+                         "10001 x 16 B leaf records) = 64 GB of HBM)")
     ap.add_argument("--cpu-repeats", type=int, default=24, help="whole searches per host thread for cpu_baseline")
-    ap.add_argument("--layout", type=int, default=0, help="tree layout: 0 auto, 1 classic, 2 compact")
-    ap.add_argument("--max-inner", type=int, default=0,
-                    help="compact layout: inner records per tree (0 = one per node)")
+    ap.add_argument("--layout", type=int, default=2, help="tree layout: 0 auto, 1 classic, 2 compact")
+    ap.add_argument("--max-inner", type=int, default=3200,
+                    help="compact layout: inner records per tree (0 = one per node); a 10 000-iteration C2 "
+                         "tree needs 2 500 +- 76 (max 2 734 over 120 trees); a tree that runs out fails the run")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2 = the headline search benchmark (default, includes a C3 rollout-kernel section); "
                          "c3 = only the batched rollout kernel (profiling)")
