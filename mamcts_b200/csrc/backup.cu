@@ -96,15 +96,19 @@ root_merge_kernel(RootGather g, uint32_t n_trees, uint32_t nA, double* __restric
         nbase = (size_t)t * g.stride_n;
         vbase = (size_t)t * g.stride_v;
       }
+      auto count_at = [&](const void* ptr, size_t idx) -> uint32_t {
+        return g.count_bytes == 2 ? (uint32_t)static_cast<const uint16_t*>(ptr)[idx]
+                                  : static_cast<const uint32_t*>(ptr)[idx];
+      };
       double v;
       if (comp < nA) {
-        v = g.n[nbase + comp] ? g.q[qbase + comp] : 0.0;
+        v = count_at(g.n, nbase + comp) ? g.q[qbase + comp] : 0.0;
       } else if (comp < 2 * nA) {
-        v = (double)g.n[nbase + comp - nA];
+        v = (double)count_at(g.n, nbase + comp - nA);
       } else if (comp < 3 * nA) {
-        v = g.n[nbase + comp - 2 * nA] ? 1.0 : 0.0;
+        v = count_at(g.n, nbase + comp - 2 * nA) ? 1.0 : 0.0;
       } else {
-        v = (double)g.visits[vbase];
+        v = (double)count_at(g.visits, vbase);
       }
       part = __dadd_rn(part, v);
     }
@@ -291,6 +295,7 @@ int mamcts_root_merge(mamcts_engine* e, const mamcts_uct_stats* stats, uint32_t 
   g.q = stg.dev<const double>(s_q);
   g.n = stg.dev<const uint32_t>(s_n);
   g.visits = stg.dev<const uint32_t>(s_vis);
+  g.count_bytes = 4;
   g.root_slot = stg.dev<const uint32_t>(t_slot);
   g.max_actions = stats->max_actions;
   return root_merge_device(e, g, n_trees, num_actions, merged_q, merged_n, merged_occurrences,

@@ -12,8 +12,9 @@ namespace mamcts {
 // the result does not depend on scheduling.
 struct RootGather {
   const double* q;        // action values
-  const uint32_t* n;      // action counts (present <=> n > 0 at iteration boundaries)
-  const uint32_t* visits;
+  const void* n;          // action counts (present <=> n > 0 at iteration boundaries), count_bytes wide
+  const void* visits;
+  uint32_t count_bytes;   // 4 (uint32) or 2 (uint16, compact layout of short searches)
   const uint32_t* root_slot;  // may be null: strided layout below (device-resident trees)
   size_t stride_q;            // doubles between consecutive trees' q rows when root_slot is null
   size_t stride_n;            // uint32s between consecutive trees' n rows

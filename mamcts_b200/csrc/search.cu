@@ -143,8 +143,9 @@ struct SearchT final : public mamcts_search {
     const char* base = static_cast<const char*>(d_nodes);
     const size_t tree_bytes = sizeof(Node) * (size_t)p.max_nodes;
     g->q = reinterpret_cast<const double*>(base + offsetof(Node, ego) + offsetof(StatRec<NE>, Q));
-    g->n = reinterpret_cast<const uint32_t*>(base + offsetof(Node, ego) + offsetof(StatRec<NE>, n));
-    g->visits = reinterpret_cast<const uint32_t*>(base + offsetof(Node, ego) + offsetof(StatRec<NE>, N));
+    g->n = base + offsetof(Node, ego) + offsetof(StatRec<NE>, n);
+    g->visits = base + offsetof(Node, ego) + offsetof(StatRec<NE>, N);
+    g->count_bytes = 4;
     g->root_slot = nullptr;
     g->stride_q = tree_bytes / sizeof(double);
     g->stride_n = tree_bytes / sizeof(uint32_t);
@@ -154,9 +155,9 @@ struct SearchT final : public mamcts_search {
 };
 
 // Compact (two-tier) layout: search_compact.cuh.
-template <class Env, int NE, int NA, int NCHILD, class CIDX>
+template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT>
 struct SearchC final : public mamcts_search {
-  using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX>;
+  using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
   using Leaf = LeafRec<Env::A>;
 
   size_t node_bytes() const override { return sizeof(Inner); }
@@ -170,7 +171,7 @@ struct SearchC final : public mamcts_search {
   int launch_reset() override {
     const uint32_t T = cfg.num_trees;
     MAMCTS_CUDA(e, cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
-    search_compact_reset_kernel<Env, NE, NA, NCHILD, CIDX><<<(T + 255) / 256, 256, 0, e->stream>>>(
+    search_compact_reset_kernel<Env, NE, NA, NCHILD, CIDX, CNT><<<(T + 255) / 256, 256, 0, e->stream>>>(
         d_inner, d_tree_nodes, d_tree_iters, d_tree_inner, d_tree_leaves, T, max_inner);
     e->launches++;
     MAMCTS_CUDA(e, cudaGetLastError());
@@ -188,9 +189,9 @@ struct SearchC final : public mamcts_search {
     const uint32_t trees_per_block = (uint32_t)(block_threads / 32) * q.lanes_per_warp;
     const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
     if (cfg.action_source == MAMCTS_SRC_PHILOX)
-      search_compact_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_PHILOX><<<grid, block_threads, 0, e->stream>>>(q, c);
+      search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX><<<grid, block_threads, 0, e->stream>>>(q, c);
     else
-      search_compact_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_REFERENCE_CONST><<<grid, block_threads, 0, e->stream>>>(q, c);
+      search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_REFERENCE_CONST><<<grid, block_threads, 0, e->stream>>>(q, c);
     e->launches++;
     MAMCTS_CUDA(e, cudaGetLastError());
     return MAMCTS_OK;
@@ -201,27 +202,33 @@ struct SearchC final : public mamcts_search {
     const Inner* nd = static_cast<const Inner*>(node);
     *parent = nd->parent;
     *depth = 0;  // not stored: the export derives it
-    *visits = nd->visit_count;
-    for (int a = 0; a < Env::A; ++a) ja[a] = nd->ja[a];
+    *visits = nd->c.visit_count;
+    for (int a = 0; a < Env::A; ++a) ja[a] = nd->c.ja[a];
   }
 
   void read_stat(const void* node, uint32_t agent, double* value, double* latest, uint32_t* visits,
                  uint32_t* nexp, double* q, uint32_t* n) const override {
     const Inner* nd = static_cast<const Inner*>(node);
-    if (agent == 0) SearchT<Env, NE, NA, NCHILD, CIDX>::template read_stat_rec<NE>(nd->ego, value, latest, visits, nexp, q, n);
-    else SearchT<Env, NE, NA, NCHILD, CIDX>::template read_stat_rec<NA>(nd->oth[agent - 1], value, latest, visits, nexp, q, n);
+    const uint32_t k = agent ? 1 : 0;
+    *value = nd->v.V[k];
+    *latest = nd->v.G[k];
+    *visits = nd->c.N[k];
+    *nexp = nd->c.nexp[k];
+    if (agent == 0) { for (int a = 0; a < NE; ++a) { q[a] = nd->q_e[a]; n[a] = nd->c.n_e[a]; } }
+    else { for (int a = 0; a < NA; ++a) { q[a] = nd->q_o[a]; n[a] = nd->c.n_o[a]; } }
   }
 
   void root_gather(RootGather* g) const override {
     const char* base = static_cast<const char*>(d_inner);
     const size_t tree_bytes = sizeof(Inner) * (size_t)max_inner;
-    g->q = reinterpret_cast<const double*>(base + offsetof(Inner, ego) + offsetof(StatRec<NE>, Q));
-    g->n = reinterpret_cast<const uint32_t*>(base + offsetof(Inner, ego) + offsetof(StatRec<NE>, n));
-    g->visits = reinterpret_cast<const uint32_t*>(base + offsetof(Inner, ego) + offsetof(StatRec<NE>, N));
+    g->q = reinterpret_cast<const double*>(base + offsetof(Inner, q_e));
+    g->n = base + offsetof(Inner, c) + offsetof(typename Inner::Counters, n_e);
+    g->visits = base + offsetof(Inner, c) + offsetof(typename Inner::Counters, N);
+    g->count_bytes = sizeof(CNT);
     g->root_slot = nullptr;
     g->stride_q = tree_bytes / sizeof(double);
-    g->stride_n = tree_bytes / sizeof(uint32_t);
-    g->stride_v = tree_bytes / sizeof(uint32_t);
+    g->stride_n = tree_bytes / sizeof(CNT);
+    g->stride_v = tree_bytes / sizeof(CNT);
     g->max_actions = NE;
   }
 
@@ -258,7 +265,7 @@ struct SearchC final : public mamcts_search {
     auto emit_inner = [&](uint32_t i, uint32_t depth, double code, size_t nkids) {
       if (count < capacity_records) {
         double* r = records + (size_t)count * stride;
-        r[0] = depth; r[1] = code; r[2] = in[i].visit_count; r[3] = (double)nkids;
+        r[0] = depth; r[1] = code; r[2] = in[i].c.visit_count; r[3] = (double)nkids;
         for (uint32_t a = 0; a < A; ++a) {
           double* o = r + 4 + a * (3 + 2 * max_actions);
           double v, l, qq[MAMCTS_MAX_ACTIONS];
@@ -318,11 +325,13 @@ struct SearchC final : public mamcts_search {
 };
 
 template <class Env, int NE, int NA, int NCHILD>
-static mamcts_search* make_search_cidx(uint32_t max_nodes, bool compact) {
+static mamcts_search* make_search_cidx(uint32_t max_nodes, bool compact, uint32_t max_iterations) {
   if (NCHILD > 0 && compact) {
     if constexpr (NCHILD > 0) {
-      if (max_nodes + 1 < 32768) return new SearchC<Env, NE, NA, NCHILD, uint16_t>();
-      return new SearchC<Env, NE, NA, NCHILD, uint32_t>();
+      // 16-bit child entries / counts where everything they hold stays below 2^15 / 2^16
+      if (max_nodes + 1 < 32768 && max_iterations < 65535) return new SearchC<Env, NE, NA, NCHILD, uint16_t, uint16_t>();
+      if (max_nodes + 1 < 32768) return new SearchC<Env, NE, NA, NCHILD, uint16_t, uint32_t>();
+      return new SearchC<Env, NE, NA, NCHILD, uint32_t, uint32_t>();
     }
   }
   if (NCHILD > 0 && max_nodes <= 65535) return new SearchT<Env, NE, NA, NCHILD, uint16_t>();
@@ -333,13 +342,13 @@ static mamcts_search* make_search(const mamcts_search_config& cfg, uint32_t n_eg
                                   uint32_t max_nodes) {
   // layout: 0 = automatic (compact wherever a direct child table exists), 1 = classic, 2 = compact
   const bool compact = cfg.layout != MAMCTS_LAYOUT_CLASSIC;
-  if (cfg.env == MAMCTS_ENV_SIMPLE) return make_search_cidx<SimpleEnv, 2, 2, 4>(max_nodes, compact);
+  if (cfg.env == MAMCTS_ENV_SIMPLE) return make_search_cidx<SimpleEnv, 2, 2, 4>(max_nodes, compact, cfg.mcts.max_number_of_iterations);
   if (n_ego == 4 && n_oth == 7) {
     switch (cfg.crossing.num_other_agents) {
-      case 1: return make_search_cidx<CrossingEnv<1>, 4, 7, 28>(max_nodes, compact);
-      case 2: return make_search_cidx<CrossingEnv<2>, 4, 7, 0>(max_nodes, false);
-      case 3: return make_search_cidx<CrossingEnv<3>, 4, 7, 0>(max_nodes, false);
-      case 7: return make_search_cidx<CrossingEnv<7>, 4, 7, 0>(max_nodes, false);
+      case 1: return make_search_cidx<CrossingEnv<1>, 4, 7, 28>(max_nodes, compact, cfg.mcts.max_number_of_iterations);
+      case 2: return make_search_cidx<CrossingEnv<2>, 4, 7, 0>(max_nodes, false, cfg.mcts.max_number_of_iterations);
+      case 3: return make_search_cidx<CrossingEnv<3>, 4, 7, 0>(max_nodes, false, cfg.mcts.max_number_of_iterations);
+      case 7: return make_search_cidx<CrossingEnv<7>, 4, 7, 0>(max_nodes, false, cfg.mcts.max_number_of_iterations);
       default: return nullptr;
     }
   }

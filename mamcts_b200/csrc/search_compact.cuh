@@ -31,16 +31,37 @@ namespace mamcts {
 
 constexpr int kPathMaxCompact = 64;  // deepest leaf the compact layout can back up (error beyond)
 
-template <class Env, int NE, int NA, int NCHILD, class CIDX>
+// Inner record, laid out by 32-byte sector so that a visit touches as few sectors as possible (the
+// kernel is bound by DRAM traffic of randomly placed records):
+//   counters  every integer a visit reads or writes: visit_count, N per agent, #expanded per agent, the
+//             joint action leading here, n[a] of both agents - ONE sector with 16-bit counts
+//             (searches of < 65 536 iterations), two with 32-bit counts
+//   values    V and G (value_, latest_return_) of both agents - one sector
+//   q_e, q_o  the action values - 1 + 2 sectors; q_o's padding holds the parent index (export only)
+//   child     the direct child table - 2 sectors, one of which a visit reads
+// A visit reads 6 sectors and dirties 4 (16-bit counts); the previous AoS-by-agent layout read 8 and
+// dirtied 6-7.
+template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT>
 struct alignas(64) InnerRec {
   static constexpr int A = Env::A;
   static_assert(NCHILD > 0, "the compact layout needs a direct child table");
-  uint32_t parent;       // inner index of the parent (export only)
-  uint32_t visit_count;  // StageNode::visit_count_
-  uint8_t ja[8];         // joint action leading here (export only)
-  StatRec<NE> ego;
-  StatRec<NA> oth[A - 1];
-  CIDX child[NCHILD];
+  static_assert(A == 2, "the compact layout is built for two agents");
+  struct alignas(32) Counters {
+    CNT visit_count;       // StageNode::visit_count_
+    CNT N[2];              // total_node_visits_ (ego, other)
+    uint8_t nexp[2];       // ucb_statistics_.size(): the first nexp entries of the widening order
+    uint8_t ja[2];         // joint action leading here (export only)
+    CNT n_e[NE];           // action_count_
+    CNT n_o[NA];
+  } c;
+  struct alignas(32) Values {
+    double V[2];           // value_
+    double G[2];           // latest_return_
+  } v;
+  alignas(32) double q_e[NE];   // action_value_
+  alignas(32) double q_o[NA];
+  uint32_t parent;              // inner index of the parent (export only)
+  alignas(32) CIDX child[NCHILD];
 };
 
 template <int A>
@@ -64,10 +85,10 @@ __device__ __forceinline__ CIDX inner_entry(uint32_t inner) { return (CIDX)((inn
 
 // counters[6] = trees that ran out of inner records, counters[7] = trees with a path deeper than
 // kPathMaxCompact; either makes mamcts_search_run's caller see an error at the next read-back.
-template <class Env, int NE, int NA, int NCHILD, class CIDX, int KIND>
+template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT, int KIND>
 __global__ void __launch_bounds__(kSearchThreads)
 search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_constant__ CompactParams c) {
-  using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX>;
+  using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
   constexpr int A = Env::A;
   using Leaf = LeafRec<A>;
   const uint32_t lane = threadIdx.x & 31u;
@@ -91,10 +112,17 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   root.flags = 0;
   root.flags = (uint32_t)Env::terminal(p.env, root);
 
+  // The path of the current iteration (collect(), node_statistic.h:115-121) and everything the backup
+  // of a level needs: the counters sector as loaded (it is updated and written back whole) and the
+  // chosen actions' Q and the V of both agents. These arrays live in local memory, which is
+  // interleaved by lane: one wavefront serves all 32 lanes, unlike a global access of 32 records.
+  using Counters = typename Inner::Counters;
+  constexpr int kCntVec = sizeof(Counters) / 16;
   uint32_t path_node[kPathMaxCompact];
   uint8_t path_ja[kPathMaxCompact][A];
   double path_r0[kPathMaxCompact], path_r1[kPathMaxCompact];
-  BackRegs path_back[kPathMaxCompact][A];
+  double path_q[kPathMaxCompact][A], path_v[kPathMaxCompact][A];
+  Counters path_cnt[kPathMaxCompact];
   uint32_t done = 0;
   bool failed = false;
 
@@ -110,25 +138,54 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
 #pragma unroll 1
     while (!failed) {
       Inner* nd = inner + node;
-      // one round trip: everything the level needs is requested before anything is used
-      const uint32_t vc = nd->visit_count;
-      const StatRegs<NE> ego = load_stat<NE>(&nd->ego);
-      StatRegs<NA> oth0;
-      if (A > 1) oth0 = load_stat<NA>(&nd->oth[0]);
+      // One round trip, and as few load instructions as possible: each lane reads its own record, so
+      // every global load costs 32 L1 wavefronts whatever its width - the record is pulled with ten
+      // 16-byte loads (the L1/LSU pipe, not DRAM, was the limiter with scalar loads; profiles/).
+      const uint4* raw = reinterpret_cast<const uint4*>(nd);
+      uint4 craw[kCntVec];
+#pragma unroll
+      for (int i = 0; i < kCntVec; ++i) craw[i] = raw[i];
+      const double2 vv = *reinterpret_cast<const double2*>(&nd->v.V[0]);   // V ego, V other (G is not read)
+      double2 qe[NE / 2 + (NE & 1)], qo[NA / 2 + (NA & 1)];
+#pragma unroll
+      for (int i = 0; i < NE / 2 + (NE & 1); ++i) qe[i] = reinterpret_cast<const double2*>(&nd->q_e[0])[i];
+#pragma unroll
+      for (int i = 0; i < NA / 2 + (NA & 1); ++i) qo[i] = reinterpret_cast<const double2*>(&nd->q_o[0])[i];
       prefetch_l1(&nd->child[0]);
-      nd->visit_count = vc + 1;                                          // :180
+      if (sizeof(CIDX) * NCHILD > 32) prefetch_l1(&nd->child[NCHILD - 1]);
+      Counters cc;
+      __builtin_memcpy(&cc, craw, sizeof(cc));
       if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) {  // :183-187
         // no rollout: the node's own latest return is backed up (mcts.h:309-329)
-        G[0] = nd->ego.G;
-        if (A > 1) G[1] = nd->oth[0].G;
+        nd->c.visit_count = (CNT)(cc.visit_count + 1);                   // :180
+        G[0] = nd->v.G[0];
+        G[1] = nd->v.G[1];
         break;
       }
       if (depth >= (uint32_t)kPathMaxCompact) { failed = true; atomicAdd(p.counters + 7, 1ull); break; }
+      StatRegs<NE> ego;
+      StatRegs<NA> oth;
+      ego.N = cc.N[0]; ego.nexp = cc.nexp[0]; ego.V = vv.x;
+      oth.N = cc.N[1]; oth.nexp = cc.nexp[1]; oth.V = vv.y;
+#pragma unroll
+      for (int a = 0; a < NE; ++a) { ego.Q[a] = (a & 1) ? qe[a / 2].y : qe[a / 2].x; ego.n[a] = cc.n_e[a]; }
+#pragma unroll
+      for (int a = 0; a < NA; ++a) { oth.Q[a] = (a & 1) ? qo[a / 2].y : qo[a / 2].x; oth.n[a] = cc.n_o[a]; }
       uint8_t ja[A];
       BackRegs back[A];
-      ja[0] = (uint8_t)choose_action<NE>(&nd->ego, ego, p, 0, p.n_ego, exact_evals, back[0]);  // :190-195
-      if (A > 1) ja[1] = (uint8_t)choose_action<NA>(&nd->oth[0], oth0, p, 1, p.n_oth, exact_evals, back[1]);
-      const uint32_t slot = (uint32_t)ja[0] * NA + (A > 1 ? (uint32_t)ja[A > 1 ? 1 : 0] : 0u);
+      bool w0, w1;
+      ja[0] = (uint8_t)select_action<NE>(ego, p, 0, p.n_ego, exact_evals, back[0], w0);  // :190-195
+      ja[1] = (uint8_t)select_action<NA>(oth, p, 1, p.n_oth, exact_evals, back[1], w1);
+      // Nothing is stored during the descent: visit_count + 1 (:180) and a newly expanded action
+      // (ucb_statistics_[a] = UcbPair()) go into the counters image, which this iteration's backup of
+      // the level writes back together with N and n[a].
+      cc.visit_count = (CNT)(cc.visit_count + 1);
+      if (w0) cc.nexp[0] = (uint8_t)(cc.nexp[0] + 1);
+      if (w1) cc.nexp[1] = (uint8_t)(cc.nexp[1] + 1);
+      path_cnt[depth] = cc;
+      path_q[depth][0] = back[0].q; path_q[depth][1] = back[1].q;
+      path_v[depth][0] = back[0].v; path_v[depth][1] = back[1].v;
+      const uint32_t slot = (uint32_t)ja[0] * NA + (uint32_t)ja[1];
       const uint32_t entry = nd->child[slot];                            // :198
       // the child's state and the reward collected on the edge (collect(), node_statistic.h:115-121)
       int32_t act[A];
@@ -140,8 +197,8 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       path_node[depth] = node;
       path_r0[depth] = r_ego;
       path_r1[depth] = r_other;
-#pragma unroll
-      for (int a = 0; a < A; ++a) { path_ja[depth][a] = ja[a]; path_back[depth][a] = back[a]; }
+      path_ja[depth][0] = ja[0];
+      path_ja[depth][1] = ja[1];
       depth += 1;
       if (entry & 1u) { node = entry >> 1; continue; }                   // existing inner node, :199-206
       if (entry == 0u) {
@@ -163,15 +220,16 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
         if (num_inner >= c.max_inner) { failed = true; atomicAdd(p.counters + 6, 1ull); break; }
         const uint32_t id = num_inner++;
         Inner* cn = inner + id;
+        cn->c.visit_count = 0;
+        cn->c.N[0] = 1; cn->c.N[1] = 1;          // update_from_heuristic left 0 + 1 visits
+        cn->c.nexp[0] = 0; cn->c.nexp[1] = 0;
+        cn->c.ja[0] = ja[0]; cn->c.ja[1] = ja[1];
+#pragma unroll
+        for (int a = 0; a < NE; ++a) cn->c.n_e[a] = 0;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) cn->c.n_o[a] = 0;
+        cn->v.V[0] = h[0]; cn->v.G[0] = h[0]; cn->v.V[1] = h[1]; cn->v.G[1] = h[1];
         cn->parent = node;
-        cn->visit_count = 0;
-#pragma unroll
-        for (int a = 0; a < 8; ++a) cn->ja[a] = (a < A) ? ja[a] : 0;
-        cn->ego.V = h[0]; cn->ego.G = h[0]; cn->ego.N = 1; cn->ego.nexp = 0;
-#pragma unroll
-        for (int j = 0; j < A - 1; ++j) {
-          cn->oth[j].V = h[j + 1]; cn->oth[j].G = h[j + 1]; cn->oth[j].N = 1; cn->oth[j].nexp = 0;
-        }
 #pragma unroll
         for (int k = 0; k < NCHILD; ++k) cn->child[k] = 0;
         nd->child[slot] = inner_entry<CIDX>(id);
@@ -192,9 +250,9 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       rollout_steps += steps;
       // update_from_heuristic (uct_statistic.h:100-110): value_ = latest_return_ = h, visits 0 + 1
       leaves[new_leaf].h[0] = ego_h;
+      leaves[new_leaf].h[1] = other;
       G[0] = ego_h;
-#pragma unroll
-      for (int j = 0; j < A - 1; ++j) { leaves[new_leaf].h[j + 1] = other; G[j + 1] = other; }
+      G[1] = other;
     }
     // ---- backpropagation: mcts.h:314-329, stage_node.h:259-271; recorded path, no loads ---------
     backup_levels += depth;
@@ -203,11 +261,29 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
     while (level > 0) {
       level -= 1;
       Inner* pn = inner + path_node[level];
-      const double r0 = path_r0[level], r1 = path_r1[level];
-      G[0] = back_apply<NE>(&pn->ego, path_ja[level][0], path_back[level][0], r0, p.gamma, G[0]);
+      Counters& ci = path_cnt[level];
+      const uint32_t ae = path_ja[level][0], ao = path_ja[level][1];
+      BackRegs be, bo;
+      be.q = path_q[level][0]; be.v = path_v[level][0]; be.cnt0 = ci.n_e[ae]; be.nv0 = ci.N[0];
+      bo.q = path_q[level][1]; bo.v = path_v[level][1]; bo.cnt0 = ci.n_o[ao]; bo.nv0 = ci.N[1];
+      const BackOut e = back_compute(be, path_r0[level], p.gamma, G[0]);
+      const BackOut o = back_compute(bo, path_r1[level], p.gamma, G[1]);
+      ci.N[0] = (CNT)e.nv; ci.N[1] = (CNT)o.nv;
+      ci.n_e[ae] = (CNT)e.cnt; ci.n_o[ao] = (CNT)o.cnt;
+      // counters sector(s) and the value sector go back whole, 16 bytes per store
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(&ci);
+        uint4* dst = reinterpret_cast<uint4*>(pn);
 #pragma unroll
-      for (int j = 0; j < A - 1; ++j)
-        G[j + 1] = back_apply<NA>(&pn->oth[j], path_ja[level][j + 1], path_back[level][j + 1], r1, p.gamma, G[j + 1]);
+        for (int i = 0; i < kCntVec; ++i) dst[i] = src[i];
+        double2* vdst = reinterpret_cast<double2*>(&pn->v.V[0]);
+        vdst[0] = make_double2(e.v, o.v);
+        vdst[1] = make_double2(e.G, o.G);
+      }
+      pn->q_e[ae] = e.q;
+      pn->q_o[ao] = o.q;
+      G[0] = e.G;
+      G[1] = o.G;
     }
     done += 1;
   }
@@ -223,19 +299,21 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   atomicAdd(p.counters + 5, exact_evals);
 }
 
-template <class Env, int NE, int NA, int NCHILD, class CIDX>
+template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT>
 __global__ void search_compact_reset_kernel(void* inner_v, uint32_t* tree_nodes, uint32_t* tree_iters,
                                             uint32_t* tree_inner, uint32_t* tree_leaves, uint32_t T,
                                             uint32_t max_inner) {
-  using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX>;
+  using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
   const uint32_t tree = blockIdx.x * blockDim.x + threadIdx.x;
   if (tree >= T) return;
   Inner* root = static_cast<Inner*>(inner_v) + (size_t)tree * max_inner;
   root->parent = kNoParent;
-  root->visit_count = 0;
-  for (int a = 0; a < 8; ++a) root->ja[a] = 0;
-  root->ego.V = 0.0; root->ego.G = 0.0; root->ego.N = 0; root->ego.nexp = 0;
-  for (int j = 0; j < Env::A - 1; ++j) { root->oth[j].V = 0.0; root->oth[j].G = 0.0; root->oth[j].N = 0; root->oth[j].nexp = 0; }
+  root->c.visit_count = 0;
+  root->c.N[0] = 0; root->c.N[1] = 0; root->c.nexp[0] = 0; root->c.nexp[1] = 0;
+  root->c.ja[0] = 0; root->c.ja[1] = 0;
+  for (int a = 0; a < NE; ++a) { root->c.n_e[a] = 0; root->q_e[a] = 0.0; }  // the root merge reads n[a] > 0 as "expanded"
+  for (int a = 0; a < NA; ++a) { root->c.n_o[a] = 0; root->q_o[a] = 0.0; }
+  root->v.V[0] = 0.0; root->v.G[0] = 0.0; root->v.V[1] = 0.0; root->v.G[1] = 0.0;
   for (int k = 0; k < NCHILD; ++k) root->child[k] = 0;
   tree_nodes[tree] = 1;
   tree_iters[tree] = 0;

@@ -130,24 +130,24 @@ __device__ __noinline__ uint32_t exact_ucb_argmax(StatRegs<NACT> r, uint32_t mas
   return best;
 }
 
-// UctStatistic::choose_next_action, reference uct_statistic.h:61-76 (+ :122-132, :223-244, :256-262).
+// UctStatistic::choose_next_action, reference uct_statistic.h:61-76 (+ :122-132, :223-244, :256-262),
+// on the register image of a statistic; no memory is written. `widened` = the action was newly
+// expanded (ucb_statistics_[a] = UcbPair(), the caller records it in its own record layout).
 // Also returns (in `back`) the values the backup of this level will need for the chosen action.
 template <int NACT>
-__device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRegs<NACT>& r,
-                                                  const SearchParams& p, int cls, uint32_t nact,
-                                                  unsigned long long& exact_evals, BackRegs& back) {
+__device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const SearchParams& p, int cls,
+                                                  uint32_t nact, unsigned long long& exact_evals,
+                                                  BackRegs& back, bool& widened) {
   const uint32_t N = r.N;
   const uint32_t nexp = r.nexp;
   back.nv0 = N;
   back.v = r.V;
+  widened = false;
   if (nexp < nact && N >= p.tab->pw_min_visits[cls][nexp]) {  // require_progressive_widening_total
-    const uint32_t a = p.tab->order[cls][nexp];               // :64-68 (deterministic order, F2)
-    s->nexp = nexp + 1;
-    s->Q[a] = 0.0;                                            // ucb_statistics_[a] = UcbPair()
-    s->n[a] = 0;
+    widened = true;
     back.cnt0 = 0;
     back.q = 0.0;
-    return a;
+    return p.tab->order[cls][nexp];                           // :64-68 (deterministic order, F2)
   }
   const uint32_t mask = p.tab->exp_mask[cls][nexp];
   double q[NACT];
@@ -232,6 +232,21 @@ __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRe
   return best;
 }
 
+// select_action on a classic StatRec: records a newly expanded action in place.
+template <int NACT>
+__device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRegs<NACT>& r,
+                                                  const SearchParams& p, int cls, uint32_t nact,
+                                                  unsigned long long& exact_evals, BackRegs& back) {
+  bool widened;
+  const uint32_t a = select_action<NACT>(r, p, cls, nact, exact_evals, back, widened);
+  if (widened) {
+    s->nexp = r.nexp + 1;
+    s->Q[a] = 0.0;  // ucb_statistics_[a] = UcbPair()
+    s->n[a] = 0;
+  }
+  return a;
+}
+
 // Loads the backup inputs of one statistic (only used below the recorded path, see deep_backup).
 template <int NACT>
 __device__ __forceinline__ BackRegs back_load(const StatRec<NACT>* s, uint32_t act) {
@@ -243,27 +258,38 @@ __device__ __forceinline__ BackRegs back_load(const StatRec<NACT>* s, uint32_t a
   return b;
 }
 
-// UctStatistic::update_statistics_from_backpropagated, reference uct_statistic.h:134-144.
-template <int NACT>
-__device__ __forceinline__ double back_apply(StatRec<NACT>* s, uint32_t act, const BackRegs& b, double r,
-                                             double gamma, double child_G) {
-  const uint32_t cnt0 = b.cnt0, nv0 = b.nv0;
-  const double q = b.q, v = b.v;
-  const double G = __dadd_rn(r, __dmul_rn(gamma, child_G));
-  const uint32_t cnt = cnt0 + 1, nv = nv0 + 1;
+// UctStatistic::update_statistics_from_backpropagated, reference uct_statistic.h:134-144, as pure
+// arithmetic: G = r + gamma G_child, n_a += 1, Q_a += (G - Q_a) / n_a, N += 1, V += (G - V) / N.
+struct BackOut {
+  double G, q, v;
+  uint32_t cnt, nv;
+};
+
+__device__ __forceinline__ BackOut back_compute(const BackRegs& b, double r, double gamma, double child_G) {
+  BackOut o;
+  o.G = __dadd_rn(r, __dmul_rn(gamma, child_G));
+  o.cnt = b.cnt0 + 1;
+  o.nv = b.nv0 + 1;
   // x + (d / k) with d == +-0 is x + d for any k > 0 (the quotient keeps d's signed zero), so the
   // division is skipped when the running mean already equals the return - always the case for the
   // reward-free other agents of CrossingState.
-  const double dq = __dsub_rn(G, q);
-  const double dv = __dsub_rn(G, v);
-  const double qn = (dq == 0.0) ? __dadd_rn(q, dq) : __dadd_rn(q, __ddiv_rn(dq, (double)cnt));
-  const double vn = (dv == 0.0) ? __dadd_rn(v, dv) : __dadd_rn(v, __ddiv_rn(dv, (double)nv));
-  s->n[act] = cnt;
-  s->Q[act] = qn;
-  s->N = nv;
-  s->V = vn;
-  s->G = G;
-  return G;
+  const double dq = __dsub_rn(o.G, b.q);
+  const double dv = __dsub_rn(o.G, b.v);
+  o.q = (dq == 0.0) ? __dadd_rn(b.q, dq) : __dadd_rn(b.q, __ddiv_rn(dq, (double)o.cnt));
+  o.v = (dv == 0.0) ? __dadd_rn(b.v, dv) : __dadd_rn(b.v, __ddiv_rn(dv, (double)o.nv));
+  return o;
+}
+
+template <int NACT>
+__device__ __forceinline__ double back_apply(StatRec<NACT>* s, uint32_t act, const BackRegs& b, double r,
+                                             double gamma, double child_G) {
+  const BackOut o = back_compute(b, r, gamma, child_G);
+  s->n[act] = o.cnt;
+  s->Q[act] = o.q;
+  s->N = o.nv;
+  s->V = o.v;
+  s->G = o.G;
+  return o.G;
 }
 
 template <int A>
@@ -565,6 +591,7 @@ __global__ void search_reset_kernel(void* nodes_v, uint32_t* tree_nodes, uint32_
   root->r_in[0] = 0.0;
   root->r_in[1] = 0.0;
   root->ego.V = 0.0; root->ego.G = 0.0; root->ego.N = 0; root->ego.nexp = 0;
+  for (int a = 0; a < NE; ++a) { root->ego.Q[a] = 0.0; root->ego.n[a] = 0; }  // the root merge reads n[a] > 0 as "expanded"
   for (int j = 0; j < Env::A - 1; ++j) { root->oth[j].V = 0.0; root->oth[j].G = 0.0; root->oth[j].N = 0; root->oth[j].nexp = 0; }
   for (int k = 0; k < (NCHILD > 0 ? NCHILD : 1); ++k) root->child[k] = 0;
   tree_nodes[tree] = 1;

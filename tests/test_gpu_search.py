@@ -264,6 +264,28 @@ def test_compact_and_classic_layouts_agree_on_large_trees(engine):
     t.close()
 
 
+@pytest.mark.parametrize("max_iter,max_nodes", [(70000, 5000), (70000, 100000000)])
+def test_compact_layout_wide_counters(engine, max_iter, max_nodes):
+    """The compact record has three instantiations: 16-bit counts and child entries (searches below
+    65 535 iterations: every other test), 32-bit counts with 16-bit entries, and 32-bit both; the
+    latter two are selected by MAX_NUMBER_OF_ITERATIONS / the node capacity of the configuration."""
+    iters = 700
+    mp = default_params(max_number_of_iterations=max_iter, max_number_of_nodes=max_nodes,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    s = Search(engine, ENV_CROSSING_I32, mp, 40, cp=cp, action_source=SRC_PHILOX, philox_seed=31,
+               layout=LAYOUT_COMPACT, max_inner_nodes_per_tree=1000)
+    s.run(iters)
+    for tree in (0, 39):
+        t = O.OracleTree(O.make_env(cp=cp), mp, [5, 5], action_source=SRC_PHILOX, seed=31, tree_id=tree)
+        t.run(iters)
+        assert np.array_equal(s.dump_tree(tree, iters + 1), t.dump(7))
+        t.close()
+    m = s.merge_roots()
+    assert m["visits"] == 40 * iters
+    s.close()
+
+
 def test_compact_layout_reports_exhausted_inner_records(engine):
     mp = default_params(max_number_of_iterations=2000, max_number_of_nodes=100000000,
                         rh_max_number_of_iterations=50)
