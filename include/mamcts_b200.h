@@ -44,6 +44,8 @@ extern "C" {
 #define MAMCTS_SRC_REPLAY 0          /* consume recorded reference joint actions           */
 #define MAMCTS_SRC_REFERENCE_CONST 1 /* the reference's constant first-draw action (F1)    */
 #define MAMCTS_SRC_PHILOX 2          /* counter-based Philox4x32-10 uniform sampling       */
+#define MAMCTS_SRC_HYPOTHESIS 3      /* CrossingState: other agents follow their behaviour
+                                        hypothesis (gap-keeping policy), ego uniform (C4)  */
 
 /* environments */
 #define MAMCTS_ENV_SIMPLE 0          /* test/uct/simple_state.h                            */
@@ -122,6 +124,14 @@ typedef struct mamcts_action_source {
   const uint32_t* stream_lo;        /* optional per-leaf, may be NULL */
   uint32_t stream_hi_base;
   uint32_t stream_lo_base;
+  /* HYPOTHESIS (CrossingState only; Philox streams as above): the desired-gap range [lo, hi] of the
+   * behaviour hypothesis currently assigned to other agent j of leaf i, at [j * n + i] - what
+   * HypothesisBeliefTracker::sample_current_hypothesis (mcts/hypothesis/hypothesis_belief_tracker.h:
+   * 136-149) selected for this iteration. Every step the agent draws a gap uniformly from the range
+   * (AgentPolicyCrossingState<int>::act, environments/crossing_state_agent_policy.h:68-75) and moves
+   * by calculate_action (:35-55); the ego agent draws uniformly among its actions. */
+  const int32_t* hyp_gap_lo;
+  const int32_t* hyp_gap_hi;
 } mamcts_action_source;
 
 /* Outputs of a batched rollout. Any pointer may be NULL (not produced). `mem` says where they

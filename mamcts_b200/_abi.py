@@ -15,7 +15,7 @@ NCCL_UNIQUE_ID_BYTES = 128
 
 OK = 0
 MEM_HOST, MEM_DEVICE = 0, 1
-SRC_REPLAY, SRC_REFERENCE_CONST, SRC_PHILOX = 0, 1, 2
+SRC_REPLAY, SRC_REFERENCE_CONST, SRC_PHILOX, SRC_HYPOTHESIS = 0, 1, 2, 3
 ENV_SIMPLE, ENV_CROSSING_I32 = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
@@ -102,6 +102,8 @@ class ActionSource(C.Structure):
         ("stream_lo", C.c_void_p),
         ("stream_hi_base", C.c_uint32),
         ("stream_lo_base", C.c_uint32),
+        ("hyp_gap_lo", C.c_void_p),
+        ("hyp_gap_hi", C.c_void_p),
     ]
 
 

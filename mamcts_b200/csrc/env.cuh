@@ -16,6 +16,7 @@ struct EnvParams {
   int32_t crossing_point;   // CROSSING_POINT() = (CHAIN_LENGTH-1)/2+1, :28
   int32_t goal_pos;
   int32_t cost_only_collision;
+  int32_t min_v_other, max_v_other;   // MIN/MAX_VELOCITY_OTHER (behaviour-hypothesis policy)
   uint32_t n_ego_actions;   // NUM_EGO_ACTIONS(), :25
   uint32_t n_other_actions;
   // SimpleState (reference test/uct/simple_state.h:16)
@@ -35,6 +36,8 @@ inline void make_crossing_env(const mamcts_crossing_params& cp, EnvParams& ep) {
   ep.crossing_point = (cp.chain_length - 1) / 2 + 1;   // CROSSING_POINT(), crossing_state_parameters.h:28
   ep.goal_pos = cp.ego_goal_pos;
   ep.cost_only_collision = cp.cost_only_collision;
+  ep.min_v_other = cp.min_velocity_other;
+  ep.max_v_other = cp.max_velocity_other;
   ep.n_ego_actions = (uint32_t)(cp.max_velocity_ego - cp.min_velocity_ego + 1);
   ep.n_other_actions = cp.num_other_actions;
   for (int f = 0; f < 8; ++f) {
@@ -99,6 +102,18 @@ struct CrossingEnv {
     cost = p.c_tab[f];
   }
 };
+
+// AgentPolicyCrossingState<int>::calculate_action (reference
+// environments/crossing_state_agent_policy.h:35-55): the velocity an other agent chooses for a desired
+// gap to the ego agent, whose position is predicted one step ahead from its last action.
+__device__ __forceinline__ int32_t crossing_policy_action(const EnvParams& p, int32_t agent_x, int32_t agent_last,
+                                                          int32_t ego_x, int32_t ego_last, int32_t desired_gap) {
+  if (agent_x >= p.crossing_point) return agent_last;                  // :51-53
+  const int32_t gap_error = ego_x + ego_last - agent_x - desired_gap;  // :39
+  if (desired_gap > 0)                                                 // :41-46
+    return gap_error < 0 ? max(gap_error, p.min_v_other) : min(gap_error, p.max_v_other);
+  return max(min(gap_error, p.max_v_other), agent_last);               // :47-50
+}
 
 // SimpleState: one int32 of state, 2 agents x 2 actions (reference test/uct/simple_state.h).
 struct SimpleEnv {

@@ -38,6 +38,8 @@ struct RolloutParams {
   const uint32_t* stream_hi;
   const uint32_t* stream_lo;
   uint32_t stream_hi_base, stream_lo_base;
+  const int32_t* hyp_lo;   // HYPOTHESIS: desired-gap range of other j of leaf i at [j * n_leaves + i]
+  const int32_t* hyp_hi;
   // mcts
   const double* disc;      // [0, disc_len): reward weight of step k; [disc_len, 2 disc_len): (1/nA_ego)^k
   uint32_t disc_len;
@@ -59,7 +61,8 @@ struct RolloutParams {
 
 template <class Env, int KIND>
 struct StepsPerBlock {
-  static constexpr int value = (KIND == MAMCTS_SRC_PHILOX && Env::A <= 8) ? 8 / Env::A : 1;
+  static constexpr bool kPhilox = KIND == MAMCTS_SRC_PHILOX || KIND == MAMCTS_SRC_HYPOTHESIS;
+  static constexpr int value = (kPhilox && Env::A <= 8) ? 8 / Env::A : 1;
 };
 
 template <class Env, int KIND, bool PARITY>
@@ -68,6 +71,8 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
   constexpr int A = Env::A;
   constexpr int S = StepsPerBlock<Env, KIND>::value;
   constexpr bool kSimple = std::is_same<Env, SimpleEnv>::value;
+  constexpr bool kPhilox = StepsPerBlock<Env, KIND>::kPhilox;   // draws come from the Philox stream
+  constexpr bool kHyp = KIND == MAMCTS_SRC_HYPOTHESIS;
   constexpr int XR = kSimple ? 1 : A;  // rows of the x arrays (SimpleState: only state_length_)
   const uint32_t G = gridDim.x * blockDim.x;
   uint32_t rid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,6 +86,7 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
   uint32_t it = 0, depth = 0, cap = 0, leaf = 0, s_lo = 0, s_hi = 0;
   bool has = false, fin = true;
   unsigned long long lane_steps = 0;
+  int32_t gap_lo[kHyp ? A : 1], gap_span[kHyp ? A : 1];   // [a]: other agent at position a (a >= 1)
 
   auto load = [&]() {
     has = rid < p.total;
@@ -95,9 +101,16 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
     depth = p.depth ? __ldg(p.depth + leaf) : 0u;
     cap = p.rh_cap;
     if (KIND == MAMCTS_SRC_REPLAY) cap = min(cap, __ldg(p.replay_steps + leaf));
-    if (KIND == MAMCTS_SRC_PHILOX) {
+    if (kPhilox) {
       s_hi = p.stream_hi ? __ldg(p.stream_hi + leaf) : p.stream_hi_base;
       s_lo = p.stream_lo ? __ldg(p.stream_lo + leaf) + (rid - leaf * p.K) : p.stream_lo_base + rid;
+    }
+    if (kHyp) {
+#pragma unroll
+      for (int a = 1; a < A; ++a) {
+        gap_lo[a] = __ldg(p.hyp_lo + (size_t)(a - 1) * p.n_leaves + leaf);
+        gap_span[a] = max(__ldg(p.hyp_hi + (size_t)(a - 1) * p.n_leaves + leaf) - gap_lo[a] + 1, 1);  // lo <= hi (agent_policy.h:28)
+      }
     }
     ego = 0.0; cost = 0.0; r_other_last = 0.0; it = 0;   // random_heuristic.h:36-49
     fin = Env::terminal(p.env, st) | (it >= cap) | (depth >= p.max_depth);  // :51-54
@@ -148,7 +161,7 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
 
     const bool active0 = has && !fin;
     Philox4 blk[(A + 7) / 8];
-    if (KIND == MAMCTS_SRC_PHILOX && active0) {
+    if (kPhilox && active0) {
       if (A <= 8) {
         blk[0] = philox4x32_10(it / S, s_lo, s_hi, 0u, p.key0, p.key1);
       } else {
@@ -169,9 +182,21 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
             act[a] = (int32_t)p.const_actions[a];
           } else {
             const uint32_t h = (A <= 8) ? philox_half(blk[0], s * A + a) : philox_half(blk[a / 8], a % 8);
-            act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi,
-                                             p.key0, p.key1);
+            if (kHyp && a > 0) {
+              // the agent's gap for this step (AgentPolicyCrossingState<int>::act, agent_policy.h:68-75);
+              // the policy itself reads the PRE-step state, so it runs after all draws (below)
+              act[a] = gap_lo[kHyp ? a : 0] + (int32_t)philox_bounded(h, (uint32_t)gap_span[kHyp ? a : 0], it * A + a,
+                                                                     s_lo, s_hi, p.key0, p.key1);
+            } else {
+              act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi,
+                                               p.key0, p.key1);
+            }
           }
+        }
+        if (kHyp && !kSimple) {
+#pragma unroll
+          for (int a = 1; a < A; ++a)
+            act[a] = crossing_policy_action(p.env, st.x[a], st.last[a], st.x[0], st.last[0], act[a]);
         }
         double r_ego, r_other, c;
         Env::step(p.env, st, act, r_ego, r_other, c);
@@ -263,6 +288,10 @@ static int launch_rollout(mamcts_engine* e, const RolloutParams& p, int kind, bo
   } while (0)
   if (kind == MAMCTS_SRC_REPLAY) MAMCTS_LAUNCH(MAMCTS_SRC_REPLAY);
   else if (kind == MAMCTS_SRC_REFERENCE_CONST) MAMCTS_LAUNCH(MAMCTS_SRC_REFERENCE_CONST);
+  else if (kind == MAMCTS_SRC_HYPOTHESIS) {
+    if constexpr (std::is_same<Env, SimpleEnv>::value) return fail(e, MAMCTS_ERR_INVALID, "rollout: HYPOTHESIS is a CrossingState action source");
+    else MAMCTS_LAUNCH(MAMCTS_SRC_HYPOTHESIS);
+  }
   else MAMCTS_LAUNCH(MAMCTS_SRC_PHILOX);
 #undef MAMCTS_LAUNCH
   e->launches += 1;
@@ -304,8 +333,10 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   if ((uint64_t)n * K > 0xF0000000ull) return fail(e, MAMCTS_ERR_INVALID, "rollout: n_leaves * K too large for one call");
   if (src->kind == MAMCTS_SRC_REPLAY && (K != 1 || !src->replay_actions || !src->replay_steps))
     return fail(e, MAMCTS_ERR_INVALID, "rollout: REPLAY needs K == 1 and replay buffers");
-  if (src->kind < MAMCTS_SRC_REPLAY || src->kind > MAMCTS_SRC_PHILOX)
+  if (src->kind < MAMCTS_SRC_REPLAY || src->kind > MAMCTS_SRC_HYPOTHESIS)
     return fail(e, MAMCTS_ERR_INVALID, "rollout: unknown action source");
+  if (src->kind == MAMCTS_SRC_HYPOTHESIS && (env_kind != MAMCTS_ENV_CROSSING_I32 || !src->hyp_gap_lo || !src->hyp_gap_hi))
+    return fail(e, MAMCTS_ERR_INVALID, "rollout: HYPOTHESIS needs CrossingState and the per-leaf gap ranges");
   if (src->kind == MAMCTS_SRC_REFERENCE_CONST) {
     for (uint32_t a = 0; a < A; ++a) {
       const uint32_t na = (env_kind == MAMCTS_ENV_SIMPLE) ? 2u : (a == 0 ? ep.n_ego_actions : ep.n_other_actions);
@@ -325,10 +356,14 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
                              (size_t)n * src->replay_stride * A, src->mem, false);
   const int t_reps = stg.plan(src->kind == MAMCTS_SRC_REPLAY ? src->replay_steps : nullptr,
                               sizeof(uint32_t) * n, src->mem, false);
-  const int t_shi = stg.plan(src->kind == MAMCTS_SRC_PHILOX ? src->stream_hi : nullptr,
+  const int t_shi = stg.plan((src->kind == MAMCTS_SRC_PHILOX || src->kind == MAMCTS_SRC_HYPOTHESIS) ? src->stream_hi : nullptr,
                              sizeof(uint32_t) * n, src->mem, false);
-  const int t_slo = stg.plan(src->kind == MAMCTS_SRC_PHILOX ? src->stream_lo : nullptr,
-                             sizeof(uint32_t) * n, src->mem, false);
+  const bool philox_like = src->kind == MAMCTS_SRC_PHILOX || src->kind == MAMCTS_SRC_HYPOTHESIS;
+  const int t_slo = stg.plan(philox_like ? src->stream_lo : nullptr, sizeof(uint32_t) * n, src->mem, false);
+  const int t_hlo = stg.plan(src->kind == MAMCTS_SRC_HYPOTHESIS ? src->hyp_gap_lo : nullptr,
+                             sizeof(int32_t) * (A - 1) * n, src->mem, false);
+  const int t_hhi = stg.plan(src->kind == MAMCTS_SRC_HYPOTHESIS ? src->hyp_gap_hi : nullptr,
+                             sizeof(int32_t) * (A - 1) * n, src->mem, false);
   const int o_ego = stg.plan(out->ego_return, sizeof(double) * n, out->mem, true);
   const int o_oth = stg.plan(out->other_return, sizeof(double) * (A - 1) * n, out->mem, true);
   const int o_cost = stg.plan(out->ego_cost, sizeof(double) * n, out->mem, true);
@@ -357,6 +392,8 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   p.key1 = (uint32_t)(src->philox_seed >> 32);
   p.stream_hi = stg.dev<const uint32_t>(t_shi);
   p.stream_lo = stg.dev<const uint32_t>(t_slo);
+  p.hyp_lo = stg.dev<const int32_t>(t_hlo);
+  p.hyp_hi = stg.dev<const int32_t>(t_hhi);
   p.stream_hi_base = src->stream_hi_base;
   p.stream_lo_base = src->stream_lo_base;
   {

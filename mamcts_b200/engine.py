@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (ENV_CROSSING_I32, ENV_SIMPLE, MAX_ACTIONS, MEM_DEVICE, MEM_HOST, SRC_PHILOX,
+from ._abi import (ENV_CROSSING_I32, ENV_SIMPLE, MAX_ACTIONS, MEM_DEVICE, MEM_HOST, SRC_HYPOTHESIS, SRC_PHILOX,
                    SRC_REFERENCE_CONST, SRC_REPLAY, ActionSource, Config, CrossingParams, Params,
                    RolloutOut, SearchConfig, SimpleParams, UctStats)
 
@@ -119,7 +119,8 @@ class Engine:
     # -- rollouts -----------------------------------------------------------------------------
     @staticmethod
     def _source(kind, A, replay_actions=None, replay_steps=None, const_actions=None, seed=0,
-                stream_hi=None, stream_hi_base=0, stream_lo_base=0, stream_lo=None, mem=MEM_HOST):
+                stream_hi=None, stream_hi_base=0, stream_lo_base=0, stream_lo=None, mem=MEM_HOST,
+                hyp_gap_lo=None, hyp_gap_hi=None):
         src = ActionSource()
         src.kind = kind
         src.mem = mem
@@ -156,6 +157,15 @@ class Engine:
                     src.stream_lo = sl.ctypes.data
                 else:
                     src.stream_lo = int(stream_lo)
+            if kind == SRC_HYPOTHESIS:
+                # [A-1, n] desired-gap ranges of the other agents' current hypotheses
+                if mem == MEM_HOST:
+                    lo = np.ascontiguousarray(hyp_gap_lo, dtype=np.int32)
+                    hi = np.ascontiguousarray(hyp_gap_hi, dtype=np.int32)
+                    keep += [lo, hi]
+                    src.hyp_gap_lo, src.hyp_gap_hi = lo.ctypes.data, hi.ctypes.data
+                else:
+                    src.hyp_gap_lo, src.hyp_gap_hi = int(hyp_gap_lo), int(hyp_gap_hi)
         return src, keep
 
     def _rollout_host(self, env, mp, envp, A, x, last, flags, depth, K, src_kw, want_parity,

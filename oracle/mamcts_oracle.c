@@ -190,11 +190,28 @@ static void orc_execute_idx(const orc_env* env, const orc_state* s, const uint32
 /* Rollout                                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 
+int32_t orc_crossing_policy_action(const mamcts_crossing_params* cp, int32_t agent_x, int32_t agent_last,
+                                   int32_t ego_x, int32_t ego_last, int32_t desired_gap) {
+  const int32_t crossing_point = (cp->chain_length - 1) / 2 + 1;  /* crossing_state_parameters.h:28 */
+  if (agent_x < crossing_point) {                                 /* agent_policy.h:37 */
+    /* forward-predicted ego position from its last action, :39 */
+    const int32_t gap_error = ego_x + ego_last - agent_x - desired_gap;
+    if (desired_gap > 0) {                                        /* :41-46 */
+      if (gap_error < 0) return gap_error > cp->min_velocity_other ? gap_error : cp->min_velocity_other;
+      return gap_error < cp->max_velocity_other ? gap_error : cp->max_velocity_other;
+    }
+    /* already ahead of the ego agent: never brake below the last velocity, :47-50 */
+    const int32_t v = gap_error < cp->max_velocity_other ? gap_error : cp->max_velocity_other;
+    return v > agent_last ? v : agent_last;
+  }
+  return agent_last;                                              /* past the crossing point, :51-53 */
+}
+
 void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* start,
                  uint32_t start_depth, int32_t kind, const int8_t* replay, uint32_t replay_steps,
                  const uint32_t* const_actions, uint64_t seed, uint32_t stream_hi,
-                 uint32_t stream_lo, orc_rollout_result* out, double* reward_trace,
-                 uint32_t trace_cap) {
+                 uint32_t stream_lo, const int32_t* gap_lo, const int32_t* gap_hi,
+                 orc_rollout_result* out, double* reward_trace, uint32_t trace_cap) {
   const uint32_t A = env->num_agents;
   orc_state state = *start;
   double ego = 0.0;                         /* random_heuristic.h:38 */
@@ -217,6 +234,14 @@ void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* s
         act[a] = replay[(size_t)it * A + a];
       } else if (kind == MAMCTS_SRC_REFERENCE_CONST) {
         act[a] = (int32_t)const_actions[a];
+      } else if (kind == MAMCTS_SRC_HYPOTHESIS && a > 0) {
+        /* HypothesisStatistic::choose_next_action of a fresh statistic samples from the hypothesis
+         * (hypothesis_statistic.h:70-81) -> CrossingState::plan_action_current_hypothesis
+         * (crossing_state.h:78-82) -> AgentPolicyCrossingState<int>::act (agent_policy.h:68-75) */
+        const uint32_t span = (uint32_t)(gap_hi[a - 1] - gap_lo[a - 1] + 1);
+        const int32_t gap = gap_lo[a - 1] + (int32_t)orc_philox_draw(seed, stream_hi, stream_lo, A, it, a, span);
+        act[a] = orc_crossing_policy_action(&env->crossing, state.x[a], state.last[a], state.x[0],
+                                            state.last[0], gap);
       } else {
         act[a] = (int32_t)orc_philox_draw(seed, stream_hi, stream_lo, A, it, a,
                                           env->num_actions[a]);
@@ -536,7 +561,7 @@ static void orc_tree_iterate(orc_tree* t) {
       uint32_t const_actions[ORC_MAX_AGENTS];
       for (uint32_t a = 0; a < A; ++a) const_actions[a] = t->cfg.expand_order[a][0];
       orc_rollout(env, mp, &nd->state, nd->depth, t->cfg.action_source, NULL, 0, const_actions,
-                  t->cfg.philox_seed, t->cfg.tree_id, node * K + k, &rr, NULL, 0);
+                  t->cfg.philox_seed, t->cfg.tree_id, node * K + k, NULL, NULL, &rr, NULL, 0);
       t->rollout_steps += rr.steps;
       ego[k] = rr.ego_return;
       for (uint32_t j = 0; j + 1 < A; ++j) oth[(size_t)j * K + k] = rr.other_return[j];

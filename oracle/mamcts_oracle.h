@@ -71,15 +71,22 @@ typedef struct orc_rollout_result {
   orc_state final_state;
 } orc_rollout_result;
 
+/* AgentPolicyCrossingState<int>::calculate_action (environments/crossing_state_agent_policy.h:35-55):
+ * the velocity an other agent chooses for a desired gap to the (forward-predicted) ego agent. */
+int32_t orc_crossing_policy_action(const mamcts_crossing_params* cp, int32_t agent_x, int32_t agent_last,
+                                   int32_t ego_x, int32_t ego_last, int32_t desired_gap);
+
 /* One rollout. Action source as in mamcts_action_source but for ONE rollout:
  *   kind REPLAY: replay[step*A + agent] (int8), replay_steps steps available;
- *   kind REFERENCE_CONST: const_actions[agent]; kind PHILOX: (seed, stream_hi, stream_lo).
+ *   kind REFERENCE_CONST: const_actions[agent]; kind PHILOX: (seed, stream_hi, stream_lo);
+ *   kind HYPOTHESIS: other agent j (position j+1) draws a gap uniformly in [gap_lo[j], gap_hi[j]] from
+ *   its Philox position and acts by orc_crossing_policy_action; the ego draws like PHILOX.
  * reward_trace (optional) receives the ego step rewards, up to trace_cap entries. */
 void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* start,
                  uint32_t start_depth, int32_t kind, const int8_t* replay, uint32_t replay_steps,
                  const uint32_t* const_actions, uint64_t seed, uint32_t stream_hi,
-                 uint32_t stream_lo, orc_rollout_result* out, double* reward_trace,
-                 uint32_t trace_cap);
+                 uint32_t stream_lo, const int32_t* gap_lo, const int32_t* gap_hi,
+                 orc_rollout_result* out, double* reward_trace, uint32_t trace_cap);
 
 /* The K-rollout mean of one leaf in the engine's fixed reduction order.
  * vals[k], k < K. K in {1,2,4,8,16} or a multiple of 32 (<=256) or a multiple of 256. */

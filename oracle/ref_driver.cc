@@ -24,6 +24,7 @@
 #include "mcts/mcts.h"
 #include "mcts/heuristics/random_heuristic.h"
 #include "mcts/statistics/uct_statistic.h"
+#include "mcts/hypothesis/hypothesis_statistic.h"
 #include "environments/crossing_state.h"
 #include "test/uct/simple_state.h"
 
@@ -119,6 +120,42 @@ class RecState : public StateInterface<RecState<Inner>> {
   std::shared_ptr<Inner> inner_;
 };
 
+// The same for a hypothesis state: HypothesisStatistic::choose_next_action reaches the state through
+// HypothesisStateInterface (mcts/hypothesis/hypothesis_statistic.h:62-81), so the wrapper forwards
+// plan_action_current_hypothesis as well.
+template <class Inner>
+class RecHypState : public HypothesisStateInterface<RecHypState<Inner>> {
+ public:
+  RecHypState(std::shared_ptr<Inner> inner, const std::unordered_map<AgentIdx, HypothesisId>& hyp)
+      : HypothesisStateInterface<RecHypState<Inner>>(hyp), inner_(std::move(inner)), hyp_(hyp) {}
+  std::shared_ptr<RecHypState> clone() const { return std::make_shared<RecHypState>(inner_->clone(), hyp_); }
+  std::shared_ptr<RecHypState> execute(const JointAction& ja, std::vector<Reward>& rewards, EgoCosts& cost) const {
+    auto next = inner_->execute(ja, rewards, cost);
+    if (g_recorder) {
+      StepRecord rec;
+      for (auto a : ja) rec.action.push_back(static_cast<long long>(a));
+      rec.rewards = rewards;
+      rec.cost = cost;
+      rec.terminal_after = next->is_terminal();
+      g_recorder->steps.push_back(rec);
+    }
+    return std::make_shared<RecHypState>(next, hyp_);
+  }
+  ActionIdx plan_action_current_hypothesis(const AgentIdx& a) const { return inner_->plan_action_current_hypothesis(a); }
+  ActionIdx get_num_actions(AgentIdx a) const { return inner_->get_num_actions(a); }
+  bool is_terminal() const { return inner_->is_terminal(); }
+  const std::vector<AgentIdx> get_other_agent_idx() const { return inner_->get_other_agent_idx(); }
+  const AgentIdx get_ego_agent_idx() const { return inner_->get_ego_agent_idx(); }
+  const std::size_t get_num_costs() const { return inner_->get_num_costs(); }
+  double get_execution_step_length() const { return inner_->get_execution_step_length(); }
+  void choose_random_seed(const unsigned& s) { inner_->choose_random_seed(s); }
+  std::string sprintf() const { return inner_->sprintf(); }
+
+ private:
+  std::shared_ptr<Inner> inner_;
+  const std::unordered_map<AgentIdx, HypothesisId>& hyp_;
+};
+
 // Long-lived pieces a CrossingState<int> keeps references to (crossing_state.h:320, hypothesis_state.h:42).
 struct CrossingWorld {
   CrossingStateParameters<int> params;
@@ -185,7 +222,7 @@ class PhiloxHeuristic : public mcts::Heuristic<PhiloxHeuristic> {
     for (uint32_t k = 0; k < c.K; ++k) {
       orc_rollout_result rr;
       orc_rollout(&c.env, &c.mp, &st, node->get_depth(), MAMCTS_SRC_PHILOX, nullptr, 0, nullptr,
-                  c.seed, c.tree_id, calls_ * c.K + k, &rr, nullptr, 0);
+                  c.seed, c.tree_id, calls_ * c.K + k, nullptr, nullptr, &rr, nullptr, 0);
       c.rollout_steps += rr.steps;
       ego[k] = rr.ego_return;
       for (uint32_t j = 0; j + 1 < A; ++j) oth[static_cast<size_t>(j) * c.K + k] = rr.other_return[j];
@@ -374,6 +411,82 @@ int ref_rollout_crossing(const mamcts_params* mp, const mamcts_crossing_params* 
                 static_cast<int8_t>(aconv<int>(ja[a]));
         }
         if (rec_rewards) rec_rewards[static_cast<size_t>(i) * rec_stride + s] = rec.steps[s].rewards[0];
+      }
+    }
+    orc_state fs;
+    pack_state(*cur, &fs);
+    for (uint32_t a = 0; a < A; ++a) {
+      if (final_x) final_x[a * n + i] = fs.x[a];
+      if (final_last) final_last[a * n + i] = fs.last[a];
+    }
+    if (final_flags) final_flags[i] = (fs.terminal ? 1 : 0) | (fs.goal ? 2 : 0) | (fs.collided ? 4 : 0);
+  }
+  return 0;
+}
+
+// AgentPolicyCrossingState<int>::calculate_action (environments/crossing_state_agent_policy.h:35-55)
+// on n independent inputs.
+int ref_policy_calculate_action(const mamcts_crossing_params* cp, uint32_t n, const int32_t* agent_x,
+                                const int32_t* agent_last, const int32_t* ego_x, const int32_t* ego_last,
+                                const int32_t* gap, int32_t* out) {
+  const CrossingStateParameters<int> params = to_ref_crossing(*cp);
+  AgentPolicyCrossingState<int> policy({0, 1}, params);
+  for (uint32_t i = 0; i < n; ++i)
+    out[i] = policy.calculate_action(AgentState<int>(agent_x[i], agent_last[i]),
+                                     AgentState<int>(ego_x[i], ego_last[i]), gap[i]);
+  return 0;
+}
+
+// RandomHeuristic::rollout with HypothesisStatistic for the other agents (the C4 instantiation:
+// Mcts<CrossingState<int>, UctStatistic, HypothesisStatistic, RandomHeuristic>, reference
+// environments/crossing_state_episode_runner.h:61): other agent j follows hypothesis
+// cur_hyp[j] of the n_hyp hypotheses {[hyp_lo[h], hyp_hi[h]]}. Records the joint actions (ego index,
+// other agents' Domain values) for REPLAY and returns the rollout's results and final state.
+int ref_rollout_crossing_hypothesis(const mamcts_params* mp, const mamcts_crossing_params* cp, uint32_t n,
+                                    const int32_t* x, const int32_t* last, const uint32_t* depth,
+                                    uint32_t n_hyp, const int32_t* hyp_lo, const int32_t* hyp_hi,
+                                    const uint32_t* cur_hyp /* [(A-1)*n] */, double* ego_ret,
+                                    double* other_ret, double* cost0, double* step_len, uint32_t* steps,
+                                    int32_t* final_x, int32_t* final_last, uint8_t* final_flags,
+                                    int8_t* rec_actions, uint32_t rec_stride) {
+  const MctsParameters rp = to_ref_params(*mp);
+  const CrossingStateParameters<int> params = to_ref_crossing(*cp);
+  const uint32_t A = cp->num_other_agents + 1;
+  using RS = RecHypState<CrossingState<int>>;
+  for (uint32_t i = 0; i < n; ++i) {
+    std::unordered_map<AgentIdx, HypothesisId> hyp_map;
+    for (AgentIdx j = 1; j < A; ++j) hyp_map[j] = cur_hyp[(j - 1) * n + i];
+    std::vector<AgentPolicyCrossingState<int>> policies;
+    for (uint32_t h = 0; h < n_hyp; ++h) policies.emplace_back(std::make_pair(hyp_lo[h], hyp_hi[h]), params);
+    std::vector<AgentState<int>> others;
+    for (uint32_t a = 1; a < A; ++a) others.emplace_back(x[a * n + i], last ? last[a * n + i] : 2);
+    AgentState<int> ego(x[i], last ? last[i] : 2);
+    auto inner = std::make_shared<CrossingState<int>>(hyp_map, params, others, ego, false, false, false, policies);
+    auto start = std::make_shared<RS>(inner, hyp_map);
+    Recorder rec;
+    g_recorder = &rec;
+    auto result = RandomHeuristic::rollout<RS, UctStatistic, HypothesisStatistic, RandomHeuristic>(
+        start, rp, depth ? depth[i] : 0);
+    g_recorder = nullptr;
+    ego_ret[i] = std::get<0>(result);
+    const auto& oth = std::get<1>(result);
+    for (uint32_t j = 0; j + 1 < A; ++j) other_ret[j * n + i] = oth.at(j + 1);
+    const auto& costs = std::get<2>(result);
+    cost0[i] = costs.empty() ? 0.0 : costs[0];
+    step_len[i] = std::get<3>(result);
+    steps[i] = static_cast<uint32_t>(rec.steps.size());
+    // replay on a plain state (no policies needed) for the final state
+    std::shared_ptr<CrossingState<int>> cur = std::make_shared<CrossingState<int>>(
+        hyp_map, params, others, ego, false, false, false, std::vector<AgentPolicyCrossingState<int>>());
+    for (size_t s = 0; s < rec.steps.size(); ++s) {
+      JointAction ja(A);
+      for (uint32_t a = 0; a < A; ++a) ja[a] = static_cast<ActionIdx>(rec.steps[s].action[a]);
+      std::vector<Reward> r; EgoCosts c;
+      cur = cur->execute(ja, r, c);
+      if (s < rec_stride && rec_actions) {
+        rec_actions[(static_cast<size_t>(i) * rec_stride + s) * A + 0] = static_cast<int8_t>(ja[0]);
+        for (uint32_t a = 1; a < A; ++a)
+          rec_actions[(static_cast<size_t>(i) * rec_stride + s) * A + a] = static_cast<int8_t>(aconv<int>(ja[a]));
       }
     }
     orc_state fs;

@@ -113,6 +113,46 @@ def gen_rollouts():
     dump("rollout_simple.json", scases)
 
 
+def gen_hypothesis():
+    """C4 (BASELINE.json configs[3]): the rollout path of hypothesis-MCTS. (a) the gap-keeping policy
+    AgentPolicyCrossingState<int>::calculate_action, (b) rollouts of
+    RandomHeuristic::rollout<.., UctStatistic, HypothesisStatistic, ..> with the hypothesis sets of the
+    reference's own tests (environments/tests/crossing_state_int_test.cc:105-106 and :190-192), recorded
+    for REPLAY."""
+    rng = np.random.default_rng(4242)
+    pol = []
+    for chain, vmin, vmax in ((21, -3, 3), (41, -2, 4)):
+        cp = default_crossing_params(chain_length=chain, min_velocity_other=vmin, max_velocity_other=vmax)
+        n = 600
+        ax = rng.integers(-2, chain, n); al = rng.integers(vmin, vmax + 1, n)
+        ex = rng.integers(-2, chain, n); el = rng.integers(-1, 3, n); gap = rng.integers(-6, 9, n)
+        out = O.ref_policy_calculate_action(cp, ax, al, ex, el, gap)
+        pol.append(dict(chain_length=chain, min_velocity_other=vmin, max_velocity_other=vmax,
+                        agent_x=ax.tolist(), agent_last=al.tolist(), ego_x=ex.tolist(), ego_last=el.tolist(),
+                        gap=gap.tolist(), action=out.tolist()))
+    cases = []
+    for seed, num_others, hyps in ((1000, 2, [(4, 5), (5, 6)]), (1000, 2, [(-2, 1), (2, 3), (4, 5)]),
+                                   (7, 3, [(4, 5), (5, 6)]), (42, 1, [(1, 4)])):
+        mp = default_params(random_seed=seed, rh_max_number_of_iterations=50)
+        cp = default_crossing_params(num_other_agents=num_others)
+        A = num_others + 1
+        n = 48
+        x = rng.integers(0, 12, size=(A, n)).astype(np.int32)
+        x[:, 0] = 5
+        last = rng.integers(-1, 3, size=(A, n)).astype(np.int32)
+        last[:, 0] = 2
+        cur = rng.integers(0, len(hyps), size=(num_others, n)).astype(np.uint32)
+        lo = [h[0] for h in hyps]; hi = [h[1] for h in hyps]
+        r = O.ref_rollout_crossing_hypothesis(mp, cp, x, last, lo, hi, cur, rec_stride=50)
+        cases.append(dict(seed=seed, num_others=num_others, hyp_lo=lo, hyp_hi=hi, cur_hyp=cur.tolist(),
+                          x=x.tolist(), last=last.tolist(), ego_return=fhex(r["ego_return"]),
+                          other_return=fhex(r["other_return"]), ego_cost=fhex(r["ego_cost"]),
+                          step_length=fhex(r["step_length"]), steps=r["steps"].tolist(),
+                          final_x=r["final_x"].tolist(), final_last_action=r["final_last_action"].tolist(),
+                          final_flags=r["final_flags"].tolist(), rec_actions=r["rec_actions"].tolist()))
+    dump("hypothesis.json", dict(policy=pol, rollouts=cases))
+
+
 def gen_search():
     cases = []
     # C1: SimpleState(4), 20 iterations (reference test/uct/uct_test.cc:22-40 parameters)
@@ -164,5 +204,6 @@ if __name__ == "__main__":
     gen_expand_order()
     gen_execute()
     gen_rollouts()
+    gen_hypothesis()
     gen_search()
     gen_merge()

@@ -182,8 +182,17 @@ def crossing_execute(cp: CrossingParams, x, last, action):
     return list(nxt.x[:A]), list(nxt.last[:A]), flags, r.value, c0.value
 
 
+def crossing_policy_action(cp: CrossingParams, agent_x, agent_last, ego_x, ego_last, gap) -> int:
+    """Oracle AgentPolicyCrossingState<int>::calculate_action."""
+    f = oracle().orc_crossing_policy_action
+    f.restype = C.c_int32
+    return int(f(C.byref(cp), C.c_int32(agent_x), C.c_int32(agent_last), C.c_int32(ego_x), C.c_int32(ego_last),
+                 C.c_int32(gap)))
+
+
 def rollout(env: OrcEnv, mp: Params, x, last=None, terminal=False, depth=0, kind=SRC_PHILOX,
-            replay=None, const_actions=None, seed=0, stream_hi=0, stream_lo=0, trace_cap=0):
+            replay=None, const_actions=None, seed=0, stream_hi=0, stream_lo=0, trace_cap=0,
+            gap_lo=None, gap_hi=None):
     """One oracle rollout; returns a dict."""
     st = make_state(x, last, terminal)
     res = OrcRolloutResult()
@@ -195,9 +204,11 @@ def rollout(env: OrcEnv, mp: Params, x, last=None, terminal=False, depth=0, kind
         rp = _ptr(rep)
     ca = (C.c_uint32 * MAX_AGENTS)(*(const_actions or []))
     trace = np.zeros(max(trace_cap, 1), dtype=np.float64)
+    glo = (C.c_int32 * MAX_AGENTS)(*[int(v) for v in gap_lo]) if gap_lo is not None else None
+    ghi = (C.c_int32 * MAX_AGENTS)(*[int(v) for v in gap_hi]) if gap_hi is not None else None
     oracle().orc_rollout(C.byref(env), C.byref(mp), C.byref(st), C.c_uint32(depth),
                          C.c_int32(kind), rp, C.c_uint32(nrep), ca, C.c_uint64(seed),
-                         C.c_uint32(stream_hi), C.c_uint32(stream_lo), C.byref(res),
+                         C.c_uint32(stream_hi), C.c_uint32(stream_lo), glo, ghi, C.byref(res),
                          _ptr(trace) if trace_cap else None, C.c_uint32(trace_cap))
     A = env.num_agents
     fs = res.final_state
@@ -211,7 +222,8 @@ def rollout(env: OrcEnv, mp: Params, x, last=None, terminal=False, depth=0, kind
 
 def rollout_batch(env: OrcEnv, mp: Params, x, last=None, flags=None, depth=None, K=1,
                   kind=SRC_PHILOX, replay=None, replay_steps=None, const_actions=None, seed=0,
-                  stream_hi=None, stream_hi_base=0, stream_lo_base=0, stream_lo=None, trace_stride=0):
+                  stream_hi=None, stream_hi_base=0, stream_lo_base=0, stream_lo=None, trace_stride=0,
+                  hyp_gap_lo=None, hyp_gap_hi=None):
     """Oracle counterpart of mamcts_rollout_* over n leaves x K rollouts (same output layout)."""
     x = np.asarray(x, dtype=np.int32)
     A = env.num_agents
@@ -236,7 +248,9 @@ def rollout_batch(env: OrcEnv, mp: Params, x, last=None, flags=None, depth=None,
             r = rollout(env, mp, x[:, i], None if last is None else np.asarray(last)[:, i],
                         bool(flags[i] & 1) if flags is not None else False,
                         int(depth[i]) if depth is not None else 0, kind, rep, const_actions, seed,
-                        hi, lo, trace_stride)
+                        hi, lo, trace_stride,
+                        None if hyp_gap_lo is None else np.asarray(hyp_gap_lo)[:, i],
+                        None if hyp_gap_hi is None else np.asarray(hyp_gap_hi)[:, i])
             idx = i * K + k
             ego[k], cost[k], sl[k] = r["ego_return"], r["cost0"], r["step_length"]
             for j in range(A - 1):
@@ -365,6 +379,41 @@ def ref_rollout_crossing(mp: Params, cp: CrossingParams, x, last=None, flags=Non
         _ptr(out["step_length"]), _ptr(out["steps"]), _ptr(out["final_x"]),
         _ptr(out["final_last_action"]), _ptr(out["final_flags"]), _ptr(out["rec_actions"]),
         _ptr(out["rec_rewards"]), C.c_uint32(rec_stride))
+    return out
+
+
+def ref_policy_calculate_action(cp: CrossingParams, agent_x, agent_last, ego_x, ego_last, gap):
+    """The reference's AgentPolicyCrossingState<int>::calculate_action on n inputs."""
+    arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (agent_x, agent_last, ego_x, ego_last, gap)]
+    out = np.zeros(arrs[0].shape[0], dtype=np.int32)
+    reference().ref_policy_calculate_action(C.byref(cp), C.c_uint32(out.shape[0]), *[_ptr(a) for a in arrs],
+                                            _ptr(out))
+    return out
+
+
+def ref_rollout_crossing_hypothesis(mp: Params, cp: CrossingParams, x, last, hyp_lo, hyp_hi, cur_hyp,
+                                    depth=None, rec_stride=64):
+    """RandomHeuristic::rollout<.., UctStatistic, HypothesisStatistic, ..> on n start states; other agent
+    j of state i follows hypothesis cur_hyp[j, i] of {[hyp_lo[h], hyp_hi[h]]}. Records the joint actions."""
+    x = np.ascontiguousarray(x, dtype=np.int32)
+    A, n = x.shape
+    last_a = None if last is None else np.ascontiguousarray(last, dtype=np.int32)
+    depth_a = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+    lo = np.ascontiguousarray(hyp_lo, dtype=np.int32)
+    hi = np.ascontiguousarray(hyp_hi, dtype=np.int32)
+    cur = np.ascontiguousarray(cur_hyp, dtype=np.uint32)
+    out = dict(ego_return=np.zeros(n), other_return=np.zeros((A - 1, n)), ego_cost=np.zeros(n),
+               step_length=np.zeros(n), steps=np.zeros(n, dtype=np.uint32),
+               final_x=np.zeros((A, n), dtype=np.int32),
+               final_last_action=np.zeros((A, n), dtype=np.int32),
+               final_flags=np.zeros(n, dtype=np.uint8),
+               rec_actions=np.zeros((n, rec_stride, A), dtype=np.int8))
+    reference().ref_rollout_crossing_hypothesis(
+        C.byref(mp), C.byref(cp), C.c_uint32(n), _ptr(x), _ptr(last_a), _ptr(depth_a),
+        C.c_uint32(lo.shape[0]), _ptr(lo), _ptr(hi), _ptr(cur), _ptr(out["ego_return"]),
+        _ptr(out["other_return"]), _ptr(out["ego_cost"]), _ptr(out["step_length"]), _ptr(out["steps"]),
+        _ptr(out["final_x"]), _ptr(out["final_last_action"]), _ptr(out["final_flags"]),
+        _ptr(out["rec_actions"]), C.c_uint32(rec_stride))
     return out
 
 

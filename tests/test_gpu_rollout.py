@@ -12,7 +12,7 @@ import pytest
 import oracle_api as O
 from helpers import assert_bit_equal, golden, unhex
 from mamcts_b200 import default_crossing_params, default_params, default_simple_params
-from mamcts_b200._abi import SRC_PHILOX, SRC_REFERENCE_CONST, SRC_REPLAY
+from mamcts_b200._abi import SRC_HYPOTHESIS, SRC_PHILOX, SRC_REFERENCE_CONST, SRC_REPLAY
 from mamcts_b200.engine import MamctsError
 
 pytestmark = pytest.mark.gpu
@@ -100,6 +100,62 @@ def test_crossing_philox_equals_oracle(engine, num_others):
     exp = O.rollout_batch(O.make_env(cp=cp), mp, x, None, flags, depth, K=1, **kw)
     _check_against(out, exp, A, n, 1)
     assert out["final_last_action"].tolist() == exp["final_last_action"].tolist()
+
+
+def test_hypothesis_golden_replay_bit_exact(engine):
+    """C4 rollout path: rollouts recorded from the reference's
+    RandomHeuristic::rollout<.., UctStatistic, HypothesisStatistic, ..> (other agents follow their
+    behaviour hypothesis, incl. negative velocities) replayed on the GPU: same terminal state, step
+    count, returns and cost, bit for bit."""
+    for case in golden("hypothesis.json")["rollouts"]:
+        mp = default_params(random_seed=case["seed"], rh_max_number_of_iterations=50)
+        cp = default_crossing_params(num_other_agents=case["num_others"])
+        x, last = np.array(case["x"], dtype=np.int32), np.array(case["last"], dtype=np.int32)
+        A, n = x.shape
+        out = engine.rollout_crossing(mp, cp, x, last, K=1, parity=True, kind=SRC_REPLAY,
+                                      replay_actions=np.array(case["rec_actions"], dtype=np.int8),
+                                      replay_steps=np.array(case["steps"], dtype=np.uint32))
+        assert out["steps"].tolist() == case["steps"]
+        assert out["final_x"].tolist() == case["final_x"]
+        assert out["final_last_action"].tolist() == case["final_last_action"]
+        assert out["final_flags"].tolist() == case["final_flags"]
+        assert_bit_equal(out["ego_return"], unhex(case["ego_return"]), "ego return")
+        assert_bit_equal(out["ego_cost"], unhex(case["ego_cost"]), "cost")
+        assert_bit_equal(out["other_return"], unhex(case["other_return"], (A - 1, n)), "other return")
+        assert_bit_equal(out["step_length"], unhex(case["step_length"]), "step length")
+
+
+@pytest.mark.parametrize("num_others", [1, 2, 3, 7])
+def test_hypothesis_source_equals_oracle(engine, num_others):
+    """MAMCTS_SRC_HYPOTHESIS: other agents draw a gap from their hypothesis' range and act by the
+    gap-keeping policy on the device; equal to the oracle driven by the same Philox streams."""
+    rng = np.random.default_rng(500 + num_others)
+    A = num_others + 1
+    mp = default_params(rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=num_others, reward_step=-0.5)
+    n = 171
+    x = rng.integers(0, 12, size=(A, n)).astype(np.int32)
+    last = rng.integers(-1, 3, size=(A, n)).astype(np.int32)
+    depth = rng.integers(0, 5, size=n).astype(np.uint32)
+    hyps = np.array([(4, 5), (5, 6), (-2, 1), (2, 3), (0, 0)])
+    pick = rng.integers(0, len(hyps), size=(num_others, n))
+    lo, hi = hyps[pick, 0].astype(np.int32), hyps[pick, 1].astype(np.int32)
+    stream_hi = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    for K in (1, 4):
+        kw = dict(kind=SRC_HYPOTHESIS, seed=0xABCDEF0123, stream_hi=stream_hi, stream_lo_base=17,
+                  hyp_gap_lo=lo, hyp_gap_hi=hi)
+        out = engine.rollout_crossing(mp, cp, x, last, None, depth, K=K, parity=True, **kw)
+        exp = O.rollout_batch(O.make_env(cp=cp), mp, x, last, None, depth, K=K, **kw)
+        _check_against(out, exp, A, n, K)
+        assert out["final_last_action"].tolist() == exp["final_last_action"].tolist()
+    assert (out["final_last_action"][1:] < 0).any()      # braking happened
+
+
+def test_hypothesis_source_rejects_bad_arguments(engine):
+    mp = default_params(rh_max_number_of_iterations=10)
+    with pytest.raises(MamctsError, match="HYPOTHESIS"):
+        engine.rollout_simple(mp, default_simple_params(), np.zeros(4, dtype=np.int32), kind=SRC_HYPOTHESIS,
+                              hyp_gap_lo=np.zeros((1, 4), dtype=np.int32), hyp_gap_hi=np.zeros((1, 4), dtype=np.int32))
 
 
 @pytest.mark.parametrize("K", [2, 4, 8, 16, 32, 64, 96, 256, 512])
