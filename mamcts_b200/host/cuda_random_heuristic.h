@@ -162,7 +162,15 @@ class CudaRandomHeuristic : public mcts::Heuristic<CudaRandomHeuristic> {
       src.stream_hi_base = opt.tree_id;
       src.stream_lo_base = call_index * opt.rollouts_per_leaf;
     }
-    const uint32_t K = opt.action_source == MAMCTS_SRC_PHILOX ? opt.rollouts_per_leaf : 1;
+    // HYPOTHESIS (hypothesis-MCTS, S derives from HypothesisStateInterface): the other agents follow the
+    // hypotheses the belief tracker sampled for this iteration (mcts.h:143-164)
+    int32_t gap_lo[MAMCTS_MAX_AGENTS] = {0}, gap_hi[MAMCTS_MAX_AGENTS] = {0};
+    if (opt.action_source == MAMCTS_SRC_HYPOTHESIS) {
+      pack_hypotheses_if_any<S>(state, gap_lo, gap_hi);
+      src.hyp_gap_lo = gap_lo;
+      src.hyp_gap_hi = gap_hi;
+    }
+    const uint32_t K = opt.action_source == MAMCTS_SRC_REFERENCE_CONST ? 1 : opt.rollouts_per_leaf;
 
     double ego_ret = 0.0, cost0 = 0.0, step_len = 0.0;
     double other_ret[MAMCTS_MAX_AGENTS] = {0.0};
@@ -187,6 +195,17 @@ class CudaRandomHeuristic : public mcts::Heuristic<CudaRandomHeuristic> {
     EgoCosts accum_cost(state.get_num_costs(), 0.0);
     if (!accum_cost.empty()) accum_cost[0] = cost0;
     return std::make_tuple(ego_ret, other_accum_rewards, accum_cost, step_len);
+  }
+
+  template <class S>
+  static auto pack_hypotheses_if_any(const S& state, int32_t* lo, int32_t* hi)
+      -> decltype(CudaState<S>::pack_hypotheses(state, lo, hi), void()) {
+    CudaState<S>::pack_hypotheses(state, lo, hi);
+  }
+  template <class S>
+  static void pack_hypotheses_if_any(...) {
+    std::cerr << "MAMCTS_SRC_HYPOTHESIS needs a hypothesis state (CrossingState)" << std::endl;
+    std::terminate();
   }
 
   template <class S>

@@ -13,6 +13,7 @@
 
 #include <cstdint>
 #include <stdexcept>
+#include <utility>
 #include <vector>
 
 #include "mamcts_b200.h"
@@ -48,6 +49,26 @@ struct CudaState<CrossingState<int>> {
     p.reward_collision = c.REWARD_COLLISION;
     p.reward_goal_reached = c.REWARD_GOAL_REACHED;
     p.reward_step = c.REWARD_STEP;
+  }
+  // Behaviour hypotheses (MAMCTS_SRC_HYPOTHESIS): CrossingState keeps its AgentPolicyCrossingState
+  // objects private (crossing_state.h:313) and a policy hides its desired-gap range
+  // (crossing_state_agent_policy.h:61), so the host registers the same ranges it passed to
+  // add_hypothesis(), in the same order (index = HypothesisId).
+  static std::vector<std::pair<int32_t, int32_t>>& hypotheses() {
+    static std::vector<std::pair<int32_t, int32_t>> h;
+    return h;
+  }
+  static void set_hypotheses(const std::vector<std::pair<int32_t, int32_t>>& gap_ranges) { hypotheses() = gap_ranges; }
+  // desired-gap range of the hypothesis currently assigned to every other agent (positional)
+  static void pack_hypotheses(const CrossingState<int>& s, int32_t* gap_lo, int32_t* gap_hi) {
+    const std::vector<AgentIdx> others = s.get_other_agent_idx();
+    for (size_t j = 0; j < others.size(); ++j) {
+      const HypothesisId h = s.get_current_hypothesis(others[j]);
+      if (h >= hypotheses().size())
+        throw std::logic_error("CudaState<CrossingState<int>>: set_hypotheses() does not cover the state's hypotheses");
+      gap_lo[j] = hypotheses()[h].first;
+      gap_hi[j] = hypotheses()[h].second;
+    }
   }
   static uint32_t num_agents(const CrossingState<int>& s) { return s.get_num_agents(); }
   // x / last: [A] positional; flags bit0 = terminal

@@ -1,0 +1,104 @@
+// tests/dropin/dropin_hypothesis.cc - C4 (BASELINE.json configs[3]) through the reference's own host
+// code: Mcts<CrossingState<int>, UctStatistic, HypothesisStatistic, H>::search(state, belief_tracker)
+// with H = CudaRandomHeuristic in MAMCTS_SRC_HYPOTHESIS mode, i.e. every rollout runs on the GPU with
+// the other agents following the hypotheses the belief tracker sampled for the iteration. Mirrors the
+// reference's closed-loop tests environments/tests/crossing_state_int_test.cc:141-229
+// (mcts_goal_reached_true_hypothesis, mcts_goal_reached_wrong_hypothesis): plan, act, update the belief,
+// until the ego agent reaches its goal without a collision. Wall-clock limits are replaced by an
+// iteration budget. Built by oracle/Makefile (target dropin).
+#include "gtest/gtest.h"
+
+#include "mcts/mcts.h"
+#include "mcts/heuristics/random_heuristic.h"
+#include "mcts/statistics/uct_statistic.h"
+#include "mcts/hypothesis/hypothesis_statistic.h"
+#include "mcts/hypothesis/hypothesis_belief_tracker.h"
+#include "environments/crossing_state.h"
+
+#include "cuda_random_heuristic.h"
+#include "cuda_state.h"
+
+using namespace mcts;
+typedef int Domain;
+
+static MctsParameters hypothesis_params(unsigned iterations) {
+  MctsParameters p = mcts_default_parameters();
+  p.MAX_NUMBER_OF_ITERATIONS = iterations;
+  p.MAX_SEARCH_TIME = 1000000000;
+  p.random_heuristic.MAX_SEARCH_TIME = 1e9;
+  p.random_heuristic.MAX_NUMBER_OF_ITERATIONS = 50;
+  return p;
+}
+
+template <class H>
+static bool closed_loop(const std::vector<std::pair<int, int>>& hypotheses, std::pair<int, int> true_policy_gap,
+                        unsigned iterations, int max_steps, bool* collision, int* steps_taken) {
+  const auto params = default_crossing_state_parameters<Domain>();
+  CudaState<CrossingState<Domain>>::set_parameters(params);
+  CudaState<CrossingState<Domain>>::set_hypotheses(hypotheses);
+  auto mcts_params = hypothesis_params(iterations);
+  HypothesisBeliefTracker belief_tracker(mcts_params);
+  auto state = std::make_shared<CrossingState<Domain>>(belief_tracker.sample_current_hypothesis(), params);
+  for (const auto& h : hypotheses) state->add_hypothesis(AgentPolicyCrossingState<Domain>(h, params));
+  auto next_state = state;
+  belief_tracker.belief_update(*state, *next_state);
+  AgentPolicyCrossingState<Domain> true_agents_policy(true_policy_gap, params);
+  std::vector<Reward> rewards;
+  EgoCosts cost;
+  *collision = false;
+  int i = 0;
+  for (; i < max_steps; ++i) {
+    auto jointaction = JointAction(state->get_num_agents());
+    Mcts<CrossingState<Domain>, UctStatistic, HypothesisStatistic, H> mcts(mcts_params);
+    mcts.search(*state, belief_tracker);
+    jointaction[CrossingState<Domain>::ego_agent_idx] = mcts.returnBestAction();
+    for (auto agent_idx : state->get_other_agent_idx()) {
+      const auto action = true_agents_policy.act(state->get_agent_state(agent_idx), state->get_ego_state());
+      jointaction[agent_idx] = aconv<Domain>(action);
+    }
+    next_state = state->execute(jointaction, rewards, cost);
+    belief_tracker.belief_update(*state, *next_state);
+    state = next_state;
+    if (state->is_terminal() && !state->ego_goal_reached()) { *collision = true; break; }
+    if (state->is_terminal()) break;
+  }
+  *steps_taken = i + 1;
+  return state->ego_goal_reached();
+}
+
+TEST(dropin_hypothesis, mcts_goal_reached_true_hypothesis_cuda_rollouts) {
+  CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();
+  CudaRandomHeuristic::options().action_source = MAMCTS_SRC_HYPOTHESIS;
+  CudaRandomHeuristic::options().rollouts_per_leaf = 8;
+  bool collision = false;
+  int steps = 0;
+  const bool goal = closed_loop<CudaRandomHeuristic>({{5, 5}}, {5, 5}, 1500, 100, &collision, &steps);
+  std::printf("  true hypothesis: goal %d collision %d after %d steps\n", (int)goal, (int)collision, steps);
+  EXPECT_TRUE(goal);
+  EXPECT_FALSE(collision);
+}
+
+TEST(dropin_hypothesis, mcts_goal_reached_wrong_hypothesis_cuda_rollouts) {
+  CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();
+  CudaRandomHeuristic::options().action_source = MAMCTS_SRC_HYPOTHESIS;
+  CudaRandomHeuristic::options().rollouts_per_leaf = 8;
+  bool collision = false;
+  int steps = 0;
+  const bool goal = closed_loop<CudaRandomHeuristic>({{-2, 1}, {2, 3}, {4, 5}}, {-2, -2}, 1500, 30, &collision, &steps);
+  std::printf("  wrong hypothesis: goal %d collision %d after %d steps\n", (int)goal, (int)collision, steps);
+  EXPECT_TRUE(goal);
+  EXPECT_FALSE(collision);
+}
+
+// the same loops with the stock heuristic, as a sanity check of the harness itself
+TEST(dropin_hypothesis, stock_heuristic_reaches_goal_too) {
+  bool collision = false;
+  int steps = 0;
+  EXPECT_TRUE(closed_loop<RandomHeuristic>({{5, 5}}, {5, 5}, 1500, 100, &collision, &steps));
+  EXPECT_FALSE(collision);
+}
+
+int main(int argc, char** argv) {
+  ::testing::InitGoogleTest(&argc, argv);
+  return RUN_ALL_TESTS();
+}

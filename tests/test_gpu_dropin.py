@@ -54,3 +54,14 @@ def test_reference_verify_uct_on_gpu_rollouts():
     for name in ("dropin_mcts.reference_verify_uct_simple_state_cuda_heuristic",
                  "dropin_mcts.reference_small_search_depth_cuda_heuristic"):
         assert f"PASS {name}" in out, out[-4000:]
+
+
+def test_reference_hypothesis_mcts_closed_loop_with_gpu_rollouts():
+    """C4: the reference's closed-loop hypothesis tests (crossing_state_int_test.cc:141-229) with every
+    rollout on the GPU (MAMCTS_SRC_HYPOTHESIS through CudaRandomHeuristic)."""
+    out = _run("dropin_hypothesis", timeout=900)
+    assert "FAIL" not in out and " 0 failures" in out, out[-4000:]
+    for name in ("dropin_hypothesis.mcts_goal_reached_true_hypothesis_cuda_rollouts",
+                 "dropin_hypothesis.mcts_goal_reached_wrong_hypothesis_cuda_rollouts",
+                 "dropin_hypothesis.stock_heuristic_reaches_goal_too"):
+        assert f"PASS {name}" in out, out[-4000:]
