@@ -144,6 +144,7 @@ void mamcts_destroy(mamcts_engine* e) {
   if (e->staging) cudaFree(e->staging);
   if (e->pinned) cudaFreeHost(e->pinned);
   if (e->disc) cudaFree(e->disc);
+  if (e->work_cursor) cudaFree(e->work_cursor);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }

@@ -23,6 +23,8 @@ struct mamcts_engine {
   size_t staging_bytes = 0;
   void* pinned = nullptr;   // pinned host staging
   size_t pinned_bytes = 0;
+  // work-list cursor of the persistent rollout kernel (one uint32, zeroed per launch)
+  unsigned int* work_cursor = nullptr;
   // discount / probability tables of the rollout (see ensure_discount_table)
   double* disc = nullptr;
   uint32_t disc_len = 0;

@@ -2,8 +2,9 @@
 // mcts/heuristics/random_heuristic.h:27-104) as a persistent CUDA kernel for sm_100a.
 //
 // Mapping: one lane = one episode, state in registers; a warp keeps 32 episodes in flight and
-// refills finished lanes from the grid-strided work list in a warp-uniform "service" step, so the
-// environment step always runs converged. PHILOX draws are laid out so that one Philox4x32-10 block
+// refills finished lanes from a global work list (one atomicAdd per refill of a whole warp) in a
+// warp-uniform "service" step, so the environment step always runs converged and no lane idles while
+// rollouts are left - episode lengths vary by 5x, a static assignment left 40 % of the lanes idle. PHILOX draws are laid out so that one Philox4x32-10 block
 // feeds S = 8/A consecutive steps and all lanes of a warp regenerate their block at the same loop
 // iteration. K > 1 rollouts per leaf go through a per-rollout scratch and a fixed-
 // order warp-shuffle segmented reduction (reduce.cu), so the means are deterministic.
@@ -57,6 +58,7 @@ struct RolloutParams {
   double* trace;
   uint32_t trace_stride;
   unsigned long long* total_steps;
+  unsigned int* work_cursor;   // rollouts handed out beyond the statically assigned first grid*threads
 };
 
 template <class Env, int KIND>
@@ -74,8 +76,7 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
   constexpr bool kPhilox = StepsPerBlock<Env, KIND>::kPhilox;   // draws come from the Philox stream
   constexpr bool kHyp = KIND == MAMCTS_SRC_HYPOTHESIS;
   constexpr int XR = kSimple ? 1 : A;  // rows of the x arrays (SimpleState: only state_length_)
-  const uint32_t G = gridDim.x * blockDim.x;
-  uint32_t rid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t rid = blockIdx.x * blockDim.x + threadIdx.x;   // first rollout: static; later ones from the cursor
 
   typename Env::State st;
   // Return accumulation (random_heuristic.h:71-88) without per-step FP64 work: the weight of step k
@@ -150,9 +151,16 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
     const unsigned need = __ballot_sync(FULL, has && fin);
     const unsigned running = __ballot_sync(FULL, has && !fin);
     if (need != 0 && (running == 0 || __popc(need) >= kServiceThreshold)) {
+      // the finished lanes take the next popc(need) rollouts of the global list
+      uint32_t base = 0;
+      const uint32_t leader = __ffs(need) - 1;
+      if ((threadIdx.x & 31u) == leader) base = atomicAdd(p.work_cursor, (unsigned int)__popc(need));
+      base = __shfl_sync(FULL, base, leader);
       if (has && fin) {
         finalize();
-        rid += G;
+        const uint32_t rank = __popc(need & ((1u << (threadIdx.x & 31u)) - 1u));
+        // lanes past the end stop asking, so the cursor never exceeds total + launched lanes < 2^32
+        rid = gridDim.x * blockDim.x + base + rank;
         load();
       }
       continue;
@@ -223,12 +231,18 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
 //   K < 32 : K-lane segments, xor-butterfly K/2..1, mean = total / K
 //   K >= 32: one warp per leaf; lane l sums vals[c*32R + j*32 + l], j < R = min(K/32, 8), then a
 //            32-lane xor-butterfly; chunk partials are added in chunk order.
-// blockIdx.y selects the array (src + y*src_stride -> dst + y*dst_stride).
+// blockIdx.y selects the array: per-rollout values at src + y*src_stride -> per-leaf means at dst.p[y]
+// (null = not requested), so one launch reduces ego, every other agent, cost and step length.
+struct ReduceDst {
+  double* p[MAMCTS_MAX_AGENTS + 2];
+};
+
 __global__ void __launch_bounds__(256)
-reduce_mean_kernel(const double* __restrict__ src, double* __restrict__ dst, uint32_t n, uint32_t K,
-                   size_t src_stride, size_t dst_stride) {
+reduce_mean_kernel(const double* __restrict__ src, const __grid_constant__ ReduceDst dsts, uint32_t n, uint32_t K,
+                   size_t src_stride) {
+  double* __restrict__ dst = dsts.p[blockIdx.y];
+  if (!dst) return;
   src += (size_t)blockIdx.y * src_stride;
-  dst += (size_t)blockIdx.y * dst_stride;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
@@ -268,12 +282,16 @@ static bool valid_k(uint32_t K) {
 
 // Persistent grid: as many blocks as stay resident (occupancy x SM count), never more than the work.
 template <class Kernel>
-static int launch_persistent(mamcts_engine* e, Kernel kernel, const RolloutParams& p) {
+static int launch_persistent(mamcts_engine* e, Kernel kernel, RolloutParams p) {
   int per_sm = 0;
   MAMCTS_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRolloutThreads, 0));
   const int max_blocks = e->num_sms * std::max(per_sm, 1);
   const int need_blocks = (int)(((uint64_t)p.total + kRolloutThreads - 1) / kRolloutThreads);
   const int grid = std::max(1, std::min(max_blocks, need_blocks));
+  // the first grid*threads rollouts are assigned statically, the cursor hands out the rest
+  if (!e->work_cursor) MAMCTS_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&e->work_cursor), sizeof(unsigned int)));
+  MAMCTS_CUDA(e, cudaMemsetAsync(e->work_cursor, 0, sizeof(unsigned int), e->stream));
+  p.work_cursor = e->work_cursor;
   kernel<<<dim3(grid), dim3(kRolloutThreads), 0, e->stream>>>(p);
   return MAMCTS_OK;
 }
@@ -442,13 +460,15 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   if (K > 1) {
     const double* s = static_cast<const double*>(e->scratch);
     const int rgrid = std::max(1, std::min(grid_for(e, 4), (int)((n + 7) / 8)));
-    if (d_ego) { reduce_mean_kernel<<<dim3(rgrid, 1), 256, 0, e->stream>>>(s, d_ego, n, K, 0, 0); e->launches++; }
-    if (d_oth && A > 1) {
-      reduce_mean_kernel<<<dim3(rgrid, A - 1), 256, 0, e->stream>>>(s + (size_t)total, d_oth, n, K, total, n);
-      e->launches++;
-    }
-    if (d_cost) { reduce_mean_kernel<<<dim3(rgrid, 1), 256, 0, e->stream>>>(s + (size_t)A * total, d_cost, n, K, 0, 0); e->launches++; }
-    if (d_len) { reduce_mean_kernel<<<dim3(rgrid, 1), 256, 0, e->stream>>>(s + (size_t)(A + 1) * total, d_len, n, K, 0, 0); e->launches++; }
+    // scratch rows: 0 ego, 1..A-1 others, A cost, A+1 step length (all `total` apart): one launch
+    ReduceDst dsts;
+    std::memset(&dsts, 0, sizeof(dsts));
+    dsts.p[0] = d_ego;
+    for (uint32_t j = 0; j + 1 < A; ++j) dsts.p[1 + j] = d_oth ? d_oth + (size_t)j * n : nullptr;
+    dsts.p[A] = d_cost;
+    dsts.p[A + 1] = d_len;
+    reduce_mean_kernel<<<dim3(rgrid, n_arrays), 256, 0, e->stream>>>(s, dsts, n, K, total);
+    e->launches++;
     MAMCTS_CUDA(e, cudaGetLastError());
   }
   return stg.finish();
