@@ -9,6 +9,7 @@
 // iteration. K > 1 rollouts per leaf go through a per-rollout scratch and a fixed-
 // order warp-shuffle segmented reduction (reduce.cu), so the means are deterministic.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -58,6 +59,7 @@ struct RolloutParams {
   double* trace;
   uint32_t trace_stride;
   unsigned long long* total_steps;
+  uint32_t service_threshold;  // finished lanes that trigger a refill while others still run
   unsigned int* work_cursor;   // rollouts handed out beyond the statically assigned first grid*threads
 };
 
@@ -150,7 +152,7 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
   while (true) {
     const unsigned need = __ballot_sync(FULL, has && fin);
     const unsigned running = __ballot_sync(FULL, has && !fin);
-    if (need != 0 && (running == 0 || __popc(need) >= kServiceThreshold)) {
+    if (need != 0 && (running == 0 || __popc(need) >= (int)p.service_threshold)) {
       // the finished lanes take the next popc(need) rollouts of the global list
       uint32_t base = 0;
       const uint32_t leader = __ffs(need) - 1;
@@ -292,6 +294,11 @@ static int launch_persistent(mamcts_engine* e, Kernel kernel, RolloutParams p) {
   if (!e->work_cursor) MAMCTS_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&e->work_cursor), sizeof(unsigned int)));
   MAMCTS_CUDA(e, cudaMemsetAsync(e->work_cursor, 0, sizeof(unsigned int), e->stream));
   p.work_cursor = e->work_cursor;
+  p.service_threshold = kServiceThreshold;
+  if (const char* v = std::getenv("MAMCTS_ROLLOUT_SERVICE")) {   // experiment knob (profiles/)
+    const int t = std::atoi(v);
+    if (t >= 1 && t <= 32) p.service_threshold = (uint32_t)t;
+  }
   kernel<<<dim3(grid), dim3(kRolloutThreads), 0, e->stream>>>(p);
   return MAMCTS_OK;
 }
