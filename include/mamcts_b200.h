@@ -251,6 +251,51 @@ int mamcts_backup_uct(mamcts_engine* e, const mamcts_params* mp, uint32_t num_ag
                       const uint32_t* edge_node, const uint8_t* edge_action,
                       const double* edge_reward, mamcts_uct_stats* stats);
 
+/* ---- backup: HypothesisStatistic (mcts/hypothesis/hypothesis_statistic.h), C4 ----------------- */
+
+/* Statistic storage of the OTHER agents in hypothesis-MCTS, SoA over slots s = node * num_others + j
+ * (j = other agent position - 1). Mirrors HypothesisStatistic's members (hypothesis_statistic.h:
+ * 310-318): ego_cost_value_, latest_ego_cost_, total_node_visits_, num_expanded_actions_,
+ * total_node_visits_hypothesis_[h] and ucb_statistics_[h][a].{action_count_, action_ego_cost_}.
+ * visits_hypothesis has num_hypotheses + 1 entries per slot: the last one is the key
+ * HYPOTHESIS_ID_NOT_SET that a statistic which never chose an action counts its heuristic update
+ * under (update_from_heuristic :100-110 reads hypothesis_id_current_iteration_ of a fresh object).
+ * Actions are small indices chosen by the caller (for CrossingState: velocity - MIN_VELOCITY_OTHER;
+ * the reference keys its maps by the bit-cast Domain value). */
+typedef struct mamcts_hyp_stats {
+  int32_t mem;
+  uint32_t num_slots;         /* nodes * num_others */
+  uint32_t num_hypotheses;    /* H */
+  uint32_t max_actions;       /* MA */
+  double* ego_cost_value;     /* [num_slots] */
+  double* latest_ego_cost;    /* [num_slots] */
+  uint32_t* total_visits;     /* [num_slots] */
+  uint32_t* num_expanded;     /* [num_slots] */
+  uint32_t* visits_hypothesis;/* [num_slots * (H + 1)] */
+  double* action_cost;        /* [num_slots * H * MA] */
+  uint32_t* action_count;     /* [num_slots * H * MA] */
+} mamcts_hyp_stats;
+
+/* One batch of independent backup paths for the other agents' HypothesisStatistic, the C4 counterpart
+ * of mamcts_backup_uct (same path / edge layout; the ego agent's UctStatistic goes through
+ * mamcts_backup_uct):
+ *   leaf update : update_from_heuristic (hypothesis_statistic.h:100-110) with the heuristic's ego cost
+ *                 estimate = mean of leaf_cost[p*C .. p*C+C) (set_heuristic_estimate :158-161) when
+ *                 leaf_has_heuristic[p] != 0.
+ *   ancestors   : update_statistic (:112-134): latest = mean(edge_cost) + gamma * latest(child), or
+ *                 max(mean(edge_cost), latest(child)) when chance_constrained_update != 0; running means
+ *                 of ucb_statistics_[h][a] and ego_cost_value_ (the latter over the visits UNDER h).
+ * edge_hypothesis / edge_action: [edge * num_others + j]; edge_cost: [edge * C + c], the ego cost vector
+ * collected on the edge (CrossingState: C = 2, crossing_state.h:149-153). */
+int mamcts_backup_hypothesis(mamcts_engine* e, const mamcts_params* mp, uint32_t num_others,
+                             uint32_t n_paths, int32_t mem, const uint32_t* leaf_node,
+                             const uint8_t* leaf_has_heuristic, const double* leaf_cost,
+                             uint32_t num_costs /* C */, const uint32_t* path_offset,
+                             const uint32_t* path_len, const uint32_t* edge_node,
+                             const uint8_t* edge_hypothesis, const uint8_t* edge_action,
+                             const double* edge_cost, int32_t chance_constrained_update,
+                             mamcts_hyp_stats* stats);
+
 /* ---- root-parallel merge: UctStatistic::merge_node_statistics (uct_statistic.h:165-184) --- */
 
 /* Reduces the ego root statistics of n_trees local trees (slot = root_slot[t]) to

@@ -140,6 +140,22 @@ class UctStats(C.Structure):
     ]
 
 
+class HypStats(C.Structure):
+    _fields_ = [
+        ("mem", C.c_int32),
+        ("num_slots", C.c_uint32),
+        ("num_hypotheses", C.c_uint32),
+        ("max_actions", C.c_uint32),
+        ("ego_cost_value", C.c_void_p),
+        ("latest_ego_cost", C.c_void_p),
+        ("total_visits", C.c_void_p),
+        ("num_expanded", C.c_void_p),
+        ("visits_hypothesis", C.c_void_p),
+        ("action_cost", C.c_void_p),
+        ("action_count", C.c_void_p),
+    ]
+
+
 LAYOUT_AUTO, LAYOUT_CLASSIC, LAYOUT_COMPACT = 0, 1, 2
 
 
@@ -211,6 +227,10 @@ def load() -> C.CDLL:
             i32,
             [vp, P(Params), u32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, P(UctStats)],
         ),
+        "mamcts_backup_hypothesis": (
+            i32,
+            [vp, P(Params), u32, u32, i32, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, i32, P(HypStats)],
+        ),
         "mamcts_root_merge": (
             i32,
             [vp, P(UctStats), u32, i32, vp, u32, c_double_p, c_u64_p, c_u32_p, c_u64_p, c_double_p,
@@ -246,7 +266,7 @@ EXPORTED_SYMBOLS = [
     "mamcts_device_alloc", "mamcts_device_free", "mamcts_memcpy_h2d", "mamcts_memcpy_d2h",
     "mamcts_default_params", "mamcts_default_crossing_params", "mamcts_default_simple_params",
     "mamcts_reference_expand_order", "mamcts_rollout_crossing_i32", "mamcts_rollout_simple",
-    "mamcts_backup_uct", "mamcts_root_merge", "mamcts_comm_get_unique_id",
+    "mamcts_backup_uct", "mamcts_backup_hypothesis", "mamcts_root_merge", "mamcts_comm_get_unique_id",
     "mamcts_comm_init_rank", "mamcts_comm_destroy", "mamcts_allreduce_f64",
     "mamcts_search_create", "mamcts_search_destroy", "mamcts_search_reset", "mamcts_search_run",
     "mamcts_search_counters", "mamcts_search_exact_ucb_evaluations", "mamcts_search_root_stats", "mamcts_search_merge_roots",

@@ -271,6 +271,50 @@ class Engine:
         self._check(rc, "mamcts_backup_uct")
 
     @staticmethod
+    def new_hyp_stats(num_slots: int, num_hypotheses: int, max_actions: int) -> dict:
+        """Empty HypothesisStatistic storage (numpy, HOST) in the layout of mamcts_hyp_stats."""
+        S, H, MA = num_slots, num_hypotheses, max_actions
+        return dict(ego_cost_value=np.zeros(S), latest_ego_cost=np.zeros(S),
+                    total_visits=np.zeros(S, dtype=np.uint32), num_expanded=np.zeros(S, dtype=np.uint32),
+                    visits_hypothesis=np.zeros((S, H + 1), dtype=np.uint32),
+                    action_cost=np.zeros((S, H, MA)), action_count=np.zeros((S, H, MA), dtype=np.uint32))
+
+    @staticmethod
+    def hyp_stats_struct(stats: dict):
+        from ._abi import HypStats
+        st = HypStats()
+        st.mem = MEM_HOST
+        st.num_slots = stats["ego_cost_value"].shape[0]
+        st.num_hypotheses = stats["action_cost"].shape[1]
+        st.max_actions = stats["action_cost"].shape[2]
+        for k in ("ego_cost_value", "latest_ego_cost", "total_visits", "num_expanded", "visits_hypothesis",
+                  "action_cost", "action_count"):
+            assert stats[k].flags["C_CONTIGUOUS"], k
+            setattr(st, k, stats[k].ctypes.data)
+        return st
+
+    def backup_hypothesis(self, mp: Params, num_others: int, leaf_node, leaf_has_heuristic, leaf_cost,
+                          path_offset, path_len, edge_node, edge_hypothesis, edge_action, edge_cost,
+                          stats: dict, chance_constrained_update: bool = False):
+        """HOST-buffer batched HypothesisStatistic backup (C4); `stats` from new_hyp_stats, updated in
+        place. leaf_cost: [n_paths, C]; edge_cost: [n_edges, C]; edge_hypothesis / edge_action: [n_edges, J]."""
+        leaf_node = np.ascontiguousarray(leaf_node, dtype=np.uint32)
+        has = np.ascontiguousarray(leaf_has_heuristic, dtype=np.uint8)
+        lc = np.ascontiguousarray(leaf_cost, dtype=np.float64)
+        off = np.ascontiguousarray(path_offset, dtype=np.uint32)
+        ln = np.ascontiguousarray(path_len, dtype=np.uint32)
+        en = np.ascontiguousarray(edge_node, dtype=np.uint32)
+        eh = np.ascontiguousarray(edge_hypothesis, dtype=np.uint8)
+        ea = np.ascontiguousarray(edge_action, dtype=np.uint8)
+        ec = np.ascontiguousarray(edge_cost, dtype=np.float64)
+        st = self.hyp_stats_struct(stats)
+        rc = self.lib.mamcts_backup_hypothesis(self.h, C.byref(mp), num_others, leaf_node.shape[0], MEM_HOST,
+                                               _vp(leaf_node), _vp(has), _vp(lc), lc.shape[1], _vp(off), _vp(ln),
+                                               _vp(en), _vp(eh), _vp(ea), _vp(ec),
+                                               1 if chance_constrained_update else 0, C.byref(st))
+        self._check(rc, "mamcts_backup_hypothesis")
+
+    @staticmethod
     def _stats_struct(stats: dict) -> UctStats:
         st = UctStats()
         st.mem = MEM_HOST

@@ -279,6 +279,59 @@ void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* s
   out->final_state.terminal = (uint8_t)orc_is_terminal(env, &state);
 }
 
+static double orc_cost_mean(const double* c, uint32_t C) {
+  double acc = 0.0; /* std::accumulate(begin, end, 0.0) / size(), hypothesis_statistic.h:120,159 */
+  for (uint32_t i = 0; i < C; ++i) acc += c[i];
+  return acc / (double)C;
+}
+
+void orc_backup_hypothesis(double gamma, uint32_t num_others, uint32_t n_paths, const uint32_t* leaf_node,
+                           const uint8_t* leaf_has_heuristic, const double* leaf_cost, uint32_t num_costs,
+                           const uint32_t* path_offset, const uint32_t* path_len, const uint32_t* edge_node,
+                           const uint8_t* edge_hypothesis, const uint8_t* edge_action, const double* edge_cost,
+                           int32_t chance_constrained_update, mamcts_hyp_stats* st) {
+  const size_t J = num_others, H = st->num_hypotheses, MA = st->max_actions, C = num_costs;
+  for (uint32_t p = 0; p < n_paths; ++p) {
+    for (size_t j = 0; j < J; ++j) {
+      const size_t leaf = (size_t)leaf_node[p] * J + j;
+      double latest_child;
+      if (leaf_has_heuristic[p]) {
+        /* set_heuristic_estimate :158-161 then update_from_heuristic :100-110 of a statistic whose
+         * hypothesis_id_current_iteration_ is still HYPOTHESIS_ID_NOT_SET */
+        const double h = orc_cost_mean(leaf_cost + (size_t)p * C, (uint32_t)C);
+        st->ego_cost_value[leaf] = h;
+        st->latest_ego_cost[leaf] = h;
+        st->visits_hypothesis[leaf * (H + 1) + H] += 1;
+        st->total_visits[leaf] += 1;
+        latest_child = h;
+      } else {
+        latest_child = st->latest_ego_cost[leaf];
+      }
+      for (uint32_t e = 0; e < path_len[p]; ++e) {
+        const size_t idx = (size_t)path_offset[p] + e;
+        const size_t slot = (size_t)edge_node[idx] * J + j;
+        const size_t hyp = edge_hypothesis[idx * J + j], act = edge_action[idx * J + j];
+        /* update_statistic :112-134 */
+        const double cw = orc_cost_mean(edge_cost + idx * C, (uint32_t)C);
+        double latest;
+        if (chance_constrained_update) latest = cw < latest_child ? latest_child : cw; /* std::max */
+        else latest = cw + gamma * latest_child;
+        st->latest_ego_cost[slot] = latest;
+        const size_t ia = (slot * H + hyp) * MA + act;
+        st->action_count[ia] += 1;
+        st->action_cost[ia] = st->action_cost[ia] + (latest - st->action_cost[ia]) / (double)st->action_count[ia];
+        const size_t ih = slot * (H + 1) + hyp;
+        st->visits_hypothesis[ih] += 1;
+        st->ego_cost_value[slot] =
+            st->ego_cost_value[slot] + (latest - st->ego_cost_value[slot]) / (double)st->visits_hypothesis[ih];
+        st->total_visits[slot] += 1;
+        st->num_expanded[slot] += 1;
+        latest_child = latest;
+      }
+    }
+  }
+}
+
 double orc_reduce_mean(const double* vals, uint32_t K) {
   if (K == 1) return vals[0];
   double v[32], nv[32];

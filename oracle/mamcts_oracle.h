@@ -92,6 +92,14 @@ void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* s
  * vals[k], k < K. K in {1,2,4,8,16} or a multiple of 32 (<=256) or a multiple of 256. */
 double orc_reduce_mean(const double* vals, uint32_t K);
 
+/* ---- backup: HypothesisStatistic (mcts/hypothesis/hypothesis_statistic.h:100-134,158-161) ---- */
+/* Same arrays as mamcts_backup_hypothesis / mamcts_hyp_stats (HOST), plain sequential restatement. */
+void orc_backup_hypothesis(double gamma, uint32_t num_others, uint32_t n_paths, const uint32_t* leaf_node,
+                           const uint8_t* leaf_has_heuristic, const double* leaf_cost, uint32_t num_costs,
+                           const uint32_t* path_offset, const uint32_t* path_len, const uint32_t* edge_node,
+                           const uint8_t* edge_hypothesis, const uint8_t* edge_action, const double* edge_cost,
+                           int32_t chance_constrained_update, mamcts_hyp_stats* stats);
+
 /* ---- backup: UctStatistic (mcts/statistics/uct_statistic.h) -------------------------------- */
 
 typedef struct orc_stat {

@@ -251,6 +251,13 @@ class PhiloxHeuristic : public mcts::Heuristic<PhiloxHeuristic> {
 // White-box reader: the reference grants `friend class UctTest` under UNIT_TESTING.
 class mcts::UctTest {
  public:
+  static void read_hyp(const HypothesisStatistic& s, double* value, double* latest, uint32_t* visits,
+                       uint32_t* expanded) {
+    *value = s.ego_cost_value_;
+    *latest = s.latest_ego_cost_;
+    *visits = s.total_node_visits_;
+    *expanded = s.num_expanded_actions_;
+  }
   static void read_stat(const UctStatistic& s, double* value, double* latest, uint32_t* visits,
                         double* q, int64_t* n, uint32_t max_actions) {
     *value = s.value_;
@@ -420,6 +427,76 @@ int ref_rollout_crossing(const mamcts_params* mp, const mamcts_crossing_params* 
       if (final_last) final_last[a * n + i] = fs.last[a];
     }
     if (final_flags) final_flags[i] = (fs.terminal ? 1 : 0) | (fs.goal ? 2 : 0) | (fs.collided ? 4 : 0);
+  }
+  return 0;
+}
+
+// A minimal hypothesis state for driving HypothesisStatistic objects directly (like the reference's
+// test/hypothesis/hypothesis_statistic_test_state.h): the current hypothesis and the action the
+// hypothesis "plans" are whatever the driver sets before the call.
+class DrivenHypState : public HypothesisStateInterface<DrivenHypState> {
+ public:
+  explicit DrivenHypState(const std::unordered_map<AgentIdx, HypothesisId>& hyp)
+      : HypothesisStateInterface<DrivenHypState>(hyp) {}
+  ActionIdx plan_action_current_hypothesis(const AgentIdx&) const { return planned; }
+  ActionIdx planned = 0;
+};
+
+// HypothesisStatistic back-propagation on the arrays of mamcts_backup_hypothesis, executed by REAL
+// HypothesisStatistic objects (one per (node, other agent)) in the order Mcts::iterate would call
+// them (mcts.h:309-329): leaf update_from_heuristic, then per ancestor choose_next_action (which fixes
+// the hypothesis of the iteration, hypothesis_statistic.h:62-66), collect, update_statistic.
+// The statistics must start empty (a fresh tree); results are written in mamcts_hyp_stats layout.
+int ref_backup_hypothesis(const mamcts_params* mp, uint32_t num_others, uint32_t n_nodes, uint32_t n_paths,
+                          const uint32_t* leaf_node, const uint8_t* leaf_has, const double* leaf_cost,
+                          uint32_t C, const uint32_t* path_offset, const uint32_t* path_len,
+                          const uint32_t* edge_node, const uint8_t* edge_hyp, const uint8_t* edge_action,
+                          const double* edge_cost, int32_t chance, uint32_t rounds_paths_per_round,
+                          mamcts_hyp_stats* out) {
+  MctsParameters rp = to_ref_params(*mp);
+  rp.cost_constrained_statistic.USE_CHANCE_CONSTRAINED_UPDATES = {chance != 0};
+  const uint32_t J = num_others, H = out->num_hypotheses, MA = out->max_actions;
+  (void)rounds_paths_per_round;
+  std::vector<std::vector<HypothesisStatistic>> stats(n_nodes);
+  for (uint32_t n = 0; n < n_nodes; ++n)
+    for (uint32_t j = 0; j < J; ++j) stats[n].emplace_back(MA, j + 1, rp);
+  std::unordered_map<AgentIdx, HypothesisId> cur;
+  for (uint32_t j = 0; j < J; ++j) cur[j + 1] = 0;
+  DrivenHypState state(cur);
+  for (uint32_t p = 0; p < n_paths; ++p) {
+    for (uint32_t j = 0; j < J; ++j) {
+      HypothesisStatistic* child = &stats[leaf_node[p]][j];
+      if (leaf_has[p]) {
+        HypothesisStatistic heuristic(0, j + 1, rp);
+        heuristic.set_heuristic_estimate(0.0, EgoCosts(leaf_cost + (size_t)p * C, leaf_cost + (size_t)p * C + C));
+        child->update_from_heuristic(heuristic);
+      }
+      for (uint32_t e = 0; e < path_len[p]; ++e) {
+        const size_t idx = (size_t)path_offset[p] + e;
+        HypothesisStatistic& st = stats[edge_node[idx]][j];
+        cur[j + 1] = edge_hyp[idx * J + j];
+        state.planned = edge_action[idx * J + j];
+        st.choose_next_action(state);
+        st.collect(0.0, EgoCosts(edge_cost + idx * C, edge_cost + idx * C + C), edge_action[idx * J + j], {0, 0});
+        st.update_statistic(*child);
+        child = &st;
+      }
+    }
+  }
+  for (uint32_t n = 0; n < n_nodes; ++n) {
+    for (uint32_t j = 0; j < J; ++j) {
+      const size_t slot = (size_t)n * J + j;
+      const HypothesisStatistic& st = stats[n][j];
+      UctTest::read_hyp(st, &out->ego_cost_value[slot], &out->latest_ego_cost[slot], &out->total_visits[slot],
+                        &out->num_expanded[slot]);
+      for (const auto& kv : st.get_total_node_visits())
+        out->visits_hypothesis[slot * (H + 1) + (kv.first < H ? kv.first : H)] = kv.second;
+      for (const auto& hv : st.get_ucb_statistics())
+        for (const auto& av : hv.second) {
+          out->action_count[(slot * H + hv.first) * MA + av.first] = av.second.action_count_;
+          out->action_cost[(slot * H + hv.first) * MA + av.first] = av.second.action_ego_cost_;
+        }
+    }
   }
   return 0;
 }

@@ -153,6 +153,73 @@ def gen_hypothesis():
     dump("hypothesis.json", dict(policy=pol, rollouts=cases))
 
 
+def hypothesis_backup_case(rng, J, H, MA, C, n_trees, L, rounds, chance):
+    """`rounds` batches of one path per tree. Every tree is a chain of up to L+1 nodes (node ids
+    t*(L+1) + depth) that grows like a search does: a batch either expands the chain by one NEW leaf,
+    which receives the heuristic update (the reference asserts it is the node's first visit,
+    hypothesis_statistic.h:105), or re-visits the current deepest node without one (a terminal node,
+    stage_node.h:183-187); all ancestors are updated in both cases, so running means see many visits."""
+    batches = []
+    depth = np.zeros(n_trees, dtype=np.int64)       # current deepest node of every chain
+    for _ in range(rounds):
+        grow = (rng.random(n_trees) < 0.75) & (depth < L)
+        depth = depth + grow
+        plen = depth.copy()                          # edges between the leaf and the root
+        leaf = np.arange(n_trees) * (L + 1) + depth
+        has = grow.astype(np.uint8)
+        lc = np.round(rng.normal(size=(n_trees, C)) * 10, 3)
+        po = np.concatenate([[0], np.cumsum(plen)[:-1]])
+        ne = int(plen.sum())
+        en = np.zeros(ne, dtype=np.uint32)
+        for t in range(n_trees):
+            for e in range(plen[t]):
+                en[po[t] + e] = t * (L + 1) + (plen[t] - 1 - e)
+        eh = rng.integers(0, H, (ne, J))
+        ea = rng.integers(0, MA, (ne, J))
+        ec = rng.choice([0.0, 1000.0, -0.5, 2.25], (ne, C))
+        batches.append(dict(leaf_node=leaf.tolist(), leaf_has=has.tolist(), leaf_cost=lc.tolist(),
+                            path_offset=po.tolist(), path_len=plen.tolist(), edge_node=en.tolist(),
+                            edge_hyp=eh.tolist(), edge_action=ea.tolist(), edge_cost=ec.tolist()))
+    return dict(J=J, H=H, MA=MA, C=C, n_nodes=n_trees * (L + 1), chance=chance, batches=batches)
+
+
+def concat_batches(batches):
+    """All batches as one sequential path list (what the reference driver executes)."""
+    out = {k: [] for k in ("leaf_node", "leaf_has", "leaf_cost", "path_offset", "path_len", "edge_node",
+                           "edge_hyp", "edge_action", "edge_cost")}
+    base = 0
+    for b in batches:
+        for k in ("leaf_node", "leaf_has", "leaf_cost", "path_len", "edge_node", "edge_hyp", "edge_action", "edge_cost"):
+            out[k] += b[k]
+        out["path_offset"] += [o + base for o in b["path_offset"]]
+        base += len(b["edge_node"])
+    return out
+
+
+def gen_hypothesis_backup():
+    """HypothesisStatistic back-propagation (hypothesis_statistic.h:100-134) executed by real
+    HypothesisStatistic objects of the reference on random path batches."""
+    from mamcts_b200.engine import Engine
+    rng = np.random.default_rng(2718)
+    cases = []
+    for J, H, MA, C, chance in ((1, 2, 6, 2, False), (2, 3, 7, 2, False), (3, 2, 7, 1, True), (2, 3, 7, 2, True)):
+        case = hypothesis_backup_case(rng, J, H, MA, C, n_trees=12, L=5, rounds=9, chance=chance)
+        mp = default_params()
+        st = Engine.new_hyp_stats(case["n_nodes"] * J, H, MA)
+        cat = concat_batches(case["batches"])
+        if not cat["edge_node"]:
+            continue
+        O.ref_backup_hypothesis(mp, J, case["n_nodes"], st, cat["leaf_node"], cat["leaf_has"], cat["leaf_cost"],
+                                cat["path_offset"], cat["path_len"], cat["edge_node"], cat["edge_hyp"],
+                                cat["edge_action"], cat["edge_cost"], chance)
+        case["expected"] = dict(ego_cost_value=fhex(st["ego_cost_value"]), latest_ego_cost=fhex(st["latest_ego_cost"]),
+                                total_visits=st["total_visits"].tolist(), num_expanded=st["num_expanded"].tolist(),
+                                visits_hypothesis=st["visits_hypothesis"].tolist(),
+                                action_cost=fhex(st["action_cost"]), action_count=st["action_count"].tolist())
+        cases.append(case)
+    dump("hypothesis_backup.json", cases)
+
+
 def gen_search():
     cases = []
     # C1: SimpleState(4), 20 iterations (reference test/uct/uct_test.cc:22-40 parameters)
@@ -205,5 +272,6 @@ if __name__ == "__main__":
     gen_execute()
     gen_rollouts()
     gen_hypothesis()
+    gen_hypothesis_backup()
     gen_search()
     gen_merge()

@@ -417,6 +417,41 @@ def ref_rollout_crossing_hypothesis(mp: Params, cp: CrossingParams, x, last, hyp
     return out
 
 
+def _hyp_arrays(leaf_node, leaf_has, leaf_cost, path_offset, path_len, edge_node, edge_hyp, edge_action, edge_cost):
+    return (np.ascontiguousarray(leaf_node, dtype=np.uint32), np.ascontiguousarray(leaf_has, dtype=np.uint8),
+            np.ascontiguousarray(leaf_cost, dtype=np.float64), np.ascontiguousarray(path_offset, dtype=np.uint32),
+            np.ascontiguousarray(path_len, dtype=np.uint32), np.ascontiguousarray(edge_node, dtype=np.uint32),
+            np.ascontiguousarray(edge_hyp, dtype=np.uint8), np.ascontiguousarray(edge_action, dtype=np.uint8),
+            np.ascontiguousarray(edge_cost, dtype=np.float64))
+
+
+def backup_hypothesis(mp: Params, num_others, stats: dict, leaf_node, leaf_has, leaf_cost, path_offset,
+                      path_len, edge_node, edge_hyp, edge_action, edge_cost, chance=False):
+    """Oracle HypothesisStatistic back-propagation on mamcts_hyp_stats-shaped numpy arrays (in place)."""
+    from mamcts_b200.engine import Engine
+    ln, lh, lc, po, pl, en, eh, ea, ec = _hyp_arrays(leaf_node, leaf_has, leaf_cost, path_offset, path_len,
+                                                     edge_node, edge_hyp, edge_action, edge_cost)
+    st = Engine.hyp_stats_struct(stats)
+    oracle().orc_backup_hypothesis(C.c_double(mp.discount_factor), C.c_uint32(num_others), C.c_uint32(ln.shape[0]),
+                                   _ptr(ln), _ptr(lh), _ptr(lc), C.c_uint32(lc.shape[1]), _ptr(po), _ptr(pl),
+                                   _ptr(en), _ptr(eh), _ptr(ea), _ptr(ec), C.c_int32(1 if chance else 0),
+                                   C.byref(st))
+
+
+def ref_backup_hypothesis(mp: Params, num_others, n_nodes, stats: dict, leaf_node, leaf_has, leaf_cost,
+                          path_offset, path_len, edge_node, edge_hyp, edge_action, edge_cost, chance=False):
+    """The same arrays executed by REAL HypothesisStatistic objects of the reference (fresh statistics);
+    results written into `stats`."""
+    from mamcts_b200.engine import Engine
+    ln, lh, lc, po, pl, en, eh, ea, ec = _hyp_arrays(leaf_node, leaf_has, leaf_cost, path_offset, path_len,
+                                                     edge_node, edge_hyp, edge_action, edge_cost)
+    st = Engine.hyp_stats_struct(stats)
+    reference().ref_backup_hypothesis(C.byref(mp), C.c_uint32(num_others), C.c_uint32(n_nodes),
+                                      C.c_uint32(ln.shape[0]), _ptr(ln), _ptr(lh), _ptr(lc),
+                                      C.c_uint32(lc.shape[1]), _ptr(po), _ptr(pl), _ptr(en), _ptr(eh), _ptr(ea),
+                                      _ptr(ec), C.c_int32(1 if chance else 0), C.c_uint32(0), C.byref(st))
+
+
 def ref_rollout_simple(mp: Params, length, depth=None, rec_stride=64):
     length = np.ascontiguousarray(length, dtype=np.int32)
     n = length.shape[0]

@@ -83,6 +83,46 @@ def test_backup_matches_oracle(engine):
     assert stats["n"].tolist() == exp_n.tolist()
 
 
+def test_hypothesis_backup_matches_reference_golden_and_oracle(engine):
+    """mamcts_backup_hypothesis (C4: the other agents' HypothesisStatistic, hypothesis_statistic.h:100-134):
+    golden results produced by REAL HypothesisStatistic objects of the reference, bit for bit; then a
+    larger random batch against the oracle."""
+    from test_hypothesis_cpu import _run_batches, check_hyp_stats_against_golden
+    from mamcts_b200.engine import Engine
+    mp = default_params()
+    for case in golden("hypothesis_backup.json"):
+        st = Engine.new_hyp_stats(case["n_nodes"] * case["J"], case["H"], case["MA"])
+        _run_batches(lambda s, *a: engine.backup_hypothesis(mp, case["J"], *a, s, chance_constrained_update=case["chance"]),
+                     case, st)
+        check_hyp_stats_against_golden(st, case["expected"])
+    # 3 000 paths x 3 other agents, three rounds over growing chains
+    rng = np.random.default_rng(8)
+    J, H, MA, Cn, T, L = 3, 4, 9, 2, 3000, 4
+    a = Engine.new_hyp_stats(T * (L + 1) * J, H, MA)
+    b = Engine.new_hyp_stats(T * (L + 1) * J, H, MA)
+    depth = np.zeros(T, dtype=np.int64)
+    for rnd in range(4):
+        grow = (rng.random(T) < 0.7) & (depth < L)
+        depth += grow
+        leaf = np.arange(T) * (L + 1) + depth
+        off = np.concatenate([[0], np.cumsum(depth)[:-1]])
+        ne = int(depth.sum())
+        en = np.zeros(ne, dtype=np.uint32)
+        for t in range(T):
+            en[off[t]:off[t] + depth[t]] = t * (L + 1) + np.arange(depth[t] - 1, -1, -1)
+        eh, ea = rng.integers(0, H, (ne, J)), rng.integers(0, MA, (ne, J))
+        ec, lc = rng.choice([0.0, 1000.0, -1.5], (ne, Cn)), rng.normal(size=(T, Cn))
+        engine.backup_hypothesis(mp, J, leaf, grow, lc, off, depth, en, eh, ea, ec, a)
+        O.backup_hypothesis(mp, J, b, leaf, grow, lc, off, depth, en, eh, ea, ec)
+    for k in a:
+        if a[k].dtype == np.float64:
+            assert_bit_equal(a[k], b[k], k)
+        else:
+            assert np.array_equal(a[k], b[k]), k
+    with pytest.raises(MamctsError, match="out of range"):
+        engine.backup_hypothesis(mp, J, [0], [1], [[0.0, 0.0]], [0], [1], [0], [[H, 0, 0]], [[0, 0, 0]], [[0.0, 0.0]], a)
+
+
 def test_root_merge_matches_golden(engine):
     for case in golden("merge.json"):
         nA = case["num_actions"]

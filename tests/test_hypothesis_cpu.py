@@ -122,3 +122,67 @@ def test_policy_and_rollouts_equal_reference_on_fresh_inputs():
         assert o["steps"] == r["steps"][i] and o["final_x"] == r["final_x"][:, i].tolist()
         assert_bit_equal(o["ego_return"], r["ego_return"][i], "ego")
         assert_bit_equal(o["cost0"], r["ego_cost"][i], "cost")
+
+
+# ---- HypothesisStatistic back-propagation ------------------------------------------------------------
+
+def _f32(v):
+    return float(np.float32(v))
+
+
+def _run_batches(run, case, stats):
+    for b in case["batches"]:
+        if not b["leaf_node"]:
+            continue
+        run(stats, b["leaf_node"], b["leaf_has"], np.array(b["leaf_cost"]).reshape(-1, case["C"]),
+            b["path_offset"], b["path_len"], b["edge_node"], np.array(b["edge_hyp"]).reshape(-1, case["J"]),
+            np.array(b["edge_action"]).reshape(-1, case["J"]), np.array(b["edge_cost"]).reshape(-1, case["C"]))
+
+
+def check_hyp_stats_against_golden(stats, exp):
+    S, Hp1 = stats["visits_hypothesis"].shape
+    assert stats["total_visits"].tolist() == exp["total_visits"]
+    assert stats["num_expanded"].tolist() == exp["num_expanded"]
+    assert stats["visits_hypothesis"].tolist() == exp["visits_hypothesis"]
+    assert stats["action_count"].tolist() == exp["action_count"]
+    assert_bit_equal(stats["ego_cost_value"], unhex(exp["ego_cost_value"]), "ego_cost_value_")
+    assert_bit_equal(stats["latest_ego_cost"], unhex(exp["latest_ego_cost"]), "latest_ego_cost_")
+    assert_bit_equal(stats["action_cost"], unhex(exp["action_cost"], stats["action_cost"].shape), "action_ego_cost_")
+
+
+def test_hypothesis_backup_reference_known_answers():
+    """reference test/hypothesis/hypothesis_statistic_test.cc:23-118 (backprop_hypothesis_action_selection):
+    the four updates of agent 1's statistic with their stated expected values (EXPECT_NEAR 1e-3)."""
+    from mamcts_b200.engine import Engine
+    mp = default_params()
+    st = Engine.new_hyp_stats(5, 2, 6)   # node 0 = the parent statistic, nodes 1..4 = the four children
+
+    def upd(child, cost, leaf_cost, hyp, act):
+        O.backup_hypothesis(mp, 1, st, [child], [1], [[_f32(leaf_cost[0]), _f32(leaf_cost[1])]], [0], [1], [0],
+                            [[hyp]], [[act]], [[_f32(cost[0]), _f32(cost[1])]])
+
+    upd(1, (2.3, 5.0), (20.0, 1.2323), 0, 5)
+    assert abs(st["action_cost"][0, 0, 5] - ((5.0 + 2.3) / 2.0 + 0.9 * (1.2323 + 20.0) / 2.0)) < 1e-3
+    assert st["action_count"][0, 0, 5] == 1 and st["visits_hypothesis"][0, 0] == 1
+    upd(2, (4.3, 4.0), (24.5, 23.0), 0, 5)
+    assert abs(st["action_cost"][0, 0, 5] - ((5.0 + 4.0 + 4.3 + 2.3) / 2.0 + 0.9 * (1.2323 + 20.0) / 2.0
+                                            + 0.9 * (23.0 + 24.5) / 2.0) / 2.0) < 1e-3
+    assert st["action_count"][0, 0, 5] == 2 and st["visits_hypothesis"][0, 0] == 2
+    upd(3, (1000.3, 1000.0), (450.5, 450.0), 0, 3)
+    assert abs(st["action_cost"][0, 0, 3] - ((1000.0 + 1000.3) / 2.0 + 0.9 * (450.0 + 450.5) / 2.0)) < 1e-3
+    assert st["action_count"][0, 0, 3] == 1 and st["visits_hypothesis"][0, 0] == 3
+    upd(4, (10.3, 10.0), (45.5, 45.0), 1, 4)
+    assert abs(st["action_cost"][0, 1, 4] - ((10.0 + 10.3) / 2.0 + 0.9 * (45.0 + 45.5) / 2.0)) < 1e-3
+    assert st["action_count"][0, 1, 4] == 1 and st["visits_hypothesis"][0, 1] == 1
+    assert st["total_visits"][0] == 4 and st["num_expanded"][0] == 4
+    # the children counted their heuristic update under HYPOTHESIS_ID_NOT_SET
+    assert st["visits_hypothesis"][1:, 2].tolist() == [1, 1, 1, 1]
+
+
+def test_hypothesis_backup_matches_golden():
+    from mamcts_b200.engine import Engine
+    mp = default_params()
+    for case in golden("hypothesis_backup.json"):
+        st = Engine.new_hyp_stats(case["n_nodes"] * case["J"], case["H"], case["MA"])
+        _run_batches(lambda s, *a: O.backup_hypothesis(mp, case["J"], s, *a, chance=case["chance"]), case, st)
+        check_hyp_stats_against_golden(st, case["expected"])
