@@ -26,28 +26,25 @@
 using namespace std;
 using namespace mcts;
 
-// reference test/uct/uct_test.cc:22-40, wall-clock limits neutralised
-MctsParameters default_uct_params() {
-  MctsParameters parameters(mcts_default_parameters());
-  parameters.DISCOUNT_FACTOR = 0.9;
-  parameters.RANDOM_SEED = 1000;
-  parameters.MAX_NUMBER_OF_ITERATIONS = 10000;
-  parameters.MAX_SEARCH_TIME = 1000000000;
-  parameters.MAX_SEARCH_DEPTH = 1000;
-  parameters.MAX_NUMBER_OF_NODES = 100;
-  parameters.NUM_PARALLEL_MCTS = 1;
-  parameters.random_heuristic.MAX_SEARCH_TIME = 1e9;
-  parameters.random_heuristic.MAX_NUMBER_OF_ITERATIONS = 40;
-  parameters.uct_statistic.LOWER_BOUND = -1000;
-  parameters.uct_statistic.UPPER_BOUND = 100;
-  parameters.uct_statistic.EXPLORATION_CONSTANT = 0.7;
-  return parameters;
+// The parameter set of the reference's UCT tests (test/uct/uct_test.cc:22-40: gamma 0.9, seed 1000,
+// 10 000 iterations, 100 nodes, bounds [-1000, 100], c = 0.7), with both wall-clock limits
+// neutralised and the rollout depth capped (its rollouts never terminate, F1).
+static MctsParameters uct_test_parameters() {
+  MctsParameters p(mcts_default_parameters());
+  p.DISCOUNT_FACTOR = 0.9;          p.RANDOM_SEED = 1000;
+  p.MAX_NUMBER_OF_ITERATIONS = 10000; p.MAX_NUMBER_OF_NODES = 100;
+  p.MAX_SEARCH_DEPTH = 1000;        p.NUM_PARALLEL_MCTS = 1;
+  p.MAX_SEARCH_TIME = 1000000000;   p.random_heuristic.MAX_SEARCH_TIME = 1e9;
+  p.random_heuristic.MAX_NUMBER_OF_ITERATIONS = 40;
+  p.uct_statistic.LOWER_BOUND = -1000; p.uct_statistic.UPPER_BOUND = 100;
+  p.uct_statistic.EXPLORATION_CONSTANT = 0.7;
+  return p;
 }
 
 // ---- 1. the reference's own test with the CUDA heuristic -----------------------------------------
 TEST(dropin_mcts, reference_verify_uct_simple_state_cuda_heuristic) {
   CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();  // REFERENCE_CONST
-  Mcts<SimpleState, UctStatistic, UctStatistic, CudaRandomHeuristic> mcts(default_uct_params());
+  Mcts<SimpleState, UctStatistic, UctStatistic, CudaRandomHeuristic> mcts(uct_test_parameters());
   SimpleState state(4);
   mcts.search(state);
   EXPECT_EQ(mcts.numIterations(), 10000u);
@@ -58,7 +55,7 @@ TEST(dropin_mcts, reference_verify_uct_simple_state_cuda_heuristic) {
 // small_search_depth (test/uct/uct_test.cc:54-64) with the CUDA heuristic
 TEST(dropin_mcts, reference_small_search_depth_cuda_heuristic) {
   CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();
-  auto params = default_uct_params();
+  auto params = uct_test_parameters();
   params.MAX_SEARCH_DEPTH = 2;
   Mcts<SimpleState, UctStatistic, UctStatistic, CudaRandomHeuristic> mcts(params);
   SimpleState state(4);

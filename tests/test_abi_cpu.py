@@ -90,6 +90,34 @@ def _have_cuda() -> bool:
         return False
 
 
+def test_ctypes_structs_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc sees include/mamcts_b200.h, against the ctypes mirrors."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    structs = {"mamcts_config": _abi.Config, "mamcts_params": _abi.Params,
+               "mamcts_crossing_params": _abi.CrossingParams, "mamcts_simple_params": _abi.SimpleParams,
+               "mamcts_action_source": _abi.ActionSource, "mamcts_rollout_out": _abi.RolloutOut,
+               "mamcts_uct_stats": _abi.UctStats, "mamcts_hyp_stats": _abi.HypStats,
+               "mamcts_search_config": _abi.SearchConfig}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mamcts_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _t in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi_sizes.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_sizes"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _t in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
 @pytest.mark.skipif(_have_cuda(), reason="only meaningful without a GPU")
 def test_no_cpu_fallback_without_gpu(lib):
     h = C.c_void_p()
