@@ -20,8 +20,10 @@
 #ifndef MAMCTS_B200_HOST_BATCHED_MCTS_H_
 #define MAMCTS_B200_HOST_BATCHED_MCTS_H_
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "cuda_random_heuristic.h"
@@ -36,11 +38,17 @@ class BatchedRootParallelMcts {
   using Node = StageNode<S, SE, SO, H>;
   using NodePtr = std::shared_ptr<Node>;
 
+  // host_threads: the trees' select/expand and back-propagation phases of a wave are split over this
+  // many std::threads (0 = hardware concurrency), as the reference's parallel_search does with
+  // USE_MULTI_THREADING (mcts.h:198-210) - including its caveat: StageNode::num_nodes_ is one static
+  // counter shared by all trees (stage_node.h:77), so node ids and the MAX_NUMBER_OF_NODES cut-off are
+  // only exact with host_threads = 1. Statistics of different trees never alias.
   BatchedRootParallelMcts(const MctsParameters& mcts_parameters, unsigned num_trees,
                           uint64_t philox_seed = 1000, unsigned first_tree_id = 0,
-                          unsigned rollouts_per_leaf = 1)
+                          unsigned rollouts_per_leaf = 1, unsigned host_threads = 1)
       : mcts_parameters_(mcts_parameters), num_trees_(num_trees), philox_seed_(philox_seed),
-        first_tree_id_(first_tree_id), K_(rollouts_per_leaf), num_iterations_(0), rollout_steps_(0) {
+        first_tree_id_(first_tree_id), K_(rollouts_per_leaf), num_iterations_(0), rollout_steps_(0),
+        host_threads_(host_threads ? host_threads : std::max(1u, std::thread::hardware_concurrency())) {
     CudaEngine::get();
   }
 
@@ -78,15 +86,17 @@ class BatchedRootParallelMcts {
     using CS = CudaState<S>;
     const uint32_t T = num_trees_;
     std::vector<NodePtr> leaf(T);
+    std::vector<uint8_t> needs_rollout(T, 0);
     std::vector<uint32_t> batch;  // trees whose leaf needs a rollout
     // ---- select & expand, one leaf per tree (mcts.h:300-305) ------------------------------------
-    for (uint32_t t = 0; t < T; ++t) {
+    parallel_over_trees([&](uint32_t t) {
       NodePtr node = roots_[t];
       std::pair<bool, bool> res(true, true);
       while (res.first) res = node->select_or_expand(node);
       leaf[t] = node;
-      if (res.second) batch.push_back(t);
-    }
+      needs_rollout[t] = res.second ? 1 : 0;
+    });
+    for (uint32_t t = 0; t < T; ++t) if (needs_rollout[t]) batch.push_back(t);
     // ---- ONE launch for all leaves (replaces T x heuristic_.calculate_heuristic_values, mcts.h:310)
     const uint32_t n = (uint32_t)batch.size();
     const uint32_t A = n ? CS::num_agents(*leaf[batch[0]]->get_state()) : 0;
@@ -135,10 +145,12 @@ class BatchedRootParallelMcts {
       rollout_steps_ += steps;
     }
     // ---- update_statistics + back-propagation per tree (mcts.h:309-329) -------------------------
-    uint32_t bi = 0;
-    for (uint32_t t = 0; t < T; ++t) {
+    std::vector<int32_t> batch_index(T, -1);
+    for (uint32_t i = 0; i < n; ++i) batch_index[batch[i]] = (int32_t)i;
+    auto finish_tree = [&](uint32_t t) {
       NodePtr node = leaf[t];
-      if (bi < n && batch[bi] == t) {
+      if (batch_index[t] >= 0) {
+        const uint32_t bi = (uint32_t)batch_index[t];
         const S* st = node->get_state();
         SE ego_h(0, st->get_ego_agent_idx(), mcts_parameters_);
         EgoCosts accum_cost(st->get_num_costs(), 0.0);
@@ -153,7 +165,6 @@ class BatchedRootParallelMcts {
           ++j;
         }
         node->update_statistics(ego_h, others_h);
-        ++bi;
       }
       NodePtr node_p = node->get_parent().lock();
       while (bool(node_p)) {
@@ -162,10 +173,30 @@ class BatchedRootParallelMcts {
         node = node->get_parent().lock();
         node_p = node_p->get_parent().lock();
       }
-    }
+    };
+    // statistics that record their updates per host thread (CudaUctStatistic) stay on one thread
+    if (kDeferredStatistic) for (uint32_t t = 0; t < T; ++t) finish_tree(t);
+    else parallel_over_trees(finish_tree);
     // deferred statistics (CudaUctStatistic): all T paths of the wave in one mamcts_backup_uct
     flush_if_deferred<SE>(0);
   }
+
+  template <class F>
+  void parallel_over_trees(F&& f) {
+    const uint32_t T = num_trees_;
+    const unsigned nt = std::min<unsigned>(host_threads_, std::max(1u, T / 64));
+    if (nt <= 1) { for (uint32_t t = 0; t < T; ++t) f(t); return; }
+    std::vector<std::thread> pool;
+    for (unsigned k = 0; k < nt; ++k)
+      pool.emplace_back([&, k] { for (uint32_t t = (uint32_t)((uint64_t)T * k / nt); t < (uint32_t)((uint64_t)T * (k + 1) / nt); ++t) f(t); });
+    for (auto& th : pool) th.join();
+  }
+
+  template <class Stat>
+  static auto has_flush(int) -> decltype(Stat::flush(), std::true_type());
+  template <class Stat>
+  static std::false_type has_flush(...);
+  static constexpr bool kDeferredStatistic = decltype(has_flush<SE>(0))::value;
 
   template <class Stat>
   static auto flush_if_deferred(int) -> decltype(Stat::flush(), void()) { Stat::flush(); }
@@ -179,6 +210,7 @@ class BatchedRootParallelMcts {
   unsigned K_;
   unsigned num_iterations_;
   uint64_t rollout_steps_;
+  unsigned host_threads_;
   std::vector<NodePtr> roots_;
   std::vector<uint32_t> calls_;
 };
