@@ -1,0 +1,6 @@
+set -x
+nvidia-smi -L | wc -l
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r28_bench_n8.json 2> gpurun_out/r28_bench_n8.err; echo "bench rc=$?"
+head -c 600 gpurun_out/r28_bench_n8.json; tail -3 gpurun_out/r28_bench_n8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29535 scripts/check_multi_gpu.py 2>&1 | grep MULTI_GPU_CHECK
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29537 bench.py --impl reference --gpus 8 --steps 2 --warmup 1 2>/dev/null | head -c 300
