@@ -51,19 +51,37 @@ static __device__ __noinline__ uint32_t philox_bounded_retry(uint32_t n, uint32_
   return m;
 }
 
-// Exactly-uniform draw in [0, n) from the 16-bit word x of stream position `pos` (Lemire's
-// multiply-shift with rejection). The r-th retry reads lane ((r) & 7) of
-// philox({pos, lo, hi, 0x10000 + (r >> 3)}).
-__device__ __forceinline__ uint32_t philox_bounded(uint32_t x, uint32_t n, uint32_t pos,
-                                                   uint32_t stream_lo, uint32_t stream_hi,
-                                                   uint32_t k0, uint32_t k1) {
-  uint32_t m = x * n;
-  const uint32_t l = m & 0xFFFFu;
-  if (l < n) {
-    const uint32_t t = 65536u % n;
-    if (l < t) m = philox_bounded_retry(n, t, pos, stream_lo, stream_hi, k0, k1);
+// Exactly-uniform draws in [0, n) from 16-bit words (Lemire's multiply-shift with rejection): a word x
+// gives m = x * n, the draw is m >> 16 unless (m & 0xFFFF) < 65536 mod n, in which case the r-th retry
+// reads 16-bit lane (r & 7) of philox({pos, lo, hi, 0x10000 + (r >> 3)}).
+//
+// The N draws of one step at once: the multiply-shift of every draw runs branch-free,
+// the rejection test of all of them is folded into one mask and a single (almost never taken) branch
+// per step handles the retries - a third of the instructions of N
+// separate draws (the per-draw branch and its reconvergence point dominated the rollout kernel).
+// x[i] in: the 16-bit word of draw i; out: the action in [0, n[i]). pos0 + i = stream position of draw i.
+template <int N>
+__device__ __forceinline__ void philox_bounded_all(uint32_t (&x)[N], const uint32_t (&n)[N], uint32_t pos0,
+                                                   uint32_t stream_lo, uint32_t stream_hi, uint32_t k0,
+                                                   uint32_t k1) {
+  uint32_t m[N];
+  uint32_t small = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    m[i] = x[i] * n[i];
+    small |= (uint32_t)((m[i] & 0xFFFFu) < n[i]) << i;
   }
-  return m >> 16;
+  if (small) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if ((small >> i) & 1u) {
+        const uint32_t t = 65536u % n[i];
+        if ((m[i] & 0xFFFFu) < t) m[i] = philox_bounded_retry(n[i], t, pos0 + i, stream_lo, stream_hi, k0, k1);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = m[i] >> 16;
 }
 
 }  // namespace mamcts

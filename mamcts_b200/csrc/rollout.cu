@@ -184,25 +184,27 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
     for (int s = 0; s < S; ++s) {
       if (has && !fin) {
         int32_t act[A];
+        if (kPhilox) {
+          // all draws of the step: 16-bit words of the block(s), then one branch-free bounded reduction
+          uint32_t h[A], span[A];
 #pragma unroll
-        for (int a = 0; a < A; ++a) {
-          if (KIND == MAMCTS_SRC_REPLAY) {
-            act[a] = (int32_t)p.replay[((size_t)leaf * p.replay_stride + it) * A + a];
-          } else if (KIND == MAMCTS_SRC_REFERENCE_CONST) {
-            act[a] = (int32_t)p.const_actions[a];
-          } else {
-            const uint32_t h = (A <= 8) ? philox_half(blk[0], s * A + a) : philox_half(blk[a / 8], a % 8);
-            if (kHyp && a > 0) {
-              // the agent's gap for this step (AgentPolicyCrossingState<int>::act, agent_policy.h:68-75);
-              // the policy itself reads the PRE-step state, so it runs after all draws (below)
-              act[a] = gap_lo[kHyp ? a : 0] + (int32_t)philox_bounded(h, (uint32_t)gap_span[kHyp ? a : 0], it * A + a,
-                                                                     s_lo, s_hi, p.key0, p.key1);
-            } else {
-              act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi,
-                                               p.key0, p.key1);
-            }
+          for (int a = 0; a < A; ++a) {
+            h[a] = (A <= 8) ? philox_half(blk[0], s * A + a) : philox_half(blk[a / 8], a % 8);
+            // HYPOTHESIS: the other agents draw their gap for this step
+            // (AgentPolicyCrossingState<int>::act, agent_policy.h:68-75)
+            span[a] = (kHyp && a > 0) ? (uint32_t)gap_span[kHyp ? a : 0] : Env::num_actions(p.env, a);
+          }
+          philox_bounded_all<A>(h, span, it * A, s_lo, s_hi, p.key0, p.key1);
+#pragma unroll
+          for (int a = 0; a < A; ++a) act[a] = (kHyp && a > 0) ? gap_lo[kHyp ? a : 0] + (int32_t)h[a] : (int32_t)h[a];
+        } else {
+#pragma unroll
+          for (int a = 0; a < A; ++a) {
+            if (KIND == MAMCTS_SRC_REPLAY) act[a] = (int32_t)p.replay[((size_t)leaf * p.replay_stride + it) * A + a];
+            else act[a] = (int32_t)p.const_actions[a];
           }
         }
+        // the hypothesis policy reads the PRE-step state of every agent, so it runs after all draws
         if (kHyp && !kSimple) {
 #pragma unroll
           for (int a = 1; a < A; ++a)

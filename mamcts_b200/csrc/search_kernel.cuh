@@ -335,23 +335,27 @@ __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename E
       }
     }
     int32_t act[A];
+    if (KIND == MAMCTS_SRC_PHILOX) {
+      uint32_t h[A], nact[A];
 #pragma unroll
-    for (int a = 0; a < A; ++a) {
-      if (KIND == MAMCTS_SRC_PHILOX) {
-        uint32_t h;
+      for (int a = 0; a < A; ++a) {
         if (A <= 8) {
           const uint32_t lane16 = sub * A + a;   // 16-bit lane of the block, DESIGN.md section 5
           const uint32_t wi = lane16 >> 1;
           const uint32_t word = (S == 1) ? blk[0].w[(a >> 1) & 3]
                                          : (wi == 0 ? blk[0].w[0] : wi == 1 ? blk[0].w[1] : wi == 2 ? blk[0].w[2] : blk[0].w[3]);
-          h = (lane16 & 1u) ? (word >> 16) : (word & 0xFFFFu);
+          h[a] = (lane16 & 1u) ? (word >> 16) : (word & 0xFFFFu);
         } else {
-          h = philox_half(blk[a / 8], a % 8);
+          h[a] = philox_half(blk[a / 8], a % 8);
         }
-        act[a] = (int32_t)philox_bounded(h, Env::num_actions(p.env, a), it * A + a, s_lo, s_hi, p.key0, p.key1);
-      } else {
-        act[a] = (int32_t)const_act[a];
+        nact[a] = Env::num_actions(p.env, a);
       }
+      philox_bounded_all<A>(h, nact, it * A, s_lo, s_hi, p.key0, p.key1);
+#pragma unroll
+      for (int a = 0; a < A; ++a) act[a] = (int32_t)h[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < A; ++a) act[a] = (int32_t)const_act[a];
     }
     double r_ego, r_other, c;
     Env::step(p.env, st, act, r_ego, r_other, c);
