@@ -118,10 +118,6 @@ int mamcts_create(const mamcts_config* cfg, mamcts_engine** out) {
   cudaDeviceProp prop;
   MAMCTS_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
   e->num_sms = prop.multiProcessorCount;
-  if (const char* g = std::getenv("MAMCTS_L2_FETCH_GRANULARITY")) {   // experiment knob (profiles/)
-    const int v = std::atoi(g);
-    if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
-  }
   if (prop.major < 10) {
     std::string msg = "mamcts_create: device " + std::string(prop.name) +
                       " is not sm_100-class; this library is compiled for sm_100a only";

@@ -297,10 +297,6 @@ static int launch_persistent(mamcts_engine* e, Kernel kernel, RolloutParams p) {
   MAMCTS_CUDA(e, cudaMemsetAsync(e->work_cursor, 0, sizeof(unsigned int), e->stream));
   p.work_cursor = e->work_cursor;
   p.service_threshold = kServiceThreshold;
-  if (const char* v = std::getenv("MAMCTS_ROLLOUT_SERVICE")) {   // experiment knob (profiles/)
-    const int t = std::atoi(v);
-    if (t >= 1 && t <= 32) p.service_threshold = (uint32_t)t;
-  }
   kernel<<<dim3(grid), dim3(kRolloutThreads), 0, e->stream>>>(p);
   return MAMCTS_OK;
 }

@@ -588,6 +588,8 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   p.gamma = mp.discount_factor; p.two_c = 2 * mp.uct_exploration_constant;
   p.lb = mp.uct_lower_bound; p.ub = mp.uct_upper_bound;
   p.env = ep;
+  // Profiling knobs (scripts/sweep_search.py, profiles/r01_search_sweeps.txt): trees per warp and block
+  // size. The defaults (32 lanes = 32 trees per warp, 64-thread blocks) measured best.
   p.lanes_per_warp = 32;
   if (const char* v = std::getenv("MAMCTS_SEARCH_LPW")) {
     const int l = std::atoi(v);
