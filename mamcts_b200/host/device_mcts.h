@@ -1,0 +1,168 @@
+// device_mcts.h - DeviceRootParallelMcts<S>: the reference's Mcts<S, UctStatistic, UctStatistic,
+// RandomHeuristic> surface (mcts/mcts.h:43-76: search, returnBestAction, numIterations, numNodes,
+// searchTime) over the DEVICE-RESIDENT search of the C ABI (mamcts_search_*): num_trees independent trees
+// live in HBM and whole iterations (select/expand, rollout, back-propagation) run on the GPU; the host
+// sends the decision state and reads root statistics. This is the root-parallel mode of the reference
+// (NUM_PARALLEL_MCTS trees merged by UctStatistic::merge_node_statistics, mcts.h:188-221,270-292) with
+// thousands of trees instead of a handful of threads.
+//
+//   DeviceRootParallelMcts<CrossingState<int>> mcts(params, /*num_trees=*/65536);
+//   mcts.search(state);
+//   ActionIdx a = mcts.returnBestAction();
+//
+// Trees are the same trees BatchedRootParallelMcts builds on the host with the reference's own
+// StageNode code (same Philox streams: tree t, evaluation c -> (first_tree_id + t, c)), which
+// tests/dropin/dropin_test.cc checks statistic by statistic. With MAMCTS_SRC_REFERENCE_CONST every tree
+// is the stock reference's tree, bit for bit.
+#ifndef MAMCTS_B200_HOST_DEVICE_MCTS_H_
+#define MAMCTS_B200_HOST_DEVICE_MCTS_H_
+
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "cuda_random_heuristic.h"  // CudaEngine, to_mamcts_params
+#include "cuda_state.h"
+#include "mamcts_b200.h"
+#include "mcts/mcts_parameters.h"
+#include "mcts/state.h"
+
+namespace mcts {
+
+template <class S>
+class DeviceRootParallelMcts {
+ public:
+  // One agent's root statistic in UctStatistic's vocabulary (uct_statistic.h:272-289).
+  struct RootStatistic {
+    double value = 0.0;                                              // value_
+    unsigned total_node_visits = 0;                                  // total_node_visits_
+    std::map<ActionIdx, std::pair<unsigned, double>> ucb_statistics;  // action -> (action_count_, action_value_)
+  };
+
+  DeviceRootParallelMcts(const MctsParameters& mcts_parameters, unsigned num_trees, uint64_t philox_seed = 1000,
+                         unsigned first_tree_id = 0, int action_source = MAMCTS_SRC_PHILOX,
+                         unsigned max_inner_nodes_per_tree = 0)
+      : mcts_parameters_(mcts_parameters), num_trees_(num_trees), philox_seed_(philox_seed),
+        first_tree_id_(first_tree_id), action_source_(action_source), max_inner_(max_inner_nodes_per_tree),
+        search_(nullptr), num_iterations_(0), search_time_(0), merged_valid_(false) {
+    CudaEngine::get();
+  }
+  ~DeviceRootParallelMcts() { if (search_) mamcts_search_destroy(search_); }
+  DeviceRootParallelMcts(const DeviceRootParallelMcts&) = delete;
+  DeviceRootParallelMcts& operator=(const DeviceRootParallelMcts&) = delete;
+
+  // Mcts::search (mcts.h:133-141) for every tree, bounded by MAX_NUMBER_OF_ITERATIONS only
+  // (the wall-clock limit MAX_SEARCH_TIME has no device counterpart).
+  void search(const S& current_state) {
+    using CS = CudaState<S>;
+    const auto start = std::chrono::high_resolution_clock::now();
+    int32_t x[MAMCTS_MAX_AGENTS] = {0}, last[MAMCTS_MAX_AGENTS] = {0};
+    uint8_t flags = 0;
+    CS::pack(current_state, x, last, &flags);
+    num_agents_ = CS::num_agents(current_state);
+    num_ego_actions_ = (unsigned)current_state.get_num_actions(current_state.get_ego_agent_idx());
+    if (!search_) {
+      mamcts_search_config cfg;
+      std::memset(&cfg, 0, sizeof(cfg));
+      cfg.env = CS::kEnv;
+      cfg.action_source = action_source_;
+      cfg.num_trees = num_trees_;
+      cfg.first_tree_id = first_tree_id_;
+      cfg.rollouts_per_leaf = 1;
+      cfg.layout = MAMCTS_LAYOUT_AUTO;
+      cfg.max_inner_nodes_per_tree = max_inner_;
+      cfg.philox_seed = philox_seed_;
+      cfg.mcts = to_mamcts_params(mcts_parameters_);
+      fill_env(cfg);
+      CudaEngine::check(mamcts_search_create(CudaEngine::get(), &cfg, x, last, &search_), "mamcts_search_create");
+    } else {
+      CudaEngine::check(mamcts_search_reset(search_, x, last), "mamcts_search_reset");
+    }
+    CudaEngine::check(mamcts_search_run(search_, mcts_parameters_.MAX_NUMBER_OF_ITERATIONS), "mamcts_search_run");
+    merge();
+    num_iterations_ = mcts_parameters_.MAX_NUMBER_OF_ITERATIONS;
+    search_time_ = (unsigned)std::chrono::duration_cast<std::chrono::milliseconds>(
+                       std::chrono::high_resolution_clock::now() - start).count();
+  }
+
+  // get_best_action of the merged ego root statistic (uct_statistic.h:78-89 after :165-184)
+  ActionIdx returnBestAction() const { require_search(); return merged_best_; }
+  unsigned numIterations() const { return num_iterations_; }   // per tree
+  unsigned searchTime() const { return search_time_; }         // ms, like Mcts::searchTime
+  unsigned numTrees() const { return num_trees_; }
+  uint64_t numNodes() const {                                  // over all trees
+    require_search();
+    uint64_t nodes = 0;
+    CudaEngine::check(mamcts_search_counters(search_, nullptr, nullptr, nullptr, &nodes, nullptr), "mamcts_search_counters");
+    return nodes;
+  }
+  uint64_t numEnvSteps() const {                               // execute() calls: rollouts + expansions
+    require_search();
+    uint64_t r = 0, x = 0;
+    CudaEngine::check(mamcts_search_counters(search_, nullptr, &r, &x, nullptr, nullptr), "mamcts_search_counters");
+    return r + x;
+  }
+
+  // The merged ego root statistic (what Mcts::get_root().get_ego_int_node() holds after parallel_search).
+  RootStatistic get_merged_root_statistic() const {
+    require_search();
+    RootStatistic s;
+    s.value = merged_value_;
+    s.total_node_visits = (unsigned)merged_visits_;
+    for (unsigned a = 0; a < num_ego_actions_; ++a)
+      if (merged_occ_[a]) s.ucb_statistics[a] = {(unsigned)merged_n_[a], merged_q_[a]};
+    return s;
+  }
+
+  // Root statistic of one tree; agent_position 0 = ego, 1.. = others in get_other_agent_idx() order.
+  RootStatistic get_root_statistic(unsigned tree, unsigned agent_position) const {
+    require_search();
+    double value = 0.0, q[MAMCTS_MAX_ACTIONS];
+    uint32_t visits = 0, n[MAMCTS_MAX_ACTIONS], mask = 0, nodes = 0;
+    CudaEngine::check(mamcts_search_root_stats(search_, tree, agent_position, &value, &visits, q, n, &mask, &nodes),
+                      "mamcts_search_root_stats");
+    RootStatistic s;
+    s.value = value;
+    s.total_node_visits = visits;
+    for (unsigned a = 0; a < MAMCTS_MAX_ACTIONS; ++a)
+      if ((mask >> a) & 1u) s.ucb_statistics[a] = {n[a], q[a]};
+    return s;
+  }
+
+ private:
+  void require_search() const {
+    if (!search_ || !merged_valid_) {
+      std::cerr << "DeviceRootParallelMcts: search() has not been called" << std::endl;
+      std::terminate();
+    }
+  }
+  void merge() {
+    CudaEngine::check(mamcts_search_merge_roots(search_, merged_q_, merged_n_, merged_occ_, &merged_visits_,
+                                                &merged_value_, &merged_best_),
+                      "mamcts_search_merge_roots");
+    merged_valid_ = true;
+  }
+  void fill_env(mamcts_search_config& cfg) {
+    if constexpr (CudaState<S>::kEnv == MAMCTS_ENV_CROSSING_I32) cfg.crossing = CudaState<S>::params();
+    else cfg.simple = CudaState<S>::params();
+  }
+
+  const MctsParameters mcts_parameters_;
+  unsigned num_trees_;
+  uint64_t philox_seed_;
+  unsigned first_tree_id_;
+  int action_source_;
+  unsigned max_inner_;
+  mamcts_search* search_;
+  unsigned num_iterations_, search_time_;
+  unsigned num_agents_ = 0, num_ego_actions_ = 0;
+  bool merged_valid_;
+  double merged_q_[MAMCTS_MAX_ACTIONS] = {0.0}, merged_value_ = 0.0;
+  uint64_t merged_n_[MAMCTS_MAX_ACTIONS] = {0}, merged_visits_ = 0;
+  uint32_t merged_occ_[MAMCTS_MAX_ACTIONS] = {0}, merged_best_ = 0;
+};
+
+}  // namespace mcts
+#endif

@@ -24,6 +24,7 @@
 #include "cuda_random_heuristic.h"
 #include "cuda_state.h"
 #include "cuda_uct_statistic.h"
+#include "device_mcts.h"
 #include "mamcts_oracle.h"  // CPU checker for the PHILOX cases (test infrastructure)
 
 using namespace mcts;
@@ -327,6 +328,71 @@ int main() {
               "philox_simple_tree_backprop_invariant");
     CHECK_MSG((philox_tree_satisfies_invariant<SimpleState, CudaUctStatistic, CudaUctStatistic>(ss, ps, 50)),
               "philox_simple_tree_backprop_invariant_cuda_statistic");
+  }
+  {  // 7. DeviceRootParallelMcts: the Mcts surface over the device-resident search
+    CrossingFixture fx(1);
+    auto state = fx.state();
+    auto same_stat = [](const auto& host_stat, const DeviceRootParallelMcts<CrossingState<int>>::RootStatistic& d) {
+      double v, g; unsigned n;
+      std::map<ActionIdx, std::pair<unsigned, double>> ucb;
+      UctTest::read(host_stat, &v, &g, &n, &ucb);
+      bool ok = n == d.total_node_visits && std::memcmp(&v, &d.value, sizeof(double)) == 0 && ucb.size() == d.ucb_statistics.size();
+      for (const auto& kv : ucb) {
+        auto it = d.ucb_statistics.find(kv.first);
+        ok = ok && it != d.ucb_statistics.end() && it->second.first == kv.second.first &&
+             std::memcmp(&it->second.second, &kv.second.second, sizeof(double)) == 0;
+      }
+      return ok;
+    };
+    {  // REFERENCE_CONST: every device tree is the stock reference's tree
+      const MctsParameters p = test_params(1200);
+      Mcts<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic> ref(p);
+      ref.search(state);
+      DeviceRootParallelMcts<CrossingState<int>> dev(p, 5, 0, 0, MAMCTS_SRC_REFERENCE_CONST);
+      dev.search(state);
+      bool ok = dev.returnBestAction() == ref.returnBestAction() && dev.numIterations() == ref.numIterations();
+      for (unsigned t : {0u, 4u}) {
+        ok = ok && same_stat(ref.get_root().get_ego_int_node(), dev.get_root_statistic(t, 0));
+        ok = ok && same_stat(ref.get_root().get_other_int_nodes()[0], dev.get_root_statistic(t, 1));
+      }
+      ok = ok && dev.numNodes() == 5ull * ref.numNodes();
+      dev.search(state);  // a second decision re-roots the same arenas
+      ok = ok && same_stat(ref.get_root().get_ego_int_node(), dev.get_root_statistic(2, 0));
+      CHECK_MSG(ok, "device_mcts_reference_const_equals_stock_mcts");
+    }
+    {  // PHILOX: device trees == the reference's StageNode trees fed by the same GPU rollouts
+      const MctsParameters p = test_params(400);
+      const unsigned T = 16, first = 300;
+      BatchedRootParallelMcts<CrossingState<int>, UctStatistic, UctStatistic> host(p, T, 4242, first);
+      host.search(state);
+      DeviceRootParallelMcts<CrossingState<int>> dev(p, T, 4242, first);
+      dev.search(state);
+      bool ok = dev.returnBestAction() == host.returnBestAction() && dev.numEnvSteps() > 0;
+      for (unsigned t = 0; t < T; ++t) {
+        ok = ok && same_stat(host.get_root(t).get_ego_int_node(), dev.get_root_statistic(t, 0));
+        ok = ok && same_stat(host.get_root(t).get_other_int_nodes()[0], dev.get_root_statistic(t, 1));
+      }
+      const auto merged = dev.get_merged_root_statistic();
+      ok = ok && merged.total_node_visits == T * 400;
+      CHECK_MSG(ok, "device_mcts_philox_equals_host_trees");
+    }
+    {  // SimpleState (config 1)
+      MctsParameters p = test_params(20);
+      p.MAX_NUMBER_OF_NODES = 100;
+      p.random_heuristic.MAX_NUMBER_OF_ITERATIONS = 40;
+      SimpleState ss(4);
+      Mcts<SimpleState, UctStatistic, UctStatistic, RandomHeuristic> ref(p);
+      ref.search(ss);
+      DeviceRootParallelMcts<SimpleState> dev(p, 3, 0, 0, MAMCTS_SRC_REFERENCE_CONST);
+      dev.search(ss);
+      double v, g; unsigned n;
+      std::map<ActionIdx, std::pair<unsigned, double>> ucb;
+      UctTest::read(ref.get_root().get_ego_int_node(), &v, &g, &n, &ucb);
+      const auto d = dev.get_root_statistic(1, 0);
+      bool ok = n == d.total_node_visits && ucb.size() == d.ucb_statistics.size() && dev.returnBestAction() == ref.returnBestAction();
+      for (const auto& kv : ucb) ok = ok && d.ucb_statistics.at(kv.first).first == kv.second.first && d.ucb_statistics.at(kv.first).second == kv.second.second;
+      CHECK_MSG(ok, "device_mcts_simple_state_20_iterations");
+    }
   }
   std::printf("%s (%d failed)\n", g_failures ? "DROPIN FAILED" : "DROPIN OK", g_failures);
   return g_failures;
