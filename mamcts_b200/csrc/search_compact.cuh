@@ -280,8 +280,12 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
         vdst[0] = make_double2(e.v, o.v);
         vdst[1] = make_double2(e.G, o.G);
       }
-      pn->q_e[ae] = e.q;
-      pn->q_o[ao] = o.q;
+      // an action value that did not change (always the case for CrossingState's reward-free other
+      // agents) is not rewritten: its sector stays clean and is never written back to HBM
+      // (bit comparison: +0.0 and -0.0 are different values to keep; a newly expanded action's slot
+      // holds no value yet)
+      if (__double_as_longlong(e.q) != __double_as_longlong(be.q) || e.cnt == 1) pn->q_e[ae] = e.q;
+      if (__double_as_longlong(o.q) != __double_as_longlong(bo.q) || o.cnt == 1) pn->q_o[ao] = o.q;
       G[0] = e.G;
       G[1] = o.G;
     }
