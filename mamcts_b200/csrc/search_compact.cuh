@@ -25,6 +25,8 @@
 // selections, the same Philox streams (stream_lo = creation index of the node), the same FP64
 // arithmetic in the same order; only where the values live changes.
 #pragma once
+#include <cstddef>
+
 #include "search_kernel.cuh"
 
 namespace mamcts {
@@ -60,8 +62,11 @@ struct alignas(64) InnerRec {
   } v;
   alignas(32) double q_e[NE];   // action_value_
   alignas(32) double q_o[NA];
+  // The child table follows the action values directly: with 16-bit entries its first 20 slots end at
+  // byte 192, i.e. inside the third 64-byte DRAM burst that the tail of q_o brings in anyway; the
+  // fourth burst is only touched for the last 8 slots.
+  CIDX child[NCHILD];
   uint32_t parent;              // inner index of the parent (export only)
-  alignas(32) CIDX child[NCHILD];
 };
 
 template <int A>
@@ -151,8 +156,9 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       for (int i = 0; i < NE / 2 + (NE & 1); ++i) qe[i] = reinterpret_cast<const double2*>(&nd->q_e[0])[i];
 #pragma unroll
       for (int i = 0; i < NA / 2 + (NA & 1); ++i) qo[i] = reinterpret_cast<const double2*>(&nd->q_o[0])[i];
-      prefetch_l1(&nd->child[0]);
-      if (sizeof(CIDX) * NCHILD > 32) prefetch_l1(&nd->child[NCHILD - 1]);
+      // child table: only the part that shares a 64-byte burst with the action values is requested
+      // up front; the entry load below fetches the rest when the chosen slot lies there
+      prefetch_l1(reinterpret_cast<const char*>(nd) + ((offsetof(Inner, child) + 31) & ~size_t(31)));
       Counters cc;
       __builtin_memcpy(&cc, craw, sizeof(cc));
       if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) {  // :183-187

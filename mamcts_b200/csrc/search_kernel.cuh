@@ -285,9 +285,11 @@ __device__ __forceinline__ double back_apply(StatRec<NACT>* s, uint32_t act, con
                                              double gamma, double child_G) {
   const BackOut o = back_compute(b, r, gamma, child_G);
   s->n[act] = o.cnt;
-  s->Q[act] = o.q;
+  // an unchanged value is not rewritten (bit comparison: +0.0 and -0.0 differ), so its sector stays
+  // clean - always the case for CrossingState's reward-free other agents
+  if (__double_as_longlong(o.q) != __double_as_longlong(b.q)) s->Q[act] = o.q;
   s->N = o.nv;
-  s->V = o.v;
+  if (__double_as_longlong(o.v) != __double_as_longlong(b.v)) s->V = o.v;
   s->G = o.G;
   return o.G;
 }
