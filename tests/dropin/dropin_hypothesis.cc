@@ -8,6 +8,8 @@
 // iteration budget. Built by oracle/Makefile (target dropin).
 #include "gtest/gtest.h"
 
+#include <random>
+
 #include "mcts/mcts.h"
 #include "mcts/heuristics/random_heuristic.h"
 #include "mcts/statistics/uct_statistic.h"
@@ -17,6 +19,7 @@
 
 #include "cuda_random_heuristic.h"
 #include "cuda_state.h"
+#include "device_mcts.h"
 
 using namespace mcts;
 typedef int Domain;
@@ -95,6 +98,43 @@ TEST(dropin_hypothesis, stock_heuristic_reaches_goal_too) {
   bool collision = false;
   int steps = 0;
   EXPECT_TRUE(closed_loop<RandomHeuristic>({{5, 5}}, {5, 5}, 1500, 100, &collision, &steps));
+  EXPECT_FALSE(collision);
+}
+
+// Closed loop in the manner of CrossingStateEpisodeRunner::step (reference
+// environments/crossing_state_episode_runner.h:51-97) with the DEVICE-RESIDENT search as the planner:
+// every step 2 048 root-parallel UCT trees are searched on the GPU from the current state and the ego
+// executes the merged best action. The planner's model of the other agents is the UCT one (action index
+// i = velocity +i), so the true agents here move by a uniformly drawn index as well - with
+// gap-keeping true agents that model is simply wrong (they never pass the crossing the ego waits at),
+// which is what the hypothesis statistics above are for.
+TEST(dropin_hypothesis, episode_with_device_resident_planner_reaches_goal) {
+  const auto params = default_crossing_state_parameters<Domain>();
+  CudaState<CrossingState<Domain>>::set_parameters(params);
+  std::unordered_map<AgentIdx, HypothesisId> hyp;
+  for (AgentIdx i = 1; i <= params.NUM_OTHER_AGENTS; ++i) hyp[i] = 0;
+  auto state = std::make_shared<CrossingState<Domain>>(hyp, params);
+  std::mt19937 true_agents_rng(12345);
+  std::uniform_int_distribution<int> true_agents_action(0, (int)params.NUM_OTHER_ACTIONS - 1);
+  auto mcts_params = hypothesis_params(400);
+  mcts_params.MAX_NUMBER_OF_NODES = 100000000;
+  DeviceRootParallelMcts<CrossingState<Domain>> planner(mcts_params, 2048, 1000);
+  std::vector<Reward> rewards;
+  EgoCosts cost;
+  bool collision = false;
+  int i = 0;
+  for (; i < 40; ++i) {
+    planner.search(*state);
+    auto jointaction = JointAction(state->get_num_agents());
+    jointaction[CrossingState<Domain>::ego_agent_idx] = planner.returnBestAction();
+    for (auto agent_idx : state->get_other_agent_idx())
+      jointaction[agent_idx] = (ActionIdx)true_agents_action(true_agents_rng);
+    state = state->execute(jointaction, rewards, cost);
+    if (state->is_terminal()) { collision = !state->ego_goal_reached(); break; }
+  }
+  std::printf("  device planner: goal %d collision %d after %d steps, %u iterations x %u trees per step\n",
+              (int)state->ego_goal_reached(), (int)collision, i + 1, planner.numIterations(), planner.numTrees());
+  EXPECT_TRUE(state->ego_goal_reached());
   EXPECT_FALSE(collision);
 }
 

@@ -65,5 +65,6 @@ def test_reference_hypothesis_mcts_closed_loop_with_gpu_rollouts():
     assert "FAIL" not in out and " 0 failures" in out, out[-4000:]
     for name in ("dropin_hypothesis.mcts_goal_reached_true_hypothesis_cuda_rollouts",
                  "dropin_hypothesis.mcts_goal_reached_wrong_hypothesis_cuda_rollouts",
-                 "dropin_hypothesis.stock_heuristic_reaches_goal_too"):
+                 "dropin_hypothesis.stock_heuristic_reaches_goal_too",
+                 "dropin_hypothesis.episode_with_device_resident_planner_reaches_goal"):
         assert f"PASS {name}" in out, out[-4000:]
