@@ -39,10 +39,10 @@ constexpr int kPathMaxCompact = 64;  // deepest leaf the compact layout can back
 //             joint action leading here, n[a] of both agents - ONE sector with 16-bit counts
 //             (searches of < 65 536 iterations), two with 32-bit counts
 //   values    V and G (value_, latest_return_) of both agents - one sector
-//   q_e, q_o  the action values - 1 + 2 sectors; q_o's padding holds the parent index (export only)
-//   child     the direct child table - 2 sectors, one of which a visit reads
-// A visit reads 6 sectors and dirties 4 (16-bit counts); the previous AoS-by-agent layout read 8 and
-// dirtied 6-7.
+//   q_e, q_o  the action values - 1 + 2 sectors
+//   child     the direct child table, directly behind q_o (see below), then the parent index
+// A visit reads 6 sectors and dirties 3-4 (16-bit counts; an action value that did not change is not
+// rewritten); the first, AoS-by-agent, layout read 8 and dirtied 6-7.
 template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT>
 struct alignas(64) InnerRec {
   static constexpr int A = Env::A;

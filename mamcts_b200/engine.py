@@ -13,6 +13,7 @@ There is no CPU path here: every compute call goes to libmamcts_b200.so and rais
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -58,6 +59,7 @@ class Engine:
         if rc != 0:
             raise MamctsError(f"mamcts_create failed ({rc}): {self.lib.mamcts_last_error(None).decode()}")
         self.device = device
+        self._searches = weakref.WeakSet()   # closed before the engine they live on
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc: int, what: str):
@@ -66,6 +68,8 @@ class Engine:
 
     def close(self):
         if self.h:
+            for s in list(self._searches):
+                s.close()
             self.lib.mamcts_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -392,11 +396,12 @@ class Search:
         rc = self.lib.mamcts_search_create(engine.h, C.byref(cfg), rx.ctypes.data_as(_abi.c_i32_p), None,
                                            C.byref(self.h))
         engine._check(rc, "mamcts_search_create")
+        engine._searches.add(self)
 
     def close(self):
-        if self.h:
+        if self.h and self.engine.h:
             self.lib.mamcts_search_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
