@@ -57,17 +57,32 @@ def _config(trees_per_gpu, n_gpus, action_source, layout="compact (16-B leaf + 2
     }
 
 
-def _measured_traffic(layout, trees, iterations):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact
-    configuration (profiles/r01_traffic.json), else None."""
+def _ncu_entry(**match):
+    """The committed ncu capture (profiles/r01_traffic.json) of exactly this configuration, else None."""
     path = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
         for e in json.load(f)["entries"]:
-            if (e["layout"], e["trees"], e["iterations"]) == (layout if layout else 2, trees, iterations):
-                return e["dram_bytes_per_launch"]
+            if all(e.get(k) == v for k, v in match.items()):
+                return e
     return None
+
+
+def _measured_traffic(layout, trees, iterations):
+    e = _ncu_entry(layout=layout if layout else 2, trees=trees, iterations=iterations)
+    return e["dram_bytes_per_launch"] if e else None
+
+
+def _issue_roofline(entry, kernel_ms, sm_mhz):
+    """Issue-limited roofline: executed warp instructions per launch (ncu) / kernel time,
+    against 148 SMs x 4 schedulers x 1 warp instruction per clock at the clock observed in this run."""
+    if not entry or not sm_mhz:
+        return None
+    peak = 148 * 4 * sm_mhz * 1e6
+    achieved = entry["warp_inst_per_launch"] / (kernel_ms * 1e-3)
+    return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "warp-inst/s", "frac": achieved / peak,
+            "warp_inst_per_launch": entry["warp_inst_per_launch"], "sm_mhz": sm_mhz, "source": entry["source"]}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -259,6 +274,7 @@ def measure_rollout_c3(engine, stream, steps=5, warmup=3):
         "mean_steps_per_rollout": total_steps / (steps * C3_ROLLOUTS), "gpu_launches": int(launches),
         "e2e_env_steps_per_s": e2e_steps / e2e_s,
         "e2e_h2d_bytes": int(xh.nbytes), "e2e_d2h_bytes": int(8 * n * (A + 2) + 8),
+        "kernel_ms_estimate": ms,
         "roofline": {"bound": "hbm", "kernel": "rollout_kernel<CrossingEnv<7>,PHILOX>", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "algorithmic_bytes_per_rollout": bytes_per_rollout,
@@ -437,10 +453,17 @@ def run_native(args):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
+        sm_mhz = (clock_info or {}).get("sm_mhz")
+        line["roofline_issue"] = _issue_roofline(_ncu_entry(layout=args.layout if args.layout else 2, trees=T,
+                                                            iterations=ITERATIONS), search_kernel_ms, sm_mhz)
     search.close()
     if rank == 0:
         # the batched rollout kernel on its own (C3), after the trees are freed
-        line["rollout_c3"] = measure_rollout_c3(engine, stream)
+        c3 = measure_rollout_c3(engine, stream)
+        # (the C3 decision time includes the reduction launch: a lower bound of the kernel's own rate)
+        c3["roofline_issue"] = _issue_roofline(_ncu_entry(kernel="rollout_kernel", workload="c3"),
+                                               c3["kernel_ms_estimate"], sm_mhz)
+        line["rollout_c3"] = c3
         print(json.dumps(line))
     if world > 1:
         engine.comm_destroy()
