@@ -352,6 +352,17 @@ static mamcts_search* make_search(const mamcts_search_config& cfg, uint32_t n_eg
       default: return nullptr;
     }
   }
+  // any other action counts up to 8 per agent (CrossingStateParameters lets the velocity ranges be
+  // chosen freely, crossing_state_parameters.h:15-33): records sized for 8 actions, the real counts are
+  // run-time values (widening order, expansion masks)
+  if (n_ego <= 8 && n_oth <= 8) {
+    switch (cfg.crossing.num_other_agents) {
+      case 1: return make_search_cidx<CrossingEnv<1>, 8, 8, 64>(max_nodes, compact, cfg.mcts.max_number_of_iterations);
+      case 2: return make_search_cidx<CrossingEnv<2>, 8, 8, 0>(max_nodes, false, cfg.mcts.max_number_of_iterations);
+      case 3: return make_search_cidx<CrossingEnv<3>, 8, 8, 0>(max_nodes, false, cfg.mcts.max_number_of_iterations);
+      default: return nullptr;
+    }
+  }
   return nullptr;
 }
 
@@ -504,8 +515,8 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   mamcts_search* s = make_search(*cfg, n_ego, n_oth, max_nodes);
   if (!s)
     return fail(e, MAMCTS_ERR_UNSUPPORTED,
-                "mamcts_search_create: compiled for SimpleState and CrossingState<int> with 4 ego / 7 other "
-                "actions and 1, 2, 3 or 7 other agents");
+                "mamcts_search_create: compiled for SimpleState and CrossingState<int> with 1, 2, 3 or 7 other agents "
+                "at 4 ego / 7 other actions, and 1, 2 or 3 other agents at any action counts up to 8");
   if (cfg->layout == MAMCTS_LAYOUT_COMPACT && !s->is_compact()) {
     delete s;
     return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: the compact layout needs a direct child table (2 agents)");

@@ -326,6 +326,29 @@ def test_compact_layout_wide_counters(engine, max_iter, max_nodes):
     s.close()
 
 
+@pytest.mark.parametrize("num_others,layout,ego_v,n_oth", [(1, LAYOUT_COMPACT, (-1, 3), 5), (1, LAYOUT_CLASSIC, (-2, 1), 8),
+                                                          (2, LAYOUT_AUTO, (0, 2), 6), (3, LAYOUT_AUTO, (-1, 1), 4)])
+def test_other_action_counts_equal_oracle(engine, num_others, layout, ego_v, n_oth):
+    """CrossingStateParameters lets the velocity ranges be chosen freely: searches with other action
+    counts than the default 4 / 7 run on the generic (up to 8 actions) instantiation."""
+    iters = 500
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50, random_seed=77)
+    cp = default_crossing_params(num_other_agents=num_others, min_velocity_ego=ego_v[0], max_velocity_ego=ego_v[1],
+                                 num_other_actions=n_oth)
+    s = Search(engine, ENV_CROSSING_I32, mp, 20, cp=cp, action_source=SRC_PHILOX, philox_seed=5, layout=layout)
+    s.run(iters)
+    ma = max(ego_v[1] - ego_v[0] + 1, n_oth)
+    for tree in (0, 19):
+        t = O.OracleTree(O.make_env(cp=cp), mp, [5] * (num_others + 1), action_source=SRC_PHILOX, seed=5, tree_id=tree)
+        t.run(iters)
+        assert np.array_equal(s.dump_tree(tree, t.num_nodes), t.dump(ma))
+        t.close()
+    m = s.merge_roots()
+    assert m["visits"] == 20 * iters and len(m["q"]) == ego_v[1] - ego_v[0] + 1
+    s.close()
+
+
 def test_compact_layout_reports_exhausted_inner_records(engine):
     mp = default_params(max_number_of_iterations=2000, max_number_of_nodes=100000000,
                         rh_max_number_of_iterations=50)
@@ -362,6 +385,8 @@ def test_search_reset_and_limits(engine, layout):
     s.close()
     with pytest.raises(MamctsError, match="compiled for"):
         Search(engine, ENV_CROSSING_I32, mp, 1, cp=default_crossing_params(num_other_agents=5))
+    with pytest.raises(MamctsError, match="compiled for"):
+        Search(engine, ENV_CROSSING_I32, mp, 1, cp=default_crossing_params(num_other_agents=1, num_other_actions=9))
 
 
 def test_root_policy_statistically_matches_cpu_twin(engine):
