@@ -96,6 +96,24 @@ typedef struct mamcts_crossing_params {
   int32_t reserved;
 } mamcts_crossing_params;
 
+/* CrossingStateParameters<float> (same struct with Domain = float; defaults
+ * default_crossing_state_parameters<float>(): 30 other actions, crossing_state_parameters.h:50-51). */
+typedef struct mamcts_crossing_params_f32 {
+  double reward_collision;
+  double reward_goal_reached;
+  double reward_step;
+  uint32_t num_other_agents;
+  uint32_t num_other_actions;
+  int32_t cost_only_collision;
+  float min_velocity_ego;
+  float max_velocity_ego;
+  float min_velocity_other;
+  float max_velocity_other;
+  float chain_length;
+  float ego_goal_pos;
+  int32_t reserved;
+} mamcts_crossing_params_f32;
+
 /* SimpleState constants (reference: test/uct/simple_state.h:16,98-101). */
 typedef struct mamcts_simple_params {
   int32_t winning_state_length;  /* 10 */
@@ -111,6 +129,8 @@ typedef struct mamcts_action_source {
    * (environments/crossing_state_common.h:19-27), SimpleState entry = action index.
    * replay_steps[leaf] = number of recorded steps for that leaf (rollout_per_leaf must be 1). */
   const int8_t* replay_actions;
+  const float* replay_actions_f32;  /* the same for CrossingState<float> (mamcts_rollout_crossing_f32):
+                                       ego entry = action index, other entry = velocity */
   const uint32_t* replay_steps;
   uint32_t replay_stride;
   uint32_t reserved;
@@ -150,6 +170,8 @@ typedef struct mamcts_rollout_out {
   int32_t* final_x;            /* [A*n*K]  SoA by agent: x positions of the last state       */
   int32_t* final_last_action;  /* [A*n*K]  SoA by agent: last_action (CrossingState)         */
   uint8_t* final_flags;        /* [n*K]    bit0 terminal, bit1 goal, bit2 collided (Crossing) */
+  float* final_x_f32;          /* [A*n*K]  the two above for mamcts_rollout_crossing_f32        */
+  float* final_last_action_f32;/* [A*n*K]                                                     */
   double* reward_trace;        /* [n*K*trace_stride] ego step rewards, replay/const parity   */
   uint32_t trace_stride;
   uint32_t reserved2;
@@ -206,6 +228,19 @@ int mamcts_rollout_crossing_i32(mamcts_engine* e, const mamcts_params* mp,
                                 const int32_t* state_x, const int32_t* state_last_action,
                                 const uint8_t* state_flags, const uint32_t* start_depth,
                                 const mamcts_action_source* src, mamcts_rollout_out* out);
+
+/* Same through CrossingState<float>::execute (Domain = float: FP32 positions and velocities, every
+ * operation the reference's own, so REPLAY is bit-exact). state_x / state_last_action: [A*n] float SoA
+ * (last action default 2.0f). Action sources: REPLAY (src->replay_actions_f32), REFERENCE_CONST, PHILOX
+ * (index-valued: an other agent's index i is the float with bit pattern i, as the reference's bit-cast
+ * yields). Per-rollout parity outputs go to out->final_x_f32 / final_last_action_f32. */
+int mamcts_rollout_crossing_f32(mamcts_engine* e, const mamcts_params* mp,
+                                const mamcts_crossing_params_f32* cp, uint32_t n_leaves,
+                                uint32_t rollouts_per_leaf, int32_t mem, const float* state_x,
+                                const float* state_last_action, const uint8_t* state_flags,
+                                const uint32_t* start_depth, const mamcts_action_source* src,
+                                mamcts_rollout_out* out);
+void mamcts_default_crossing_params_f32(mamcts_crossing_params_f32* p);
 
 /* Same through SimpleState::execute (test/uct/simple_state.h:26-54); A = 2.
  *   state_len: [n] int32 state_length_. */

@@ -5,6 +5,7 @@ in include/mamcts_b200.h). This package is the thin Python binding over that ABI
 fallback.
 """
 from . import _abi  # noqa: F401
-from .params import default_crossing_params, default_params, default_simple_params  # noqa: F401
+from .params import (default_crossing_params, default_crossing_params_f32, default_params,  # noqa: F401
+                     default_simple_params)
 
-__all__ = ["default_params", "default_crossing_params", "default_simple_params"]
+__all__ = ["default_params", "default_crossing_params", "default_crossing_params_f32", "default_simple_params"]

@@ -88,11 +88,32 @@ class SimpleParams(C.Structure):
     _fields_ = [("winning_state_length", C.c_int32), ("loosing_state_length", C.c_int32)]
 
 
+class CrossingParamsF32(C.Structure):
+    """mamcts_crossing_params_f32 <- CrossingStateParameters<float>."""
+
+    _fields_ = [
+        ("reward_collision", C.c_double),
+        ("reward_goal_reached", C.c_double),
+        ("reward_step", C.c_double),
+        ("num_other_agents", C.c_uint32),
+        ("num_other_actions", C.c_uint32),
+        ("cost_only_collision", C.c_int32),
+        ("min_velocity_ego", C.c_float),
+        ("max_velocity_ego", C.c_float),
+        ("min_velocity_other", C.c_float),
+        ("max_velocity_other", C.c_float),
+        ("chain_length", C.c_float),
+        ("ego_goal_pos", C.c_float),
+        ("reserved", C.c_int32),
+    ]
+
+
 class ActionSource(C.Structure):
     _fields_ = [
         ("kind", C.c_int32),
         ("mem", C.c_int32),
         ("replay_actions", C.c_void_p),
+        ("replay_actions_f32", C.c_void_p),
         ("replay_steps", C.c_void_p),
         ("replay_stride", C.c_uint32),
         ("reserved", C.c_uint32),
@@ -120,6 +141,8 @@ class RolloutOut(C.Structure):
         ("final_x", C.c_void_p),
         ("final_last_action", C.c_void_p),
         ("final_flags", C.c_void_p),
+        ("final_x_f32", C.c_void_p),
+        ("final_last_action_f32", C.c_void_p),
         ("reward_trace", C.c_void_p),
         ("trace_stride", C.c_uint32),
         ("reserved2", C.c_uint32),
@@ -219,6 +242,12 @@ def load() -> C.CDLL:
             [vp, P(Params), P(CrossingParams), u32, u32, i32, vp, vp, vp, vp, P(ActionSource),
              P(RolloutOut)],
         ),
+        "mamcts_rollout_crossing_f32": (
+            i32,
+            [vp, P(Params), P(CrossingParamsF32), u32, u32, i32, vp, vp, vp, vp, P(ActionSource),
+             P(RolloutOut)],
+        ),
+        "mamcts_default_crossing_params_f32": (None, [P(CrossingParamsF32)]),
         "mamcts_rollout_simple": (
             i32,
             [vp, P(Params), P(SimpleParams), u32, u32, i32, vp, vp, P(ActionSource), P(RolloutOut)],
@@ -266,6 +295,7 @@ EXPORTED_SYMBOLS = [
     "mamcts_device_alloc", "mamcts_device_free", "mamcts_memcpy_h2d", "mamcts_memcpy_d2h",
     "mamcts_default_params", "mamcts_default_crossing_params", "mamcts_default_simple_params",
     "mamcts_reference_expand_order", "mamcts_rollout_crossing_i32", "mamcts_rollout_simple",
+    "mamcts_rollout_crossing_f32", "mamcts_default_crossing_params_f32",
     "mamcts_backup_uct", "mamcts_backup_hypothesis", "mamcts_root_merge", "mamcts_comm_get_unique_id",
     "mamcts_comm_init_rank", "mamcts_comm_destroy", "mamcts_allreduce_f64",
     "mamcts_search_create", "mamcts_search_destroy", "mamcts_search_reset", "mamcts_search_run",

@@ -225,6 +225,24 @@ void mamcts_default_params(mamcts_params* p) {
 }
 
 // default_crossing_state_parameters<int>(), reference environments/crossing_state_parameters.h:36-59
+void mamcts_default_crossing_params_f32(mamcts_crossing_params_f32* p) {
+  // default_crossing_state_parameters<float>(), environments/crossing_state_parameters.h:36-59
+  if (!p) return;
+  p->num_other_agents = 2;
+  p->cost_only_collision = 0;
+  p->max_velocity_other = 3.0f;
+  p->min_velocity_other = -3.0f;
+  p->max_velocity_ego = 2.0f;
+  p->min_velocity_ego = -1.0f;
+  p->chain_length = 21.0f;
+  p->ego_goal_pos = 12.0f;
+  p->num_other_actions = 30;
+  p->reward_collision = -1000.0;
+  p->reward_goal_reached = 100.0;
+  p->reward_step = 0.0;
+  p->reserved = 0;
+}
+
 void mamcts_default_crossing_params(mamcts_crossing_params* p) {
   std::memset(p, 0, sizeof(*p));
   p->num_other_agents = 2;

@@ -21,11 +21,17 @@ struct EnvParams {
   uint32_t n_other_actions;
   // SimpleState (reference test/uct/simple_state.h:16)
   int32_t win_len, lose_len;
+  // CrossingState<float> (Domain-typed parameters, crossing_state_parameters.h:15-28)
+  float f_min_v_ego, f_crossing_point, f_goal_pos;
   // CrossingState: the ego reward and cost of a step only depend on (goal, collision, out_of_map);
   // the 8 possible values are evaluated once on the host in the reference's operation order
   // (crossing_state.h:146-153) and looked up with index goal | collision << 1 | out_of_map << 2.
   double r_tab[8], c_tab[8];
 };
+
+// CrossingStateParameters<float>: the Domain-typed fields are floats and CROSSING_POINT() is evaluated
+// in float ((CHAIN_LENGTH - 1) / 2 + 1, crossing_state_parameters.h:28); rewards stay doubles.
+inline void make_crossing_env_f32(const mamcts_crossing_params_f32& cp, EnvParams& ep);
 
 // Fills every CrossingState field of EnvParams from the public parameter struct.
 inline void make_crossing_env(const mamcts_crossing_params& cp, EnvParams& ep) {
@@ -55,9 +61,37 @@ inline void make_crossing_env(const mamcts_crossing_params& cp, EnvParams& ep) {
   }
 }
 
+inline void make_crossing_env_f32(const mamcts_crossing_params_f32& cp, EnvParams& ep) {
+  mamcts_crossing_params ip;   // the Domain-independent part (rewards, cost mode, counts) through the int path
+  ip.reward_collision = cp.reward_collision;
+  ip.reward_goal_reached = cp.reward_goal_reached;
+  ip.reward_step = cp.reward_step;
+  ip.num_other_agents = cp.num_other_agents;
+  ip.num_other_actions = cp.num_other_actions;
+  ip.cost_only_collision = cp.cost_only_collision;
+  ip.min_velocity_ego = 0; ip.max_velocity_ego = 0; ip.min_velocity_other = 0; ip.max_velocity_other = 0;
+  ip.chain_length = 3; ip.ego_goal_pos = 0; ip.reserved = 0;
+  make_crossing_env(ip, ep);
+  // the reference's cost for Domain = float is built from float literals: {collision * 1.0f, 0.0f} or
+  // {-1.0f * rewards[0], 0.0f} (crossing_state.h:149-153) - the products are doubles either way
+  volatile float chain_m1 = cp.chain_length - 1.0f;
+  volatile float half = chain_m1 / 2.0f;
+  ep.f_crossing_point = half + 1.0f;
+  ep.f_goal_pos = cp.ego_goal_pos;
+  ep.f_min_v_ego = cp.min_velocity_ego;
+  // NUM_EGO_ACTIONS() is a float for this Domain and get_num_actions converts it to ActionIdx (:165-171)
+  volatile float n_ego = cp.max_velocity_ego - cp.min_velocity_ego + 1.0f;
+  ep.n_ego_actions = (uint32_t)n_ego;
+  ep.n_other_actions = cp.num_other_actions;
+}
+
 // CrossingState<int> with NO other agents. Positions / last actions live in registers.
 template <int NO>
 struct CrossingEnv {
+  using Domain = int32_t;
+  // a joint-action entry given as an action INDEX, as the statistics of the reference produce it: the
+  // ego's stays an index, an other agent's is bit-cast to the Domain (crossing_state_common.h:19-27, F5)
+  __device__ __forceinline__ static int32_t action_from_index(int, uint32_t idx) { return (int32_t)idx; }
   static constexpr int A = NO + 1;
   static constexpr int kStateInts = A;     // x_pos per agent
   static constexpr bool kHasCost = true;   // get_num_costs() == 1, crossing_state.h:101-103
@@ -103,6 +137,58 @@ struct CrossingEnv {
   }
 };
 
+// CrossingState<float> with NO other agents (reference environments/crossing_state.h with Domain = float;
+// 30 other actions by default, crossing_state_parameters.h:50-51). Positions and velocities are FP32 and
+// every operation is the reference's single IEEE operation (no contraction: -fmad=false), so REPLAY is
+// bit-exact. Index-valued other actions are bit-cast like the reference does: index i is the denormal
+// float with bit pattern i (F5), which the adds preserve (no flush-to-zero in this build).
+template <int NO>
+struct CrossingEnvF {
+  using Domain = float;
+  static constexpr int A = NO + 1;
+  static constexpr int kStateInts = A;
+  static constexpr bool kHasCost = true;
+  struct State {
+    float x[A];
+    float last[A];
+    uint32_t flags;  // bit0 terminal, bit1 goal, bit2 collided
+  };
+  __device__ __forceinline__ static float action_from_index(int agent, uint32_t idx) {
+    return agent == 0 ? (float)idx : __uint_as_float(idx);   // ego: ActionIdx -> Domain conversion (:306-309)
+  }
+  __device__ __forceinline__ static uint32_t num_actions(const EnvParams& p, int agent) {
+    return agent == 0 ? p.n_ego_actions : p.n_other_actions;
+  }
+  __device__ __forceinline__ static bool terminal(const EnvParams&, const State& s) { return s.flags & 1u; }
+  // act[0] = the ego action index as a float; act[i>0] = the velocity of other i.
+  __device__ __forceinline__ static void step(const EnvParams& p, State& s, const float (&act)[A],
+                                              double& r_ego, double& r_other, double& cost) {
+    const float old_x = s.x[0];
+    const float v_ego = __fadd_rn(act[0], p.f_min_v_ego);       // :306-309
+    const float new_x = __fadd_rn(old_x, v_ego);                // :119
+    const bool oob = new_x < 0.0f;                              // :121-123
+    const bool ego_encloses = (new_x >= p.f_crossing_point) & (old_x <= p.f_crossing_point);
+    bool coll = false;
+#pragma unroll
+    for (int i = 1; i < A; ++i) {
+      const float ox = s.x[i];
+      const float moved = __fadd_rn(ox, act[i]);                // :130
+      const float nx = (moved >= 0.0f) ? moved : 0.0f;          // :131
+      coll |= ego_encloses & (nx >= p.f_crossing_point) & (ox <= p.f_crossing_point);  // :135-139
+      s.x[i] = nx;
+      s.last[i] = act[i];
+    }
+    s.x[0] = new_x;
+    s.last[0] = v_ego;
+    const bool goal = (new_x >= p.f_goal_pos) & !coll;          // :142
+    s.flags = (uint32_t)(goal | coll | oob) | ((uint32_t)goal << 1) | ((uint32_t)coll << 2);
+    const uint32_t f = (uint32_t)goal | ((uint32_t)coll << 1) | ((uint32_t)oob << 2);
+    r_ego = p.r_tab[f];
+    r_other = 0.0;
+    cost = p.c_tab[f];
+  }
+};
+
 // AgentPolicyCrossingState<int>::calculate_action (reference
 // environments/crossing_state_agent_policy.h:35-55): the velocity an other agent chooses for a desired
 // gap to the ego agent, whose position is predicted one step ahead from its last action.
@@ -117,6 +203,8 @@ __device__ __forceinline__ int32_t crossing_policy_action(const EnvParams& p, in
 
 // SimpleState: one int32 of state, 2 agents x 2 actions (reference test/uct/simple_state.h).
 struct SimpleEnv {
+  using Domain = int32_t;
+  __device__ __forceinline__ static int32_t action_from_index(int, uint32_t idx) { return (int32_t)idx; }
   static constexpr int A = 2;
   static constexpr int kStateInts = 1;     // state_length_
   static constexpr bool kHasCost = false;  // get_num_costs() == 0, :60-62

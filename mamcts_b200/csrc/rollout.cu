@@ -26,13 +26,14 @@ constexpr int kServiceThreshold = 8;  // finished lanes that trigger a refill wh
 
 struct RolloutParams {
   uint32_t n_leaves, K, total;
-  // inputs (device)
-  const int32_t* x;
-  const int32_t* last;
+  // inputs (device); x / last are Env::Domain-typed (int32 or float)
+  const void* x;
+  const void* last;
   const uint8_t* flags;
   const uint32_t* depth;
   // action source
   const int8_t* replay;
+  const float* replay_f;   // CrossingState<float>
   const uint32_t* replay_steps;
   uint32_t replay_stride;
   uint32_t const_actions[MAMCTS_MAX_AGENTS];
@@ -53,8 +54,8 @@ struct RolloutParams {
   double* cost;
   double* step_len;
   uint32_t* steps;
-  int32_t* final_x;
-  int32_t* final_last;
+  void* final_x;           // Env::Domain-typed
+  void* final_last;
   uint8_t* final_flags;
   double* trace;
   uint32_t trace_stride;
@@ -75,6 +76,12 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
   constexpr int A = Env::A;
   constexpr int S = StepsPerBlock<Env, KIND>::value;
   constexpr bool kSimple = std::is_same<Env, SimpleEnv>::value;
+  using D = typename Env::Domain;   // int32_t, or float for CrossingState<float>
+  constexpr bool kFloat = std::is_same<D, float>::value;
+  const D* const in_x = static_cast<const D*>(p.x);
+  const D* const in_last = static_cast<const D*>(p.last);
+  D* const out_x = static_cast<D*>(p.final_x);
+  D* const out_last = static_cast<D*>(p.final_last);
   constexpr bool kPhilox = StepsPerBlock<Env, KIND>::kPhilox;   // draws come from the Philox stream
   constexpr bool kHyp = KIND == MAMCTS_SRC_HYPOTHESIS;
   constexpr int XR = kSimple ? 1 : A;  // rows of the x arrays (SimpleState: only state_length_)
@@ -97,8 +104,8 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
     leaf = (p.K == 1) ? rid : rid / p.K;
 #pragma unroll
     for (int a = 0; a < A; ++a) {
-      st.x[a] = (a < XR) ? __ldg(p.x + (size_t)a * p.n_leaves + leaf) : 0;
-      st.last[a] = (p.last && !kSimple) ? __ldg(p.last + (size_t)a * p.n_leaves + leaf) : 2;
+      st.x[a] = (a < XR) ? __ldg(in_x + (size_t)a * p.n_leaves + leaf) : (D)0;
+      st.last[a] = (in_last && !kSimple) ? __ldg(in_last + (size_t)a * p.n_leaves + leaf) : (D)2;
     }
     st.flags = p.flags ? (uint32_t)(__ldg(p.flags + leaf) & 1u) : 0u;
     depth = p.depth ? __ldg(p.depth + leaf) : 0u;
@@ -137,11 +144,11 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
       if (p.steps) p.steps[rid] = it;
       if (p.final_x) {
 #pragma unroll
-        for (int a = 0; a < XR; ++a) p.final_x[(size_t)a * p.total + rid] = st.x[a];
+        for (int a = 0; a < XR; ++a) out_x[(size_t)a * p.total + rid] = st.x[a];
       }
       if (p.final_last) {
 #pragma unroll
-        for (int a = 0; a < A; ++a) p.final_last[(size_t)a * p.total + rid] = st.last[a];
+        for (int a = 0; a < A; ++a) out_last[(size_t)a * p.total + rid] = st.last[a];
       }
       if (p.final_flags) p.final_flags[rid] = (uint8_t)((st.flags & ~1u) | (uint32_t)Env::terminal(p.env, st));
     }
@@ -183,7 +190,7 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       if (has && !fin) {
-        int32_t act[A];
+        D act[A];
         if (kPhilox) {
           // all draws of the step: 16-bit words of the block(s), then one branch-free bounded reduction
           uint32_t h[A], span[A];
@@ -196,16 +203,21 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
           }
           philox_bounded_all<A>(h, span, it * A, s_lo, s_hi, p.key0, p.key1);
 #pragma unroll
-          for (int a = 0; a < A; ++a) act[a] = (kHyp && a > 0) ? gap_lo[kHyp ? a : 0] + (int32_t)h[a] : (int32_t)h[a];
+          for (int a = 0; a < A; ++a)
+            act[a] = (kHyp && a > 0) ? (D)(gap_lo[kHyp ? a : 0] + (int32_t)h[a]) : Env::action_from_index(a, h[a]);
         } else {
 #pragma unroll
           for (int a = 0; a < A; ++a) {
-            if (KIND == MAMCTS_SRC_REPLAY) act[a] = (int32_t)p.replay[((size_t)leaf * p.replay_stride + it) * A + a];
-            else act[a] = (int32_t)p.const_actions[a];
+            if (KIND == MAMCTS_SRC_REPLAY) {
+              const size_t ri = ((size_t)leaf * p.replay_stride + it) * A + a;
+              act[a] = kFloat ? (D)p.replay_f[kFloat ? ri : 0] : (D)p.replay[kFloat ? 0 : ri];
+            } else {
+              act[a] = Env::action_from_index(a, p.const_actions[a]);
+            }
           }
         }
         // the hypothesis policy reads the PRE-step state of every agent, so it runs after all draws
-        if (kHyp && !kSimple) {
+        if constexpr (kHyp && !kSimple && !kFloat) {
 #pragma unroll
           for (int a = 1; a < A; ++a)
             act[a] = crossing_policy_action(p.env, st.x[a], st.last[a], st.x[0], st.last[0], act[a]);
@@ -340,10 +352,28 @@ static int dispatch_crossing(mamcts_engine* e, const RolloutParams& p, int num_o
   }
 }
 
-// Shared body of the two entry points. A = number of agents; x_rows = rows of the state array.
+// CrossingState<float>: the same kernel over CrossingEnvF (fewer agent counts are compiled: the
+// reference's float tests use 2 other agents, crossing_state_float_test.cc)
+constexpr int kEnvCrossingF32 = 100;   // internal environment kind of rollout_common
+
+static int dispatch_crossing_f32(mamcts_engine* e, const RolloutParams& p, int num_others, int kind, bool parity) {
+  if (kind == MAMCTS_SRC_HYPOTHESIS)
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "rollout: HYPOTHESIS is built for CrossingState<int>; replay float-domain policies");
+  switch (num_others) {
+    case 1: return launch_rollout<CrossingEnvF<1>>(e, p, kind, parity);
+    case 2: return launch_rollout<CrossingEnvF<2>>(e, p, kind, parity);
+    case 3: return launch_rollout<CrossingEnvF<3>>(e, p, kind, parity);
+    case 7: return launch_rollout<CrossingEnvF<7>>(e, p, kind, parity);
+    default:
+      return fail(e, MAMCTS_ERR_UNSUPPORTED, "rollout: CrossingState<float> is compiled for 1, 2, 3 or 7 other agents");
+  }
+}
+
+// Shared body of the entry points. A = number of agents; x_rows = rows of the state array; the state
+// arrays are int32 or (kEnvCrossingF32) float - both 4 bytes per element.
 static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* mp, const EnvParams& ep,
-                          uint32_t A, uint32_t n, uint32_t K, int32_t mem, const int32_t* state_x,
-                          const int32_t* state_last, const uint8_t* state_flags,
+                          uint32_t A, uint32_t n, uint32_t K, int32_t mem, const void* state_x,
+                          const void* state_last, const uint8_t* state_flags,
                           const uint32_t* start_depth, const mamcts_action_source* src,
                           mamcts_rollout_out* out) {
   if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "rollout: null engine");
@@ -354,7 +384,9 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
     return fail(e, MAMCTS_ERR_INVALID,
                 "rollout: rollouts_per_leaf must be 1,2,4,8,16, a multiple of 32 up to 256, or a multiple of 256");
   if ((uint64_t)n * K > 0xF0000000ull) return fail(e, MAMCTS_ERR_INVALID, "rollout: n_leaves * K too large for one call");
-  if (src->kind == MAMCTS_SRC_REPLAY && (K != 1 || !src->replay_actions || !src->replay_steps))
+  const bool f32 = env_kind == kEnvCrossingF32;
+  if (src->kind == MAMCTS_SRC_REPLAY &&
+      (K != 1 || !(f32 ? (const void*)src->replay_actions_f32 : (const void*)src->replay_actions) || !src->replay_steps))
     return fail(e, MAMCTS_ERR_INVALID, "rollout: REPLAY needs K == 1 and replay buffers");
   if (src->kind < MAMCTS_SRC_REPLAY || src->kind > MAMCTS_SRC_HYPOTHESIS)
     return fail(e, MAMCTS_ERR_INVALID, "rollout: unknown action source");
@@ -375,8 +407,10 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   const int t_last = stg.plan(state_last, sizeof(int32_t) * x_rows * n, mem, false);
   const int t_flags = stg.plan(state_flags, n, mem, false);
   const int t_depth = stg.plan(start_depth, sizeof(uint32_t) * n, mem, false);
-  const int t_rep = stg.plan(src->kind == MAMCTS_SRC_REPLAY ? src->replay_actions : nullptr,
+  const int t_rep = stg.plan(src->kind == MAMCTS_SRC_REPLAY && !f32 ? src->replay_actions : nullptr,
                              (size_t)n * src->replay_stride * A, src->mem, false);
+  const int t_repf = stg.plan(src->kind == MAMCTS_SRC_REPLAY && f32 ? src->replay_actions_f32 : nullptr,
+                              sizeof(float) * (size_t)n * src->replay_stride * A, src->mem, false);
   const int t_reps = stg.plan(src->kind == MAMCTS_SRC_REPLAY ? src->replay_steps : nullptr,
                               sizeof(uint32_t) * n, src->mem, false);
   const int t_shi = stg.plan((src->kind == MAMCTS_SRC_PHILOX || src->kind == MAMCTS_SRC_HYPOTHESIS) ? src->stream_hi : nullptr,
@@ -393,8 +427,9 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   const int o_len = stg.plan(out->step_length, sizeof(double) * n, out->mem, true);
   const int o_tot = stg.plan(out->total_steps, sizeof(uint64_t), out->mem, true);
   const int o_steps = stg.plan(out->steps, sizeof(uint32_t) * total, out->mem, true);
-  const int o_fx = stg.plan(out->final_x, sizeof(int32_t) * x_rows * total, out->mem, true);
-  const int o_fl = stg.plan(out->final_last_action, sizeof(int32_t) * A * total, out->mem, true);
+  const int o_fx = stg.plan(f32 ? (void*)out->final_x_f32 : (void*)out->final_x, sizeof(int32_t) * x_rows * total, out->mem, true);
+  const int o_fl = stg.plan(f32 ? (void*)out->final_last_action_f32 : (void*)out->final_last_action,
+                            sizeof(int32_t) * A * total, out->mem, true);
   const int o_ff = stg.plan(out->final_flags, total, out->mem, true);
   const int o_tr = stg.plan(out->reward_trace, sizeof(double) * (size_t)total * out->trace_stride, out->mem, true);
   int rc = stg.commit();
@@ -403,11 +438,12 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   RolloutParams p;
   std::memset(&p, 0, sizeof(p));
   p.n_leaves = n; p.K = K; p.total = total;
-  p.x = stg.dev<const int32_t>(t_x);
-  p.last = stg.dev<const int32_t>(t_last);
+  p.x = stg.dev<const void>(t_x);
+  p.last = stg.dev<const void>(t_last);
   p.flags = stg.dev<const uint8_t>(t_flags);
   p.depth = stg.dev<const uint32_t>(t_depth);
   p.replay = stg.dev<const int8_t>(t_rep);
+  p.replay_f = stg.dev<const float>(t_repf);
   p.replay_steps = stg.dev<const uint32_t>(t_reps);
   p.replay_stride = src->replay_stride;
   for (int a = 0; a < MAMCTS_MAX_AGENTS; ++a) p.const_actions[a] = src->const_actions[a];
@@ -431,8 +467,8 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   p.max_depth = mp->max_search_depth;
   p.env = ep;
   p.steps = stg.dev<uint32_t>(o_steps);
-  p.final_x = stg.dev<int32_t>(o_fx);
-  p.final_last = stg.dev<int32_t>(o_fl);
+  p.final_x = stg.dev<void>(o_fx);
+  p.final_last = stg.dev<void>(o_fl);
   p.final_flags = stg.dev<uint8_t>(o_ff);
   p.trace = stg.dev<double>(o_tr);
   p.trace_stride = out->trace_stride;
@@ -459,6 +495,7 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   const bool parity = p.steps || p.final_x || p.final_last || p.final_flags || p.trace;
 
   if (env_kind == MAMCTS_ENV_SIMPLE) rc = launch_rollout<SimpleEnv>(e, p, src->kind, parity);
+  else if (f32) rc = dispatch_crossing_f32(e, p, (int)A - 1, src->kind, parity);
   else rc = dispatch_crossing(e, p, (int)A - 1, src->kind, parity);
   if (rc != MAMCTS_OK) return rc;
 
@@ -503,6 +540,25 @@ int mamcts_rollout_crossing_i32(mamcts_engine* e, const mamcts_params* mp,
   return rollout_common(e, MAMCTS_ENV_CROSSING_I32, mp, ep, cp->num_other_agents + 1, n_leaves,
                         rollouts_per_leaf, mem, state_x, state_last_action, state_flags, start_depth,
                         src, out);
+}
+
+int mamcts_rollout_crossing_f32(mamcts_engine* e, const mamcts_params* mp,
+                                const mamcts_crossing_params_f32* cp, uint32_t n_leaves,
+                                uint32_t rollouts_per_leaf, int32_t mem, const float* state_x,
+                                const float* state_last_action, const uint8_t* state_flags,
+                                const uint32_t* start_depth, const mamcts_action_source* src,
+                                mamcts_rollout_out* out) {
+  if (!cp) return fail(e, MAMCTS_ERR_INVALID, "mamcts_rollout_crossing_f32: null crossing params");
+  if (cp->num_other_agents + 1 > MAMCTS_MAX_AGENTS || cp->num_other_agents == 0)
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_rollout_crossing_f32: 1..15 other agents supported");
+  EnvParams ep;
+  std::memset(&ep, 0, sizeof(ep));
+  make_crossing_env_f32(*cp, ep);
+  if (ep.n_ego_actions == 0 || ep.n_ego_actions > MAMCTS_MAX_ACTIONS || ep.n_other_actions == 0 ||
+      ep.n_other_actions > MAMCTS_MAX_ACTIONS)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_rollout_crossing_f32: action counts out of range");
+  return rollout_common(e, kEnvCrossingF32, mp, ep, cp->num_other_agents + 1, n_leaves, rollouts_per_leaf, mem,
+                        state_x, state_last_action, state_flags, start_depth, src, out);
 }
 
 int mamcts_rollout_simple(mamcts_engine* e, const mamcts_params* mp, const mamcts_simple_params* sp,

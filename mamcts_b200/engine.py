@@ -226,6 +226,48 @@ class Engine:
         return self._rollout_host(ENV_CROSSING_I32, mp, cp, cp.num_other_agents + 1, x, last, flags,
                                   depth, K, dict(kind=kind, **src_kw), parity, trace_stride)
 
+    def rollout_crossing_f32(self, mp: Params, cp, x, last=None, flags=None, depth=None, K: int = 1,
+                             kind: int = SRC_PHILOX, parity: bool = False, replay_actions=None,
+                             replay_steps=None, **src_kw):
+        """HOST-buffer batched rollout through CrossingState<float>::execute. x / last: [A, n] float32;
+        replay_actions: [n, stride, A] float32 (ego index, others' velocities)."""
+        A = cp.num_other_agents + 1
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[1]
+        total = n * K
+        last_a = None if last is None else np.ascontiguousarray(last, dtype=np.float32)
+        flags_a = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        depth_a = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+        if kind == SRC_REPLAY:
+            src = ActionSource()
+            src.kind, src.mem = SRC_REPLAY, MEM_HOST
+            ra = np.ascontiguousarray(replay_actions, dtype=np.float32)
+            rs = np.ascontiguousarray(replay_steps, dtype=np.uint32)
+            src.replay_actions_f32, src.replay_steps, src.replay_stride = ra.ctypes.data, rs.ctypes.data, ra.shape[1]
+            keep = [ra, rs]
+        else:
+            src, keep = self._source(A=A, kind=kind, **src_kw)
+        res = dict(ego_return=np.zeros(n), other_return=np.zeros((A - 1, n)), ego_cost=np.zeros(n),
+                   step_length=np.zeros(n), total_steps=np.zeros(1, dtype=np.uint64))
+        out = RolloutOut()
+        out.mem = MEM_HOST
+        for k in ("ego_return", "other_return", "ego_cost", "step_length", "total_steps"):
+            setattr(out, k, res[k].ctypes.data)
+        if parity:
+            res.update(steps=np.zeros(total, dtype=np.uint32), final_x=np.zeros((A, total), dtype=np.float32),
+                       final_last_action=np.zeros((A, total), dtype=np.float32),
+                       final_flags=np.zeros(total, dtype=np.uint8))
+            out.steps = res["steps"].ctypes.data
+            out.final_x_f32 = res["final_x"].ctypes.data
+            out.final_last_action_f32 = res["final_last_action"].ctypes.data
+            out.final_flags = res["final_flags"].ctypes.data
+        rc = self.lib.mamcts_rollout_crossing_f32(self.h, C.byref(mp), C.byref(cp), n, K, MEM_HOST, _vp(x), _vp(last_a),
+                                                  _vp(flags_a), _vp(depth_a), C.byref(src), C.byref(out))
+        self._check(rc, "mamcts_rollout_crossing_f32")
+        res["total_steps"] = int(res["total_steps"][0])
+        del keep
+        return res
+
     def rollout_simple(self, mp: Params, sp: SimpleParams, length, depth=None, K: int = 1,
                        kind: int = SRC_PHILOX, parity: bool = False, trace_stride: int = 0, **src_kw):
         """HOST-buffer batched rollout through SimpleState::execute. length: [n] int32."""

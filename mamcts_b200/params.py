@@ -6,7 +6,7 @@ SimpleState constants                     : reference test/uct/simple_state.h:16
 """
 from __future__ import annotations
 
-from ._abi import CrossingParams, Params, SimpleParams
+from ._abi import CrossingParams, CrossingParamsF32, Params, SimpleParams
 
 
 def default_params(**over) -> Params:
@@ -42,6 +42,28 @@ def default_crossing_params(**over) -> CrossingParams:
     c.chain_length = 21
     c.ego_goal_pos = 12
     c.num_other_actions = 7
+    c.reward_collision = -1000.0
+    c.reward_goal_reached = 100.0
+    c.reward_step = 0.0
+    for k, v in over.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def default_crossing_params_f32(**over) -> CrossingParamsF32:
+    """default_crossing_state_parameters<float>(): the same values, 30 other actions (:50-51)."""
+    c = CrossingParamsF32()
+    c.num_other_agents = 2
+    c.cost_only_collision = 0
+    c.max_velocity_other = 3.0
+    c.min_velocity_other = -3.0
+    c.max_velocity_ego = 2.0
+    c.min_velocity_ego = -1.0
+    c.chain_length = 21.0
+    c.ego_goal_pos = 12.0
+    c.num_other_actions = 30
     c.reward_collision = -1000.0
     c.reward_goal_reached = 100.0
     c.reward_step = 0.0

@@ -279,6 +279,94 @@ void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* s
   out->final_state.terminal = (uint8_t)orc_is_terminal(env, &state);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* CrossingState<float>                                                                       */
+/* ------------------------------------------------------------------------------------------ */
+
+void orc_crossing_f32_execute(const mamcts_crossing_params_f32* cp, const orc_state_f32* s, const float* action,
+                              orc_state_f32* next, double* ego_reward, double* cost0) {
+  const uint32_t A = cp->num_other_agents + 1;
+  const float crossing_point = (cp->chain_length - 1.0f) / 2.0f + 1.0f; /* CROSSING_POINT(), parameters.h:28 */
+  const float old_x_ego = s->x[0];
+  const float v_ego = action[0] + cp->min_velocity_ego;                 /* :306-309 (ActionIdx -> float) */
+  const float new_x_ego = s->x[0] + v_ego;                              /* :119 */
+  const int out_of_map = new_x_ego < 0.0f;                              /* :121-123 */
+  int collision = 0;
+  memset(next, 0, sizeof(*next));
+  next->x[0] = new_x_ego;
+  next->last[0] = v_ego;
+  for (uint32_t i = 1; i < A; ++i) {
+    const float new_x = s->x[i] + action[i];                            /* :130 */
+    next->x[i] = (new_x >= 0.0f) ? new_x : 0.0f;                        /* :131 */
+    next->last[i] = action[i];
+    if (new_x_ego >= crossing_point && old_x_ego <= crossing_point && next->x[i] >= crossing_point &&
+        s->x[i] <= crossing_point)
+      collision = 1;                                                    /* :135-139 */
+  }
+  const int goal = (new_x_ego >= cp->ego_goal_pos) && !collision;       /* :142 */
+  next->terminal = (uint8_t)(goal || collision || out_of_map);          /* :144 */
+  next->goal = (uint8_t)goal;
+  next->collided = (uint8_t)collision;
+  double r = (double)goal * cp->reward_goal_reached + (double)collision * cp->reward_collision; /* :146-148 */
+  r = r + cp->reward_collision * (double)out_of_map;
+  r = r + cp->reward_step;
+  *ego_reward = r;
+  *cost0 = cp->cost_only_collision ? (double)((float)collision * 1.0f) : (double)-1.0f * r; /* :149-153 */
+}
+
+void orc_rollout_f32(const mamcts_crossing_params_f32* cp, const mamcts_params* mp, const orc_state_f32* start,
+                     uint32_t start_depth, int32_t kind, const float* replay, uint32_t replay_steps,
+                     const uint32_t* const_actions, uint64_t seed, uint32_t stream_hi, uint32_t stream_lo,
+                     orc_rollout_result_f32* out) {
+  const uint32_t A = cp->num_other_agents + 1;
+  const uint32_t n_ego = (uint32_t)(cp->max_velocity_ego - cp->min_velocity_ego + 1.0f); /* NUM_EGO_ACTIONS() */
+  orc_state_f32 state = *start;
+  double ego = 0.0, cost0 = 0.0, len = 0.0, prob = 1.0;
+  double other[ORC_MAX_AGENTS];
+  for (uint32_t j = 0; j < ORC_MAX_AGENTS; ++j) other[j] = 0.0;
+  const double gamma = mp->discount_factor;
+  double m = gamma;
+  uint32_t it = 0, depth = start_depth;
+  uint32_t cap = mp->rh_max_number_of_iterations;
+  if (kind == MAMCTS_SRC_REPLAY && replay_steps < cap) cap = replay_steps;
+  while (!state.terminal && it < cap && depth < mp->max_search_depth) {
+    float act[ORC_MAX_AGENTS];
+    for (uint32_t a = 0; a < A; ++a) {
+      if (kind == MAMCTS_SRC_REPLAY) {
+        act[a] = replay[(size_t)it * A + a];
+      } else {
+        const uint32_t idx = kind == MAMCTS_SRC_REFERENCE_CONST
+                                 ? const_actions[a]
+                                 : orc_philox_draw(seed, stream_hi, stream_lo, A, it, a, a == 0 ? n_ego : cp->num_other_actions);
+        if (a == 0) {
+          act[a] = (float)idx;
+        } else {
+          memcpy(&act[a], &idx, sizeof(float)); /* aconv<float>(ActionIdx): the low bytes reinterpreted */
+        }
+      }
+    }
+    orc_state_f32 next;
+    double r, c0;
+    orc_crossing_f32_execute(cp, &state, act, &next, &r, &c0);
+    m = gamma * m;
+    ego += m * r;
+    for (uint32_t j = 1; j < A; ++j) other[j - 1] = m * 0.0;
+    cost0 += c0;
+    m = m * gamma;
+    len += 1.0;
+    prob *= 1.0 / (double)n_ego;
+    it += 1;
+    depth += 1;
+    state = next;
+  }
+  out->ego_return = ego * prob;
+  for (uint32_t j = 0; j < ORC_MAX_AGENTS; ++j) out->other_return[j] = other[j];
+  out->cost0 = cost0 * prob;
+  out->step_length = len;
+  out->steps = it;
+  out->final_state = state;
+}
+
 static double orc_cost_mean(const double* c, uint32_t C) {
   double acc = 0.0; /* std::accumulate(begin, end, 0.0) / size(), hypothesis_statistic.h:120,159 */
   for (uint32_t i = 0; i < C; ++i) acc += c[i];

@@ -92,6 +92,34 @@ void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* s
  * vals[k], k < K. K in {1,2,4,8,16} or a multiple of 32 (<=256) or a multiple of 256. */
 double orc_reduce_mean(const double* vals, uint32_t K);
 
+/* ---- CrossingState<float> (environments/crossing_state.h with Domain = float) ------------------ */
+
+typedef struct orc_state_f32 {
+  float x[ORC_MAX_AGENTS];
+  float last[ORC_MAX_AGENTS];
+  uint8_t terminal, goal, collided, pad;
+} orc_state_f32;
+
+typedef struct orc_rollout_result_f32 {
+  double ego_return;
+  double other_return[ORC_MAX_AGENTS];
+  double cost0;
+  double step_length;
+  uint32_t steps;
+  orc_state_f32 final_state;
+} orc_rollout_result_f32;
+
+/* execute (:115-163). action[0] = ego action index (as float), action[1..] = the others' velocities. */
+void orc_crossing_f32_execute(const mamcts_crossing_params_f32* cp, const orc_state_f32* s, const float* action,
+                              orc_state_f32* next, double* ego_reward, double* cost0);
+/* RandomHeuristic::rollout over it. kind REPLAY: replay[step*A + agent] floats; REFERENCE_CONST / PHILOX:
+ * index-valued, an other agent's index i acts as the float with bit pattern i (crossing_state_common.h:
+ * 19-27). */
+void orc_rollout_f32(const mamcts_crossing_params_f32* cp, const mamcts_params* mp, const orc_state_f32* start,
+                     uint32_t start_depth, int32_t kind, const float* replay, uint32_t replay_steps,
+                     const uint32_t* const_actions, uint64_t seed, uint32_t stream_hi, uint32_t stream_lo,
+                     orc_rollout_result_f32* out);
+
 /* ---- backup: HypothesisStatistic (mcts/hypothesis/hypothesis_statistic.h:100-134,158-161) ---- */
 /* Same arrays as mamcts_backup_hypothesis / mamcts_hyp_stats (HOST), plain sequential restatement. */
 void orc_backup_hypothesis(double gamma, uint32_t num_others, uint32_t n_paths, const uint32_t* leaf_node,

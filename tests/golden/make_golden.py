@@ -220,6 +220,56 @@ def gen_hypothesis_backup():
     dump("hypothesis_backup.json", cases)
 
 
+def f32hex(a):
+    """float32 arrays as their uint32 bit patterns (exact, incl. denormals and -0.0)."""
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).ravel().tolist()
+
+
+def gen_float_domain():
+    """CrossingState<float>: execute on random float states / velocities and whole
+    RandomHeuristic rollouts with UCT statistics (index-valued actions: an other agent's index i acts as
+    the float with bit pattern i, F5), recorded for REPLAY."""
+    from mamcts_b200 import default_crossing_params_f32
+    rng = np.random.default_rng(31415)
+    ex = []
+    for num_others, chain, goal, cost_only in ((1, 21.0, 12.0, 0), (2, 20.0, 11.5, 1), (3, 41.0, 26.0, 0)):
+        cp = default_crossing_params_f32(num_other_agents=num_others, chain_length=chain, ego_goal_pos=goal,
+                                         cost_only_collision=cost_only, reward_step=-0.25)
+        A, n = num_others + 1, 96
+        x = (rng.random((A, n)) * (chain / 2 + 6) - 1).astype(np.float32)
+        x[1:] = np.maximum(x[1:], 0)
+        last = (rng.random((A, n)) * 6 - 3).astype(np.float32)
+        act = np.zeros((A, n), dtype=np.float32)
+        act[0] = rng.integers(0, 4, n)
+        act[1:] = (rng.random((A - 1, n)) * 8 - 4).astype(np.float32)
+        # a third of the cases sit just before the crossing point and move forward: collisions
+        cpt = (chain - 1) / 2 + 1
+        k = n // 3
+        x[:, :k] = (cpt - rng.random((A, k)) * 2.5).astype(np.float32)
+        act[0, :k] = rng.integers(2, 4, k)
+        act[1:, :k] = (rng.random((A - 1, k)) * 4).astype(np.float32)
+        nx, nl, fl, r, c0 = O.ref_crossing_execute_f32(cp, x, last, act)
+        ex.append(dict(num_others=num_others, chain_length=chain, ego_goal_pos=goal, cost_only_collision=cost_only,
+                       reward_step=-0.25, x=f32hex(x), last=f32hex(last), action=f32hex(act), next_x=f32hex(nx),
+                       next_last=f32hex(nl), flags=fl.tolist(), reward=fhex(r), cost0=fhex(c0)))
+    ro = []
+    for seed, num_others in ((1000, 2), (7, 1), (42, 3)):
+        mp = default_params(random_seed=seed, rh_max_number_of_iterations=50)
+        cp = default_crossing_params_f32(num_other_agents=num_others)
+        A, n = num_others + 1, 40
+        x = (rng.random((A, n)) * 12).astype(np.float32)
+        x[:, 0] = 5.0
+        depth = rng.integers(0, 4, size=n).astype(np.uint32)
+        r = O.ref_rollout_crossing_f32(mp, cp, x, None, depth, rec_stride=50)
+        ro.append(dict(seed=seed, num_others=num_others, x=f32hex(x), depth=depth.tolist(),
+                       const_actions=[O.ref_expand_order(mp, 4)[0]] + [O.ref_expand_order(mp, 30)[0]] * num_others,
+                       ego_return=fhex(r["ego_return"]), ego_cost=fhex(r["ego_cost"]),
+                       step_length=fhex(r["step_length"]), steps=r["steps"].tolist(), final_x=f32hex(r["final_x"]),
+                       final_last_action=f32hex(r["final_last_action"]), final_flags=r["final_flags"].tolist(),
+                       rec_actions=f32hex(r["rec_actions"])))
+    dump("float_domain.json", dict(execute=ex, rollouts=ro))
+
+
 def gen_search():
     cases = []
     # C1: SimpleState(4), 20 iterations (reference test/uct/uct_test.cc:22-40 parameters)
@@ -273,5 +323,6 @@ if __name__ == "__main__":
     gen_rollouts()
     gen_hypothesis()
     gen_hypothesis_backup()
+    gen_float_domain()
     gen_search()
     gen_merge()

@@ -382,6 +382,89 @@ def ref_rollout_crossing(mp: Params, cp: CrossingParams, x, last=None, flags=Non
     return out
 
 
+# ---- CrossingState<float> -----------------------------------------------------------------------
+
+class OrcStateF32(C.Structure):
+    _fields_ = [("x", C.c_float * MAX_AGENTS), ("last", C.c_float * MAX_AGENTS), ("terminal", C.c_uint8),
+                ("goal", C.c_uint8), ("collided", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class OrcRolloutResultF32(C.Structure):
+    _fields_ = [("ego_return", C.c_double), ("other_return", C.c_double * MAX_AGENTS), ("cost0", C.c_double),
+                ("step_length", C.c_double), ("steps", C.c_uint32), ("final_state", OrcStateF32)]
+
+
+def _state_f32(x, last=None, terminal=False):
+    s = OrcStateF32()
+    for a, v in enumerate(x):
+        s.x[a] = float(v)
+        s.last[a] = 2.0 if last is None else float(last[a])
+    s.terminal = 1 if terminal else 0
+    return s
+
+
+def crossing_execute_f32(cp, x, last, action):
+    """Oracle CrossingState<float>::execute. action[0]: ego index; [1:]: other velocities (float)."""
+    s = _state_f32(x, last)
+    nxt = OrcStateF32()
+    r, c0 = C.c_double(), C.c_double()
+    act = (C.c_float * MAX_AGENTS)(*[float(a) for a in action])
+    oracle().orc_crossing_f32_execute(C.byref(cp), C.byref(s), act, C.byref(nxt), C.byref(r), C.byref(c0))
+    A = cp.num_other_agents + 1
+    flags = (1 if nxt.terminal else 0) | (2 if nxt.goal else 0) | (4 if nxt.collided else 0)
+    return (np.array(nxt.x[:A], dtype=np.float32), np.array(nxt.last[:A], dtype=np.float32), flags, r.value, c0.value)
+
+
+def rollout_f32(cp, mp: Params, x, last=None, terminal=False, depth=0, kind=SRC_PHILOX, replay=None,
+                const_actions=None, seed=0, stream_hi=0, stream_lo=0):
+    """One oracle rollout on CrossingState<float>."""
+    st = _state_f32(x, last, terminal)
+    res = OrcRolloutResultF32()
+    rp, nrep = None, 0
+    if replay is not None:
+        rep_a = np.ascontiguousarray(replay, dtype=np.float32)
+        nrep, rp = rep_a.shape[0], _ptr(rep_a)
+    ca = (C.c_uint32 * MAX_AGENTS)(*(const_actions or []))
+    oracle().orc_rollout_f32(C.byref(cp), C.byref(mp), C.byref(st), C.c_uint32(depth), C.c_int32(kind), rp,
+                             C.c_uint32(nrep), ca, C.c_uint64(seed), C.c_uint32(stream_hi), C.c_uint32(stream_lo),
+                             C.byref(res))
+    A = cp.num_other_agents + 1
+    fs = res.final_state
+    return dict(ego_return=res.ego_return, other_return=list(res.other_return[:A - 1]), cost0=res.cost0,
+                step_length=res.step_length, steps=res.steps,
+                final_x=np.array(fs.x[:A], dtype=np.float32), final_last=np.array(fs.last[:A], dtype=np.float32),
+                final_flags=(1 if fs.terminal else 0) | (2 if fs.goal else 0) | (4 if fs.collided else 0))
+
+
+def ref_rollout_crossing_f32(mp: Params, cp, x, last=None, depth=None, rec_stride=64):
+    """The reference's RandomHeuristic::rollout on CrossingState<float> (UCT statistics), recorded."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    A, n = x.shape
+    last_a = None if last is None else np.ascontiguousarray(last, dtype=np.float32)
+    depth_a = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+    out = dict(ego_return=np.zeros(n), ego_cost=np.zeros(n), step_length=np.zeros(n),
+               steps=np.zeros(n, dtype=np.uint32), final_x=np.zeros((A, n), dtype=np.float32),
+               final_last_action=np.zeros((A, n), dtype=np.float32), final_flags=np.zeros(n, dtype=np.uint8),
+               rec_actions=np.zeros((n, rec_stride, A), dtype=np.float32))
+    reference().ref_rollout_crossing_f32(
+        C.byref(mp), C.byref(cp), C.c_uint32(n), _ptr(x), _ptr(last_a), _ptr(depth_a), _ptr(out["ego_return"]),
+        _ptr(out["ego_cost"]), _ptr(out["step_length"]), _ptr(out["steps"]), _ptr(out["final_x"]),
+        _ptr(out["final_last_action"]), _ptr(out["final_flags"]), _ptr(out["rec_actions"]), C.c_uint32(rec_stride))
+    return out
+
+
+def ref_crossing_execute_f32(cp, x, last, action):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    A, n = x.shape
+    last = np.ascontiguousarray(last, dtype=np.float32)
+    action = np.ascontiguousarray(action, dtype=np.float32)
+    nx, nl = np.zeros((A, n), dtype=np.float32), np.zeros((A, n), dtype=np.float32)
+    fl, r, c0 = np.zeros(n, dtype=np.uint8), np.zeros(n), np.zeros(n)
+    reference().ref_crossing_execute_f32(C.byref(cp), C.c_uint32(n), _ptr(x), _ptr(last), _ptr(action), _ptr(nx),
+                                         _ptr(nl), _ptr(fl), _ptr(r), _ptr(c0))
+    return nx, nl, fl, r, c0
+
+
 def ref_policy_calculate_action(cp: CrossingParams, agent_x, agent_last, ego_x, ego_last, gap):
     """The reference's AgentPolicyCrossingState<int>::calculate_action on n inputs."""
     arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (agent_x, agent_last, ego_x, ego_last, gap)]

@@ -41,8 +41,8 @@ def test_struct_layouts_match_header_sizes(lib):
     assert C.sizeof(_abi.Params) == 6 * 8 + 8 * 4
     assert C.sizeof(_abi.CrossingParams) == 3 * 8 + 10 * 4
     assert C.sizeof(_abi.SimpleParams) == 8
-    assert C.sizeof(_abi.ActionSource) == 8 + 16 + 8 + 16 * 4 + 8 + 8 + 8 + 8 + 16
-    assert C.sizeof(_abi.RolloutOut) == 8 + 10 * 8 + 8
+    assert C.sizeof(_abi.ActionSource) == 8 + 24 + 8 + 16 * 4 + 8 + 8 + 8 + 8 + 16
+    assert C.sizeof(_abi.RolloutOut) == 8 + 12 * 8 + 8
     assert C.sizeof(_abi.UctStats) == 16 + 5 * 8
 
 
@@ -98,6 +98,7 @@ def test_ctypes_structs_match_the_c_compiler(tmp_path):
         pytest.skip("no gcc")
     structs = {"mamcts_config": _abi.Config, "mamcts_params": _abi.Params,
                "mamcts_crossing_params": _abi.CrossingParams, "mamcts_simple_params": _abi.SimpleParams,
+               "mamcts_crossing_params_f32": _abi.CrossingParamsF32,
                "mamcts_action_source": _abi.ActionSource, "mamcts_rollout_out": _abi.RolloutOut,
                "mamcts_uct_stats": _abi.UctStats, "mamcts_hyp_stats": _abi.HypStats,
                "mamcts_search_config": _abi.SearchConfig}
