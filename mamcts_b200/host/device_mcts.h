@@ -19,8 +19,13 @@
 
 #include <chrono>
 #include <cstring>
+#include <fstream>
+#include <iomanip>
 #include <map>
+#include <sstream>
+#include <string>
 #include <utility>
+#include <cmath>
 #include <vector>
 
 #include "cuda_random_heuristic.h"  // CudaEngine, to_mamcts_params
@@ -63,6 +68,12 @@ class DeviceRootParallelMcts {
     CS::pack(current_state, x, last, &flags);
     num_agents_ = CS::num_agents(current_state);
     num_ego_actions_ = (unsigned)current_state.get_num_actions(current_state.get_ego_agent_idx());
+    agent_ids_.assign(1, current_state.get_ego_agent_idx());
+    num_actions_.assign(1, num_ego_actions_);
+    for (auto ai : current_state.get_other_agent_idx()) {
+      agent_ids_.push_back(ai);
+      num_actions_.push_back((unsigned)current_state.get_num_actions(ai));
+    }
     if (!search_) {
       mamcts_search_config cfg;
       std::memset(&cfg, 0, sizeof(cfg));
@@ -131,6 +142,66 @@ class DeviceRootParallelMcts {
     return s;
   }
 
+  // Mcts::printTreeToDotFile (mcts.h:370-372 -> StageNode::printTree / printLayer, stage_node.h:322-391) for
+  // one device tree: the same Graphviz text - a dotted cluster per stage node with one "V=.., N=.."
+  // node per agent (UctStatistic::print_node_information), one "a=.., N=.., V=.." edge per agent and
+  // child (print_edge_information) - down to max_depth. Node ids are depth-first indices (the
+  // reference numbers nodes in creation order); an other agent's edge label uses its POSITION in the
+  // joint action (the reference indexes the joint action by agent id there, which only coincides for
+  // CrossingState).
+  void printTreeToDotFile(std::string filename = "tree", unsigned tree = 0, unsigned max_depth = 5) const {
+    require_search();
+    uint32_t nodes = 0;
+    {
+      double v; uint32_t vis, mask; double q[MAMCTS_MAX_ACTIONS]; uint32_t n[MAMCTS_MAX_ACTIONS];
+      CudaEngine::check(mamcts_search_root_stats(search_, tree, 0, &v, &vis, q, n, &mask, &nodes), "mamcts_search_root_stats");
+    }
+    unsigned max_actions = 0;
+    for (unsigned na : num_actions_) max_actions = std::max(max_actions, na);
+    const size_t stride = 4 + (size_t)num_agents_ * (3 + 2 * max_actions);
+    std::vector<double> rec((size_t)nodes * stride);
+    uint32_t count = 0;
+    CudaEngine::check(mamcts_search_dump_tree(search_, tree, rec.data(), nodes, &count), "mamcts_search_dump_tree");
+    std::ofstream out(filename + ".gv");
+    out << "digraph G {" << std::endl << "labelloc = \"t\";" << std::endl;
+    auto stat = [&](uint32_t i, unsigned p) { return rec.data() + (size_t)i * stride + 4 + (size_t)p * (3 + 2 * max_actions); };
+    auto node_label = [&](uint32_t i, unsigned p) {
+      std::stringstream ss;
+      ss << std::setprecision(2) << "V=" << stat(i, p)[1] << ", N=" << (unsigned)stat(i, p)[0];
+      return ss.str();
+    };
+    std::vector<uint32_t> path;  // depth-first: path[d] = record index of the current ancestor at depth d
+    for (uint32_t i = 0; i < count; ++i) {
+      const double* r = rec.data() + (size_t)i * stride;
+      const unsigned depth = (unsigned)r[0];
+      path.resize(depth + 1);
+      path[depth] = i;
+      if (depth > max_depth) continue;
+      const uint32_t id = i + 1;
+      out << "subgraph cluster_node_" << id << "{" << std::endl;
+      for (unsigned p = 0; p < num_agents_; ++p)
+        out << "node" << id << "_" << int(agent_ids_[p]) << "[label=\"" << node_label(i, p) << " \n Ag." << int(agent_ids_[p])
+            << "\"]" << ";" << std::endl;
+      out << "label= \"ID " << id << "\";" << std::endl << "graph[style=dotted]; }" << std::endl;
+      if (depth == 0) continue;
+      // the edges from the parent (line order is irrelevant to Graphviz; the reference prints them after
+      // the child's subtree)
+      const uint32_t parent = path[depth - 1];
+      double code = r[1];
+      for (unsigned p = 0; p < num_agents_; ++p) {
+        const unsigned a = (unsigned)std::fmod(code, (double)max_actions);
+        code = std::floor(code / max_actions);
+        std::stringstream lab;
+        if (stat(parent, p)[3 + a] >= 0.0)
+          lab << std::setprecision(2) << "a=" << int(a) << ", N=" << (unsigned)stat(parent, p)[3 + a] << ", V="
+              << stat(parent, p)[3 + max_actions + a];
+        out << "node" << (parent + 1) << "_" << int(agent_ids_[p]) << " -> " << "node" << id << "_" << int(agent_ids_[p])
+            << "[label=\"" << lab.str() << "\"]" << ";" << std::endl;
+      }
+    }
+    out << "}" << std::endl;
+  }
+
  private:
   void require_search() const {
     if (!search_ || !merged_valid_) {
@@ -158,6 +229,8 @@ class DeviceRootParallelMcts {
   mamcts_search* search_;
   unsigned num_iterations_, search_time_;
   unsigned num_agents_ = 0, num_ego_actions_ = 0;
+  std::vector<AgentIdx> agent_ids_;      // positional: ego, then get_other_agent_idx() order
+  std::vector<unsigned> num_actions_;
   bool merged_valid_;
   double merged_q_[MAMCTS_MAX_ACTIONS] = {0.0}, merged_value_ = 0.0;
   uint64_t merged_n_[MAMCTS_MAX_ACTIONS] = {0}, merged_visits_ = 0;

@@ -9,7 +9,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <functional>
+#include <iterator>
+#include <set>
+#include <string>
 #include <map>
 #include <sstream>
 #include <vector>
@@ -359,6 +363,26 @@ int main() {
       dev.search(state);  // a second decision re-roots the same arenas
       ok = ok && same_stat(ref.get_root().get_ego_int_node(), dev.get_root_statistic(2, 0));
       CHECK_MSG(ok, "device_mcts_reference_const_equals_stock_mcts");
+      // Graphviz export: same labels as the reference's printTreeToDotFile (ids and line order differ)
+      ref.printTreeToDotFile("/tmp/mamcts_dropin_ref_tree");
+      dev.printTreeToDotFile("/tmp/mamcts_dropin_dev_tree", 3);
+      auto labels = [](const char* path) {
+        std::ifstream f(path);
+        std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        std::multiset<std::string> out;
+        size_t pos = 0, clusters = 0;
+        while ((pos = text.find("[label=\"", pos)) != std::string::npos) {
+          const size_t end = text.find("\"]", pos);
+          out.insert(text.substr(pos + 8, end - pos - 8));
+          pos = end;
+        }
+        pos = 0;
+        while ((pos = text.find("subgraph cluster_node_", pos)) != std::string::npos) { ++clusters; ++pos; }
+        out.insert("clusters=" + std::to_string(clusters));
+        return out;
+      };
+      const auto lr = labels("/tmp/mamcts_dropin_ref_tree.gv"), ld = labels("/tmp/mamcts_dropin_dev_tree.gv");
+      CHECK_MSG(lr == ld && lr.size() > 100, "device_mcts_dot_export_labels_equal_reference");
     }
     {  // PHILOX: device trees == the reference's StageNode trees fed by the same GPU rollouts
       const MctsParameters p = test_params(400);

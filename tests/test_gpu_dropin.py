@@ -45,7 +45,8 @@ def test_reference_mcts_with_cuda_heuristic_and_statistic_is_bit_equal():
                  "batched_host_trees_equal_oracle", "batched_host_trees_cuda_statistic_equal_oracle",
                  "philox_crossing_tree_backprop_invariant", "philox_crossing_tree_backprop_invariant_cuda_statistic",
                  "philox_simple_tree_backprop_invariant", "philox_simple_tree_backprop_invariant_cuda_statistic",
-                 "device_mcts_reference_const_equals_stock_mcts", "device_mcts_philox_equals_host_trees",
+                 "device_mcts_reference_const_equals_stock_mcts", "device_mcts_dot_export_labels_equal_reference",
+                 "device_mcts_philox_equals_host_trees",
                  "device_mcts_simple_state_20_iterations"):
         assert f"PASS {name}" in out, f"{name} did not pass:\n{out[-4000:]}"
 
