@@ -95,6 +95,9 @@ struct CrossingEnv {
   static constexpr int A = NO + 1;
   static constexpr int kStateInts = A;     // x_pos per agent
   static constexpr bool kHasCost = true;   // get_num_costs() == 1, crossing_state.h:101-103
+  // rewards[1..] are always 0 (:145): with a non-negative discount every return, V and Q of the other
+  // agents is exactly +0.0 for the whole search
+  static constexpr bool kOtherRewardZero = true;
   struct State {
     int32_t x[A];
     int32_t last[A];
@@ -208,6 +211,7 @@ struct SimpleEnv {
   static constexpr int A = 2;
   static constexpr int kStateInts = 1;     // state_length_
   static constexpr bool kHasCost = false;  // get_num_costs() == 0, :60-62
+  static constexpr bool kOtherRewardZero = false;
   struct State {
     int32_t x[A];     // x[0] = state_length_, x[1] unused (kept for a uniform interface)
     int32_t last[A];  // unused

@@ -130,6 +130,12 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   Counters path_cnt[kPathMaxCompact];
   uint32_t done = 0;
   bool failed = false;
+  // Environments whose other agents never receive a reward (CrossingState: rewards[1..] stay 0,
+  // crossing_state.h:145): with a discount >= 0 every return of theirs is +0.0 (m >= 0, m * 0.0 = +0.0),
+  // hence every G = 0.0 + gamma * (+0.0), Q and V of theirs is +0.0 for the whole search - their action
+  // values need not be loaded (they are still written when an action is first expanded, so the record
+  // always holds what the reference's statistic holds).
+  const bool other_values_zero = Env::kOtherRewardZero && p.gamma >= 0.0;
 
 #pragma unroll 1
   for (uint32_t iter = 0; iter < p.iterations; ++iter) {   // a failed lane idles through the barriers
@@ -155,7 +161,8 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
 #pragma unroll
       for (int i = 0; i < NE / 2 + (NE & 1); ++i) qe[i] = reinterpret_cast<const double2*>(&nd->q_e[0])[i];
 #pragma unroll
-      for (int i = 0; i < NA / 2 + (NA & 1); ++i) qo[i] = reinterpret_cast<const double2*>(&nd->q_o[0])[i];
+      for (int i = 0; i < NA / 2 + (NA & 1); ++i)
+        qo[i] = other_values_zero ? make_double2(0.0, 0.0) : reinterpret_cast<const double2*>(&nd->q_o[0])[i];
       // child table: only the part that shares a 64-byte burst with the action values is requested
       // up front; the entry load below fetches the rest when the chosen slot lies there
       prefetch_l1(reinterpret_cast<const char*>(nd) + ((offsetof(Inner, child) + 31) & ~size_t(31)));

@@ -21,7 +21,7 @@ def _random_case(rng):
     chain, goal = [(21, 12), (41, 26), (15, 9)][int(rng.integers(0, 3))]
     iters = int(rng.integers(50, 900))
     mp = default_params(
-        discount_factor=float(rng.choice([0.9, 0.95, 1.0, 0.5])),
+        discount_factor=float(rng.choice([0.9, 0.95, 1.0, 0.5, -0.9])),
         random_seed=int(rng.integers(1, 5000)),
         max_number_of_iterations=iters,
         max_number_of_nodes=int(rng.choice([100000000, 100000000, 60, 300])),
