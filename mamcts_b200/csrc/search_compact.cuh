@@ -60,13 +60,14 @@ struct alignas(64) InnerRec {
     double V[2];           // value_
     double G[2];           // latest_return_
   } v;
-  alignas(32) double q_e[NE];   // action_value_
-  alignas(32) double q_o[NA];
-  // The child table follows the action values directly: with 16-bit entries its first 20 slots end at
-  // byte 192, i.e. inside the third 64-byte DRAM burst that the tail of q_o brings in anyway; the
-  // fourth burst is only touched for the last 8 slots.
+  alignas(32) double q_e[NE];   // action_value_ of the ego agent
+  // The child table follows the ego's action values: with 16-bit entries its first 16 slots complete the
+  // second 64-byte DRAM burst of the record. The other agent's action values come last: for
+  // environments whose other agents are reward-free they are never read (see the kernel), so a visit
+  // touches two bursts, or three when the chosen slot is one of the last 12.
   CIDX child[NCHILD];
   uint32_t parent;              // inner index of the parent (export only)
+  alignas(32) double q_o[NA];
 };
 
 template <int A>
