@@ -200,7 +200,8 @@ class SearchConfig(C.Structure):
 
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmamcts_b200.so")
+_LIB_PATH = os.environ.get("MAMCTS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc",
+                                                            "libmamcts_b200.so")
 
 
 def lib_path() -> str:

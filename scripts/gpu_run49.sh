@@ -1,0 +1,5 @@
+python scripts/sweep_search.py "32,64,65536,10000,0,2,3200;32,64,75776,10000,0,2,3200" 2>&1 | grep lpw
+echo "== min blocks 10 (96 regs)"
+MAMCTS_B200_LIB=$PWD/scripts/micro/libmamcts_mb10.so python scripts/sweep_search.py "32,64,65536,10000,0,2,3200;32,64,75776,10000,0,2,3200;32,64,94720,10000,0,2,3200" 2>&1 | grep lpw
+echo "== min blocks 12 (80 regs)"
+MAMCTS_B200_LIB=$PWD/scripts/micro/libmamcts_mb12.so python scripts/sweep_search.py "32,64,65536,10000,0,2,3200;32,64,94720,10000,0,2,3200;32,64,113664,10000,0,2,3200" 2>&1 | grep lpw
