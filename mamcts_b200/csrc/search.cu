@@ -155,6 +155,10 @@ struct SearchT final : public mamcts_search {
 };
 
 // Compact (two-tier) layout: search_compact.cuh.
+static_assert(sizeof(InnerRec<CrossingEnv<1>, 4, 7, 28, uint16_t, uint16_t>) == 256 &&
+                  sizeof(InnerRec<CrossingEnv<1>, 4, 7, 28, uint16_t, uint16_t>::Counters) == 32 &&
+                  sizeof(InnerRec<CrossingEnv<1>, 4, 7, 28, uint16_t, uint32_t>::Counters) == 64,
+              "C2 inner record: 256 bytes, counters in one sector (16-bit counts) or two (32-bit)");
 template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT>
 struct SearchC final : public mamcts_search {
   using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
@@ -202,7 +206,7 @@ struct SearchC final : public mamcts_search {
     const Inner* nd = static_cast<const Inner*>(node);
     *parent = nd->parent;
     *depth = 0;  // not stored: the export derives it
-    *visits = nd->c.visit_count;
+    *visits = nd->c.h.visit_count;
     for (int a = 0; a < Env::A; ++a) ja[a] = nd->c.ja[a];
   }
 
@@ -212,8 +216,8 @@ struct SearchC final : public mamcts_search {
     const uint32_t k = agent ? 1 : 0;
     *value = nd->v.V[k];
     *latest = nd->v.G[k];
-    *visits = nd->c.N[k];
-    *nexp = nd->c.nexp[k];
+    *visits = nd->c.h.N[k];
+    *nexp = nd->c.h.nexp[k];
     if (agent == 0) { for (int a = 0; a < NE; ++a) { q[a] = nd->q_e[a]; n[a] = nd->c.n_e[a]; } }
     else { for (int a = 0; a < NA; ++a) { q[a] = nd->q_o[a]; n[a] = nd->c.n_o[a]; } }
   }
@@ -223,7 +227,7 @@ struct SearchC final : public mamcts_search {
     const size_t tree_bytes = sizeof(Inner) * (size_t)max_inner;
     g->q = reinterpret_cast<const double*>(base + offsetof(Inner, q_e));
     g->n = base + offsetof(Inner, c) + offsetof(typename Inner::Counters, n_e);
-    g->visits = base + offsetof(Inner, c) + offsetof(typename Inner::Counters, N);
+    g->visits = base + offsetof(Inner, c) + offsetof(typename Inner::Counters, h) + offsetof(typename Inner::Head, N);
     g->count_bytes = sizeof(CNT);
     g->root_slot = nullptr;
     g->stride_q = tree_bytes / sizeof(double);
@@ -265,7 +269,7 @@ struct SearchC final : public mamcts_search {
     auto emit_inner = [&](uint32_t i, uint32_t depth, double code, size_t nkids) {
       if (count < capacity_records) {
         double* r = records + (size_t)count * stride;
-        r[0] = depth; r[1] = code; r[2] = in[i].c.visit_count; r[3] = (double)nkids;
+        r[0] = depth; r[1] = code; r[2] = in[i].c.h.visit_count; r[3] = (double)nkids;
         for (uint32_t a = 0; a < A; ++a) {
           double* o = r + 4 + a * (3 + 2 * max_actions);
           double v, l, qq[MAMCTS_MAX_ACTIONS];

@@ -26,6 +26,7 @@
 // arithmetic in the same order; only where the values live changes.
 #pragma once
 #include <cstddef>
+#include <type_traits>
 
 #include "search_kernel.cuh"
 
@@ -48,13 +49,17 @@ struct alignas(64) InnerRec {
   static constexpr int A = Env::A;
   static_assert(NCHILD > 0, "the compact layout needs a direct child table");
   static_assert(A == 2, "the compact layout is built for two agents");
-  struct alignas(32) Counters {
-    CNT visit_count;       // StageNode::visit_count_
+  // the part of the counters every backup of a visit rewrites, sized for ONE 8- or 16-byte store
+  struct alignas(4 * sizeof(CNT)) Head {
     CNT N[2];              // total_node_visits_ (ego, other)
+    CNT visit_count;       // StageNode::visit_count_
     uint8_t nexp[2];       // ucb_statistics_.size(): the first nexp entries of the widening order
-    uint8_t ja[2];         // joint action leading here (export only)
+  };
+  struct alignas(32) Counters {
+    Head h;
     CNT n_e[NE];           // action_count_
     CNT n_o[NA];
+    uint8_t ja[2];         // joint action leading here (export only)
   } c;
   struct alignas(32) Values {
     double V[2];           // value_
@@ -119,16 +124,22 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   root.flags = (uint32_t)Env::terminal(p.env, root);
 
   // The path of the current iteration (collect(), node_statistic.h:115-121) and everything the backup
-  // of a level needs: the counters sector as loaded (it is updated and written back whole) and the
-  // chosen actions' Q and the V of both agents. These arrays live in local memory, which is
-  // interleaved by lane: one wavefront serves all 32 lanes, unlike a global access of 32 records.
+  // of a level needs: the head of the counters as loaded, the counts and values of the chosen actions
+  // and the node values. These arrays live in local memory, which is interleaved by lane (one
+  // wavefront serves all 32 lanes, unlike a global access of 32 records) - but every word of them is
+  // L2 traffic, as much as the tree itself, so a level records 42 bytes (66 when the other agent's
+  // values are not known to be zero), not the whole counters sector.
   using Counters = typename Inner::Counters;
+  using Head = typename Inner::Head;
+  using HeadWord = typename std::conditional<sizeof(Head) == 8, uint2, uint4>::type;
+  static_assert(sizeof(Head) == sizeof(HeadWord), "the head is written with one store");
   constexpr int kCntVec = sizeof(Counters) / 16;
   uint32_t path_node[kPathMaxCompact];
   uint8_t path_ja[kPathMaxCompact][A];
-  double path_r0[kPathMaxCompact], path_r1[kPathMaxCompact];
-  double path_q[kPathMaxCompact][A], path_v[kPathMaxCompact][A];
-  Counters path_cnt[kPathMaxCompact];
+  double path_r0[kPathMaxCompact], path_q0[kPathMaxCompact], path_v0[kPathMaxCompact];
+  double path_r1[kPathMaxCompact], path_q1[kPathMaxCompact], path_v1[kPathMaxCompact];  // unused if zero
+  HeadWord path_head[kPathMaxCompact];
+  CNT path_n[kPathMaxCompact][A];
   uint32_t done = 0;
   bool failed = false;
   // Environments whose other agents never receive a reward (CrossingState: rewards[1..] stay 0,
@@ -171,7 +182,7 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       __builtin_memcpy(&cc, craw, sizeof(cc));
       if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) {  // :183-187
         // no rollout: the node's own latest return is backed up (mcts.h:309-329)
-        nd->c.visit_count = (CNT)(cc.visit_count + 1);                   // :180
+        nd->c.h.visit_count = (CNT)(cc.h.visit_count + 1);               // :180
         G[0] = nd->v.G[0];
         G[1] = nd->v.G[1];
         break;
@@ -179,8 +190,8 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       if (depth >= (uint32_t)kPathMaxCompact) { failed = true; atomicAdd(p.counters + 7, 1ull); break; }
       StatRegs<NE> ego;
       StatRegs<NA> oth;
-      ego.N = cc.N[0]; ego.nexp = cc.nexp[0]; ego.V = vv.x;
-      oth.N = cc.N[1]; oth.nexp = cc.nexp[1]; oth.V = vv.y;
+      ego.N = cc.h.N[0]; ego.nexp = cc.h.nexp[0]; ego.V = vv.x;
+      oth.N = cc.h.N[1]; oth.nexp = cc.h.nexp[1]; oth.V = vv.y;
 #pragma unroll
       for (int a = 0; a < NE; ++a) { ego.Q[a] = (a & 1) ? qe[a / 2].y : qe[a / 2].x; ego.n[a] = cc.n_e[a]; }
 #pragma unroll
@@ -191,14 +202,15 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       ja[0] = (uint8_t)select_action<NE>(ego, p, 0, p.n_ego, exact_evals, back[0], w0);  // :190-195
       ja[1] = (uint8_t)select_action<NA>(oth, p, 1, p.n_oth, exact_evals, back[1], w1);
       // Nothing is stored during the descent: visit_count + 1 (:180) and a newly expanded action
-      // (ucb_statistics_[a] = UcbPair()) go into the counters image, which this iteration's backup of
-      // the level writes back together with N and n[a].
-      cc.visit_count = (CNT)(cc.visit_count + 1);
-      if (w0) cc.nexp[0] = (uint8_t)(cc.nexp[0] + 1);
-      if (w1) cc.nexp[1] = (uint8_t)(cc.nexp[1] + 1);
-      path_cnt[depth] = cc;
-      path_q[depth][0] = back[0].q; path_q[depth][1] = back[1].q;
-      path_v[depth][0] = back[0].v; path_v[depth][1] = back[1].v;
+      // (ucb_statistics_[a] = UcbPair()) go into the image of the head, which this iteration's backup
+      // of the level writes back together with N, followed by the two n[a].
+      cc.h.visit_count = (CNT)(cc.h.visit_count + 1);
+      if (w0) cc.h.nexp[0] = (uint8_t)(cc.h.nexp[0] + 1);
+      if (w1) cc.h.nexp[1] = (uint8_t)(cc.h.nexp[1] + 1);
+      __builtin_memcpy(&path_head[depth], &cc.h, sizeof(Head));
+      path_n[depth][0] = (CNT)back[0].cnt0; path_n[depth][1] = (CNT)back[1].cnt0;
+      path_q0[depth] = back[0].q; path_v0[depth] = back[0].v;
+      if (!other_values_zero) { path_q1[depth] = back[1].q; path_v1[depth] = back[1].v; }
       const uint32_t slot = (uint32_t)ja[0] * NA + (uint32_t)ja[1];
       const uint32_t entry = nd->child[slot];                            // :198
       // the child's state and the reward collected on the edge (collect(), node_statistic.h:115-121)
@@ -210,7 +222,7 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       st.flags = (st.flags & ~1u) | (uint32_t)Env::terminal(p.env, st);
       path_node[depth] = node;
       path_r0[depth] = r_ego;
-      path_r1[depth] = r_other;
+      if (!other_values_zero) path_r1[depth] = r_other;
       path_ja[depth][0] = ja[0];
       path_ja[depth][1] = ja[1];
       depth += 1;
@@ -234,9 +246,9 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
         if (num_inner >= c.max_inner) { failed = true; atomicAdd(p.counters + 6, 1ull); break; }
         const uint32_t id = num_inner++;
         Inner* cn = inner + id;
-        cn->c.visit_count = 0;
-        cn->c.N[0] = 1; cn->c.N[1] = 1;          // update_from_heuristic left 0 + 1 visits
-        cn->c.nexp[0] = 0; cn->c.nexp[1] = 0;
+        cn->c.h.visit_count = 0;
+        cn->c.h.N[0] = 1; cn->c.h.N[1] = 1;      // update_from_heuristic left 0 + 1 visits
+        cn->c.h.nexp[0] = 0; cn->c.h.nexp[1] = 0;
         cn->c.ja[0] = ja[0]; cn->c.ja[1] = ja[1];
 #pragma unroll
         for (int a = 0; a < NE; ++a) cn->c.n_e[a] = 0;
@@ -275,21 +287,25 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
     while (level > 0) {
       level -= 1;
       Inner* pn = inner + path_node[level];
-      Counters& ci = path_cnt[level];
+      Head hd;
+      __builtin_memcpy(&hd, &path_head[level], sizeof(Head));
       const uint32_t ae = path_ja[level][0], ao = path_ja[level][1];
       BackRegs be, bo;
-      be.q = path_q[level][0]; be.v = path_v[level][0]; be.cnt0 = ci.n_e[ae]; be.nv0 = ci.N[0];
-      bo.q = path_q[level][1]; bo.v = path_v[level][1]; bo.cnt0 = ci.n_o[ao]; bo.nv0 = ci.N[1];
+      be.q = path_q0[level]; be.v = path_v0[level]; be.cnt0 = path_n[level][0]; be.nv0 = hd.N[0];
+      bo.q = other_values_zero ? 0.0 : path_q1[level];
+      bo.v = other_values_zero ? 0.0 : path_v1[level];
+      bo.cnt0 = path_n[level][1]; bo.nv0 = hd.N[1];
       const BackOut e = back_compute(be, path_r0[level], p.gamma, G[0]);
-      const BackOut o = back_compute(bo, path_r1[level], p.gamma, G[1]);
-      ci.N[0] = (CNT)e.nv; ci.N[1] = (CNT)o.nv;
-      ci.n_e[ae] = (CNT)e.cnt; ci.n_o[ao] = (CNT)o.cnt;
-      // counters sector(s) and the value sector go back whole, 16 bytes per store
+      const BackOut o = back_compute(bo, other_values_zero ? 0.0 : path_r1[level], p.gamma, G[1]);
+      hd.N[0] = (CNT)e.nv; hd.N[1] = (CNT)o.nv;
+      // the head of the counters goes back with one store, then the two action counts; the value
+      // sector goes back whole, 16 bytes per store
       {
-        const uint4* src = reinterpret_cast<const uint4*>(&ci);
-        uint4* dst = reinterpret_cast<uint4*>(pn);
-#pragma unroll
-        for (int i = 0; i < kCntVec; ++i) dst[i] = src[i];
+        HeadWord hw;
+        __builtin_memcpy(&hw, &hd, sizeof(Head));
+        *reinterpret_cast<HeadWord*>(&pn->c.h) = hw;
+        pn->c.n_e[ae] = (CNT)e.cnt;
+        pn->c.n_o[ao] = (CNT)o.cnt;
         double2* vdst = reinterpret_cast<double2*>(&pn->v.V[0]);
         vdst[0] = make_double2(e.v, o.v);
         vdst[1] = make_double2(e.G, o.G);
@@ -326,8 +342,8 @@ __global__ void search_compact_reset_kernel(void* inner_v, uint32_t* tree_nodes,
   if (tree >= T) return;
   Inner* root = static_cast<Inner*>(inner_v) + (size_t)tree * max_inner;
   root->parent = kNoParent;
-  root->c.visit_count = 0;
-  root->c.N[0] = 0; root->c.N[1] = 0; root->c.nexp[0] = 0; root->c.nexp[1] = 0;
+  root->c.h.visit_count = 0;
+  root->c.h.N[0] = 0; root->c.h.N[1] = 0; root->c.h.nexp[0] = 0; root->c.h.nexp[1] = 0;
   root->c.ja[0] = 0; root->c.ja[1] = 0;
   for (int a = 0; a < NE; ++a) { root->c.n_e[a] = 0; root->q_e[a] = 0.0; }  // the root merge reads n[a] > 0 as "expanded"
   for (int a = 0; a < NA; ++a) { root->c.n_o[a] = 0; root->q_o[a] = 0.0; }
