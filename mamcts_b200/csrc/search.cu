@@ -565,6 +565,7 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   auto alloc = [&](void** ptr, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(ptr, bytes); };
   if (s->is_compact()) {
     s->max_inner = cfg->max_inner_nodes_per_tree ? std::min(cfg->max_inner_nodes_per_tree, max_nodes) : max_nodes;
+    s->max_inner = std::min(s->max_inner, 1u << 24);   // the path record keeps an inner index in 24 bits
     alloc(&s->d_inner, s->node_bytes() * (size_t)T * s->max_inner);
     alloc(&s->d_leaves, s->leaf_bytes() * (size_t)T * max_nodes);
     alloc((void**)&s->d_tree_inner, sizeof(uint32_t) * T);

@@ -127,19 +127,20 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   // of a level needs: the head of the counters as loaded, the counts and values of the chosen actions
   // and the node values. These arrays live in local memory, which is interleaved by lane (one
   // wavefront serves all 32 lanes, unlike a global access of 32 records) - but every word of them is
-  // L2 traffic, as much as the tree itself, so a level records 42 bytes (66 when the other agent's
-  // values are not known to be zero), not the whole counters sector.
+  // L2 traffic, as much as the tree itself, so a level records 32 bytes (48 when the other agent's
+  // values are not known to be zero) plus its rewards when they are not +0.0 (a bit mask in a
+  // register says which levels have one), not the whole counters sector.
   using Counters = typename Inner::Counters;
   using Head = typename Inner::Head;
   using HeadWord = typename std::conditional<sizeof(Head) == 8, uint2, uint4>::type;
   static_assert(sizeof(Head) == sizeof(HeadWord), "the head is written with one store");
   constexpr int kCntVec = sizeof(Counters) / 16;
-  uint32_t path_node[kPathMaxCompact];
-  uint8_t path_ja[kPathMaxCompact][A];
+  using CountPair = typename std::conditional<sizeof(CNT) == 2, uint32_t, uint2>::type;
+  uint32_t path_node[kPathMaxCompact];   // inner index | ego action << 24 | other action << 28
   double path_r0[kPathMaxCompact], path_q0[kPathMaxCompact], path_v0[kPathMaxCompact];
   double path_r1[kPathMaxCompact], path_q1[kPathMaxCompact], path_v1[kPathMaxCompact];  // unused if zero
   HeadWord path_head[kPathMaxCompact];
-  CNT path_n[kPathMaxCompact][A];
+  CountPair path_n[kPathMaxCompact];     // n[a] of the chosen actions as loaded
   uint32_t done = 0;
   bool failed = false;
   // Environments whose other agents never receive a reward (CrossingState: rewards[1..] stay 0,
@@ -156,6 +157,7 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
     typename Env::State st = root;
     double G[A];
     bool do_rollout = false;
+    unsigned long long reward_levels = 0;   // bit d: the edge leaving level d carries a reward != +0.0
     uint32_t new_leaf = 0, creation = 0;
     // ---- select & expand: mcts.h:300-305, stage_node.h:167-232 --------------------------------
 #pragma unroll 1
@@ -208,7 +210,13 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       if (w0) cc.h.nexp[0] = (uint8_t)(cc.h.nexp[0] + 1);
       if (w1) cc.h.nexp[1] = (uint8_t)(cc.h.nexp[1] + 1);
       __builtin_memcpy(&path_head[depth], &cc.h, sizeof(Head));
-      path_n[depth][0] = (CNT)back[0].cnt0; path_n[depth][1] = (CNT)back[1].cnt0;
+      if (sizeof(CNT) == 2) {
+        const uint32_t pair = back[0].cnt0 | (back[1].cnt0 << 16);
+        __builtin_memcpy(&path_n[depth], &pair, sizeof(pair));
+      } else {
+        const uint2 pair = make_uint2(back[0].cnt0, back[1].cnt0);
+        __builtin_memcpy(&path_n[depth], &pair, sizeof(CountPair));
+      }
       path_q0[depth] = back[0].q; path_v0[depth] = back[0].v;
       if (!other_values_zero) { path_q1[depth] = back[1].q; path_v1[depth] = back[1].v; }
       const uint32_t slot = (uint32_t)ja[0] * NA + (uint32_t)ja[1];
@@ -220,11 +228,12 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       double r_ego, r_other, c0;
       Env::step(p.env, st, act, r_ego, r_other, c0);
       st.flags = (st.flags & ~1u) | (uint32_t)Env::terminal(p.env, st);
-      path_node[depth] = node;
-      path_r0[depth] = r_ego;
-      if (!other_values_zero) path_r1[depth] = r_other;
-      path_ja[depth][0] = ja[0];
-      path_ja[depth][1] = ja[1];
+      path_node[depth] = node | ((uint32_t)ja[0] << 24) | ((uint32_t)ja[1] << 28);
+      if (__double_as_longlong(r_ego) != 0ll || (!other_values_zero && __double_as_longlong(r_other) != 0ll)) {
+        path_r0[depth] = r_ego;
+        if (!other_values_zero) path_r1[depth] = r_other;
+        reward_levels |= 1ull << depth;
+      }
       depth += 1;
       if (entry & 1u) { node = entry >> 1; continue; }                   // existing inner node, :199-206
       if (entry == 0u) {
@@ -286,17 +295,29 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
 #pragma unroll 1
     while (level > 0) {
       level -= 1;
-      Inner* pn = inner + path_node[level];
+      const uint32_t word = path_node[level];
+      Inner* pn = inner + (word & 0xFFFFFFu);
       Head hd;
       __builtin_memcpy(&hd, &path_head[level], sizeof(Head));
-      const uint32_t ae = path_ja[level][0], ao = path_ja[level][1];
+      const uint32_t ae = (word >> 24) & 15u, ao = word >> 28;
+      uint32_t n_ego, n_oth;
+      if (sizeof(CNT) == 2) {
+        uint32_t pair;
+        __builtin_memcpy(&pair, &path_n[level], sizeof(pair));
+        n_ego = pair & 0xFFFFu; n_oth = pair >> 16;
+      } else {
+        uint2 pair;
+        __builtin_memcpy(&pair, &path_n[level], sizeof(CountPair));
+        n_ego = pair.x; n_oth = pair.y;
+      }
+      const bool has_reward = (reward_levels >> level) & 1ull;
       BackRegs be, bo;
-      be.q = path_q0[level]; be.v = path_v0[level]; be.cnt0 = path_n[level][0]; be.nv0 = hd.N[0];
+      be.q = path_q0[level]; be.v = path_v0[level]; be.cnt0 = n_ego; be.nv0 = hd.N[0];
       bo.q = other_values_zero ? 0.0 : path_q1[level];
       bo.v = other_values_zero ? 0.0 : path_v1[level];
-      bo.cnt0 = path_n[level][1]; bo.nv0 = hd.N[1];
-      const BackOut e = back_compute(be, path_r0[level], p.gamma, G[0]);
-      const BackOut o = back_compute(bo, other_values_zero ? 0.0 : path_r1[level], p.gamma, G[1]);
+      bo.cnt0 = n_oth; bo.nv0 = hd.N[1];
+      const BackOut e = back_compute(be, has_reward ? path_r0[level] : 0.0, p.gamma, G[0]);
+      const BackOut o = back_compute(bo, (has_reward && !other_values_zero) ? path_r1[level] : 0.0, p.gamma, G[1]);
       hd.N[0] = (CNT)e.nv; hd.N[1] = (CNT)o.nv;
       // the head of the counters goes back with one store, then the two action counts; the value
       // sector goes back whole, 16 bytes per store
