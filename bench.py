@@ -478,9 +478,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--trees", type=int, default=65536,
-                    help="root-parallel trees per GPU (compact layout: 65536 trees x (3200 x 256 B inner + "
-                         "10001 x 16 B leaf records) = 64 GB of HBM)")
+    ap.add_argument("--trees", type=int, default=75776,
+                    help="root-parallel trees per GPU: 75776 = 148 SMs x 8 resident blocks x 64 lanes, one full "
+                         "wave of the search grid (compact layout: 75776 trees x (3200 x 256 B inner + "
+                         "10001 x 16 B leaf records) = 74 GB of HBM)")
     ap.add_argument("--cpu-repeats", type=int, default=24, help="whole searches per host thread for cpu_baseline")
     ap.add_argument("--layout", type=int, default=2, help="tree layout: 0 auto, 1 classic, 2 compact")
     ap.add_argument("--max-inner", type=int, default=3200,

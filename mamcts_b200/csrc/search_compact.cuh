@@ -32,6 +32,12 @@
 
 namespace mamcts {
 
+#ifndef MAMCTS_COMPACT_MIN_BLOCKS
+#define MAMCTS_COMPACT_MIN_BLOCKS 8   // 128 registers; 10 or 12 (96 / 80 registers) spill and are slower
+#endif
+#ifndef MAMCTS_PATH_SHARED_LEVELS
+#define MAMCTS_PATH_SHARED_LEVELS 5
+#endif
 constexpr int kPathMaxCompact = 64;  // deepest leaf the compact layout can back up (error beyond)
 
 // Inner record, laid out by 32-byte sector so that a visit touches as few sectors as possible (the
@@ -97,7 +103,7 @@ __device__ __forceinline__ CIDX inner_entry(uint32_t inner) { return (CIDX)((inn
 // counters[6] = trees that ran out of inner records, counters[7] = trees with a path deeper than
 // kPathMaxCompact; either makes mamcts_search_run's caller see an error at the next read-back.
 template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT, int KIND>
-__global__ void __launch_bounds__(kSearchThreads)
+__global__ void __launch_bounds__(kSearchThreads, MAMCTS_COMPACT_MIN_BLOCKS)
 search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_constant__ CompactParams c) {
   using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
   constexpr int A = Env::A;
@@ -141,6 +147,15 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   double path_r1[kPathMaxCompact], path_q1[kPathMaxCompact], path_v1[kPathMaxCompact];  // unused if zero
   HeadWord path_head[kPathMaxCompact];
   CountPair path_n[kPathMaxCompact];     // n[a] of the chosen actions as loaded
+  // The first kSharedLevels levels (nearly every visit) keep their record in shared memory instead:
+  // no L1/L2 traffic at all. Column = thread, so a warp's access is conflict-free.
+  constexpr int kSharedLevels = MAMCTS_PATH_SHARED_LEVELS;
+  constexpr int kSL = kSharedLevels > 0 ? kSharedLevels : 1;
+  __shared__ uint32_t s_node[kSL][kSearchThreads];
+  __shared__ CountPair s_n[kSL][kSearchThreads];
+  __shared__ HeadWord s_head[kSL][kSearchThreads];
+  __shared__ double s_q0[kSL][kSearchThreads], s_v0[kSL][kSearchThreads];
+  const uint32_t tid = threadIdx.x;
   uint32_t done = 0;
   bool failed = false;
   // Environments whose other agents never receive a reward (CrossingState: rewards[1..] stay 0,
@@ -209,15 +224,24 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       cc.h.visit_count = (CNT)(cc.h.visit_count + 1);
       if (w0) cc.h.nexp[0] = (uint8_t)(cc.h.nexp[0] + 1);
       if (w1) cc.h.nexp[1] = (uint8_t)(cc.h.nexp[1] + 1);
-      __builtin_memcpy(&path_head[depth], &cc.h, sizeof(Head));
+      HeadWord head_w;
+      __builtin_memcpy(&head_w, &cc.h, sizeof(Head));
+      CountPair pair_w;
       if (sizeof(CNT) == 2) {
         const uint32_t pair = back[0].cnt0 | (back[1].cnt0 << 16);
-        __builtin_memcpy(&path_n[depth], &pair, sizeof(pair));
+        __builtin_memcpy(&pair_w, &pair, sizeof(pair));
       } else {
         const uint2 pair = make_uint2(back[0].cnt0, back[1].cnt0);
-        __builtin_memcpy(&path_n[depth], &pair, sizeof(CountPair));
+        __builtin_memcpy(&pair_w, &pair, sizeof(CountPair));
       }
-      path_q0[depth] = back[0].q; path_v0[depth] = back[0].v;
+      const uint32_t node_w = node | ((uint32_t)ja[0] << 24) | ((uint32_t)ja[1] << 28);
+      if (depth < (uint32_t)kSharedLevels) {
+        s_head[depth][tid] = head_w; s_n[depth][tid] = pair_w; s_node[depth][tid] = node_w;
+        s_q0[depth][tid] = back[0].q; s_v0[depth][tid] = back[0].v;
+      } else {
+        path_head[depth] = head_w; path_n[depth] = pair_w; path_node[depth] = node_w;
+        path_q0[depth] = back[0].q; path_v0[depth] = back[0].v;
+      }
       if (!other_values_zero) { path_q1[depth] = back[1].q; path_v1[depth] = back[1].v; }
       const uint32_t slot = (uint32_t)ja[0] * NA + (uint32_t)ja[1];
       const uint32_t entry = nd->child[slot];                            // :198
@@ -228,7 +252,6 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       double r_ego, r_other, c0;
       Env::step(p.env, st, act, r_ego, r_other, c0);
       st.flags = (st.flags & ~1u) | (uint32_t)Env::terminal(p.env, st);
-      path_node[depth] = node | ((uint32_t)ja[0] << 24) | ((uint32_t)ja[1] << 28);
       if (__double_as_longlong(r_ego) != 0ll || (!other_values_zero && __double_as_longlong(r_other) != 0ll)) {
         path_r0[depth] = r_ego;
         if (!other_values_zero) path_r1[depth] = r_other;
@@ -295,24 +318,34 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
 #pragma unroll 1
     while (level > 0) {
       level -= 1;
-      const uint32_t word = path_node[level];
+      uint32_t word;
+      HeadWord head_w;
+      CountPair pair_w;
+      double q0, v0;
+      if (level < (uint32_t)kSharedLevels) {
+        word = s_node[level][tid]; head_w = s_head[level][tid]; pair_w = s_n[level][tid];
+        q0 = s_q0[level][tid]; v0 = s_v0[level][tid];
+      } else {
+        word = path_node[level]; head_w = path_head[level]; pair_w = path_n[level];
+        q0 = path_q0[level]; v0 = path_v0[level];
+      }
       Inner* pn = inner + (word & 0xFFFFFFu);
       Head hd;
-      __builtin_memcpy(&hd, &path_head[level], sizeof(Head));
+      __builtin_memcpy(&hd, &head_w, sizeof(Head));
       const uint32_t ae = (word >> 24) & 15u, ao = word >> 28;
       uint32_t n_ego, n_oth;
       if (sizeof(CNT) == 2) {
         uint32_t pair;
-        __builtin_memcpy(&pair, &path_n[level], sizeof(pair));
+        __builtin_memcpy(&pair, &pair_w, sizeof(pair));
         n_ego = pair & 0xFFFFu; n_oth = pair >> 16;
       } else {
         uint2 pair;
-        __builtin_memcpy(&pair, &path_n[level], sizeof(CountPair));
+        __builtin_memcpy(&pair, &pair_w, sizeof(CountPair));
         n_ego = pair.x; n_oth = pair.y;
       }
       const bool has_reward = (reward_levels >> level) & 1ull;
       BackRegs be, bo;
-      be.q = path_q0[level]; be.v = path_v0[level]; be.cnt0 = n_ego; be.nv0 = hd.N[0];
+      be.q = q0; be.v = v0; be.cnt0 = n_ego; be.nv0 = hd.N[0];
       bo.q = other_values_zero ? 0.0 : path_q1[level];
       bo.v = other_values_zero ? 0.0 : path_v1[level];
       bo.cnt0 = n_oth; bo.nv0 = hd.N[1];
