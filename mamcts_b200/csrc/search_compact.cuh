@@ -193,7 +193,8 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       for (int i = 0; i < NA / 2 + (NA & 1); ++i)
         qo[i] = other_values_zero ? make_double2(0.0, 0.0) : reinterpret_cast<const double2*>(&nd->q_o[0])[i];
       // child table: only the part that shares a 64-byte burst with the action values is requested
-      // up front; the entry load below fetches the rest when the chosen slot lies there
+      // up front; the entry load below fetches the rest when the chosen slot lies there (requesting all of
+      // it up front changes nothing: profiles/r01_search_sweeps.txt r57)
       prefetch_l1(reinterpret_cast<const char*>(nd) + ((offsetof(Inner, child) + 31) & ~size_t(31)));
       Counters cc;
       __builtin_memcpy(&cc, craw, sizeof(cc));
