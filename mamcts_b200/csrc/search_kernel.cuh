@@ -187,8 +187,12 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   // bit-identical (Q, n) have identical exact scores, so the strict-> first-max rule picks the same
   // one either way. Anything else (including non-finite intermediates) falls through to the exact
   // FP64 evaluation, so the selected action is ALWAYS the reference's.
+  // The exact evaluation then only has to look at the actions within `delta` of the FP32 maximum:
+  // every other action's exact score is provably below the exact score of the FP32 winner, so it
+  // cannot be the (first) exact maximum.
   int bi = -1;
   bool ok;
+  uint32_t candidates = mask;
   {
     const float rangef = (float)range;
     const float inv_range = __frcp_rn(rangef);
@@ -214,10 +218,13 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
     for (int a = 0; a < NACT; ++a) if (a == bi) { qb = q[a]; nb = cnt[a]; }
     if (ok) {
       const float delta = 6e-6f * (best_sc + 1.0f);
+      candidates = 0u;
 #pragma unroll
       for (int a = 0; a < NACT; ++a) {
-        if (((mask >> a) & 1u) && a != bi && sc[a] >= best_sc - delta)
-          ok &= (q[a] == qb) & (cnt[a] == nb);
+        if (((mask >> a) & 1u) && sc[a] >= best_sc - delta) {
+          candidates |= 1u << a;
+          if (a != bi) ok &= (q[a] == qb) & (cnt[a] == nb);
+        }
       }
     }
     back.q = qb;
@@ -226,7 +233,7 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   if (ok) return (uint32_t)bi;
 
   exact_evals += 1;
-  const uint32_t best = exact_ucb_argmax<NACT>(r, mask, lo, range, log2N, p.two_c);
+  const uint32_t best = exact_ucb_argmax<NACT>(r, candidates, lo, range, log2N, p.two_c);
 #pragma unroll
   for (int a = 0; a < NACT; ++a) if ((uint32_t)a == best) { back.q = r.Q[a]; back.cnt0 = r.n[a]; }
   return best;
