@@ -604,9 +604,17 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   p.gamma = mp.discount_factor; p.two_c = 2 * mp.uct_exploration_constant;
   p.lb = mp.uct_lower_bound; p.ub = mp.uct_upper_bound;
   p.env = ep;
-  // Profiling knobs (scripts/sweep_search.py, profiles/r01_search_sweeps.txt): trees per warp and block
-  // size. The defaults (32 lanes = 32 trees per warp, 64-thread blocks) measured best.
-  p.lanes_per_warp = 32;
+  // Trees per warp: lanes of a warp wait for the deepest path and the longest rollout among them, so a
+  // warp should carry as few trees as the GPU has room for - the smallest power of two that still fits
+  // all trees into the resident warps (16 per SM). 75 776 trees and more: 32; 8 192 trees (C5 per GPU): 4,
+  // +21 % over 32; 1 024 trees: 1, +77 % (profiles/r01_search_sweeps.txt r60). The environment variables
+  // are profiling knobs (scripts/sweep_search.py).
+  {
+    const uint64_t warp_slots = (uint64_t)std::max(e->num_sms, 1) * 16u;
+    uint32_t lpw = 1;
+    while (lpw < 32 && (uint64_t)lpw * warp_slots < (uint64_t)cfg->num_trees) lpw <<= 1;
+    p.lanes_per_warp = lpw;
+  }
   if (const char* v = std::getenv("MAMCTS_SEARCH_LPW")) {
     const int l = std::atoi(v);
     if (l >= 1 && l <= 32) p.lanes_per_warp = (uint32_t)l;
