@@ -158,6 +158,35 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
     q[a] = ex ? r.Q[a] : 0.0;
     cnt[a] = ex ? r.n[a] : 1u;
   }
+  // Equal action values (always the case for an agent that never receives a reward, e.g. the other
+  // agents of CrossingState): with bound estimation the normalised value is the same for every action
+  // (0 when the common value is 0, else exactly q / q = 1), so the UCB score is
+  // norm + fl(2c * fl(sqrt(fl(2 ln N / n_a)))), a non-increasing function of n_a. It is STRICTLY
+  // decreasing under the conditions checked here - N >= 2 (2 ln N >= 1.38), 2c >= 0.01, n_a <= 2^20: two
+  // counts differ by a factor >= 1 + 2^-20, their bonuses by a relative 4.7e-7 and an absolute
+  // >= 5e-12 * max(1, bonus), far beyond the four roundings (1.1e-16 relative each) and the ulp of the
+  // sum - and every score exceeds DBL_MIN, the initial maximum of the reference's loop. So the first
+  // maximum of the exact scores is the first minimum of the counts; no floating-point work is needed.
+  if (p.use_bound_est && N >= 2u && p.two_c >= 0.01) {
+    long long q_first = 0;
+    bool first = true, same = true;
+    uint32_t min_cnt = 0xFFFFFFFFu, max_cnt = 0u, arg = 0u;
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) {
+      if ((mask >> a) & 1u) {
+        const long long bits = __double_as_longlong(q[a]);
+        if (first) { q_first = bits; first = false; }
+        same &= (bits == q_first);
+        if (cnt[a] < min_cnt) { min_cnt = cnt[a]; arg = (uint32_t)a; }
+        max_cnt = cnt[a] > max_cnt ? cnt[a] : max_cnt;
+      }
+    }
+    if (same && !first && min_cnt >= 1u && max_cnt <= (1u << 20) && isfinite(__longlong_as_double(q_first))) {
+      back.q = __longlong_as_double(q_first);
+      back.cnt0 = min_cnt;
+      return arg;
+    }
+  }
   double lo = p.lb, hi = p.ub;
   if (p.use_bound_est) {  // calculate_bounds_based_on_stat :122-132
     double mn = 0.0, mx = 0.0;
