@@ -218,7 +218,7 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       BackRegs back[A];
       bool w0, w1;
       ja[0] = (uint8_t)select_action<NE>(ego, p, 0, p.n_ego, exact_evals, back[0], w0);  // :190-195
-      ja[1] = (uint8_t)select_action<NA>(oth, p, 1, p.n_oth, exact_evals, back[1], w1);
+      ja[1] = (uint8_t)select_action<NA>(oth, p, 1, p.n_oth, exact_evals, back[1], w1, other_values_zero);
       // Nothing is stored during the descent: visit_count + 1 (:180) and a newly expanded action
       // (ucb_statistics_[a] = UcbPair()) go into the image of the head, which this iteration's backup
       // of the level writes back together with N, followed by the two n[a].
@@ -351,7 +351,9 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       bo.v = other_values_zero ? 0.0 : path_v1[level];
       bo.cnt0 = n_oth; bo.nv0 = hd.N[1];
       const BackOut e = back_compute(be, has_reward ? path_r0[level] : 0.0, p.gamma, G[0]);
-      const BackOut o = back_compute(bo, (has_reward && !other_values_zero) ? path_r1[level] : 0.0, p.gamma, G[1]);
+      BackOut o;   // a reward-free agent: every value stays +0.0 (see other_values_zero), only the counts move
+      if (other_values_zero) { o.G = 0.0; o.q = 0.0; o.v = 0.0; o.cnt = bo.cnt0 + 1; o.nv = bo.nv0 + 1; }
+      else o = back_compute(bo, has_reward ? path_r1[level] : 0.0, p.gamma, G[1]);
       hd.N[0] = (CNT)e.nv; hd.N[1] = (CNT)o.nv;
       // the head of the counters goes back with one store, then the two action counts; the value
       // sector goes back whole, 16 bytes per store

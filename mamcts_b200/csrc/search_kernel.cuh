@@ -137,7 +137,8 @@ __device__ __noinline__ uint32_t exact_ucb_argmax(StatRegs<NACT> r, uint32_t mas
 template <int NACT>
 __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const SearchParams& p, int cls,
                                                   uint32_t nact, unsigned long long& exact_evals,
-                                                  BackRegs& back, bool& widened) {
+                                                  BackRegs& back, bool& widened,
+                                                  bool values_known_equal = false) {
   const uint32_t N = r.N;
   const uint32_t nexp = r.nexp;
   back.nv0 = N;
@@ -176,7 +177,7 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
       if ((mask >> a) & 1u) {
         const long long bits = __double_as_longlong(q[a]);
         if (first) { q_first = bits; first = false; }
-        same &= (bits == q_first);
+        if (!values_known_equal) same &= (bits == q_first);
         if (cnt[a] < min_cnt) { min_cnt = cnt[a]; arg = (uint32_t)a; }
         max_cnt = cnt[a] > max_cnt ? cnt[a] : max_cnt;
       }
@@ -343,9 +344,8 @@ __device__ __forceinline__ uint32_t hash_ja(uint32_t parent, const uint8_t (&ja)
 
 // RandomHeuristic::rollout for one lane (reference random_heuristic.h:27-104); same arithmetic and
 // the same Philox stream positions as rollout_kernel. Returns the ego return; `other` = the (shared)
-// other-agent return. The step loop is NOT unrolled over the S steps a Philox block feeds: all lanes
-// of a warp start their rollout together, so `it % S` is uniform among the active lanes and the
-// 16-bit lane is picked with a short select chain; the body stays a few hundred bytes of code.
+// other-agent return. All lanes of a warp start their rollout together, so the position inside a
+// Philox block is uniform among the active lanes.
 template <class Env, int KIND>
 __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename Env::State st,
                                                uint32_t depth, uint32_t s_hi, uint32_t s_lo,
@@ -357,51 +357,45 @@ __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename E
   // accumulation without per-step FP64 work: see rollout_kernel (rollout.cu)
   double ego = 0.0, r_other_last = 0.0;
   uint32_t it = 0;
-  bool fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
-  Philox4 blk[NB];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) blk[b].w[0] = blk[b].w[1] = blk[b].w[2] = blk[b].w[3] = 0u;
+  // it >= rh_cap or depth >= max_depth (random_heuristic.h:45-47) as one limit on `it`
+  const uint32_t depth_room = p.max_depth > depth ? p.max_depth - depth : 0u;
+  const uint32_t limit = p.rh_cap < depth_room ? p.rh_cap : depth_room;
+  bool fin = Env::terminal(p.env, st) | (it >= limit);
 #pragma unroll 1
   while (!fin) {
-    const uint32_t sub = (S > 1) ? it % S : 0u;
+    // one Philox block feeds S steps; the S steps are unrolled so that every step reads its 16-bit
+    // lanes from fixed registers (a dynamic pick cost 8 % of the kernel's instructions)
+    Philox4 blk[NB];
     if (KIND == MAMCTS_SRC_PHILOX) {
-      if (A <= 8) {
-        if (sub == 0) blk[0] = philox4x32_10(it / S, s_lo, s_hi, 0u, p.key0, p.key1);
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        blk[b] = philox4x32_10((A <= 8 ? it / S : it * NB + b), s_lo, s_hi, 0u, p.key0, p.key1);
+    }
+#pragma unroll
+    for (int sub = 0; sub < S; ++sub) {
+      int32_t act[A];
+      if (KIND == MAMCTS_SRC_PHILOX) {
+        uint32_t h[A], nact[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          h[a] = (A <= 8) ? philox_half(blk[0], sub * A + a) : philox_half(blk[a / 8], a % 8);
+          nact[a] = Env::num_actions(p.env, a);
+        }
+        philox_bounded_all<A>(h, nact, it * A, s_lo, s_hi, p.key0, p.key1);
+#pragma unroll
+        for (int a = 0; a < A; ++a) act[a] = (int32_t)h[a];
       } else {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) blk[b] = philox4x32_10(it * NB + b, s_lo, s_hi, 0u, p.key0, p.key1);
+        for (int a = 0; a < A; ++a) act[a] = (int32_t)const_act[a];
       }
+      double r_ego, r_other, c;
+      Env::step(p.env, st, act, r_ego, r_other, c);
+      if (r_ego != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it), r_ego));
+      r_other_last = r_other;
+      it += 1;
+      fin = Env::terminal(p.env, st) | (it >= limit);
+      if (fin) break;
     }
-    int32_t act[A];
-    if (KIND == MAMCTS_SRC_PHILOX) {
-      uint32_t h[A], nact[A];
-#pragma unroll
-      for (int a = 0; a < A; ++a) {
-        if (A <= 8) {
-          const uint32_t lane16 = sub * A + a;   // 16-bit lane of the block, DESIGN.md section 5
-          const uint32_t wi = lane16 >> 1;
-          const uint32_t word = (S == 1) ? blk[0].w[(a >> 1) & 3]
-                                         : (wi == 0 ? blk[0].w[0] : wi == 1 ? blk[0].w[1] : wi == 2 ? blk[0].w[2] : blk[0].w[3]);
-          h[a] = (lane16 & 1u) ? (word >> 16) : (word & 0xFFFFu);
-        } else {
-          h[a] = philox_half(blk[a / 8], a % 8);
-        }
-        nact[a] = Env::num_actions(p.env, a);
-      }
-      philox_bounded_all<A>(h, nact, it * A, s_lo, s_hi, p.key0, p.key1);
-#pragma unroll
-      for (int a = 0; a < A; ++a) act[a] = (int32_t)h[a];
-    } else {
-#pragma unroll
-      for (int a = 0; a < A; ++a) act[a] = (int32_t)const_act[a];
-    }
-    double r_ego, r_other, c;
-    Env::step(p.env, st, act, r_ego, r_other, c);
-    if (r_ego != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it), r_ego));
-    r_other_last = r_other;
-    it += 1;
-    depth += 1;
-    fin = Env::terminal(p.env, st) | (it >= p.rh_cap) | (depth >= p.max_depth);
   }
   steps = it;
   other = it ? __dmul_rn(__ldg(p.disc + it - 1), r_other_last) : 0.0;

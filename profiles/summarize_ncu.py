@@ -75,6 +75,11 @@ def main():
         print(f"{f}:{l:4d} samples {num(d.get('Warp Stall Sampling (All Samples)')) / ts * 100:5.1f}% "
               f"inst {num(d.get('Instructions Executed')) / ti * 100:5.1f}% "
               f"lanes {num(d.get('Thread Instructions Executed')) / max(num(d.get('Instructions Executed')), 1):4.1f}  {s}")
+    print("\n== per source line (top 30 by executed warp instructions)")
+    for f, l, s, d in sorted(lines, key=lambda t: -num(t[3].get("Instructions Executed")))[:30]:
+        print(f"{f}:{l:4d} inst {num(d.get('Instructions Executed')) / ti * 100:5.1f}% "
+              f"samples {num(d.get('Warp Stall Sampling (All Samples)')) / ts * 100:5.1f}% "
+              f"lanes {num(d.get('Thread Instructions Executed')) / max(num(d.get('Instructions Executed')), 1):4.1f}  {s}")
     print("\n== per source file")
     agg = collections.defaultdict(lambda: [0.0, 0.0])
     for f, l, s, d in lines:
