@@ -114,6 +114,19 @@ struct CrossingEnv {
   // Restates CrossingState<int>::execute, reference environments/crossing_state.h:115-163.
   __device__ __forceinline__ static void step(const EnvParams& p, State& s, const int32_t (&act)[A],
                                               double& r_ego, double& r_other, double& cost) {
+    const uint32_t f = step_outcome(p, s, act);
+    // :146-153: one of 8 host-evaluated values (see EnvParams::r_tab)
+    r_ego = p.r_tab[f];
+    r_other = 0.0;                                         // rewards[1..] stay 0 (:145 resize)
+    cost = p.c_tab[f];
+  }
+
+  // The reward and the cost of a step are functions of its outcome code f = goal | collision << 1 |
+  // out of bounds << 2 alone (r_tab / c_tab), and f != 0 exactly when the step ends the episode: a
+  // caller that only needs the rewards of an episode can look them up afterwards (lane_rollout).
+  static constexpr bool kOutcomeRewards = true;
+  __device__ __forceinline__ static double outcome_reward(const EnvParams& p, uint32_t f) { return p.r_tab[f]; }
+  __device__ __forceinline__ static uint32_t step_outcome(const EnvParams& p, State& s, const int32_t (&act)[A]) {
     const int32_t old_x = s.x[0];
     const int32_t v_ego = act[0] + p.min_v_ego;            // :306-309
     const int32_t new_x = old_x + v_ego;                   // :119 (ego not clamped)
@@ -132,11 +145,7 @@ struct CrossingEnv {
     s.last[0] = v_ego;
     const bool goal = (new_x >= p.goal_pos) & !coll;       // :142
     s.flags = (uint32_t)(goal | coll | oob) | ((uint32_t)goal << 1) | ((uint32_t)coll << 2);  // :144
-    // :146-153: one of 8 host-evaluated values (see EnvParams::r_tab)
-    const uint32_t f = (uint32_t)goal | ((uint32_t)coll << 1) | ((uint32_t)oob << 2);
-    r_ego = p.r_tab[f];
-    r_other = 0.0;                                         // rewards[1..] stay 0 (:145 resize)
-    cost = p.c_tab[f];
+    return (uint32_t)goal | ((uint32_t)coll << 1) | ((uint32_t)oob << 2);
   }
 };
 
@@ -151,6 +160,7 @@ struct CrossingEnvF {
   static constexpr int A = NO + 1;
   static constexpr int kStateInts = A;
   static constexpr bool kHasCost = true;
+  static constexpr bool kOutcomeRewards = false;
   struct State {
     float x[A];
     float last[A];
@@ -212,6 +222,7 @@ struct SimpleEnv {
   static constexpr int kStateInts = 1;     // state_length_
   static constexpr bool kHasCost = false;  // get_num_costs() == 0, :60-62
   static constexpr bool kOtherRewardZero = false;
+  static constexpr bool kOutcomeRewards = false;
   struct State {
     int32_t x[A];     // x[0] = state_length_, x[1] unused (kept for a uniform interface)
     int32_t last[A];  // unused
