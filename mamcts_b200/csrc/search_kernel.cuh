@@ -151,14 +151,6 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
     return p.tab->order[cls][nexp];                           // :64-68 (deterministic order, F2)
   }
   const uint32_t mask = p.tab->exp_mask[cls][nexp];
-  double q[NACT];
-  uint32_t cnt[NACT];
-#pragma unroll
-  for (int a = 0; a < NACT; ++a) {
-    const bool ex = (mask >> a) & 1u;
-    q[a] = ex ? r.Q[a] : 0.0;
-    cnt[a] = ex ? r.n[a] : 1u;
-  }
   // Equal action values (always the case for an agent that never receives a reward, e.g. the other
   // agents of CrossingState): with bound estimation the normalised value is the same for every action
   // (0 when the common value is 0, else exactly q / q = 1), so the UCB score is
@@ -168,25 +160,45 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   // >= 5e-12 * max(1, bonus), far beyond the four roundings (1.1e-16 relative each) and the ulp of the
   // sum - and every score exceeds DBL_MIN, the initial maximum of the reference's loop. So the first
   // maximum of the exact scores is the first minimum of the counts; no floating-point work is needed.
-  if (p.use_bound_est && N >= 2u && p.two_c >= 0.01) {
+  if (p.use_bound_est && N >= 2u && N <= (1u << 20) && p.two_c >= 0.01) {   // every n_a <= N
     long long q_first = 0;
     bool first = true, same = true;
-    uint32_t min_cnt = 0xFFFFFFFFu, max_cnt = 0u, arg = 0u;
+    if (!values_known_equal) {
 #pragma unroll
-    for (int a = 0; a < NACT; ++a) {
-      if ((mask >> a) & 1u) {
-        const long long bits = __double_as_longlong(q[a]);
-        if (first) { q_first = bits; first = false; }
-        if (!values_known_equal) same &= (bits == q_first);
-        if (cnt[a] < min_cnt) { min_cnt = cnt[a]; arg = (uint32_t)a; }
-        max_cnt = cnt[a] > max_cnt ? cnt[a] : max_cnt;
+      for (int a = 0; a < NACT; ++a) {
+        if ((mask >> a) & 1u) {
+          const long long bits = __double_as_longlong(r.Q[a]);
+          if (first) { q_first = bits; first = false; }
+          same &= (bits == q_first);
+        }
+      }
+    } else {
+      q_first = __double_as_longlong(r.Q[0]);
+    }
+    if (same) {
+      // first minimum of the counts: minimum of the keys n_a * 8 + a (NACT <= 8, n_a <= 2^20)
+      static_assert(NACT <= 8, "three key bits for the action");
+      uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+      for (int a = 0; a < NACT; ++a) {
+        const uint32_t k = ((mask >> a) & 1u) ? ((r.n[a] << 3) | (uint32_t)a) : 0xFFFFFFFFu;
+        key = k < key ? k : key;
+      }
+      const uint32_t min_cnt = key >> 3;
+      if (key != 0xFFFFFFFFu && min_cnt >= 1u && isfinite(__longlong_as_double(q_first))) {
+        back.q = __longlong_as_double(q_first);
+        back.cnt0 = min_cnt;
+        return key & 7u;
       }
     }
-    if (same && !first && min_cnt >= 1u && max_cnt <= (1u << 20) && isfinite(__longlong_as_double(q_first))) {
-      back.q = __longlong_as_double(q_first);
-      back.cnt0 = min_cnt;
-      return arg;
-    }
+  }
+  double q[NACT];
+  uint32_t cnt[NACT];
+#pragma unroll
+  for (int a = 0; a < NACT; ++a) {
+    const bool ex = (mask >> a) & 1u;
+    q[a] = ex ? r.Q[a] : 0.0;
+    cnt[a] = ex ? r.n[a] : 1u;
   }
   double lo = p.lb, hi = p.ub;
   if (p.use_bound_est) {  // calculate_bounds_based_on_stat :122-132

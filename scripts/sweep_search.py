@@ -33,7 +33,8 @@ def main():
         c = s.counters()
         steps = c["rollout_steps"] + c["expand_steps"]
         print(f"lpw={lpw} threads={threads} trees={trees} iters={iters} maxn={maxn} layout={layout} inner={inner} ms={best*1e3:.1f} "
-              f"env_steps/s={steps/best:.4g} it/s={c['iterations']/best:.4g}", flush=True)
+              f"env_steps/s={steps/best:.4g} it/s={c['iterations']/best:.4g} "
+              f"exact_ucb/it={s.exact_ucb_evaluations()/max(c['iterations'],1):.4f} levels/it={c['backup_levels']/max(c['iterations'],1):.3f}", flush=True)
         s.close()
     e.close()
 main()
