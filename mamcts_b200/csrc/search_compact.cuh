@@ -279,18 +279,28 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
         if (num_inner >= c.max_inner) { failed = true; atomicAdd(p.counters + 6, 1ull); break; }
         const uint32_t id = num_inner++;
         Inner* cn = inner + id;
-        cn->c.h.visit_count = 0;
-        cn->c.h.N[0] = 1; cn->c.h.N[1] = 1;      // update_from_heuristic left 0 + 1 visits
-        cn->c.h.nexp[0] = 0; cn->c.h.nexp[1] = 0;
-        cn->c.ja[0] = ja[0]; cn->c.ja[1] = ja[1];
+        // The WHOLE record is written, every sector completely (zeros where the reference's statistic
+        // has nothing yet: action values of unexpanded actions, padding): a sector that is only partly
+        // written has to be read from HBM first when it leaves the L2, and one that is never written
+        // would be read as is by the visit that follows. (A new action value is 0 = what is stored, so
+        // the backup of a first visit needs no store for it - no partial write of the q_o sectors.)
+        {
+          uint4 img[sizeof(Inner) / 16];
 #pragma unroll
-        for (int a = 0; a < NE; ++a) cn->c.n_e[a] = 0;
+          for (size_t i = 0; i < sizeof(Inner) / 16; ++i) img[i] = make_uint4(0u, 0u, 0u, 0u);
+          Counters c0;
+          __builtin_memcpy(&c0, img, sizeof(Counters));
+          c0.h.N[0] = 1; c0.h.N[1] = 1;          // update_from_heuristic left 0 + 1 visits
+          c0.ja[0] = ja[0]; c0.ja[1] = ja[1];
+          __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, c), &c0, sizeof(Counters));
+          const double vals[4] = {h[0], h[1], h[0], h[1]};   // V[2], G[2]
+          __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, v), vals, sizeof(vals));
+          __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, parent), &node, sizeof(uint32_t));
+          uint4* dst = reinterpret_cast<uint4*>(cn);
+          constexpr size_t used = (offsetof(Inner, q_o) + sizeof(double) * NA + 31) / 32 * 2;   // whole sectors
 #pragma unroll
-        for (int a = 0; a < NA; ++a) cn->c.n_o[a] = 0;
-        cn->v.V[0] = h[0]; cn->v.G[0] = h[0]; cn->v.V[1] = h[1]; cn->v.G[1] = h[1];
-        cn->parent = node;
-#pragma unroll
-        for (int k = 0; k < NCHILD; ++k) cn->child[k] = 0;
+          for (size_t i = 0; i < used; ++i) dst[i] = img[i];
+        }
         nd->child[slot] = inner_entry<CIDX>(id);
         node = id;
       }
@@ -370,9 +380,9 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       // an action value that did not change (always the case for CrossingState's reward-free other
       // agents) is not rewritten: its sector stays clean and is never written back to HBM
       // (bit comparison: +0.0 and -0.0 are different values to keep; a newly expanded action's slot
-      // holds no value yet)
-      if (__double_as_longlong(e.q) != __double_as_longlong(be.q) || e.cnt == 1) pn->q_e[ae] = e.q;
-      if (__double_as_longlong(o.q) != __double_as_longlong(bo.q) || o.cnt == 1) pn->q_o[ao] = o.q;
+      // already holds its initial 0.0 - records are created zero-filled)
+      if (__double_as_longlong(e.q) != __double_as_longlong(be.q)) pn->q_e[ae] = e.q;
+      if (__double_as_longlong(o.q) != __double_as_longlong(bo.q)) pn->q_o[ao] = o.q;
       G[0] = e.G;
       G[1] = o.G;
     }
