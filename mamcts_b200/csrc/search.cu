@@ -214,8 +214,8 @@ struct SearchC final : public mamcts_search {
                  uint32_t* nexp, double* q, uint32_t* n) const override {
     const Inner* nd = static_cast<const Inner*>(node);
     const uint32_t k = agent ? 1 : 0;
-    *value = nd->v.V[k];
-    *latest = nd->v.G[k];
+    *value = k ? nd->vg_o[0] : nd->vg_e[0];
+    *latest = k ? nd->vg_o[1] : nd->vg_e[1];
     *visits = nd->c.h.N[k];
     *nexp = nd->c.h.nexp[k];
     if (agent == 0) { for (int a = 0; a < NE; ++a) { q[a] = nd->q_e[a]; n[a] = nd->c.n_e[a]; } }
