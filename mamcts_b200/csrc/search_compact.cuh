@@ -96,6 +96,23 @@ struct CompactParams {
   const int32_t* root_x;  // the decision state
 };
 
+// One 32-byte sector per lane in one instruction (LDG.256 / STG.256, sm_100): a record visit is a handful
+// of whole-sector accesses, and every load instruction of 32 different records costs 32 L1 wavefronts
+// whatever its width.
+struct alignas(32) Sector { uint32_t w[8]; };
+__device__ __forceinline__ Sector ld_sector(const void* ptr) {
+  Sector s;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]), "=r"(s.w[4]), "=r"(s.w[5]),
+                 "=r"(s.w[6]), "=r"(s.w[7]) : "l"(ptr));
+  return s;
+}
+__device__ __forceinline__ void st_sector(void* ptr, const Sector& s) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(ptr), "r"(s.w[0]), "r"(s.w[1]), "r"(s.w[2]), "r"(s.w[3]), "r"(s.w[4]), "r"(s.w[5]),
+                  "r"(s.w[6]), "r"(s.w[7]) : "memory");
+}
+
 template <class CIDX>
 __device__ __forceinline__ CIDX leaf_entry(uint32_t leaf) { return (CIDX)((leaf + 1u) << 1); }
 template <class CIDX>
@@ -141,7 +158,6 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   using Head = typename Inner::Head;
   using HeadWord = typename std::conditional<sizeof(Head) == 8, uint2, uint4>::type;
   static_assert(sizeof(Head) == sizeof(HeadWord), "the head is written with one store");
-  constexpr int kCntVec = sizeof(Counters) / 16;
   using CountPair = typename std::conditional<sizeof(CNT) == 2, uint32_t, uint2>::type;
   uint32_t path_node[kPathMaxCompact];   // inner index | ego action << 24 | other action << 28
   double path_r0[kPathMaxCompact], path_q0[kPathMaxCompact], path_v0[kPathMaxCompact];
@@ -182,15 +198,17 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       // One round trip, and as few load instructions as possible: each lane reads its own record, so
       // every global load costs 32 L1 wavefronts whatever its width - the record is pulled with ten
       // 16-byte loads (the L1/LSU pipe, not DRAM, was the limiter with scalar loads; profiles/).
-      const uint4* raw = reinterpret_cast<const uint4*>(nd);
-      uint4 craw[kCntVec];
+      // the counters, the ego's V / G and its action values: the first kPrefix sectors of the record
+      constexpr int kPrefix = (int)((offsetof(Inner, q_e) + sizeof(double) * NE + 31) / 32);
+      Sector pre[kPrefix];
 #pragma unroll
-      for (int i = 0; i < kCntVec; ++i) craw[i] = raw[i];
-      const double2 vge = *reinterpret_cast<const double2*>(&nd->vg_e[0]);   // V, G of the ego
+      for (int i = 0; i < kPrefix; ++i) pre[i] = ld_sector(reinterpret_cast<const char*>(nd) + 32 * i);
+      double2 vge;                                                            // V, G of the ego
+      __builtin_memcpy(&vge, reinterpret_cast<const char*>(pre) + offsetof(Inner, vg_e), sizeof(vge));
       const double2 vgo = other_values_zero ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(&nd->vg_o[0]);
       double2 qe[NE / 2 + (NE & 1)], qo[NA / 2 + (NA & 1)];
-#pragma unroll
-      for (int i = 0; i < NE / 2 + (NE & 1); ++i) qe[i] = reinterpret_cast<const double2*>(&nd->q_e[0])[i];
+      __builtin_memcpy(qe, reinterpret_cast<const char*>(pre) + offsetof(Inner, q_e), sizeof(double) * NE);
+      if (NE & 1) qe[NE / 2].y = 0.0;
 #pragma unroll
       for (int i = 0; i < NA / 2 + (NA & 1); ++i)
         qo[i] = other_values_zero ? make_double2(0.0, 0.0) : reinterpret_cast<const double2*>(&nd->q_o[0])[i];
@@ -199,7 +217,7 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       // it up front changes nothing: profiles/r01_search_sweeps.txt r57)
       prefetch_l1(reinterpret_cast<const char*>(nd) + ((offsetof(Inner, child) + 31) & ~size_t(31)));
       Counters cc;
-      __builtin_memcpy(&cc, craw, sizeof(cc));
+      __builtin_memcpy(&cc, pre, sizeof(cc));
       if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) {  // :183-187
         // no rollout: the node's own latest return is backed up (mcts.h:309-329)
         nd->c.h.visit_count = (CNT)(cc.h.visit_count + 1);               // :180
@@ -299,10 +317,13 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
           __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, vg_e), ve, sizeof(ve));
           __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, vg_o), vo, sizeof(vo));
           __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, parent), &node, sizeof(uint32_t));
-          uint4* dst = reinterpret_cast<uint4*>(cn);
-          constexpr size_t used = (offsetof(Inner, q_o) + sizeof(double) * NA + 31) / 32 * 2;   // whole sectors
+          constexpr size_t used = (offsetof(Inner, q_o) + sizeof(double) * NA + 31) / 32;   // whole sectors
 #pragma unroll
-          for (size_t i = 0; i < used; ++i) dst[i] = img[i];
+          for (size_t i = 0; i < used; ++i) {
+            Sector sec;
+            __builtin_memcpy(&sec, &img[2 * i], sizeof(sec));
+            st_sector(reinterpret_cast<char*>(cn) + 32 * i, sec);
+          }
         }
         nd->child[slot] = inner_entry<CIDX>(id);
         node = id;

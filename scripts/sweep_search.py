@@ -13,6 +13,12 @@ def main():
     pts = [tuple(int(x) for x in p.split(",")) for p in sys.argv[1].split(";") if p]
     others = int(os.environ.get("SWEEP_OTHERS", "1"))
     e = Engine(0)
+    if os.environ.get("SWEEP_L2_GRAN"):   # cudaLimitMaxL2FetchGranularity = 5
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["SWEEP_L2_GRAN"])))
+        v = ctypes.c_size_t(0); rt.cudaDeviceGetLimit(ctypes.byref(v), 5)
+        print("L2 fetch granularity set rc", rc, "now", v.value, flush=True)
     for pt in pts:
         lpw, threads, trees, iters = pt[:4]
         maxn = pt[4] if len(pt) > 4 else 0
