@@ -421,12 +421,17 @@ def run_native(args):
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "traffic": _measured_traffic(args.layout, T, ITERATIONS),
                     "algorithmic_bytes_per_iteration": bytes_per_it, "mean_leaf_depth": mean_depth,
+                    # the same with SURVEY.md 8(d)'s two terms only (rollout + backup, no selection reads)
+                    "frac_rollout_and_backup_bytes_only":
+                        ((16 * A + 8 + 8) + 80 * A * mean_depth) * it_local / (search_kernel_ms * 1e-3) / 1e9 / peak,
                     "kernel_ms": search_kernel_ms,
                     "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
                                     "profiles/r01_traffic.json; null when this configuration was not captured)",
-                    "note": "one lane per tree, one randomly placed 256-B record per level: bound by HBM random-record "
-                            "access (about 2.8 TB/s of DRAM traffic at this size, profiles/r01_randrec_microbench.txt), "
-                            "not by streaming bandwidth; see DESIGN.md section 7"}
+                    "note": "one lane per tree, one randomly placed 256-B record per level; measured DRAM traffic "
+                            "(`traffic`) is below the algorithmic bytes because the roots stay in the L2 and a "
+                            "reward-free agent's values never move; random-record access tops out near 2.8 TB/s of "
+                            "DRAM traffic (profiles/r01_randrec_microbench.txt), not at the streaming peak; "
+                            "see DESIGN.md section 7"}
         # ---- cpu baseline: the reference's own search on the host cores, bounded sample -----------
         threads = os.cpu_count() or 1
         cb = cpu_reference_search(threads, max(1, args.cpu_repeats))
