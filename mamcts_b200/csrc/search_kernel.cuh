@@ -100,6 +100,19 @@ struct BackRegs {
   uint32_t cnt0, nv0;
 };
 
+// The statistic of an agent whose values are known to be +0.0 (a reward-free agent, see
+// Env::kOtherRewardZero): only the counts are read.
+template <int NACT>
+__device__ __forceinline__ StatRegs<NACT> load_stat_counts(const StatRec<NACT>* s) {
+  StatRegs<NACT> r;
+  r.N = s->N;
+  r.nexp = s->nexp;
+  r.V = 0.0;
+#pragma unroll
+  for (int a = 0; a < NACT; ++a) { r.Q[a] = 0.0; r.n[a] = s->n[a]; }
+  return r;
+}
+
 template <int NACT>
 __device__ __forceinline__ StatRegs<NACT> load_stat(const StatRec<NACT>* s) {
   StatRegs<NACT> r;
@@ -285,9 +298,10 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
 template <int NACT>
 __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRegs<NACT>& r,
                                                   const SearchParams& p, int cls, uint32_t nact,
-                                                  unsigned long long& exact_evals, BackRegs& back) {
+                                                  unsigned long long& exact_evals, BackRegs& back,
+                                                  bool values_known_equal = false) {
   bool widened;
-  const uint32_t a = select_action<NACT>(r, p, cls, nact, exact_evals, back, widened);
+  const uint32_t a = select_action<NACT>(r, p, cls, nact, exact_evals, back, widened, values_known_equal);
   if (widened) {
     s->nexp = r.nexp + 1;
     s->Q[a] = 0.0;  // ucb_statistics_[a] = UcbPair()
@@ -341,6 +355,14 @@ __device__ __forceinline__ double back_apply(StatRec<NACT>* s, uint32_t act, con
   if (__double_as_longlong(o.v) != __double_as_longlong(b.v)) s->V = o.v;
   s->G = o.G;
   return o.G;
+}
+
+// back_apply for an agent whose values are known to stay +0.0: only the counts move (V, G and Q hold
+// +0.0 since the node was created or the action expanded, exactly what the recurrence would rewrite).
+template <int NACT>
+__device__ __forceinline__ void back_apply_counts(StatRec<NACT>* s, uint32_t act, const BackRegs& b) {
+  s->n[act] = b.cnt0 + 1;
+  s->N = b.nv0 + 1;
 }
 
 template <int A>
@@ -498,6 +520,11 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
   uint8_t const_act[A];
 #pragma unroll
   for (int a = 0; a < A; ++a) const_act[a] = p.tab->order[a == 0 ? 0 : 1][0];  // F1: first draw
+  // Reward-free other agents (CrossingState: rewards[1..] stay 0, crossing_state.h:145) with a discount
+  // >= 0: every return, V, G and Q of theirs is +0.0 for the whole search (m >= 0, m * 0.0 = +0.0), so
+  // their values are neither loaded nor recomputed nor rewritten, and their selection is the integer
+  // first-minimum of the counts (select_action).
+  const bool other_values_zero = Env::kOtherRewardZero && p.gamma >= 0.0;
 
   // the path of the current iteration (collect(), node_statistic.h:115-121): per edge the parent
   // node, the joint action taken, the rewards collected on it and, per agent, the four statistic
@@ -522,7 +549,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
       const uint32_t flags = nd->flags;
       const StatRegs<NE> ego = load_stat<NE>(&nd->ego);
       StatRegs<NA> oth0;
-      if (A > 1) oth0 = load_stat<NA>(&nd->oth[0]);
+      if (A > 1) oth0 = other_values_zero ? load_stat_counts<NA>(&nd->oth[0]) : load_stat<NA>(&nd->oth[0]);
       if (A > 2) {
 #pragma unroll 1
         for (int j = 1; j < A - 1; ++j) { prefetch_l1(&nd->oth[j]); prefetch_l1(&nd->oth[j].Q[NA - 1]); }
@@ -538,14 +565,14 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
       uint8_t ja[A];
       BackRegs back[A];
       ja[0] = (uint8_t)choose_action<NE>(&nd->ego, ego, p, 0, p.n_ego, exact_evals, back[0]);  // :190-195
-      if (A > 1) ja[1] = (uint8_t)choose_action<NA>(&nd->oth[0], oth0, p, 1, p.n_oth, exact_evals, back[1]);
+      if (A > 1) ja[1] = (uint8_t)choose_action<NA>(&nd->oth[0], oth0, p, 1, p.n_oth, exact_evals, back[1], other_values_zero);
       if (A > 2) {
         // further other agents: one copy of the selection code, statistics come from L1 (prefetched)
 #pragma unroll 1
         for (int j = 1; j < A - 1; ++j) {
-          const StatRegs<NA> o = load_stat<NA>(&nd->oth[j]);
+          const StatRegs<NA> o = other_values_zero ? load_stat_counts<NA>(&nd->oth[j]) : load_stat<NA>(&nd->oth[j]);
           BackRegs b;
-          ja[j + 1] = (uint8_t)choose_action<NA>(&nd->oth[j], o, p, 1, p.n_oth, exact_evals, b);
+          ja[j + 1] = (uint8_t)choose_action<NA>(&nd->oth[j], o, p, 1, p.n_oth, exact_evals, b, other_values_zero);
           back[j + 1] = b;
         }
       }
@@ -650,9 +677,14 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
       Node* pn = nodes + path_node[level];
       const double r0 = path_r0[level], r1 = path_r1[level];
       G[0] = back_apply<NE>(&pn->ego, path_ja[level][0], path_back[level][0], r0, p.gamma, G[0]);
+      if (other_values_zero) {
 #pragma unroll
-      for (int j = 0; j < A - 1; ++j)
-        G[j + 1] = back_apply<NA>(&pn->oth[j], path_ja[level][j + 1], path_back[level][j + 1], r1, p.gamma, G[j + 1]);
+        for (int j = 0; j < A - 1; ++j) back_apply_counts<NA>(&pn->oth[j], path_ja[level][j + 1], path_back[level][j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < A - 1; ++j)
+          G[j + 1] = back_apply<NA>(&pn->oth[j], path_ja[level][j + 1], path_back[level][j + 1], r1, p.gamma, G[j + 1]);
+      }
     }
   }
   p.tree_nodes[tree] = num_nodes;
