@@ -192,6 +192,15 @@ struct SearchC final : public mamcts_search {
     const uint32_t T = cfg.num_trees;
     const uint32_t trees_per_block = (uint32_t)(block_threads / 32) * q.lanes_per_warp;
     const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
+    if (std::getenv("MAMCTS_SEARCH_DEBUG")) {   // resident blocks per SM as the runtime computes them
+      int nb = 0;
+      cudaFuncAttributes fa;
+      auto kern = search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX>;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block_threads, 0);
+      cudaFuncGetAttributes(&fa, kern);
+      std::fprintf(stderr, "search_compact_kernel: %d blocks/SM of %d threads, %d regs, %zu B smem, %zu B local, grid %d, lanes/warp %u\n",
+                   nb, block_threads, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, grid, q.lanes_per_warp);
+    }
     if (cfg.action_source == MAMCTS_SRC_PHILOX)
       search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX><<<grid, block_threads, 0, e->stream>>>(q, c);
     else

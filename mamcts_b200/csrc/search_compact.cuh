@@ -33,7 +33,9 @@
 namespace mamcts {
 
 #ifndef MAMCTS_COMPACT_MIN_BLOCKS
-#define MAMCTS_COMPACT_MIN_BLOCKS 8   // 128 registers; 10 or 12 (96 / 80 registers) spill and are slower
+#define MAMCTS_COMPACT_MIN_BLOCKS 8   // 124 registers used. Registers are granted in steps that make 96 the
+                                      // next useful budget (112 or 104 still give 8 blocks per SM, r82); 96 and
+                                      // 80 registers (10 / 12 blocks) spill and are slower (r49, r57)
 #endif
 #ifndef MAMCTS_PATH_SHARED_LEVELS
 #define MAMCTS_PATH_SHARED_LEVELS 5
