@@ -227,18 +227,20 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
     if (mn == mx) { lo = 0.0; hi = (mx != 0.0) ? mx : 1.0; }
     else { lo = mn; hi = mx; }
   }
-  const double log2N = __dmul_rn(2.0, __ldg(p.log_table + N));  // 2 * log(total_node_visits_)
   const double range = __dsub_rn(hi, lo);
 
   // FP32 screen. The FP64 UCB values cost two divisions and a square root per action; the arg-max
   // almost never needs that precision. Scores are first evaluated in FP32 with one correctly
   // rounded reciprocal and square root per statistic and one MUFU.RSQ (<= 2 ulp) per action:
   //   norm  = float(q - lo) * rcp(float(range))                     |error| <= 4 u          (u = 2^-24)
-  //   bonus = (float(2c) * sqrt(float(2 ln N))) * rsqrt(float(n))   |error| <= 8.5 u * bonus
-  //   score = fma(...)                                              |error| <= 9.5 u * (score + 1)
-  // so two scores compare wrongly only if they are closer than 1.2e-6 * (score + 1). When the first
+  //   bonus = (float(2c) * sqrt(2 * logf(N))) * rsqrt(float(n))     |error| <= 11 u * bonus
+  //           (__logf: <= 3 ulp = 6 u for N >= 2, halved by the square root; the host's exact
+  //            log table is only read by the exact evaluation - a table lookup here would be one
+  //            more dependent memory access on the critical path of every level)
+  //   score = fma(...)                                              |error| <= 12 u * (score + 1)
+  // so two scores compare wrongly only if they are closer than 1.45e-6 * (score + 1). When the first
   // maximum beats every action with different inputs by more than `delta` = 6e-6 * (score + 1)
-  // (5x that bound), the exact arg-max is provably the same and is returned. Actions with
+  // (4x that bound), the exact arg-max is provably the same and is returned. Actions with
   // bit-identical (Q, n) have identical exact scores, so the strict-> first-max rule picks the same
   // one either way. Anything else (including non-finite intermediates) falls through to the exact
   // FP64 evaluation, so the selected action is ALWAYS the reference's.
@@ -251,7 +253,7 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   {
     const float rangef = (float)range;
     const float inv_range = __frcp_rn(rangef);
-    const float csl = (float)p.two_c * __fsqrt_rn((float)log2N);
+    const float csl = (float)p.two_c * __fsqrt_rn(2.0f * __logf((float)N));
     float sc[NACT];
     float best_sc = -1.0f;
     ok = isfinite(rangef) && rangef != 0.0f;
@@ -288,6 +290,7 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   if (ok) return (uint32_t)bi;
 
   exact_evals += 1;
+  const double log2N = __dmul_rn(2.0, __ldg(p.log_table + N));  // 2 * log(total_node_visits_), host libm
   const uint32_t best = exact_ucb_argmax<NACT>(r, candidates, lo, range, log2N, p.two_c);
 #pragma unroll
   for (int a = 0; a < NACT; ++a) if ((uint32_t)a == best) { back.q = r.Q[a]; back.cnt0 = r.n[a]; }
