@@ -128,6 +128,8 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
   constexpr int A = Env::A;
   using Leaf = LeafRec<A>;
+  __shared__ SearchTables tab;
+  stage_tables(tab, p.tab);   // before any lane leaves: contains a block barrier
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t tree = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * p.lanes_per_warp + lane;
   // the lanes that own a tree; they re-converge explicitly once per iteration (see below)
@@ -142,7 +144,7 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   const uint32_t nodes_before = num_nodes;
   uint8_t const_act[A];
 #pragma unroll
-  for (int a = 0; a < A; ++a) const_act[a] = p.tab->order[a == 0 ? 0 : 1][0];  // F1: first draw
+  for (int a = 0; a < A; ++a) const_act[a] = tab.order[a == 0 ? 0 : 1][0];  // F1: first draw
   typename Env::State root;
 #pragma unroll
   for (int i = 0; i < A; ++i) { root.x[i] = (i < Env::kStateInts) ? __ldg(c.root_x + i) : 0; root.last[i] = 0; }
@@ -239,8 +241,8 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       uint8_t ja[A];
       BackRegs back[A];
       bool w0, w1;
-      ja[0] = (uint8_t)select_action<NE>(ego, p, 0, p.n_ego, exact_evals, back[0], w0);  // :190-195
-      ja[1] = (uint8_t)select_action<NA>(oth, p, 1, p.n_oth, exact_evals, back[1], w1, other_values_zero);
+      ja[0] = (uint8_t)select_action<NE>(ego, p, tab, 0, p.n_ego, exact_evals, back[0], w0);  // :190-195
+      ja[1] = (uint8_t)select_action<NA>(oth, p, tab, 1, p.n_oth, exact_evals, back[1], w1, other_values_zero);
       // Nothing is stored during the descent: visit_count + 1 (:180) and a newly expanded action
       // (ucb_statistics_[a] = UcbPair()) go into the image of the head, which this iteration's backup
       // of the level writes back together with N, followed by the two n[a].

@@ -59,6 +59,17 @@ struct SearchTables {
   uint32_t pw_min_visits[2][MAMCTS_MAX_ACTIONS];// smallest N with k <= pw_k * pow(N, pw_alpha)
 };
 
+// The selection tables are read at every level with an index that comes out of the node record:
+// staged in shared memory once per block, the lookup is a fixed ~25-cycle access instead of a global
+// load that competes with the tree records for the L1.
+__device__ __forceinline__ void stage_tables(SearchTables& dst, const SearchTables* src) {
+  static_assert(sizeof(SearchTables) % 4 == 0, "copied by words");
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+  for (uint32_t i = threadIdx.x; i < sizeof(SearchTables) / 4; i += blockDim.x) d[i] = s[i];
+  __syncthreads();
+}
+
 struct SearchParams {
   void* nodes;
   uint32_t* hash;
@@ -148,7 +159,8 @@ __device__ __noinline__ uint32_t exact_ucb_argmax(StatRegs<NACT> r, uint32_t mas
 // expanded (ucb_statistics_[a] = UcbPair(), the caller records it in its own record layout).
 // Also returns (in `back`) the values the backup of this level will need for the chosen action.
 template <int NACT>
-__device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const SearchParams& p, int cls,
+__device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const SearchParams& p,
+                                                  const SearchTables& tab, int cls,
                                                   uint32_t nact, unsigned long long& exact_evals,
                                                   BackRegs& back, bool& widened,
                                                   bool values_known_equal = false) {
@@ -157,13 +169,13 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   back.nv0 = N;
   back.v = r.V;
   widened = false;
-  if (nexp < nact && N >= p.tab->pw_min_visits[cls][nexp]) {  // require_progressive_widening_total
+  if (nexp < nact && N >= tab.pw_min_visits[cls][nexp]) {  // require_progressive_widening_total
     widened = true;
     back.cnt0 = 0;
     back.q = 0.0;
-    return p.tab->order[cls][nexp];                           // :64-68 (deterministic order, F2)
+    return tab.order[cls][nexp];                              // :64-68 (deterministic order, F2)
   }
-  const uint32_t mask = p.tab->exp_mask[cls][nexp];
+  const uint32_t mask = tab.exp_mask[cls][nexp];
   // Equal action values (always the case for an agent that never receives a reward, e.g. the other
   // agents of CrossingState): with bound estimation the normalised value is the same for every action
   // (0 when the common value is 0, else exactly q / q = 1), so the UCB score is
@@ -300,11 +312,11 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
 // select_action on a classic StatRec: records a newly expanded action in place.
 template <int NACT>
 __device__ __forceinline__ uint32_t choose_action(StatRec<NACT>* s, const StatRegs<NACT>& r,
-                                                  const SearchParams& p, int cls, uint32_t nact,
+                                                  const SearchParams& p, const SearchTables& tab, int cls, uint32_t nact,
                                                   unsigned long long& exact_evals, BackRegs& back,
                                                   bool values_known_equal = false) {
   bool widened;
-  const uint32_t a = select_action<NACT>(r, p, cls, nact, exact_evals, back, widened, values_known_equal);
+  const uint32_t a = select_action<NACT>(r, p, tab, cls, nact, exact_evals, back, widened, values_known_equal);
   if (widened) {
     s->nexp = r.nexp + 1;
     s->Q[a] = 0.0;  // ucb_statistics_[a] = UcbPair()
@@ -511,6 +523,8 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
   using Node = NodeRec<Env, NE, NA, NCHILD, CIDX>;
   constexpr int A = Env::A;
   constexpr bool kDirect = NCHILD > 0;
+  __shared__ SearchTables tab;
+  stage_tables(tab, p.tab);   // before any lane leaves: contains a block barrier
   const uint32_t lane = threadIdx.x & 31u;
   if (lane >= p.lanes_per_warp) return;
   const uint32_t tree = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * p.lanes_per_warp + lane;
@@ -522,7 +536,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
   const uint32_t nodes_before = num_nodes;
   uint8_t const_act[A];
 #pragma unroll
-  for (int a = 0; a < A; ++a) const_act[a] = p.tab->order[a == 0 ? 0 : 1][0];  // F1: first draw
+  for (int a = 0; a < A; ++a) const_act[a] = tab.order[a == 0 ? 0 : 1][0];  // F1: first draw
   // Reward-free other agents (CrossingState: rewards[1..] stay 0, crossing_state.h:145) with a discount
   // >= 0: every return, V, G and Q of theirs is +0.0 for the whole search (m >= 0, m * 0.0 = +0.0), so
   // their values are neither loaded nor recomputed nor rewritten, and their selection is the integer
@@ -567,15 +581,15 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
       if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) break;  // :183-187
       uint8_t ja[A];
       BackRegs back[A];
-      ja[0] = (uint8_t)choose_action<NE>(&nd->ego, ego, p, 0, p.n_ego, exact_evals, back[0]);  // :190-195
-      if (A > 1) ja[1] = (uint8_t)choose_action<NA>(&nd->oth[0], oth0, p, 1, p.n_oth, exact_evals, back[1], other_values_zero);
+      ja[0] = (uint8_t)choose_action<NE>(&nd->ego, ego, p, tab, 0, p.n_ego, exact_evals, back[0]);  // :190-195
+      if (A > 1) ja[1] = (uint8_t)choose_action<NA>(&nd->oth[0], oth0, p, tab, 1, p.n_oth, exact_evals, back[1], other_values_zero);
       if (A > 2) {
         // further other agents: one copy of the selection code, statistics come from L1 (prefetched)
 #pragma unroll 1
         for (int j = 1; j < A - 1; ++j) {
           const StatRegs<NA> o = other_values_zero ? load_stat_counts<NA>(&nd->oth[j]) : load_stat<NA>(&nd->oth[j]);
           BackRegs b;
-          ja[j + 1] = (uint8_t)choose_action<NA>(&nd->oth[j], o, p, 1, p.n_oth, exact_evals, b, other_values_zero);
+          ja[j + 1] = (uint8_t)choose_action<NA>(&nd->oth[j], o, p, tab, 1, p.n_oth, exact_evals, b, other_values_zero);
           back[j + 1] = b;
         }
       }
