@@ -416,3 +416,47 @@ def test_root_policy_statistically_matches_cpu_twin(engine):
     assert tv <= 0.02, (tv, gpu_freq, cpu_freq)
     assert int(np.argmax(cpu_q)) == m["best"]
     s.close()
+
+
+@pytest.mark.parametrize("lpw", [2, 8, 32])
+@pytest.mark.parametrize("layout", [LAYOUT_CLASSIC, LAYOUT_COMPACT])
+def test_trees_per_warp_do_not_change_results(engine, lpw, layout, monkeypatch):
+    """mamcts_search_create packs 1..32 trees into a warp depending on the tree count (few trees: one per
+    warp); the small tests above all run one tree per warp, the bench 32. Forced here through the
+    profiling knob: every packing must build the same trees."""
+    monkeypatch.setenv("MAMCTS_SEARCH_LPW", str(lpw))
+    iters, T = 500, 100
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    s = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=SRC_PHILOX, philox_seed=77, layout=layout)
+    s.run(iters)
+    env = O.make_env(cp=cp)
+    for tree in (0, 1, lpw - 1, lpw % T, 63, 99):
+        t = O.OracleTree(env, mp, [5, 5], action_source=SRC_PHILOX, seed=77, tree_id=tree)
+        t.run(iters)
+        assert np.array_equal(s.dump_tree(tree, t.num_nodes), t.dump(7)), f"lpw {lpw}: tree {tree} differs"
+        t.close()
+    assert s.counters()["iterations"] == T * iters
+    s.close()
+
+
+def test_full_wave_sampled_trees_equal_oracle(engine):
+    """As many trees as the bench runs per wave class (automatic packing: 32 trees per warp): sampled
+    trees against the oracle, and the sum of the root visit counts against iterations x trees."""
+    iters, T = 150, 40000
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    s = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=SRC_PHILOX, philox_seed=9, layout=LAYOUT_COMPACT)
+    s.run(iters)
+    env = O.make_env(cp=cp)
+    for tree in (0, 31, 32, 20011, T - 1):
+        t = O.OracleTree(env, mp, [5, 5], action_source=SRC_PHILOX, seed=9, tree_id=tree)
+        t.run(iters)
+        assert np.array_equal(s.dump_tree(tree, t.num_nodes), t.dump(7)), f"tree {tree} differs"
+        t.close()
+    m = s.merge_roots()
+    assert int(m["n"].sum()) == T * iters   # every iteration of every tree backed up through its root
+    assert s.counters()["iterations"] == T * iters
+    s.close()
