@@ -126,6 +126,7 @@ struct CrossingEnv {
   // caller that only needs the rewards of an episode can look them up afterwards (lane_rollout).
   static constexpr bool kOutcomeRewards = true;
   __device__ __forceinline__ static double outcome_reward(const EnvParams& p, uint32_t f) { return p.r_tab[f]; }
+  __device__ __forceinline__ static double outcome_cost(const EnvParams& p, uint32_t f) { return p.c_tab[f]; }
   __device__ __forceinline__ static uint32_t step_outcome(const EnvParams& p, State& s, const int32_t (&act)[A]) {
     const int32_t old_x = s.x[0];
     const int32_t v_ego = act[0] + p.min_v_ego;            // :306-309

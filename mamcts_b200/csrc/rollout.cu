@@ -94,6 +94,16 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
   // additions are skipped; other agents' returns are ASSIGNED (:75), so only the last step matters.
   double ego = 0.0, cost = 0.0, r_other_last = 0.0;
   uint32_t it = 0, depth = 0, cap = 0, leaf = 0, s_lo = 0, s_hi = 0;
+  // Environments whose reward and cost are functions of the step's outcome code, which is nonzero exactly
+  // on the step that ends the episode (CrossingState<int>): when the per-step reward and cost are zero
+  // (the default), the loop carries neither; the one nonzero term of each sum is looked up from the last
+  // outcome afterwards (0.0 + x = x, so the sums are the reference's bit for bit).
+  uint32_t last_outcome = 0;
+  bool lazy = false;
+  if constexpr (Env::kOutcomeRewards) {
+    lazy = __double_as_longlong(Env::outcome_reward(p.env, 0u)) == 0ll &&
+           __double_as_longlong(Env::outcome_cost(p.env, 0u)) == 0ll && !(PARITY && p.trace);
+  }
   bool has = false, fin = true;
   unsigned long long lane_steps = 0;
   int32_t gap_lo[kHyp ? A : 1], gap_span[kHyp ? A : 1];   // [a]: other agent at position a (a >= 1)
@@ -111,6 +121,8 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
     depth = p.depth ? __ldg(p.depth + leaf) : 0u;
     cap = p.rh_cap;
     if (KIND == MAMCTS_SRC_REPLAY) cap = min(cap, __ldg(p.replay_steps + leaf));
+    // it >= cap or depth >= max_depth (random_heuristic.h:45-47, :51-54) as one limit on `it`
+    cap = min(cap, p.max_depth > depth ? p.max_depth - depth : 0u);
     if (kPhilox) {
       s_hi = p.stream_hi ? __ldg(p.stream_hi + leaf) : p.stream_hi_base;
       s_lo = p.stream_lo ? __ldg(p.stream_lo + leaf) + (rid - leaf * p.K) : p.stream_lo_base + rid;
@@ -123,10 +135,19 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
       }
     }
     ego = 0.0; cost = 0.0; r_other_last = 0.0; it = 0;   // random_heuristic.h:36-49
-    fin = Env::terminal(p.env, st) | (it >= cap) | (depth >= p.max_depth);  // :51-54
+    last_outcome = 0;
+    fin = Env::terminal(p.env, st) | (it >= cap);        // :51-54
   };
 
   auto finalize = [&]() {
+    if constexpr (Env::kOutcomeRewards) {
+      if (lazy && it) {
+        const double r_last = Env::outcome_reward(p.env, last_outcome);
+        const double c_last = Env::outcome_cost(p.env, last_outcome);
+        if (r_last != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it - 1), r_last));
+        if (c_last != 0.0) cost = __dadd_rn(cost, c_last);
+      }
+    }
     // random_heuristic.h:95-101
     const double prob = __ldg(p.disc + p.disc_len + it);
     const double other = it ? __dmul_rn(__ldg(p.disc + it - 1), r_other_last) : 0.0;  // :73-77
@@ -222,15 +243,29 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
           for (int a = 1; a < A; ++a)
             act[a] = crossing_policy_action(p.env, st.x[a], st.last[a], st.x[0], st.last[0], act[a]);
         }
-        double r_ego, r_other, c;
-        Env::step(p.env, st, act, r_ego, r_other, c);
-        if (PARITY && p.trace && it < p.trace_stride) p.trace[(size_t)rid * p.trace_stride + it] = r_ego;
-        if (r_ego != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it), r_ego));  // :71-72
-        r_other_last = r_other;                                                        // :73-77
-        if (Env::kHasCost && c != 0.0) cost = __dadd_rn(cost, c);                      // :79-84
-        it += 1;                                   // :89
-        depth += 1;                                // :90
-        fin = Env::terminal(p.env, st) | (it >= cap) | (depth >= p.max_depth);
+        bool ended;
+        if constexpr (Env::kOutcomeRewards) {
+          const uint32_t f = Env::step_outcome(p.env, st, act);
+          last_outcome = f;
+          ended = f != 0u;
+          if (!lazy) {
+            const double r_ego = Env::outcome_reward(p.env, f), c = Env::outcome_cost(p.env, f);
+            if (PARITY && p.trace && it < p.trace_stride) p.trace[(size_t)rid * p.trace_stride + it] = r_ego;
+            if (r_ego != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it), r_ego));  // :71-72
+            if (c != 0.0) cost = __dadd_rn(cost, c);                                       // :79-84
+          }
+          r_other_last = 0.0;                      // rewards[1..] stay 0 (crossing_state.h:145)
+        } else {
+          double r_ego, r_other, c;
+          Env::step(p.env, st, act, r_ego, r_other, c);
+          if (PARITY && p.trace && it < p.trace_stride) p.trace[(size_t)rid * p.trace_stride + it] = r_ego;
+          if (r_ego != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it), r_ego));  // :71-72
+          r_other_last = r_other;                                                        // :73-77
+          if (Env::kHasCost && c != 0.0) cost = __dadd_rn(cost, c);                      // :79-84
+          ended = Env::terminal(p.env, st);
+        }
+        it += 1;                                   // :89 (depth advances with it, :90: folded into cap)
+        fin = ended | (it >= cap);
       }
     }
   }
