@@ -141,15 +141,22 @@ __device__ __forceinline__ StatRegs<NACT> load_stat(const StatRec<NACT>* s) {
 template <int NACT>
 __device__ __noinline__ uint32_t exact_ucb_argmax(StatRegs<NACT> r, uint32_t mask, double lo, double range,
                                                   double log2N, double two_c) {
-  uint32_t best = 0;
-  double max_value = DBL_MIN;  // std::numeric_limits<double>::min(), :225
-#pragma unroll 1
+  // the scores of all candidates first, as independent chains (two divisions and a square root each: the
+  // latency of this path is what the rest of the warp waits for), then the reference's loop over them
+  double v[NACT];
+#pragma unroll
   for (int a = 0; a < NACT; ++a) {
+    v[a] = 0.0;
     if ((mask >> a) & 1u) {
       const double norm = __ddiv_rn(__dsub_rn(r.Q[a], lo), range);
-      const double v = __dadd_rn(norm, __dmul_rn(two_c, __dsqrt_rn(__ddiv_rn(log2N, (double)r.n[a]))));
-      if (v > max_value) { max_value = v; best = a; }
+      v[a] = __dadd_rn(norm, __dmul_rn(two_c, __dsqrt_rn(__ddiv_rn(log2N, (double)r.n[a]))));
     }
+  }
+  uint32_t best = 0;
+  double max_value = DBL_MIN;  // std::numeric_limits<double>::min(), :225
+#pragma unroll
+  for (int a = 0; a < NACT; ++a) {
+    if (((mask >> a) & 1u) && v[a] > max_value) { max_value = v[a]; best = a; }
   }
   return best;
 }
