@@ -327,6 +327,24 @@ def run_native(args):
         return
     mp, cp = _params()
     T = args.trees
+    # the tree arenas must fit into what is free on this GPU (compact layout: inner + leaf records; classic:
+    # 288-byte nodes); fewer trees are named in `config`, never silently
+    free_b, _total_b = torch.cuda.mem_get_info(local_rank)
+    if args.layout == 1:
+        per_tree = (ITERATIONS + 1) * 288
+    else:
+        per_tree = (min(args.max_inner, ITERATIONS + 1) if args.max_inner else ITERATIONS + 1) * 256 + (ITERATIONS + 1) * 16
+    fit = int((free_b - (2 << 30)) // (per_tree + 64))
+    if fit < T:
+        wave = 148 * 64
+        T_fit = max(wave, (fit // wave) * wave) if fit >= wave else max(1, fit)
+        if world > 1:   # every rank runs the same number of trees
+            t = torch.tensor([T_fit], device=f"cuda:{local_rank}", dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            T_fit = int(t.item())
+        sys.stderr.write(f"bench.py: {T} trees need {T * per_tree / 2**30:.0f} GiB, {free_b / 2**30:.0f} GiB are free: "
+                         f"running {T_fit} trees per GPU\n")
+        T = T_fit
     shard = sharding.weak_shard(T, world, rank)   # fixed trees per GPU, global ids rank*T ...
     search = Search(engine, ENV_CROSSING_I32, mp, shard.num_trees, cp=cp, action_source=SRC_PHILOX,
                     philox_seed=1000, first_tree_id=shard.first_tree_id, layout=args.layout,
