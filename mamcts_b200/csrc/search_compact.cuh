@@ -42,8 +42,9 @@ namespace mamcts {
 #endif
 constexpr int kPathMaxCompact = 64;  // deepest leaf the compact layout can back up (error beyond)
 
-// Inner record, laid out by 32-byte sector so that a visit touches as few sectors as possible (the
-// kernel is bound by DRAM traffic of randomly placed records):
+// Inner record, laid out by 32-byte sector so that a visit touches as few sectors as possible (DRAM
+// sectors of randomly placed records and the latency of fetching them are what the kernel's time goes
+// into):
 // (C2 offsets, 16-bit counts and child entries)
 //   [  0, 32) counters  every integer a visit reads or writes: N per agent, visit_count, #expanded per
 //                       agent, n[a] of both agents, the joint action leading here - ONE sector with
@@ -200,8 +201,8 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
     while (!failed) {
       Inner* nd = inner + node;
       // One round trip, and as few load instructions as possible: each lane reads its own record, so
-      // every global load costs 32 L1 wavefronts whatever its width - the record is pulled with ten
-      // 16-byte loads (the L1/LSU pipe, not DRAM, was the limiter with scalar loads; profiles/).
+      // every global load costs 32 L1 wavefronts whatever its width (the L1/LSU pipe, not DRAM, was the
+      // limiter with scalar loads; profiles/) - the record's prefix is pulled with 256-bit loads.
       // the counters, the ego's V / G and its action values: the first kPrefix sectors of the record
       constexpr int kPrefix = (int)((offsetof(Inner, q_e) + sizeof(double) * NE + 31) / 32);
       Sector pre[kPrefix];
