@@ -182,9 +182,9 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   bool failed = false;
   // Environments whose other agents never receive a reward (CrossingState: rewards[1..] stay 0,
   // crossing_state.h:145): with a discount >= 0 every return of theirs is +0.0 (m >= 0, m * 0.0 = +0.0),
-  // hence every G = 0.0 + gamma * (+0.0), Q and V of theirs is +0.0 for the whole search - their action
-  // values need not be loaded (they are still written when an action is first expanded, so the record
-  // always holds what the reference's statistic holds).
+  // hence every G = 0.0 + gamma * (+0.0), Q and V of theirs is +0.0 for the whole search - their values
+  // are neither loaded nor recomputed nor rewritten: a record is created with them zero-filled, which
+  // is what the reference's statistic holds, and their selection is integer-only (select_action).
   const bool other_values_zero = Env::kOtherRewardZero && p.gamma >= 0.0;
 
 #pragma unroll 1
@@ -217,9 +217,9 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
 #pragma unroll
       for (int i = 0; i < NA / 2 + (NA & 1); ++i)
         qo[i] = other_values_zero ? make_double2(0.0, 0.0) : reinterpret_cast<const double2*>(&nd->q_o[0])[i];
-      // child table: only the part that shares a 64-byte burst with the action values is requested
-      // up front; the entry load below fetches the rest when the chosen slot lies there (requesting all of
-      // it up front changes nothing: profiles/r01_search_sweeps.txt r57)
+      // child table: its first entries came with the prefix, the sector behind the prefix is requested
+      // up front, and the entry load below fetches the last one when the chosen slot lies there
+      // (requesting all of it up front is neutral or costs DRAM sectors: r01_search_sweeps.txt r57, r86)
       prefetch_l1(reinterpret_cast<const char*>(nd) + ((offsetof(Inner, child) + 31) & ~size_t(31)));
       Counters cc;
       __builtin_memcpy(&cc, pre, sizeof(cc));
