@@ -374,7 +374,7 @@ typedef struct mamcts_search_config {
   int32_t action_source;       /* MAMCTS_SRC_REFERENCE_CONST or MAMCTS_SRC_PHILOX */
   uint32_t num_trees;          /* local trees on this engine */
   uint32_t first_tree_id;      /* global id of local tree 0 (root-parallel sharding, §8e) */
-  uint32_t rollouts_per_leaf;  /* K >= 1 (K > 1 only with PHILOX) */
+  uint32_t rollouts_per_leaf;  /* K = 1, 2, 4, 8 or 16 (K > 1 only with PHILOX): leaf value = mean of K rollouts */
   uint32_t max_nodes_per_tree; /* arena size; iterations stop expanding past it like
                                   MAX_NUMBER_OF_NODES (mcts/stage_node.h:184) */
   uint32_t layout;             /* MAMCTS_LAYOUT_*: how a tree is stored in HBM */

@@ -104,7 +104,9 @@ struct SearchT final : public mamcts_search {
     const uint32_t T = cfg.num_trees;
     const uint32_t trees_per_block = (uint32_t)(block_threads / 32) * q.lanes_per_warp;
     const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
-    if (cfg.action_source == MAMCTS_SRC_PHILOX)
+    if (cfg.action_source == MAMCTS_SRC_PHILOX && cfg.rollouts_per_leaf > 1)
+      search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_PHILOX, true><<<grid, block_threads, 0, e->stream>>>(q);
+    else if (cfg.action_source == MAMCTS_SRC_PHILOX)
       search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_PHILOX><<<grid, block_threads, 0, e->stream>>>(q);
     else
       search_kernel<Env, NE, NA, NCHILD, CIDX, MAMCTS_SRC_REFERENCE_CONST><<<grid, block_threads, 0, e->stream>>>(q);
@@ -201,7 +203,9 @@ struct SearchC final : public mamcts_search {
       std::fprintf(stderr, "search_compact_kernel: %d blocks/SM of %d threads, %d regs, %zu B smem, %zu B local, grid %d, lanes/warp %u\n",
                    nb, block_threads, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, grid, q.lanes_per_warp);
     }
-    if (cfg.action_source == MAMCTS_SRC_PHILOX)
+    if (cfg.action_source == MAMCTS_SRC_PHILOX && cfg.rollouts_per_leaf > 1)
+      search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX, true><<<grid, block_threads, 0, e->stream>>>(q, c);
+    else if (cfg.action_source == MAMCTS_SRC_PHILOX)
       search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX><<<grid, block_threads, 0, e->stream>>>(q, c);
     else
       search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_REFERENCE_CONST><<<grid, block_threads, 0, e->stream>>>(q, c);
@@ -495,8 +499,14 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
     return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: action source must be REFERENCE_CONST or PHILOX");
   if (cfg->layout > MAMCTS_LAYOUT_COMPACT)
     return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: unknown layout");
-  if (cfg->rollouts_per_leaf != 1)
-    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: rollouts_per_leaf must be 1 in this build");
+  {
+    const uint32_t K = cfg->rollouts_per_leaf;
+    if (K == 0 || K > 16 || (K & (K - 1)) != 0)
+      return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: rollouts_per_leaf must be 1, 2, 4, 8 or 16");
+    if (K > 1 && cfg->action_source != MAMCTS_SRC_PHILOX)
+      return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: rollouts_per_leaf > 1 needs MAMCTS_SRC_PHILOX "
+                                         "(the reference's rollouts are all the same, SURVEY.md F1)");
+  }
   const mamcts_params& mp = cfg->mcts;
   if (!(mp.uct_pw_k >= 0.0) || !(mp.uct_pw_alpha >= 0.0))
     return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_create: progressive widening k, alpha must be >= 0");
@@ -610,6 +620,7 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   p.use_bound_est = mp.use_bound_estimation; p.max_depth = mp.max_search_depth;
   p.node_budget = mp.max_number_of_nodes; p.rh_cap = mp.rh_max_number_of_iterations;
   p.key0 = (uint32_t)cfg->philox_seed; p.key1 = (uint32_t)(cfg->philox_seed >> 32);
+  p.rollouts_per_leaf = cfg->rollouts_per_leaf;
   p.gamma = mp.discount_factor; p.two_c = 2 * mp.uct_exploration_constant;
   p.lb = mp.uct_lower_bound; p.ub = mp.uct_upper_bound;
   p.env = ep;

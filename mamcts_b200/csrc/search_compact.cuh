@@ -123,7 +123,7 @@ __device__ __forceinline__ CIDX inner_entry(uint32_t inner) { return (CIDX)((inn
 
 // counters[6] = trees that ran out of inner records, counters[7] = trees with a path deeper than
 // kPathMaxCompact; either makes mamcts_search_run's caller see an error at the next read-back.
-template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT, int KIND>
+template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT, int KIND, bool MULTI = false>
 __global__ void __launch_bounds__(kSearchThreads, MAMCTS_COMPACT_MIN_BLOCKS)
 search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_constant__ CompactParams c) {
   using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
@@ -343,8 +343,8 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
     if (do_rollout) {
       double other = 0.0;
       uint32_t steps = 0;
-      const double ego_h = lane_rollout<Env, KIND>(p, st, depth, p.first_tree_id + tree, creation, const_act,
-                                                   other, steps);
+      const double ego_h = leaf_heuristic<Env, KIND, MULTI>(p, st, depth, p.first_tree_id + tree, creation, const_act,
+                                                     other, steps);
       rollout_steps += steps;
       // update_from_heuristic (uct_statistic.h:100-110): value_ = latest_return_ = h, visits 0 + 1
       leaves[new_leaf].h[0] = ego_h;

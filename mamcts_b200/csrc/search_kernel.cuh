@@ -85,6 +85,7 @@ struct SearchParams {
   uint32_t n_ego, n_oth;
   uint32_t use_bound_est, max_depth, node_budget, rh_cap;
   uint32_t key0, key1;
+  uint32_t rollouts_per_leaf;   // K >= 1 (power of two <= 16): the leaf value is the mean of K rollouts
   double gamma, two_c, lb, ub;
   EnvParams env;
 };
@@ -503,6 +504,40 @@ __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename E
   return __dmul_rn(ego, __ldg(p.disc + p.disc_len + it));
 }
 
+// The heuristic value of a new leaf (RandomHeuristic::calculate_heuristic_values, random_heuristic.h:106-134).
+// MULTI = false is the reference: one rollout. MULTI = true (K = rollouts_per_leaf > 1, a power of two <= 16,
+// PHILOX): the mean of K rollouts from the same state with stream_lo = creation index * K + k, summed in the
+// fixed pairwise order of DESIGN.md section 6 (what reduce_mean_kernel and the oracle's orc_reduce_mean
+// compute for K < 32), divided by K. A template parameter of the kernels, so that the K = 1 kernel is exactly
+// what it is without this (a run-time branch around the rollout cost it 2-6 %).
+template <class Env, int KIND, bool MULTI>
+__device__ __forceinline__ double leaf_heuristic(const SearchParams& p, const typename Env::State& st,
+                                                 uint32_t depth, uint32_t s_hi, uint32_t creation,
+                                                 const uint8_t* const_act, double& other, uint32_t& steps) {
+  if constexpr (!MULTI) {
+    return lane_rollout<Env, KIND>(p, st, depth, s_hi, creation, const_act, other, steps);
+  } else {
+    const uint32_t K = p.rollouts_per_leaf;
+    double ev[16], ov[16];
+    steps = 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < K; ++k) {
+      uint32_t n = 0;
+      double o = 0.0;
+      ev[k] = lane_rollout<Env, KIND>(p, st, depth, s_hi, creation * K + k, const_act, o, n);
+      ov[k] = o;
+      steps += n;
+    }
+#pragma unroll 1
+    for (uint32_t off = K / 2; off >= 1; off /= 2) {   // v[l] + v[l ^ off], the entries that reach index 0
+#pragma unroll 1
+      for (uint32_t l = 0; l < off; ++l) { ev[l] = __dadd_rn(ev[l], ev[l + off]); ov[l] = __dadd_rn(ov[l], ov[l + off]); }
+    }
+    other = __ddiv_rn(ov[0], (double)K);
+    return __ddiv_rn(ev[0], (double)K);
+  }
+}
+
 // Backup below the recorded path (leaves deeper than kPathMax): follows parent pointers and loads the
 // statistics. Cold for every configuration of the reference; kept out of line.
 template <class Node, int NE, int NA, int A>
@@ -525,7 +560,7 @@ __device__ __noinline__ uint32_t deep_backup(Node* nodes, uint32_t child, uint32
   return child;
 }
 
-template <class Env, int NE, int NA, int NCHILD, class CIDX, int KIND>
+template <class Env, int NE, int NA, int NCHILD, class CIDX, int KIND, bool MULTI = false>
 __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_constant__ SearchParams p) {
   using Node = NodeRec<Env, NE, NA, NCHILD, CIDX>;
   constexpr int A = Env::A;
@@ -672,8 +707,8 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(const __grid_con
     if (do_rollout) {
       double other = 0.0;
       uint32_t steps = 0;
-      const double ego = lane_rollout<Env, KIND>(p, st, depth, p.first_tree_id + tree, node, const_act,
-                                                 other, steps);
+      const double ego = leaf_heuristic<Env, KIND, MULTI>(p, st, depth, p.first_tree_id + tree, node, const_act,
+                                                   other, steps);
       rollout_steps += steps;
       leaf->ego.V = ego; leaf->ego.G = ego; leaf->ego.N = 1;   // fresh node: 0 + 1
       G[0] = ego;

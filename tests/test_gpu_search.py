@@ -460,3 +460,35 @@ def test_full_wave_sampled_trees_equal_oracle(engine):
     assert int(m["n"].sum()) == T * iters   # every iteration of every tree backed up through its root
     assert s.counters()["iterations"] == T * iters
     s.close()
+
+
+@pytest.mark.parametrize("K", [2, 4, 16])
+@pytest.mark.parametrize("layout", [LAYOUT_CLASSIC, LAYOUT_COMPACT])
+def test_k_rollouts_per_leaf_equal_oracle_tree(engine, K, layout):
+    """Leaf-batched rollouts: the value of a new leaf is the mean of K Philox rollouts (stream = creation
+    index * K + k) summed in the fixed pairwise order of DESIGN.md section 6; the oracle builds the same tree."""
+    iters = 300
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    s = Search(engine, ENV_CROSSING_I32, mp, 40, cp=cp, action_source=SRC_PHILOX, philox_seed=21, layout=layout,
+               rollouts_per_leaf=K)
+    s.run(iters)
+    env = O.make_env(cp=cp)
+    steps = 0
+    for tree in (0, 7, 39):
+        t = O.OracleTree(env, mp, [5, 5], action_source=SRC_PHILOX, K=K, seed=21, tree_id=tree)
+        t.run(iters)
+        assert np.array_equal(s.dump_tree(tree, t.num_nodes), t.dump(7)), f"K {K}: tree {tree} differs"
+        t.close()
+    s.close()
+
+
+def test_k_rollouts_per_leaf_validation(engine):
+    mp = default_params(max_number_of_iterations=10)
+    cp = default_crossing_params(num_other_agents=1)
+    for bad in (0, 3, 32):
+        with pytest.raises(MamctsError):
+            Search(engine, ENV_CROSSING_I32, mp, 1, cp=cp, action_source=SRC_PHILOX, rollouts_per_leaf=bad)
+    with pytest.raises(MamctsError):   # the reference's own rollouts are all identical (F1)
+        Search(engine, ENV_CROSSING_I32, mp, 1, cp=cp, action_source=SRC_REFERENCE_CONST, rollouts_per_leaf=4)
