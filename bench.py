@@ -480,7 +480,35 @@ def run_native(args):
         line["roofline_issue"] = _issue_roofline(_ncu_entry(layout=args.layout if args.layout else 2, trees=T,
                                                             iterations=ITERATIONS), search_kernel_ms, sm_mhz)
     search.close()
+    leaf_batched = None
+    if rank == 0 and args.leaf_batch > 1 and world == 1:
+        # the same search with K rollouts per new leaf (leaf-batched heuristic, BASELINE.json configs[1]):
+        # a different algorithm setting than the reference's K = 1, so it is reported beside the headline,
+        # never as the headline
+        K = args.leaf_batch
+        sk = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=SRC_PHILOX, philox_seed=1000,
+                    layout=args.layout, max_inner_nodes_per_tree=args.max_inner, rollouts_per_leaf=K)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            sk.run(ITERATIONS)           # warm-up decision
+            torch.cuda.synchronize()
+            reps = 2
+            ev0.record(stream)
+            for _ in range(reps):
+                sk.reset(None)
+                sk.run(ITERATIONS)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / reps
+        ck = sk.counters()
+        leaf_batched = {"rollouts_per_leaf": K, "ms_per_decision": ms,
+                        "env_steps_per_s": (ck["rollout_steps"] + ck["expand_steps"]) / (ms * 1e-3),
+                        "iterations_per_s": ck["iterations"] / (ms * 1e-3),
+                        "note": "leaf value = mean of K Philox rollouts in a fixed order (DESIGN.md section 6); "
+                                "bit-equal to the oracle's K-rollout trees (tests/test_gpu_search.py)"}
+        sk.close()
     if rank == 0:
+        line["leaf_batched"] = leaf_batched
         # the batched rollout kernel on its own (C3), after the trees are freed
         c3 = measure_rollout_c3(engine, stream)
         # (the C3 decision time includes the reduction launch: a lower bound of the kernel's own rate)
@@ -513,6 +541,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
                     help="c2 = the headline search benchmark (default, includes a C3 rollout-kernel section); "
                          "c3 = only the batched rollout kernel (profiling)")
+    ap.add_argument("--leaf-batch", type=int, default=4,
+                    help="also time the search with this many rollouts per new leaf (N = 1 only; 1 = skip)")
     ap.add_argument("--iterations", type=int, default=ITERATIONS,
                     help="iterations per tree (C2 = 10000; smaller values only for profiling runs)")
     args = ap.parse_args()

@@ -1,6 +1,6 @@
 """Sweep of the device-resident search over (lanes per warp, block threads, trees); prints one line per
 point. Profiling helper, not part of the product or the tests.
-   python scripts/sweep_search.py "lpw,threads,trees,iterations;..." """
+   python scripts/sweep_search.py "lpw,threads,trees,iterations[,max_nodes,layout,inner,K];..." """
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -24,12 +24,13 @@ def main():
         maxn = pt[4] if len(pt) > 4 else 0
         layout = pt[5] if len(pt) > 5 else 0
         inner = pt[6] if len(pt) > 6 else 0
+        K = pt[7] if len(pt) > 7 else 1
         os.environ["MAMCTS_SEARCH_LPW"] = str(lpw)
         os.environ["MAMCTS_SEARCH_THREADS"] = str(threads)
         mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000, rh_max_number_of_iterations=50)
         cp = default_crossing_params(num_other_agents=others)
         s = Search(e, ENV_CROSSING_I32, mp, trees, cp=cp, action_source=SRC_PHILOX, philox_seed=1000,
-                   max_nodes_per_tree=maxn, layout=layout, max_inner_nodes_per_tree=inner)
+                   max_nodes_per_tree=maxn, layout=layout, max_inner_nodes_per_tree=inner, rollouts_per_leaf=K)
         s.run(iters); e.sync()
         best = 1e9
         for _ in range(2):
@@ -38,7 +39,7 @@ def main():
             best = min(best, dt)
         c = s.counters()
         steps = c["rollout_steps"] + c["expand_steps"]
-        print(f"lpw={lpw} threads={threads} trees={trees} iters={iters} maxn={maxn} layout={layout} inner={inner} ms={best*1e3:.1f} "
+        print(f"lpw={lpw} threads={threads} trees={trees} iters={iters} maxn={maxn} layout={layout} inner={inner} K={K} ms={best*1e3:.1f} "
               f"env_steps/s={steps/best:.4g} it/s={c['iterations']/best:.4g} "
               f"exact_ucb/it={s.exact_ucb_evaluations()/max(c['iterations'],1):.4f} levels/it={c['backup_levels']/max(c['iterations'],1):.3f}", flush=True)
         s.close()
