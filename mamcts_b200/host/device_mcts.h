@@ -48,9 +48,10 @@ class DeviceRootParallelMcts {
 
   DeviceRootParallelMcts(const MctsParameters& mcts_parameters, unsigned num_trees, uint64_t philox_seed = 1000,
                          unsigned first_tree_id = 0, int action_source = MAMCTS_SRC_PHILOX,
-                         unsigned max_inner_nodes_per_tree = 0)
+                         unsigned max_inner_nodes_per_tree = 0, unsigned rollouts_per_leaf = 1)
       : mcts_parameters_(mcts_parameters), num_trees_(num_trees), philox_seed_(philox_seed),
         first_tree_id_(first_tree_id), action_source_(action_source), max_inner_(max_inner_nodes_per_tree),
+        rollouts_per_leaf_(rollouts_per_leaf),
         search_(nullptr), num_iterations_(0), search_time_(0), merged_valid_(false) {
     CudaEngine::get();
   }
@@ -81,7 +82,7 @@ class DeviceRootParallelMcts {
       cfg.action_source = action_source_;
       cfg.num_trees = num_trees_;
       cfg.first_tree_id = first_tree_id_;
-      cfg.rollouts_per_leaf = 1;
+      cfg.rollouts_per_leaf = rollouts_per_leaf_;   // 1 = the reference's heuristic; 2..16 = leaf-batched mean
       cfg.layout = MAMCTS_LAYOUT_AUTO;
       cfg.max_inner_nodes_per_tree = max_inner_;
       cfg.philox_seed = philox_seed_;
@@ -225,6 +226,7 @@ class DeviceRootParallelMcts {
   uint64_t philox_seed_;
   unsigned first_tree_id_;
   int action_source_;
+  unsigned rollouts_per_leaf_ = 1;
   unsigned max_inner_;
   mamcts_search* search_;
   unsigned num_iterations_, search_time_;
