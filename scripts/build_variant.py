@@ -12,5 +12,5 @@ obj = f"/tmp/search_{name}.o"
 subprocess.check_call([g._nvcc()] + g.NVCC_FLAGS + flags + inc + ["-c", os.path.join(g.CSRC, "search.cu"), "-o", obj])
 objs = [os.path.join(g.CSRC, s.replace(".cu", ".o")) for s in g.CUDA_SOURCES if s != "search.cu"] + [obj]
 out = os.path.join(ROOT, "scripts", "micro", f"libmamcts_{name}.so")
-subprocess.check_call([g._nvcc(), "-shared", "-o", out] + objs + ["-lcudart", "-ldl", "-lpthread"])
+subprocess.check_call([g._nvcc(), "-Wno-deprecated-gpu-targets", "-shared", "-o", out] + objs + ["-lcudart", "-ldl", "-lpthread"])
 print(out)
