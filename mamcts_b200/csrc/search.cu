@@ -194,6 +194,10 @@ struct SearchC final : public mamcts_search {
     const uint32_t T = cfg.num_trees;
     const uint32_t trees_per_block = (uint32_t)(block_threads / 32) * q.lanes_per_warp;
     const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
+    if (const char* v = std::getenv("MAMCTS_SEARCH_CARVEOUT")) {   // profiling knob: shared-memory carve-out in percent
+      auto kern = search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(v));
+    }
     if (std::getenv("MAMCTS_SEARCH_DEBUG")) {   // resident blocks per SM as the runtime computes them
       int nb = 0;
       cudaFuncAttributes fa;
