@@ -88,3 +88,43 @@ def finish(acc: np.ndarray, num_actions: int) -> dict:
             present += 1
     return dict(q=q, n=acc[nA:2 * nA].astype(np.uint64), occurrences=acc[2 * nA:3 * nA].astype(np.uint32),
                 visits=int(acc[3 * nA]), value=(value / present) if present else 0.0, best=best)
+
+
+# ---------------------------------------------------------------------------------------------
+# C3: one decision, a large number of rollouts from the same leaf set
+# ---------------------------------------------------------------------------------------------
+# The rollout index range is partitioned like the trees; rollout r draws from Philox stream
+# (stream_hi, stream_lo_base + r) with the GLOBAL index r, so the set of rollouts is the same for any
+# number of GPUs. The exchange step is one all-reduce of {sum, sum of squares, count} per agent.
+
+@dataclass(frozen=True)
+class RolloutShard:
+    first_rollout: int   # global index of this rank's rollout 0 (added to stream_lo_base)
+    num_rollouts: int
+
+
+def rollout_shard(total_rollouts: int, world_size: int, rank: int) -> RolloutShard:
+    s = strong_shard(total_rollouts, world_size, rank)
+    return RolloutShard(s.first_tree_id, s.num_trees)
+
+
+def moments_partial(returns: np.ndarray) -> np.ndarray:
+    """The all-reduce payload of one rank: per agent [sum, sum of squares], then the rollout count.
+    returns: [agents, local rollouts] (ego first, then the other agents)."""
+    r = np.atleast_2d(np.asarray(returns, dtype=np.float64))
+    acc = np.zeros(2 * r.shape[0] + 1)
+    acc[0:2 * r.shape[0]:2] = r.sum(axis=1)
+    acc[1:2 * r.shape[0]:2] = (r * r).sum(axis=1)
+    acc[-1] = r.shape[1]
+    return acc
+
+
+def moments_finish(acc: np.ndarray) -> dict:
+    """Mean and (population) variance per agent from a fully reduced payload."""
+    acc = np.asarray(acc, dtype=np.float64)
+    count = acc[-1]
+    if count <= 0:
+        raise ValueError("no rollouts")
+    s, ss = acc[0:-1:2], acc[1:-1:2]
+    mean = s / count
+    return dict(count=int(count), mean=mean, variance=np.maximum(ss / count - mean * mean, 0.0))

@@ -148,3 +148,62 @@ def test_world_size_2_gloo_equals_single_process(tmp_path):
             assert merged.n[a] == int(r0["n"][a])
             assert abs(merged.q[a] - r0["q"][a]) <= 1e-12 * max(1.0, abs(merged.q[a]))
     assert O.oracle().orc_stat_best_action(C.byref(merged)) == int(r0["best"])
+
+
+# ---------------------------------------------------------------------------------------------
+# C3: the rollout index range sharded over ranks, one all-reduce of {sum, sum of squares, count}
+# ---------------------------------------------------------------------------------------------
+C3_TOTAL = 2003          # ragged on purpose
+C3_OTHERS = 3
+
+
+def _c3_returns(first, count):
+    """Returns of rollouts [first, first + count) of one decision from the oracle (global stream ids)."""
+    import oracle_api as O
+    from mamcts_b200 import default_crossing_params, default_params
+    from mamcts_b200._abi import SRC_PHILOX
+    mpar = default_params(rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=C3_OTHERS)
+    A = C3_OTHERS + 1
+    x = np.full((A, count), 5, dtype=np.int32)
+    out = O.rollout_batch(O.make_env(cp=cp), mpar, x, None, None, None, K=1, kind=SRC_PHILOX, seed=1000,
+                          stream_hi_base=0, stream_lo_base=first)
+    return np.vstack([out["ego_return"][None, :], out["other_return"].reshape(A - 1, count)])
+
+
+def _c3_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+    import torch
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+    sh = sharding.rollout_shard(C3_TOTAL, world, rank)
+    acc = torch.from_numpy(sharding.moments_partial(_c3_returns(sh.first_rollout, sh.num_rollouts)))
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    res = sharding.moments_finish(acc.numpy())
+    np.savez(os.path.join(outdir, f"c3_rank{rank}.npz"), first=sh.first_rollout, count=sh.num_rollouts,
+             total=res["count"], mean=res["mean"], variance=res["variance"])
+    dist.destroy_process_group()
+
+
+def test_c3_rollout_range_world_size_2_gloo_equals_single_process(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_c3_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(tmp_path / "c3_rank0.npz")
+    r1 = np.load(tmp_path / "c3_rank1.npz")
+    assert (int(r0["first"]), int(r0["count"]), int(r1["first"]), int(r1["count"])) == (0, 1002, 1002, 1001)
+    for k in ("total", "mean", "variance"):
+        assert np.array_equal(r0[k], r1[k]), k
+    one = sharding.moments_finish(sharding.moments_partial(_c3_returns(0, C3_TOTAL)))
+    assert int(r0["total"]) == one["count"] == C3_TOTAL
+    np.testing.assert_allclose(r0["mean"], one["mean"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(r0["variance"], one["variance"], rtol=1e-9, atol=1e-15)
+    assert np.all(one["mean"][1:] == 0.0)      # reward-free other agents (crossing_state.h:145)
+
+
+def test_rollout_shards_cover_the_range():
+    for world in (1, 2, 3, 8):
+        got = []
+        for r in range(world):
+            sh = sharding.rollout_shard(C3_TOTAL, world, r)
+            got += list(range(sh.first_rollout, sh.first_rollout + sh.num_rollouts))
+        assert got == list(range(C3_TOTAL))
