@@ -120,6 +120,21 @@ class Engine:
     def comm_destroy(self):
         self._check(self.lib.mamcts_comm_destroy(self.h), "mamcts_comm_destroy")
 
+    def allreduce_f64(self, values: np.ndarray) -> np.ndarray:
+        """Sum all-reduce of a small vector of doubles over the engine's NCCL communicator (host in, host
+        out: the payload goes through a device buffer; the collective itself is mamcts_allreduce_f64)."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        d = self.device_alloc(v.nbytes)
+        try:
+            self.h2d(d, v)
+            self._check(self.lib.mamcts_allreduce_f64(self.h, C.c_void_p(d), v.size), "mamcts_allreduce_f64")
+            out = np.empty_like(v)
+            self.d2h(out, d)
+            self.sync()
+        finally:
+            self.device_free(d)
+        return out
+
     # -- rollouts -----------------------------------------------------------------------------
     @staticmethod
     def _source(kind, A, replay_actions=None, replay_steps=None, const_actions=None, seed=0,

@@ -34,15 +34,36 @@ def main():
     gathered = [None] * world
     dist.all_gather_object(gathered, (m["n"].tolist(), m["q"].tolist(), m["visits"], m["best"]))
     ok = all(g == gathered[0] for g in gathered)
+    # C3: one decision, the rollout index range sharded over the ranks (global Philox stream ids), one
+    # all-reduce of {sum, sum of squares, count} per agent
+    c3_total, c3_others = 100003, 7
+    mp3 = default_params(rh_max_number_of_iterations=50)
+    cp3 = default_crossing_params(num_other_agents=c3_others)
+
+    def c3_returns(engine, first, count):
+        x = np.full((c3_others + 1, count), 5, dtype=np.int32)
+        out = engine.rollout_crossing(mp3, cp3, x, None, None, None, K=1, kind=SRC_PHILOX, seed=1000,
+                                      stream_hi_base=0, stream_lo_base=first)
+        return np.vstack([out["ego_return"][None, :], out["other_return"].reshape(c3_others, count)])
+
+    rs = sharding.rollout_shard(c3_total, world, rank)
+    c3 = sharding.moments_finish(e.allreduce_f64(sharding.moments_partial(c3_returns(e, rs.first_rollout, rs.num_rollouts))))
     e.comm_destroy()
     if rank == 0:
         e1 = Engine(local)
         s1 = Search(e1, ENV_CROSSING_I32, mp, total, cp=cp, action_source=SRC_PHILOX, philox_seed=77)
         s1.run(iters)
         r = s1.merge_roots()
-        s1.close(); e1.close()
+        s1.close()
         ok = ok and r["n"].tolist() == m["n"].tolist() and r["visits"] == m["visits"] == total * iters
         ok = ok and r["best"] == m["best"] and np.allclose(r["q"], m["q"], rtol=1e-12, atol=0)
+        one = sharding.moments_finish(sharding.moments_partial(c3_returns(e1, 0, c3_total)))
+        c3_ok = (c3["count"] == one["count"] == c3_total and np.allclose(c3["mean"], one["mean"], rtol=1e-12, atol=1e-15)
+                 and np.allclose(c3["variance"], one["variance"], rtol=1e-9, atol=1e-15))
+        ok = ok and c3_ok
+        print(f"MULTI_GPU_CHECK_C3 world={world} rollouts={c3_total} {'OK' if c3_ok else 'FAILED'} "
+              f"mean ego return {c3['mean'][0]:.9g} (single GPU {one['mean'][0]:.9g})")
+        e1.close()
         print(f"MULTI_GPU_CHECK world={world} trees={total} {'OK' if ok else 'FAILED'} n={m['n'].tolist()} q={m['q'].tolist()}")
     dist.barrier()
     dist.destroy_process_group()
