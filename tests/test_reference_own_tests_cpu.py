@@ -1,7 +1,9 @@
 """The reference's OWN tests for the path, compiled unmodified from the reference checkout against the
 gtest / glog / boost stand-ins under oracle/shim (oracle/Makefile target `reftests`): test/uct/uct_test.cc
-(verify_uct and friends: 5 tests, 663 checks) and environments/tests/crossing_state_int_test.cc (execute,
-hypothesis policies, belief tracker, closed-loop episodes: 7 tests). They pin the reference build that
+(verify_uct and friends: 5 tests, 663 checks), environments/tests/crossing_state_int_test.cc (execute,
+hypothesis policies, belief tracker, closed-loop episodes: 7 tests), crossing_state_float_test.cc (the float
+domain: 10 tests), test/hypothesis/hypothesis_statistic_test.cc (3 tests: the known answers the hypothesis
+backup kernel is also checked against) and belief_tracker_test.cc (2 tests). They pin the reference build that
 oracle/_ref (the checker the parity tests compare with) is made from: same sources, same flags, same shims.
 The binaries are built where the reference checkout exists and travel with the repository snapshot."""
 from __future__ import annotations
@@ -50,3 +52,23 @@ def test_reference_crossing_state_int_test_passes(tmp_path):
                       "crossing_state.mcts_goal_reached_true_hypothesis",
                       "crossing_state.mcts_goal_reached_wrong_hypothesis",
                       "episode_runner.four_agents_reached_goal", "episode_runner.run_some_steps"]
+
+
+def test_reference_crossing_state_float_test_passes(tmp_path):
+    passed, _checks = _run("ref_crossing_state_float_test", tmp_path, 400)
+    assert len(passed) == 10 and "hypothesis_crossing_state_float.policy_probability" in passed
+    assert "hypothesis_crossing_state_float.collision" in passed and "episode_runner.run_some_steps" in passed
+
+
+def test_reference_hypothesis_statistic_test_passes(tmp_path):
+    passed, checks = _run("ref_hypothesis_statistic_test", tmp_path, 120)
+    assert passed == ["hypothesis_statistic.backprop_hypothesis_action_selection",
+                      "hypothesis_statistic.backprop_heuristic_hyp1",
+                      "hypothesis_statistic.worst_case_action_selection"]
+    assert checks == 20
+
+
+def test_reference_belief_tracker_test_passes(tmp_path):
+    passed, checks = _run("ref_belief_tracker_test", tmp_path, 120)
+    assert passed == ["belief_tracker.simple_tracking_state", "belief_tracker.fixed_hypothesis_set"]
+    assert checks == 13
