@@ -165,12 +165,51 @@ def cpu_reference_search(threads: int, repeats: int):
                 seconds=el, searches=repeats, env_steps_per_search=steps / repeats)
 
 
+def cpu_baselines(repeats: int):
+    """Every CPU leg BASELINE.md promises, timed on this box's host cores BEFORE any GPU rank starts work
+    (the other ranks of a torchrun launch wait for rank 0's flag file, see _cpu_gate), each a bounded sample:
+    (i) `nproc` independent single_search of C2 (the embarrassingly parallel ceiling, the headline baseline),
+    (ii) the reference's own root-parallel path Mcts::parallel_search with USE_MULTI_THREADING
+    (mcts/mcts.h:188-221; the runnable stand-in for test/parallel_mcts, which needs OR-tools),
+    (iii) RandomHeuristic::rollout loops at A = 2 and A = 8 (random_heuristic.h:27-104)."""
+    import oracle_api as O
+    from mamcts_b200 import default_crossing_params, default_params
+    threads = os.cpu_count() or 1
+    cb = cpu_reference_search(threads, max(1, repeats))
+    out = {"value": cb["env_steps_per_s"], "unit": UNIT, "cores": threads, "kind": cb["kind"],
+           "iterations_per_s": cb["iterations_per_s"],
+           "sample": f"{cb['searches']} whole C2 searches ({ITERATIONS} iterations each, the reference's stock "
+                     f"deterministic rollouts, {cb['env_steps_per_search']:.0f} execute() calls per search) on "
+                     f"{threads} host threads, {cb['seconds']:.1f} s; timed before the GPU ranks start"}
+    if O.reference_available():
+        mp, cp = _params()
+        it_s, sec, _q, n = O.ref_time_parallel_search(mp, cp, threads)
+        out["parallel_search"] = {
+            "iterations_per_s": it_s, "seconds": sec, "num_parallel_mcts": threads,
+            "env_steps_per_s": it_s * cb["env_steps_per_search"] / ITERATIONS,
+            "root_visits": int(sum(int(v) for v in n if v > 0)),
+            "what": "Mcts::parallel_search, USE_MULTI_THREADING = true, NUM_PARALLEL_MCTS = nproc "
+                    "(reference mcts/mcts.h:188-221), one call"}
+        mpr = default_params(rh_max_number_of_iterations=DEPTH_CAP)
+        for others in (1, C3_OTHERS):
+            st, ro = O.ref_time_rollouts(mpr, default_crossing_params(num_other_agents=others), threads, 2.0)
+            out[f"rollout_loop_a{others + 1}"] = {
+                "env_steps_per_s": st, "rollouts_per_s": ro, "cores": threads,
+                "what": f"RandomHeuristic::rollout from the start state, {others + 1} agents, depth cap {DEPTH_CAP}, "
+                        "2 s on every host thread"}
+    return out
+
+
+def _cpu_gate_path():
+    # all ranks of one torchrun launch share the launcher as parent process
+    return os.path.join("/tmp", f"mamcts_bench_cpu_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}.json")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    total_steps = args.warmup + args.steps
     # each bench step = every host thread runs `rep` whole searches; sized to ~1 s per step
     rep = 1
     cpu_reference_search(threads, 1) if args.warmup else None
@@ -182,20 +221,29 @@ def run_reference(args):
     sample = (f"{threads} host threads x {rep} independent single_search of the C2 configuration per step "
               f"({ITERATIONS} iterations each, deterministic reference rollouts, "
               f"{results[0]['env_steps_per_search']:.0f} execute() calls per search)")
+    cfg = _config(threads * rep, 1, "the reference's stock RandomHeuristic: every rollout step applies the one joint "
+                  "action a fresh statistic draws first (mt19937 first draw, SURVEY.md F1) - the reference has no "
+                  "other rollout policy; 5.7 execute() calls per iteration against 11.9 with uniform Philox actions, "
+                  "so compare the arms in iterations_per_s",
+                  "n/a for this arm (the reference keeps each tree in shared_ptr / std::map nodes on the host)")
+    cfg["workload"] = ("C2: CrossingState<int> 2 agents (ego 4 / other 7 actions), UctStatistic ego+other, "
+                       f"{ITERATIONS} iterations per tree, rollout depth cap {DEPTH_CAP}, {threads * rep} independent "
+                       "trees per step on the host cores (one per thread)")
+    cfg.pop("trees_per_gpu"); cfg.pop("trees_total")
+    cfg["cache"] = "n/a (host arm: every tree is built in host memory)"
+    cfg["trees_per_step"] = threads * rep
+    cfg["parallelism"] = f"{threads} host threads, one single_search each (mcts/mcts.h:166-186)"
     line = {
         "impl": "reference", "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": _config(args.trees, args.gpus, "philox4x32-10 uniform joint actions",
-                          "n/a for this arm (the reference keeps each tree in shared_ptr / std::map nodes on the host)"),
-        "reference_action_source": "the reference's stock RandomHeuristic (mt19937 first-draw constant "
-                                   "actions, SURVEY.md F1); it has no other rollout policy",
+        "config": cfg,
         "iterations_per_s": its_per_s,
-        "cpu_baseline": {"value": steps_per_s, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": steps_per_s, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "iterations_per_s": its_per_s},
         "e2e": {"value": steps_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    del total_steps
     print(json.dumps(line))
 
 
@@ -205,89 +253,228 @@ def run_reference(args):
 
 C3_OTHERS = 7            # 8 agents
 C3_ROLLOUTS = 1 << 20    # 1M rollouts per decision
+C5_TREES = 65536         # BASELINE.json configs[4]: 65 536 trees in total over the GPUs
+C5_ITERATIONS = 1000
 
 
-def measure_rollout_c3(engine, stream, steps=5, warmup=3):
-    """CrossingState<int>, 8 agents, 2^20 Philox rollouts per decision (4096 start states x 256
-    rollouts each, depth cap 50), device-resident inputs; returns env-steps/s from the kernel's own
-    step counter, timed with CUDA events on the engine stream, plus the HBM roofline of
-    rollout_kernel (algorithmic bytes 16A+8C+8 per rollout)."""
+def measure_rollout_c3(engine, stream, world=1, rank=0, steps=5, warmup=3, dist=None, e2e=True):
+    """CrossingState<int>, 8 agents, 2^20 Philox rollouts per decision from the decision state, depth cap 50.
+    The rollout index range is sharded over the ranks (sharding.rollout_shard; rollout r keeps its GLOBAL
+    Philox stream id, so the set of rollouts does not depend on the number of GPUs); each decision is one
+    rollout launch, one on-device moments reduction ({sum, sum^2} per agent + count, reduce.cu) and one
+    ncclAllReduce of those 2A+1 doubles (mamcts_rollout_moments). Device-resident inputs; env-steps/s from the
+    kernel's own step counter, CUDA events on the engine stream, max over ranks, L2 flushed between decisions;
+    plus the HBM roofline of rollout_kernel (algorithmic bytes 16A+8C+8 per rollout)."""
     import numpy as np
     import torch
-    from mamcts_b200 import default_crossing_params, default_params
+    from mamcts_b200 import default_crossing_params, default_params, sharding
     from mamcts_b200._abi import SRC_PHILOX
     mp = default_params(rh_max_number_of_iterations=DEPTH_CAP)
     cp = default_crossing_params(num_other_agents=C3_OTHERS)
     A = C3_OTHERS + 1
-    n, K = 4096, C3_ROLLOUTS // 4096
+    sh = sharding.rollout_shard(C3_ROLLOUTS, world, rank)
+    n = sh.num_rollouts
     dev = torch.device("cuda", engine.device)
     with torch.cuda.stream(stream):
         # the decision state (all agents at x = 5, reference crossing_state_common.h:31) in every slot
         x = torch.full((A, n), 5, dtype=torch.int32, device=dev)
         ego = torch.zeros(n, dtype=torch.float64, device=dev)
         oth = torch.zeros((A - 1, n), dtype=torch.float64, device=dev)
-        cost = torch.zeros(n, dtype=torch.float64, device=dev)
-        ln = torch.zeros(n, dtype=torch.float64, device=dev)
         tot = torch.zeros(1, dtype=torch.int64, device=dev)
+        mom = torch.zeros(2 * A + 1, dtype=torch.float64, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
 
     def one(i):
-        engine.rollout_crossing_device(mp, cp, n, K, x.data_ptr(), ego.data_ptr(), oth.data_ptr(),
-                                       cost.data_ptr(), ln.data_ptr(), tot.data_ptr(), kind=SRC_PHILOX,
-                                       seed=1000, stream_hi_base=i, stream_lo_base=0)
+        engine.rollout_crossing_device(mp, cp, n, 1, x.data_ptr(), ego.data_ptr(), oth.data_ptr(),
+                                       0, 0, tot.data_ptr(), kind=SRC_PHILOX,
+                                       seed=1000, stream_hi_base=i, stream_lo_base=sh.first_rollout)
+        engine.rollout_moments(ego.data_ptr(), oth.data_ptr(), A - 1, n, d_out=mom.data_ptr())
+
+    def barrier():
+        if dist is not None and world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for i in range(warmup):
         one(i)
-    stream.synchronize()
-    times, total_steps = [], 0
+    barrier()
+    times, kern_times, total_steps = [], [], 0
     launches0 = engine.launch_count
     for i in range(steps):
         with torch.cuda.stream(stream):
             flush.fill_(i & 0xFF)                     # flush L2 between timed iterations
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, k, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record(stream)
-        one(warmup + i)
+        engine.rollout_crossing_device(mp, cp, n, 1, x.data_ptr(), ego.data_ptr(), oth.data_ptr(),
+                                       0, 0, tot.data_ptr(), kind=SRC_PHILOX,
+                                       seed=1000, stream_hi_base=warmup + i, stream_lo_base=sh.first_rollout)
+        k.record(stream)
+        engine.rollout_moments(ego.data_ptr(), oth.data_ptr(), A - 1, n, d_out=mom.data_ptr())
         b.record(stream)
         stream.synchronize()
         times.append(a.elapsed_time(b))
+        kern_times.append(a.elapsed_time(k))
         total_steps += int(tot.item())
     launches = engine.launch_count - launches0
-    ms = sum(times) / len(times)
-    steps_per_s = total_steps / (sum(times) * 1e-3)
-    # e2e: host buffers through the public call (pinned numpy in, numpy out)
-    xh = np.full((A, n), 5, dtype=np.int32)
-    engine.rollout_crossing(mp, cp, xh, K=K, kind=SRC_PHILOX, seed=1000, stream_hi_base=99)
-    t0 = time.perf_counter()
-    e2e_steps = 0
-    for i in range(steps):
-        r = engine.rollout_crossing(mp, cp, xh, K=K, kind=SRC_PHILOX, seed=1000, stream_hi_base=100 + i)
-        e2e_steps += r["total_steps"]
-    e2e_s = time.perf_counter() - t0
+    moments = mom.cpu().numpy()
+    agg = torch.tensor([sum(times), float(total_steps), sum(kern_times)], dtype=torch.float64, device=dev)
+    mx = agg.clone()
+    if dist is not None and world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    total_ms, all_steps, kern_ms_sum = float(mx[0]), float(agg[1]), float(mx[2])
+    ms = total_ms / steps
+    kern_ms = kern_ms_sum / steps
+    steps_per_s = all_steps / (total_ms * 1e-3)
+    fin = sharding.moments_finish(moments)
+    out = {
+        "workload": f"C3: CrossingState<int> {A} agents, {C3_ROLLOUTS} Philox rollouts per decision from the decision "
+                    f"state sharded over {world} GPU(s) by global rollout index, depth cap {DEPTH_CAP}, device-side "
+                    "moments reduction + one ncclAllReduce of 2A+1 doubles per decision, L2 flushed between decisions",
+        "env_steps_per_s": steps_per_s, "rollouts_per_s": C3_ROLLOUTS / (ms * 1e-3), "ms_per_decision": ms,
+        "rollout_kernel_ms": kern_ms, "n_gpus": world, "scaling": "strong",
+        "mean_steps_per_rollout": all_steps / (steps * C3_ROLLOUTS), "gpu_launches": int(launches),
+        "rollouts_counted": int(fin["count"]), "mean_ego_return": float(fin["mean"][0]),
+        "kernel_ms_estimate": kern_ms,
+    }
+    if fin["count"] != C3_ROLLOUTS:
+        raise SystemExit(f"bench.py: C3 all-reduced rollout count {fin['count']} != {C3_ROLLOUTS}")
+    if e2e and rank == 0:
+        # e2e: host buffers through the public call (numpy in, numpy out), this rank's shard
+        xh = np.full((A, n), 5, dtype=np.int32)
+        engine.rollout_crossing(mp, cp, xh, K=1, kind=SRC_PHILOX, seed=1000, stream_hi_base=99)
+        t0 = time.perf_counter()
+        e2e_steps = 0
+        for i in range(steps):
+            r = engine.rollout_crossing(mp, cp, xh, K=1, kind=SRC_PHILOX, seed=1000, stream_hi_base=100 + i,
+                                        stream_lo_base=sh.first_rollout)
+            engine.rollout_moments(r["ego_return"], r["other_return"])
+            e2e_steps += r["total_steps"]
+        e2e_s = time.perf_counter() - t0
+        out.update({"e2e_env_steps_per_s_rank0_shard": e2e_steps / e2e_s, "e2e_h2d_bytes": int(xh.nbytes),
+                    "e2e_d2h_bytes": int(8 * n * (A + 2) + 8)})
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
     bytes_per_rollout = 16 * A + 8 * 1 + 8
-    achieved = bytes_per_rollout * C3_ROLLOUTS / (ms * 1e-3) / 1e9
-    return {
-        "workload": f"C3: CrossingState<int> {A} agents, {C3_ROLLOUTS} Philox rollouts per decision "
-                    f"({n} leaves x {K}), depth cap {DEPTH_CAP}, L2 flushed between decisions",
-        "env_steps_per_s": steps_per_s, "rollouts_per_s": C3_ROLLOUTS / (ms * 1e-3), "ms_per_decision": ms,
-        "mean_steps_per_rollout": total_steps / (steps * C3_ROLLOUTS), "gpu_launches": int(launches),
-        "e2e_env_steps_per_s": e2e_steps / e2e_s,
-        "e2e_h2d_bytes": int(xh.nbytes), "e2e_d2h_bytes": int(8 * n * (A + 2) + 8),
-        "kernel_ms_estimate": ms,
-        "roofline": {"bound": "hbm", "kernel": "rollout_kernel<CrossingEnv<7>,PHILOX>", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "algorithmic_bytes_per_rollout": bytes_per_rollout,
-                     "note": "state lives in registers for the whole episode: issue-bound, see "
-                             "profiles/ for smsp__issue_active and instructions per env-step"},
-    }
+    achieved = bytes_per_rollout * n / (kern_ms * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm", "kernel": "rollout_kernel<CrossingEnv<7>,PHILOX>", "achieved": achieved,
+                       "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                       "algorithmic_bytes_per_rollout": bytes_per_rollout,
+                       "note": "per GPU; state lives in registers for the whole episode: issue-bound, see "
+                               "profiles/ for smsp__issue_active and instructions per env-step"}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
 # this repository's engine
 # ---------------------------------------------------------------------------------------------
 
+def measure_c5_strong(engine, stream, world, rank, dist, steps=5, warmup=2):
+    """BASELINE.json configs[4] (C5): 65 536 root-parallel C2 trees IN TOTAL, sharded over the ranks by global
+    tree id (sharding.strong_shard - the union of the ranks' trees is the same for every N), 1 000 iterations
+    per tree, one NCCL all-reduce of the ego root statistics per decision. Strong scaling: total work is fixed.
+    A step = one decision through the public call (host root state in, merged statistics and best action out:
+    Search.reset(host) + run + merge_roots), timed with CUDA events on the engine stream, max over ranks."""
+    import numpy as np
+    import torch
+    from mamcts_b200 import default_crossing_params, default_params, sharding
+    from mamcts_b200._abi import ENV_CROSSING_I32, SRC_PHILOX
+    from mamcts_b200.engine import Search
+    mp = default_params(max_number_of_iterations=C5_ITERATIONS, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=DEPTH_CAP)
+    cp = default_crossing_params(num_other_agents=NUM_OTHERS)
+    sh = sharding.strong_shard(C5_TREES, world, rank)
+    s = Search(engine, ENV_CROSSING_I32, mp, sh.num_trees, cp=cp, action_source=SRC_PHILOX, philox_seed=1000,
+               first_tree_id=sh.first_tree_id)
+    root = np.full(NUM_OTHERS + 1, 5, dtype=np.int32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    merged = None
+    for _ in range(warmup):
+        s.reset(root); s.run(C5_ITERATIONS); merged = s.merge_roots()
+    barrier()
+    launches0 = engine.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kern = []
+    t0 = time.perf_counter()
+    ev[0].record(stream)
+    for _ in range(steps):
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.reset(root)
+        ka.record(stream)
+        s.run(C5_ITERATIONS)
+        kb.record(stream)
+        merged = s.merge_roots()          # local reduce + ncclAllReduce + device -> host read
+        kern.append((ka, kb))
+    ev[1].record(stream)
+    barrier()
+    wall_s = time.perf_counter() - t0
+    launches = engine.launch_count - launches0
+    c = s.counters()
+    dev = torch.device("cuda", engine.device)
+    mx = torch.tensor([ev[0].elapsed_time(ev[1]), sum(a.elapsed_time(b) for a, b in kern) / len(kern), wall_s * 1e3],
+                      dtype=torch.float64, device=dev)
+    sm = torch.tensor([c["rollout_steps"] + c["expand_steps"], c["iterations"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    total_ms, kern_ms, wall_ms = (float(v) for v in mx.tolist())
+    env_steps, iters = (float(v) for v in sm.tolist())
+    s.close()
+    # every tree's root was visited once per iteration, on every rank, and the collective saw all of them
+    if int(merged["visits"]) != C5_TREES * C5_ITERATIONS or int(sum(int(v) for v in merged["n"])) != C5_TREES * C5_ITERATIONS:
+        raise SystemExit(f"bench.py: C5 merged root visits {merged['visits']} != {C5_TREES * C5_ITERATIONS}")
+    return {
+        "workload": f"C5: {C5_TREES} root-parallel C2 trees in total over {world} GPU(s) ({sh.num_trees} on rank 0), "
+                    f"{C5_ITERATIONS} iterations per tree, one NCCL all-reduce of 13 doubles per decision; a step = one "
+                    "decision through Search.reset(host root) + run + merge_roots",
+        "scaling": "strong", "n_gpus": world, "trees_total": C5_TREES, "trees_per_gpu": sh.num_trees,
+        "iterations_per_tree": C5_ITERATIONS, "steps": steps,
+        "env_steps_per_s": env_steps * steps / (total_ms * 1e-3), "iterations_per_s": iters * steps / (total_ms * 1e-3),
+        "ms_per_decision": total_ms / steps, "search_kernel_ms": kern_ms, "wall_ms_per_decision": wall_ms / steps,
+        "merged_root_visits": int(merged["visits"]), "merged_root_n": [int(v) for v in merged["n"]],
+        "best_action": int(merged["best"]), "gpu_launches": int(launches),
+    }
+
+
+def _check_sampled_tree(search, mp, cp, first_tree_id, tree):
+    """Outside the timed region: one of the trees the bench just timed, node for node, against the CPU oracle
+    driven by the same Philox stream (tests/oracle_api.py; the checker, never the thing measured)."""
+    import numpy as np
+    import oracle_api as O
+    from mamcts_b200._abi import SRC_PHILOX
+    t = O.OracleTree(O.make_env(cp=cp), mp, [5] * (NUM_OTHERS + 1), action_source=SRC_PHILOX, seed=1000,
+                     tree_id=first_tree_id + tree)
+    t.run(ITERATIONS)
+    got = search.dump_tree(tree, t.num_nodes + 1)
+    ok = got.shape[0] == t.num_nodes and np.array_equal(got, t.dump(7))
+    nodes = t.num_nodes
+    t.close()
+    return bool(ok), int(nodes)
+
+
 def run_native(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # ---- cpu baseline first: the reference's own search on the host cores while no GPU rank is working ----
+    cpu_baseline = None
+    gate = _cpu_gate_path()
+    if rank == 0:
+        cpu_baseline = cpu_baselines(args.cpu_repeats)
+        if world > 1:
+            with open(gate + ".tmp", "w") as f:
+                json.dump({"done": True}, f)
+            os.replace(gate + ".tmp", gate)
+    else:
+        t_wait = time.time()
+        while not os.path.exists(gate) and time.time() - t_wait < 600:
+            time.sleep(0.2)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -301,12 +488,14 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the mamcts_b200 engine has no CPU fallback")
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if rank == 0:
+            try:
+                os.remove(gate)
+            except OSError:
+                pass
     engine = Engine(local_rank)
     stream = torch.cuda.Stream(device=local_rank)
     engine.set_stream(stream.cuda_stream)
@@ -320,9 +509,15 @@ def run_native(args):
 
     from mamcts_b200 import sharding
     if args.workload == "c3":
+        c3 = measure_rollout_c3(engine, stream, world, rank, args.steps, args.warmup, dist if world > 1 else None)
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": 1,
-                              **measure_rollout_c3(engine, stream, args.steps, args.warmup)}))
+            print(json.dumps({"metric": METRIC, "unit": UNIT, **c3}))
+        engine.close()
+        return
+    if args.workload == "c5":
+        c5 = measure_c5_strong(engine, stream, world, rank, dist, args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "unit": UNIT, **c5}))
         engine.close()
         return
     mp, cp = _params()
@@ -416,10 +611,31 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = env_steps_per_step * args.steps / float(t_e2e.item())
+    e2e_its = iters_per_step * args.steps / float(t_e2e.item())
     nA = 4
 
+    # ---- correctness gate on the trees just timed (outside every timed region) -------------------
+    # every iteration of every tree on every rank went through its root, and the all-reduce saw all of them;
+    # one tree of rank 0 is compared node for node with the CPU oracle on the same Philox stream
+    total_trees = T * world
+    if int(merged["visits"]) != total_trees * ITERATIONS or sum(int(v) for v in merged["n"]) != total_trees * ITERATIONS:
+        raise SystemExit(f"bench.py: merged root visits {merged['visits']} / counts {merged['n']} != trees x iterations "
+                         f"= {total_trees * ITERATIONS}")
+    gate_info = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (search_kernel), rank 0's launch -------------------
+        sample = (12345 * 7919) % T
+        ok, nodes_sample = _check_sampled_tree(search, mp, cp, shard.first_tree_id, sample)
+        if not ok:
+            raise SystemExit(f"bench.py: tree {sample} of the timed search differs from the CPU oracle")
+        gate_info = {"merged_root_visits": int(merged["visits"]), "expected": total_trees * ITERATIONS,
+                     "sampled_tree": int(sample), "sampled_tree_nodes": nodes_sample,
+                     "sampled_tree_equals_oracle": True,
+                     "what": "sum of root visits over all ranks = trees x iterations; one timed tree dumped and "
+                             "compared node for node (bit-exact) with the CPU oracle on the same Philox stream"}
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (the search kernel), rank 0's launch -----------------
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             with open(peaks_path) as f:
@@ -429,34 +645,31 @@ def run_native(args):
         A = NUM_OTHERS + 1
         it_local = c["iterations"]
         mean_depth = c["backup_levels"] / max(it_local, 1)
-        # algorithmic bytes per iteration: rollout 16A+8C+8, backup 80*A*L,
-        # selection reads (12*nA+12) per agent per level = 60 (ego) + 96 (other)
-        bytes_per_it = (16 * A + 8 + 8) + 80 * A * mean_depth + (60 + 96 * (A - 1)) * (mean_depth + 1)
-        algo_bytes = bytes_per_it * it_local
-        achieved = algo_bytes / (search_kernel_ms * 1e-3) / 1e9
+        # ALGORITHMIC bytes per iteration, SURVEY.md 8(d): rollout 16A + 8C + 8 and backup 80 * A * L
+        bytes_per_it = (16 * A + 8 + 8) + 80 * A * mean_depth
+        # the same plus the selection reads of the device-resident tree:
+        # (12 nA + 12) per agent per level = 60 (ego) + 96 (other); most of these hit the L2
+        bytes_per_it_sel = bytes_per_it + (60 + 96 * (A - 1)) * (mean_depth + 1)
+        kern_s = search_kernel_ms * 1e-3
+        achieved = bytes_per_it * it_local / kern_s / 1e9
+        traffic = _measured_traffic(args.layout, T, ITERATIONS)
         roofline = {"bound": "hbm", "kernel": ("search_kernel" if args.layout == 1 else "search_compact_kernel") +
                                               "<CrossingEnv<1>,4,7,PHILOX>",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": _measured_traffic(args.layout, T, ITERATIONS),
+                    "peak_source": peak_src, "traffic": traffic,
                     "algorithmic_bytes_per_iteration": bytes_per_it, "mean_leaf_depth": mean_depth,
-                    # the same with SURVEY.md 8(d)'s two terms only (rollout + backup, no selection reads)
-                    "frac_rollout_and_backup_bytes_only":
-                        ((16 * A + 8 + 8) + 80 * A * mean_depth) * it_local / (search_kernel_ms * 1e-3) / 1e9 / peak,
+                    "dram_frac": (traffic / kern_s / 1e9 / peak) if traffic else None,
+                    "frac_with_selection_reads": bytes_per_it_sel * it_local / kern_s / 1e9 / peak,
+                    "algorithmic_bytes_per_iteration_with_selection_reads": bytes_per_it_sel,
                     "kernel_ms": search_kernel_ms,
-                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                                    "profiles/r01_traffic.json; null when this configuration was not captured)",
-                    "note": "one lane per tree, one randomly placed 256-B record per level; measured DRAM traffic "
-                            "(`traffic`) is below the algorithmic bytes because the roots stay in the L2 and a "
-                            "reward-free agent's values never move; random-record access tops out near 2.8 TB/s of "
-                            "DRAM traffic (profiles/r01_randrec_microbench.txt), not at the streaming peak; "
-                            "see DESIGN.md section 7"}
-        # ---- cpu baseline: the reference's own search on the host cores, bounded sample -----------
-        threads = os.cpu_count() or 1
-        cb = cpu_reference_search(threads, max(1, args.cpu_repeats))
-        cpu_baseline = {"value": cb["env_steps_per_s"], "unit": UNIT, "cores": threads, "kind": cb["kind"],
-                        "iterations_per_s": cb["iterations_per_s"],
-                        "sample": f"{cb['searches']} whole C2 searches ({ITERATIONS} iterations each) on "
-                                  f"{threads} host threads, {cb['seconds']:.1f} s"}
+                    "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of the "
+                                    "committed capture of this configuration, profiles/*_traffic.json; null when "
+                                    "this configuration was not captured)",
+                    "note": "frac = SURVEY.md 8(d) bytes (rollout in/out + backup read-modify-write) / kernel time / "
+                            "measured HBM copy bandwidth; dram_frac = measured DRAM bytes of the capture / this run's "
+                            "kernel time / the same peak. One lane per tree, one randomly placed 256-B record per "
+                            "level: random-record access tops out near 2.8 TB/s of DRAM traffic "
+                            "(profiles/r01_randrec_microbench.txt), not at the streaming peak; DESIGN.md section 7"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -469,10 +682,11 @@ def run_native(args):
             "nodes_per_decision": nodes,
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64,  # the int32[16] root-state vector mamcts_search_reset copies
-                    "d2h_bytes_per_step": 8 * (3 * nA + 3),
+                    "d2h_bytes_per_step": 8 * (3 * nA + 3), "iterations_per_s": e2e_its,
                     "api": "Search.reset(host root) + Search.run + Search.merge_roots -> best action",
                     "best_action": int(merged["best"])},
             "gpu_launches": int(launches),
+            "correctness_gate": gate_info,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
@@ -507,13 +721,17 @@ def run_native(args):
                         "note": "leaf value = mean of K Philox rollouts in a fixed order (DESIGN.md section 6); "
                                 "bit-equal to the oracle's K-rollout trees (tests/test_gpu_search.py)"}
         sk.close()
+    # ---- the sections every N carries: C5 (strong scaling) and C3 (rollouts sharded), after the trees are freed
+    c5 = measure_c5_strong(engine, stream, world, rank, dist) if not args.no_sections else None
+    c3 = measure_rollout_c3(engine, stream, world, rank, dist=dist if world > 1 else None) if not args.no_sections else None
     if rank == 0:
         line["leaf_batched"] = leaf_batched
-        # the batched rollout kernel on its own (C3), after the trees are freed
-        c3 = measure_rollout_c3(engine, stream)
-        # (the C3 decision time includes the reduction launch: a lower bound of the kernel's own rate)
-        c3["roofline_issue"] = _issue_roofline(_ncu_entry(kernel="rollout_kernel", workload="c3"),
-                                               c3["kernel_ms_estimate"], sm_mhz)
+        line["c5_strong"] = c5
+        if c3 is not None:
+            c3["roofline_issue"] = _issue_roofline(_ncu_entry(kernel="rollout_kernel", workload="c3"),
+                                                   c3["kernel_ms_estimate"], sm_mhz)
+            if cpu_baseline and "rollout_loop_a8" in cpu_baseline:
+                c3["cpu_rollout_loop_a8_env_steps_per_s"] = cpu_baseline["rollout_loop_a8"]["env_steps_per_s"]
         line["rollout_c3"] = c3
         print(json.dumps(line))
     if world > 1:
@@ -538,9 +756,10 @@ def main():
     ap.add_argument("--max-inner", type=int, default=3200,
                     help="compact layout: inner records per tree (0 = one per node); a 10 000-iteration C2 "
                          "tree needs 2 500 +- 76 (max 2 734 over 120 trees); a tree that runs out fails the run")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2 = the headline search benchmark (default, includes a C3 rollout-kernel section); "
-                         "c3 = only the batched rollout kernel (profiling)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = the headline search benchmark (default; carries the c5_strong and rollout_c3 sections); "
+                         "c3 / c5 = only that section (profiling)")
+    ap.add_argument("--no-sections", action="store_true", help="c2 only: skip the c5_strong and rollout_c3 sections")
     ap.add_argument("--leaf-batch", type=int, default=4,
                     help="also time the search with this many rollouts per new leaf (N = 1 only; 1 = skip)")
     ap.add_argument("--iterations", type=int, default=ITERATIONS,

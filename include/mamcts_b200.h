@@ -344,6 +344,18 @@ int mamcts_root_merge(mamcts_engine* e, const mamcts_uct_stats* stats, uint32_t 
                       uint64_t* merged_total_visits, double* merged_value,
                       uint32_t* best_action);
 
+/* ---- one decision, many rollouts (BASELINE configs[2]): the exchange step ------------------------ */
+
+/* {sum, sum of squares} of the per-rollout returns of every agent, then the rollout count:
+ * moments[2*a], moments[2*a+1] for agent position a (0 = ego_return[n], a > 0 = other_return[(a-1)*n ..]),
+ * moments[2*(num_others+1)] = n. Reduced on the device in a fixed order, then all-reduced over the
+ * engine's communicator when one is attached (one ncclAllReduce of 2A+1 doubles per decision,
+ * SURVEY.md 8e; the reference has no counterpart - it runs one rollout per leaf, mcts/mcts.h:310).
+ * mem = where ego_return / other_return AND moments live. */
+int mamcts_rollout_moments(mamcts_engine* e, int32_t mem, const double* ego_return,
+                           const double* other_return, uint32_t num_others, uint32_t n,
+                           double* moments);
+
 /* ---- NCCL communicator over the GPUs of one host (NVLink 5 / NVSwitch) -------------------- */
 
 #define MAMCTS_NCCL_UNIQUE_ID_BYTES 128

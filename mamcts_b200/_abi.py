@@ -266,6 +266,7 @@ def load() -> C.CDLL:
             [vp, P(UctStats), u32, i32, vp, u32, c_double_p, c_u64_p, c_u32_p, c_u64_p, c_double_p,
              c_u32_p],
         ),
+        "mamcts_rollout_moments": (i32, [vp, i32, vp, vp, u32, u32, vp]),
         "mamcts_comm_get_unique_id": (i32, [vp, c_u8_p]),
         "mamcts_comm_init_rank": (i32, [vp, c_u8_p, i32, i32]),
         "mamcts_comm_destroy": (i32, [vp]),
@@ -297,7 +298,7 @@ EXPORTED_SYMBOLS = [
     "mamcts_default_params", "mamcts_default_crossing_params", "mamcts_default_simple_params",
     "mamcts_reference_expand_order", "mamcts_rollout_crossing_i32", "mamcts_rollout_simple",
     "mamcts_rollout_crossing_f32", "mamcts_default_crossing_params_f32",
-    "mamcts_backup_uct", "mamcts_backup_hypothesis", "mamcts_root_merge", "mamcts_comm_get_unique_id",
+    "mamcts_backup_uct", "mamcts_backup_hypothesis", "mamcts_root_merge", "mamcts_rollout_moments", "mamcts_comm_get_unique_id",
     "mamcts_comm_init_rank", "mamcts_comm_destroy", "mamcts_allreduce_f64",
     "mamcts_search_create", "mamcts_search_destroy", "mamcts_search_reset", "mamcts_search_run",
     "mamcts_search_counters", "mamcts_search_exact_ucb_evaluations", "mamcts_search_root_stats", "mamcts_search_merge_roots",

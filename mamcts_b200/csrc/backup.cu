@@ -4,16 +4,12 @@
 //   sequential recurrence along the path (reference mcts/mcts.h:309-329,
 //   mcts/statistics/uct_statistic.h:100-110,134-144), so A adjacent lanes walk one path together
 //   and read the edge records coalesced.
-// root_merge_kernel : fixed-order block reduction of the local trees' ego root statistics into
-//   {sum_q[a], sum_n[a], occ[a], sum_visits} (reference uct_statistic.h:165-184); one
-//   ncclAllReduce of those 3*nA+1 doubles when a communicator is attached; root_finish_kernel
-//   divides and picks the best action (uct_statistic.h:78-89).
+// (The root-parallel merge, reference uct_statistic.h:165-184, lives in reduce.cu.)
 #include <algorithm>
 #include <cstring>
 
 #include "engine.h"
 #include "staging.h"
-#include "root_merge.h"
 
 namespace mamcts {
 
@@ -157,114 +153,6 @@ __global__ void __launch_bounds__(256) backup_hypothesis_kernel(const __grid_con
   }
 }
 
-// ---- root merge -------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(1024)
-root_merge_kernel(RootGather g, uint32_t n_trees, uint32_t nA, double* __restrict__ acc) {
-  extern __shared__ double sm[];  // [blockDim.x]
-  const uint32_t tid = threadIdx.x;
-  for (uint32_t comp = 0; comp < 3 * nA + 1; ++comp) {
-    double part = 0.0;
-    for (uint32_t t = tid; t < n_trees; t += blockDim.x) {
-      size_t qbase, nbase, vbase;
-      if (g.root_slot) {
-        qbase = nbase = (size_t)g.root_slot[t] * g.max_actions;
-        vbase = g.root_slot[t];
-      } else {
-        qbase = (size_t)t * g.stride_q;
-        nbase = (size_t)t * g.stride_n;
-        vbase = (size_t)t * g.stride_v;
-      }
-      auto count_at = [&](const void* ptr, size_t idx) -> uint32_t {
-        return g.count_bytes == 2 ? (uint32_t)static_cast<const uint16_t*>(ptr)[idx]
-                                  : static_cast<const uint32_t*>(ptr)[idx];
-      };
-      double v;
-      if (comp < nA) {
-        v = count_at(g.n, nbase + comp) ? g.q[qbase + comp] : 0.0;
-      } else if (comp < 2 * nA) {
-        v = (double)count_at(g.n, nbase + comp - nA);
-      } else if (comp < 3 * nA) {
-        v = count_at(g.n, nbase + comp - 2 * nA) ? 1.0 : 0.0;
-      } else {
-        v = (double)count_at(g.visits, vbase);
-      }
-      part = __dadd_rn(part, v);
-    }
-    sm[tid] = part;
-    __syncthreads();
-    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
-      if (tid < s) sm[tid] = __dadd_rn(sm[tid], sm[tid + s]);
-      __syncthreads();
-    }
-    if (tid == 0) acc[comp] = sm[0];
-    __syncthreads();
-  }
-}
-
-// out (doubles): [0,nA) merged q, [nA,2nA) merged n, [2nA,3nA) occurrences, [3nA] visits,
-// [3nA+1] value, [3nA+2] best action.  Reference uct_statistic.h:173-183 and :78-89.
-__global__ void root_finish_kernel(const double* __restrict__ acc, uint32_t nA, double* __restrict__ out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  double value = 0.0;
-  uint32_t present = 0;
-  double best_q = 0.0;
-  uint32_t best = 0;
-  bool first = true;
-  for (uint32_t a = 0; a < nA; ++a) {
-    const double occ = acc[2 * nA + a];
-    double q = 0.0;
-    if (occ > 0.0) {
-      q = acc[a] / occ;
-      value = __dadd_rn(value, q);
-      present += 1;
-      if (first) { best_q = q; best = a; first = false; }
-      else if (q > best_q) { best_q = q; best = a; }
-    }
-    out[a] = q;
-    out[nA + a] = acc[nA + a];
-    out[2 * nA + a] = occ;
-  }
-  out[3 * nA] = acc[3 * nA];
-  out[3 * nA + 1] = present ? value / (double)present : 0.0;
-  out[3 * nA + 2] = (double)best;
-}
-
-// Shared by mamcts_root_merge and mamcts_search_merge_roots (search.cu).
-int root_merge_device(mamcts_engine* e, const RootGather& g, uint32_t n_trees, uint32_t nA,
-                      double* merged_q, uint64_t* merged_n, uint32_t* merged_occ,
-                      uint64_t* merged_total_visits, double* merged_value, uint32_t* best_action) {
-  if (nA == 0 || nA > MAMCTS_MAX_ACTIONS) return fail(e, MAMCTS_ERR_INVALID, "root merge: bad num_actions");
-  const size_t nacc = 3 * (size_t)nA + 1, nout = 3 * (size_t)nA + 3;
-  int rc = ensure_scratch(e, sizeof(double) * (nacc + nout));
-  if (rc != MAMCTS_OK) return rc;
-  double* acc = static_cast<double*>(e->scratch);
-  double* out = acc + nacc;
-  const int threads = n_trees >= 1024 ? 1024 : (n_trees > 32 ? 256 : 32);
-  root_merge_kernel<<<1, threads, threads * sizeof(double), e->stream>>>(g, n_trees, nA, acc);
-  e->launches++;
-  MAMCTS_CUDA(e, cudaGetLastError());
-  if (e->nccl_comm) {
-    rc = mamcts_allreduce_f64(e, acc, nacc);  // one all-reduce per decision
-    if (rc != MAMCTS_OK) return rc;
-  }
-  root_finish_kernel<<<1, 32, 0, e->stream>>>(acc, nA, out);
-  e->launches++;
-  MAMCTS_CUDA(e, cudaGetLastError());
-  double host[3 * MAMCTS_MAX_ACTIONS + 3];
-  MAMCTS_CUDA(e, cudaMemcpyAsync(host, out, sizeof(double) * nout, cudaMemcpyDeviceToHost, e->stream));
-  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
-  for (uint32_t a = 0; a < nA; ++a) {
-    if (merged_q) merged_q[a] = host[a];
-    if (merged_n) merged_n[a] = (uint64_t)host[nA + a];
-    if (merged_occ) merged_occ[a] = (uint32_t)host[2 * nA + a];
-  }
-  if (merged_total_visits) *merged_total_visits = (uint64_t)host[3 * nA];
-  if (merged_value) *merged_value = host[3 * nA + 1];
-  if (best_action) *best_action = (uint32_t)host[3 * nA + 2];
-  return MAMCTS_OK;
-}
-
 }  // namespace mamcts
 
 using namespace mamcts;
@@ -299,6 +187,15 @@ int mamcts_backup_uct(mamcts_engine* e, const mamcts_params* mp, uint32_t num_ag
   }
   if (mem == MAMCTS_MEM_HOST && n_edges > 0 && (!edge_node || !edge_action || !edge_reward))
     return fail(e, MAMCTS_ERR_INVALID, "mamcts_backup_uct: null edge arrays");
+  if (mem == MAMCTS_MEM_HOST) {
+    for (size_t i = 0; i < n_edges; ++i) {
+      if ((size_t)edge_node[i] * num_agents >= stats->num_slots)
+        return fail(e, MAMCTS_ERR_INVALID, "mamcts_backup_uct: edge node out of range");
+      for (uint32_t a = 0; a < num_agents; ++a)
+        if (edge_action[i * num_agents + a] >= stats->max_actions)
+          return fail(e, MAMCTS_ERR_INVALID, "mamcts_backup_uct: action index out of range");
+    }
+  }
   const size_t A = num_agents, S = stats->num_slots, MA = stats->max_actions;
   ArgStager stg(e);
   const int t_leaf = stg.plan(leaf_node, sizeof(uint32_t) * n_paths, mem, false);
@@ -439,36 +336,6 @@ int mamcts_backup_hypothesis(mamcts_engine* e, const mamcts_params* mp, uint32_t
     MAMCTS_CUDA(e, cudaMemcpyAsync(stats->action_count, p.a_count, sizeof(uint32_t) * S * H * MA, cudaMemcpyDeviceToHost, e->stream));
   }
   return stg.finish();
-}
-
-int mamcts_root_merge(mamcts_engine* e, const mamcts_uct_stats* stats, uint32_t n_trees,
-                      int32_t mem, const uint32_t* root_slot, uint32_t num_actions,
-                      double* merged_q, uint64_t* merged_n, uint32_t* merged_occurrences,
-                      uint64_t* merged_total_visits, double* merged_value,
-                      uint32_t* best_action) {
-  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_root_merge: null engine");
-  std::lock_guard<std::mutex> lock(e->mu);
-  if (!stats || !root_slot || n_trees == 0) return fail(e, MAMCTS_ERR_INVALID, "mamcts_root_merge: null argument");
-  if (num_actions > stats->max_actions) return fail(e, MAMCTS_ERR_INVALID, "mamcts_root_merge: num_actions > max_actions");
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  const size_t S = stats->num_slots, MA = stats->max_actions;
-  ArgStager stg(e);
-  const int t_slot = stg.plan(root_slot, sizeof(uint32_t) * n_trees, mem, false);
-  const int s_vis = stg.plan(stats->total_visits, sizeof(uint32_t) * S, stats->mem, false);
-  const int s_q = stg.plan(stats->q, sizeof(double) * S * MA, stats->mem, false);
-  const int s_n = stg.plan(stats->n, sizeof(uint32_t) * S * MA, stats->mem, false);
-  int rc = stg.commit();
-  if (rc != MAMCTS_OK) return rc;
-  RootGather g;
-  std::memset(&g, 0, sizeof(g));
-  g.q = stg.dev<const double>(s_q);
-  g.n = stg.dev<const uint32_t>(s_n);
-  g.visits = stg.dev<const uint32_t>(s_vis);
-  g.count_bytes = 4;
-  g.root_slot = stg.dev<const uint32_t>(t_slot);
-  g.max_actions = stats->max_actions;
-  return root_merge_device(e, g, n_trees, num_actions, merged_q, merged_n, merged_occurrences,
-                           merged_total_visits, merged_value, best_action);
 }
 
 }  // extern "C"

@@ -19,7 +19,10 @@ void set_global_error(const std::string& msg) {
 }
 
 int fail(mamcts_engine* e, int code, const std::string& msg) {
-  if (e) e->last_error = msg;
+  if (e) {
+    std::lock_guard<std::mutex> lock(e->err_mu);
+    e->last_error = msg;
+  }
   set_global_error(msg);
   return code;
 }
@@ -114,9 +117,10 @@ int mamcts_create(const mamcts_config* cfg, mamcts_engine** out) {
     return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_create: device ordinal out of range");
   mamcts_engine* e = new mamcts_engine();
   e->device = cfg->device;
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
   cudaDeviceProp prop;
-  MAMCTS_CUDA(e, cudaGetDeviceProperties(&prop, e->device));
+  err = cudaSetDevice(e->device);
+  if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, e->device);
+  if (err != cudaSuccess) { int rc = cuda_fail(nullptr, err, "mamcts_create: cudaSetDevice / cudaGetDeviceProperties"); delete e; return rc; }
   e->num_sms = prop.multiProcessorCount;
   if (prop.major < 10) {
     std::string msg = "mamcts_create: device " + std::string(prop.name) +
@@ -146,8 +150,14 @@ void mamcts_destroy(mamcts_engine* e) {
 }
 
 const char* mamcts_last_error(const mamcts_engine* e) {
-  if (e) return e->last_error.c_str();
+  // a per-thread copy: the engine may be shared by several host threads, one of which may fail while another reads
   static thread_local std::string copy;
+  if (e) {
+    mamcts_engine* m = const_cast<mamcts_engine*>(e);
+    std::lock_guard<std::mutex> lock(m->err_mu);
+    copy = m->last_error;
+    return copy.c_str();
+  }
   std::lock_guard<std::mutex> lock(g_err_mu);
   copy = g_last_error;
   return copy.c_str();

@@ -14,6 +14,7 @@ struct mamcts_engine {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::mutex mu;  // calls on one engine are serialised (SURVEY.md §8b threading)
+  std::mutex err_mu;   // guards last_error alone (fail() runs with or without `mu` held)
   std::string last_error;
   uint64_t launches = 0;
   // staging / scratch (grow-only)

@@ -551,7 +551,10 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   s->e = e;
   s->cfg = *cfg;
   s->A = A;
-  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  {
+    const cudaError_t derr = cudaSetDevice(e->device);
+    if (derr != cudaSuccess) { delete s; return cuda_fail(e, derr, "mamcts_search_create: cudaSetDevice"); }
+  }
 
   // host tables: widening order (libstdc++), expanded masks, widening thresholds (libm pow), log table
   SearchTables& tab = s->tab;
@@ -560,7 +563,7 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   for (int cls = 0; cls < 2; ++cls) {
     uint32_t order[MAMCTS_MAX_ACTIONS];
     int rc = mamcts_reference_expand_order(mp.random_seed, nact[cls], order);
-    if (rc != MAMCTS_OK) { delete s; return rc; }
+    if (rc != MAMCTS_OK) { delete s; return fail(e, rc, mamcts_last_error(nullptr)); }   // the message of the failing call
     uint32_t mask = 0;
     tab.exp_mask[cls][0] = 0;
     for (uint32_t k = 0; k < nact[cls]; ++k) {

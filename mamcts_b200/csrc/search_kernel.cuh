@@ -188,12 +188,14 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   // agents of CrossingState): with bound estimation the normalised value is the same for every action
   // (0 when the common value is 0, else exactly q / q = 1), so the UCB score is
   // norm + fl(2c * fl(sqrt(fl(2 ln N / n_a)))), a non-increasing function of n_a. It is STRICTLY
-  // decreasing under the conditions checked here - N >= 2 (2 ln N >= 1.38), 2c >= 0.01, n_a <= 2^20: two
+  // decreasing under the conditions checked here - N >= 2 (2 ln N >= 1.38), 0.01 <= 2c <= 1e6 (every bonus
+  // finite: with a huge exploration constant all bonuses overflow to +inf, the scores tie and the
+  // reference's strict > keeps the FIRST expanded index, not the least visited), n_a <= 2^20: two
   // counts differ by a factor >= 1 + 2^-20, their bonuses by a relative 4.7e-7 and an absolute
   // >= 5e-12 * max(1, bonus), far beyond the four roundings (1.1e-16 relative each) and the ulp of the
   // sum - and every score exceeds DBL_MIN, the initial maximum of the reference's loop. So the first
   // maximum of the exact scores is the first minimum of the counts; no floating-point work is needed.
-  if (p.use_bound_est && N >= 2u && N <= (1u << 20) && p.two_c >= 0.01) {   // every n_a <= N
+  if (p.use_bound_est && N >= 2u && N <= (1u << 20) && p.two_c >= 0.01 && p.two_c <= 1e6) {   // every n_a <= N
     long long q_first = 0;
     bool first = true, same = true;
     if (!values_known_equal) {
@@ -254,7 +256,9 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   // rounded reciprocal and square root per statistic and one MUFU.RSQ (<= 2 ulp) per action:
   //   norm  = float(q - lo) * rcp(float(range))                     |error| <= 4 u          (u = 2^-24)
   //   bonus = (float(2c) * sqrt(2 * logf(N))) * rsqrt(float(n))     |error| <= 11 u * bonus
-  //           (__logf: <= 3 ulp = 6 u for N >= 2, halved by the square root; the host's exact
+  //           (__logf: absolute error <= 2^-21.41 on [0.5, 2] and <= 2 ulp elsewhere (CUDA C Programming Guide);
+  //            the screen only runs for N >= 3, where ln N >= 1.09 makes that <= 3 ulp = 6 u relative,
+  //            halved by the square root; N = 2 goes to the exact evaluation; the host's exact
   //            log table is only read by the exact evaluation - a table lookup here would be one
   //            more dependent memory access on the critical path of every level)
   //   score = fma(...)                                              |error| <= 12 u * (score + 1)
@@ -276,7 +280,7 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
     const float csl = (float)p.two_c * __fsqrt_rn(2.0f * __logf((float)N));
     float sc[NACT];
     float best_sc = -1.0f;
-    ok = isfinite(rangef) && rangef != 0.0f;
+    ok = isfinite(rangef) && rangef != 0.0f && N >= 3u;
 #pragma unroll
     for (int a = 0; a < NACT; ++a) {
       sc[a] = -2.0f;

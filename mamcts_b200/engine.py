@@ -135,6 +135,36 @@ class Engine:
             self.device_free(d)
         return out
 
+    def rollout_moments(self, ego_return, other_return, num_others: int = None, n: int = None, d_out: int = 0):
+        """{sum, sum of squares} per agent + count of per-rollout returns (C3's exchange step), reduced on the
+        device and all-reduced over the engine's communicator (mamcts_rollout_moments). numpy arrays = HOST
+        buffers ([n] and [A-1, n]), result returned as numpy; ints = device pointers (num_others and n
+        required): with d_out (device, 2A+1 doubles) the call is asynchronous on the engine stream and returns
+        None, without it the result is copied back."""
+        if isinstance(ego_return, np.ndarray):
+            ego = np.ascontiguousarray(ego_return, dtype=np.float64)
+            oth = None if other_return is None else np.ascontiguousarray(other_return, dtype=np.float64)
+            n = ego.shape[0]
+            num_others = 0 if oth is None else oth.reshape(-1, n).shape[0]
+            out = np.zeros(2 * (num_others + 1) + 1)
+            self._check(self.lib.mamcts_rollout_moments(self.h, MEM_HOST, _vp(ego), _vp(oth), num_others, n, _vp(out)),
+                        "mamcts_rollout_moments")
+            return out
+        nacc = 2 * (num_others + 1) + 1
+        d = d_out or self.device_alloc(8 * nacc)
+        try:
+            self._check(self.lib.mamcts_rollout_moments(self.h, MEM_DEVICE, _vp(ego_return), _vp(other_return or None),
+                                                        num_others, n, C.c_void_p(d)), "mamcts_rollout_moments")
+            if d_out:
+                return None
+            out = np.zeros(nacc)
+            self.d2h(out, d)
+            self.sync()
+        finally:
+            if not d_out:
+                self.device_free(d)
+        return out
+
     # -- rollouts -----------------------------------------------------------------------------
     @staticmethod
     def _source(kind, A, replay_actions=None, replay_steps=None, const_actions=None, seed=0,

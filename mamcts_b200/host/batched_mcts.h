@@ -43,12 +43,17 @@ class BatchedRootParallelMcts {
   // USE_MULTI_THREADING (mcts.h:198-210) - including its caveat: StageNode::num_nodes_ is one static
   // counter shared by all trees (stage_node.h:77), so node ids and the MAX_NUMBER_OF_NODES cut-off are
   // only exact with host_threads = 1. Statistics of different trees never alias.
+  // env_parameters: the environment's parameters in the C ABI's form (CudaState<S>::to_params(...)); nullptr =
+  // whatever is registered with CudaState<S>::set_parameters at the time of each search().
   BatchedRootParallelMcts(const MctsParameters& mcts_parameters, unsigned num_trees,
                           uint64_t philox_seed = 1000, unsigned first_tree_id = 0,
-                          unsigned rollouts_per_leaf = 1, unsigned host_threads = 1)
+                          unsigned rollouts_per_leaf = 1, unsigned host_threads = 1,
+                          const typename CudaState<S>::EnvParams* env_parameters = nullptr)
       : mcts_parameters_(mcts_parameters), num_trees_(num_trees), philox_seed_(philox_seed),
         first_tree_id_(first_tree_id), K_(rollouts_per_leaf), num_iterations_(0), rollout_steps_(0),
-        host_threads_(host_threads ? host_threads : std::max(1u, std::thread::hardware_concurrency())) {
+        host_threads_(host_threads ? host_threads : std::max(1u, std::thread::hardware_concurrency())),
+        own_env_(env_parameters != nullptr) {
+    if (env_parameters) env_ = *env_parameters;
     CudaEngine::get();
   }
 
@@ -56,6 +61,8 @@ class BatchedRootParallelMcts {
   // NB StageNode::num_nodes_ is one static counter per instantiation (stage_node.h:77): as in the
   // reference's parallel_search, MAX_NUMBER_OF_NODES is a budget over ALL trees.
   void search(const S& current_state) {
+    if (!own_env_) env_ = CudaState<S>::params();
+    CudaState<S>::check_state(current_state, env_);
     Node::reset_counter();
     roots_.clear();
     calls_.assign(num_trees_, 0);
@@ -133,12 +140,12 @@ class BatchedRootParallelMcts {
       uint64_t steps = 0;
       out.total_steps = &steps;
       if constexpr (CS::kEnv == MAMCTS_ENV_CROSSING_I32) {
-        CudaEngine::check(mamcts_rollout_crossing_i32(CudaEngine::get(), &mp, &CS::params(), n, K_,
+        CudaEngine::check(mamcts_rollout_crossing_i32(CudaEngine::get(), &mp, &env_, n, K_,
                                                       MAMCTS_MEM_HOST, x.data(), last.data(), flags.data(),
                                                       depth.data(), &src, &out),
                           "mamcts_rollout_crossing_i32");
       } else {
-        CudaEngine::check(mamcts_rollout_simple(CudaEngine::get(), &mp, &CS::params(), n, K_, MAMCTS_MEM_HOST,
+        CudaEngine::check(mamcts_rollout_simple(CudaEngine::get(), &mp, &env_, n, K_, MAMCTS_MEM_HOST,
                                                 x.data(), depth.data(), &src, &out),
                           "mamcts_rollout_simple");
       }
@@ -211,6 +218,8 @@ class BatchedRootParallelMcts {
   unsigned num_iterations_;
   uint64_t rollout_steps_;
   unsigned host_threads_;
+  bool own_env_;
+  typename CudaState<S>::EnvParams env_{};
   std::vector<NodePtr> roots_;
   std::vector<uint32_t> calls_;
 };

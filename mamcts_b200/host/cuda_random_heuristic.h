@@ -139,6 +139,7 @@ class CudaRandomHeuristic : public mcts::Heuristic<CudaRandomHeuristic> {
     const uint32_t A = CS::num_agents(state);
     int32_t x[MAMCTS_MAX_AGENTS] = {0}, last[MAMCTS_MAX_AGENTS] = {0};
     uint8_t flags = 0;
+    CS::check_state(state, CS::params());   // throws if set_parameters() was never called or does not fit
     CS::pack(state, x, last, &flags);
     const uint32_t depth = current_depth;
 

@@ -29,14 +29,28 @@ struct CudaState;  // specialise per environment
 template <>
 struct CudaState<CrossingState<int>> {
   static constexpr int kEnv = MAMCTS_ENV_CROSSING_I32;
-  // CrossingState keeps its parameters private (crossing_state.h:320); the host registers the same
-  // CrossingStateParameters<int> object it built its states from, once per process.
-  static mamcts_crossing_params& params() {
+  using EnvParams = mamcts_crossing_params;
+  // CrossingState keeps its parameters private (crossing_state.h:320), and the reference's Mcts<> constructs
+  // its heuristic from MctsParameters alone (mcts.h:43-48), so the host registers the same
+  // CrossingStateParameters<int> object it built its states from. There is no silent default: params()
+  // throws until set_parameters() was called, and pack() checks everything a state lets it check (number
+  // of other agents, action counts) against the registered parameters. The drivers that own their
+  // configuration (DeviceRootParallelMcts, BatchedRootParallelMcts) also take the parameters in their
+  // constructor and re-create the device search when they change.
+  static bool& registered() { static bool r = false; return r; }
+  static mamcts_crossing_params& storage() {
     static mamcts_crossing_params p = [] { mamcts_crossing_params d; mamcts_default_crossing_params(&d); return d; }();
     return p;
   }
-  static void set_parameters(const CrossingStateParameters<int>& c) {
-    mamcts_crossing_params& p = params();
+  static mamcts_crossing_params& params() {
+    if (!registered())
+      throw std::logic_error("CudaState<CrossingState<int>>: call set_parameters(CrossingStateParameters<int>) with the "
+                             "parameters the states were built from before using the CUDA engine");
+    return storage();
+  }
+  static mamcts_crossing_params to_params(const CrossingStateParameters<int>& c) {
+    mamcts_crossing_params p;
+    mamcts_default_crossing_params(&p);
     p.num_other_agents = c.NUM_OTHER_AGENTS;
     p.num_other_actions = c.NUM_OTHER_ACTIONS;
     p.cost_only_collision = c.COST_ONLY_COLLISION ? 1 : 0;
@@ -49,6 +63,21 @@ struct CudaState<CrossingState<int>> {
     p.reward_collision = c.REWARD_COLLISION;
     p.reward_goal_reached = c.REWARD_GOAL_REACHED;
     p.reward_step = c.REWARD_STEP;
+    return p;
+  }
+  static void set_parameters(const CrossingStateParameters<int>& c) {
+    storage() = to_params(c);
+    registered() = true;
+  }
+  // what a state reveals about its parameters must agree with `p`
+  static void check_state(const CrossingState<int>& s, const mamcts_crossing_params& p) {
+    if (s.get_agent_states().size() != p.num_other_agents)
+      throw std::logic_error("CudaState<CrossingState<int>>: the registered parameters do not match the state (other agents)");
+    if ((int64_t)s.get_num_actions(s.get_ego_agent_idx()) != (int64_t)p.max_velocity_ego - p.min_velocity_ego + 1)
+      throw std::logic_error("CudaState<CrossingState<int>>: the registered parameters do not match the state (ego actions)");
+    const std::vector<AgentIdx> others = s.get_other_agent_idx();
+    if (!others.empty() && s.get_num_actions(others[0]) != p.num_other_actions)
+      throw std::logic_error("CudaState<CrossingState<int>>: the registered parameters do not match the state (other actions)");
   }
   // Behaviour hypotheses (MAMCTS_SRC_HYPOTHESIS): CrossingState keeps its AgentPolicyCrossingState
   // objects private (crossing_state.h:313) and a policy hides its desired-gap range
@@ -73,8 +102,6 @@ struct CudaState<CrossingState<int>> {
   static uint32_t num_agents(const CrossingState<int>& s) { return s.get_num_agents(); }
   // x / last: [A] positional; flags bit0 = terminal
   static void pack(const CrossingState<int>& s, int32_t* x, int32_t* last, uint8_t* flags) {
-    if (s.get_agent_states().size() != params().num_other_agents)
-      throw std::logic_error("CudaState<CrossingState<int>>: set_parameters() does not match the state");
     x[0] = s.get_ego_state().x_pos;
     last[0] = s.get_ego_state().last_action;
     const auto& others = s.get_agent_states();
@@ -92,6 +119,8 @@ struct CudaState<CrossingState<int>> {
 template <>
 struct CudaState<SimpleState> {
   static constexpr int kEnv = MAMCTS_ENV_SIMPLE;
+  using EnvParams = mamcts_simple_params;
+  static void check_state(const SimpleState&, const mamcts_simple_params&) {}
   static mamcts_simple_params& params() {
     static mamcts_simple_params p = [] { mamcts_simple_params d; mamcts_default_simple_params(&d); return d; }();
     return p;

@@ -23,6 +23,7 @@
 #include <iomanip>
 #include <map>
 #include <sstream>
+#include <stdexcept>
 #include <string>
 #include <utility>
 #include <cmath>
@@ -46,13 +47,21 @@ class DeviceRootParallelMcts {
     std::map<ActionIdx, std::pair<unsigned, double>> ucb_statistics;  // action -> (action_count_, action_value_)
   };
 
+  // env_parameters: the environment's parameters in the C ABI's form (CudaState<S>::to_params(...)); nullptr =
+  // whatever is registered with CudaState<S>::set_parameters at the time of each search(). Either way the
+  // device search is re-created when the parameters (or the shape of the state) differ from the ones it was
+  // created with - a later set_parameters() is never silently ignored.
   DeviceRootParallelMcts(const MctsParameters& mcts_parameters, unsigned num_trees, uint64_t philox_seed = 1000,
                          unsigned first_tree_id = 0, int action_source = MAMCTS_SRC_PHILOX,
-                         unsigned max_inner_nodes_per_tree = 0, unsigned rollouts_per_leaf = 1)
+                         unsigned max_inner_nodes_per_tree = 0, unsigned rollouts_per_leaf = 1,
+                         const typename CudaState<S>::EnvParams* env_parameters = nullptr)
       : mcts_parameters_(mcts_parameters), num_trees_(num_trees), philox_seed_(philox_seed),
         first_tree_id_(first_tree_id), action_source_(action_source), max_inner_(max_inner_nodes_per_tree),
         rollouts_per_leaf_(rollouts_per_leaf),
-        search_(nullptr), num_iterations_(0), search_time_(0), merged_valid_(false) {
+        search_(nullptr), num_iterations_(0), search_time_(0), merged_valid_(false),
+        own_env_(env_parameters != nullptr) {
+    std::memset(&created_env_, 0, sizeof(created_env_));
+    if (env_parameters) env_ = *env_parameters;
     CudaEngine::get();
   }
   ~DeviceRootParallelMcts() { if (search_) mamcts_search_destroy(search_); }
@@ -66,7 +75,19 @@ class DeviceRootParallelMcts {
     const auto start = std::chrono::high_resolution_clock::now();
     int32_t x[MAMCTS_MAX_AGENTS] = {0}, last[MAMCTS_MAX_AGENTS] = {0};
     uint8_t flags = 0;
+    if (!own_env_) env_ = CS::params();
+    CS::check_state(current_state, env_);
     CS::pack(current_state, x, last, &flags);
+    if (flags & 1u) {
+      // the reference returns from select_or_expand without expanding a terminal root (stage_node.h:183-187):
+      // there is nothing to search and no best action to report
+      merged_valid_ = false;
+      throw std::logic_error("DeviceRootParallelMcts::search: the state is terminal");
+    }
+    if (search_ && std::memcmp(&created_env_, &env_, sizeof(env_)) != 0) {   // parameters changed since creation
+      mamcts_search_destroy(search_);
+      search_ = nullptr;
+    }
     num_agents_ = CS::num_agents(current_state);
     num_ego_actions_ = (unsigned)current_state.get_num_actions(current_state.get_ego_agent_idx());
     agent_ids_.assign(1, current_state.get_ego_agent_idx());
@@ -89,6 +110,7 @@ class DeviceRootParallelMcts {
       cfg.mcts = to_mamcts_params(mcts_parameters_);
       fill_env(cfg);
       CudaEngine::check(mamcts_search_create(CudaEngine::get(), &cfg, x, last, &search_), "mamcts_search_create");
+      created_env_ = env_;
     } else {
       CudaEngine::check(mamcts_search_reset(search_, x, last), "mamcts_search_reset");
     }
@@ -217,8 +239,8 @@ class DeviceRootParallelMcts {
     merged_valid_ = true;
   }
   void fill_env(mamcts_search_config& cfg) {
-    if constexpr (CudaState<S>::kEnv == MAMCTS_ENV_CROSSING_I32) cfg.crossing = CudaState<S>::params();
-    else cfg.simple = CudaState<S>::params();
+    if constexpr (CudaState<S>::kEnv == MAMCTS_ENV_CROSSING_I32) cfg.crossing = env_;
+    else cfg.simple = env_;
   }
 
   const MctsParameters mcts_parameters_;
@@ -234,6 +256,8 @@ class DeviceRootParallelMcts {
   std::vector<AgentIdx> agent_ids_;      // positional: ego, then get_other_agent_idx() order
   std::vector<unsigned> num_actions_;
   bool merged_valid_;
+  bool own_env_;
+  typename CudaState<S>::EnvParams env_{}, created_env_{};
   double merged_q_[MAMCTS_MAX_ACTIONS] = {0.0}, merged_value_ = 0.0;
   uint64_t merged_n_[MAMCTS_MAX_ACTIONS] = {0}, merged_visits_ = 0;
   uint32_t merged_occ_[MAMCTS_MAX_ACTIONS] = {0}, merged_best_ = 0;

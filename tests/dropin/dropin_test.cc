@@ -418,6 +418,69 @@ int main() {
       CHECK_MSG(ok, "device_mcts_simple_state_20_iterations");
     }
   }
+  {  // 8. NON-DEFAULT environment parameters (other rewards, chain length, goal, velocity range): the device
+     //    search follows them - through the constructor or through a later set_parameters() - and is never
+     //    left simulating the parameters it was first created with; a terminal root is refused.
+    CrossingStateParameters<int> cp = default_crossing_state_parameters<int>();
+    cp.NUM_OTHER_AGENTS = 1;
+    cp.CHAIN_LENGTH = 41;
+    cp.EGO_GOAL_POS = 26;
+    cp.REWARD_COLLISION = -300;
+    cp.REWARD_GOAL_REACHED = 77;
+    cp.REWARD_STEP = -1;
+    cp.MAX_VELOCITY_EGO = 3;          // 5 ego actions
+    std::unordered_map<AgentIdx, HypothesisId> hyp{{1, 0}};
+    CrossingState<int> state(hyp, cp);
+    const MctsParameters p = test_params(700);
+    CudaState<CrossingState<int>>::set_parameters(cp);
+    Mcts<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic> ref(p);
+    ref.search(state);
+    auto same_root = [&](DeviceRootParallelMcts<CrossingState<int>>& dev) {
+      double v, g; unsigned n;
+      std::map<ActionIdx, std::pair<unsigned, double>> ucb;
+      UctTest::read(ref.get_root().get_ego_int_node(), &v, &g, &n, &ucb);
+      const auto d = dev.get_root_statistic(1, 0);
+      bool ok = n == d.total_node_visits && std::memcmp(&v, &d.value, sizeof(double)) == 0 && ucb.size() == d.ucb_statistics.size() &&
+                dev.returnBestAction() == ref.returnBestAction();
+      for (const auto& kv : ucb) {
+        auto it = d.ucb_statistics.find(kv.first);
+        ok = ok && it != d.ucb_statistics.end() && it->second.first == kv.second.first &&
+             std::memcmp(&it->second.second, &kv.second.second, sizeof(double)) == 0;
+      }
+      return ok;
+    };
+    {
+      // created under the DEFAULT parameters first, then the parameters change: the search is re-created
+      CrossingFixture fx(1);   // registers the defaults
+      DeviceRootParallelMcts<CrossingState<int>> dev(p, 2, 0, 0, MAMCTS_SRC_REFERENCE_CONST);
+      auto st0 = fx.state();
+      dev.search(st0);
+      CudaState<CrossingState<int>>::set_parameters(cp);
+      dev.search(state);
+      const bool ok_global = same_root(dev);
+      // parameters handed to the constructor win over whatever is registered globally
+      CrossingFixture fx2(1);  // registers the defaults again
+      const mamcts_crossing_params env = CudaState<CrossingState<int>>::to_params(cp);
+      DeviceRootParallelMcts<CrossingState<int>> dev2(p, 2, 0, 0, MAMCTS_SRC_REFERENCE_CONST, 0, 1, &env);
+      dev2.search(state);
+      CHECK_MSG(ok_global && same_root(dev2), "device_mcts_non_default_parameters_follow_the_state");
+      // a state that does not fit the registered parameters is refused, never simulated under the wrong ones
+      bool threw = false;
+      try { DeviceRootParallelMcts<CrossingState<int>> dev3(p, 2, 0, 0, MAMCTS_SRC_REFERENCE_CONST); dev3.search(state); }
+      catch (const std::logic_error&) { threw = true; }
+      CHECK_MSG(threw, "device_mcts_mismatching_parameters_are_refused");
+    }
+    {  // terminal root (ego already past the goal): the reference does not expand it (stage_node.h:183-187)
+      CudaState<CrossingState<int>>::set_parameters(cp);
+      std::vector<Reward> rewards; EgoCosts cost;
+      std::shared_ptr<CrossingState<int>> s = std::make_shared<CrossingState<int>>(state);
+      for (int k = 0; k < 40 && !s->is_terminal(); ++k) s = s->execute(JointAction{4, 0}, rewards, cost);
+      bool threw = false;
+      try { DeviceRootParallelMcts<CrossingState<int>> dev(p, 2, 0, 0, MAMCTS_SRC_REFERENCE_CONST); dev.search(*s); }
+      catch (const std::logic_error&) { threw = true; }
+      CHECK_MSG(s->is_terminal() && threw, "device_mcts_terminal_root_is_refused");
+    }
+  }
   std::printf("%s (%d failed)\n", g_failures ? "DROPIN FAILED" : "DROPIN OK", g_failures);
   return g_failures;
 }

@@ -47,7 +47,9 @@ def test_reference_mcts_with_cuda_heuristic_and_statistic_is_bit_equal():
                  "philox_simple_tree_backprop_invariant", "philox_simple_tree_backprop_invariant_cuda_statistic",
                  "device_mcts_reference_const_equals_stock_mcts", "device_mcts_dot_export_labels_equal_reference",
                  "device_mcts_philox_equals_host_trees",
-                 "device_mcts_simple_state_20_iterations"):
+                 "device_mcts_simple_state_20_iterations",
+                 "device_mcts_non_default_parameters_follow_the_state",
+                 "device_mcts_mismatching_parameters_are_refused", "device_mcts_terminal_root_is_refused"):
         assert f"PASS {name}" in out, f"{name} did not pass:\n{out[-4000:]}"
 
 

@@ -142,6 +142,50 @@ def test_root_merge_matches_golden(engine):
         assert m["best"] == case["best"]
 
 
+def test_root_merge_many_trees_multi_block(engine):
+    """The multi-block warp-shuffle reduction (reduce.cu): 70 001 roots (274 blocks + a ragged tail), actions that
+    are missing in some trees, against the host statement of merge_node_statistics (sharding.local_partial /
+    finish); counts exact, sums of Q to rounding; two calls give bit-identical results (fixed order)."""
+    from mamcts_b200 import sharding
+    rng = np.random.default_rng(77)
+    T, nA, MA = 70001, 5, 7
+    n = rng.integers(0, 4000, size=(T, MA)).astype(np.uint32)
+    n[rng.random((T, MA)) < 0.2] = 0
+    q = rng.normal(size=(T, MA)) * 50.0
+    vis = rng.integers(0, 10000, size=T).astype(np.uint32)
+    stats = dict(value=np.zeros(T), latest_return=np.zeros(T), total_visits=vis, q=np.ascontiguousarray(q),
+                 n=np.ascontiguousarray(n))
+    slots = rng.permutation(T).astype(np.uint32)
+    m1 = engine.root_merge(stats, slots, nA)
+    m2 = engine.root_merge(stats, slots, nA)
+    exp = sharding.finish(sharding.local_partial(q[:, :nA], n[:, :nA], n[:, :nA] > 0, vis), nA)
+    assert m1["n"].tolist() == exp["n"].tolist() and m1["occurrences"].tolist() == exp["occurrences"].tolist()
+    assert m1["visits"] == exp["visits"] and m1["best"] == exp["best"]
+    assert rel_close(m1["q"], exp["q"], 1e-9) and rel_close(m1["value"], exp["value"], 1e-9)
+    assert_bit_equal(m1["q"], m2["q"], "root merge is deterministic")
+    with pytest.raises(MamctsError, match="out of range"):
+        engine.root_merge(stats, np.array([T], dtype=np.uint32), nA)
+
+
+def test_rollout_moments_device_reduction(engine):
+    """mamcts_rollout_moments (C3's exchange step): {sum, sum^2} per agent + count, reduced on the device in a
+    fixed order; against numpy (to rounding) and against itself (bit-identical on repetition)."""
+    from mamcts_b200 import sharding
+    rng = np.random.default_rng(3)
+    for n, others in ((1, 0), (37, 1), (4096, 3), (300007, 7)):
+        ego = rng.normal(size=n) * 3.0
+        oth = rng.normal(size=(others, n)) if others else None
+        a = engine.rollout_moments(ego, oth)
+        b = engine.rollout_moments(ego, oth)
+        assert_bit_equal(a, b, "moments are deterministic")
+        rows = np.vstack([ego[None, :]] + ([oth] if others else []))
+        exp = sharding.moments_partial(rows)
+        assert a[-1] == n and a.shape == exp.shape
+        assert np.allclose(a, exp, rtol=1e-11, atol=1e-9)
+        fin = sharding.moments_finish(a)
+        assert np.allclose(fin["mean"], rows.mean(axis=1), rtol=1e-9, atol=1e-12)
+
+
 # ---- device-resident search ---------------------------------------------------------------------
 
 def _golden_search(engine, case, num_trees=3, layout=LAYOUT_AUTO):
