@@ -260,11 +260,12 @@ C5_ITERATIONS = 1000
 def measure_rollout_c3(engine, stream, world=1, rank=0, steps=5, warmup=3, dist=None, e2e=True):
     """CrossingState<int>, 8 agents, 2^20 Philox rollouts per decision from the decision state, depth cap 50.
     The rollout index range is sharded over the ranks (sharding.rollout_shard; rollout r keeps its GLOBAL
-    Philox stream id, so the set of rollouts does not depend on the number of GPUs); each decision is one
-    rollout launch, one on-device moments reduction ({sum, sum^2} per agent + count, reduce.cu) and one
-    ncclAllReduce of those 2A+1 doubles (mamcts_rollout_moments). Device-resident inputs; env-steps/s from the
-    kernel's own step counter, CUDA events on the engine stream, max over ranks, L2 flushed between decisions;
-    plus the HBM roofline of rollout_kernel (algorithmic bytes 16A+8C+8 per rollout)."""
+    Philox stream id, so the set of rollouts does not depend on the number of GPUs). Each decision is ONE
+    call, mamcts_rollout_crossing_i32 with out->moments: the rollout launch, the on-device moments reduction
+    ({sum, sum^2} per agent + count over the per-rollout returns, reduce.cu), the K-rollout means, and one
+    ncclAllReduce of the 2A+1 doubles. Device-resident inputs; env-steps/s from the kernel's own step counter,
+    CUDA events on the engine stream, max over ranks, L2 flushed between decisions; plus the HBM roofline of
+    rollout_kernel (algorithmic bytes 16A+8C+8 per rollout)."""
     import numpy as np
     import torch
     from mamcts_b200 import default_crossing_params, default_params, sharding
@@ -272,8 +273,11 @@ def measure_rollout_c3(engine, stream, world=1, rank=0, steps=5, warmup=3, dist=
     mp = default_params(rh_max_number_of_iterations=DEPTH_CAP)
     cp = default_crossing_params(num_other_agents=C3_OTHERS)
     A = C3_OTHERS + 1
+    K = 256
     sh = sharding.rollout_shard(C3_ROLLOUTS, world, rank)
-    n = sh.num_rollouts
+    if sh.num_rollouts % K or sh.first_rollout % K:
+        raise SystemExit("bench.py: the C3 shard is not a whole number of leaves")
+    n = sh.num_rollouts // K            # start states ("leaves") of this rank, K rollouts each
     dev = torch.device("cuda", engine.device)
     with torch.cuda.stream(stream):
         # the decision state (all agents at x = 5, reference crossing_state_common.h:31) in every slot
@@ -285,10 +289,10 @@ def measure_rollout_c3(engine, stream, world=1, rank=0, steps=5, warmup=3, dist=
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
 
     def one(i):
-        engine.rollout_crossing_device(mp, cp, n, 1, x.data_ptr(), ego.data_ptr(), oth.data_ptr(),
-                                       0, 0, tot.data_ptr(), kind=SRC_PHILOX,
+        # rollout r = leaf * K + k of this rank draws from stream (i, first_rollout + r): global ids
+        engine.rollout_crossing_device(mp, cp, n, K, x.data_ptr(), ego.data_ptr(), oth.data_ptr(),
+                                       0, 0, tot.data_ptr(), kind=SRC_PHILOX, d_moments=mom.data_ptr(),
                                        seed=1000, stream_hi_base=i, stream_lo_base=sh.first_rollout)
-        engine.rollout_moments(ego.data_ptr(), oth.data_ptr(), A - 1, n, d_out=mom.data_ptr())
 
     def barrier():
         if dist is not None and world > 1:
@@ -298,70 +302,73 @@ def measure_rollout_c3(engine, stream, world=1, rank=0, steps=5, warmup=3, dist=
     for i in range(warmup):
         one(i)
     barrier()
-    times, kern_times, total_steps = [], [], 0
+    times, total_steps = [], 0
     launches0 = engine.launch_count
     for i in range(steps):
         with torch.cuda.stream(stream):
             flush.fill_(i & 0xFF)                     # flush L2 between timed iterations
-        a, k, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        engine.rollout_crossing_device(mp, cp, n, 1, x.data_ptr(), ego.data_ptr(), oth.data_ptr(),
-                                       0, 0, tot.data_ptr(), kind=SRC_PHILOX,
-                                       seed=1000, stream_hi_base=warmup + i, stream_lo_base=sh.first_rollout)
-        k.record(stream)
-        engine.rollout_moments(ego.data_ptr(), oth.data_ptr(), A - 1, n, d_out=mom.data_ptr())
+        one(warmup + i)
         b.record(stream)
         stream.synchronize()
         times.append(a.elapsed_time(b))
-        kern_times.append(a.elapsed_time(k))
         total_steps += int(tot.item())
     launches = engine.launch_count - launches0
     moments = mom.cpu().numpy()
-    agg = torch.tensor([sum(times), float(total_steps), sum(kern_times)], dtype=torch.float64, device=dev)
+    agg = torch.tensor([sum(times), float(total_steps)], dtype=torch.float64, device=dev)
     mx = agg.clone()
     if dist is not None and world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    total_ms, all_steps, kern_ms_sum = float(mx[0]), float(agg[1]), float(mx[2])
+    total_ms, all_steps = float(mx[0]), float(agg[1])
     ms = total_ms / steps
-    kern_ms = kern_ms_sum / steps
     steps_per_s = all_steps / (total_ms * 1e-3)
     fin = sharding.moments_finish(moments)
     out = {
         "workload": f"C3: CrossingState<int> {A} agents, {C3_ROLLOUTS} Philox rollouts per decision from the decision "
-                    f"state sharded over {world} GPU(s) by global rollout index, depth cap {DEPTH_CAP}, device-side "
-                    "moments reduction + one ncclAllReduce of 2A+1 doubles per decision, L2 flushed between decisions",
+                    f"state ({C3_ROLLOUTS // K} start-state slots x {K}) sharded over {world} GPU(s) by global rollout "
+                    f"index, depth cap {DEPTH_CAP}; one call per decision: rollouts + device-side moments reduction + one "
+                    "ncclAllReduce of 2A+1 doubles; L2 flushed between decisions",
         "env_steps_per_s": steps_per_s, "rollouts_per_s": C3_ROLLOUTS / (ms * 1e-3), "ms_per_decision": ms,
-        "rollout_kernel_ms": kern_ms, "n_gpus": world, "scaling": "strong",
+        "n_gpus": world, "scaling": "strong",
         "mean_steps_per_rollout": all_steps / (steps * C3_ROLLOUTS), "gpu_launches": int(launches),
         "rollouts_counted": int(fin["count"]), "mean_ego_return": float(fin["mean"][0]),
-        "kernel_ms_estimate": kern_ms,
+        "kernel_ms_estimate": ms,
     }
     if fin["count"] != C3_ROLLOUTS:
         raise SystemExit(f"bench.py: C3 all-reduced rollout count {fin['count']} != {C3_ROLLOUTS}")
-    if e2e and rank == 0:
-        # e2e: host buffers through the public call (numpy in, numpy out), this rank's shard
+    if e2e:
+        # e2e: host buffers through the public call: start states in (numpy), per-slot means + moments out
         xh = np.full((A, n), 5, dtype=np.int32)
-        engine.rollout_crossing(mp, cp, xh, K=1, kind=SRC_PHILOX, seed=1000, stream_hi_base=99)
+        engine.rollout_crossing(mp, cp, xh, K=K, kind=SRC_PHILOX, seed=1000, stream_hi_base=99, moments=True,
+                                stream_lo_base=sh.first_rollout)
+        barrier()
         t0 = time.perf_counter()
         e2e_steps = 0
         for i in range(steps):
-            r = engine.rollout_crossing(mp, cp, xh, K=1, kind=SRC_PHILOX, seed=1000, stream_hi_base=100 + i,
-                                        stream_lo_base=sh.first_rollout)
-            engine.rollout_moments(r["ego_return"], r["other_return"])
+            r = engine.rollout_crossing(mp, cp, xh, K=K, kind=SRC_PHILOX, seed=1000, stream_hi_base=100 + i,
+                                        stream_lo_base=sh.first_rollout, moments=True)
             e2e_steps += r["total_steps"]
+        barrier()
         e2e_s = time.perf_counter() - t0
-        out.update({"e2e_env_steps_per_s_rank0_shard": e2e_steps / e2e_s, "e2e_h2d_bytes": int(xh.nbytes),
-                    "e2e_d2h_bytes": int(8 * n * (A + 2) + 8)})
+        ag = torch.tensor([e2e_s, float(e2e_steps)], dtype=torch.float64, device=dev)
+        mx2 = ag.clone()
+        if dist is not None and world > 1:
+            dist.all_reduce(mx2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ag, op=dist.ReduceOp.SUM)
+        out.update({"e2e_env_steps_per_s": float(ag[1]) / float(mx2[0]), "e2e_h2d_bytes": int(xh.nbytes),
+                    "e2e_d2h_bytes": int(8 * n * (A + 2) + 8 + 8 * (2 * A + 1))})
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
     bytes_per_rollout = 16 * A + 8 * 1 + 8
-    achieved = bytes_per_rollout * n / (kern_ms * 1e-3) / 1e9
+    achieved = bytes_per_rollout * sh.num_rollouts / (ms * 1e-3) / 1e9
     out["roofline"] = {"bound": "hbm", "kernel": "rollout_kernel<CrossingEnv<7>,PHILOX>", "achieved": achieved,
                        "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                        "algorithmic_bytes_per_rollout": bytes_per_rollout,
-                       "note": "per GPU; state lives in registers for the whole episode: issue-bound, see "
-                               "profiles/ for smsp__issue_active and instructions per env-step"}
+                       "note": "per GPU, over the whole decision (rollouts + reductions); state lives in registers for "
+                               "the whole episode: issue-bound, see profiles/ for smsp__issue_active and instructions "
+                               "per env-step"}
     return out
 
 

@@ -175,6 +175,12 @@ typedef struct mamcts_rollout_out {
   double* reward_trace;        /* [n*K*trace_stride] ego step rewards, replay/const parity   */
   uint32_t trace_stride;
   uint32_t reserved2;
+  /* one decision, many rollouts (BASELINE configs[2]): {sum, sum of squares} per agent position over ALL n*K
+   * per-rollout returns, then the rollout count - 2A+1 doubles in the layout of mamcts_rollout_moments,
+   * reduced on the device right after the rollouts (and all-reduced over the engine's communicator when one
+   * is attached), so a 2^20-rollout decision returns 2A+1 doubles instead of 2^20 values. With K = 1 the
+   * per-leaf arrays ego_return (and other_return when A > 1) must be requested too. */
+  double* moments;
 } mamcts_rollout_out;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

@@ -146,6 +146,7 @@ class RolloutOut(C.Structure):
         ("reward_trace", C.c_void_p),
         ("trace_stride", C.c_uint32),
         ("reserved2", C.c_uint32),
+        ("moments", C.c_void_p),
     ]
 
 

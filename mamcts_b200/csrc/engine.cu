@@ -49,6 +49,7 @@ static int grow(mamcts_engine* e, void** buf, size_t* have, size_t need, bool pi
 }
 
 int ensure_scratch(mamcts_engine* e, size_t bytes) { return grow(e, &e->scratch, &e->scratch_bytes, bytes, false); }
+int ensure_reduce_buf(mamcts_engine* e, size_t bytes) { return grow(e, &e->reduce_buf, &e->reduce_bytes, bytes, false); }
 int ensure_staging(mamcts_engine* e, size_t bytes) { return grow(e, &e->staging, &e->staging_bytes, bytes, false); }
 int ensure_pinned(mamcts_engine* e, size_t bytes) { return grow(e, &e->pinned, &e->pinned_bytes, bytes, true); }
 
@@ -141,6 +142,7 @@ void mamcts_destroy(mamcts_engine* e) {
   cudaStreamSynchronize(e->stream);
   mamcts_comm_destroy(e);
   if (e->scratch) cudaFree(e->scratch);
+  if (e->reduce_buf) cudaFree(e->reduce_buf);
   if (e->staging) cudaFree(e->staging);
   if (e->pinned) cudaFreeHost(e->pinned);
   if (e->disc) cudaFree(e->disc);

@@ -20,6 +20,8 @@ struct mamcts_engine {
   // staging / scratch (grow-only)
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  void* reduce_buf = nullptr;  // ticket + partials of the reductions (reduce.cu); separate from `scratch`,
+  size_t reduce_bytes = 0;     // which holds the per-rollout values a moments reduction may be reading
   void* staging = nullptr;  // device staging for host-buffer calls
   size_t staging_bytes = 0;
   void* pinned = nullptr;   // pinned host staging
@@ -50,6 +52,11 @@ int cuda_fail(mamcts_engine* e, cudaError_t err, const char* what);
 
 // grow-only device scratch / staging; contents undefined after the call
 int ensure_scratch(mamcts_engine* e, size_t bytes);
+int ensure_reduce_buf(mamcts_engine* e, size_t bytes);
+// {sum, sum^2} per agent + count over device arrays (reduce.cu), asynchronous on the engine stream, all-reduced
+// over the communicator when one is attached; d_dst: 2 * (num_others + 1) + 1 doubles on the device. No lock taken.
+int rollout_moments_device(mamcts_engine* e, const double* d_ego, const double* d_other, uint32_t num_others,
+                           uint32_t n, double* d_dst);
 int ensure_staging(mamcts_engine* e, size_t bytes);
 int ensure_pinned(mamcts_engine* e, size_t bytes);
 

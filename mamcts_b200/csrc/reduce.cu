@@ -176,16 +176,13 @@ struct ReduceScratch {
 
 static int reduce_scratch(mamcts_engine* e, size_t nacc, size_t nout, size_t blocks, ReduceScratch* rs) {
   const size_t bytes = 256 + sizeof(double) * (nacc + nout + blocks * nacc);
-  const bool fresh = e->scratch_bytes < bytes;
-  int rc = ensure_scratch(e, bytes);
+  int rc = ensure_reduce_buf(e, bytes);
   if (rc != MAMCTS_OK) return rc;
-  char* base = static_cast<char*>(e->scratch);
+  char* base = static_cast<char*>(e->reduce_buf);
   rs->ticket = reinterpret_cast<unsigned int*>(base);
   rs->acc = reinterpret_cast<double*>(base + 256);
   rs->out = rs->acc + nacc;
   rs->partials = rs->out + nout;
-  // the ticket is left at zero by every launch; other users of the scratch area may have written it
-  (void)fresh;
   MAMCTS_CUDA(e, cudaMemsetAsync(rs->ticket, 0, sizeof(unsigned int), e->stream));
   return MAMCTS_OK;
 }
@@ -223,6 +220,26 @@ int root_merge_device(mamcts_engine* e, const RootGather& g, uint32_t n_trees, u
   if (merged_total_visits) *merged_total_visits = (uint64_t)host[3 * nA];
   if (merged_value) *merged_value = host[3 * nA + 1];
   if (best_action) *best_action = (uint32_t)host[3 * nA + 2];
+  return MAMCTS_OK;
+}
+
+int rollout_moments_device(mamcts_engine* e, const double* d_ego, const double* d_other, uint32_t num_others,
+                           uint32_t n, double* d_dst) {
+  const uint32_t rows = num_others + 1;
+  const size_t nacc = 2 * (size_t)rows + 1;
+  // 4096 values per block and row, at most 1024 blocks: the geometry is a function of n alone
+  uint32_t per_block = 4096;
+  while ((uint64_t)per_block * 1024u < n) per_block *= 2;
+  const uint32_t blocks = std::max(1u, (n + per_block - 1) / per_block);
+  ReduceScratch rs;
+  int rc = reduce_scratch(e, nacc, 0, blocks, &rs);
+  if (rc != MAMCTS_OK) return rc;
+  moments_kernel<<<blocks, kReduceThreads, 0, e->stream>>>(d_ego, d_other, rows, n, per_block, rs.partials, rs.ticket, rs.acc);
+  e->launches++;
+  MAMCTS_CUDA(e, cudaGetLastError());
+  rc = mamcts_allreduce_f64(e, rs.acc, nacc);   // no communicator: the local sums
+  if (rc != MAMCTS_OK) return rc;
+  MAMCTS_CUDA(e, cudaMemcpyAsync(d_dst, rs.acc, sizeof(double) * nacc, cudaMemcpyDeviceToDevice, e->stream));
   return MAMCTS_OK;
 }
 
@@ -274,30 +291,16 @@ int mamcts_rollout_moments(mamcts_engine* e, int32_t mem, const double* ego_retu
     return fail(e, MAMCTS_ERR_INVALID, "mamcts_rollout_moments: null argument");
   if (num_others >= MAMCTS_MAX_AGENTS) return fail(e, MAMCTS_ERR_INVALID, "mamcts_rollout_moments: too many agents");
   MAMCTS_CUDA(e, cudaSetDevice(e->device));
-  const uint32_t rows = num_others + 1;
-  const size_t nacc = 2 * (size_t)rows + 1;
-  // 4096 values per block and row, at most 4 blocks per SM worth of blocks (a function of n alone)
-  uint32_t per_block = 4096;
-  while ((uint64_t)per_block * 1024u < n) per_block *= 2;
-  const uint32_t blocks = std::max(1u, (n + per_block - 1) / per_block);
   ArgStager stg(e);
   const int t_ego = stg.plan(ego_return, sizeof(double) * n, mem, false);
   const int t_oth = stg.plan(num_others ? other_return : nullptr, sizeof(double) * (size_t)num_others * n, mem, false);
+  const int t_out = stg.plan(moments, sizeof(double) * (2 * ((size_t)num_others + 1) + 1), mem, true);
   int rc = stg.commit();
   if (rc != MAMCTS_OK) return rc;
-  ReduceScratch rs;
-  rc = reduce_scratch(e, nacc, 0, blocks, &rs);
+  rc = rollout_moments_device(e, stg.dev<const double>(t_ego), stg.dev<const double>(t_oth), num_others, n,
+                              stg.dev<double>(t_out));
   if (rc != MAMCTS_OK) return rc;
-  moments_kernel<<<blocks, kReduceThreads, 0, e->stream>>>(stg.dev<const double>(t_ego), stg.dev<const double>(t_oth),
-                                                           rows, n, per_block, rs.partials, rs.ticket, rs.acc);
-  e->launches++;
-  MAMCTS_CUDA(e, cudaGetLastError());
-  rc = mamcts_allreduce_f64(e, rs.acc, nacc);   // no communicator: the local sums
-  if (rc != MAMCTS_OK) return rc;
-  MAMCTS_CUDA(e, cudaMemcpyAsync(moments, rs.acc, sizeof(double) * nacc,
-                                 mem == MAMCTS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, e->stream));
-  if (mem == MAMCTS_MEM_HOST) MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
-  return MAMCTS_OK;
+  return stg.finish();
 }
 
 }  // extern "C"

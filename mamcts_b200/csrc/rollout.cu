@@ -467,6 +467,9 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
                             sizeof(int32_t) * A * total, out->mem, true);
   const int o_ff = stg.plan(out->final_flags, total, out->mem, true);
   const int o_tr = stg.plan(out->reward_trace, sizeof(double) * (size_t)total * out->trace_stride, out->mem, true);
+  const int o_mom = stg.plan(out->moments, sizeof(double) * (2 * (size_t)A + 1), out->mem, true);
+  if (out->moments && K == 1 && (!out->ego_return || (A > 1 && !out->other_return)))
+    return fail(e, MAMCTS_ERR_INVALID, "rollout: moments with K == 1 need ego_return and other_return as well");
   int rc = stg.commit();
   if (rc != MAMCTS_OK) return rc;
 
@@ -534,6 +537,10 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   else rc = dispatch_crossing(e, p, (int)A - 1, src->kind, parity);
   if (rc != MAMCTS_OK) return rc;
 
+  if (out->moments) {   // over the per-rollout values: the outputs themselves (K = 1) or the scratch rows
+    rc = rollout_moments_device(e, p.ego_ret, p.other_ret, A - 1, total, stg.dev<double>(o_mom));
+    if (rc != MAMCTS_OK) return rc;
+  }
   if (K > 1) {
     const double* s = static_cast<const double*>(e->scratch);
     const int rgrid = std::max(1, std::min(grid_for(e, 4), (int)((n + 7) / 8)));

@@ -218,7 +218,7 @@ class Engine:
         return src, keep
 
     def _rollout_host(self, env, mp, envp, A, x, last, flags, depth, K, src_kw, want_parity,
-                      trace_stride):
+                      trace_stride, want_moments=False):
         x = np.ascontiguousarray(x, dtype=np.int32)
         if env == ENV_SIMPLE:
             x = x.reshape(1, -1)
@@ -237,6 +237,9 @@ class Engine:
         out.ego_cost = res["ego_cost"].ctypes.data
         out.step_length = res["step_length"].ctypes.data
         out.total_steps = res["total_steps"].ctypes.data
+        if want_moments:   # {sum, sum^2} per agent + count over all n*K per-rollout returns, reduced on the device
+            res["moments"] = np.zeros(2 * A + 1)
+            out.moments = res["moments"].ctypes.data
         if want_parity:
             xr = 1 if env == ENV_SIMPLE else A
             res.update(steps=np.zeros(total, dtype=np.uint32),
@@ -266,10 +269,11 @@ class Engine:
 
     def rollout_crossing(self, mp: Params, cp: CrossingParams, x, last=None, flags=None, depth=None,
                          K: int = 1, kind: int = SRC_PHILOX, parity: bool = False,
-                         trace_stride: int = 0, **src_kw):
-        """HOST-buffer batched rollout through CrossingState<int>::execute. x: [A, n] int32."""
+                         trace_stride: int = 0, moments: bool = False, **src_kw):
+        """HOST-buffer batched rollout through CrossingState<int>::execute. x: [A, n] int32.
+        moments=True adds res["moments"]: {sum, sum^2} per agent + count over all n*K rollouts."""
         return self._rollout_host(ENV_CROSSING_I32, mp, cp, cp.num_other_agents + 1, x, last, flags,
-                                  depth, K, dict(kind=kind, **src_kw), parity, trace_stride)
+                                  depth, K, dict(kind=kind, **src_kw), parity, trace_stride, moments)
 
     def rollout_crossing_f32(self, mp: Params, cp, x, last=None, flags=None, depth=None, K: int = 1,
                              kind: int = SRC_PHILOX, parity: bool = False, replay_actions=None,
@@ -322,7 +326,7 @@ class Engine:
     def rollout_crossing_device(self, mp: Params, cp: CrossingParams, n: int, K: int, d_x: int,
                                 d_ego: int, d_other: int = 0, d_cost: int = 0, d_len: int = 0,
                                 d_total_steps: int = 0, d_last: int = 0, d_flags: int = 0,
-                                d_depth: int = 0, kind: int = SRC_PHILOX, **src_kw):
+                                d_depth: int = 0, kind: int = SRC_PHILOX, d_moments: int = 0, **src_kw):
         """DEVICE-buffer variant: raw device pointers, fully asynchronous on the engine stream."""
         src, keep = self._source(A=cp.num_other_agents + 1, kind=kind, mem=MEM_DEVICE, **src_kw)
         out = RolloutOut()
@@ -332,6 +336,7 @@ class Engine:
         out.ego_cost = d_cost or None
         out.step_length = d_len or None
         out.total_steps = d_total_steps or None
+        out.moments = d_moments or None
         rc = self.lib.mamcts_rollout_crossing_i32(
             self.h, C.byref(mp), C.byref(cp), n, K, MEM_DEVICE, C.c_void_p(d_x),
             C.c_void_p(d_last) if d_last else None, C.c_void_p(d_flags) if d_flags else None,

@@ -266,3 +266,21 @@ def test_full_size_properties(engine):
     out2 = engine.rollout_crossing(mp, cp, x, K=K, **kw)
     assert_bit_equal(out2["ego_return"], out["ego_return"], "idempotence")
     assert out2["total_steps"] == out["total_steps"]
+
+
+def test_moments_inside_the_rollout_call(engine):
+    """out->moments (one decision, many rollouts: C3): the same {sum, sum^2, count} whether the rollouts are
+    launched as n leaves x K or as n*K leaves x 1 with the same global stream ids, and equal to the separate
+    mamcts_rollout_moments call over the per-rollout returns - bit for bit (same values, same fixed order)."""
+    from helpers import assert_bit_equal
+    mp = default_params(rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=3)
+    n, K = 40, 32
+    a = engine.rollout_crossing(mp, cp, np.full((4, n), 5, dtype=np.int32), K=K, kind=SRC_PHILOX, seed=9,
+                                stream_hi_base=3, stream_lo_base=1000, moments=True)
+    b = engine.rollout_crossing(mp, cp, np.full((4, n * K), 5, dtype=np.int32), K=1, kind=SRC_PHILOX, seed=9,
+                                stream_hi_base=3, stream_lo_base=1000, moments=True)
+    assert a["total_steps"] == b["total_steps"] and a["moments"][-1] == n * K
+    assert_bit_equal(a["moments"], b["moments"], "moments K=32 vs K=1")
+    assert_bit_equal(b["moments"], engine.rollout_moments(b["ego_return"], b["other_return"]), "in-call vs separate call")
+    assert np.allclose(a["moments"][0] / (n * K), b["ego_return"].mean(), rtol=1e-12, atol=1e-15)
