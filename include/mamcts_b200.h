@@ -256,6 +256,43 @@ int mamcts_rollout_simple(mamcts_engine* e, const mamcts_params* mp,
                           const uint32_t* start_depth, const mamcts_action_source* src,
                           mamcts_rollout_out* out);
 
+/* ---- per-ego-action heuristic: ActionValueRandomHeuristic::calculate_heuristic_values ---------
+ * (mcts/heuristics/action_value_random_heuristic.h:27-112), its compute part (:37-85): for every leaf and every
+ * ego action a, ONE first step of CrossingState<int>::execute with the joint action (a, what a fresh statistic of
+ * every other agent chooses) and ONE RandomHeuristic::rollout from the resulting state at depth + 1; n_leaves *
+ * nA_ego rollouts in one launch. Outputs per leaf (HOST or DEVICE, any may be NULL):
+ *   action_return[leaf * nA + a]      = gamma * first-step ego reward + gamma * rollout return          (:64-65)
+ *   action_cost[leaf * nA + a]        = first-step cost[0] + rollout cost[0], not discounted           (:73-81)
+ *   action_step_length[leaf * nA + a] = 1 + rollout length                                             (:83-84)
+ *   other_return[j * n + leaf]        = the LAST action's rollout return of other j (+ gamma * 0): the reference
+ *                                       ties the rollout's map to the accumulator itself (:58-60)
+ *   mean_cost[leaf]                   = the mean of the action costs, added in the order the reference's
+ *                                       std::unordered_map yields them (:97-103); what every other agent's
+ *                                       statistic receives through set_heuristic_estimate
+ * A terminal leaf tries no action (:38): all of its outputs are 0. These arrays are the arguments of the
+ * map-valued SE::set_heuristic_estimate(action_returns, action_costs) (:93; CostConstrainedStatistic, or
+ * UctStatistic::set_heuristic_estimate_from_backpropagated(map), uct_statistic.h:156-163).
+ * Action sources: MAMCTS_SRC_REFERENCE_CONST (src->const_actions[1..]: the others' first-draw constants; the
+ * rollouts use const_actions[0..]) and MAMCTS_SRC_PHILOX: with (hi, lo) = the leaf's stream (stream_hi[leaf] or
+ * stream_hi_base, stream_lo[leaf] or stream_lo_base + leaf), action a's rollout draws from stream
+ * (hi, lo * nA + a) and its first step's other agents from (step 0, agent j) of stream (hi ^ 0x80000000, lo * nA + a). */
+typedef struct mamcts_action_values_out {
+  int32_t mem;
+  int32_t reserved;
+  double* action_return;        /* [n * nA_ego] */
+  double* action_cost;          /* [n * nA_ego] */
+  double* action_step_length;   /* [n * nA_ego] */
+  double* other_return;         /* [(A-1) * n] */
+  double* mean_cost;            /* [n] */
+  uint64_t* total_steps;        /* [1] execute() calls: first steps + rollout steps */
+} mamcts_action_values_out;
+
+int mamcts_action_values_crossing_i32(mamcts_engine* e, const mamcts_params* mp,
+                                      const mamcts_crossing_params* cp, uint32_t n_leaves, int32_t mem,
+                                      const int32_t* state_x, const int32_t* state_last_action,
+                                      const uint8_t* state_flags, const uint32_t* start_depth,
+                                      const mamcts_action_source* src, mamcts_action_values_out* out);
+
 /* ---- backup: UctStatistic (mcts/statistics/uct_statistic.h) ------------------------------ */
 
 /* Statistic storage, SoA over (node, agent) slots s = node * A + agent; action stride

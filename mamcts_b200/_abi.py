@@ -150,6 +150,19 @@ class RolloutOut(C.Structure):
     ]
 
 
+class ActionValuesOut(C.Structure):
+    _fields_ = [
+        ("mem", C.c_int32),
+        ("reserved", C.c_int32),
+        ("action_return", C.c_void_p),
+        ("action_cost", C.c_void_p),
+        ("action_step_length", C.c_void_p),
+        ("other_return", C.c_void_p),
+        ("mean_cost", C.c_void_p),
+        ("total_steps", C.c_void_p),
+    ]
+
+
 class UctStats(C.Structure):
     _fields_ = [
         ("mem", C.c_int32),
@@ -250,6 +263,10 @@ def load() -> C.CDLL:
              P(RolloutOut)],
         ),
         "mamcts_default_crossing_params_f32": (None, [P(CrossingParamsF32)]),
+        "mamcts_action_values_crossing_i32": (
+            i32,
+            [vp, P(Params), P(CrossingParams), u32, i32, vp, vp, vp, vp, P(ActionSource), P(ActionValuesOut)],
+        ),
         "mamcts_rollout_simple": (
             i32,
             [vp, P(Params), P(SimpleParams), u32, u32, i32, vp, vp, P(ActionSource), P(RolloutOut)],
@@ -298,7 +315,7 @@ EXPORTED_SYMBOLS = [
     "mamcts_device_alloc", "mamcts_device_free", "mamcts_memcpy_h2d", "mamcts_memcpy_d2h",
     "mamcts_default_params", "mamcts_default_crossing_params", "mamcts_default_simple_params",
     "mamcts_reference_expand_order", "mamcts_rollout_crossing_i32", "mamcts_rollout_simple",
-    "mamcts_rollout_crossing_f32", "mamcts_default_crossing_params_f32",
+    "mamcts_rollout_crossing_f32", "mamcts_default_crossing_params_f32", "mamcts_action_values_crossing_i32",
     "mamcts_backup_uct", "mamcts_backup_hypothesis", "mamcts_root_merge", "mamcts_rollout_moments", "mamcts_comm_get_unique_id",
     "mamcts_comm_init_rank", "mamcts_comm_destroy", "mamcts_allreduce_f64",
     "mamcts_search_create", "mamcts_search_destroy", "mamcts_search_reset", "mamcts_search_run",

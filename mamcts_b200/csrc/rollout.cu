@@ -406,13 +406,12 @@ static int dispatch_crossing_f32(mamcts_engine* e, const RolloutParams& p, int n
 
 // Shared body of the entry points. A = number of agents; x_rows = rows of the state array; the state
 // arrays are int32 or (kEnvCrossingF32) float - both 4 bytes per element.
-static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* mp, const EnvParams& ep,
+// (the caller holds e->mu)
+static int rollout_locked(mamcts_engine* e, int env_kind, const mamcts_params* mp, const EnvParams& ep,
                           uint32_t A, uint32_t n, uint32_t K, int32_t mem, const void* state_x,
                           const void* state_last, const uint8_t* state_flags,
                           const uint32_t* start_depth, const mamcts_action_source* src,
                           mamcts_rollout_out* out) {
-  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "rollout: null engine");
-  std::lock_guard<std::mutex> lock(e->mu);
   if (!mp || !src || !out || !state_x) return fail(e, MAMCTS_ERR_INVALID, "rollout: null argument");
   if (n == 0) return MAMCTS_OK;
   if (!valid_k(K))
@@ -558,11 +557,287 @@ static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* m
   return stg.finish();
 }
 
+static int rollout_common(mamcts_engine* e, int env_kind, const mamcts_params* mp, const EnvParams& ep,
+                          uint32_t A, uint32_t n, uint32_t K, int32_t mem, const void* state_x,
+                          const void* state_last, const uint8_t* state_flags,
+                          const uint32_t* start_depth, const mamcts_action_source* src,
+                          mamcts_rollout_out* out) {
+  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "rollout: null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  return rollout_locked(e, env_kind, mp, ep, A, n, K, mem, state_x, state_last, state_flags, start_depth, src, out);
+}
+
+// ---- per-ego-action heuristic: ActionValueRandomHeuristic (action_value_random_heuristic.h:27-112) -----------
+// For every leaf and every ego action a: one first step (ego = a, the other agents as a fresh statistic makes
+// them act) and one RandomHeuristic::rollout from the resulting state at depth + 1 (:37-61). The rollouts are
+// exactly the batched rollout kernel above over n * nA start states; two small kernels sit around it:
+//   av_first_step_kernel   item (leaf, a) -> the stepped state, its depth, the first step's reward and cost
+//   av_combine_kernel      leaf -> action_return / action_cost / action_step_length per action (:64-84), the
+//                          other agents' returns (of the LAST action: :58-60 ties the rollout's map to the
+//                          accumulator) and the mean cost in the reference's summation order (:97-103)
+struct ActionValueParams {
+  uint32_t n_leaves, nA;
+  const int32_t* x;          // [A][n]
+  const int32_t* last;       // [A][n] or null (2)
+  const uint8_t* flags;      // [n] or null
+  const uint32_t* depth;     // [n] or null
+  int kind;
+  uint32_t const_actions[MAMCTS_MAX_AGENTS];
+  uint32_t key0, key1;
+  const uint32_t* stream_hi;
+  const uint32_t* stream_lo;
+  uint32_t stream_hi_base, stream_lo_base;
+  EnvParams env;
+  // per item (leaf * nA + a)
+  int32_t* x2;               // [A][n * nA]
+  int32_t* last2;            // [A][n * nA]
+  uint8_t* flags2;           // [n * nA]
+  uint32_t* depth2;          // [n * nA]
+  uint32_t* s_hi2;           // [n * nA] Philox stream of the item's rollout
+  uint32_t* s_lo2;
+  double* r0;                // [n * nA] first-step ego reward
+  double* c0;                // [n * nA] first-step cost[0]
+};
+
+template <class Env>
+__global__ void __launch_bounds__(256) av_first_step_kernel(const __grid_constant__ ActionValueParams p) {
+  constexpr int A = Env::A;
+  const uint32_t total = p.n_leaves * p.nA;
+  for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+    const uint32_t leaf = item / p.nA, a = item - leaf * p.nA;
+    typename Env::State st;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      st.x[i] = __ldg(p.x + (size_t)i * p.n_leaves + leaf);
+      st.last[i] = p.last ? __ldg(p.last + (size_t)i * p.n_leaves + leaf) : 2;
+    }
+    st.flags = p.flags ? (uint32_t)(__ldg(p.flags + leaf) & 1u) : 0u;
+    const uint32_t depth = p.depth ? __ldg(p.depth + leaf) : 0u;
+    const uint32_t s_hi = p.stream_hi ? __ldg(p.stream_hi + leaf) : p.stream_hi_base;
+    const uint32_t s_lo = (p.stream_lo ? __ldg(p.stream_lo + leaf) : p.stream_lo_base + leaf) * p.nA + a;
+    double r0 = 0.0, c0 = 0.0;
+    if (!Env::terminal(p.env, st)) {                      // :38: a terminal state tries no action
+      int32_t act[A];
+      act[0] = (int32_t)a;                                // :41
+      if (p.kind == MAMCTS_SRC_PHILOX) {
+        // (step 0, agent j) of stream (s_hi ^ 0x80000000, s_lo): same layout as the rollout's draws
+        const uint32_t hi2 = s_hi ^ 0x80000000u;
+        Philox4 blk[(A + 7) / 8];
+#pragma unroll
+        for (int b = 0; b < (A + 7) / 8; ++b) blk[b] = philox4x32_10((A <= 8 ? 0 : b), s_lo, hi2, 0u, p.key0, p.key1);
+        uint32_t h[A], span[A];
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+          h[i] = (A <= 8) ? philox_half(blk[0], i) : philox_half(blk[i / 8], i % 8);
+          span[i] = Env::num_actions(p.env, i);
+        }
+        philox_bounded_all<A>(h, span, 0u, s_lo, hi2, p.key0, p.key1);
+#pragma unroll
+        for (int i = 1; i < A; ++i) act[i] = Env::action_from_index(i, h[i]);
+      } else {
+#pragma unroll
+        for (int i = 1; i < A; ++i) act[i] = Env::action_from_index(i, p.const_actions[i]);   // :43-47
+      }
+      double r_other;
+      Env::step(p.env, st, act, r0, r_other, c0);         // :52
+    }
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      p.x2[(size_t)i * total + item] = st.x[i];
+      p.last2[(size_t)i * total + item] = st.last[i];
+    }
+    p.flags2[item] = (uint8_t)(st.flags & 1u);
+    p.depth2[item] = depth + 1u;
+    p.s_hi2[item] = s_hi;
+    p.s_lo2[item] = s_lo;
+    p.r0[item] = r0;
+    p.c0[item] = c0;
+  }
+}
+
+struct ActionValueCombine {
+  uint32_t n_leaves, nA, num_others;
+  double gamma;
+  const uint8_t* flags;      // leaf flags or null
+  const double* r0;          // per item
+  const double* c0;
+  const double* ego_roll;    // per item: the rollout's outputs (K = 1)
+  const double* other_roll;  // [num_others][n * nA]
+  const double* cost_roll;
+  const double* len_roll;
+  double* action_return;     // [n][nA]
+  double* action_cost;
+  double* action_len;
+  double* other_return;      // [num_others][n]
+  double* mean_cost;         // [n]
+  unsigned long long* total_steps;   // += one first step per item of a non-terminal leaf
+};
+
+__global__ void __launch_bounds__(256) av_combine_kernel(const __grid_constant__ ActionValueCombine p) {
+  unsigned long long first_steps = 0;
+  for (uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < p.n_leaves; leaf += gridDim.x * blockDim.x) {
+    const bool terminal = p.flags && (p.flags[leaf] & 1u);
+    const size_t total = (size_t)p.n_leaves * p.nA;
+    double mean = 0.0;
+    for (uint32_t k = 0; k < p.nA; ++k) {                  // :97-103 in the reference container's order: last first
+      const uint32_t a = p.nA - 1u - k;
+      const size_t item = (size_t)leaf * p.nA + a;
+      double ret = 0.0, cost = 0.0, len = 0.0;
+      if (!terminal) {
+        ret = __dadd_rn(0.0, __dadd_rn(__dmul_rn(p.gamma, p.r0[item]), __dmul_rn(p.gamma, p.ego_roll[item])));   // :64-65
+        cost = __dadd_rn(0.0, __dadd_rn(p.c0[item], p.cost_roll[item]));                                          // :73-81
+        len = __dadd_rn(0.0, __dadd_rn(1.0, p.len_roll[item]));                                                   // :83-84
+      }
+      if (p.action_return) p.action_return[item] = ret;
+      if (p.action_cost) p.action_cost[item] = cost;
+      if (p.action_len) p.action_len[item] = len;
+      mean = __dadd_rn(mean, cost);
+    }
+    if (p.mean_cost) p.mean_cost[leaf] = __ddiv_rn(mean, (double)p.nA);
+    if (p.other_return) {
+      const size_t last_item = (size_t)leaf * p.nA + (p.nA - 1u);
+      for (uint32_t j = 0; j < p.num_others; ++j)   // :66-71 on the tied map; rewards[1..] of CrossingState are 0
+        p.other_return[(size_t)j * p.n_leaves + leaf] =
+            terminal ? 0.0 : __dadd_rn(p.other_roll[(size_t)j * total + last_item],
+                                       __dadd_rn(__dmul_rn(p.gamma, 0.0), __dmul_rn(p.gamma, 0.0)));
+    }
+    if (!terminal) first_steps += p.nA;
+  }
+  if (p.total_steps && first_steps) atomicAdd(p.total_steps, first_steps);
+}
+
+template <class Env>
+static void launch_av_first_step(mamcts_engine* e, const ActionValueParams& p) {
+  const uint32_t total = p.n_leaves * p.nA;
+  const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((total + 255) / 256, (uint32_t)e->num_sms * 8u));
+  av_first_step_kernel<Env><<<grid, 256, 0, e->stream>>>(p);
+}
+
 }  // namespace mamcts
 
 using namespace mamcts;
 
 extern "C" {
+
+int mamcts_action_values_crossing_i32(mamcts_engine* e, const mamcts_params* mp, const mamcts_crossing_params* cp,
+                                      uint32_t n_leaves, int32_t mem, const int32_t* state_x,
+                                      const int32_t* state_last_action, const uint8_t* state_flags,
+                                      const uint32_t* start_depth, const mamcts_action_source* src,
+                                      mamcts_action_values_out* out) {
+  if (!e) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_action_values_crossing_i32: null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!mp || !cp || !src || !out || !state_x) return fail(e, MAMCTS_ERR_INVALID, "mamcts_action_values_crossing_i32: null argument");
+  if (cp->num_other_agents + 1 > MAMCTS_MAX_AGENTS || cp->num_other_agents == 0)
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_action_values_crossing_i32: 1..15 other agents supported");
+  if (src->kind != MAMCTS_SRC_REFERENCE_CONST && src->kind != MAMCTS_SRC_PHILOX)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_action_values_crossing_i32: action source must be REFERENCE_CONST or PHILOX");
+  if (n_leaves == 0) return MAMCTS_OK;
+  EnvParams ep;
+  std::memset(&ep, 0, sizeof(ep));
+  make_crossing_env(*cp, ep);
+  if (ep.n_ego_actions == 0 || ep.n_ego_actions > MAMCTS_MAX_ACTIONS || ep.n_other_actions == 0 ||
+      ep.n_other_actions > MAMCTS_MAX_ACTIONS)
+    return fail(e, MAMCTS_ERR_INVALID, "mamcts_action_values_crossing_i32: action counts out of range");
+  const uint32_t A = cp->num_other_agents + 1, nA = ep.n_ego_actions, n = n_leaves;
+  if ((uint64_t)n * nA > 0x40000000ull) return fail(e, MAMCTS_ERR_INVALID, "mamcts_action_values_crossing_i32: too many leaves for one call");
+  if (src->kind == MAMCTS_SRC_REFERENCE_CONST)
+    for (uint32_t a = 1; a < A; ++a)
+      if (src->const_actions[a] >= ep.n_other_actions) return fail(e, MAMCTS_ERR_INVALID, "mamcts_action_values_crossing_i32: const action out of range");
+  MAMCTS_CUDA(e, cudaSetDevice(e->device));
+  const uint32_t total = n * nA;
+
+  ArgStager stg(e);
+  const int t_x = stg.plan(state_x, sizeof(int32_t) * A * n, mem, false);
+  const int t_last = stg.plan(state_last_action, sizeof(int32_t) * A * n, mem, false);
+  const int t_flags = stg.plan(state_flags, n, mem, false);
+  const int t_depth = stg.plan(start_depth, sizeof(uint32_t) * n, mem, false);
+  const int t_shi = stg.plan(src->kind == MAMCTS_SRC_PHILOX ? src->stream_hi : nullptr, sizeof(uint32_t) * n, src->mem, false);
+  const int t_slo = stg.plan(src->kind == MAMCTS_SRC_PHILOX ? src->stream_lo : nullptr, sizeof(uint32_t) * n, src->mem, false);
+  const int o_ret = stg.plan(out->action_return, sizeof(double) * total, out->mem, true);
+  const int o_cost = stg.plan(out->action_cost, sizeof(double) * total, out->mem, true);
+  const int o_len = stg.plan(out->action_step_length, sizeof(double) * total, out->mem, true);
+  const int o_oth = stg.plan(out->other_return, sizeof(double) * (A - 1) * n, out->mem, true);
+  const int o_mean = stg.plan(out->mean_cost, sizeof(double) * n, out->mem, true);
+  const int o_tot = stg.plan(out->total_steps, sizeof(uint64_t), out->mem, true);
+  int rc = stg.commit();
+  if (rc != MAMCTS_OK) return rc;
+
+  // scratch: the stepped states and the rollouts' per-item results
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t b_i32 = up(sizeof(int32_t) * (size_t)A * total), b_u32 = up(sizeof(uint32_t) * (size_t)total),
+               b_u8 = up(total), b_f64 = up(sizeof(double) * (size_t)total);
+  rc = ensure_scratch(e, 2 * b_i32 + 3 * b_u32 + b_u8 + (5 + (size_t)(A - 1)) * b_f64);
+  if (rc != MAMCTS_OK) return rc;
+  char* base = static_cast<char*>(e->scratch);
+  auto take = [&](size_t bytes) { char* ptr = base; base += bytes; return ptr; };
+  ActionValueParams ap;
+  std::memset(&ap, 0, sizeof(ap));
+  ap.n_leaves = n; ap.nA = nA;
+  ap.x = stg.dev<const int32_t>(t_x); ap.last = stg.dev<const int32_t>(t_last);
+  ap.flags = stg.dev<const uint8_t>(t_flags); ap.depth = stg.dev<const uint32_t>(t_depth);
+  ap.kind = src->kind;
+  for (int a = 0; a < MAMCTS_MAX_AGENTS; ++a) ap.const_actions[a] = src->const_actions[a];
+  ap.key0 = (uint32_t)src->philox_seed; ap.key1 = (uint32_t)(src->philox_seed >> 32);
+  ap.stream_hi = stg.dev<const uint32_t>(t_shi); ap.stream_lo = stg.dev<const uint32_t>(t_slo);
+  ap.stream_hi_base = src->stream_hi_base; ap.stream_lo_base = src->stream_lo_base;
+  ap.env = ep;
+  ap.x2 = reinterpret_cast<int32_t*>(take(b_i32));
+  ap.last2 = reinterpret_cast<int32_t*>(take(b_i32));
+  ap.depth2 = reinterpret_cast<uint32_t*>(take(b_u32));
+  ap.s_hi2 = reinterpret_cast<uint32_t*>(take(b_u32));
+  ap.s_lo2 = reinterpret_cast<uint32_t*>(take(b_u32));
+  ap.flags2 = reinterpret_cast<uint8_t*>(take(b_u8));
+  ap.r0 = reinterpret_cast<double*>(take(b_f64));
+  ap.c0 = reinterpret_cast<double*>(take(b_f64));
+  double* ego_roll = reinterpret_cast<double*>(take(b_f64));
+  double* cost_roll = reinterpret_cast<double*>(take(b_f64));
+  double* len_roll = reinterpret_cast<double*>(take(b_f64));
+  double* other_roll = reinterpret_cast<double*>(take((size_t)(A - 1) * b_f64));   // rows `total` apart
+  switch (A - 1) {
+    case 1: launch_av_first_step<CrossingEnv<1>>(e, ap); break;
+    case 2: launch_av_first_step<CrossingEnv<2>>(e, ap); break;
+    case 3: launch_av_first_step<CrossingEnv<3>>(e, ap); break;
+    case 4: launch_av_first_step<CrossingEnv<4>>(e, ap); break;
+    case 5: launch_av_first_step<CrossingEnv<5>>(e, ap); break;
+    case 6: launch_av_first_step<CrossingEnv<6>>(e, ap); break;
+    case 7: launch_av_first_step<CrossingEnv<7>>(e, ap); break;
+    case 11: launch_av_first_step<CrossingEnv<11>>(e, ap); break;
+    case 15: launch_av_first_step<CrossingEnv<15>>(e, ap); break;
+    default: return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_action_values_crossing_i32: compiled for 1..7, 11 or 15 other agents");
+  }
+  e->launches++;
+  MAMCTS_CUDA(e, cudaGetLastError());
+
+  // the rollouts: n * nA start states, one rollout each, on the same stream (device buffers throughout)
+  mamcts_action_source rs = *src;
+  rs.mem = MAMCTS_MEM_DEVICE;
+  rs.stream_hi = ap.s_hi2;
+  rs.stream_lo = ap.s_lo2;
+  mamcts_rollout_out ro;
+  std::memset(&ro, 0, sizeof(ro));
+  ro.mem = MAMCTS_MEM_DEVICE;
+  ro.ego_return = ego_roll; ro.other_return = other_roll; ro.ego_cost = cost_roll; ro.step_length = len_roll;
+  uint64_t* d_tot = stg.dev<uint64_t>(o_tot);
+  ro.total_steps = d_tot;
+  // (the rollout kernel writes other j of item r at other_roll[j * total + r]: rows `total` doubles apart)
+  rc = rollout_locked(e, MAMCTS_ENV_CROSSING_I32, mp, ep, A, total, 1, MAMCTS_MEM_DEVICE, ap.x2, ap.last2, ap.flags2,
+                      ap.depth2, &rs, &ro);
+  if (rc != MAMCTS_OK) return rc;
+  ActionValueCombine cb;
+  std::memset(&cb, 0, sizeof(cb));
+  cb.n_leaves = n; cb.nA = nA; cb.num_others = A - 1; cb.gamma = mp->discount_factor;
+  cb.flags = ap.flags; cb.r0 = ap.r0; cb.c0 = ap.c0;
+  cb.ego_roll = ego_roll; cb.other_roll = other_roll; cb.cost_roll = cost_roll; cb.len_roll = len_roll;
+  cb.action_return = stg.dev<double>(o_ret); cb.action_cost = stg.dev<double>(o_cost);
+  cb.action_len = stg.dev<double>(o_len); cb.other_return = stg.dev<double>(o_oth);
+  cb.mean_cost = stg.dev<double>(o_mean);
+  cb.total_steps = reinterpret_cast<unsigned long long*>(d_tot);
+  const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((n + 255) / 256, (uint32_t)e->num_sms * 8u));
+  av_combine_kernel<<<grid, 256, 0, e->stream>>>(cb);
+  e->launches++;
+  MAMCTS_CUDA(e, cudaGetLastError());
+  return stg.finish();
+}
 
 int mamcts_rollout_crossing_i32(mamcts_engine* e, const mamcts_params* mp,
                                 const mamcts_crossing_params* cp, uint32_t n_leaves,

@@ -275,6 +275,32 @@ class Engine:
         return self._rollout_host(ENV_CROSSING_I32, mp, cp, cp.num_other_agents + 1, x, last, flags,
                                   depth, K, dict(kind=kind, **src_kw), parity, trace_stride, moments)
 
+    def action_values_crossing(self, mp: Params, cp: CrossingParams, x, last=None, flags=None, depth=None,
+                               kind: int = SRC_PHILOX, **src_kw):
+        """ActionValueRandomHeuristic's compute part (reference action_value_random_heuristic.h:37-85) for n leaves:
+        per ego action one first step + one rollout (mamcts_action_values_crossing_i32). x: [A, n] int32, HOST.
+        Returns action_return / action_cost / action_step_length [n, nA], other_return [A-1, n], mean_cost [n]."""
+        from ._abi import ActionValuesOut
+        A, nA = cp.num_other_agents + 1, cp.num_ego_actions
+        x = np.ascontiguousarray(x, dtype=np.int32)
+        n = x.shape[1]
+        last_a = None if last is None else np.ascontiguousarray(last, dtype=np.int32)
+        flags_a = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        depth_a = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+        src, keep = self._source(A=A, kind=kind, **src_kw)
+        res = dict(action_return=np.zeros((n, nA)), action_cost=np.zeros((n, nA)), action_step_length=np.zeros((n, nA)),
+                   other_return=np.zeros((A - 1, n)), mean_cost=np.zeros(n), total_steps=np.zeros(1, dtype=np.uint64))
+        out = ActionValuesOut()
+        out.mem = MEM_HOST
+        for k in res:
+            setattr(out, k, res[k].ctypes.data)
+        rc = self.lib.mamcts_action_values_crossing_i32(self.h, C.byref(mp), C.byref(cp), n, MEM_HOST, _vp(x), _vp(last_a),
+                                                        _vp(flags_a), _vp(depth_a), C.byref(src), C.byref(out))
+        self._check(rc, "mamcts_action_values_crossing_i32")
+        res["total_steps"] = int(res["total_steps"][0])
+        del keep
+        return res
+
     def rollout_crossing_f32(self, mp: Params, cp, x, last=None, flags=None, depth=None, K: int = 1,
                              kind: int = SRC_PHILOX, parity: bool = False, replay_actions=None,
                              replay_steps=None, **src_kw):

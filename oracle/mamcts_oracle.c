@@ -279,6 +279,41 @@ void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* s
   out->final_state.terminal = (uint8_t)orc_is_terminal(env, &state);
 }
 
+/* mcts/heuristics/action_value_random_heuristic.h:27-112 (see the header for the arithmetic). */
+void orc_action_values(const orc_env* env, const mamcts_params* mp, const orc_state* start, uint32_t start_depth,
+                       int32_t kind, const uint32_t* const_actions, uint64_t seed, uint32_t stream_hi,
+                       uint32_t stream_lo, orc_action_values_result* out) {
+  const uint32_t A = env->num_agents;
+  const uint32_t nA = env->num_actions[0];
+  const double gamma = mp->discount_factor;
+  memset(out, 0, sizeof(*out));
+  if (orc_is_terminal(env, start)) return;                       /* :38 - no action is tried */
+  for (uint32_t a = 0; a < nA; ++a) {
+    int32_t act[ORC_MAX_AGENTS];
+    const uint32_t lo = stream_lo * nA + a;
+    act[0] = (int32_t)a;                                         /* :41 */
+    for (uint32_t j = 1; j < A; ++j)                             /* :43-47: a fresh statistic's choice */
+      act[j] = kind == MAMCTS_SRC_REFERENCE_CONST
+                   ? (int32_t)const_actions[j]
+                   : (int32_t)orc_philox_draw(seed, stream_hi ^ 0x80000000u, lo, A, 0, j, env->num_actions[j]);
+    orc_state next;
+    double r0 = 0.0, c0 = 0.0;
+    orc_crossing_execute(&env->crossing, start, act, &next, &r0, &c0);   /* :52 */
+    orc_rollout_result rr;
+    orc_rollout(env, mp, &next, start_depth + 1, kind, NULL, 0, const_actions, seed, stream_hi, lo, NULL, NULL, &rr,
+                NULL, 0);                                        /* :58-61 */
+    out->action_return[a] = 0.0 + (gamma * r0 + gamma * rr.ego_return);  /* :64-65 */
+    for (uint32_t j = 0; j + 1 < A; ++j)                         /* :66-71 on the tied map: rewards[1..] are 0 */
+      out->other_return[j] = rr.other_return[j] + (gamma * 0.0 + gamma * 0.0);
+    out->action_cost[a] = 0.0 + (c0 + rr.cost0);                 /* :73-81 */
+    out->action_len[a] = 0.0 + (1.0 + rr.step_length);           /* :83-84 */
+    out->steps += 1 + rr.steps;
+  }
+  double mean = 0.0;                                             /* :97-103, unordered_map order: last first */
+  for (uint32_t a = nA; a-- > 0;) mean += out->action_cost[a];
+  out->mean_cost = mean / (double)nA;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* CrossingState<float>                                                                       */
 /* ------------------------------------------------------------------------------------------ */

@@ -88,6 +88,34 @@ void orc_rollout(const orc_env* env, const mamcts_params* mp, const orc_state* s
                  uint32_t stream_lo, const int32_t* gap_lo, const int32_t* gap_hi,
                  orc_rollout_result* out, double* reward_trace, uint32_t trace_cap);
 
+/* ---- per-ego-action heuristic: ActionValueRandomHeuristic::calculate_heuristic_values
+ * (mcts/heuristics/action_value_random_heuristic.h:27-112), the part before the statistics are filled:
+ * for every ego action a one first step (the other agents act as a fresh statistic makes them act) and one
+ * RandomHeuristic::rollout from the resulting state at depth + 1 (:37-61), then
+ *   action_return[a] = gamma * r_ego + gamma * rollout return      (:64-65)
+ *   action_cost[a]   = first-step cost[0] + rollout cost[0]         (:73-81, not discounted)
+ *   action_len[a]    = step length + rollout length                (:83-84)
+ *   other_return[j]  = what the LAST action's rollout returned for other j, plus gamma * its first-step reward
+ *                      (:58-60 ties the rollout's map to the accumulator itself, so earlier actions are overwritten)
+ *   mean_cost        = the action costs added up in the iteration order of the reference's
+ *                      std::unordered_map<ActionIdx, EgoCosts> (libstdc++: last inserted first) / nA_ego (:97-103)
+ * A terminal start state runs no action at all (:38): everything is 0.
+ * Action sources: REFERENCE_CONST (const_actions[agent], the first-draw constants) and PHILOX: the first
+ * step's other-agent draws are (step 0, agent j) of stream (stream_hi ^ 0x80000000, stream_lo * nA_ego + a), the
+ * rollout of action a is stream (stream_hi, stream_lo * nA_ego + a). CrossingState<int> only. */
+typedef struct orc_action_values_result {
+  double action_return[ORC_MAX_ACTIONS];
+  double action_cost[ORC_MAX_ACTIONS];
+  double action_len[ORC_MAX_ACTIONS];
+  double other_return[ORC_MAX_AGENTS];
+  double mean_cost;
+  uint32_t steps;   /* execute() calls: first steps + rollout steps */
+} orc_action_values_result;
+
+void orc_action_values(const orc_env* env, const mamcts_params* mp, const orc_state* start, uint32_t start_depth,
+                       int32_t kind, const uint32_t* const_actions, uint64_t seed, uint32_t stream_hi,
+                       uint32_t stream_lo, orc_action_values_result* out);
+
 /* The K-rollout mean of one leaf in the engine's fixed reduction order.
  * vals[k], k < K. K in {1,2,4,8,16} or a multiple of 32 (<=256) or a multiple of 256. */
 double orc_reduce_mean(const double* vals, uint32_t K);

@@ -23,6 +23,7 @@
 
 #include "mcts/mcts.h"
 #include "mcts/heuristics/random_heuristic.h"
+#include "mcts/heuristics/action_value_random_heuristic.h"
 #include "mcts/statistics/uct_statistic.h"
 #include "mcts/hypothesis/hypothesis_statistic.h"
 #include "environments/crossing_state.h"
@@ -831,6 +832,72 @@ int ref_merge_uct(const mamcts_params* mp, uint32_t n, uint32_t num_actions, uin
   double latest;
   UctTest::read_stat(merged, merged_value, &latest, merged_visits, merged_q, merged_n, max_actions);
   *best_action = static_cast<uint32_t>(merged.get_best_action());
+  return 0;
+}
+
+// ---- ActionValueRandomHeuristic (mcts/heuristics/action_value_random_heuristic.h:27-112) --------------------
+// Its non-cost-constrained branch calls a map-valued SE::set_heuristic_estimate(action_returns, action_costs)
+// (:93) that UctStatistic does not offer, so the reference only ever instantiates it with
+// CostConstrainedStatistic (needs OR-tools). These two test-only adapters add exactly that overload (and let
+// the mean cost handed to the other agents' statistics be read), so the reference's own loop :37-85 compiles
+// and runs unmodified as the checker of mamcts_action_values_crossing_i32.
+namespace {
+class AvEgoStat : public UctStatistic {
+ public:
+  using UctStatistic::UctStatistic;
+  using UctStatistic::set_heuristic_estimate;
+  void set_heuristic_estimate(const std::unordered_map<ActionIdx, Reward>& action_returns,
+                              const std::unordered_map<ActionIdx, EgoCosts>& action_costs) {
+    returns = action_returns;
+    costs = action_costs;
+    set_heuristic_estimate_from_backpropagated(action_returns);   // uct_statistic.h:156-163
+  }
+  std::unordered_map<ActionIdx, Reward> returns;
+  std::unordered_map<ActionIdx, EgoCosts> costs;
+};
+class AvOtherStat : public UctStatistic {
+ public:
+  using UctStatistic::UctStatistic;
+  void set_heuristic_estimate(const Reward& accum_rewards, const EgoCosts& accum_ego_cost) {
+    seen_cost = accum_ego_cost;
+    reward = accum_rewards;
+    UctStatistic::set_heuristic_estimate(accum_rewards, accum_ego_cost);
+  }
+  EgoCosts seen_cost;
+  Reward reward = 0.0;
+};
+}  // namespace
+
+extern "C" int ref_action_values_crossing(const mamcts_params* mp, const mamcts_crossing_params* cp, uint32_t n,
+                                          const int32_t* x, const int32_t* last, const uint8_t* flags,
+                                          const uint32_t* depth, uint32_t max_actions, double* action_return,
+                                          double* action_cost, double* other_ret, double* mean_cost) {
+  const MctsParameters rp = to_ref_params(*mp);
+  CrossingWorld world(*cp);
+  const uint32_t A = cp->num_other_agents + 1;
+  using S = CrossingState<int>;
+  using H = ActionValueRandomHeuristic;
+  using Node = StageNode<S, AvEgoStat, AvOtherStat, H>;
+  for (uint32_t i = 0; i < n; ++i) {
+    std::vector<int32_t> xi(A), li(A);
+    for (uint32_t a = 0; a < A; ++a) { xi[a] = x[a * n + i]; li[a] = last ? last[a * n + i] : 2; }
+    auto state = world.make(xi.data(), li.data(), flags ? (flags[i] & 1) : false);
+    const unsigned d = depth ? depth[i] : 0;
+    auto node = std::make_shared<Node, std::shared_ptr<Node>, std::shared_ptr<S>, const JointAction&, const unsigned int&>(
+        nullptr, state->clone(), JointAction(), d, rp);
+    H heuristic(rp);
+    auto result = heuristic.calculate_heuristic_values<S, AvEgoStat, AvOtherStat, H>(node);
+    for (uint32_t a = 0; a < max_actions; ++a) { action_return[(size_t)i * max_actions + a] = 0.0; action_cost[(size_t)i * max_actions + a] = 0.0; }
+    for (const auto& kv : result.first.returns) action_return[(size_t)i * max_actions + kv.first] = kv.second;
+    for (const auto& kv : result.first.costs) action_cost[(size_t)i * max_actions + kv.first] = kv.second.empty() ? 0.0 : kv.second[0];
+    uint32_t j = 0;
+    for (auto ai : state->get_other_agent_idx()) {
+      const AvOtherStat& so = result.second.at(ai);
+      other_ret[(size_t)j * n + i] = so.reward;
+      mean_cost[i] = so.seen_cost.empty() ? 0.0 : so.seen_cost[0];
+      ++j;
+    }
+  }
   return 0;
 }
 

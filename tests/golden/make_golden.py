@@ -316,6 +316,28 @@ def gen_merge():
     dump("merge.json", cases)
 
 
+def gen_action_values():
+    """ActionValueRandomHeuristic::calculate_heuristic_values (action_value_random_heuristic.h:27-112) run by the
+    reference's own loop (oracle/ref_driver.cc: ref_action_values_crossing) on random CrossingState<int> leaves."""
+    rng = np.random.default_rng(2024)
+    cases = []
+    for others, seed, kw in ((1, 1000, {}), (2, 1000, {}), (3, 7, dict(chain_length=41, ego_goal_pos=26)),
+                             (7, 42, {}), (1, 5, dict(reward_step=-1.0, cost_only_collision=1))):
+        cp = default_crossing_params(num_other_agents=others, **kw)
+        mp = default_params(random_seed=seed, rh_max_number_of_iterations=50, max_search_depth=60)
+        A, n = others + 1, 48
+        x = rng.integers(-1, cp.chain_length + 3, size=(A, n)).astype(np.int32)
+        last = rng.integers(-2, 4, size=(A, n)).astype(np.int32)
+        flags = (rng.random(n) < 0.1).astype(np.uint8)
+        depth = rng.choice([0, 3, 20, 58, 59, 60], size=n).astype(np.uint32)
+        r = O.ref_action_values_crossing(mp, cp, x, last, flags, depth)
+        cases.append(dict(num_others=others, seed=seed, params=kw, x=x.tolist(), last=last.tolist(), flags=flags.tolist(),
+                          depth=depth.tolist(), const_actions=[O.ref_expand_order(mp, 4 if a == 0 else 7)[0] for a in range(A)],
+                          action_return=fhex(r["action_return"]), action_cost=fhex(r["action_cost"]),
+                          other_return=fhex(r["other_return"]), mean_cost=fhex(r["mean_cost"])))
+    dump("action_values.json", cases)
+
+
 if __name__ == "__main__":
     assert O.reference_available(), "needs /root/reference (or a prebuilt oracle/_ref)"
     gen_expand_order()
@@ -326,3 +348,4 @@ if __name__ == "__main__":
     gen_float_domain()
     gen_search()
     gen_merge()
+    gen_action_values()

@@ -271,6 +271,58 @@ def rollout_batch(env: OrcEnv, mp: Params, x, last=None, flags=None, depth=None,
     return out
 
 
+class OrcActionValuesResult(C.Structure):
+    _fields_ = [("action_return", C.c_double * MAX_ACTIONS), ("action_cost", C.c_double * MAX_ACTIONS),
+                ("action_len", C.c_double * MAX_ACTIONS), ("other_return", C.c_double * MAX_AGENTS),
+                ("mean_cost", C.c_double), ("steps", C.c_uint32)]
+
+
+def action_values_batch(env: OrcEnv, mp: Params, x, last=None, flags=None, depth=None, kind=SRC_PHILOX,
+                        const_actions=None, seed=0, stream_hi=None, stream_hi_base=0, stream_lo_base=0,
+                        stream_lo=None):
+    """Oracle counterpart of mamcts_action_values_crossing_i32 (ActionValueRandomHeuristic's per-ego-action
+    first step + rollout, action_value_random_heuristic.h:37-85) over n leaves; same output layout."""
+    x = np.asarray(x, dtype=np.int32)
+    A, nA = env.num_agents, env.num_actions[0]
+    n = x.shape[1]
+    out = dict(action_return=np.zeros((n, nA)), action_cost=np.zeros((n, nA)), action_step_length=np.zeros((n, nA)),
+               other_return=np.zeros((max(A - 1, 0), n)), mean_cost=np.zeros(n), total_steps=0)
+    ca = (C.c_uint32 * MAX_AGENTS)(*(const_actions or []))
+    for i in range(n):
+        st = make_state(x[:, i], None if last is None else np.asarray(last)[:, i],
+                        bool(flags[i] & 1) if flags is not None else False)
+        hi = int(stream_hi[i]) if stream_hi is not None else stream_hi_base
+        lo = (int(stream_lo[i]) if stream_lo is not None else (stream_lo_base + i)) & 0xFFFFFFFF
+        res = OrcActionValuesResult()
+        oracle().orc_action_values(C.byref(env), C.byref(mp), C.byref(st), C.c_uint32(int(depth[i]) if depth is not None else 0),
+                                   C.c_int32(kind), ca, C.c_uint64(seed), C.c_uint32(hi), C.c_uint32(lo), C.byref(res))
+        out["action_return"][i] = res.action_return[:nA]
+        out["action_cost"][i] = res.action_cost[:nA]
+        out["action_step_length"][i] = res.action_len[:nA]
+        out["other_return"][:, i] = res.other_return[:A - 1]
+        out["mean_cost"][i] = res.mean_cost
+        out["total_steps"] += res.steps
+    return out
+
+
+def ref_action_values_crossing(mp: Params, cp: CrossingParams, x, last=None, flags=None, depth=None):
+    """The reference's own ActionValueRandomHeuristic::calculate_heuristic_values (with the two test-only
+    statistic adapters of oracle/ref_driver.cc) over n leaves."""
+    x = np.ascontiguousarray(x, dtype=np.int32)
+    A = cp.num_other_agents + 1
+    n = x.shape[1]
+    nA = cp.num_ego_actions
+    la = None if last is None else np.ascontiguousarray(last, dtype=np.int32)
+    fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+    de = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+    ret, cost = np.zeros((n, nA)), np.zeros((n, nA))
+    oth, mean = np.zeros((max(A - 1, 1), n)), np.zeros(n)
+    reference().ref_action_values_crossing(C.byref(mp), C.byref(cp), C.c_uint32(n), _ptr(x), _ptr(la) if la is not None else None,
+                                           _ptr(fl) if fl is not None else None, _ptr(de) if de is not None else None,
+                                           C.c_uint32(nA), _ptr(ret), _ptr(cost), _ptr(oth), _ptr(mean))
+    return dict(action_return=ret, action_cost=cost, other_return=oth[:A - 1], mean_cost=mean)
+
+
 # ------------------------------------------------------------------------------------------------
 # search (oracle restatement)
 # ------------------------------------------------------------------------------------------------

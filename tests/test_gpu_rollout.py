@@ -284,3 +284,43 @@ def test_moments_inside_the_rollout_call(engine):
     assert_bit_equal(a["moments"], b["moments"], "moments K=32 vs K=1")
     assert_bit_equal(b["moments"], engine.rollout_moments(b["ego_return"], b["other_return"]), "in-call vs separate call")
     assert np.allclose(a["moments"][0] / (n * K), b["ego_return"].mean(), rtol=1e-12, atol=1e-15)
+
+
+def test_action_values_match_reference_golden_and_oracle(engine):
+    """mamcts_action_values_crossing_i32 = the compute part of ActionValueRandomHeuristic
+    (action_value_random_heuristic.h:37-85): REFERENCE_CONST against the committed vectors of the reference's own
+    loop (bit for bit), PHILOX against the oracle on the same streams (bit for bit), 1 to 7 other agents."""
+    from helpers import assert_bit_equal
+    for case in golden("action_values.json"):
+        cp = default_crossing_params(num_other_agents=case["num_others"], **case["params"])
+        mp = default_params(random_seed=case["seed"], rh_max_number_of_iterations=50, max_search_depth=60)
+        x = np.array(case["x"], dtype=np.int32)
+        n, nA, J = x.shape[1], cp.num_ego_actions, case["num_others"]
+        last, flags, depth = np.array(case["last"]), np.array(case["flags"], dtype=np.uint8), np.array(case["depth"])
+        got = engine.action_values_crossing(mp, cp, x, last, flags, depth, kind=SRC_REFERENCE_CONST,
+                                            const_actions=case["const_actions"])
+        assert_bit_equal(got["action_return"], unhex(case["action_return"], (n, nA)), "action returns")
+        assert_bit_equal(got["action_cost"], unhex(case["action_cost"], (n, nA)), "action costs")
+        assert_bit_equal(got["other_return"], unhex(case["other_return"], (J, n)), "other returns")
+        assert_bit_equal(got["mean_cost"], unhex(case["mean_cost"]), "mean cost")
+        # uniform Philox actions: the oracle twin on the same streams, per-leaf stream ids
+        rng = np.random.default_rng(case["seed"])
+        hi = rng.integers(0, 2**31, size=n).astype(np.uint32)
+        lo = rng.integers(0, 2**20, size=n).astype(np.uint32)
+        a = engine.action_values_crossing(mp, cp, x, last, flags, depth, kind=SRC_PHILOX, seed=77, stream_hi=hi, stream_lo=lo)
+        b = O.action_values_batch(O.make_env(cp=cp), mp, x, last, flags, depth, kind=SRC_PHILOX, seed=77, stream_hi=hi, stream_lo=lo)
+        for k in ("action_return", "action_cost", "action_step_length", "other_return", "mean_cost"):
+            assert_bit_equal(a[k], b[k], f"philox {k}")
+        assert a["total_steps"] == b["total_steps"] > 0
+        assert np.all(a["action_return"][flags == 1] == 0.0) and np.all(a["action_step_length"][flags == 1] == 0.0)
+    # a larger batch: 20 000 leaves x 4 actions in one call, stream ids from the bases
+    cp = default_crossing_params(num_other_agents=2)
+    mp = default_params(rh_max_number_of_iterations=50)
+    n = 20000
+    x = np.random.default_rng(1).integers(0, 12, size=(3, n)).astype(np.int32)
+    a = engine.action_values_crossing(mp, cp, x, kind=SRC_PHILOX, seed=5, stream_hi_base=9, stream_lo_base=100)
+    sel = np.arange(0, n, 997)
+    b = O.action_values_batch(O.make_env(cp=cp), mp, x[:, sel], kind=SRC_PHILOX, seed=5,
+                              stream_hi=np.full(sel.size, 9), stream_lo=100 + sel)
+    assert_bit_equal(a["action_return"][sel], b["action_return"], "large batch action returns")
+    assert_bit_equal(a["mean_cost"][sel], b["mean_cost"], "large batch mean cost")

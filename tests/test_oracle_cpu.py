@@ -318,3 +318,47 @@ def test_expand_order_golden_equals_reference():
         mp = default_params(random_seed=int(seed))
         for n, order in per_n.items():
             assert O.ref_expand_order(mp, int(n)) == order
+
+
+@pytest.mark.skipif(not O.reference_available(), reason="compiled reference not on this box")
+def test_oracle_action_values_equal_reference():
+    """ActionValueRandomHeuristic's per-ego-action first step + rollout (action_value_random_heuristic.h:37-85),
+    executed by the REFERENCE'S OWN loop (compiled with the two test-only statistic adapters of ref_driver.cc),
+    against the restatement orc_action_values: action returns, action costs, the other agents' returns and
+    the mean cost handed to their statistics, bit for bit - random states, depths near the depth limit,
+    terminal states, other parameter sets and seeds (the first-draw constants change with the seed)."""
+    rng = np.random.default_rng(11)
+    for others, seed, kw in ((1, 1000, {}), (2, 1000, {}), (3, 7, {}), (2, 42, dict(chain_length=41, ego_goal_pos=26)),
+                             (1, 5, dict(reward_step=-1.0, cost_only_collision=1))):
+        cp = default_crossing_params(num_other_agents=others, **kw)
+        mp = default_params(random_seed=seed, rh_max_number_of_iterations=50, max_search_depth=60)
+        A, n = others + 1, 160
+        x = rng.integers(-1, cp.chain_length + 3, size=(A, n)).astype(np.int32)
+        last = rng.integers(-2, 4, size=(A, n)).astype(np.int32)
+        flags = (rng.random(n) < 0.1).astype(np.uint8)
+        depth = rng.choice([0, 3, 20, 58, 59, 60], size=n).astype(np.uint32)
+        ref = O.ref_action_values_crossing(mp, cp, x, last, flags, depth)
+        env = O.make_env(cp=cp)
+        const = [O.ref_expand_order(mp, env.num_actions[a])[0] for a in range(A)]
+        orc = O.action_values_batch(env, mp, x, last, flags, depth, kind=SRC_REFERENCE_CONST, const_actions=const)
+        assert_bit_equal(orc["action_return"], ref["action_return"], "action returns")
+        assert_bit_equal(orc["action_cost"], ref["action_cost"], "action costs")
+        assert_bit_equal(orc["other_return"], ref["other_return"], "other returns")
+        assert_bit_equal(orc["mean_cost"], ref["mean_cost"], "mean cost")
+        assert np.all(orc["action_return"][flags == 1] == 0.0)
+
+
+def test_oracle_action_values_equal_golden():
+    """The committed vectors of the reference's ActionValueRandomHeuristic loop (tests/golden/action_values.json,
+    generated by make_golden.py from oracle/_ref) against the restatement - runs wherever the oracle builds."""
+    for case in golden("action_values.json"):
+        cp = default_crossing_params(num_other_agents=case["num_others"], **case["params"])
+        mp = default_params(random_seed=case["seed"], rh_max_number_of_iterations=50, max_search_depth=60)
+        x = np.array(case["x"], dtype=np.int32)
+        n, nA = x.shape[1], cp.num_ego_actions
+        orc = O.action_values_batch(O.make_env(cp=cp), mp, x, np.array(case["last"]), np.array(case["flags"], dtype=np.uint8),
+                                    np.array(case["depth"]), kind=SRC_REFERENCE_CONST, const_actions=case["const_actions"])
+        assert_bit_equal(orc["action_return"], unhex(case["action_return"], (n, nA)), "action returns")
+        assert_bit_equal(orc["action_cost"], unhex(case["action_cost"], (n, nA)), "action costs")
+        assert_bit_equal(orc["other_return"], unhex(case["other_return"], (case["num_others"], n)), "other returns")
+        assert_bit_equal(orc["mean_cost"], unhex(case["mean_cost"]), "mean cost")
