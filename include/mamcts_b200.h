@@ -445,6 +445,78 @@ typedef struct mamcts_search_config {
 
 typedef struct mamcts_search mamcts_search;
 
+/* ---- hypothesis-MCTS (BASELINE configs[3]): Mcts<CrossingState<int>, UctStatistic, HypothesisStatistic,
+ * RandomHeuristic>::search(state, belief_tracker) on the device (mcts/mcts.h:143-164) -------------------------- */
+
+/* MctsParameters::hypothesis_statistic (mcts/mcts_parameters.h:71-79, defaults :118-124) and the one
+ * cost_constrained_statistic field HypothesisStatistic reads (USE_CHANCE_CONSTRAINED_UPDATES[0],
+ * hypothesis_statistic.h:116). */
+typedef struct mamcts_hypothesis_params {
+  double upper_cost_bound;                    /* UPPER_COST_BOUND */
+  double lower_cost_bound;                    /* LOWER_COST_BOUND */
+  double pw_k;                                /* PROGRESSIVE_WIDENING_K */
+  double pw_alpha;                            /* PROGRESSIVE_WIDENING_ALPHA */
+  double exploration_constant;                /* EXPLORATION_CONSTANT */
+  uint32_t cost_based_action_selection;       /* COST_BASED_ACTION_SELECTION */
+  uint32_t progressive_widening_hypothesis_based; /* PROGRESSIVE_WIDENING_HYPOTHESIS_BASED: must be 1 (the default) */
+  uint32_t chance_constrained_update;         /* USE_CHANCE_CONSTRAINED_UPDATES[0] (empty vector = 0) */
+  uint32_t policy_random_seed;                /* CrossingStateParameters::OTHER_AGENTS_POLICY_RANDOM_SEED */
+} mamcts_hypothesis_params;
+void mamcts_default_hypothesis_params(mamcts_hypothesis_params* p);
+
+#define MAMCTS_MAX_HYPOTHESES 4
+#define MAMCTS_HYP_MAX_OTHER_ACTIONS 8     /* MAX_VELOCITY_OTHER - MIN_VELOCITY_OTHER + 1 (default 7) */
+
+typedef struct mamcts_hyp_search_config {
+  uint32_t num_trees;
+  uint32_t first_tree_id;
+  uint32_t max_nodes_per_tree;         /* 0 = min(MAX_NUMBER_OF_NODES, iterations) + 1 */
+  uint32_t num_hypotheses;             /* H <= MAMCTS_MAX_HYPOTHESES: CrossingState::add_hypothesis calls, in order */
+  int32_t gap_lo[MAMCTS_MAX_HYPOTHESES];   /* desired-gap range of hypothesis h (AgentPolicyCrossingState ctor) */
+  int32_t gap_hi[MAMCTS_MAX_HYPOTHESES];
+  /* 0: every tree is the reference's tree (all random streams start where the reference's generators start).
+   * 1: tree t starts its policy / statistic generators and its hypothesis sequence at offsets derived from its
+   *    global id, i.e. differently seeded generators per tree: independent root-parallel trees. */
+  uint32_t decorrelate_trees;
+  uint32_t reserved;
+  mamcts_params mcts;
+  mamcts_hypothesis_params hypothesis;
+  mamcts_crossing_params crossing;
+} mamcts_hyp_search_config;
+
+/* The hypothesis every other agent is assigned in every iteration, as HypothesisBeliefTracker::
+ * sample_current_hypothesis (mcts/hypothesis/hypothesis_belief_tracker.h:136-149) draws it: a
+ * std::discrete_distribution over the agent's beliefs from the tracker's mt19937, agents in the order the
+ * tracker's std::unordered_map<AgentIdx, ...> yields them (libstdc++, like mamcts_reference_expand_order).
+ * beliefs: [num_others][num_hypotheses] (agent ids 1..num_others); the generator is seeded with `seed`
+ * (RANDOM_SEED_HYPOTHESIS_SAMPLING) and `skip_iterations` earlier sample_current_hypothesis() calls with the
+ * same beliefs are discarded first. out: [n_iterations][num_others] (positional). A C++ host that owns a real
+ * HypothesisBeliefTracker copies it and samples from the copy instead (mamcts_b200/host/device_hypothesis_mcts.h). */
+int mamcts_reference_hypothesis_sequence(uint32_t seed, const float* beliefs, uint32_t num_others,
+                                         uint32_t num_hypotheses, uint32_t skip_iterations,
+                                         uint32_t n_iterations, uint8_t* out);
+
+/* T device-resident hypothesis-MCTS trees: the ego agent's UctStatistic, every other agent's HypothesisStatistic
+ * (choose_next_action with hypothesis-based progressive widening, random or worst-case selection among the
+ * expanded actions, hypothesis_statistic.h:62-98,178-202; update_statistic :112-134), the hypothesis policies
+ * acting inside the tree and the rollouts (AgentPolicyCrossingState<int>::act, crossing_state_agent_policy.h:
+ * 35-55,68-75), all on the device. hypothesis_sequence: [MAX_NUMBER_OF_ITERATIONS][num_others] HOST, see above.
+ * The reference's generators (one mt19937 per policy object copied with every state, one per statistic) are
+ * reproduced by stream POSITIONS into host-tabulated draws of the same libstdc++ distributions, so with
+ * decorrelate_trees = 0 every tree equals the reference's tree bit for bit. The handle is a mamcts_search:
+ * mamcts_search_run / _reset / _counters / _root_stats (agent 0) / _merge_roots / _dump_tree / _destroy apply.
+ * Dump record of a node (doubles): depth, joint-action code (ego + M * sum_j (v_j - MIN_VELOCITY_OTHER) M^j,
+ * M = max(nA_ego, MA)), visit_count, children; ego {N, V, G, n[NE], q[NE]}; per other agent {N, ego cost value,
+ * latest ego cost, num_expanded_actions_, visits under HYPOTHESIS_ID_NOT_SET, 0; per hypothesis {visits, number of
+ * expanded actions, the actions in the iteration order of the reference's unordered_map (-1 padded)}; per
+ * (hypothesis, action) {count (-1 = absent), cost}} with MA = MAX_VELOCITY_OTHER - MIN_VELOCITY_OTHER + 1. */
+int mamcts_hyp_search_create(mamcts_engine* e, const mamcts_hyp_search_config* cfg, const int32_t* root_x,
+                             const int32_t* root_last_action, const uint8_t* hypothesis_sequence,
+                             mamcts_search** out);
+/* New decision: new root state and a new hypothesis sequence (NULL keeps the resident one). */
+int mamcts_hyp_search_reset(mamcts_search* s, const int32_t* root_x, const int32_t* root_last_action,
+                            const uint8_t* hypothesis_sequence);
+
 /* Allocates T tree arenas in HBM and resets every tree to the given root state
  * (root_x / root_last_action: [A] for CrossingState, root_x[0] = state_length for SimpleState). */
 int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, const int32_t* root_x,

@@ -5,7 +5,8 @@ in include/mamcts_b200.h). This package is the thin Python binding over that ABI
 fallback.
 """
 from . import _abi  # noqa: F401
-from .params import (default_crossing_params, default_crossing_params_f32, default_params,  # noqa: F401
-                     default_simple_params)
+from .params import (default_crossing_params, default_crossing_params_f32, default_hypothesis_params,  # noqa: F401
+                     default_params, default_simple_params)
 
-__all__ = ["default_params", "default_crossing_params", "default_crossing_params_f32", "default_simple_params"]
+__all__ = ["default_params", "default_crossing_params", "default_crossing_params_f32", "default_simple_params",
+           "default_hypothesis_params"]

@@ -150,6 +150,41 @@ class RolloutOut(C.Structure):
     ]
 
 
+class HypothesisParams(C.Structure):
+    """mamcts_hypothesis_params: MctsParameters::hypothesis_statistic (reference mcts/mcts_parameters.h:71-79)."""
+    _fields_ = [
+        ("upper_cost_bound", C.c_double),
+        ("lower_cost_bound", C.c_double),
+        ("pw_k", C.c_double),
+        ("pw_alpha", C.c_double),
+        ("exploration_constant", C.c_double),
+        ("cost_based_action_selection", C.c_uint32),
+        ("progressive_widening_hypothesis_based", C.c_uint32),
+        ("chance_constrained_update", C.c_uint32),
+        ("policy_random_seed", C.c_uint32),
+    ]
+
+
+MAX_HYPOTHESES = 4
+HYP_MAX_OTHER_ACTIONS = 8
+
+
+class HypSearchConfig(C.Structure):
+    _fields_ = [
+        ("num_trees", C.c_uint32),
+        ("first_tree_id", C.c_uint32),
+        ("max_nodes_per_tree", C.c_uint32),
+        ("num_hypotheses", C.c_uint32),
+        ("gap_lo", C.c_int32 * MAX_HYPOTHESES),
+        ("gap_hi", C.c_int32 * MAX_HYPOTHESES),
+        ("decorrelate_trees", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("mcts", Params),
+        ("hypothesis", HypothesisParams),
+        ("crossing", CrossingParams),
+    ]
+
+
 class ActionValuesOut(C.Structure):
     _fields_ = [
         ("mem", C.c_int32),
@@ -289,6 +324,10 @@ def load() -> C.CDLL:
         "mamcts_comm_init_rank": (i32, [vp, c_u8_p, i32, i32]),
         "mamcts_comm_destroy": (i32, [vp]),
         "mamcts_allreduce_f64": (i32, [vp, vp, sz]),
+        "mamcts_default_hypothesis_params": (None, [P(HypothesisParams)]),
+        "mamcts_reference_hypothesis_sequence": (i32, [u32, vp, u32, u32, u32, u32, c_u8_p]),
+        "mamcts_hyp_search_create": (i32, [vp, P(HypSearchConfig), c_i32_p, c_i32_p, c_u8_p, P(vp)]),
+        "mamcts_hyp_search_reset": (i32, [vp, c_i32_p, c_i32_p, c_u8_p]),
         "mamcts_search_create": (i32, [vp, P(SearchConfig), c_i32_p, c_i32_p, P(vp)]),
         "mamcts_search_destroy": (i32, [vp]),
         "mamcts_search_reset": (i32, [vp, c_i32_p, c_i32_p]),
@@ -318,6 +357,8 @@ EXPORTED_SYMBOLS = [
     "mamcts_rollout_crossing_f32", "mamcts_default_crossing_params_f32", "mamcts_action_values_crossing_i32",
     "mamcts_backup_uct", "mamcts_backup_hypothesis", "mamcts_root_merge", "mamcts_rollout_moments", "mamcts_comm_get_unique_id",
     "mamcts_comm_init_rank", "mamcts_comm_destroy", "mamcts_allreduce_f64",
+    "mamcts_default_hypothesis_params", "mamcts_reference_hypothesis_sequence", "mamcts_hyp_search_create",
+    "mamcts_hyp_search_reset",
     "mamcts_search_create", "mamcts_search_destroy", "mamcts_search_reset", "mamcts_search_run",
     "mamcts_search_counters", "mamcts_search_exact_ucb_evaluations", "mamcts_search_root_stats", "mamcts_search_merge_roots",
     "mamcts_search_dump_tree",

@@ -21,54 +21,8 @@
 #include "engine.h"
 #include "root_merge.h"
 #include "search_compact.cuh"
+#include "search_host.h"
 #include "search_kernel.cuh"
-
-// Type-erased handle behind the C ABI; one concrete SearchT per compiled (environment, action-count,
-// child-index) combination.
-struct mamcts_search {
-  mamcts_engine* e = nullptr;
-  mamcts_search_config cfg;
-  mamcts::SearchParams p;
-  mamcts::SearchTables tab;  // host copy
-  uint32_t A = 0, state_ints = 0;
-  void* d_nodes = nullptr;
-  uint32_t* d_hash = nullptr;
-  uint32_t* d_tree_nodes = nullptr;
-  uint32_t* d_tree_iters = nullptr;
-  mamcts::SearchTables* d_tab = nullptr;
-  double* d_log = nullptr;
-  double* d_disc = nullptr;
-  unsigned long long* d_counters = nullptr;
-  int32_t* d_root_x = nullptr;
-  // compact (two-tier) layout, search_compact.cuh
-  void* d_inner = nullptr;
-  void* d_leaves = nullptr;
-  uint32_t* d_tree_inner = nullptr;
-  uint32_t* d_tree_leaves = nullptr;
-  uint32_t max_inner = 0;
-  uint32_t iters_done = 0;
-  int block_threads = mamcts::kSearchThreads;
-
-  virtual ~mamcts_search() {}
-  virtual size_t node_bytes() const = 0;     // bytes of the record that carries the statistics
-  virtual size_t leaf_bytes() const { return 0; }
-  virtual bool uses_hash() const = 0;
-  virtual bool is_compact() const { return false; }
-  // first record (the root) of a tree and the distance between consecutive trees' roots
-  virtual const char* root_record(uint32_t tree) const {
-    return static_cast<const char*>(d_nodes) + node_bytes() * (size_t)tree * p.max_nodes;
-  }
-  // canonical depth-first export of one tree (mamcts_search_dump_tree)
-  virtual int dump(uint32_t tree, double* records, uint32_t capacity_records, uint32_t* num_records) = 0;
-  virtual int launch_reset() = 0;
-  virtual int launch_run(uint32_t iterations) = 0;
-  // host-side views of a node record copied back from the device
-  virtual void read_header(const void* node, uint32_t* parent, uint32_t* depth, uint32_t* visits,
-                           uint8_t* ja) const = 0;
-  virtual void read_stat(const void* node, uint32_t agent, double* value, double* latest,
-                         uint32_t* visits, uint32_t* nexp, double* q, uint32_t* n) const = 0;
-  virtual void root_gather(mamcts::RootGather* g) const = 0;
-};
 
 namespace mamcts {
 
@@ -387,10 +341,11 @@ static mamcts_search* make_search(const mamcts_search_config& cfg, uint32_t n_eg
   return nullptr;
 }
 
-static void free_search(mamcts_search* s) {
+void free_search(mamcts_search* s) {
   if (!s) return;
   cudaSetDevice(s->e->device);
   cudaStreamSynchronize(s->e->stream);
+  s->free_extra();
   cudaFree(s->d_inner); cudaFree(s->d_leaves); cudaFree(s->d_tree_inner); cudaFree(s->d_tree_leaves);
   cudaFree(s->d_nodes); cudaFree(s->d_hash); cudaFree(s->d_tree_nodes); cudaFree(s->d_tree_iters);
   cudaFree(s->d_tab); cudaFree(s->d_log); cudaFree(s->d_disc); cudaFree(s->d_counters); cudaFree(s->d_root_x);
@@ -399,9 +354,22 @@ static void free_search(mamcts_search* s) {
 
 // Device-side failures of the compact layout are counted (search_compact.cuh); every read-back
 // reports them instead of returning statistics of an unfinished search.
-static int check_search_health(mamcts_search* s) {
+static int check_search_health(mamcts_search* s) { return s->health(); }
+
+}  // namespace mamcts
+
+int mamcts_search::upload_root(const int32_t* root_x, const int32_t* /*root_last_action*/) {
+  int32_t rx[MAMCTS_MAX_AGENTS] = {0};
+  for (uint32_t i = 0; i < state_ints; ++i) rx[i] = root_x[i];
+  MAMCTS_CUDA(e, cudaMemcpyAsync(d_root_x, rx, sizeof(rx), cudaMemcpyHostToDevice, e->stream));
+  MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+  return MAMCTS_OK;
+}
+
+int mamcts_search::health() {
+  using namespace mamcts;
+  mamcts_search* s = this;
   if (!s->is_compact()) return MAMCTS_OK;
-  mamcts_engine* e = s->e;
   unsigned long long h[2] = {0, 0};
   MAMCTS_CUDA(e, cudaMemcpyAsync(h, s->d_counters + 6, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
   MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -413,8 +381,6 @@ static int check_search_health(mamcts_search* s) {
                 "use layout = MAMCTS_LAYOUT_CLASSIC for such searches");
   return MAMCTS_OK;
 }
-
-}  // namespace mamcts
 
 namespace mamcts {
 static int dump_classic(mamcts_search* s, uint32_t tree, double* records, uint32_t capacity_records,
@@ -673,16 +639,13 @@ int mamcts_search_destroy(mamcts_search* s) {
 }
 
 int mamcts_search_reset(mamcts_search* s, const int32_t* root_x, const int32_t* root_last_action) {
-  (void)root_last_action;
   if (!s) return fail(nullptr, MAMCTS_ERR_INVALID, "mamcts_search_reset: null handle");
   mamcts_engine* e = s->e;
   std::lock_guard<std::mutex> lock(e->mu);
   MAMCTS_CUDA(e, cudaSetDevice(e->device));
   if (root_x) {  // NULL: re-root at the state already resident on the device (no copy)
-    int32_t rx[MAMCTS_MAX_AGENTS] = {0};
-    for (uint32_t i = 0; i < s->state_ints; ++i) rx[i] = root_x[i];
-    MAMCTS_CUDA(e, cudaMemcpyAsync(s->d_root_x, rx, sizeof(rx), cudaMemcpyHostToDevice, e->stream));
-    MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+    const int rc = s->upload_root(root_x, root_last_action);
+    if (rc != MAMCTS_OK) return rc;
   }
   return s->launch_reset();
 }

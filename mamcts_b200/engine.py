@@ -581,3 +581,84 @@ class Search:
                                                             capacity, C.byref(cnt)),
                            "mamcts_search_dump_tree")
         return rec[:min(cnt.value, capacity)]
+
+
+def reference_hypothesis_sequence(seed: int, beliefs, skip_iterations: int, n_iterations: int) -> np.ndarray:
+    """The hypothesis of every other agent in every iteration as HypothesisBeliefTracker::sample_current_hypothesis
+    draws it (reference hypothesis_belief_tracker.h:136-149; mamcts_reference_hypothesis_sequence).
+    beliefs: [num_others, num_hypotheses]. Returns uint8 [n_iterations, num_others]."""
+    lib = _abi.load()
+    b = np.ascontiguousarray(beliefs, dtype=np.float32)
+    out = np.zeros((n_iterations, b.shape[0]), dtype=np.uint8)
+    rc = lib.mamcts_reference_hypothesis_sequence(seed, b.ctypes.data_as(C.c_void_p), b.shape[0], b.shape[1], skip_iterations,
+                                                  n_iterations, out.ctypes.data_as(_abi.c_u8_p))
+    if rc != 0:
+        raise MamctsError(lib.mamcts_last_error(None).decode())
+    return out
+
+
+class HypSearch(Search):
+    """T device-resident hypothesis-MCTS trees (mamcts_hyp_search_create): Mcts<CrossingState<int>, UctStatistic,
+    HypothesisStatistic, RandomHeuristic>::search(state, belief_tracker), reference mcts/mcts.h:143-164.
+    gaps: [(lo, hi)] desired-gap range per hypothesis; hypothesis_sequence: uint8 [iterations, num_others]."""
+
+    def __init__(self, engine: Engine, mp: Params, hp, cp: CrossingParams, num_trees: int, gaps, hypothesis_sequence,
+                 root_x=None, root_last=None, first_tree_id: int = 0, decorrelate_trees: bool = False,
+                 max_nodes_per_tree: int = 0):
+        from ._abi import HypSearchConfig
+        self.engine = engine
+        self.lib = engine.lib
+        cfg = HypSearchConfig()
+        cfg.num_trees = num_trees
+        cfg.first_tree_id = first_tree_id
+        cfg.max_nodes_per_tree = max_nodes_per_tree
+        cfg.num_hypotheses = len(gaps)
+        for h, (lo, hi) in enumerate(gaps):
+            cfg.gap_lo[h], cfg.gap_hi[h] = lo, hi
+        cfg.decorrelate_trees = 1 if decorrelate_trees else 0
+        cfg.mcts, cfg.hypothesis, cfg.crossing = mp, hp, cp
+        self.cfg = cfg
+        self.A = cp.num_other_agents + 1
+        self.num_actions = [cp.num_ego_actions] + [cp.num_other_actions] * (self.A - 1)
+        self.MA = cp.max_velocity_other - cp.min_velocity_other + 1
+        self.H = len(gaps)
+        rx, rl = self._root(root_x, root_last)
+        seq = np.ascontiguousarray(hypothesis_sequence, dtype=np.uint8)
+        if seq.shape != (mp.max_number_of_iterations, self.A - 1):
+            raise ValueError("hypothesis_sequence must be [MAX_NUMBER_OF_ITERATIONS, num_others]")
+        self.h = C.c_void_p()
+        rc = self.lib.mamcts_hyp_search_create(engine.h, C.byref(cfg), rx.ctypes.data_as(_abi.c_i32_p),
+                                               rl.ctypes.data_as(_abi.c_i32_p), seq.ctypes.data_as(_abi.c_u8_p),
+                                               C.byref(self.h))
+        engine._check(rc, "mamcts_hyp_search_create")
+        engine._searches.add(self)
+
+    def _root(self, root_x, root_last):
+        rx = np.zeros(_abi.MAX_AGENTS, dtype=np.int32)
+        rl = np.zeros(_abi.MAX_AGENTS, dtype=np.int32)
+        rx[:self.A] = [5] * self.A if root_x is None else list(root_x)
+        rl[:self.A] = [2] * self.A if root_last is None else list(root_last)
+        return rx, rl
+
+    def reset(self, root_x=None, root_last=None, hypothesis_sequence=None):
+        """New decision: root state (None = the resident one) and hypothesis sequence (None = the resident one)."""
+        px = pl = ps = None
+        if root_x is not None:
+            rx, rl = self._root(root_x, root_last)
+            px, pl = rx.ctypes.data_as(_abi.c_i32_p), rl.ctypes.data_as(_abi.c_i32_p)
+        if hypothesis_sequence is not None:
+            seq = np.ascontiguousarray(hypothesis_sequence, dtype=np.uint8)
+            ps = seq.ctypes.data_as(_abi.c_u8_p)
+        self.engine._check(self.lib.mamcts_hyp_search_reset(self.h, px, pl, ps), "mamcts_hyp_search_reset")
+
+    @property
+    def dump_stride(self) -> int:
+        NE = self.num_actions[0]
+        return 4 + (3 + 2 * NE) + (self.A - 1) * (6 + self.H * (2 + self.MA) + 2 * self.H * self.MA)
+
+    def dump_tree(self, tree: int, capacity: int):
+        rec = np.zeros((capacity, self.dump_stride))
+        cnt = C.c_uint32(0)
+        self.engine._check(self.lib.mamcts_search_dump_tree(self.h, tree, rec.ctypes.data_as(_abi.c_double_p),
+                                                            capacity, C.byref(cnt)), "mamcts_search_dump_tree")
+        return rec[:min(cnt.value, capacity)]

@@ -6,7 +6,7 @@ SimpleState constants                     : reference test/uct/simple_state.h:16
 """
 from __future__ import annotations
 
-from ._abi import CrossingParams, CrossingParamsF32, Params, SimpleParams
+from ._abi import CrossingParams, CrossingParamsF32, HypothesisParams, Params, SimpleParams
 
 
 def default_params(**over) -> Params:
@@ -29,6 +29,26 @@ def default_params(**over) -> Params:
             raise AttributeError(k)
         setattr(p, k, v)
     return p
+
+
+def default_hypothesis_params(**over) -> HypothesisParams:
+    """MctsParameters::hypothesis_statistic defaults (mcts_parameters.h:118-124) and the policy seed
+    (default_crossing_state_parameters: OTHER_AGENTS_POLICY_RANDOM_SEED = 1000)."""
+    h = HypothesisParams()
+    h.cost_based_action_selection = 0
+    h.lower_cost_bound = 0.0
+    h.upper_cost_bound = 100.0
+    h.progressive_widening_hypothesis_based = 1
+    h.pw_alpha = 0.5
+    h.pw_k = 1.0
+    h.exploration_constant = 0.7
+    h.chance_constrained_update = 0
+    h.policy_random_seed = 1000
+    for k, v in over.items():
+        if not hasattr(h, k):
+            raise AttributeError(k)
+        setattr(h, k, v)
+    return h
 
 
 def default_crossing_params(**over) -> CrossingParams:

@@ -274,6 +274,75 @@ class mcts::UctTest {
   }
   static void force_visits(UctStatistic& s, unsigned v) { s.total_node_visits_ = v; }
 
+  // canonical dump of a hypothesis-MCTS tree (record layout: include/mamcts_b200.h, mamcts_hyp_search_create)
+  template <class S, class H>
+  static uint32_t dump_hyp(const std::shared_ptr<StageNode<S, UctStatistic, HypothesisStatistic, H>>& node, double* rec,
+                           uint32_t cap, uint32_t count, uint32_t NE, uint32_t MA, uint32_t NH, int min_v) {
+    const uint32_t A = node->state_->get_num_agents();
+    const uint32_t J = A - 1;
+    const uint32_t M = NE > MA ? NE : MA;
+    const uint32_t per_other = 6 + NH * (2 + MA) + 2 * NH * MA;
+    const uint32_t stride = 4 + (3 + 2 * NE) + J * per_other;
+    auto code_of = [&](const JointAction& ja) {
+      double code = static_cast<double>(ja[0]), mul = M;
+      for (uint32_t a = 1; a < A; ++a) { code += mul * static_cast<double>(aconv<int>(ja[a]) - min_v); mul *= M; }
+      return code;
+    };
+    if (count < cap) {
+      double* r = rec + static_cast<size_t>(count) * stride;
+      for (uint32_t i = 0; i < stride; ++i) r[i] = 0.0;
+      r[0] = node->depth_;
+      r[1] = node->is_root() ? -1.0 : code_of(node->joint_action_);
+      r[2] = node->visit_count_;
+      r[3] = static_cast<double>(node->children_.size());
+      {
+        const UctStatistic& st = node->ego_int_node_;
+        double* e = r + 4;
+        e[0] = st.total_node_visits_; e[1] = st.value_; e[2] = st.latest_return_;
+        for (uint32_t k = 0; k < NE; ++k) { e[3 + k] = -1.0; e[3 + NE + k] = 0.0; }
+        for (const auto& kv : st.ucb_statistics_)
+          if (kv.first < NE) { e[3 + kv.first] = kv.second.action_count_; e[3 + NE + kv.first] = kv.second.action_value_; }
+      }
+      for (uint32_t j = 0; j < J; ++j) {
+        const HypothesisStatistic& st = node->other_int_nodes_[j];
+        double* o = r + 4 + (3 + 2 * NE) + j * per_other;
+        o[0] = st.total_node_visits_; o[1] = st.ego_cost_value_; o[2] = st.latest_ego_cost_; o[3] = st.num_expanded_actions_;
+        auto ns = st.total_node_visits_hypothesis_.find(HYPOTHESIS_ID_NOT_SET);
+        o[4] = ns == st.total_node_visits_hypothesis_.end() ? 0.0 : ns->second;
+        o[5] = 0.0;
+        for (uint32_t h = 0; h < NH; ++h) {
+          double* oh = o + 6 + h * (2 + MA);
+          auto vit = st.total_node_visits_hypothesis_.find(h);
+          oh[0] = vit == st.total_node_visits_hypothesis_.end() ? -1.0 : vit->second;
+          auto uit = st.ucb_statistics_.find(h);
+          oh[1] = uit == st.ucb_statistics_.end() ? -1.0 : static_cast<double>(uit->second.size());
+          for (uint32_t k = 0; k < MA; ++k) oh[2 + k] = -1.0;
+          double* oc = o + 6 + NH * (2 + MA) + 2 * h * MA;
+          for (uint32_t k = 0; k < MA; ++k) { oc[2 * k] = -1.0; oc[2 * k + 1] = 0.0; }
+          if (uit != st.ucb_statistics_.end()) {
+            uint32_t pos = 0;
+            for (const auto& kv : uit->second) {   // the container's own iteration order
+              const int a = aconv<int>(kv.first) - min_v;
+              if (pos < MA) oh[2 + pos] = a;
+              ++pos;
+              if (a >= 0 && static_cast<uint32_t>(a) < MA) { oc[2 * a] = kv.second.action_count_; oc[2 * a + 1] = kv.second.action_ego_cost_; }
+            }
+          }
+        }
+      }
+    }
+    ++count;
+    std::map<double, std::shared_ptr<StageNode<S, UctStatistic, HypothesisStatistic, H>>> sorted;
+    for (const auto& kv : node->children_) sorted[code_of(kv.first)] = kv.second;
+    for (const auto& kv : sorted) count = dump_hyp<S, H>(kv.second, rec, cap, count, NE, MA, NH, min_v);
+    return count;
+  }
+  template <class S, class H>
+  static std::shared_ptr<StageNode<S, UctStatistic, HypothesisStatistic, H>> root_of_hyp(
+      Mcts<S, UctStatistic, HypothesisStatistic, H>& m) {
+    return m.root_;
+  }
+
   template <class S, class H>
   static uint32_t dump(const std::shared_ptr<StageNode<S, UctStatistic, UctStatistic, H>>& node,
                        double* rec, uint32_t cap, uint32_t count, uint32_t max_actions) {
@@ -897,6 +966,77 @@ extern "C" int ref_action_values_crossing(const mamcts_params* mp, const mamcts_
       mean_cost[i] = so.seen_cost.empty() ? 0.0 : so.seen_cost[0];
       ++j;
     }
+  }
+  return 0;
+}
+
+// ---- hypothesis-MCTS (BASELINE configs[3]) -------------------------------------------------------------------
+// Mcts<CrossingState<int>, UctStatistic, HypothesisStatistic, RandomHeuristic>::search(state, belief_tracker)
+// (mcts/mcts.h:143-164) exactly as environments/tests/crossing_state_int_test.cc:141-229 sets it up: a
+// HypothesisBeliefTracker, a CrossingState referring to its sampled hypotheses, add_hypothesis per gap range,
+// belief_update(state, state) to initialise the beliefs from the priors. `skip` earlier
+// sample_current_hypothesis() calls emulate a tracker that has already served other decisions.
+// Outputs: the hypothesis ids the tracker hands out during the search (from a copy of the tracker, sequence
+// [iterations][J]), the canonical tree dump (UctTest::dump_hyp) and counters {nodes, iterations, best action}.
+namespace {
+MctsParameters to_ref_hyp_params(const mamcts_params& mp, const mamcts_hypothesis_params& hp) {
+  MctsParameters r = to_ref_params(mp);
+  r.hypothesis_statistic.UPPER_COST_BOUND = hp.upper_cost_bound;
+  r.hypothesis_statistic.LOWER_COST_BOUND = hp.lower_cost_bound;
+  r.hypothesis_statistic.PROGRESSIVE_WIDENING_K = hp.pw_k;
+  r.hypothesis_statistic.PROGRESSIVE_WIDENING_ALPHA = hp.pw_alpha;
+  r.hypothesis_statistic.EXPLORATION_CONSTANT = hp.exploration_constant;
+  r.hypothesis_statistic.COST_BASED_ACTION_SELECTION = hp.cost_based_action_selection != 0;
+  r.hypothesis_statistic.PROGRESSIVE_WIDENING_HYPOTHESIS_BASED = hp.progressive_widening_hypothesis_based != 0;
+  r.cost_constrained_statistic.USE_CHANCE_CONSTRAINED_UPDATES.clear();
+  if (hp.chance_constrained_update) r.cost_constrained_statistic.USE_CHANCE_CONSTRAINED_UPDATES.push_back(true);
+  return r;
+}
+}  // namespace
+
+extern "C" int ref_search_hypothesis(const mamcts_params* mp, const mamcts_hypothesis_params* hp,
+                                     const mamcts_crossing_params* cp, uint32_t num_hyp, const int32_t* gap_lo,
+                                     const int32_t* gap_hi, const int32_t* root_x, const int32_t* root_last,
+                                     uint32_t skip, uint8_t* sequence /* [iterations][J] */, uint32_t* counters /* [3] */,
+                                     double* tree_records, uint32_t tree_capacity, uint32_t* tree_count,
+                                     double* iterations_per_s) {
+  const MctsParameters rp = to_ref_hyp_params(*mp, *hp);
+  CrossingStateParameters<int> params = to_ref_crossing(*cp);
+  params.OTHER_AGENTS_POLICY_RANDOM_SEED = hp->policy_random_seed;
+  const uint32_t J = cp->num_other_agents;
+  HypothesisBeliefTracker tracker(rp);
+  std::vector<AgentState<int>> others;
+  for (uint32_t j = 0; j < J; ++j) others.emplace_back(root_x[j + 1], root_last ? root_last[j + 1] : 2);
+  AgentState<int> ego(root_x[0], root_last ? root_last[0] : 2);
+  std::vector<AgentPolicyCrossingState<int>> hyps;
+  for (uint32_t h = 0; h < num_hyp; ++h) hyps.emplace_back(std::pair<int, int>(gap_lo[h], gap_hi[h]), params);
+  // the map the state refers to must hold every agent BEFORE the first sample (crossing_state_int_test.cc:147)
+  auto state = std::make_shared<CrossingState<int>>(tracker.sample_current_hypothesis(), params, others, ego, false, false,
+                                                    false, hyps);
+  tracker.belief_update(*state, *state);
+  for (uint32_t k = 0; k < skip; ++k) tracker.sample_current_hypothesis();
+  if (sequence) {
+    HypothesisBeliefTracker copy = tracker;
+    for (uint32_t it = 0; it < rp.MAX_NUMBER_OF_ITERATIONS; ++it) {
+      const auto& cur = copy.sample_current_hypothesis();
+      for (uint32_t j = 0; j < J; ++j) sequence[static_cast<size_t>(it) * J + j] = static_cast<uint8_t>(cur.at(j + 1));
+    }
+  }
+  using M = Mcts<CrossingState<int>, UctStatistic, HypothesisStatistic, RandomHeuristic>;
+  M mcts(rp);
+  const auto t0 = std::chrono::steady_clock::now();
+  mcts.search(*state, tracker);
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (iterations_per_s) *iterations_per_s = mcts.numIterations() / el;
+  counters[0] = mcts.numNodes();
+  counters[1] = mcts.numIterations();
+  counters[2] = static_cast<uint32_t>(mcts.returnBestAction());
+  if (tree_records && tree_count) {
+    const uint32_t NE = static_cast<uint32_t>(cp->max_velocity_ego - cp->min_velocity_ego + 1);
+    const uint32_t MA = static_cast<uint32_t>(cp->max_velocity_other - cp->min_velocity_other + 1);
+    *tree_count = UctTest::dump_hyp<CrossingState<int>, RandomHeuristic>(
+        UctTest::root_of_hyp<CrossingState<int>, RandomHeuristic>(mcts), tree_records, tree_capacity, 0, NE, MA, num_hyp,
+        cp->min_velocity_other);
   }
   return 0;
 }

@@ -338,6 +338,27 @@ def gen_action_values():
     dump("action_values.json", cases)
 
 
+def gen_hypothesis_search():
+    """Whole hypothesis-MCTS searches of the reference (Mcts<CrossingState<int>, UctStatistic, HypothesisStatistic,
+    RandomHeuristic>::search(state, belief_tracker)): the hypothesis sequence its belief tracker handed out, the
+    number of nodes, the best action and a digest of the canonical dump of every node statistic."""
+    from mamcts_b200 import default_hypothesis_params
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_hypothesis_search import CASES
+    out = []
+    for case in CASES:
+        mp = default_params(max_number_of_iterations=case["iters"], max_number_of_nodes=case.get("max_nodes", 100000000),
+                            rh_max_number_of_iterations=50)
+        hp = default_hypothesis_params(**case["hkw"])
+        cp = default_crossing_params(num_other_agents=case["others"], **case["kw"])
+        r = O.ref_search_hypothesis(mp, hp, cp, case["gaps"], skip=case["skip"], tree_capacity=case["iters"] + 1)
+        assert r["tree_count"] == r["num_nodes"]
+        out.append(dict(name=case["name"], others=case["others"], gaps=case["gaps"], iters=case["iters"], skip=case["skip"],
+                        sequence=r["sequence"].ravel().tolist(), num_nodes=r["num_nodes"], best=r["best"],
+                        tree_sha256=tree_digest(r["tree"]), root_record=fhex(r["tree"][0])))
+    dump("hypothesis_search.json", out)
+
+
 if __name__ == "__main__":
     assert O.reference_available(), "needs /root/reference (or a prebuilt oracle/_ref)"
     gen_expand_order()
@@ -349,3 +370,4 @@ if __name__ == "__main__":
     gen_search()
     gen_merge()
     gen_action_values()
+    gen_hypothesis_search()

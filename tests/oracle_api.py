@@ -693,6 +693,38 @@ def ref_merge_uct(mp: Params, q, cnt, visits, num_actions):
     return dict(q=mq, n=mn, visits=mv.value, value=val.value, best=best.value)
 
 
+def hyp_dump_stride(cp: CrossingParams, num_hyp: int) -> int:
+    NE = cp.num_ego_actions
+    MA = cp.max_velocity_other - cp.min_velocity_other + 1
+    return 4 + (3 + 2 * NE) + cp.num_other_agents * (6 + num_hyp * (2 + MA) + 2 * num_hyp * MA)
+
+
+def ref_search_hypothesis(mp: Params, hp, cp: CrossingParams, gaps, root_x=None, root_last=None, skip=0,
+                          tree_capacity=0):
+    """The reference's own hypothesis-MCTS: Mcts<CrossingState<int>, UctStatistic, HypothesisStatistic,
+    RandomHeuristic>::search(state, belief_tracker) (oracle/ref_driver.cc: ref_search_hypothesis).
+    gaps: [(lo, hi)] per hypothesis. Returns the hypothesis sequence the tracker handed out, the canonical
+    tree dump and the counters."""
+    A = cp.num_other_agents + 1
+    H = len(gaps)
+    lo = np.ascontiguousarray([g[0] for g in gaps], dtype=np.int32)
+    hi = np.ascontiguousarray([g[1] for g in gaps], dtype=np.int32)
+    rx = np.ascontiguousarray(root_x if root_x is not None else [5] * A, dtype=np.int32)
+    rl = np.ascontiguousarray(root_last if root_last is not None else [2] * A, dtype=np.int32)
+    seq = np.zeros((mp.max_number_of_iterations, A - 1), dtype=np.uint8)
+    counters = np.zeros(3, dtype=np.uint32)
+    stride = hyp_dump_stride(cp, H)
+    tree = np.zeros((max(tree_capacity, 1), stride))
+    count = C.c_uint32(0)
+    its = C.c_double(0)
+    reference().ref_search_hypothesis(C.byref(mp), C.byref(hp), C.byref(cp), C.c_uint32(H), _ptr(lo), _ptr(hi), _ptr(rx),
+                                      _ptr(rl), C.c_uint32(skip), _ptr(seq), _ptr(counters),
+                                      _ptr(tree) if tree_capacity else None, C.c_uint32(tree_capacity), C.byref(count),
+                                      C.byref(its))
+    return dict(sequence=seq, num_nodes=int(counters[0]), iterations=int(counters[1]), best=int(counters[2]),
+                tree=tree[:min(count.value, tree_capacity)], tree_count=count.value, iterations_per_s=its.value)
+
+
 def ref_time_rollouts(mp: Params, cp: CrossingParams, threads: int, seconds: float):
     s, r = C.c_double(0), C.c_double(0)
     reference().ref_time_rollouts(C.byref(mp), C.byref(cp), C.c_uint32(threads),
