@@ -67,8 +67,11 @@ struct CudaState<CrossingState<int>> {
   }
   static void set_parameters(const CrossingStateParameters<int>& c) {
     storage() = to_params(c);
+    policy_seed() = c.OTHER_AGENTS_POLICY_RANDOM_SEED;
     registered() = true;
   }
+  // the seed every AgentPolicyCrossingState generator starts from (crossing_state_agent_policy.h:25)
+  static unsigned& policy_seed() { static unsigned s = 1000; return s; }
   // what a state reveals about its parameters must agree with `p`
   static void check_state(const CrossingState<int>& s, const mamcts_crossing_params& p) {
     if (s.get_agent_states().size() != p.num_other_agents)

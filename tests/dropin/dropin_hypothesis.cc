@@ -19,6 +19,7 @@
 
 #include "cuda_random_heuristic.h"
 #include "cuda_state.h"
+#include "device_hypothesis_mcts.h"
 #include "device_mcts.h"
 
 using namespace mcts;
@@ -134,6 +135,109 @@ TEST(dropin_hypothesis, episode_with_device_resident_planner_reaches_goal) {
   }
   std::printf("  device planner: goal %d collision %d after %d steps, %u iterations x %u trees per step\n",
               (int)state->ego_goal_reached(), (int)collision, i + 1, planner.numIterations(), planner.numTrees());
+  EXPECT_TRUE(state->ego_goal_reached());
+  EXPECT_FALSE(collision);
+}
+
+// The device-resident hypothesis-MCTS as the planner of the reference's own closed-loop tests
+// (crossing_state_int_test.cc:141-229): at every step the device search (one tree, reference-identical
+// generators) must choose the action, build as many nodes and leave the belief tracker in the state the
+// reference's own search does - then the loop goes on with the device planner's action.
+static bool closed_loop_device_vs_stock(const std::vector<std::pair<int, int>>& hypotheses, std::pair<int, int> true_gap,
+                                        unsigned iterations, int max_steps, bool* collision, int* mismatches) {
+  const auto params = default_crossing_state_parameters<Domain>();
+  CudaState<CrossingState<Domain>>::set_parameters(params);
+  CudaState<CrossingState<Domain>>::set_hypotheses(hypotheses);
+  auto mcts_params = hypothesis_params(iterations);
+  mcts_params.MAX_NUMBER_OF_NODES = 100000000;
+  HypothesisBeliefTracker tracker_dev(mcts_params), tracker_ref(mcts_params);
+  auto state = std::make_shared<CrossingState<Domain>>(tracker_dev.sample_current_hypothesis(), params);
+  for (const auto& h : hypotheses) state->add_hypothesis(AgentPolicyCrossingState<Domain>(h, params));
+  tracker_dev.belief_update(*state, *state);
+  AgentPolicyCrossingState<Domain> true_agents_policy(true_gap, params);
+  DeviceHypothesisMcts planner(mcts_params, 1);
+  std::vector<Reward> rewards;
+  EgoCosts cost;
+  *collision = false;
+  *mismatches = 0;
+  for (int i = 0; i < max_steps; ++i) {
+    // the reference's own search from the same state with a tracker in the same condition
+    tracker_ref = tracker_dev;
+    auto ref_state = state->change_belief_reference(tracker_ref.sample_current_hypothesis());   // no beliefs change
+    tracker_ref = tracker_dev;   // undo the sample: both trackers start the search alike
+    // (change_belief_reference keeps a reference to tracker_ref's map, which assignment updates in place)
+    Mcts<CrossingState<Domain>, UctStatistic, HypothesisStatistic, RandomHeuristic> ref(mcts_params);
+    ref.search(*ref_state, tracker_ref);
+    planner.search(*state, tracker_dev);
+    const auto root = planner.get_root_statistic(0);
+    bool same = planner.returnBestAction() == ref.returnBestAction() && planner.numNodes() == ref.numNodes() &&
+                root.total_node_visits == iterations;
+    // both trackers must be in the same state afterwards: their next samples agree
+    HypothesisBeliefTracker a = tracker_dev, b = tracker_ref;
+    for (int k = 0; k < 8 && same; ++k) same = a.sample_current_hypothesis() == b.sample_current_hypothesis();
+    if (!same) ++*mismatches;
+    auto jointaction = JointAction(state->get_num_agents());
+    jointaction[CrossingState<Domain>::ego_agent_idx] = planner.returnBestAction();
+    for (auto agent_idx : state->get_other_agent_idx())
+      jointaction[agent_idx] = aconv<Domain>(true_agents_policy.act(state->get_agent_state(agent_idx), state->get_ego_state()));
+    auto next_state = state->execute(jointaction, rewards, cost);
+    tracker_dev.belief_update(*state, *next_state);
+    state = next_state;
+    if (state->is_terminal() && !state->ego_goal_reached()) { *collision = true; break; }
+    if (state->is_terminal()) break;
+  }
+  return state->ego_goal_reached();
+}
+
+TEST(dropin_hypothesis, device_hypothesis_mcts_true_hypothesis_equals_reference_search_every_step) {
+  bool collision = false;
+  int mismatches = 0;
+  const bool goal = closed_loop_device_vs_stock({{5, 5}}, {5, 5}, 800, 100, &collision, &mismatches);
+  std::printf("  device hypothesis planner, true hypothesis: goal %d collision %d mismatching steps %d\n", (int)goal, (int)collision, mismatches);
+  EXPECT_TRUE(goal);
+  EXPECT_FALSE(collision);
+  EXPECT_EQ(mismatches, 0);
+}
+
+TEST(dropin_hypothesis, device_hypothesis_mcts_wrong_hypothesis_equals_reference_search_every_step) {
+  bool collision = false;
+  int mismatches = 0;
+  const bool goal = closed_loop_device_vs_stock({{-2, 1}, {2, 3}, {4, 5}}, {-2, -2}, 800, 30, &collision, &mismatches);
+  std::printf("  device hypothesis planner, wrong hypothesis: goal %d collision %d mismatching steps %d\n", (int)goal, (int)collision, mismatches);
+  EXPECT_TRUE(goal);
+  EXPECT_FALSE(collision);
+  EXPECT_EQ(mismatches, 0);
+}
+
+// 4 096 decorrelated root-parallel hypothesis trees per decision
+TEST(dropin_hypothesis, device_hypothesis_mcts_root_parallel_reaches_goal) {
+  const auto params = default_crossing_state_parameters<Domain>();
+  CudaState<CrossingState<Domain>>::set_parameters(params);
+  const std::vector<std::pair<int, int>> hypotheses{{-2, 1}, {2, 3}, {4, 5}};
+  CudaState<CrossingState<Domain>>::set_hypotheses(hypotheses);
+  auto mcts_params = hypothesis_params(300);
+  mcts_params.MAX_NUMBER_OF_NODES = 100000000;
+  HypothesisBeliefTracker tracker(mcts_params);
+  auto state = std::make_shared<CrossingState<Domain>>(tracker.sample_current_hypothesis(), params);
+  for (const auto& h : hypotheses) state->add_hypothesis(AgentPolicyCrossingState<Domain>(h, params));
+  tracker.belief_update(*state, *state);
+  AgentPolicyCrossingState<Domain> true_agents_policy({-2, -2}, params);
+  DeviceHypothesisMcts planner(mcts_params, 4096, true);
+  std::vector<Reward> rewards;
+  EgoCosts cost;
+  bool collision = false;
+  for (int i = 0; i < 30; ++i) {
+    planner.search(*state, tracker);
+    auto jointaction = JointAction(state->get_num_agents());
+    jointaction[CrossingState<Domain>::ego_agent_idx] = planner.returnBestAction();
+    for (auto agent_idx : state->get_other_agent_idx())
+      jointaction[agent_idx] = aconv<Domain>(true_agents_policy.act(state->get_agent_state(agent_idx), state->get_ego_state()));
+    auto next_state = state->execute(jointaction, rewards, cost);
+    tracker.belief_update(*state, *next_state);
+    state = next_state;
+    if (state->is_terminal()) { collision = !state->ego_goal_reached(); break; }
+  }
+  EXPECT_TRUE(planner.get_merged_root_statistic().total_node_visits == 4096u * 300u);
   EXPECT_TRUE(state->ego_goal_reached());
   EXPECT_FALSE(collision);
 }

@@ -69,5 +69,8 @@ def test_reference_hypothesis_mcts_closed_loop_with_gpu_rollouts():
     for name in ("dropin_hypothesis.mcts_goal_reached_true_hypothesis_cuda_rollouts",
                  "dropin_hypothesis.mcts_goal_reached_wrong_hypothesis_cuda_rollouts",
                  "dropin_hypothesis.stock_heuristic_reaches_goal_too",
-                 "dropin_hypothesis.episode_with_device_resident_planner_reaches_goal"):
+                 "dropin_hypothesis.episode_with_device_resident_planner_reaches_goal",
+                 "dropin_hypothesis.device_hypothesis_mcts_true_hypothesis_equals_reference_search_every_step",
+                 "dropin_hypothesis.device_hypothesis_mcts_wrong_hypothesis_equals_reference_search_every_step",
+                 "dropin_hypothesis.device_hypothesis_mcts_root_parallel_reaches_goal"):
         assert f"PASS {name}" in out, out[-4000:]
