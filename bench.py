@@ -191,6 +191,7 @@ def cpu_baselines(repeats: int):
             "what": "Mcts::parallel_search, USE_MULTI_THREADING = true, NUM_PARALLEL_MCTS = nproc "
                     "(reference mcts/mcts.h:188-221), one call"}
         mpr = default_params(rh_max_number_of_iterations=DEPTH_CAP)
+        out["c4_hypothesis"] = cpu_c4_hypothesis(threads)
         for others in (1, C3_OTHERS):
             st, ro = O.ref_time_rollouts(mpr, default_crossing_params(num_other_agents=others), threads, 2.0)
             out[f"rollout_loop_a{others + 1}"] = {
@@ -446,6 +447,73 @@ def measure_c5_strong(engine, stream, world, rank, dist, steps=5, warmup=2):
         "merged_root_visits": int(merged["visits"]), "merged_root_n": [int(v) for v in merged["n"]],
         "best_action": int(merged["best"]), "gpu_launches": int(launches),
     }
+
+
+def measure_c4_hypothesis(engine, stream, trees=4096, iterations=10000, steps=3):
+    """BASELINE.json configs[3] (C4): hypothesis-MCTS on CrossingState<int> - 2 other agents whose behaviour
+    hypotheses are the three desired-gap ranges of the reference's own closed-loop test
+    (environments/tests/crossing_state_int_test.cc:190-192), a hypothesis per agent and iteration drawn from uniform
+    beliefs as HypothesisBeliefTracker draws them, UctStatistic for the ego, HypothesisStatistic for the others,
+    `iterations` per tree, `trees` decorrelated root-parallel trees on one GPU (mamcts_hyp_search_*). With
+    decorrelate_trees = 0 every tree is the reference's tree bit for bit (tests/test_gpu_hypothesis_search.py)."""
+    import numpy as np
+    import torch
+    from mamcts_b200 import default_crossing_params, default_hypothesis_params, default_params
+    from mamcts_b200.engine import HypSearch, reference_hypothesis_sequence
+    gaps = [(-2, 1), (2, 3), (4, 5)]
+    mp = default_params(max_number_of_iterations=iterations, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=DEPTH_CAP)
+    hp = default_hypothesis_params()
+    cp = default_crossing_params(num_other_agents=2)
+    seq = reference_hypothesis_sequence(1000, np.full((2, len(gaps)), 1.0 / len(gaps)), 0, iterations)
+    s = HypSearch(engine, mp, hp, cp, trees, gaps, seq, decorrelate_trees=True)
+    s.run(iterations)                       # warm-up decision
+    torch.cuda.synchronize()
+    launches0 = engine.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(steps):
+        s.reset([5, 5, 5], [2, 2, 2], seq)  # host -> device: root state and the iteration's hypothesis ids
+        s.run(iterations)
+        merged = s.merge_roots()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = ev0.elapsed_time(ev1) / steps
+    c = s.counters()
+    launches = engine.launch_count - launches0
+    s.close()
+    if int(merged["visits"]) != trees * iterations:
+        raise SystemExit(f"bench.py: C4 merged root visits {merged['visits']} != {trees * iterations}")
+    return {
+        "workload": f"C4: hypothesis-MCTS, CrossingState<int>, 2 other agents, hypotheses {gaps} (desired-gap ranges of "
+                    f"crossing_state_int_test.cc:190-192), uniform beliefs, {iterations} iterations per tree, {trees} "
+                    "decorrelated root-parallel trees on one GPU; a step = one decision through HypSearch.reset(host root, "
+                    "host hypothesis sequence) + run + merge_roots",
+        "trees": trees, "iterations_per_tree": iterations, "steps": steps,
+        "iterations_per_s": c["iterations"] / (ms * 1e-3),
+        "env_steps_per_s": (c["rollout_steps"] + c["expand_steps"]) / (ms * 1e-3),
+        "ms_per_decision": ms, "wall_ms_per_decision": 1e3 * wall / steps, "nodes_per_tree": c["nodes"] / trees,
+        "best_action": int(merged["best"]), "gpu_launches": int(launches),
+    }
+
+
+def cpu_c4_hypothesis(threads: int, iterations=10000):
+    """The reference's own hypothesis-MCTS on the host cores: `threads` independent
+    Mcts<CrossingState<int>, UctStatistic, HypothesisStatistic, RandomHeuristic>::search(state, belief_tracker)
+    calls of the C4 configuration (oracle/_ref: ref_time_search_hypothesis), one std::thread each."""
+    import oracle_api as O
+    if not O.reference_available():
+        return None
+    from mamcts_b200 import default_crossing_params, default_hypothesis_params, default_params
+    mp = default_params(max_number_of_iterations=iterations, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=DEPTH_CAP)
+    it_s, sec = O.ref_time_search_hypothesis(mp, default_hypothesis_params(), default_crossing_params(num_other_agents=2),
+                                             [(-2, 1), (2, 3), (4, 5)], threads)
+    return {"iterations_per_s": it_s, "cores": threads, "seconds": sec,
+            "what": f"{threads} independent hypothesis searches of the C4 configuration ({iterations} iterations each), "
+                    "one per host thread (mcts/mcts.h:143-164)"}
 
 
 def _check_sampled_tree(search, mp, cp, first_tree_id, tree):
@@ -731,8 +799,13 @@ def run_native(args):
     # ---- the sections every N carries: C5 (strong scaling) and C3 (rollouts sharded), after the trees are freed
     c5 = measure_c5_strong(engine, stream, world, rank, dist) if not args.no_sections else None
     c3 = measure_rollout_c3(engine, stream, world, rank, dist=dist if world > 1 else None) if not args.no_sections else None
+    c4 = measure_c4_hypothesis(engine, stream) if (rank == 0 and not args.no_sections) else None
     if rank == 0:
         line["leaf_batched"] = leaf_batched
+        line["c4_hypothesis"] = c4
+        if c4 is not None and cpu_baseline and cpu_baseline.get("c4_hypothesis"):
+            c4["cpu_iterations_per_s"] = cpu_baseline["c4_hypothesis"]["iterations_per_s"]
+            c4["cpu_cores"] = cpu_baseline["c4_hypothesis"]["cores"]
         line["c5_strong"] = c5
         if c3 is not None:
             c3["roofline_issue"] = _issue_roofline(_ncu_entry(kernel="rollout_kernel", workload="c3"),

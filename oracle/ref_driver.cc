@@ -1041,6 +1041,33 @@ extern "C" int ref_search_hypothesis(const mamcts_params* mp, const mamcts_hypot
   return 0;
 }
 
+// `threads` independent hypothesis searches of the same configuration, one std::thread each (the reference's own
+// root-parallel mode for hypothesis searches does the same, mcts.h:237-251); returns iterations / wall time.
+extern "C" int ref_time_search_hypothesis(const mamcts_params* mp, const mamcts_hypothesis_params* hp,
+                                          const mamcts_crossing_params* cp, uint32_t num_hyp, const int32_t* gap_lo,
+                                          const int32_t* gap_hi, uint32_t threads, double* iterations_per_s,
+                                          double* seconds_out) {
+  std::vector<uint64_t> iters(threads, 0);
+  const uint32_t A = cp->num_other_agents + 1;
+  std::vector<int32_t> x(A, 5), last(A, 2);
+  const auto t0 = std::chrono::steady_clock::now();
+  auto body = [&](uint32_t tid) {
+    uint32_t counters[3] = {0, 0, 0};
+    ref_search_hypothesis(mp, hp, cp, num_hyp, gap_lo, gap_hi, x.data(), last.data(), tid, nullptr, counters, nullptr, 0,
+                          nullptr, nullptr);
+    iters[tid] = counters[1];
+  };
+  std::vector<std::thread> pool;
+  for (uint32_t t = 0; t < threads; ++t) pool.emplace_back(body, t);
+  for (auto& th : pool) th.join();
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  uint64_t it = 0;
+  for (uint32_t t = 0; t < threads; ++t) it += iters[t];
+  *iterations_per_s = it / el;
+  *seconds_out = el;
+  return 0;
+}
+
 // ---- timing of the reference's own CPU path (bench.py --impl reference / cpu_baseline) ---------
 
 // `threads` independent loops of RandomHeuristic::rollout from the default start state for about

@@ -725,6 +725,15 @@ def ref_search_hypothesis(mp: Params, hp, cp: CrossingParams, gaps, root_x=None,
                 tree=tree[:min(count.value, tree_capacity)], tree_count=count.value, iterations_per_s=its.value)
 
 
+def ref_time_search_hypothesis(mp: Params, hp, cp: CrossingParams, gaps, threads: int):
+    lo = np.ascontiguousarray([g[0] for g in gaps], dtype=np.int32)
+    hi = np.ascontiguousarray([g[1] for g in gaps], dtype=np.int32)
+    it, sec = C.c_double(0), C.c_double(0)
+    reference().ref_time_search_hypothesis(C.byref(mp), C.byref(hp), C.byref(cp), C.c_uint32(len(gaps)), _ptr(lo), _ptr(hi),
+                                           C.c_uint32(threads), C.byref(it), C.byref(sec))
+    return it.value, sec.value
+
+
 def ref_time_rollouts(mp: Params, cp: CrossingParams, threads: int, seconds: float):
     s, r = C.c_double(0), C.c_double(0)
     reference().ref_time_rollouts(C.byref(mp), C.byref(cp), C.c_uint32(threads),
