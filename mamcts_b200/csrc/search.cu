@@ -21,6 +21,7 @@
 #include "engine.h"
 #include "root_merge.h"
 #include "search_compact.cuh"
+#include "search_compact_multi.cuh"
 #include "search_host.h"
 #include "search_kernel.cuh"
 
@@ -299,6 +300,186 @@ struct SearchC final : public mamcts_search {
   }
 };
 
+// Compact layout for more than two agents with reward-free other agents: search_compact_multi.cuh.
+static_assert(sizeof(InnerRecM<CrossingEnv<7>, 4, 7, uint16_t>) == 192, "8-agent inner record: 192 bytes with 16-bit counts");
+template <class Env, int NE, int NA, class CNT>
+struct SearchCM final : public mamcts_search {
+  using Inner = InnerRecM<Env, NE, NA, CNT>;
+  static constexpr int A = Env::A;
+  unsigned long long* d_table = nullptr;
+  uint32_t table_size = 0;
+
+  size_t node_bytes() const override { return sizeof(Inner); }
+  size_t leaf_bytes() const override { return sizeof(double); }
+  bool uses_hash() const override { return false; }   // its own 64-bit table, not d_hash
+  bool is_compact() const override { return true; }
+  void free_extra() override { cudaFree(d_table); }
+  const char* root_record(uint32_t tree) const override {
+    return static_cast<const char*>(d_inner) + sizeof(Inner) * (size_t)tree * max_inner;
+  }
+  int alloc_extra(uint32_t max_nodes) override {
+    table_size = 16;
+    while (table_size * 5u < max_nodes * 8u) table_size <<= 1;   // load factor <= 0.625
+    MAMCTS_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&d_table), sizeof(unsigned long long) * (size_t)cfg.num_trees * table_size));
+    return MAMCTS_OK;
+  }
+  int launch_reset() override {
+    const uint32_t T = cfg.num_trees;
+    MAMCTS_CUDA(e, cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 8, e->stream));
+    MAMCTS_CUDA(e, cudaMemsetAsync(d_table, 0, sizeof(unsigned long long) * (size_t)T * table_size, e->stream));
+    search_compact_multi_reset_kernel<Env, NE, NA, CNT><<<(T + 255) / 256, 256, 0, e->stream>>>(
+        d_inner, d_tree_nodes, d_tree_iters, d_tree_inner, d_tree_leaves, T, max_inner);
+    e->launches++;
+    MAMCTS_CUDA(e, cudaGetLastError());
+    iters_done = 0;
+    return MAMCTS_OK;
+  }
+  int launch_run(uint32_t iterations) override {
+    SearchParams q = p;
+    q.iterations = iterations;
+    CompactMultiParams c;
+    c.inner = d_inner; c.leaves = static_cast<double*>(d_leaves); c.table = d_table;
+    c.tree_inner = d_tree_inner; c.tree_leaves = d_tree_leaves;
+    c.max_inner = max_inner; c.table_mask = table_size - 1; c.root_x = d_root_x;
+    const uint32_t T = cfg.num_trees;
+    const uint32_t trees_per_block = (uint32_t)(block_threads / 32) * q.lanes_per_warp;
+    const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
+    if (cfg.action_source == MAMCTS_SRC_PHILOX && cfg.rollouts_per_leaf > 1)
+      search_compact_multi_kernel<Env, NE, NA, CNT, MAMCTS_SRC_PHILOX, true><<<grid, block_threads, 0, e->stream>>>(q, c);
+    else if (cfg.action_source == MAMCTS_SRC_PHILOX)
+      search_compact_multi_kernel<Env, NE, NA, CNT, MAMCTS_SRC_PHILOX><<<grid, block_threads, 0, e->stream>>>(q, c);
+    else
+      search_compact_multi_kernel<Env, NE, NA, CNT, MAMCTS_SRC_REFERENCE_CONST><<<grid, block_threads, 0, e->stream>>>(q, c);
+    e->launches++;
+    MAMCTS_CUDA(e, cudaGetLastError());
+    return MAMCTS_OK;
+  }
+  void read_header(const void* node, uint32_t* parent, uint32_t* depth, uint32_t* visits, uint8_t* ja) const override {
+    const Inner* nd = static_cast<const Inner*>(node);
+    *parent = nd->parent; *depth = 0; *visits = nd->visit_count;
+    for (int a = 0; a < A; ++a) ja[a] = nd->ja[a];
+  }
+  void read_stat(const void* node, uint32_t agent, double* value, double* latest, uint32_t* visits, uint32_t* nexp,
+                 double* q, uint32_t* n) const override {
+    const Inner* nd = static_cast<const Inner*>(node);
+    *visits = nd->N;
+    if (agent == 0) {
+      *value = nd->vg_e[0]; *latest = nd->vg_e[1]; *nexp = nd->nexp_e;
+      for (int a = 0; a < NE; ++a) { q[a] = nd->q_e[a]; n[a] = nd->n_e[a]; }
+    } else {   // a reward-free agent: every value is +0.0
+      *value = 0.0; *latest = 0.0; *nexp = nd->nexp_o[agent - 1];
+      for (int a = 0; a < NA; ++a) { q[a] = 0.0; n[a] = nd->n_o[agent - 1][a]; }
+    }
+  }
+  void root_gather(RootGather* g) const override {
+    const char* base = static_cast<const char*>(d_inner);
+    const size_t tree_bytes = sizeof(Inner) * (size_t)max_inner;
+    g->q = reinterpret_cast<const double*>(base + offsetof(Inner, q_e));
+    g->n = base + offsetof(Inner, n_e);
+    g->visits = base + offsetof(Inner, N);
+    g->count_bytes = sizeof(CNT);
+    g->root_slot = nullptr;
+    g->stride_q = tree_bytes / sizeof(double);
+    g->stride_n = tree_bytes / sizeof(CNT);
+    g->stride_v = tree_bytes / sizeof(CNT);
+    g->max_actions = NE;
+  }
+  // Export: depth-first from the root; the children of an inner node are the slots of the tree's table whose
+  // key names it, in ascending joint-action code; a leaf is written out as the node the reference would hold.
+  int dump(uint32_t tree, double* records, uint32_t capacity_records, uint32_t* num_records) override {
+    uint32_t ni = 0, nl = 0;
+    MAMCTS_CUDA(e, cudaMemcpyAsync(&ni, d_tree_inner + tree, sizeof(ni), cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaMemcpyAsync(&nl, d_tree_leaves + tree, sizeof(nl), cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+    std::vector<Inner> in(ni);
+    std::vector<double> lf(nl ? nl : 1);
+    std::vector<unsigned long long> tb(table_size);
+    MAMCTS_CUDA(e, cudaMemcpyAsync(in.data(), root_record(tree), sizeof(Inner) * ni, cudaMemcpyDeviceToHost, e->stream));
+    if (nl)
+      MAMCTS_CUDA(e, cudaMemcpyAsync(lf.data(), static_cast<const double*>(d_leaves) + (size_t)tree * p.max_nodes,
+                                     sizeof(double) * nl, cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaMemcpyAsync(tb.data(), d_table + (size_t)tree * table_size, sizeof(unsigned long long) * table_size,
+                                   cudaMemcpyDeviceToHost, e->stream));
+    MAMCTS_CUDA(e, cudaStreamSynchronize(e->stream));
+    const uint32_t max_actions = std::max(p.n_ego, p.n_oth);
+    const uint32_t stride = 4 + A * (3 + 2 * max_actions);
+    struct Kid { double code; uint32_t entry; };
+    std::vector<std::vector<Kid>> kids(ni);
+    for (unsigned long long w : tb) {
+      if (!w) continue;
+      const unsigned long long key = w >> 16;
+      const uint32_t parent = (uint32_t)(key >> 24), packed = (uint32_t)(key & 0xFFFFFFull);
+      if (parent >= ni) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: corrupt child table");
+      double code = 0.0, mul = 1.0;
+      for (int a = 0; a < A; ++a) { code += mul * (double)((packed >> (3 * a)) & 7u); mul *= max_actions; }
+      kids[parent].push_back({code, (uint32_t)(w & 0xFFFFull)});
+    }
+    for (auto& k : kids) std::sort(k.begin(), k.end(), [](const Kid& a, const Kid& b) { return a.code < b.code; });
+    uint32_t count = 0;
+    auto emit_inner = [&](uint32_t i, uint32_t depth, double code) {
+      if (count < capacity_records) {
+        double* r = records + (size_t)count * stride;
+        r[0] = depth; r[1] = code; r[2] = in[i].visit_count; r[3] = (double)kids[i].size();
+        for (uint32_t a = 0; a < (uint32_t)A; ++a) {
+          double* o = r + 4 + a * (3 + 2 * max_actions);
+          double v, l, qq[MAMCTS_MAX_ACTIONS];
+          uint32_t vis, nexp, cnt[MAMCTS_MAX_ACTIONS + 1];
+          read_stat(&in[i], a, &v, &l, &vis, &nexp, qq, cnt);
+          const uint32_t nact = a == 0 ? p.n_ego : p.n_oth;
+          const uint32_t mask = tab.exp_mask[a == 0 ? 0 : 1][std::min(nexp, nact)];
+          o[0] = vis; o[1] = v; o[2] = l;
+          for (uint32_t k = 0; k < max_actions; ++k) {
+            const bool ex = k < nact && ((mask >> k) & 1u);
+            o[3 + k] = ex ? (double)cnt[k] : -1.0;
+            o[3 + max_actions + k] = ex ? qq[k] : 0.0;
+          }
+        }
+      }
+      ++count;
+    };
+    auto emit_leaf = [&](uint32_t l, uint32_t depth, double code) {
+      if (count < capacity_records) {
+        double* r = records + (size_t)count * stride;
+        r[0] = depth; r[1] = code; r[2] = 0.0; r[3] = 0.0;
+        for (uint32_t a = 0; a < (uint32_t)A; ++a) {
+          double* o = r + 4 + a * (3 + 2 * max_actions);
+          o[0] = 1.0; o[1] = a == 0 ? lf[l] : 0.0; o[2] = o[1];
+          for (uint32_t k = 0; k < max_actions; ++k) { o[3 + k] = -1.0; o[3 + max_actions + k] = 0.0; }
+        }
+      }
+      ++count;
+    };
+    struct Frame { uint32_t node; size_t next; uint32_t depth; };
+    std::vector<Frame> stack;
+    emit_inner(0, 0, -1.0);
+    stack.push_back({0u, 0, 0});
+    while (!stack.empty()) {
+      Frame& top = stack.back();
+      if (top.next >= kids[top.node].size()) { stack.pop_back(); continue; }
+      const Kid kid = kids[top.node][top.next++];
+      const uint32_t d = top.depth + 1;
+      if (kid.entry & 1u) {
+        const uint32_t i = kid.entry >> 1;
+        if (i >= ni) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: corrupt child table");
+        emit_inner(i, d, kid.code);
+        stack.push_back({i, 0, d});
+      } else {
+        const uint32_t l = (kid.entry >> 1) - 1u;
+        if (l >= nl) return fail(e, MAMCTS_ERR_INVALID, "mamcts_search_dump_tree: corrupt child table");
+        emit_leaf(l, d, kid.code);
+      }
+    }
+    *num_records = count;
+    return MAMCTS_OK;
+  }
+};
+
+template <class Env, int NE, int NA>
+static mamcts_search* make_search_multi(uint32_t max_iterations) {
+  if (max_iterations < 65535) return new SearchCM<Env, NE, NA, uint16_t>();
+  return new SearchCM<Env, NE, NA, uint32_t>();
+}
+
 template <class Env, int NE, int NA, int NCHILD>
 static mamcts_search* make_search_cidx(uint32_t max_nodes, bool compact, uint32_t max_iterations) {
   if (NCHILD > 0 && compact) {
@@ -318,6 +499,23 @@ static mamcts_search* make_search(const mamcts_search_config& cfg, uint32_t n_eg
   // layout: 0 = automatic (compact wherever a direct child table exists), 1 = classic, 2 = compact
   const bool compact = cfg.layout != MAMCTS_LAYOUT_CLASSIC;
   if (cfg.env == MAMCTS_ENV_SIMPLE) return make_search_cidx<SimpleEnv, 2, 2, 4>(max_nodes, compact, cfg.mcts.max_number_of_iterations);
+  // more than two agents: the counts-only compact layout (search_compact_multi.cuh) wherever the other agents'
+  // values are provably +0.0 (CrossingState, discount >= 0) and leaf / inner indices fit 15 bits
+  const bool multi = compact && cfg.env == MAMCTS_ENV_CROSSING_I32 && cfg.mcts.discount_factor >= 0.0 && max_nodes < 32767;
+  if (multi && n_ego == 4 && n_oth == 7) {
+    switch (cfg.crossing.num_other_agents) {
+      case 2: return make_search_multi<CrossingEnv<2>, 4, 7>(cfg.mcts.max_number_of_iterations);
+      case 3: return make_search_multi<CrossingEnv<3>, 4, 7>(cfg.mcts.max_number_of_iterations);
+      case 7: return make_search_multi<CrossingEnv<7>, 4, 7>(cfg.mcts.max_number_of_iterations);
+      default: break;
+    }
+  } else if (multi && n_ego <= 8 && n_oth <= 8) {
+    switch (cfg.crossing.num_other_agents) {
+      case 2: return make_search_multi<CrossingEnv<2>, 8, 8>(cfg.mcts.max_number_of_iterations);
+      case 3: return make_search_multi<CrossingEnv<3>, 8, 8>(cfg.mcts.max_number_of_iterations);
+      default: break;
+    }
+  }
   if (n_ego == 4 && n_oth == 7) {
     switch (cfg.crossing.num_other_agents) {
       case 1: return make_search_cidx<CrossingEnv<1>, 4, 7, 28>(max_nodes, compact, cfg.mcts.max_number_of_iterations);
@@ -512,7 +710,8 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
                 "at 4 ego / 7 other actions, and 1, 2 or 3 other agents at any action counts up to 8");
   if (cfg->layout == MAMCTS_LAYOUT_COMPACT && !s->is_compact()) {
     delete s;
-    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: the compact layout needs a direct child table (2 agents)");
+    return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: the compact layouts are built for SimpleState, for CrossingState with 2 agents, "
+                "and for 3, 4 or 8 agents with a discount >= 0 and fewer than 32 767 nodes per tree");
   }
   s->e = e;
   s->cfg = *cfg;
@@ -574,6 +773,7 @@ int mamcts_search_create(mamcts_engine* e, const mamcts_search_config* cfg, cons
   alloc((void**)&s->d_disc, sizeof(double) * 2 * ((size_t)std::min(max_steps, 1u << 24) + 1));
   alloc((void**)&s->d_counters, sizeof(unsigned long long) * 8);
   alloc((void**)&s->d_root_x, sizeof(int32_t) * MAMCTS_MAX_AGENTS);
+  if (err == cudaSuccess && s->alloc_extra(max_nodes) != MAMCTS_OK) err = cudaErrorMemoryAllocation;
   if (err == cudaSuccess && max_steps > (1u << 24)) {
     free_search(s);
     return fail(e, MAMCTS_ERR_UNSUPPORTED, "mamcts_search_create: min(random_heuristic.MAX_NUMBER_OF_ITERATIONS, MAX_SEARCH_DEPTH) above 2^24");

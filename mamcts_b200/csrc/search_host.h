@@ -58,6 +58,7 @@ struct mamcts_search {
   // device-side failures a read-back must report instead of returning statistics of an unfinished search
   virtual int health();
   // buffers a subclass owns beyond the ones below
+  virtual int alloc_extra(uint32_t /*max_nodes*/) { return MAMCTS_OK; }
   virtual void free_extra() {}
 };
 

@@ -244,7 +244,8 @@ def test_reference_const_search_reproduces_reference_tree(engine, layout):
 
 
 @pytest.mark.parametrize("num_others,layout", [(1, LAYOUT_CLASSIC), (1, LAYOUT_COMPACT), (2, LAYOUT_AUTO),
-                                               (3, LAYOUT_AUTO), (7, LAYOUT_AUTO)])
+                                               (3, LAYOUT_AUTO), (7, LAYOUT_AUTO), (2, LAYOUT_CLASSIC),
+                                               (3, LAYOUT_COMPACT), (7, LAYOUT_CLASSIC), (7, LAYOUT_COMPACT)])
 def test_philox_search_equals_oracle_tree(engine, num_others, layout):
     iters = 600
     mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
@@ -318,6 +319,39 @@ def test_philox_search_equals_reference_twin(engine):
     assert m["visits"] == exp["visits"] and m["best"] == exp["best"]
     assert rel_close(m["value"], exp["value"], 1e-6)
     s.close()
+
+
+def test_multi_agent_compact_layout_agrees_with_classic_on_large_trees(engine):
+    """3, 4 and 8 agents (the reference's own 4-agent setting included: chain 41, goal 26,
+    environments/tests/crossing_state_int_test.cc:231-252) at the benchmark's tree size: the counts-only compact
+    layout (search_compact_multi.cuh) and the classic one hold the same trees, statistic for statistic, and one of
+    them is checked against the CPU oracle; 70 000-iteration configurations use the 32-bit-count records."""
+    for others, kw, iters, max_iter in ((2, {}, 10000, 10000), (3, dict(chain_length=41, ego_goal_pos=26), 6000, 6000),
+                                        (7, {}, 10000, 10000), (7, {}, 1500, 70000)):
+        mp = default_params(max_number_of_iterations=max_iter, max_number_of_nodes=20000 if max_iter > 65000 else 100000000,
+                            rh_max_number_of_iterations=50)
+        cp = default_crossing_params(num_other_agents=others, **kw)
+        dumps, merged, counters = [], [], []
+        for layout in (LAYOUT_CLASSIC, LAYOUT_COMPACT):
+            s = Search(engine, ENV_CROSSING_I32, mp, 40, cp=cp, action_source=SRC_PHILOX, philox_seed=1000,
+                       first_tree_id=3, layout=layout)
+            s.run(iters // 2)
+            s.run(iters - iters // 2)
+            dumps.append([s.dump_tree(t, iters + 1) for t in (0, 39)])
+            merged.append(s.merge_roots())
+            counters.append(s.counters())
+            for agent in (0, others):
+                assert s.root_stats(5, agent)["visits"] == iters
+            s.close()
+        for a, b in zip(*dumps):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        assert counters[0] == counters[1]
+        assert merged[0]["n"].tolist() == merged[1]["n"].tolist() and merged[0]["best"] == merged[1]["best"]
+        assert_bit_equal(merged[0]["q"], merged[1]["q"], "merged q")
+        t = O.OracleTree(O.make_env(cp=cp), mp, [5] * (others + 1), action_source=SRC_PHILOX, seed=1000, tree_id=3 + 39)
+        t.run(iters)
+        assert np.array_equal(dumps[1][1], t.dump(7))
+        t.close()
 
 
 def test_compact_and_classic_layouts_agree_on_large_trees(engine):
@@ -405,9 +439,21 @@ def test_compact_layout_reports_exhausted_inner_records(engine):
     with pytest.raises(MamctsError, match="inner node records"):
         s.counters()
     s.close()
-    with pytest.raises(MamctsError, match="direct child table"):
-        Search(engine, ENV_CROSSING_I32, mp, 1, cp=default_crossing_params(num_other_agents=2),
-               layout=LAYOUT_COMPACT)
+    # the same for the multi-agent compact layout
+    s = Search(engine, ENV_CROSSING_I32, mp, 8, cp=default_crossing_params(num_other_agents=3), action_source=SRC_PHILOX,
+               philox_seed=5, layout=LAYOUT_COMPACT, max_inner_nodes_per_tree=50)
+    s.run(2000)
+    with pytest.raises(MamctsError, match="inner node records"):
+        s.merge_roots()
+    s.close()
+    # a compact layout that does not exist for the configuration is refused, not silently replaced:
+    # a negative discount (the other agents' values are no longer known to be +0.0), trees of >= 32 767 nodes
+    with pytest.raises(MamctsError, match="compact layouts"):
+        Search(engine, ENV_CROSSING_I32, default_params(max_number_of_iterations=100, discount_factor=-0.5), 1,
+               cp=default_crossing_params(num_other_agents=2), layout=LAYOUT_COMPACT)
+    with pytest.raises(MamctsError, match="compact layouts"):
+        Search(engine, ENV_CROSSING_I32, default_params(max_number_of_iterations=40000, max_number_of_nodes=100000000), 1,
+               cp=default_crossing_params(num_other_agents=2), layout=LAYOUT_COMPACT)
 
 
 @pytest.mark.parametrize("layout", [LAYOUT_CLASSIC, LAYOUT_COMPACT])
