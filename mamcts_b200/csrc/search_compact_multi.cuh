@@ -98,6 +98,8 @@ search_compact_multi_kernel(const __grid_constant__ SearchParams p, const __grid
   uint8_t path_ja[kPathMaxMulti][A];
   BackRegs path_back[kPathMaxMulti];   // the ego's values as the descent saw them
   double path_r0[kPathMaxMulti];
+  CNT path_cnt_o[kPathMaxMulti][NO];   // n[a] of every other agent's chosen action as the descent saw it: the
+                                       // backup does no loads (a tree is touched by its lane only)
 
 #pragma unroll 1
   for (uint32_t iter = 0; iter < p.iterations; ++iter) {
@@ -110,6 +112,10 @@ search_compact_multi_kernel(const __grid_constant__ SearchParams p, const __grid
 #pragma unroll 1
     while (!failed) {
       Inner* nd = inner + node;
+      // one memory round trip for the whole record: every line of it is requested before the first use (the
+      // loop over the agents below would otherwise fetch them one after the other)
+#pragma unroll
+      for (size_t off = 64; off < sizeof(Inner); off += 64) prefetch_l1(reinterpret_cast<const char*>(nd) + off);
       const uint32_t vc = nd->visit_count;
       nd->visit_count = (CNT)(vc + 1);                                          // :180
       if (Env::terminal(p.env, st) || depth == p.max_depth || num_nodes > p.node_budget) {   // :183-187
@@ -140,6 +146,7 @@ search_compact_multi_kernel(const __grid_constant__ SearchParams p, const __grid
         bool w;
         ja[j + 1] = (uint8_t)select_action<NA>(oth, p, tab, 1, p.n_oth, exact_evals, back, w, true);
         if (w) nd->nexp_o[j] = (uint8_t)(oth.nexp + 1);
+        path_cnt_o[depth][j] = (CNT)back.cnt0;
       }
       path_node[depth] = node;
       uint32_t code = 0;
@@ -155,6 +162,7 @@ search_compact_multi_kernel(const __grid_constant__ SearchParams p, const __grid
         if ((w >> 16) == key) { entry = (uint32_t)(w & 0xFFFFull); break; }
         slot = (slot + 1) & c.table_mask;
       }
+      if (entry & 1u) prefetch_l1(inner + (entry >> 1));   // the child's record travels while the state is stepped
       // the child's state and the reward collected on the edge (collect(), node_statistic.h:115-121)
       int32_t act[A];
 #pragma unroll
@@ -221,7 +229,7 @@ search_compact_multi_kernel(const __grid_constant__ SearchParams p, const __grid
 #pragma unroll
       for (int j = 0; j < NO; ++j) {   // reward-free agents: only the counts move
         const uint32_t ao = path_ja[level][j + 1];
-        pn->n_o[j][ao] = (CNT)(pn->n_o[j][ao] + 1);
+        pn->n_o[j][ao] = (CNT)(path_cnt_o[level][j] + 1);
       }
       G = e.G;
     }

@@ -21,6 +21,7 @@
 #define MAMCTS_B200_HOST_BATCHED_MCTS_H_
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -69,7 +70,7 @@ class BatchedRootParallelMcts {
     for (unsigned t = 0; t < num_trees_; ++t)
       roots_.push_back(std::make_shared<Node, NodePtr, std::shared_ptr<S>, const JointAction&, const unsigned int&>(
           nullptr, current_state.clone(), JointAction(), 0, mcts_parameters_));
-    for (num_iterations_ = 0; num_iterations_ < mcts_parameters_.MAX_NUMBER_OF_ITERATIONS; ++num_iterations_) wave();
+    run_waves(mcts_parameters_.MAX_NUMBER_OF_ITERATIONS);
   }
 
   const Node& get_root(unsigned tree) const { return *roots_.at(tree); }
@@ -89,114 +90,146 @@ class BatchedRootParallelMcts {
   }
 
  private:
-  void wave() {
+  // Per-wave buffers, allocated once per search: slot t belongs to tree t (no compaction - a tree whose
+  // leaf needs no rollout is marked terminal, which makes its rollout a no-op), so every phase but the one
+  // launch is independent per tree and is split over the host threads.
+  struct WaveBuffers {
+    std::vector<NodePtr> leaf;
+    std::vector<uint8_t> needs_rollout, flags;
+    std::vector<int32_t> x, last;
+    std::vector<uint32_t> depth, stream_hi, stream_lo;
+    std::vector<double> ego, other, cost, len;
+  };
+  // A reusable barrier for the worker threads (they spin: a phase is a few milliseconds, the launch ~100 us).
+  struct SpinBarrier {
+    explicit SpinBarrier(unsigned n) : n_(n) {}
+    void wait() {
+      const unsigned gen = gen_.load(std::memory_order_acquire);
+      if (count_.fetch_add(1, std::memory_order_acq_rel) + 1 == n_) {
+        count_.store(0, std::memory_order_relaxed);
+        gen_.fetch_add(1, std::memory_order_release);
+      } else {
+        while (gen_.load(std::memory_order_acquire) == gen) std::this_thread::yield();
+      }
+    }
+    const unsigned n_;
+    std::atomic<unsigned> count_{0}, gen_{0};
+  };
+
+  void run_waves(unsigned iterations) {
     using CS = CudaState<S>;
     const uint32_t T = num_trees_;
-    std::vector<NodePtr> leaf(T);
-    std::vector<uint8_t> needs_rollout(T, 0);
-    std::vector<uint32_t> batch;  // trees whose leaf needs a rollout
-    // ---- select & expand, one leaf per tree (mcts.h:300-305) ------------------------------------
-    parallel_over_trees([&](uint32_t t) {
-      NodePtr node = roots_[t];
-      std::pair<bool, bool> res(true, true);
-      while (res.first) res = node->select_or_expand(node);
-      leaf[t] = node;
-      needs_rollout[t] = res.second ? 1 : 0;
-    });
-    for (uint32_t t = 0; t < T; ++t) if (needs_rollout[t]) batch.push_back(t);
-    // ---- ONE launch for all leaves (replaces T x heuristic_.calculate_heuristic_values, mcts.h:310)
-    const uint32_t n = (uint32_t)batch.size();
-    const uint32_t A = n ? CS::num_agents(*leaf[batch[0]]->get_state()) : 0;
-    std::vector<double> ego(n), other((size_t)(A > 1 ? A - 1 : 1) * (n ? n : 1)), cost(n), len(n);
-    if (n) {
-      const uint32_t XR = CS::kEnv == MAMCTS_ENV_SIMPLE ? 1 : A;
-      std::vector<int32_t> x((size_t)XR * n), last((size_t)A * n);
-      std::vector<uint8_t> flags(n);
-      std::vector<uint32_t> depth(n), stream_hi(n), stream_lo(n);
-      for (uint32_t i = 0; i < n; ++i) {
-        int32_t xi[MAMCTS_MAX_AGENTS] = {0}, li[MAMCTS_MAX_AGENTS] = {0};
-        CS::pack(*leaf[batch[i]]->get_state(), xi, li, &flags[i]);
-        for (uint32_t a = 0; a < XR; ++a) x[(size_t)a * n + i] = xi[a];
-        for (uint32_t a = 0; a < A; ++a) last[(size_t)a * n + i] = li[a];
-        depth[i] = leaf[batch[i]]->get_depth();
-        stream_hi[i] = first_tree_id_ + batch[i];
-        stream_lo[i] = ++calls_[batch[i]] * K_;
-      }
-      const mamcts_params mp = to_mamcts_params(mcts_parameters_);
-      mamcts_action_source src;
-      std::memset(&src, 0, sizeof(src));
-      src.kind = MAMCTS_SRC_PHILOX;
-      src.mem = MAMCTS_MEM_HOST;
-      src.philox_seed = philox_seed_;
-      src.stream_hi = stream_hi.data();
-      src.stream_lo = stream_lo.data();
-      mamcts_rollout_out out;
-      std::memset(&out, 0, sizeof(out));
-      out.mem = MAMCTS_MEM_HOST;
-      out.ego_return = ego.data();
-      out.other_return = other.data();
-      out.ego_cost = cost.data();
-      out.step_length = len.data();
-      uint64_t steps = 0;
-      out.total_steps = &steps;
-      if constexpr (CS::kEnv == MAMCTS_ENV_CROSSING_I32) {
-        CudaEngine::check(mamcts_rollout_crossing_i32(CudaEngine::get(), &mp, &env_, n, K_,
-                                                      MAMCTS_MEM_HOST, x.data(), last.data(), flags.data(),
-                                                      depth.data(), &src, &out),
-                          "mamcts_rollout_crossing_i32");
-      } else {
-        CudaEngine::check(mamcts_rollout_simple(CudaEngine::get(), &mp, &env_, n, K_, MAMCTS_MEM_HOST,
-                                                x.data(), depth.data(), &src, &out),
-                          "mamcts_rollout_simple");
-      }
-      rollout_steps_ += steps;
-    }
-    // ---- update_statistics + back-propagation per tree (mcts.h:309-329) -------------------------
-    std::vector<int32_t> batch_index(T, -1);
-    for (uint32_t i = 0; i < n; ++i) batch_index[batch[i]] = (int32_t)i;
-    auto finish_tree = [&](uint32_t t) {
-      NodePtr node = leaf[t];
-      if (batch_index[t] >= 0) {
-        const uint32_t bi = (uint32_t)batch_index[t];
-        const S* st = node->get_state();
-        SE ego_h(0, st->get_ego_agent_idx(), mcts_parameters_);
-        EgoCosts accum_cost(st->get_num_costs(), 0.0);
-        if (!accum_cost.empty()) accum_cost[0] = cost[bi];
-        ego_h.set_heuristic_estimate(ego[bi], accum_cost);
-        std::unordered_map<AgentIdx, SO> others_h;
-        uint32_t j = 0;
-        for (auto ai : st->get_other_agent_idx()) {
-          SO so(0, ai, mcts_parameters_);
-          so.set_heuristic_estimate(other[(size_t)j * n + bi], accum_cost);
-          others_h.insert(std::pair<AgentIdx, SO>(ai, so));
-          ++j;
-        }
-        node->update_statistics(ego_h, others_h);
-      }
-      NodePtr node_p = node->get_parent().lock();
-      while (bool(node_p)) {
-        node_p->update_statistics(node);
-        if (node_p->is_root()) break;
-        node = node->get_parent().lock();
-        node_p = node_p->get_parent().lock();
+    const uint32_t A = CS::num_agents(*roots_[0]->get_state());
+    const uint32_t XR = CS::kEnv == MAMCTS_ENV_SIMPLE ? 1 : A;
+    WaveBuffers w;
+    w.leaf.resize(T); w.needs_rollout.assign(T, 0); w.flags.assign(T, 0);
+    w.x.assign((size_t)XR * T, 0); w.last.assign((size_t)A * T, 0);
+    w.depth.assign(T, 0); w.stream_hi.assign(T, 0); w.stream_lo.assign(T, 0);
+    w.ego.assign(T, 0.0); w.other.assign((size_t)(A > 1 ? A - 1 : 1) * T, 0.0); w.cost.assign(T, 0.0); w.len.assign(T, 0.0);
+    // statistics that record their updates per host thread (CudaUctStatistic) stay on one thread
+    const unsigned nt = kDeferredStatistic ? 1u : std::min<unsigned>(host_threads_, std::max(1u, T / 64));
+    SpinBarrier barrier(nt);
+    auto worker = [&](unsigned k) {
+      const uint32_t t0 = (uint32_t)((uint64_t)T * k / nt), t1 = (uint32_t)((uint64_t)T * (k + 1) / nt);
+      for (unsigned it = 0; it < iterations; ++it) {
+        for (uint32_t t = t0; t < t1; ++t) select_and_pack(w, t, T, A, XR);
+        barrier.wait();
+        if (k == 0) { launch_rollouts(w, T, A); num_iterations_ = it + 1; }
+        barrier.wait();
+        for (uint32_t t = t0; t < t1; ++t) finish_tree(w, t, T);
+        // deferred statistics (CudaUctStatistic, one thread): all T paths of the wave in one mamcts_backup_uct
+        if (k == 0) flush_if_deferred<SE>(0);
       }
     };
-    // statistics that record their updates per host thread (CudaUctStatistic) stay on one thread
-    if (kDeferredStatistic) for (uint32_t t = 0; t < T; ++t) finish_tree(t);
-    else parallel_over_trees(finish_tree);
-    // deferred statistics (CudaUctStatistic): all T paths of the wave in one mamcts_backup_uct
-    flush_if_deferred<SE>(0);
+    num_iterations_ = 0;
+    if (nt <= 1) { worker(0); return; }
+    std::vector<std::thread> pool;
+    for (unsigned k = 1; k < nt; ++k) pool.emplace_back(worker, k);
+    worker(0);
+    for (auto& th : pool) th.join();
   }
 
-  template <class F>
-  void parallel_over_trees(F&& f) {
-    const uint32_t T = num_trees_;
-    const unsigned nt = std::min<unsigned>(host_threads_, std::max(1u, T / 64));
-    if (nt <= 1) { for (uint32_t t = 0; t < T; ++t) f(t); return; }
-    std::vector<std::thread> pool;
-    for (unsigned k = 0; k < nt; ++k)
-      pool.emplace_back([&, k] { for (uint32_t t = (uint32_t)((uint64_t)T * k / nt); t < (uint32_t)((uint64_t)T * (k + 1) / nt); ++t) f(t); });
-    for (auto& th : pool) th.join();
+  // ---- select & expand, one leaf per tree (mcts.h:300-305), and its state into slot t ----------------
+  void select_and_pack(WaveBuffers& w, uint32_t t, uint32_t T, uint32_t A, uint32_t XR) {
+    using CS = CudaState<S>;
+    NodePtr node = roots_[t];
+    std::pair<bool, bool> res(true, true);
+    while (res.first) res = node->select_or_expand(node);
+    w.leaf[t] = node;
+    w.needs_rollout[t] = res.second ? 1 : 0;
+    int32_t xi[MAMCTS_MAX_AGENTS] = {0}, li[MAMCTS_MAX_AGENTS] = {0};
+    uint8_t fl = 0;
+    CS::pack(*node->get_state(), xi, li, &fl);
+    for (uint32_t a = 0; a < XR; ++a) w.x[(size_t)a * T + t] = xi[a];
+    for (uint32_t a = 0; a < A; ++a) w.last[(size_t)a * T + t] = li[a];
+    w.flags[t] = res.second ? fl : (uint8_t)1;   // no rollout wanted: a terminal start state skips the loop
+    w.depth[t] = node->get_depth();
+    w.stream_hi[t] = first_tree_id_ + t;
+    if (res.second) w.stream_lo[t] = ++calls_[t] * K_;
+  }
+
+  // ---- ONE launch for all leaves (replaces T x heuristic_.calculate_heuristic_values, mcts.h:310) ------
+  void launch_rollouts(WaveBuffers& w, uint32_t T, uint32_t A) {
+    using CS = CudaState<S>;
+    (void)A;
+    const mamcts_params mp = to_mamcts_params(mcts_parameters_);
+    mamcts_action_source src;
+    std::memset(&src, 0, sizeof(src));
+    src.kind = MAMCTS_SRC_PHILOX;
+    src.mem = MAMCTS_MEM_HOST;
+    src.philox_seed = philox_seed_;
+    src.stream_hi = w.stream_hi.data();
+    src.stream_lo = w.stream_lo.data();
+    mamcts_rollout_out out;
+    std::memset(&out, 0, sizeof(out));
+    out.mem = MAMCTS_MEM_HOST;
+    out.ego_return = w.ego.data();
+    out.other_return = w.other.data();
+    out.ego_cost = w.cost.data();
+    out.step_length = w.len.data();
+    uint64_t steps = 0;
+    out.total_steps = &steps;
+    if constexpr (CS::kEnv == MAMCTS_ENV_CROSSING_I32) {
+      CudaEngine::check(mamcts_rollout_crossing_i32(CudaEngine::get(), &mp, &env_, T, K_, MAMCTS_MEM_HOST, w.x.data(),
+                                                    w.last.data(), w.flags.data(), w.depth.data(), &src, &out),
+                        "mamcts_rollout_crossing_i32");
+    } else {
+      // SimpleState: is_terminal() is a function of the state length; a tree that wants no rollout gets the
+      // depth limit instead (random_heuristic.h:45-47)
+      for (uint32_t t = 0; t < T; ++t) if (!w.needs_rollout[t]) w.depth[t] = mcts_parameters_.MAX_SEARCH_DEPTH;
+      CudaEngine::check(mamcts_rollout_simple(CudaEngine::get(), &mp, &env_, T, K_, MAMCTS_MEM_HOST, w.x.data(),
+                                              w.depth.data(), &src, &out),
+                        "mamcts_rollout_simple");
+    }
+    rollout_steps_ += steps;
+  }
+
+  // ---- update_statistics + back-propagation of one tree (mcts.h:309-329) -------------------------------
+  void finish_tree(WaveBuffers& w, uint32_t t, uint32_t T) {
+    NodePtr node = w.leaf[t];
+    if (w.needs_rollout[t]) {
+      const S* st = node->get_state();
+      SE ego_h(0, st->get_ego_agent_idx(), mcts_parameters_);
+      EgoCosts accum_cost(st->get_num_costs(), 0.0);
+      if (!accum_cost.empty()) accum_cost[0] = w.cost[t];
+      ego_h.set_heuristic_estimate(w.ego[t], accum_cost);
+      std::unordered_map<AgentIdx, SO> others_h;
+      uint32_t j = 0;
+      for (auto ai : st->get_other_agent_idx()) {
+        SO so(0, ai, mcts_parameters_);
+        so.set_heuristic_estimate(w.other[(size_t)j * T + t], accum_cost);
+        others_h.insert(std::pair<AgentIdx, SO>(ai, so));
+        ++j;
+      }
+      node->update_statistics(ego_h, others_h);
+    }
+    NodePtr node_p = node->get_parent().lock();
+    while (bool(node_p)) {
+      node_p->update_statistics(node);
+      if (node_p->is_root()) break;
+      node = node->get_parent().lock();
+      node_p = node_p->get_parent().lock();
+    }
   }
 
   template <class Stat>

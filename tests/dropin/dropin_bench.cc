@@ -29,6 +29,7 @@ static double seconds_since(Clock::time_point t0) {
 int main(int argc, char** argv) {
   const unsigned iterations = argc > 1 ? std::atoi(argv[1]) : 2000;
   const unsigned trees = argc > 2 ? std::atoi(argv[2]) : 4096;
+  const bool only_threads = argc > 3 && std::atoi(argv[3]) == 1;   // only the all-host-threads batched driver
   MctsParameters p = mcts_default_parameters();
   p.MAX_NUMBER_OF_ITERATIONS = iterations;
   p.MAX_NUMBER_OF_NODES = 100000000;
@@ -40,13 +41,13 @@ int main(int argc, char** argv) {
   CudaState<CrossingState<int>>::set_parameters(cparams);
   std::unordered_map<AgentIdx, HypothesisId> hyp{{1, 0}};
   CrossingState<int> state(hyp, cparams);
-  {
+  if (!only_threads) {
     Mcts<CrossingState<int>, UctStatistic, UctStatistic, RandomHeuristic> m(p);
     auto t0 = Clock::now();
     m.search(state);
     std::printf("stock CPU, 1 tree:                 %9.0f iterations/s\n", m.numIterations() / seconds_since(t0));
   }
-  {
+  if (!only_threads) {
     CudaRandomHeuristic::options() = CudaRandomHeuristic::Options();
     CudaRandomHeuristic::options().action_source = MAMCTS_SRC_PHILOX;
     Mcts<CrossingState<int>, UctStatistic, UctStatistic, CudaRandomHeuristic> m(p);
@@ -55,7 +56,7 @@ int main(int argc, char** argv) {
     m.search(state);
     std::printf("drop-in heuristic, 1 leaf/launch:  %9.0f iterations/s\n", m.numIterations() / seconds_since(t0));
   }
-  {
+  if (!only_threads) {
     BatchedRootParallelMcts<CrossingState<int>, UctStatistic, UctStatistic> b(p, trees, 1000);
     auto t0 = Clock::now();
     b.search(state);
@@ -71,7 +72,7 @@ int main(int argc, char** argv) {
     std::printf("batched driver, %5u trees, all host threads: %9.0f iterations/s (%.2f s)\n", trees,
                 (double)trees * iterations / s, s);
   }
-  {
+  if (!only_threads) {
     BatchedRootParallelMcts<CrossingState<int>, CudaUctStatistic, CudaUctStatistic> b(p, trees / 8, 1000);
     auto t0 = Clock::now();
     b.search(state);
