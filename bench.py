@@ -799,6 +799,8 @@ def run_native(args):
     # ---- the sections every N carries: C5 (strong scaling) and C3 (rollouts sharded), after the trees are freed
     c5 = measure_c5_strong(engine, stream, world, rank, dist) if not args.no_sections else None
     c3 = measure_rollout_c3(engine, stream, world, rank, dist=dist if world > 1 else None) if not args.no_sections else None
+    if world > 1:
+        engine.comm_destroy()   # every collective of the bench is done; what follows runs on rank 0 alone
     c4 = measure_c4_hypothesis(engine, stream) if (rank == 0 and not args.no_sections) else None
     if rank == 0:
         line["leaf_batched"] = leaf_batched
@@ -815,7 +817,6 @@ def run_native(args):
         line["rollout_c3"] = c3
         print(json.dumps(line))
     if world > 1:
-        engine.comm_destroy()
         dist.barrier()
         dist.destroy_process_group()
     engine.close()

@@ -33,4 +33,28 @@ def run():
     m = s.merge_roots()
     assert m["visits"] == 64 * 200
     s.close()
+    # 8 agents: the counts-only compact layout (search_compact_multi.cuh)
+    cp8 = default_crossing_params(num_other_agents=7)
+    s = Search(e, ENV_CROSSING_I32, mp, 32, cp=cp8, action_source=SRC_PHILOX, philox_seed=1000)
+    s.run(200)
+    t = O.OracleTree(O.make_env(cp=cp8), mp, [5] * 8, action_source=SRC_PHILOX, seed=1000, tree_id=3)
+    t.run(200)
+    assert np.array_equal(s.dump_tree(3, 201), t.dump(7)), "smoke 8-agent search tree differs from the oracle"
+    s.close()
+    # per-ego-action heuristic (ActionValueRandomHeuristic's compute part)
+    cp3 = default_crossing_params(num_other_agents=2)
+    av = e.action_values_crossing(mp, cp3, x[:, :64].repeat(2, axis=0)[:3], kind=SRC_PHILOX, seed=5, stream_hi_base=2)
+    ex = O.action_values_batch(O.make_env(cp=cp3), mp, x[:, :64].repeat(2, axis=0)[:3], kind=SRC_PHILOX, seed=5, stream_hi_base=2)
+    assert_bit_equal(av["action_return"], ex["action_return"], "smoke action values")
+    # hypothesis-MCTS on the device against the digest of the reference's own search (tests/golden)
+    from helpers import golden, tree_digest
+    from mamcts_b200 import default_hypothesis_params
+    from mamcts_b200.engine import HypSearch
+    g = [c for c in golden("hypothesis_search.json") if c["name"] == "int_test_wrong_hypothesis"][0]
+    mph = default_params(max_number_of_iterations=g["iters"], max_number_of_nodes=100000000, rh_max_number_of_iterations=50)
+    hs = HypSearch(e, mph, default_hypothesis_params(), default_crossing_params(num_other_agents=g["others"]), 2,
+                   [tuple(r) for r in g["gaps"]], np.array(g["sequence"], dtype=np.uint8).reshape(g["iters"], g["others"]))
+    hs.run(g["iters"])
+    assert tree_digest(hs.dump_tree(1, g["num_nodes"] + 1)) == g["tree_sha256"], "smoke hypothesis tree differs from the reference"
+    hs.close()
     e.close()
