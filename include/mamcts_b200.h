@@ -152,6 +152,12 @@ typedef struct mamcts_action_source {
    * by calculate_action (:35-55); the ego agent draws uniformly among its actions. */
   const int32_t* hyp_gap_lo;
   const int32_t* hyp_gap_hi;
+  /* HYPOTHESIS for mamcts_rollout_crossing_f32 (AgentPolicyCrossingState<float>::act, agent_policy.h:78-84): the
+   * same ranges as floats; every step the agent's desired gap is lo + (hi - lo) * (w / 65536) with w the 16-bit
+   * word of its Philox position (the reference draws a std::uniform_real_distribution from the policy's own
+   * mt19937 - exactness for that generator is REPLAY), then calculate_action in FP32. */
+  const float* hyp_gap_lo_f32;
+  const float* hyp_gap_hi_f32;
 } mamcts_action_source;
 
 /* Outputs of a batched rollout. Any pointer may be NULL (not produced). `mem` says where they

@@ -125,6 +125,8 @@ class ActionSource(C.Structure):
         ("stream_lo_base", C.c_uint32),
         ("hyp_gap_lo", C.c_void_p),
         ("hyp_gap_hi", C.c_void_p),
+        ("hyp_gap_lo_f32", C.c_void_p),
+        ("hyp_gap_hi_f32", C.c_void_p),
     ]
 
 

@@ -23,6 +23,7 @@ struct EnvParams {
   int32_t win_len, lose_len;
   // CrossingState<float> (Domain-typed parameters, crossing_state_parameters.h:15-28)
   float f_min_v_ego, f_crossing_point, f_goal_pos;
+  float f_min_v_other, f_max_v_other;   // MIN/MAX_VELOCITY_OTHER of CrossingState<float> (behaviour-hypothesis policy)
   // CrossingState: the ego reward and cost of a step only depend on (goal, collision, out_of_map);
   // the 8 possible values are evaluated once on the host in the reference's operation order
   // (crossing_state.h:146-153) and looked up with index goal | collision << 1 | out_of_map << 2.
@@ -79,6 +80,8 @@ inline void make_crossing_env_f32(const mamcts_crossing_params_f32& cp, EnvParam
   ep.f_crossing_point = half + 1.0f;
   ep.f_goal_pos = cp.ego_goal_pos;
   ep.f_min_v_ego = cp.min_velocity_ego;
+  ep.f_min_v_other = cp.min_velocity_other;
+  ep.f_max_v_other = cp.max_velocity_other;
   // NUM_EGO_ACTIONS() is a float for this Domain and get_num_actions converts it to ActionIdx (:165-171)
   volatile float n_ego = cp.max_velocity_ego - cp.min_velocity_ego + 1.0f;
   ep.n_ego_actions = (uint32_t)n_ego;
@@ -213,6 +216,20 @@ __device__ __forceinline__ int32_t crossing_policy_action(const EnvParams& p, in
   if (desired_gap > 0)                                                 // :41-46
     return gap_error < 0 ? max(gap_error, p.min_v_other) : min(gap_error, p.max_v_other);
   return max(min(gap_error, p.max_v_other), agent_last);               // :47-50
+}
+
+// AgentPolicyCrossingState<float>::calculate_action (the same lines with Domain = float): every operation one
+// FP32 operation in the reference's order; std::max(a, b) = a < b ? b : a and std::min(a, b) = b < a ? b : a,
+// which also fixes the signs of zeros.
+__device__ __forceinline__ float crossing_policy_action_f32(const EnvParams& p, float agent_x, float agent_last,
+                                                            float ego_x, float ego_last, float desired_gap) {
+  if (!(agent_x < p.f_crossing_point)) return agent_last;                                   // :51-53
+  const float gap_error = __fsub_rn(__fsub_rn(__fadd_rn(ego_x, ego_last), agent_x), desired_gap);   // :39
+  if (desired_gap > 0.0f)                                                                  // :41-46
+    return gap_error < 0.0f ? (gap_error < p.f_min_v_other ? p.f_min_v_other : gap_error)
+                            : (p.f_max_v_other < gap_error ? p.f_max_v_other : gap_error);
+  const float lim = p.f_max_v_other < gap_error ? p.f_max_v_other : gap_error;             // :47-50
+  return lim < agent_last ? agent_last : lim;
 }
 
 // SimpleState: one int32 of state, 2 agents x 2 actions (reference test/uct/simple_state.h).

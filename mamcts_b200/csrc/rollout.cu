@@ -43,6 +43,8 @@ struct RolloutParams {
   uint32_t stream_hi_base, stream_lo_base;
   const int32_t* hyp_lo;   // HYPOTHESIS: desired-gap range of other j of leaf i at [j * n_leaves + i]
   const int32_t* hyp_hi;
+  const float* hyp_lo_f;   // the same for CrossingState<float>
+  const float* hyp_hi_f;
   // mcts
   const double* disc;      // [0, disc_len): reward weight of step k; [disc_len, 2 disc_len): (1/nA_ego)^k
   uint32_t disc_len;
@@ -107,6 +109,7 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
   bool has = false, fin = true;
   unsigned long long lane_steps = 0;
   int32_t gap_lo[kHyp ? A : 1], gap_span[kHyp ? A : 1];   // [a]: other agent at position a (a >= 1)
+  float gap_lo_f[(kHyp && kFloat) ? A : 1], gap_span_f[(kHyp && kFloat) ? A : 1];   // CrossingState<float>: lo, hi - lo
 
   auto load = [&]() {
     has = rid < p.total;
@@ -127,11 +130,18 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
       s_hi = p.stream_hi ? __ldg(p.stream_hi + leaf) : p.stream_hi_base;
       s_lo = p.stream_lo ? __ldg(p.stream_lo + leaf) + (rid - leaf * p.K) : p.stream_lo_base + rid;
     }
-    if (kHyp) {
+    if (kHyp && !kFloat) {
 #pragma unroll
       for (int a = 1; a < A; ++a) {
         gap_lo[a] = __ldg(p.hyp_lo + (size_t)(a - 1) * p.n_leaves + leaf);
         gap_span[a] = max(__ldg(p.hyp_hi + (size_t)(a - 1) * p.n_leaves + leaf) - gap_lo[a] + 1, 1);  // lo <= hi (agent_policy.h:28)
+      }
+    }
+    if constexpr (kHyp && kFloat) {
+#pragma unroll
+      for (int a = 1; a < A; ++a) {
+        gap_lo_f[a] = __ldg(p.hyp_lo_f + (size_t)(a - 1) * p.n_leaves + leaf);
+        gap_span_f[a] = __fsub_rn(__ldg(p.hyp_hi_f + (size_t)(a - 1) * p.n_leaves + leaf), gap_lo_f[a]);
       }
     }
     ego = 0.0; cost = 0.0; r_other_last = 0.0; it = 0;   // random_heuristic.h:36-49
@@ -222,10 +232,22 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
             // (AgentPolicyCrossingState<int>::act, agent_policy.h:68-75)
             span[a] = (kHyp && a > 0) ? (uint32_t)gap_span[kHyp ? a : 0] : Env::num_actions(p.env, a);
           }
+          // CrossingState<float> hypotheses: the desired gap is lo + (hi - lo) * (w / 65536) of the raw 16-bit word
+          // w (uniform_real_distribution's stand-in, agent_policy.h:78-84); only the ego's draw is a bounded index
+          float gap_f[(kHyp && kFloat) ? A : 1];
+          if constexpr (kHyp && kFloat) {
+#pragma unroll
+            for (int a = 1; a < A; ++a) {
+              gap_f[a] = __fadd_rn(gap_lo_f[a], __fmul_rn(gap_span_f[a], __fmul_rn((float)h[a], 1.0f / 65536.0f)));
+              span[a] = 65536u;   // no rejection: the word itself is the draw
+            }
+          }
           philox_bounded_all<A>(h, span, it * A, s_lo, s_hi, p.key0, p.key1);
 #pragma unroll
-          for (int a = 0; a < A; ++a)
-            act[a] = (kHyp && a > 0) ? (D)(gap_lo[kHyp ? a : 0] + (int32_t)h[a]) : Env::action_from_index(a, h[a]);
+          for (int a = 0; a < A; ++a) {
+            if constexpr (kHyp && kFloat) act[a] = a > 0 ? (D)gap_f[a] : Env::action_from_index(a, h[a]);
+            else act[a] = (kHyp && a > 0) ? (D)(gap_lo[kHyp ? a : 0] + (int32_t)h[a]) : Env::action_from_index(a, h[a]);
+          }
         } else {
 #pragma unroll
           for (int a = 0; a < A; ++a) {
@@ -242,6 +264,14 @@ rollout_kernel(const __grid_constant__ RolloutParams p) {
 #pragma unroll
           for (int a = 1; a < A; ++a)
             act[a] = crossing_policy_action(p.env, st.x[a], st.last[a], st.x[0], st.last[0], act[a]);
+        }
+        if constexpr (kHyp && kFloat) {
+          D v[A];
+#pragma unroll
+          for (int a = 1; a < A; ++a)
+            v[a] = crossing_policy_action_f32(p.env, st.x[a], st.last[a], st.x[0], st.last[0], act[a]);
+#pragma unroll
+          for (int a = 1; a < A; ++a) act[a] = v[a];
         }
         bool ended;
         if constexpr (Env::kOutcomeRewards) {
@@ -392,8 +422,6 @@ static int dispatch_crossing(mamcts_engine* e, const RolloutParams& p, int num_o
 constexpr int kEnvCrossingF32 = 100;   // internal environment kind of rollout_common
 
 static int dispatch_crossing_f32(mamcts_engine* e, const RolloutParams& p, int num_others, int kind, bool parity) {
-  if (kind == MAMCTS_SRC_HYPOTHESIS)
-    return fail(e, MAMCTS_ERR_UNSUPPORTED, "rollout: HYPOTHESIS is built for CrossingState<int>; replay float-domain policies");
   switch (num_others) {
     case 1: return launch_rollout<CrossingEnvF<1>>(e, p, kind, parity);
     case 2: return launch_rollout<CrossingEnvF<2>>(e, p, kind, parity);
@@ -424,7 +452,9 @@ static int rollout_locked(mamcts_engine* e, int env_kind, const mamcts_params* m
     return fail(e, MAMCTS_ERR_INVALID, "rollout: REPLAY needs K == 1 and replay buffers");
   if (src->kind < MAMCTS_SRC_REPLAY || src->kind > MAMCTS_SRC_HYPOTHESIS)
     return fail(e, MAMCTS_ERR_INVALID, "rollout: unknown action source");
-  if (src->kind == MAMCTS_SRC_HYPOTHESIS && (env_kind != MAMCTS_ENV_CROSSING_I32 || !src->hyp_gap_lo || !src->hyp_gap_hi))
+  if (src->kind == MAMCTS_SRC_HYPOTHESIS &&
+      !((env_kind == MAMCTS_ENV_CROSSING_I32 && src->hyp_gap_lo && src->hyp_gap_hi) ||
+        (f32 && src->hyp_gap_lo_f32 && src->hyp_gap_hi_f32)))
     return fail(e, MAMCTS_ERR_INVALID, "rollout: HYPOTHESIS needs CrossingState and the per-leaf gap ranges");
   if (src->kind == MAMCTS_SRC_REFERENCE_CONST) {
     for (uint32_t a = 0; a < A; ++a) {
@@ -451,9 +481,10 @@ static int rollout_locked(mamcts_engine* e, int env_kind, const mamcts_params* m
                              sizeof(uint32_t) * n, src->mem, false);
   const bool philox_like = src->kind == MAMCTS_SRC_PHILOX || src->kind == MAMCTS_SRC_HYPOTHESIS;
   const int t_slo = stg.plan(philox_like ? src->stream_lo : nullptr, sizeof(uint32_t) * n, src->mem, false);
-  const int t_hlo = stg.plan(src->kind == MAMCTS_SRC_HYPOTHESIS ? src->hyp_gap_lo : nullptr,
+  const bool hyp = src->kind == MAMCTS_SRC_HYPOTHESIS;
+  const int t_hlo = stg.plan(hyp ? (f32 ? (const void*)src->hyp_gap_lo_f32 : (const void*)src->hyp_gap_lo) : nullptr,
                              sizeof(int32_t) * (A - 1) * n, src->mem, false);
-  const int t_hhi = stg.plan(src->kind == MAMCTS_SRC_HYPOTHESIS ? src->hyp_gap_hi : nullptr,
+  const int t_hhi = stg.plan(hyp ? (f32 ? (const void*)src->hyp_gap_hi_f32 : (const void*)src->hyp_gap_hi) : nullptr,
                              sizeof(int32_t) * (A - 1) * n, src->mem, false);
   const int o_ego = stg.plan(out->ego_return, sizeof(double) * n, out->mem, true);
   const int o_oth = stg.plan(out->other_return, sizeof(double) * (A - 1) * n, out->mem, true);
@@ -490,6 +521,8 @@ static int rollout_locked(mamcts_engine* e, int env_kind, const mamcts_params* m
   p.stream_lo = stg.dev<const uint32_t>(t_slo);
   p.hyp_lo = stg.dev<const int32_t>(t_hlo);
   p.hyp_hi = stg.dev<const int32_t>(t_hhi);
+  p.hyp_lo_f = stg.dev<const float>(t_hlo);
+  p.hyp_hi_f = stg.dev<const float>(t_hhi);
   p.stream_hi_base = src->stream_hi_base;
   p.stream_lo_base = src->stream_lo_base;
   {

@@ -169,7 +169,7 @@ class Engine:
     @staticmethod
     def _source(kind, A, replay_actions=None, replay_steps=None, const_actions=None, seed=0,
                 stream_hi=None, stream_hi_base=0, stream_lo_base=0, stream_lo=None, mem=MEM_HOST,
-                hyp_gap_lo=None, hyp_gap_hi=None):
+                hyp_gap_lo=None, hyp_gap_hi=None, f32=False):
         src = ActionSource()
         src.kind = kind
         src.mem = mem
@@ -206,15 +206,19 @@ class Engine:
                     src.stream_lo = sl.ctypes.data
                 else:
                     src.stream_lo = int(stream_lo)
-            if kind == SRC_HYPOTHESIS:
-                # [A-1, n] desired-gap ranges of the other agents' current hypotheses
+            if kind == SRC_HYPOTHESIS and hyp_gap_lo is not None and hyp_gap_hi is not None:
+                # [A-1, n] desired-gap ranges of the other agents' current hypotheses (missing: the call fails)
                 if mem == MEM_HOST:
-                    lo = np.ascontiguousarray(hyp_gap_lo, dtype=np.int32)
-                    hi = np.ascontiguousarray(hyp_gap_hi, dtype=np.int32)
+                    lo = np.ascontiguousarray(hyp_gap_lo, dtype=np.float32 if f32 else np.int32)
+                    hi = np.ascontiguousarray(hyp_gap_hi, dtype=np.float32 if f32 else np.int32)
                     keep += [lo, hi]
-                    src.hyp_gap_lo, src.hyp_gap_hi = lo.ctypes.data, hi.ctypes.data
+                    plo, phi = lo.ctypes.data, hi.ctypes.data
                 else:
-                    src.hyp_gap_lo, src.hyp_gap_hi = int(hyp_gap_lo), int(hyp_gap_hi)
+                    plo, phi = int(hyp_gap_lo), int(hyp_gap_hi)
+                if f32:   # CrossingState<float>: float ranges
+                    src.hyp_gap_lo_f32, src.hyp_gap_hi_f32 = plo, phi
+                else:
+                    src.hyp_gap_lo, src.hyp_gap_hi = plo, phi
         return src, keep
 
     def _rollout_host(self, env, mp, envp, A, x, last, flags, depth, K, src_kw, want_parity,
@@ -321,7 +325,7 @@ class Engine:
             src.replay_actions_f32, src.replay_steps, src.replay_stride = ra.ctypes.data, rs.ctypes.data, ra.shape[1]
             keep = [ra, rs]
         else:
-            src, keep = self._source(A=A, kind=kind, **src_kw)
+            src, keep = self._source(A=A, kind=kind, f32=True, **src_kw)
         res = dict(ego_return=np.zeros(n), other_return=np.zeros((A - 1, n)), ego_cost=np.zeros(n),
                    step_length=np.zeros(n), total_steps=np.zeros(1, dtype=np.uint64))
         out = RolloutOut()

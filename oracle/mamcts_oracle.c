@@ -402,6 +402,80 @@ void orc_rollout_f32(const mamcts_crossing_params_f32* cp, const mamcts_params* 
   out->final_state = state;
 }
 
+/* environments/crossing_state_agent_policy.h:35-55, Domain = float */
+float orc_crossing_policy_action_f32(const mamcts_crossing_params_f32* cp, float agent_x, float agent_last, float ego_x,
+                                     float ego_last, float desired_gap) {
+  volatile float chain_m1 = cp->chain_length - 1.0f;      /* CROSSING_POINT() in float, crossing_state_parameters.h:28 */
+  volatile float half = chain_m1 / 2.0f;
+  const float crossing_point = half + 1.0f;
+  if (agent_x < crossing_point) {                          /* :37 */
+    volatile float t0 = ego_x + ego_last;                  /* :39, left to right in float */
+    volatile float t1 = t0 - agent_x;
+    const float gap_error = t1 - desired_gap;
+    if (desired_gap > 0) {                                 /* :41-46 */
+      /* std::max(a, b) = a < b ? b : a; std::min(a, b) = b < a ? b : a (the signs of zeros follow from this) */
+      if (gap_error < 0) return gap_error < cp->min_velocity_other ? cp->min_velocity_other : gap_error;
+      return cp->max_velocity_other < gap_error ? cp->max_velocity_other : gap_error;
+    }
+    {                                                      /* :47-50 */
+      const float lim = cp->max_velocity_other < gap_error ? cp->max_velocity_other : gap_error;
+      return lim < agent_last ? agent_last : lim;
+    }
+  }
+  return agent_last;                                       /* :51-53 */
+}
+
+void orc_rollout_f32_hypothesis(const mamcts_crossing_params_f32* cp, const mamcts_params* mp, const orc_state_f32* start,
+                                uint32_t start_depth, uint64_t seed, uint32_t stream_hi, uint32_t stream_lo,
+                                const float* gap_lo, const float* gap_hi, orc_rollout_result_f32* out) {
+  const uint32_t A = cp->num_other_agents + 1;
+  const uint32_t n_ego = (uint32_t)(cp->max_velocity_ego - cp->min_velocity_ego + 1.0f);
+  orc_state_f32 state = *start;
+  double ego = 0.0, cost0 = 0.0, len = 0.0, prob = 1.0;
+  double other[ORC_MAX_AGENTS];
+  for (uint32_t j = 0; j < ORC_MAX_AGENTS; ++j) other[j] = 0.0;
+  const double gamma = mp->discount_factor;
+  double m = gamma;
+  uint32_t it = 0, depth = start_depth;
+  const uint32_t cap = mp->rh_max_number_of_iterations;
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  while (!state.terminal && it < cap && depth < mp->max_search_depth) {
+    float act[ORC_MAX_AGENTS];
+    act[0] = (float)orc_philox_draw(seed, stream_hi, stream_lo, A, it, 0, n_ego);
+    for (uint32_t a = 1; a < A; ++a) {
+      uint32_t block, h, w[4];
+      orc_draw_position(A, it, a, &block, &h);
+      const uint32_t ctr[4] = {block, stream_lo, stream_hi, 0u};
+      orc_philox4x32_10(ctr, key, w);
+      const uint32_t word = (w[h >> 1] >> (16u * (h & 1u))) & 0xFFFFu;
+      volatile float span = gap_hi[a - 1] - gap_lo[a - 1];
+      volatile float frac = (float)word * (1.0f / 65536.0f);
+      volatile float scaled = span * frac;
+      const float gap = gap_lo[a - 1] + scaled;
+      act[a] = orc_crossing_policy_action_f32(cp, state.x[a], state.last[a], state.x[0], state.last[0], gap);
+    }
+    orc_state_f32 next;
+    double r, c0;
+    orc_crossing_f32_execute(cp, &state, act, &next, &r, &c0);
+    m = gamma * m;
+    ego += m * r;
+    for (uint32_t j = 1; j < A; ++j) other[j - 1] = m * 0.0;
+    cost0 += c0;
+    m = m * gamma;
+    len += 1.0;
+    prob *= 1.0 / (double)n_ego;
+    it += 1;
+    depth += 1;
+    state = next;
+  }
+  out->ego_return = ego * prob;
+  for (uint32_t j = 0; j < ORC_MAX_AGENTS; ++j) out->other_return[j] = other[j];
+  out->cost0 = cost0 * prob;
+  out->step_length = len;
+  out->steps = it;
+  out->final_state = state;
+}
+
 static double orc_cost_mean(const double* c, uint32_t C) {
   double acc = 0.0; /* std::accumulate(begin, end, 0.0) / size(), hypothesis_statistic.h:120,159 */
   for (uint32_t i = 0; i < C; ++i) acc += c[i];

@@ -147,6 +147,17 @@ void orc_rollout_f32(const mamcts_crossing_params_f32* cp, const mamcts_params* 
                      uint32_t start_depth, int32_t kind, const float* replay, uint32_t replay_steps,
                      const uint32_t* const_actions, uint64_t seed, uint32_t stream_hi, uint32_t stream_lo,
                      orc_rollout_result_f32* out);
+/* AgentPolicyCrossingState<float>::calculate_action (environments/crossing_state_agent_policy.h:35-55 with
+ * Domain = float): every operation a single FP32 operation in the reference's order. */
+float orc_crossing_policy_action_f32(const mamcts_crossing_params_f32* cp, float agent_x, float agent_last, float ego_x,
+                                     float ego_last, float desired_gap);
+/* orc_rollout_f32 with kind HYPOTHESIS: the ego draws uniformly (like PHILOX), other agent j draws its desired
+ * gap as gap_lo[j] + (gap_hi[j] - gap_lo[j]) * (w / 65536) from the 16-bit word w of its Philox position (the
+ * engine's stand-in for AgentPolicyCrossingState<float>::act's uniform_real_distribution, agent_policy.h:78-84;
+ * exactness for the reference's own generator is REPLAY) and acts by orc_crossing_policy_action_f32. */
+void orc_rollout_f32_hypothesis(const mamcts_crossing_params_f32* cp, const mamcts_params* mp, const orc_state_f32* start,
+                                uint32_t start_depth, uint64_t seed, uint32_t stream_hi, uint32_t stream_lo,
+                                const float* gap_lo, const float* gap_hi, orc_rollout_result_f32* out);
 
 /* ---- backup: HypothesisStatistic (mcts/hypothesis/hypothesis_statistic.h:100-134,158-161) ---- */
 /* Same arrays as mamcts_backup_hypothesis / mamcts_hyp_stats (HOST), plain sequential restatement. */

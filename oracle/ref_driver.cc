@@ -631,6 +631,83 @@ int ref_rollout_crossing_f32(const mamcts_params* mp, const mamcts_crossing_para
   return 0;
 }
 
+// AgentPolicyCrossingState<float>::calculate_action (environments/crossing_state_agent_policy.h:35-55).
+int ref_policy_calculate_action_f32(const mamcts_crossing_params_f32* cp, uint32_t n, const float* agent_x,
+                                    const float* agent_last, const float* ego_x, const float* ego_last,
+                                    const float* gap, float* out) {
+  CrossingStateParameters<float> params = default_crossing_state_parameters<float>();
+  params.MIN_VELOCITY_OTHER = cp->min_velocity_other; params.MAX_VELOCITY_OTHER = cp->max_velocity_other;
+  params.CHAIN_LENGTH = cp->chain_length;
+  AgentPolicyCrossingState<float> policy({0.0f, 1.0f}, params);
+  for (uint32_t i = 0; i < n; ++i)
+    out[i] = policy.calculate_action(AgentState<float>(agent_x[i], agent_last[i]),
+                                     AgentState<float>(ego_x[i], ego_last[i]), gap[i]);
+  return 0;
+}
+
+// RandomHeuristic::rollout<RecHypState<CrossingState<float>>, UctStatistic, HypothesisStatistic, RandomHeuristic>:
+// the float-domain hypothesis rollout (other agents act by AgentPolicyCrossingState<float>::act, agent_policy.h:
+// 78-84, with the reference's own uniform_real_distribution draws); records the joint actions for REPLAY.
+int ref_rollout_crossing_f32_hypothesis(const mamcts_params* mp, const mamcts_crossing_params_f32* cp, uint32_t n,
+                                        const float* x, const float* last, const uint32_t* depth, uint32_t n_hyp,
+                                        const float* hyp_lo, const float* hyp_hi, const uint32_t* cur_hyp,
+                                        double* ego_ret, double* cost0, double* step_len, uint32_t* steps,
+                                        float* final_x, float* final_last, uint8_t* final_flags, float* rec_actions,
+                                        uint32_t rec_stride) {
+  const MctsParameters rp = to_ref_params(*mp);
+  CrossingStateParameters<float> params = default_crossing_state_parameters<float>();
+  params.NUM_OTHER_AGENTS = cp->num_other_agents;
+  params.NUM_OTHER_ACTIONS = cp->num_other_actions;
+  params.COST_ONLY_COLLISION = cp->cost_only_collision != 0;
+  params.MIN_VELOCITY_EGO = cp->min_velocity_ego; params.MAX_VELOCITY_EGO = cp->max_velocity_ego;
+  params.MIN_VELOCITY_OTHER = cp->min_velocity_other; params.MAX_VELOCITY_OTHER = cp->max_velocity_other;
+  params.CHAIN_LENGTH = cp->chain_length; params.EGO_GOAL_POS = cp->ego_goal_pos;
+  params.REWARD_COLLISION = cp->reward_collision; params.REWARD_GOAL_REACHED = cp->reward_goal_reached;
+  params.REWARD_STEP = cp->reward_step;
+  const uint32_t A = cp->num_other_agents + 1;
+  using RS = RecHypState<CrossingState<float>>;
+  for (uint32_t i = 0; i < n; ++i) {
+    std::unordered_map<AgentIdx, HypothesisId> hyp_map;
+    for (AgentIdx j = 1; j < A; ++j) hyp_map[j] = cur_hyp[(j - 1) * n + i];
+    std::vector<AgentPolicyCrossingState<float>> policies;
+    for (uint32_t h = 0; h < n_hyp; ++h) policies.emplace_back(std::make_pair(hyp_lo[h], hyp_hi[h]), params);
+    std::vector<AgentState<float>> others;
+    for (uint32_t a = 1; a < A; ++a) others.emplace_back(x[a * n + i], last ? last[a * n + i] : 2.0f);
+    AgentState<float> ego(x[i], last ? last[i] : 2.0f);
+    auto inner = std::make_shared<CrossingState<float>>(hyp_map, params, others, ego, false, false, false, policies);
+    auto start = std::make_shared<RS>(inner, hyp_map);
+    Recorder rec;
+    g_recorder = &rec;
+    auto result = RandomHeuristic::rollout<RS, UctStatistic, HypothesisStatistic, RandomHeuristic>(start, rp, depth ? depth[i] : 0);
+    g_recorder = nullptr;
+    ego_ret[i] = std::get<0>(result);
+    const auto& costs = std::get<2>(result);
+    cost0[i] = costs.empty() ? 0.0 : costs[0];
+    step_len[i] = std::get<3>(result);
+    steps[i] = static_cast<uint32_t>(rec.steps.size());
+    std::shared_ptr<CrossingState<float>> cur = std::make_shared<CrossingState<float>>(
+        hyp_map, params, others, ego, false, false, false, std::vector<AgentPolicyCrossingState<float>>());
+    for (size_t s = 0; s < rec.steps.size(); ++s) {
+      JointAction ja(A);
+      for (uint32_t a = 0; a < A; ++a) ja[a] = static_cast<ActionIdx>(rec.steps[s].action[a]);
+      std::vector<Reward> r; EgoCosts c;
+      cur = cur->execute(ja, r, c);
+      if (s < rec_stride && rec_actions) {
+        rec_actions[(static_cast<size_t>(i) * rec_stride + s) * A + 0] = static_cast<float>(ja[0]);
+        for (uint32_t a = 1; a < A; ++a)
+          rec_actions[(static_cast<size_t>(i) * rec_stride + s) * A + a] = aconv<float>(ja[a]);
+      }
+    }
+    for (uint32_t a = 0; a < A; ++a) {
+      const AgentState<float>& st = a == 0 ? cur->get_ego_state() : cur->get_agent_states()[a - 1];
+      if (final_x) final_x[a * n + i] = st.x_pos;
+      if (final_last) final_last[a * n + i] = st.last_action;
+    }
+    if (final_flags) final_flags[i] = (cur->is_terminal() ? 1 : 0) | (cur->ego_goal_reached() ? 2 : 0) | (cur->ego_collided() ? 4 : 0);
+  }
+  return 0;
+}
+
 // CrossingState<float>::execute on n states with explicit joint actions (ego index as float, others'
 // velocities as floats, passed through aconv like the reference's own float tests do,
 // environments/tests/crossing_state_float_test.cc:155-217).

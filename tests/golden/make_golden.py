@@ -270,6 +270,42 @@ def gen_float_domain():
     dump("float_domain.json", dict(execute=ex, rollouts=ro))
 
 
+def gen_float_hypothesis():
+    """CrossingState<float> with behaviour hypotheses (AgentPolicyCrossingState<float>, crossing_state_agent_policy.h:
+    35-55,78-84): calculate_action on random inputs, and whole hypothesis rollouts of the reference (its own
+    uniform_real_distribution gap draws) recorded for REPLAY."""
+    from mamcts_b200 import default_crossing_params_f32
+    rng = np.random.default_rng(27182)
+    cp = default_crossing_params_f32(num_other_agents=2)
+    n = 400
+    ax = (rng.random(n) * 16 - 1).astype(np.float32)
+    al = (rng.random(n) * 6 - 3).astype(np.float32)
+    ex = (rng.random(n) * 16 - 1).astype(np.float32)
+    el = (rng.random(n) * 3 - 1).astype(np.float32)
+    gap = (rng.random(n) * 10 - 4).astype(np.float32)
+    gap[:40] = 0.0
+    al[40:80] = np.float32(-0.0)
+    pol = dict(agent_x=f32hex(ax), agent_last=f32hex(al), ego_x=f32hex(ex), ego_last=f32hex(el), gap=f32hex(gap),
+               action=f32hex(O.ref_policy_calculate_action_f32(cp, ax, al, ex, el, gap)))
+    ro = []
+    for seed, num_others, hyps in ((1000, 2, [(4.0, 5.0), (5.0, 6.0)]), (7, 1, [(-2.0, 1.0), (2.0, 3.0), (4.0, 5.5)]),
+                                   (42, 3, [(0.5, 2.5)])):
+        mp = default_params(random_seed=seed, rh_max_number_of_iterations=50)
+        cpx = default_crossing_params_f32(num_other_agents=num_others)
+        A, n = num_others + 1, 40
+        x = (rng.random((A, n)) * 10).astype(np.float32)
+        last = (rng.random((A, n)) * 3 - 1).astype(np.float32)
+        depth = rng.integers(0, 4, size=n).astype(np.uint32)
+        cur = rng.integers(0, len(hyps), size=(num_others, n)).astype(np.uint32)
+        r = O.ref_rollout_crossing_f32_hypothesis(mp, cpx, x, last, [h[0] for h in hyps], [h[1] for h in hyps], cur, depth,
+                                                  rec_stride=50)
+        ro.append(dict(seed=seed, num_others=num_others, hyps=hyps, x=f32hex(x), last=f32hex(last), depth=depth.tolist(),
+                       cur_hyp=cur.tolist(), ego_return=fhex(r["ego_return"]), ego_cost=fhex(r["ego_cost"]),
+                       steps=r["steps"].tolist(), final_x=f32hex(r["final_x"]), final_last_action=f32hex(r["final_last_action"]),
+                       final_flags=r["final_flags"].tolist(), rec_actions=f32hex(r["rec_actions"])))
+    dump("float_hypothesis.json", dict(policy=pol, rollouts=ro))
+
+
 def gen_search():
     cases = []
     # C1: SimpleState(4), 20 iterations (reference test/uct/uct_test.cc:22-40 parameters)
@@ -367,6 +403,7 @@ if __name__ == "__main__":
     gen_hypothesis()
     gen_hypothesis_backup()
     gen_float_domain()
+    gen_float_hypothesis()
     gen_search()
     gen_merge()
     gen_action_values()

@@ -488,6 +488,56 @@ def rollout_f32(cp, mp: Params, x, last=None, terminal=False, depth=0, kind=SRC_
                 final_flags=(1 if fs.terminal else 0) | (2 if fs.goal else 0) | (4 if fs.collided else 0))
 
 
+def crossing_policy_action_f32(cp, agent_x, agent_last, ego_x, ego_last, gap) -> float:
+    f = oracle().orc_crossing_policy_action_f32
+    f.restype = C.c_float
+    f.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+    return float(f(C.byref(cp), float(agent_x), float(agent_last), float(ego_x), float(ego_last), float(gap)))
+
+
+def rollout_f32_hypothesis(cp, mp: Params, x, last=None, depth=0, seed=0, stream_hi=0, stream_lo=0, gap_lo=None, gap_hi=None):
+    """One oracle hypothesis rollout on CrossingState<float> (Philox gap draws)."""
+    st = _state_f32(x, last, False)
+    res = OrcRolloutResultF32()
+    glo = (C.c_float * MAX_AGENTS)(*[float(v) for v in gap_lo])
+    ghi = (C.c_float * MAX_AGENTS)(*[float(v) for v in gap_hi])
+    oracle().orc_rollout_f32_hypothesis(C.byref(cp), C.byref(mp), C.byref(st), C.c_uint32(depth), C.c_uint64(seed),
+                                        C.c_uint32(stream_hi), C.c_uint32(stream_lo), glo, ghi, C.byref(res))
+    A = cp.num_other_agents + 1
+    fs = res.final_state
+    return dict(ego_return=res.ego_return, cost0=res.cost0, step_length=res.step_length, steps=res.steps,
+                final_x=np.array(fs.x[:A], dtype=np.float32), final_last=np.array(fs.last[:A], dtype=np.float32),
+                final_flags=(1 if fs.terminal else 0) | (2 if fs.goal else 0) | (4 if fs.collided else 0))
+
+
+def ref_policy_calculate_action_f32(cp, agent_x, agent_last, ego_x, ego_last, gap):
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (agent_x, agent_last, ego_x, ego_last, gap)]
+    out = np.zeros(arrs[0].shape[0], dtype=np.float32)
+    reference().ref_policy_calculate_action_f32(C.byref(cp), C.c_uint32(out.shape[0]), *[_ptr(a) for a in arrs], _ptr(out))
+    return out
+
+
+def ref_rollout_crossing_f32_hypothesis(mp: Params, cp, x, last, hyp_lo, hyp_hi, cur_hyp, depth=None, rec_stride=64):
+    """The reference's float-domain hypothesis rollout (RandomHeuristic::rollout<.., UctStatistic, HypothesisStatistic, ..>
+    over CrossingState<float>, other agents by AgentPolicyCrossingState<float>::act), recorded for REPLAY."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    A, n = x.shape
+    last_a = None if last is None else np.ascontiguousarray(last, dtype=np.float32)
+    depth_a = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+    lo, hi = np.ascontiguousarray(hyp_lo, dtype=np.float32), np.ascontiguousarray(hyp_hi, dtype=np.float32)
+    ch = np.ascontiguousarray(cur_hyp, dtype=np.uint32)
+    out = dict(ego_return=np.zeros(n), ego_cost=np.zeros(n), step_length=np.zeros(n),
+               steps=np.zeros(n, dtype=np.uint32), final_x=np.zeros((A, n), dtype=np.float32),
+               final_last_action=np.zeros((A, n), dtype=np.float32), final_flags=np.zeros(n, dtype=np.uint8),
+               rec_actions=np.zeros((n, rec_stride, A), dtype=np.float32))
+    reference().ref_rollout_crossing_f32_hypothesis(
+        C.byref(mp), C.byref(cp), C.c_uint32(n), _ptr(x), _ptr(last_a) if last_a is not None else None,
+        _ptr(depth_a) if depth_a is not None else None, C.c_uint32(lo.shape[0]), _ptr(lo), _ptr(hi), _ptr(ch),
+        _ptr(out["ego_return"]), _ptr(out["ego_cost"]), _ptr(out["step_length"]), _ptr(out["steps"]), _ptr(out["final_x"]),
+        _ptr(out["final_last_action"]), _ptr(out["final_flags"]), _ptr(out["rec_actions"]), C.c_uint32(rec_stride))
+    return out
+
+
 def ref_rollout_crossing_f32(mp: Params, cp, x, last=None, depth=None, rec_stride=64):
     """The reference's RandomHeuristic::rollout on CrossingState<float> (UCT statistics), recorded."""
     x = np.ascontiguousarray(x, dtype=np.float32)

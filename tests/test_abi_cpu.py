@@ -41,7 +41,7 @@ def test_struct_layouts_match_header_sizes(lib):
     assert C.sizeof(_abi.Params) == 6 * 8 + 8 * 4
     assert C.sizeof(_abi.CrossingParams) == 3 * 8 + 10 * 4
     assert C.sizeof(_abi.SimpleParams) == 8
-    assert C.sizeof(_abi.ActionSource) == 8 + 24 + 8 + 16 * 4 + 8 + 8 + 8 + 8 + 16
+    assert C.sizeof(_abi.ActionSource) == 8 + 24 + 8 + 16 * 4 + 8 + 8 + 8 + 8 + 16 + 16
     assert C.sizeof(_abi.RolloutOut) == 8 + 12 * 8 + 8 + 8
     assert C.sizeof(_abi.UctStats) == 16 + 5 * 8
 

@@ -59,3 +59,36 @@ def test_rollouts_match_golden():
                 assert_bit_equal(o["cost0"], cost[i], "cost")
                 assert same_bits(o["final_x"], fx[:, i]) and same_bits(o["final_last"], fl[:, i])
                 assert o["final_flags"] == case["final_flags"][i]
+
+
+def test_float_policy_matches_golden():
+    """AgentPolicyCrossingState<float>::calculate_action (crossing_state_agent_policy.h:35-55): the oracle's FP32
+    restatement against the reference's results on 400 inputs (zero gaps, signed zeros included), bit for bit."""
+    g = golden("float_hypothesis.json")["policy"]
+    cp = default_crossing_params_f32(num_other_agents=2)
+    ax, al, ex, el, gap, act = (f32(g[k]) for k in ("agent_x", "agent_last", "ego_x", "ego_last", "gap", "action"))
+    got = np.array([O.crossing_policy_action_f32(cp, ax[i], al[i], ex[i], el[i], gap[i]) for i in range(ax.shape[0])],
+                   dtype=np.float32)
+    assert same_bits(got, act)
+
+
+def test_float_hypothesis_rollouts_replay_matches_golden():
+    """The reference's float-domain hypothesis rollouts (its own uniform_real_distribution gap draws), replayed by
+    the oracle from the recorded velocities: steps, returns, costs and final states bit for bit."""
+    for case in golden("float_hypothesis.json")["rollouts"]:
+        mp = default_params(random_seed=case["seed"], rh_max_number_of_iterations=50)
+        cp = default_crossing_params_f32(num_other_agents=case["num_others"])
+        A = case["num_others"] + 1
+        x, last = f32(case["x"], (A, -1)), f32(case["last"], (A, -1))
+        n = x.shape[1]
+        rec = f32(case["rec_actions"], (n, 50, A))
+        fx, fl = f32(case["final_x"], (A, n)), f32(case["final_last_action"], (A, n))
+        ego, cost = unhex(case["ego_return"]), unhex(case["ego_cost"])
+        for i in range(n):
+            o = O.rollout_f32(cp, mp, x[:, i], last[:, i], depth=case["depth"][i], kind=SRC_REPLAY,
+                              replay=rec[i, :case["steps"][i]])
+            assert o["steps"] == case["steps"][i]
+            assert_bit_equal(o["ego_return"], ego[i], "ego return")
+            assert_bit_equal(o["cost0"], cost[i], "cost")
+            assert same_bits(o["final_x"], fx[:, i]) and same_bits(o["final_last"], fl[:, i])
+            assert o["final_flags"] == case["final_flags"][i]

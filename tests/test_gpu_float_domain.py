@@ -85,8 +85,51 @@ def test_float_leaf_parallel_and_errors(engine):
     b = engine.rollout_crossing_f32(mp, cp, x, K=32, kind=SRC_PHILOX, seed=5)
     assert_bit_equal(a["ego_return"], b["ego_return"], "determinism")
     assert a["total_steps"] == b["total_steps"] > 0
-    with pytest.raises(MamctsError, match="HYPOTHESIS"):
-        engine.rollout_crossing_f32(mp, cp, x, kind=SRC_HYPOTHESIS, hyp_gap_lo=np.zeros((2, 64), dtype=np.int32),
-                                    hyp_gap_hi=np.zeros((2, 64), dtype=np.int32))
+    with pytest.raises(MamctsError, match="HYPOTHESIS"):   # the gap ranges are required
+        engine.rollout_crossing_f32(mp, cp, x, kind=SRC_HYPOTHESIS)
     with pytest.raises(MamctsError, match="compiled for"):
         engine.rollout_crossing_f32(mp, default_crossing_params_f32(num_other_agents=5), np.zeros((6, 4), dtype=np.float32))
+
+
+def test_float_hypothesis_policy_on_device(engine):
+    """AgentPolicyCrossingState<float> on the device (MAMCTS_SRC_HYPOTHESIS of mamcts_rollout_crossing_f32): (1) the
+    reference's own float-domain hypothesis rollouts - its uniform_real_distribution gap draws recorded as
+    velocities - replay bit-exactly; (2) the device policy (Philox gap, calculate_action in FP32,
+    crossing_state_agent_policy.h:35-55,78-84) equals the oracle twin step for step on the same streams."""
+    for case in golden("float_hypothesis.json")["rollouts"]:
+        mp = default_params(random_seed=case["seed"], rh_max_number_of_iterations=50)
+        cp = default_crossing_params_f32(num_other_agents=case["num_others"])
+        A = case["num_others"] + 1
+        x, last = f32(case["x"], (A, -1)), f32(case["last"], (A, -1))
+        n = x.shape[1]
+        depth = np.array(case["depth"], dtype=np.uint32)
+        out = engine.rollout_crossing_f32(mp, cp, x, last, None, depth, K=1, parity=True, kind=SRC_REPLAY,
+                                          replay_actions=f32(case["rec_actions"], (n, 50, A)),
+                                          replay_steps=np.array(case["steps"], dtype=np.uint32))
+        assert out["steps"].tolist() == case["steps"]
+        assert same_bits(out["final_x"], f32(case["final_x"], (A, n)))
+        assert same_bits(out["final_last_action"], f32(case["final_last_action"], (A, n)))
+        assert out["final_flags"].tolist() == case["final_flags"]
+        assert_bit_equal(out["ego_return"], unhex(case["ego_return"]), "ego return")
+        assert_bit_equal(out["ego_cost"], unhex(case["ego_cost"]), "cost")
+        # the device policy with Philox gaps against the oracle twin
+        hyps = case["hyps"]
+        cur = np.array(case["cur_hyp"])
+        lo = np.array([[hyps[h][0] for h in row] for row in cur], dtype=np.float32)
+        hi = np.array([[hyps[h][1] for h in row] for row in cur], dtype=np.float32)
+        got = engine.rollout_crossing_f32(mp, cp, x, last, None, depth, K=1, parity=True, kind=SRC_HYPOTHESIS, seed=321,
+                                          stream_hi_base=5, stream_lo_base=70, hyp_gap_lo=lo, hyp_gap_hi=hi)
+        for i in range(n):
+            o = O.rollout_f32_hypothesis(cp, mp, x[:, i], last[:, i], depth=int(depth[i]), seed=321, stream_hi=5,
+                                         stream_lo=70 + i, gap_lo=lo[:, i], gap_hi=hi[:, i])
+            assert got["steps"][i] == o["steps"] and got["final_flags"][i] == o["final_flags"]
+            assert_bit_equal(got["ego_return"][i], o["ego_return"], "ego")
+            assert_bit_equal(got["ego_cost"][i], o["cost0"], "cost")
+            assert same_bits(got["final_x"][:, i], o["final_x"]) and same_bits(got["final_last_action"][:, i], o["final_last"])
+    # K rollouts per leaf, 7 other agents
+    cp7 = default_crossing_params_f32(num_other_agents=7)
+    x = np.full((8, 256), 5.0, dtype=np.float32)
+    lo, hi = np.full((7, 256), 2.0, dtype=np.float32), np.full((7, 256), 4.5, dtype=np.float32)
+    a = engine.rollout_crossing_f32(default_params(rh_max_number_of_iterations=50), cp7, x, K=32, kind=SRC_HYPOTHESIS, seed=1,
+                                    hyp_gap_lo=lo, hyp_gap_hi=hi)
+    assert a["total_steps"] > 256 * 32
