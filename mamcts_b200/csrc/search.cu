@@ -20,6 +20,7 @@
 
 #include "engine.h"
 #include "root_merge.h"
+#include "search_async.cuh"
 #include "search_compact.cuh"
 #include "search_compact_multi.cuh"
 #include "search_host.h"
@@ -140,6 +141,66 @@ struct SearchC final : public mamcts_search {
     return MAMCTS_OK;
   }
 
+  // Asynchronous tree-pool scheduling (search_async.cuh): the same trees, the same results, trees not bound to lanes.
+  void* d_async_path = nullptr;
+  double* d_async_path_r = nullptr;
+  void free_extra() override { cudaFree(d_async_path); cudaFree(d_async_path_r); }
+  static constexpr bool kAsyncBuilt = Env::A == 2 && Env::kOtherRewardZero && Env::kOutcomeRewards &&
+                                      sizeof(CNT) == 2 && sizeof(CIDX) == 2;
+  // slots per lane of the pool (0 = lane-per-tree kernel)
+  int async_spl() const {
+    if (!kAsyncBuilt) return 0;
+    if (!(p.gamma >= 0.0) || cfg.rollouts_per_leaf != 1) return 0;
+    unsigned long long bits;
+    std::memcpy(&bits, &p.env.r_tab[0], sizeof(bits));
+    if (bits != 0ull) return 0;   // a per-step reward: the rollout accumulates in FP64 (lane-per-tree kernel)
+    // opt-in (profiling / comparison): the lane-per-tree kernel is faster at every size measured
+    // (profiles/r02_search_async_pool.txt), MAMCTS_SEARCH_ASYNC = 2 or 4 tree slots per lane
+    int spl = 0;
+    if (const char* v = std::getenv("MAMCTS_SEARCH_ASYNC")) spl = std::atoi(v);
+    return (spl == 2 || spl == 4) ? spl : 0;
+  }
+  template <int KIND, int SPL>
+  int launch_async(const SearchParams& q, const CompactParams& c) {
+    if constexpr (kAsyncBuilt) {
+      using Pool = AsyncPool<32 * SPL, MAMCTS_ASYNC_SHARED_LEVELS, typename AsyncPathRec<CNT>::HeadWord,
+                             typename AsyncPathRec<CNT>::CountPair>;
+      const uint32_t T = cfg.num_trees;
+      if (!d_async_path) {
+        MAMCTS_CUDA(e, cudaMalloc(&d_async_path, sizeof(AsyncPathRec<CNT>) * (size_t)T * kPathMaxCompact));
+        MAMCTS_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&d_async_path_r), sizeof(double) * (size_t)T * kPathMaxCompact));
+      }
+      AsyncParams ap;
+      ap.path = d_async_path; ap.path_r = d_async_path_r;
+      ap.slots_per_warp = 32 * SPL;
+      if (const char* v = std::getenv("MAMCTS_SEARCH_ASYNC_SPW")) {
+        const int w = std::atoi(v);
+        if (w >= 1 && w <= 32 * SPL) ap.slots_per_warp = (uint32_t)w;
+      }
+      const size_t smem = sizeof(Pool) * kAsyncWarps;
+      auto kern = search_async_kernel<Env, NE, NA, NCHILD, CIDX, CNT, KIND, SPL>;
+      MAMCTS_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const uint32_t trees_per_block = ap.slots_per_warp * kAsyncWarps;
+      const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
+      if (std::getenv("MAMCTS_SEARCH_DEBUG")) {
+        int nb = 0;
+        cudaFuncAttributes fa;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAsyncThreads, smem);
+        cudaFuncGetAttributes(&fa, kern);
+        std::fprintf(stderr, "search_async_kernel<SPL=%d>: %d blocks/SM of %d threads, %d regs, %zu B dynamic smem, %zu B local, grid %d, trees/warp %u\n",
+                     SPL, nb, kAsyncThreads, fa.numRegs, smem, fa.localSizeBytes, grid, ap.slots_per_warp);
+      }
+      kern<<<grid, kAsyncThreads, smem, e->stream>>>(q, c, ap);
+      e->launches++;
+      MAMCTS_CUDA(e, cudaGetLastError());
+    }
+    return MAMCTS_OK;
+  }
+  template <int KIND>
+  int launch_async_spl(int spl, const SearchParams& q, const CompactParams& c) {
+    return spl >= 4 ? launch_async<KIND, 4>(q, c) : launch_async<KIND, 2>(q, c);
+  }
+
   int launch_run(uint32_t iterations) override {
     SearchParams q = p;
     q.iterations = iterations;
@@ -147,6 +208,10 @@ struct SearchC final : public mamcts_search {
     c.inner = d_inner; c.leaves = d_leaves; c.tree_inner = d_tree_inner; c.tree_leaves = d_tree_leaves;
     c.max_inner = max_inner; c.root_x = d_root_x;
     const uint32_t T = cfg.num_trees;
+    if (const int spl = async_spl()) {
+      return cfg.action_source == MAMCTS_SRC_PHILOX ? launch_async_spl<MAMCTS_SRC_PHILOX>(spl, q, c)
+                                                    : launch_async_spl<MAMCTS_SRC_REFERENCE_CONST>(spl, q, c);
+    }
     const uint32_t trees_per_block = (uint32_t)(block_threads / 32) * q.lanes_per_warp;
     const int grid = (int)((T + trees_per_block - 1) / trees_per_block);
     if (const char* v = std::getenv("MAMCTS_SEARCH_CARVEOUT")) {   // profiling knob: shared-memory carve-out in percent
@@ -161,6 +226,21 @@ struct SearchC final : public mamcts_search {
       cudaFuncGetAttributes(&fa, kern);
       std::fprintf(stderr, "search_compact_kernel: %d blocks/SM of %d threads, %d regs, %zu B smem, %zu B local, grid %d, lanes/warp %u\n",
                    nb, block_threads, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, grid, q.lanes_per_warp);
+    }
+    // a reward-free other agent with a discount >= 0: its values are +0.0 for the whole search (search_compact.cuh)
+    const bool ovz = Env::kOtherRewardZero && p.gamma >= 0.0;
+    if constexpr (Env::kOtherRewardZero) {
+      if (ovz) {
+        if (cfg.action_source == MAMCTS_SRC_PHILOX && cfg.rollouts_per_leaf > 1)
+          search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX, true, true><<<grid, block_threads, 0, e->stream>>>(q, c);
+        else if (cfg.action_source == MAMCTS_SRC_PHILOX)
+          search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX, false, true><<<grid, block_threads, 0, e->stream>>>(q, c);
+        else
+          search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_REFERENCE_CONST, false, true><<<grid, block_threads, 0, e->stream>>>(q, c);
+        e->launches++;
+        MAMCTS_CUDA(e, cudaGetLastError());
+        return MAMCTS_OK;
+      }
     }
     if (cfg.action_source == MAMCTS_SRC_PHILOX && cfg.rollouts_per_leaf > 1)
       search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX, true><<<grid, block_threads, 0, e->stream>>>(q, c);

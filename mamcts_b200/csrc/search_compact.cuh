@@ -123,7 +123,7 @@ __device__ __forceinline__ CIDX inner_entry(uint32_t inner) { return (CIDX)((inn
 
 // counters[6] = trees that ran out of inner records, counters[7] = trees with a path deeper than
 // kPathMaxCompact; either makes mamcts_search_run's caller see an error at the next read-back.
-template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT, int KIND, bool MULTI = false>
+template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT, int KIND, bool MULTI = false, bool OVZ = false>
 __global__ void __launch_bounds__(kSearchThreads, MAMCTS_COMPACT_MIN_BLOCKS)
 search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_constant__ CompactParams c) {
   using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
@@ -141,16 +141,14 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   uint32_t num_nodes = p.tree_nodes[tree];   // nodes created (root included): the creation index
   uint32_t num_inner = c.tree_inner[tree];
   uint32_t num_leaves = c.tree_leaves[tree];
-  unsigned long long rollout_steps = 0, expand_steps = 0, backup_levels = 0, exact_evals = 0;
-  const uint32_t nodes_before = num_nodes;
+  // Launch totals per lane. With 16-bit counts a launch has fewer than 65 535 iterations of at most 64 levels
+  // and min(rollout cap, 2^24) steps... the sums of one lane fit 32 bits whenever iterations * cap does; the
+  // expansions of a launch are the nodes it created (num_nodes - p.tree_nodes[tree], read again at the end).
+  using Acc = typename std::conditional<sizeof(CNT) == 2, uint32_t, unsigned long long>::type;
+  Acc rollout_steps = 0, backup_levels = 0, exact_evals = 0;
   uint8_t const_act[A];
 #pragma unroll
   for (int a = 0; a < A; ++a) const_act[a] = tab.order[a == 0 ? 0 : 1][0];  // F1: first draw
-  typename Env::State root;
-#pragma unroll
-  for (int i = 0; i < A; ++i) { root.x[i] = (i < Env::kStateInts) ? __ldg(c.root_x + i) : 0; root.last[i] = 0; }
-  root.flags = 0;
-  root.flags = (uint32_t)Env::terminal(p.env, root);
 
   // The path of the current iteration (collect(), node_statistic.h:115-121) and everything the backup
   // of a level needs: the head of the counters as loaded, the counts and values of the chosen actions
@@ -185,13 +183,22 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   // hence every G = 0.0 + gamma * (+0.0), Q and V of theirs is +0.0 for the whole search - their values
   // are neither loaded nor recomputed nor rewritten: a record is created with them zero-filled, which
   // is what the reference's statistic holds, and their selection is integer-only (select_action).
-  const bool other_values_zero = Env::kOtherRewardZero && p.gamma >= 0.0;
+  // A template parameter (the launch picks OVZ = Env::kOtherRewardZero && gamma >= 0): the other agent's V, G
+  // and seven action values drop out of the register allocation, not just out of the executed path.
+  static_assert(!OVZ || Env::kOtherRewardZero, "OVZ needs a reward-free other agent");
+  constexpr bool other_values_zero = OVZ;
 
 #pragma unroll 1
   for (uint32_t iter = 0; iter < p.iterations; ++iter) {   // a failed lane idles through the barriers
     uint32_t node = 0;
     uint32_t depth = 0;
-    typename Env::State st = root;
+    // the decision state, read again every iteration (two L1 hits next to the root record's fetch) rather
+    // than held in registers for the whole launch
+    typename Env::State st;
+#pragma unroll
+    for (int i = 0; i < A; ++i) { st.x[i] = (i < Env::kStateInts) ? __ldg(c.root_x + i) : 0; st.last[i] = 0; }
+    st.flags = 0;
+    st.flags = (uint32_t)Env::terminal(p.env, st);
     double G[A];
     bool do_rollout = false;
     unsigned long long reward_levels = 0;   // bit d: the edge leaving level d carries a reward != +0.0
@@ -290,7 +297,6 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
         // lanes of the warp have reconverged (inside the loop every depth would run its own copy).
         new_leaf = num_leaves++;
         creation = num_nodes++;
-        expand_steps += 1;
         nd->child[slot] = leaf_entry<CIDX>(new_leaf);
         do_rollout = true;
         break;
@@ -346,6 +352,10 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       const double ego_h = leaf_heuristic<Env, KIND, MULTI>(p, st, depth, p.first_tree_id + tree, creation, const_act,
                                                      other, steps);
       rollout_steps += steps;
+      if (sizeof(Acc) == 4 && rollout_steps >= 0x80000000u) {   // never with realistic rollout caps; keeps the sum exact
+        atomicAdd(p.counters + 1, (unsigned long long)rollout_steps);
+        rollout_steps = 0;
+      }
       // update_from_heuristic (uct_statistic.h:100-110): value_ = latest_return_ = h, visits 0 + 1
       leaves[new_leaf].h[0] = ego_h;
       leaves[new_leaf].h[1] = other;
@@ -416,16 +426,17 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
     }
     done += 1;
   }
+  const uint32_t nodes_before = p.tree_nodes[tree];
   p.tree_nodes[tree] = num_nodes;
   c.tree_inner[tree] = num_inner;
   c.tree_leaves[tree] = num_leaves;
   p.tree_iters[tree] += done;
   atomicAdd(p.counters + 0, (unsigned long long)done);
-  atomicAdd(p.counters + 1, rollout_steps);
-  atomicAdd(p.counters + 2, expand_steps);
+  atomicAdd(p.counters + 1, (unsigned long long)rollout_steps);
+  atomicAdd(p.counters + 2, (unsigned long long)(num_nodes - nodes_before));   // one execute() per expansion
   atomicAdd(p.counters + 3, (unsigned long long)(num_nodes - nodes_before));
-  atomicAdd(p.counters + 4, backup_levels);
-  atomicAdd(p.counters + 5, exact_evals);
+  atomicAdd(p.counters + 4, (unsigned long long)backup_levels);
+  atomicAdd(p.counters + 5, (unsigned long long)exact_evals);
 }
 
 template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT>

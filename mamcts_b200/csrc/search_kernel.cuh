@@ -166,10 +166,10 @@ __device__ __noinline__ uint32_t exact_ucb_argmax(StatRegs<NACT> r, uint32_t mas
 // on the register image of a statistic; no memory is written. `widened` = the action was newly
 // expanded (ucb_statistics_[a] = UcbPair(), the caller records it in its own record layout).
 // Also returns (in `back`) the values the backup of this level will need for the chosen action.
-template <int NACT>
+template <int NACT, class CTR = unsigned long long>
 __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const SearchParams& p,
                                                   const SearchTables& tab, int cls,
-                                                  uint32_t nact, unsigned long long& exact_evals,
+                                                  uint32_t nact, CTR& exact_evals,
                                                   BackRegs& back, bool& widened,
                                                   bool values_known_equal = false) {
   const uint32_t N = r.N;

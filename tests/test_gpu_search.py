@@ -531,6 +531,44 @@ def test_trees_per_warp_do_not_change_results(engine, lpw, layout, monkeypatch):
     s.close()
 
 
+@pytest.mark.parametrize("spl,spw", [(2, 0), (2, 40), (4, 0)])
+@pytest.mark.parametrize("source", ["philox", "reference_const"])
+def test_async_tree_pool_scheduler_builds_the_same_trees(engine, spl, spw, source, monkeypatch):
+    """search_async.cuh (opt-in, MAMCTS_SEARCH_ASYNC = tree slots per lane): trees are not bound to lanes, a warp
+    owns a pool of 32 * spl trees and runs one kind of work item (one descent level / one Philox block of the
+    rollout / one backup) per pass for up to 32 of them. Per tree the order of operations is unchanged, so
+    every tree must equal the oracle's (and the lane-per-tree kernel's) bit for bit - also across several
+    launches and with a partly filled last pool."""
+    monkeypatch.setenv("MAMCTS_SEARCH_ASYNC", str(spl))
+    if spw:
+        monkeypatch.setenv("MAMCTS_SEARCH_ASYNC_SPW", str(spw))
+    iters, T = 600, 333
+    src = SRC_PHILOX if source == "philox" else SRC_REFERENCE_CONST
+    mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
+                        rh_max_number_of_iterations=50)
+    cp = default_crossing_params(num_other_agents=1)
+    s = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=src, philox_seed=31, layout=LAYOUT_COMPACT)
+    s.run(250); s.run(1); s.run(iters - 251)
+    env = O.make_env(cp=cp)
+    for tree in (0, 1, 31, 32, 127, 128, 300, T - 1):
+        t = O.OracleTree(env, mp, [5, 5], action_source=src, seed=31, tree_id=tree)
+        t.run(iters)
+        assert np.array_equal(s.dump_tree(tree, t.num_nodes), t.dump(7)), f"spl {spl}: tree {tree} differs"
+        t.close()
+    c = s.counters()
+    assert c["iterations"] == T * iters
+    m = s.merge_roots()
+    assert int(m["n"].sum()) == T * iters
+    s.close()
+    # the counters of the two schedulers agree (same trees, same rollouts)
+    monkeypatch.delenv("MAMCTS_SEARCH_ASYNC")
+    s2 = Search(engine, ENV_CROSSING_I32, mp, T, cp=cp, action_source=src, philox_seed=31, layout=LAYOUT_COMPACT)
+    s2.run(iters)
+    c2 = s2.counters()
+    assert c2 == c, (c, c2)
+    s2.close()
+
+
 def test_full_wave_sampled_trees_equal_oracle(engine):
     """As many trees as the bench runs per wave class (automatic packing: 32 trees per warp): sampled
     trees against the oracle, and the sum of the root visit counts against iterations x trees."""
