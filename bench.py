@@ -449,7 +449,7 @@ def measure_c5_strong(engine, stream, world, rank, dist, steps=5, warmup=2):
     }
 
 
-def measure_c4_hypothesis(engine, stream, trees=4096, iterations=10000, steps=3):
+def measure_c4_hypothesis(engine, stream, trees=8192, iterations=10000, steps=3):
     """BASELINE.json configs[3] (C4): hypothesis-MCTS on CrossingState<int> - 2 other agents whose behaviour
     hypotheses are the three desired-gap ranges of the reference's own closed-loop test
     (environments/tests/crossing_state_int_test.cc:190-192), a hypothesis per agent and iteration drawn from uniform

@@ -39,6 +39,9 @@
 
 namespace mamcts {
 
+#ifndef MAMCTS_HYP_RECONVERGE
+#define MAMCTS_HYP_RECONVERGE 1   // 4 096 trees: 336 -> 319 ms; 12 288 trees: 908 -> 763 ms (profiles/r02_hyp_search.txt)
+#endif
 constexpr int kHMax = MAMCTS_MAX_HYPOTHESES;
 constexpr int kHypMA = MAMCTS_HYP_MAX_OTHER_ACTIONS;
 constexpr int kHypPathMax = 96;
@@ -69,7 +72,7 @@ struct alignas(16) HypNode {
   double r_in;                       // ego reward collected on the incoming edge
   double c_in;                       // mean of the ego cost vector collected on the incoming edge (:120)
   StatRec<NE> ego;
-  uint32_t pol_pos[kHMax];           // position of the state's policy generator of hypothesis h
+  alignas(16) uint32_t pol_pos[kHMax]; // position of the state's policy generator of hypothesis h
   HypOther oth[J];
 };
 
@@ -91,6 +94,15 @@ struct HypParams {
   double hyp_two_c, hyp_lb, hyp_ub;
   HypTables tab;
 };
+
+// A visit reads and writes fields all over a node's ~1.1-KB record, each a dependent global access; requesting every
+// line of the record at once when the node index becomes known turns that chain of HBM round trips into one round
+// trip followed by L1 hits (profiles/r02_hyp_search.txt: 84 -> ... us per iteration at 4 096 trees).
+template <class Node>
+__device__ __forceinline__ void hyp_prefetch_node(const Node* nd) {
+#pragma unroll
+  for (size_t off = 0; off < sizeof(Node); off += 128) prefetch_l1(reinterpret_cast<const char*>(nd) + off);
+}
 
 __device__ __forceinline__ uint32_t hyp_hash(uint32_t parent, const uint8_t* ja, int n) {
   uint32_t h = parent * 0x9E3779B1u;
@@ -137,9 +149,11 @@ __global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid
   __shared__ SearchTables tab;
   stage_tables(tab, p.tab);
   const uint32_t lane = threadIdx.x & 31u;
-  if (lane >= p.lanes_per_warp) return;
   const uint32_t tree = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * p.lanes_per_warp + lane;
-  if (tree >= p.T) return;
+  // the lanes that own a tree; with MAMCTS_HYP_RECONVERGE they meet again once per iteration
+  const unsigned live = __ballot_sync(0xFFFFFFFFu, lane < p.lanes_per_warp && tree < p.T);
+  (void)live;
+  if (lane >= p.lanes_per_warp || tree >= p.T) return;
   Node* nodes = static_cast<Node*>(hp.nodes) + (size_t)tree * p.max_nodes;
   uint32_t* hash = hp.hash + (size_t)tree * (p.hash_mask + 1);
   uint32_t num_nodes = p.tree_nodes[tree];
@@ -153,13 +167,18 @@ __global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid
   const uint32_t seq_off = hp.decorrelate ? (gid * 7919u) % hp.seq_len : 0u;
   const uint8_t ego_const = tab.order[0][0];   // a fresh UctStatistic's first draw
   bool failed = false;
+  uint32_t done = 0;
 
   uint32_t path_node[kHypPathMax];
   uint8_t path_ja[kHypPathMax][A];
   BackRegs path_back[kHypPathMax];
 
 #pragma unroll 1
-  for (uint32_t iter = 0; iter < p.iterations && !failed; ++iter) {
+  for (uint32_t iter = 0; iter < p.iterations; ++iter) {   // a failed lane idles through the barriers
+#if MAMCTS_HYP_RECONVERGE
+    __syncwarp(live);
+#endif
+    if (failed) continue;
     // the hypotheses of this iteration: HypothesisBeliefTracker::sample_current_hypothesis (mcts.h:158)
     uint8_t hyp[J];
     {
@@ -172,6 +191,7 @@ __global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid
     typename Env::State st;
     uint32_t leaf_pos[kHMax];
     // ---- select & expand: mcts.h:300-305, stage_node.h:167-232 ------------------------------------------
+    hyp_prefetch_node(nodes);   // the root
 #pragma unroll 1
     while (true) {
       Node* nd = nodes + node;
@@ -188,42 +208,69 @@ __global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid
         ja[0] = (uint8_t)choose_action<NE>(&nd->ego, ego, p, tab, 0, p.n_ego, exact_evals, back);   // :190
         path_back[depth] = back;
       }
-#pragma unroll 1
+      // what the other agents' choices read, requested together (one round trip for the level, see the backup):
+      // the generator positions of the node's policy objects (one per hypothesis; two agents under the same
+      // hypothesis draw from the same object one after the other, so they are carried in registers through the
+      // agent loop and written back once) and, per agent, the counters of its hypothesis
+      uint32_t pp[kHMax];
+      {
+        static_assert(kHMax == 4 && offsetof(Node, pol_pos) % 16 == 0, "the positions are one 16-byte load");
+        const uint4 w = *reinterpret_cast<const uint4*>(&nd->pol_pos[0]);
+        pp[0] = w.x; pp[1] = w.y; pp[2] = w.z; pp[3] = w.w;
+      }
+      uint32_t nexp0[J], vis0[J], pres0[J], spos0[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const HypOther& o = nd->oth[j];
+        const uint32_t h = hyp[j];
+        nexp0[j] = o.nexp_h[h]; vis0[j] = o.visits_h[h]; pres0[j] = o.present[h]; spos0[j] = o.stat_pos;
+      }
+      bool pp_moved = false;
+#pragma unroll
       for (int j = 0; j < J; ++j) {                                             // :191-194, agent order
         HypOther& o = nd->oth[j];
         const uint32_t h = hyp[j];                                              // hypothesis_statistic.h:64-65
         o.seen_h[h] = 1;                                                        // init_hypothesis_variables
-        const uint32_t nexp = o.nexp_h[h];
-        uint32_t a;
-        if (nexp < hp.n_oth_actions && o.visits_h[h] >= hp.tab.pw_min_visits[nexp]) {   // :270-276
+        const uint32_t nexp = nexp0[j];
+        uint32_t a = 0;
+        if (failed) {
+        } else if (nexp < hp.n_oth_actions && vis0[j] >= hp.tab.pw_min_visits[nexp]) {   // :270-276
           // sample from the hypothesis: the policy object of the NODE's state draws a gap (:73-78)
-          const uint32_t pos = nd->pol_pos[h] + pol_off;
-          if (pos >= hp.pol_len) { failed = true; atomicAdd(p.counters + 6, 1ull); break; }
-          const uint32_t e = __ldg(hp.gap_tab + (size_t)h * hp.pol_len + pos);
-          nd->pol_pos[h] += e >> 8;
-          const int32_t gap = hp.gap_lo[h] + (int32_t)(e & 0xFFu);
-          const int32_t v = crossing_policy_action(p.env, st.x[j + 1], st.last[j + 1], st.x[0], st.last[0], gap);
-          a = (uint32_t)(v - hp.min_v_other);
-          if (!((o.present[h] >> a) & 1u)) {                                    // ucb_statistics_[h][a] created
-            o.present[h] = (uint8_t)(o.present[h] | (1u << a));
-            o.order[h][nexp] = (uint8_t)a;
-            o.nexp_h[h] = (uint8_t)(nexp + 1u);
-            o.cost[h][a] = 0.0;
-            o.count[h][a] = 0;
+          const uint32_t pph = h == 0 ? pp[0] : h == 1 ? pp[1] : h == 2 ? pp[2] : pp[3];
+          const uint32_t pos = pph + pol_off;
+          if (pos >= hp.pol_len) { failed = true; atomicAdd(p.counters + 6, 1ull); }
+          else {
+            const uint32_t e = __ldg(hp.gap_tab + (size_t)h * hp.pol_len + pos);
+            const uint32_t adv = e >> 8;
+            pp[0] += h == 0 ? adv : 0u; pp[1] += h == 1 ? adv : 0u; pp[2] += h == 2 ? adv : 0u; pp[3] += h == 3 ? adv : 0u;
+            pp_moved = true;
+            const int32_t gap = hp.gap_lo[h] + (int32_t)(e & 0xFFu);
+            const int32_t v = crossing_policy_action(p.env, st.x[j + 1], st.last[j + 1], st.x[0], st.last[0], gap);
+            a = (uint32_t)(v - hp.min_v_other);
+            if (!((pres0[j] >> a) & 1u)) {                                      // ucb_statistics_[h][a] created
+              o.present[h] = (uint8_t)(pres0[j] | (1u << a));
+              o.order[h][nexp] = (uint8_t)a;
+              o.nexp_h[h] = (uint8_t)(nexp + 1u);
+              o.cost[h][a] = 0.0;
+              o.count[h][a] = 0;
+            }
           }
         } else if (hp.cost_based) {
           a = hyp_worst_case(o, h, p, hp);                                      // :85-87
         } else {
           // sample_from_hypothesis_expanded_actions (:204-212): the statistic's own generator picks an index
           // into the container's iteration order (last inserted first)
-          const uint32_t pos = o.stat_pos + sel_off;
-          if (pos >= hp.sel_len) { failed = true; atomicAdd(p.counters + 6, 1ull); break; }
-          const uint32_t e = __ldg(hp.sel_tab + (size_t)(nexp - 1u) * hp.sel_len + pos);
-          o.stat_pos += e >> 8;
-          a = o.order[h][nexp - 1u - (e & 0xFFu)];
+          const uint32_t pos = spos0[j] + sel_off;
+          if (pos >= hp.sel_len) { failed = true; atomicAdd(p.counters + 6, 1ull); }
+          else {
+            const uint32_t e = __ldg(hp.sel_tab + (size_t)(nexp - 1u) * hp.sel_len + pos);
+            o.stat_pos = spos0[j] + (e >> 8);
+            a = o.order[h][nexp - 1u - (e & 0xFFu)];
+          }
         }
         ja[j + 1] = (uint8_t)a;
       }
+      if (pp_moved) *reinterpret_cast<uint4*>(&nd->pol_pos[0]) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
       if (failed) break;
       path_node[depth] = node;
 #pragma unroll
@@ -235,6 +282,7 @@ __global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid
         const uint32_t c = hash[slot];
         if (c == 0) break;
         const Node* cn = nodes + c;
+        hyp_prefetch_node(cn);   // nearly always the child the descent goes on with
         bool same = cn->parent == node;
 #pragma unroll
         for (int i = 0; i < A; ++i) same &= cn->ja[i] == ja[i];
@@ -267,14 +315,17 @@ __global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid
       // collected_cost_worst_case: std::accumulate over the ego cost vector {c0, 0} / its size (:120)
       cn->c_in = __ddiv_rn(__dadd_rn(__dadd_rn(0.0, c0), 0.0), 2.0);
 #pragma unroll
-      for (int h = 0; h < kHMax; ++h) { cn->pol_pos[h] = nd->pol_pos[h]; leaf_pos[h] = nd->pol_pos[h]; }
+      for (int h = 0; h < kHMax; ++h) { cn->pol_pos[h] = pp[h]; leaf_pos[h] = pp[h]; }
       hash[slot] = child;
       node = child;
       depth += 1;
       do_rollout = true;
       break;
     }
-    if (failed) break;
+#if MAMCTS_HYP_RECONVERGE
+    __syncwarp(live);   // the descent leaves its loop at different depths
+#endif
+    if (failed) continue;
     // ---- heuristic: mcts.h:309-312 -> RandomHeuristic::rollout<S, UctStatistic, HypothesisStatistic, H> --------
     Node* leaf = nodes + node;
     double G_ego, L[J];
@@ -314,7 +365,7 @@ __global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid
         it += 1;
         fin = Env::terminal(p.env, st) | (it >= limit);
       }
-      if (failed) { atomicAdd(p.counters + 6, 1ull); break; }
+      if (failed) { atomicAdd(p.counters + 6, 1ull); continue; }
       rollout_steps += it;
       const double prob = __ldg(p.disc + p.disc_len + it);
       const double ego_h = __dmul_rn(ego, prob);                                         // :95
@@ -339,37 +390,50 @@ __global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid
     // ---- back-propagation: mcts.h:314-329, stage_node.h:259-271 -------------------------------------------
     backup_levels += depth;
     uint32_t level = depth, child = node;
+    // the path's records were read a few microseconds ago; ask for them again in one batch in case the L1 let go
+    for (uint32_t l = 0; l < depth; ++l) hyp_prefetch_node(nodes + path_node[l]);
 #pragma unroll 1
     while (level > 0) {
       level -= 1;
       Node* pn = nodes + path_node[level];
       const Node* cn = nodes + child;
+      // every value the level reads, requested before anything is computed or stored: the loads are independent
+      // of each other, so the level costs one memory round trip instead of one per field (stores to the same
+      // record with run-time indices in between would otherwise keep the compiler from hoisting them)
       const double r0 = cn->r_in, cw = cn->c_in;
+      uint32_t cnt0[J], nh0[J], N0[J], nt0[J];
+      double ac0[J], cv0[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const HypOther& o = pn->oth[j];
+        const uint32_t h = hyp[j], a = path_ja[level][j + 1];
+        cnt0[j] = o.count[h][a]; ac0[j] = o.cost[h][a]; nh0[j] = o.visits_h[h]; cv0[j] = o.cost_value;
+        N0[j] = o.N; nt0[j] = o.nexp_total;
+      }
       G_ego = back_apply<NE>(&pn->ego, path_ja[level][0], path_back[level], r0, p.gamma, G_ego);
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < J; ++j) {   // HypothesisStatistic::update_statistic, :112-134
         HypOther& o = pn->oth[j];
         const uint32_t h = hyp[j], a = path_ja[level][j + 1];
         const double Lc = L[j];
         const double Ln = hp.chance ? (cw < Lc ? Lc : cw) : __dadd_rn(cw, __dmul_rn(p.gamma, Lc));
         o.latest = Ln;
-        const uint32_t cnt = o.count[h][a] + 1;
+        const uint32_t cnt = cnt0[j] + 1;
         o.count[h][a] = cnt;
-        const double ac = o.cost[h][a];
-        o.cost[h][a] = __dadd_rn(ac, __ddiv_rn(__dsub_rn(Ln, ac), (double)cnt));
-        const uint32_t nh = o.visits_h[h] + 1;
+        o.cost[h][a] = __dadd_rn(ac0[j], __ddiv_rn(__dsub_rn(Ln, ac0[j]), (double)cnt));
+        const uint32_t nh = nh0[j] + 1;
         o.visits_h[h] = nh;
-        o.cost_value = __dadd_rn(o.cost_value, __ddiv_rn(__dsub_rn(Ln, o.cost_value), (double)nh));
-        o.N += 1;
-        o.nexp_total += 1;
+        o.cost_value = __dadd_rn(cv0[j], __ddiv_rn(__dsub_rn(Ln, cv0[j]), (double)nh));
+        o.N = N0[j] + 1;
+        o.nexp_total = nt0[j] + 1;
         L[j] = Ln;
       }
       child = path_node[level];
     }
-    p.tree_iters[tree] = iter0 + iter + 1;
+    done += 1;
   }
+  p.tree_iters[tree] = iter0 + done;
   p.tree_nodes[tree] = num_nodes;
-  const uint32_t done = p.tree_iters[tree] - iter0;
   atomicAdd(p.counters + 0, (unsigned long long)done);
   atomicAdd(p.counters + 1, rollout_steps);
   atomicAdd(p.counters + 2, expand_steps);
