@@ -245,7 +245,9 @@ def test_reference_const_search_reproduces_reference_tree(engine, layout):
 
 @pytest.mark.parametrize("num_others,layout", [(1, LAYOUT_CLASSIC), (1, LAYOUT_COMPACT), (2, LAYOUT_AUTO),
                                                (3, LAYOUT_AUTO), (7, LAYOUT_AUTO), (2, LAYOUT_CLASSIC),
-                                               (3, LAYOUT_COMPACT), (7, LAYOUT_CLASSIC), (7, LAYOUT_COMPACT)])
+                                               (3, LAYOUT_COMPACT), (7, LAYOUT_CLASSIC), (7, LAYOUT_COMPACT),
+                                               (4, LAYOUT_COMPACT), (4, LAYOUT_CLASSIC), (5, LAYOUT_AUTO),
+                                               (5, LAYOUT_CLASSIC), (6, LAYOUT_COMPACT), (6, LAYOUT_CLASSIC)])
 def test_philox_search_equals_oracle_tree(engine, num_others, layout):
     iters = 600
     mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
