@@ -58,8 +58,8 @@ def _config(trees_per_gpu, n_gpus, action_source, layout="compact (16-B leaf + 2
 
 
 def _ncu_entry(**match):
-    """The committed ncu capture (profiles/r01_traffic.json) of exactly this configuration, else None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """The committed ncu capture (profiles/r02_traffic.json) of exactly this configuration, else None."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
