@@ -476,7 +476,7 @@ def test_search_reset_and_limits(engine, layout):
     assert s.root_stats(0, 0)["visits"] == 50
     s.close()
     with pytest.raises(MamctsError, match="compiled for"):
-        Search(engine, ENV_CROSSING_I32, mp, 1, cp=default_crossing_params(num_other_agents=5))
+        Search(engine, ENV_CROSSING_I32, mp, 1, cp=default_crossing_params(num_other_agents=9))
     with pytest.raises(MamctsError, match="compiled for"):
         Search(engine, ENV_CROSSING_I32, mp, 1, cp=default_crossing_params(num_other_agents=1, num_other_actions=9))
 
