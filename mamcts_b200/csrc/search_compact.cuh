@@ -123,19 +123,31 @@ __device__ __forceinline__ CIDX inner_entry(uint32_t inner) { return (CIDX)((inn
 
 // counters[6] = trees that ran out of inner records, counters[7] = trees with a path deeper than
 // kPathMaxCompact; either makes mamcts_search_run's caller see an error at the next read-back.
-template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT, int KIND, bool MULTI = false, bool OVZ = false>
+// HELP (few trees per GPU: at most 4 per warp, reward-free others, PHILOX, one rollout per leaf): a tree gets a group
+// of 8 lanes instead of one. Lane 0 of the group owns the tree and runs the descent as ever; the other seven would
+// have been idle and now shorten the two serial parts that do not touch the tree's records in order: the rollout
+// (group_rollout: the Philox blocks of 32 steps computed side by side) and the backup of the shared-memory levels
+// (one lane per level after the short chain of returns). Same trees bit for bit.
+template <class Env, int NE, int NA, int NCHILD, class CIDX, class CNT, int KIND, bool MULTI = false, bool OVZ = false,
+          bool HELP = false>
 __global__ void __launch_bounds__(kSearchThreads, MAMCTS_COMPACT_MIN_BLOCKS)
 search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_constant__ CompactParams c) {
   using Inner = InnerRec<Env, NE, NA, NCHILD, CIDX, CNT>;
   constexpr int A = Env::A;
   using Leaf = LeafRec<A>;
+  static_assert(!HELP || (OVZ && !MULTI && KIND == MAMCTS_SRC_PHILOX && A == 2), "see the comment above");
   __shared__ SearchTables tab;
   stage_tables(tab, p.tab);   // before any lane leaves: contains a block barrier
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t tree = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * p.lanes_per_warp + lane;
-  // the lanes that own a tree; they re-converge explicitly once per iteration (see below)
-  const unsigned live = __ballot_sync(0xFFFFFFFFu, lane < p.lanes_per_warp && tree < p.T);
-  if (lane >= p.lanes_per_warp || tree >= p.T) return;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t gl = HELP ? (lane & 7u) : 0u;               // position inside the tree's group of lanes
+  const bool owner = gl == 0u;                                // the lane that owns the tree
+  const uint32_t slot_in_warp = HELP ? (lane >> 3) : lane;
+  const unsigned gmask = HELP ? (0xFFu << (lane & 24u)) : 0u; // the group's lanes
+  const uint32_t tree = warp * p.lanes_per_warp + slot_in_warp;
+  // the lanes that work on a tree; they re-converge explicitly once per iteration (see below)
+  const unsigned live = __ballot_sync(0xFFFFFFFFu, slot_in_warp < p.lanes_per_warp && tree < p.T);
+  if (slot_in_warp >= p.lanes_per_warp || tree >= p.T) return;
   Inner* inner = static_cast<Inner*>(c.inner) + (size_t)tree * c.max_inner;
   Leaf* leaves = static_cast<Leaf*>(c.leaves) + (size_t)tree * p.max_nodes;
   uint32_t num_nodes = p.tree_nodes[tree];   // nodes created (root included): the creation index
@@ -175,7 +187,10 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
   __shared__ CountPair s_n[kSL][kSearchThreads];
   __shared__ HeadWord s_head[kSL][kSearchThreads];
   __shared__ double s_q0[kSL][kSearchThreads], s_v0[kSL][kSearchThreads];
+  __shared__ double s_r0[HELP ? kSL : 1][HELP ? kSearchThreads : 1];   // HELP: the rewards of the shared levels
+  static_assert(!HELP || (kSharedLevels >= 1 && kSharedLevels <= 8), "HELP: one lane of the group per shared level");
   const uint32_t tid = threadIdx.x;
+  const uint32_t otid = HELP ? (tid & ~7u) : tid;            // the owner's column of the shared arrays
   uint32_t done = 0;
   bool failed = false;
   // Environments whose other agents never receive a reward (CrossingState: rewards[1..] stay 0,
@@ -205,7 +220,7 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
     uint32_t new_leaf = 0, creation = 0;
     // ---- select & expand: mcts.h:300-305, stage_node.h:167-232 --------------------------------
 #pragma unroll 1
-    while (!failed) {
+    while (!failed && (!HELP || owner)) {
       Inner* nd = inner + node;
       // One round trip, and as few load instructions as possible: each lane reads its own record, so
       // every global load costs 32 L1 wavefronts whatever its width (the L1/LSU pipe, not DRAM, was the
@@ -287,6 +302,7 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       st.flags = (st.flags & ~1u) | (uint32_t)Env::terminal(p.env, st);
       if (__double_as_longlong(r_ego) != 0ll || (!other_values_zero && __double_as_longlong(r_other) != 0ll)) {
         path_r0[depth] = r_ego;
+        if (HELP && depth < (uint32_t)kSharedLevels) s_r0[depth][tid] = r_ego;
         if (!other_values_zero) path_r1[depth] = r_other;
         reward_levels |= 1ull << depth;
       }
@@ -344,29 +360,55 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
     // barrier the compiler threads the rollout onto the "expand" exit and every group of lanes runs
     // its own copy of the step loop (measured: 4.9 active lanes instead of 10.9).
     __syncwarp(live);
+    if constexpr (HELP) {
+      // what the group needs from the owner: where the descent ended
+      uint32_t fl = (failed ? 1u : 0u) | (do_rollout ? 2u : 0u) | ((st.flags & 7u) << 2) | (depth << 8);
+      fl = __shfl_sync(gmask, fl, 0, 8);
+      failed = fl & 1u; do_rollout = fl & 2u; st.flags = (fl >> 2) & 7u; depth = fl >> 8;
+#pragma unroll
+      for (int i = 0; i < A; ++i) st.x[i] = __shfl_sync(gmask, st.x[i], 0, 8);
+      creation = __shfl_sync(gmask, creation, 0, 8);
+    }
     if (failed) continue;
     // ---- heuristic: mcts.h:309-312, random_heuristic.h:106-134 ------------------------------------
     if (do_rollout) {
       double other = 0.0;
       uint32_t steps = 0;
-      const double ego_h = leaf_heuristic<Env, KIND, MULTI>(p, st, depth, p.first_tree_id + tree, creation, const_act,
-                                                     other, steps);
+      double ego_h;
+      if constexpr (HELP) ego_h = group_rollout<Env>(p, st, depth, p.first_tree_id + tree, creation, gl, gmask, other, steps);
+      else ego_h = leaf_heuristic<Env, KIND, MULTI>(p, st, depth, p.first_tree_id + tree, creation, const_act, other, steps);
+      if (!owner) steps = 0;
       rollout_steps += steps;
       if (sizeof(Acc) == 4 && rollout_steps >= 0x80000000u) {   // never with realistic rollout caps; keeps the sum exact
         atomicAdd(p.counters + 1, (unsigned long long)rollout_steps);
         rollout_steps = 0;
       }
       // update_from_heuristic (uct_statistic.h:100-110): value_ = latest_return_ = h, visits 0 + 1
-      leaves[new_leaf].h[0] = ego_h;
-      leaves[new_leaf].h[1] = other;
+      if (owner) {
+        leaves[new_leaf].h[0] = ego_h;
+        leaves[new_leaf].h[1] = other;
+      }
       G[0] = ego_h;
       G[1] = other;
     }
     // ---- backpropagation: mcts.h:314-329, stage_node.h:259-271; recorded path, no loads ---------
-    backup_levels += depth;
+    if (owner) backup_levels += depth;
     uint32_t level = depth;
+    if constexpr (HELP) {
+      // The levels kept in shared memory (nearly all of a path), one lane of the group each: the return that
+      // reaches a level is a short chain (G = r + gamma G' per level below it, r != 0 on flagged levels only)
+      // that every lane walks; the update of the level's statistic (two FP64 divisions) and its stores then
+      // run side by side. Deeper levels stay with the owner (the loop below), before the shared ones.
+      const uint32_t top = depth < (uint32_t)kSharedLevels ? depth : (uint32_t)kSharedLevels;
+      {
+        uint32_t lo = (uint32_t)reward_levels, hi = (uint32_t)(reward_levels >> 32);
+        lo = __shfl_sync(gmask, lo, 0, 8); hi = __shfl_sync(gmask, hi, 0, 8);
+        reward_levels = ((unsigned long long)hi << 32) | lo;
+      }
+      level = owner ? depth : top;      // the owner's loop below stops at the shared levels; the others skip it
+    }
 #pragma unroll 1
-    while (level > 0) {
+    while (level > (HELP ? (depth < (uint32_t)kSharedLevels ? depth : (uint32_t)kSharedLevels) : 0u)) {
       level -= 1;
       uint32_t word;
       HeadWord head_w;
@@ -424,8 +466,57 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
       G[0] = e.G;
       G[1] = o.G;
     }
+    if constexpr (HELP) {
+      const uint32_t top = depth < (uint32_t)kSharedLevels ? depth : (uint32_t)kSharedLevels;
+      // the return that enters the shared levels, from the owner (its own rollout value or the deeper levels')
+      double Gc;
+      {
+        int lo = __double2loint(G[0]), hi = __double2hiint(G[0]);
+        lo = __shfl_sync(gmask, lo, 0, 8); hi = __shfl_sync(gmask, hi, 0, 8);
+        Gc = __hiloint2double(hi, lo);
+      }
+      double child_G = 0.0, my_r = 0.0;
+#pragma unroll 1
+      for (uint32_t l = top; l-- > 0u;) {
+        const double r = ((reward_levels >> l) & 1ull) ? s_r0[l][otid] : 0.0;
+        if (l == gl) { child_G = Gc; my_r = r; }
+        Gc = __dadd_rn(r, __dmul_rn(p.gamma, Gc));     // back_compute's o.G of level l
+      }
+      if (gl < top) {
+        const uint32_t word = s_node[gl][otid];
+        const HeadWord head_w = s_head[gl][otid];
+        const CountPair pair_w = s_n[gl][otid];
+        Inner* pn = inner + (word & 0xFFFFFFu);
+        Head hd;
+        __builtin_memcpy(&hd, &head_w, sizeof(Head));
+        const uint32_t ae = (word >> 24) & 15u, ao = word >> 28;
+        uint32_t n_ego, n_oth;
+        if (sizeof(CNT) == 2) {
+          uint32_t pair;
+          __builtin_memcpy(&pair, &pair_w, sizeof(pair));
+          n_ego = pair & 0xFFFFu; n_oth = pair >> 16;
+        } else {
+          uint2 pair;
+          __builtin_memcpy(&pair, &pair_w, sizeof(CountPair));
+          n_ego = pair.x; n_oth = pair.y;
+        }
+        BackRegs be;
+        be.q = s_q0[gl][otid]; be.v = s_v0[gl][otid]; be.cnt0 = n_ego; be.nv0 = hd.N[0];
+        const BackOut e = back_compute(be, my_r, p.gamma, child_G);
+        hd.N[0] = (CNT)e.nv; hd.N[1] = (CNT)(hd.N[1] + 1);   // a reward-free agent: only the counts move
+        HeadWord hw;
+        __builtin_memcpy(&hw, &hd, sizeof(Head));
+        *reinterpret_cast<HeadWord*>(&pn->c.h) = hw;
+        pn->c.n_e[ae] = (CNT)e.cnt;
+        pn->c.n_o[ao] = (CNT)(n_oth + 1u);
+        *reinterpret_cast<double2*>(&pn->vg_e[0]) = make_double2(e.v, e.G);
+        if (__double_as_longlong(e.q) != __double_as_longlong(be.q)) pn->q_e[ae] = e.q;
+      }
+      __syncwarp(gmask);   // the shared levels are read before the owner's next descent overwrites them
+    }
     done += 1;
   }
+  if (HELP && !owner) return;
   const uint32_t nodes_before = p.tree_nodes[tree];
   p.tree_nodes[tree] = num_nodes;
   c.tree_inner[tree] = num_inner;

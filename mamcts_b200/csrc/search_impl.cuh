@@ -225,6 +225,20 @@ struct SearchC final : public mamcts_search {
     const bool ovz = Env::kOtherRewardZero && p.gamma >= 0.0;
     if constexpr (Env::kOtherRewardZero) {
       if (ovz) {
+        // few trees (at most 4 per warp): 8 lanes per tree, search_compact.cuh HELP
+        if constexpr (Env::A == 2 && Env::kOutcomeRewards) {
+          unsigned long long r0_bits;
+          std::memcpy(&r0_bits, &p.env.r_tab[0], sizeof(r0_bits));
+          const char* knob = std::getenv("MAMCTS_SEARCH_HELPERS");
+          if (q.lanes_per_warp <= 4 && cfg.action_source == MAMCTS_SRC_PHILOX && cfg.rollouts_per_leaf == 1 &&
+              r0_bits == 0ull && !(knob && std::atoi(knob) == 0)) {
+            search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX, false, true, true>
+                <<<grid, block_threads, 0, e->stream>>>(q, c);
+            e->launches++;
+            MAMCTS_CUDA(e, cudaGetLastError());
+            return MAMCTS_OK;
+          }
+        }
         if (cfg.action_source == MAMCTS_SRC_PHILOX && cfg.rollouts_per_leaf > 1)
           search_compact_kernel<Env, NE, NA, NCHILD, CIDX, CNT, MAMCTS_SRC_PHILOX, true, true><<<grid, block_threads, 0, e->stream>>>(q, c);
         else if (cfg.action_source == MAMCTS_SRC_PHILOX)

@@ -508,6 +508,49 @@ __device__ __forceinline__ double lane_rollout(const SearchParams& p, typename E
   return __dmul_rn(ego, __ldg(p.disc + p.disc_len + it));
 }
 
+// lane_rollout for a GROUP of 8 lanes that work on one tree (search_compact_kernel with HELP: few trees per GPU,
+// where a decision's time is the serial chain of one tree's iteration and most lanes would be idle). Philox is
+// counter-based, so the blocks of the next 32 steps are computed side by side, one per lane; the step loop then
+// runs on every lane of the group alike (same state, same control flow) and takes the 16-bit words of step s from
+// lane s / 4 with one shuffle. Same stream positions, same arithmetic, same result as lane_rollout - for
+// environments with outcome rewards and a zero per-step reward (the caller checks), two agents, PHILOX.
+template <class Env>
+__device__ __forceinline__ double group_rollout(const SearchParams& p, typename Env::State st, uint32_t depth,
+                                                uint32_t s_hi, uint32_t s_lo, uint32_t gl, unsigned gmask,
+                                                double& other, uint32_t& steps) {
+  constexpr int A = Env::A;
+  static_assert(A == 2 && Env::kOutcomeRewards, "group_rollout: two agents, outcome rewards");
+  uint32_t it = 0, f = 0;
+  const uint32_t depth_room = p.max_depth > depth ? p.max_depth - depth : 0u;
+  const uint32_t limit = p.rh_cap < depth_room ? p.rh_cap : depth_room;
+  bool fin = Env::terminal(p.env, st) | (it >= limit);
+#pragma unroll 1
+  while (!fin) {
+    const Philox4 blk = philox4x32_10(it / 4u + gl, s_lo, s_hi, 0u, p.key0, p.key1);   // steps [it + 4 gl, it + 4 gl + 4)
+#pragma unroll 1
+    for (int src = 0; src < 8 && !fin; ++src) {
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        const uint32_t w = __shfl_sync(gmask, blk.w[sub], src, 8);   // halves 2 sub, 2 sub + 1: the two agents of the step
+        uint32_t h[A] = {w & 0xFFFFu, w >> 16};
+        const uint32_t nact[A] = {Env::num_actions(p.env, 0), Env::num_actions(p.env, 1)};
+        philox_bounded_all<A>(h, nact, it * A, s_lo, s_hi, p.key0, p.key1);
+        const int32_t act[A] = {(int32_t)h[0], (int32_t)h[1]};
+        f = Env::step_outcome(p.env, st, act);
+        it += 1;
+        fin = (f != 0u) | (it >= limit);
+        if (fin) break;
+      }
+    }
+  }
+  steps = it;
+  double ego = 0.0;
+  const double r_last = it ? Env::outcome_reward(p.env, f) : 0.0;
+  if (r_last != 0.0) ego = __dadd_rn(ego, __dmul_rn(__ldg(p.disc + it - 1), r_last));
+  other = it ? __dmul_rn(__ldg(p.disc + it - 1), 0.0) : 0.0;   // rewards[1..] are 0
+  return __dmul_rn(ego, __ldg(p.disc + p.disc_len + it));
+}
+
 // The heuristic value of a new leaf (RandomHeuristic::calculate_heuristic_values, random_heuristic.h:106-134).
 // MULTI = false is the reference: one rollout. MULTI = true (K = rollouts_per_leaf > 1, a power of two <= 16,
 // PHILOX): the mean of K rollouts from the same state with stream_lo = creation index * K + k, summed in the
