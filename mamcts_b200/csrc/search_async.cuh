@@ -284,7 +284,7 @@ search_async_kernel(const __grid_constant__ SearchParams p, const __grid_constan
               __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, vg_e), ve, sizeof(ve));
               __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, vg_o), vo, sizeof(vo));
               __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, parent), &node, sizeof(uint32_t));
-              constexpr size_t used = (offsetof(Inner, q_o) + sizeof(double) * NA + 31) / 32;   // whole sectors
+              constexpr size_t used = (offsetof(Inner, q_o) + 31) / 32;   // whole sectors; the reward-free agent's action values are never stored (search_compact.cuh)
 #pragma unroll
               for (size_t i = 0; i < used; ++i) {
                 Sector sec;

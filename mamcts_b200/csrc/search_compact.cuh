@@ -344,7 +344,11 @@ search_compact_kernel(const __grid_constant__ SearchParams p, const __grid_const
           __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, vg_e), ve, sizeof(ve));
           __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, vg_o), vo, sizeof(vo));
           __builtin_memcpy(reinterpret_cast<char*>(img) + offsetof(Inner, parent), &node, sizeof(uint32_t));
-          constexpr size_t used = (offsetof(Inner, q_o) + sizeof(double) * NA + 31) / 32;   // whole sectors
+          // whole sectors; a reward-free agent's action values (+0.0 for the whole search) are never read by
+          // the kernel and the export reports them as the zeros they are (SearchC::read_stat), so the sectors
+          // that hold nothing else are not written at all
+          constexpr size_t used = other_values_zero ? (offsetof(Inner, q_o) + 31) / 32
+                                                    : (offsetof(Inner, q_o) + sizeof(double) * NA + 31) / 32;
 #pragma unroll
           for (size_t i = 0; i < used; ++i) {
             Sector sec;

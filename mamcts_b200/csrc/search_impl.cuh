@@ -279,7 +279,11 @@ struct SearchC final : public mamcts_search {
     *visits = nd->c.h.N[k];
     *nexp = nd->c.h.nexp[k];
     if (agent == 0) { for (int a = 0; a < NE; ++a) { q[a] = nd->q_e[a]; n[a] = nd->c.n_e[a]; } }
-    else { for (int a = 0; a < NA; ++a) { q[a] = nd->q_o[a]; n[a] = nd->c.n_o[a]; } }
+    else {
+      // a reward-free agent with a discount >= 0: every action value is +0.0 and the kernels do not store them
+      const bool zero = Env::kOtherRewardZero && p.gamma >= 0.0;
+      for (int a = 0; a < NA; ++a) { q[a] = zero ? 0.0 : nd->q_o[a]; n[a] = nd->c.n_o[a]; }
+    }
   }
 
   void root_gather(RootGather* g) const override {
