@@ -136,12 +136,63 @@ __device__ __forceinline__ StatRegs<NACT> load_stat(const StatRec<NACT>* s) {
   return r;
 }
 
+// 1 / x and 1 / sqrt(x) in FP64 to ~2^-50 relative: the hardware's approximations (rcp.approx.ftz.f64 and
+// rsqrt.approx.ftz.f64: relative error <= 2^-22, PTX ISA) refined by two Newton steps each (error e -> ~1.5 e^2 per
+// step, plus a few roundings). For normal, finite x only (the callers check). Used by the second screening stage
+// below, never for a value that is stored.
+__device__ __forceinline__ double fast_rcp64(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+  for (int k = 0; k < 2; ++k) { const double e = __fma_rn(-x, y, 1.0); y = __fma_rn(y, e, y); }
+  return y;
+}
+__device__ __forceinline__ double fast_rsqrt64(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) { const double e = __fma_rn(-h * y, y, 0.5); y = __fma_rn(y, e, y); }
+  return y;
+}
+
 // Exact UCB arg-max, calculate_ucb_and_max_action (reference uct_statistic.h:223-244). Cold: only
 // reached when the FP32 screen of choose_action cannot prove the winner, so it is kept out of line
 // (the hot loop must stay small enough for the instruction cache).
+//
+// Second screening stage (try_fast: the FP32 screen's preconditions held and `mask` is its set of near-maximal
+// candidates, every other action provably below the winner). The FP32 screen cannot separate scores closer than
+// ~1e-5 - at the root of a converged tree, where two actions have nearly the same value and 2 000 visits each, that
+// is most of its failures - but FP64 with approximate reciprocal / square root can, at a quarter of the cost of the
+// correctly rounded divisions and square roots (this path runs with one or two lanes of a warp while the others
+// wait): score' = (Q - lo) * rcp(range) + 2c * sqrt(L) * rsqrt(n), |score' - score| <= 1e-14 (|norm| + |bonus|) (two
+// Newton steps from 2^-22: 2^-50 per factor, a handful of roundings), the reference's own five roundings stay within
+// 1e-15 (|norm| + |bonus|). A candidate whose score' exceeds every other candidate's by more than
+// 1e-11 (max(|norm| + |bonus|) + 1) - a thousand times those bounds - therefore has the strictly largest reference
+// score (and a positive one, above the DBL_MIN the reference's loop starts from) and is what that loop returns.
+// Anything closer, or not finite, goes on to the exact evaluation. Bit 31 of the result says the exact one ran.
 template <int NACT>
 __device__ __noinline__ uint32_t exact_ucb_argmax(StatRegs<NACT> r, uint32_t mask, double lo, double range,
-                                                  double log2N, double two_c) {
+                                                  double log2N, double two_c, bool try_fast) {
+  if (try_fast) {
+    const double ir = fast_rcp64(range);
+    const double sq = two_c * (log2N * fast_rsqrt64(log2N));
+    double s_best = -1.0, s_next = -1.0, mag = 0.0;   // mag: the largest |norm| + |bonus| - what the error bounds scale with
+    int bi = -1;
+    bool clean = true;
+#pragma unroll
+    for (int a = 0; a < NACT; ++a) {
+      if ((mask >> a) & 1u) {
+        const double nrm = (r.Q[a] - lo) * ir, bonus = sq * fast_rsqrt64((double)r.n[a]);
+        const double s = nrm + bonus, m = fabs(nrm) + fabs(bonus);
+        clean &= (s == s) & (m < 1e300);               // not NaN, not huge
+        mag = m > mag ? m : mag;
+        if (s > s_best) { s_next = s_best; s_best = s; bi = a; }
+        else if (s > s_next) s_next = s;
+      }
+    }
+    if (clean && bi >= 0 && s_best > 0.0 && s_best - s_next > 1e-11 * (mag + 1.0)) return (uint32_t)bi;
+  }
   // the scores of all candidates first, as independent chains (two divisions and a square root each: the
   // latency of this path is what the rest of the warp waits for), then the reference's loop over them
   double v[NACT];
@@ -159,7 +210,7 @@ __device__ __noinline__ uint32_t exact_ucb_argmax(StatRegs<NACT> r, uint32_t mas
   for (int a = 0; a < NACT; ++a) {
     if (((mask >> a) & 1u) && v[a] > max_value) { max_value = v[a]; best = a; }
   }
-  return best;
+  return best | 0x80000000u;
 }
 
 // UctStatistic::choose_next_action, reference uct_statistic.h:61-76 (+ :122-132, :223-244, :256-262),
@@ -273,6 +324,7 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   // cannot be the (first) exact maximum.
   int bi = -1;
   bool ok;
+  bool narrowed = false;   // `candidates` is the FP32 screen's near-maximal set (its preconditions held)
   uint32_t candidates = mask;
   {
     const float rangef = (float)range;
@@ -299,6 +351,7 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
     for (int a = 0; a < NACT; ++a) if (a == bi) { qb = q[a]; nb = cnt[a]; }
     if (ok) {
       const float delta = 6e-6f * (best_sc + 1.0f);
+      narrowed = true;
       candidates = 0u;
 #pragma unroll
       for (int a = 0; a < NACT; ++a) {
@@ -313,9 +366,12 @@ __device__ __forceinline__ uint32_t select_action(const StatRegs<NACT>& r, const
   }
   if (ok) return (uint32_t)bi;
 
-  exact_evals += 1;
   const double log2N = __dmul_rn(2.0, __ldg(p.log_table + N));  // 2 * log(total_node_visits_), host libm
-  const uint32_t best = exact_ucb_argmax<NACT>(r, candidates, lo, range, log2N, p.two_c);
+  // the near-maximal candidates in FP64 with approximate reciprocals, then (rarely) the reference's exact evaluation
+  const bool try_fast = narrowed && range > 1e-300 && range < 1e300 && p.two_c < 1e6;
+  uint32_t best = exact_ucb_argmax<NACT>(r, candidates, lo, range, log2N, p.two_c, try_fast);
+  exact_evals += best >> 31;
+  best &= 0x7FFFFFFFu;
 #pragma unroll
   for (int a = 0; a < NACT; ++a) if ((uint32_t)a == best) { back.q = r.Q[a]; back.cnt0 = r.n[a]; }
   return best;

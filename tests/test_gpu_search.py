@@ -510,13 +510,16 @@ def test_root_policy_statistically_matches_cpu_twin(engine):
     s.close()
 
 
-@pytest.mark.parametrize("lpw", [2, 8, 32])
+@pytest.mark.parametrize("lpw,helpers", [(2, "1"), (2, "0"), (4, "1"), (1, "0"), (8, "1"), (32, "1")])
 @pytest.mark.parametrize("layout", [LAYOUT_CLASSIC, LAYOUT_COMPACT])
-def test_trees_per_warp_do_not_change_results(engine, lpw, layout, monkeypatch):
+def test_trees_per_warp_do_not_change_results(engine, lpw, helpers, layout, monkeypatch):
     """mamcts_search_create packs 1..32 trees into a warp depending on the tree count (few trees: one per
     warp); the small tests above all run one tree per warp, the bench 32. Forced here through the
-    profiling knob: every packing must build the same trees."""
+    profiling knob: every packing must build the same trees - with at most 4 trees per warp the compact layout
+    gives a tree a group of 8 lanes (Philox blocks of the rollout side by side, one lane per level of the
+    backup; MAMCTS_SEARCH_HELPERS=0 switches that off), which must not change a bit either."""
     monkeypatch.setenv("MAMCTS_SEARCH_LPW", str(lpw))
+    monkeypatch.setenv("MAMCTS_SEARCH_HELPERS", helpers)
     iters, T = 500, 100
     mp = default_params(max_number_of_iterations=iters, max_number_of_nodes=100000000,
                         rh_max_number_of_iterations=50)
