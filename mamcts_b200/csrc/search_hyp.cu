@@ -140,8 +140,11 @@ __device__ __noinline__ uint32_t hyp_worst_case(const HypOther& o, uint32_t h, c
   return worst;
 }
 
+#ifndef MAMCTS_HYP_MIN_BLOCKS
+#define MAMCTS_HYP_MIN_BLOCKS 8
+#endif
 template <int J, int NE>
-__global__ void __launch_bounds__(kSearchThreads) hyp_search_kernel(const __grid_constant__ SearchParams p,
+__global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_search_kernel(const __grid_constant__ SearchParams p,
                                                                    const __grid_constant__ HypParams hp) {
   using Env = CrossingEnv<J>;
   using Node = HypNode<J, NE>;
@@ -882,10 +885,14 @@ int mamcts_hyp_search_create(mamcts_engine* e, const mamcts_hyp_search_config* c
   p.lb = mp.uct_lower_bound; p.ub = mp.uct_upper_bound;
   make_crossing_env(cp, p.env);
   {
-    const uint64_t warp_slots = (uint64_t)std::max(e->num_sms, 1) * 16u;
+    const uint64_t warp_slots = (uint64_t)std::max(e->num_sms, 1) * (2u * MAMCTS_HYP_MIN_BLOCKS);
     uint32_t lpw = 1;
     while (lpw < 32 && (uint64_t)lpw * warp_slots < (uint64_t)T) lpw <<= 1;
     p.lanes_per_warp = lpw;
+    if (const char* v = std::getenv("MAMCTS_SEARCH_LPW")) {   // profiling knob, as for the UCT searches
+      const int l = std::atoi(v);
+      if (l >= 1 && l <= 32) p.lanes_per_warp = (uint32_t)l;
+    }
   }
   err = cudaMemcpyAsync(s->d_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice, e->stream);
   if (err == cudaSuccess) err = cudaMemcpyAsync(s->d_log, logs.data(), sizeof(double) * logs.size(), cudaMemcpyHostToDevice, e->stream);
