@@ -360,6 +360,8 @@ def measure_rollout_c3(engine, stream, world=1, rank=0, steps=5, warmup=3, dist=
             dist.all_reduce(ag, op=dist.ReduceOp.SUM)
         out.update({"e2e_env_steps_per_s": float(ag[1]) / float(mx2[0]), "e2e_h2d_bytes": int(xh.nbytes),
                     "e2e_d2h_bytes": int(8 * n * (A + 2) + 8 + 8 * (2 * A + 1))})
+    if rank == 0 and e2e:
+        out["variants"] = _c3_variants(engine, stream, mp, A, K, steps)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
     bytes_per_rollout = 16 * A + 8 * 1 + 8
@@ -447,6 +449,80 @@ def measure_c5_strong(engine, stream, world, rank, dist, steps=5, warmup=2):
         "merged_root_visits": int(merged["visits"]), "merged_root_n": [int(v) for v in merged["n"]],
         "best_action": int(merged["best"]), "gpu_launches": int(launches),
     }
+
+
+def _c3_variants(engine, stream, mp, A, K, steps):
+    """The two other C3 inputs SURVEY.md 8(d) names, on one GPU, device-resident, same kernel and call as the main
+    section: (1) longer, branchier episodes - CHAIN_LENGTH = 41, EGO_GOAL_POS = 26, the reference's own 4-agent
+    setting (environments/tests/crossing_state_int_test.cc:232-235) with C3's 8 agents; (2) a ragged batch as a
+    leaf-parallel search hands it over: start states at depths 1..6 instead of the decision state - every slot's
+    state is what 1..6 random joint actions lead to (produced by the same entry point: a rollout capped at that
+    many steps returns its final state), terminal ones included (a leaf can be terminal: zero steps)."""
+    import numpy as np
+    import torch
+    from mamcts_b200 import default_crossing_params, default_params
+    from mamcts_b200._abi import SRC_PHILOX
+    dev = torch.device("cuda", engine.device)
+    n = C3_ROLLOUTS // K
+    res = {}
+
+    def timed(cp, x_t, flags_t, depth_t, tag):
+        with torch.cuda.stream(stream):
+            ego = torch.zeros(n, dtype=torch.float64, device=dev)
+            oth = torch.zeros((A - 1, n), dtype=torch.float64, device=dev)
+            tot = torch.zeros(1, dtype=torch.int64, device=dev)
+            mom = torch.zeros(2 * A + 1, dtype=torch.float64, device=dev)
+        def one(i):
+            engine.rollout_crossing_device(mp, cp, n, K, x_t.data_ptr(), ego.data_ptr(), oth.data_ptr(), 0, 0,
+                                           tot.data_ptr(), d_flags=flags_t.data_ptr() if flags_t is not None else 0,
+                                           d_depth=depth_t.data_ptr() if depth_t is not None else 0,
+                                           kind=SRC_PHILOX, d_moments=mom.data_ptr(), seed=1000,
+                                           stream_hi_base=1000 + i, stream_lo_base=0)
+        for i in range(2):
+            one(i)
+        torch.cuda.synchronize()
+        total_ms, total_steps = 0.0, 0
+        for i in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            one(2 + i)
+            b.record(stream)
+            stream.synchronize()
+            total_ms += a.elapsed_time(b)
+            total_steps += int(tot.item())
+        return {"what": tag, "env_steps_per_s": total_steps / (total_ms * 1e-3), "ms_per_decision": total_ms / steps,
+                "mean_steps_per_rollout": total_steps / (steps * C3_ROLLOUTS)}
+
+    # (1) longer episodes
+    cp_long = default_crossing_params(num_other_agents=A - 1, chain_length=41, ego_goal_pos=26)
+    with torch.cuda.stream(stream):
+        x0 = torch.full((A, n), 5, dtype=torch.int32, device=dev)
+    res["long_episodes"] = timed(cp_long, x0, None, None,
+                                 f"CHAIN_LENGTH 41, EGO_GOAL_POS 26, {A} agents, {C3_ROLLOUTS} rollouts from the decision state")
+    # (2) ragged leaf batch: states and depths as a search's leaves have them
+    cp = default_crossing_params(num_other_agents=A - 1)
+    rng = np.random.default_rng(1000)
+    depth = rng.integers(1, 7, size=n).astype(np.uint32)
+    xs = np.full((A, n), 5, dtype=np.int32)
+    fl = np.zeros(n, dtype=np.uint8)
+    for d in range(1, 7):
+        sel = np.nonzero(depth == d)[0]
+        if sel.size == 0:
+            continue
+        mpd = default_params(rh_max_number_of_iterations=d)
+        r = engine.rollout_crossing(mpd, cp, np.full((A, sel.size), 5, dtype=np.int32), K=1, kind=SRC_PHILOX,
+                                    parity=True, seed=4711, stream_hi_base=d)
+        xs[:, sel] = r["final_x"]
+        fl[sel] = r["final_flags"]
+        depth[sel] = r["steps"]            # a walk that ended early sits at the depth it reached
+    with torch.cuda.stream(stream):
+        x_t = torch.from_numpy(xs).to(dev)
+        f_t = torch.from_numpy(fl).to(dev)
+        d_t = torch.from_numpy(depth.astype(np.int32)).to(dev)
+    r2 = timed(cp, x_t, f_t, d_t, f"{n} leaf states at depths 1..6 (terminal ones included) x {K} rollouts each")
+    r2["terminal_leaves"] = int((fl & 1).sum())
+    res["leaf_states"] = r2
+    return res
 
 
 def measure_c4_hypothesis(engine, stream, trees=8192, iterations=10000, steps=3):
