@@ -192,6 +192,24 @@ def cpu_baselines(repeats: int):
                     "(reference mcts/mcts.h:188-221), one call"}
         mpr = default_params(rh_max_number_of_iterations=DEPTH_CAP)
         out["c4_hypothesis"] = cpu_c4_hypothesis(threads)
+        # C1 (BASELINE configs[0], the reference's own CPU-runnable case): SimpleState(4), 20 iterations, one thread
+        mp1 = default_params(max_number_of_iterations=20, rh_max_number_of_iterations=1000)
+        n1, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 1.0:
+            O.ref_search_simple(mp1, 4)
+            n1 += 1
+        el1 = time.perf_counter() - t1
+        out["c1_simple"] = {"iterations_per_s": 20 * n1 / el1, "searches": n1, "cores": 1,
+                            "what": "Mcts<SimpleState, UctStatistic, UctStatistic, RandomHeuristic>::search, 20 iterations "
+                                    "(test/uct/uct_test.cc:22-40), one host thread; every rollout runs into its 1 000-step cap "
+                                    "(the stock policy repeats one joint action, which never ends a SimpleState "
+                                    "episode: SURVEY.md F1), so an iteration is ~1 000 execute() calls"}
+        # C3-shaped search: 8 agents, the C2 search parameters
+        mp8, _ = _params()
+        it8, sec8 = O.ref_time_search(mp8, default_crossing_params(num_other_agents=C3_OTHERS), threads, 1)
+        out["search_a8"] = {"iterations_per_s": it8, "seconds": sec8, "cores": threads,
+                            "what": f"{threads} independent searches of the C2 parameters with {C3_OTHERS + 1} agents "
+                                    f"({ITERATIONS} iterations each), one per host thread"}
         for others in (1, C3_OTHERS):
             st, ro = O.ref_time_rollouts(mpr, default_crossing_params(num_other_agents=others), threads, 2.0)
             out[f"rollout_loop_a{others + 1}"] = {
