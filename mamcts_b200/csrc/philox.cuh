@@ -64,17 +64,22 @@ template <int N>
 __device__ __forceinline__ void philox_bounded_all(uint32_t (&x)[N], const uint32_t (&n)[N], uint32_t pos0,
                                                    uint32_t stream_lo, uint32_t stream_hi, uint32_t k0,
                                                    uint32_t k1) {
+  // the pre-filter of the rejection test, once for the step: a draw can only be rejected if the low half of its
+  // product is below 65536 mod n < n, so the smallest low half against the largest n decides whether anything has
+  // to be looked at (one AND + one MIN per draw instead of AND + compare + merge)
   uint32_t m[N];
-  uint32_t small = 0;
+  uint32_t low_min = 0xFFFFFFFFu, n_max = 0u;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     m[i] = x[i] * n[i];
-    small |= (uint32_t)((m[i] & 0xFFFFu) < n[i]) << i;
+    const uint32_t low = m[i] & 0xFFFFu;
+    low_min = low < low_min ? low : low_min;
+    n_max = n[i] > n_max ? n[i] : n_max;
   }
-  if (small) {
+  if (low_min < n_max) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      if ((small >> i) & 1u) {
+      if ((m[i] & 0xFFFFu) < n[i]) {
         const uint32_t t = 65536u % n[i];
         if ((m[i] & 0xFFFFu) < t) m[i] = philox_bounded_retry(n[i], t, pos0 + i, stream_lo, stream_hi, k0, k1);
       }
