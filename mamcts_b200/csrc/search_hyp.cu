@@ -47,24 +47,41 @@ constexpr int kHypMA = MAMCTS_HYP_MAX_OTHER_ACTIONS;
 constexpr int kHypPathMax = 96;
 constexpr uint32_t kNotSetHyp = 0xFFu;
 
-struct HypOther {
+// A node's record, laid out by 128-byte line in the way a visit uses it (round 2; the first version kept one array
+// per member over all hypotheses, ~9 lines touched and ~6 dirtied per visit, 1 104 bytes zero-filled per new node):
+//   line 0      header, state, reward / cost of the incoming edge, the ego agent's UctStatistic
+//   line 1      the generator positions of the state's policy objects and, per other agent, the members of its
+//               HypothesisStatistic that do not depend on the hypothesis
+//   lines 2..   one line per (other agent, hypothesis): visits, the expanded actions in insertion order, their
+//               counts and costs
+// A visit under hypotheses (h_1 .. h_J) touches lines 0, 1 and the J lines (j, h_j). A hypothesis line is
+// initialised when the agent first chooses under that hypothesis at the node (HypothesisStatistic::
+// init_hypothesis_variables, hypothesis_statistic.h:52-61 - the reference does the same), so a new node costs two
+// lines of stores and the three quarters of the nodes that are never selected again never touch the rest.
+struct alignas(128) HypHyp {
+  uint32_t visits;                   // total_node_visits_hypothesis_[h]
+  uint8_t nexp;                      // ucb_statistics_[h].size()
+  uint8_t present;                   // bit a: action a is a key of ucb_statistics_[h]
+  uint8_t pad[2];
+  uint8_t order[kHypMA];             // insertion order of the actions of ucb_statistics_[h]
+  uint32_t count[kHypMA];            // action_count_
+  double cost[kHypMA];               // action_ego_cost_
+};
+static_assert(sizeof(HypHyp) == 128, "one line per (agent, hypothesis)");
+
+struct HypCommon {
   double cost_value;                 // ego_cost_value_
   double latest;                     // latest_ego_cost_
   uint32_t N;                        // total_node_visits_
   uint32_t nexp_total;               // num_expanded_actions_ (one per back-propagation, :132)
   uint32_t stat_pos;                 // words this statistic's generator has produced
   uint32_t visits_notset;            // total_node_visits_hypothesis_[HYPOTHESIS_ID_NOT_SET] (:106)
-  uint32_t visits_h[kHMax];          // total_node_visits_hypothesis_[h]
-  uint8_t nexp_h[kHMax];             // ucb_statistics_[h].size()
-  uint8_t seen_h[kHMax];             // init_hypothesis_variables(h) ran (:52-61)
-  uint8_t present[kHMax];            // bit a: action a is a key of ucb_statistics_[h]
-  uint8_t order[kHMax][kHypMA];      // insertion order of the actions of ucb_statistics_[h]
-  double cost[kHMax][kHypMA];        // action_ego_cost_
-  uint32_t count[kHMax][kHypMA];     // action_count_
+  uint8_t seen[kHMax];               // init_hypothesis_variables(h) ran (:52-61): the line (agent, h) is valid
+  uint32_t pad;
 };
 
 template <int J, int NE>
-struct alignas(16) HypNode {
+struct alignas(128) HypNode {
   uint32_t parent, visit_count, depth;
   uint8_t flags;                     // bit0 terminal, bit1 goal, bit2 collided
   uint8_t ja[J + 1];                 // ego action index, others: velocity - MIN_VELOCITY_OTHER
@@ -72,8 +89,9 @@ struct alignas(16) HypNode {
   double r_in;                       // ego reward collected on the incoming edge
   double c_in;                       // mean of the ego cost vector collected on the incoming edge (:120)
   StatRec<NE> ego;
-  alignas(16) uint32_t pol_pos[kHMax]; // position of the state's policy generator of hypothesis h
-  HypOther oth[J];
+  alignas(128) uint32_t pol_pos[kHMax]; // position of the state's policy generator of hypothesis h
+  HypCommon com[J];
+  HypHyp hyp[J][kHMax];
 };
 
 struct HypTables {
@@ -95,13 +113,14 @@ struct HypParams {
   HypTables tab;
 };
 
-// A visit reads and writes fields all over a node's ~1.1-KB record, each a dependent global access; requesting every
-// line of the record at once when the node index becomes known turns that chain of HBM round trips into one round
-// trip followed by L1 hits (profiles/r02_hyp_search.txt: 84 -> ... us per iteration at 4 096 trees).
-template <class Node>
-__device__ __forceinline__ void hyp_prefetch_node(const Node* nd) {
+// The lines a visit will touch, requested at once when the node index becomes known: one round trip to HBM for the
+// level instead of one per field (profiles/r02_hyp_search.txt).
+template <class Node, int J>
+__device__ __forceinline__ void hyp_prefetch_node(const Node* nd, const uint8_t (&hyp)[J]) {
 #pragma unroll
-  for (size_t off = 0; off < sizeof(Node); off += 128) prefetch_l1(reinterpret_cast<const char*>(nd) + off);
+  for (size_t off = 0; off < offsetof(Node, hyp); off += 128) prefetch_l1(reinterpret_cast<const char*>(nd) + off);
+#pragma unroll
+  for (int j = 0; j < J; ++j) prefetch_l1(&nd->hyp[j][hyp[j]]);
 }
 
 __device__ __forceinline__ uint32_t hyp_hash(uint32_t parent, const uint8_t* ja, int n) {
@@ -115,26 +134,26 @@ __device__ __forceinline__ uint32_t hyp_hash(uint32_t parent, const uint8_t* ja,
 
 // get_worst_case_action (hypothesis_statistic.h:178-202) over the actions of hypothesis h in the container's
 // iteration order (last inserted first): normalised ego cost + 2c sqrt(2 ln(visits_h) / count), strict >.
-__device__ __noinline__ uint32_t hyp_worst_case(const HypOther& o, uint32_t h, const SearchParams& p, const HypParams& hp) {
-  const uint32_t nexp = o.nexp_h[h];
+__device__ __noinline__ uint32_t hyp_worst_case(const HypHyp& o, const SearchParams& p, const HypParams& hp) {
+  const uint32_t nexp = o.nexp;
   double lo = hp.hyp_lb, hi = hp.hyp_ub;
   if (p.use_bound_est) {   // calculate_bounds_based_on_stat :214-222
     double mn = 0.0, mx = 0.0;
     for (uint32_t k = 0; k < nexp; ++k) {
-      const double c = o.cost[h][o.order[h][nexp - 1u - k]];
+      const double c = o.cost[o.order[nexp - 1u - k]];
       if (k == 0) { mn = c; mx = c; }
       else { mn = c < mn ? c : mn; mx = c < mx ? mx : c; }   // std::minmax_element semantics on values
     }
     if (mn == mx) { lo = 0.0; hi = mx; } else { lo = mn; hi = mx; }
   }
   const double range = __dsub_rn(hi, lo);
-  const double log2N = __dmul_rn(2.0, __ldg(p.log_table + o.visits_h[h]));
+  const double log2N = __dmul_rn(2.0, __ldg(p.log_table + o.visits));
   double largest = -1.7976931348623157e308;   // std::numeric_limits<double>::lowest()
-  uint32_t worst = o.order[h][nexp - 1u];     // ucb_statistics.begin()->first
+  uint32_t worst = o.order[nexp - 1u];        // ucb_statistics.begin()->first
   for (uint32_t k = 0; k < nexp; ++k) {
-    const uint32_t a = o.order[h][nexp - 1u - k];
-    const double norm = __ddiv_rn(__dsub_rn(o.cost[h][a], lo), range);
-    const double ucb = __dadd_rn(norm, __dmul_rn(hp.hyp_two_c, __dsqrt_rn(__ddiv_rn(log2N, (double)o.count[h][a]))));
+    const uint32_t a = o.order[nexp - 1u - k];
+    const double norm = __ddiv_rn(__dsub_rn(o.cost[a], lo), range);
+    const double ucb = __dadd_rn(norm, __dmul_rn(hp.hyp_two_c, __dsqrt_rn(__ddiv_rn(log2N, (double)o.count[a]))));
     if (ucb > largest) { largest = ucb; worst = a; }
   }
   return worst;
@@ -194,7 +213,7 @@ __global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_sea
     typename Env::State st;
     uint32_t leaf_pos[kHMax];
     // ---- select & expand: mcts.h:300-305, stage_node.h:167-232 ------------------------------------------
-    hyp_prefetch_node(nodes);   // the root
+    hyp_prefetch_node<Node, J>(nodes, hyp);   // the root
 #pragma unroll 1
     while (true) {
       Node* nd = nodes + node;
@@ -222,18 +241,29 @@ __global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_sea
         pp[0] = w.x; pp[1] = w.y; pp[2] = w.z; pp[3] = w.w;
       }
       uint32_t nexp0[J], vis0[J], pres0[J], spos0[J];
+      bool seen0[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const HypOther& o = nd->oth[j];
-        const uint32_t h = hyp[j];
-        nexp0[j] = o.nexp_h[h]; vis0[j] = o.visits_h[h]; pres0[j] = o.present[h]; spos0[j] = o.stat_pos;
+        const HypHyp& o = nd->hyp[j][hyp[j]];
+        nexp0[j] = o.nexp; vis0[j] = o.visits; pres0[j] = o.present;
+        spos0[j] = nd->com[j].stat_pos; seen0[j] = nd->com[j].seen[hyp[j]] != 0;
+      }
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        // the line of a hypothesis the agent has not chosen under at this node holds nothing yet (see HypNode)
+        if (!seen0[j]) { nexp0[j] = 0; vis0[j] = 0; pres0[j] = 0; }
       }
       bool pp_moved = false;
 #pragma unroll
       for (int j = 0; j < J; ++j) {                                             // :191-194, agent order
-        HypOther& o = nd->oth[j];
+        HypHyp& o = nd->hyp[j][hyp[j]];
         const uint32_t h = hyp[j];                                              // hypothesis_statistic.h:64-65
-        o.seen_h[h] = 1;                                                        // init_hypothesis_variables
+        if (!seen0[j]) {                                                        // init_hypothesis_variables
+          uint4* w = reinterpret_cast<uint4*>(&o);
+#pragma unroll
+          for (size_t i = 0; i < sizeof(HypHyp) / 16; ++i) w[i] = make_uint4(0u, 0u, 0u, 0u);
+          nd->com[j].seen[h] = 1;
+        }
         const uint32_t nexp = nexp0[j];
         uint32_t a = 0;
         if (failed) {
@@ -251,15 +281,15 @@ __global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_sea
             const int32_t v = crossing_policy_action(p.env, st.x[j + 1], st.last[j + 1], st.x[0], st.last[0], gap);
             a = (uint32_t)(v - hp.min_v_other);
             if (!((pres0[j] >> a) & 1u)) {                                      // ucb_statistics_[h][a] created
-              o.present[h] = (uint8_t)(pres0[j] | (1u << a));
-              o.order[h][nexp] = (uint8_t)a;
-              o.nexp_h[h] = (uint8_t)(nexp + 1u);
-              o.cost[h][a] = 0.0;
-              o.count[h][a] = 0;
+              o.present = (uint8_t)(pres0[j] | (1u << a));
+              o.order[nexp] = (uint8_t)a;
+              o.nexp = (uint8_t)(nexp + 1u);
+              o.cost[a] = 0.0;
+              o.count[a] = 0;
             }
           }
         } else if (hp.cost_based) {
-          a = hyp_worst_case(o, h, p, hp);                                      // :85-87
+          a = hyp_worst_case(o, p, hp);                                         // :85-87
         } else {
           // sample_from_hypothesis_expanded_actions (:204-212): the statistic's own generator picks an index
           // into the container's iteration order (last inserted first)
@@ -267,8 +297,8 @@ __global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_sea
           if (pos >= hp.sel_len) { failed = true; atomicAdd(p.counters + 6, 1ull); }
           else {
             const uint32_t e = __ldg(hp.sel_tab + (size_t)(nexp - 1u) * hp.sel_len + pos);
-            o.stat_pos = spos0[j] + (e >> 8);
-            a = o.order[h][nexp - 1u - (e & 0xFFu)];
+            nd->com[j].stat_pos = spos0[j] + (e >> 8);
+            a = o.order[nexp - 1u - (e & 0xFFu)];
           }
         }
         ja[j + 1] = (uint8_t)a;
@@ -285,7 +315,7 @@ __global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_sea
         const uint32_t c = hash[slot];
         if (c == 0) break;
         const Node* cn = nodes + c;
-        hyp_prefetch_node(cn);   // nearly always the child the descent goes on with
+        hyp_prefetch_node<Node, J>(cn, hyp);   // nearly always the child the descent goes on with
         bool same = cn->parent == node;
 #pragma unroll
         for (int i = 0; i < A; ++i) same &= cn->ja[i] == ja[i];
@@ -305,9 +335,10 @@ __global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_sea
       child = num_nodes++;
       Node* cn = nodes + child;
       {
-        // zero the record, then the header (a fresh node: every statistic empty)
+        // zero the header, the ego statistic and the agents' common members (a fresh node: every statistic
+        // empty); the per-hypothesis lines are initialised when first used (HypNode)
         uint4* w = reinterpret_cast<uint4*>(cn);
-        for (size_t i = 0; i < sizeof(Node) / 16; ++i) w[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = 0; i < offsetof(Node, hyp) / 16; ++i) w[i] = make_uint4(0u, 0u, 0u, 0u);
       }
       cn->parent = node;
       cn->depth = depth + 1;
@@ -381,20 +412,20 @@ __global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_sea
       const double hc = __ddiv_rn(__dadd_rn(0.0, cost_h), 1.0);
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        leaf->oth[j].cost_value = hc; leaf->oth[j].latest = hc;
-        leaf->oth[j].visits_notset += 1; leaf->oth[j].N += 1;
+        leaf->com[j].cost_value = hc; leaf->com[j].latest = hc;
+        leaf->com[j].visits_notset += 1; leaf->com[j].N += 1;
         L[j] = hc;
       }
     } else {
       G_ego = leaf->ego.G;
 #pragma unroll
-      for (int j = 0; j < J; ++j) L[j] = leaf->oth[j].latest;
+      for (int j = 0; j < J; ++j) L[j] = leaf->com[j].latest;
     }
     // ---- back-propagation: mcts.h:314-329, stage_node.h:259-271 -------------------------------------------
     backup_levels += depth;
     uint32_t level = depth, child = node;
     // the path's records were read a few microseconds ago; ask for them again in one batch in case the L1 let go
-    for (uint32_t l = 0; l < depth; ++l) hyp_prefetch_node(nodes + path_node[l]);
+    for (uint32_t l = 0; l < depth; ++l) hyp_prefetch_node<Node, J>(nodes + path_node[l], hyp);
 #pragma unroll 1
     while (level > 0) {
       level -= 1;
@@ -408,27 +439,29 @@ __global__ void __launch_bounds__(kSearchThreads, MAMCTS_HYP_MIN_BLOCKS) hyp_sea
       double ac0[J], cv0[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const HypOther& o = pn->oth[j];
-        const uint32_t h = hyp[j], a = path_ja[level][j + 1];
-        cnt0[j] = o.count[h][a]; ac0[j] = o.cost[h][a]; nh0[j] = o.visits_h[h]; cv0[j] = o.cost_value;
-        N0[j] = o.N; nt0[j] = o.nexp_total;
+        const HypHyp& o = pn->hyp[j][hyp[j]];
+        const HypCommon& cm = pn->com[j];
+        const uint32_t a = path_ja[level][j + 1];
+        cnt0[j] = o.count[a]; ac0[j] = o.cost[a]; nh0[j] = o.visits; cv0[j] = cm.cost_value;
+        N0[j] = cm.N; nt0[j] = cm.nexp_total;
       }
       G_ego = back_apply<NE>(&pn->ego, path_ja[level][0], path_back[level], r0, p.gamma, G_ego);
 #pragma unroll
       for (int j = 0; j < J; ++j) {   // HypothesisStatistic::update_statistic, :112-134
-        HypOther& o = pn->oth[j];
-        const uint32_t h = hyp[j], a = path_ja[level][j + 1];
+        HypHyp& o = pn->hyp[j][hyp[j]];
+        HypCommon& cm = pn->com[j];
+        const uint32_t a = path_ja[level][j + 1];
         const double Lc = L[j];
         const double Ln = hp.chance ? (cw < Lc ? Lc : cw) : __dadd_rn(cw, __dmul_rn(p.gamma, Lc));
-        o.latest = Ln;
+        cm.latest = Ln;
         const uint32_t cnt = cnt0[j] + 1;
-        o.count[h][a] = cnt;
-        o.cost[h][a] = __dadd_rn(ac0[j], __ddiv_rn(__dsub_rn(Ln, ac0[j]), (double)cnt));
+        o.count[a] = cnt;
+        o.cost[a] = __dadd_rn(ac0[j], __ddiv_rn(__dsub_rn(Ln, ac0[j]), (double)cnt));
         const uint32_t nh = nh0[j] + 1;
-        o.visits_h[h] = nh;
-        o.cost_value = __dadd_rn(cv0[j], __ddiv_rn(__dsub_rn(Ln, cv0[j]), (double)nh));
-        o.N = N0[j] + 1;
-        o.nexp_total = nt0[j] + 1;
+        o.visits = nh;
+        cm.cost_value = __dadd_rn(cv0[j], __ddiv_rn(__dsub_rn(Ln, cv0[j]), (double)nh));
+        cm.N = N0[j] + 1;
+        cm.nexp_total = nt0[j] + 1;
         L[j] = Ln;
       }
       child = path_node[level];
@@ -453,7 +486,7 @@ __global__ void hyp_reset_kernel(void* nodes_v, uint32_t* tree_nodes, uint32_t* 
   if (tree >= T) return;
   Node* root = static_cast<Node*>(nodes_v) + (size_t)tree * max_nodes;
   uint4* w = reinterpret_cast<uint4*>(root);
-  for (size_t i = 0; i < sizeof(Node) / 16; ++i) w[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = 0; i < offsetof(Node, hyp) / 16; ++i) w[i] = make_uint4(0u, 0u, 0u, 0u);   // see HypNode
   root->parent = kNoParent;
   for (int i = 0; i <= J; ++i) { root->x[i] = root_x[i]; root->last[i] = root_last[i]; }
   tree_nodes[tree] = 1;
@@ -600,19 +633,23 @@ struct SearchH final : public mamcts_search {
           eo[3 + nE + k] = ex ? nd.ego.Q[k] : 0.0;
         }
         for (int j = 0; j < J; ++j) {
-          const HypOther& o = nd.oth[j];
+          const HypCommon& o = nd.com[j];
           double* oo = r + 4 + (3 + 2 * nE) + j * per_other;
           oo[0] = o.N; oo[1] = o.cost_value; oo[2] = o.latest; oo[3] = o.nexp_total; oo[4] = o.visits_notset; oo[5] = 0.0;
           for (uint32_t h = 0; h < H; ++h) {
+            // a hypothesis the agent never chose under at this node: its line was never initialised - nothing in it
+            HypHyp empty;
+            std::memset(&empty, 0, sizeof(empty));
+            const HypHyp& q = o.seen[h] ? nd.hyp[j][h] : empty;
             double* oh = oo + 6 + h * (2 + MA);
-            oh[0] = o.seen_h[h] ? (double)o.visits_h[h] : -1.0;
-            oh[1] = o.seen_h[h] ? (double)o.nexp_h[h] : -1.0;
-            for (uint32_t k = 0; k < MA; ++k) oh[2 + k] = k < o.nexp_h[h] ? (double)o.order[h][o.nexp_h[h] - 1u - k] : -1.0;
+            oh[0] = o.seen[h] ? (double)q.visits : -1.0;
+            oh[1] = o.seen[h] ? (double)q.nexp : -1.0;
+            for (uint32_t k = 0; k < MA; ++k) oh[2 + k] = k < q.nexp ? (double)q.order[q.nexp - 1u - k] : -1.0;
             double* oc = oo + 6 + H * (2 + MA) + 2 * h * MA;
             for (uint32_t k = 0; k < MA; ++k) {
-              const bool pr = (o.present[h] >> k) & 1u;
-              oc[2 * k] = pr ? (double)o.count[h][k] : -1.0;
-              oc[2 * k + 1] = pr ? o.cost[h][k] : 0.0;
+              const bool pr = (q.present >> k) & 1u;
+              oc[2 * k] = pr ? (double)q.count[k] : -1.0;
+              oc[2 * k + 1] = pr ? q.cost[k] : 0.0;
             }
           }
         }
