@@ -378,8 +378,6 @@ def measure_rollout_c3(engine, stream, world=1, rank=0, steps=5, warmup=3, dist=
             dist.all_reduce(ag, op=dist.ReduceOp.SUM)
         out.update({"e2e_env_steps_per_s": float(ag[1]) / float(mx2[0]), "e2e_h2d_bytes": int(xh.nbytes),
                     "e2e_d2h_bytes": int(8 * n * (A + 2) + 8 + 8 * (2 * A + 1))})
-    if rank == 0 and e2e:
-        out["variants"] = _c3_variants(engine, stream, mp, A, K, steps)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
     bytes_per_rollout = 16 * A + 8 * 1 + 8
@@ -469,9 +467,10 @@ def measure_c5_strong(engine, stream, world, rank, dist, steps=5, warmup=2):
     }
 
 
-def _c3_variants(engine, stream, mp, A, K, steps):
-    """The two other C3 inputs SURVEY.md 8(d) names, on one GPU, device-resident, same kernel and call as the main
-    section: (1) longer, branchier episodes - CHAIN_LENGTH = 41, EGO_GOAL_POS = 26, the reference's own 4-agent
+def _c3_variants(engine, stream, steps=5):
+    """The two other C3 inputs SURVEY.md 8(d) names, on ONE GPU (rank 0, called after the engine's communicator is
+    gone: a call that asks for the moments all-reduces them when a communicator is attached, which a single rank must
+    never do - so these calls do not ask for them either), device-resident, same kernel as the main section: (1) longer, branchier episodes - CHAIN_LENGTH = 41, EGO_GOAL_POS = 26, the reference's own 4-agent
     setting (environments/tests/crossing_state_int_test.cc:232-235) with C3's 8 agents; (2) a ragged batch as a
     leaf-parallel search hands it over: start states at depths 1..6 instead of the decision state - every slot's
     state is what 1..6 random joint actions lead to (produced by the same entry point: a rollout capped at that
@@ -481,6 +480,8 @@ def _c3_variants(engine, stream, mp, A, K, steps):
     from mamcts_b200 import default_crossing_params, default_params
     from mamcts_b200._abi import SRC_PHILOX
     dev = torch.device("cuda", engine.device)
+    mp = default_params(rh_max_number_of_iterations=DEPTH_CAP)
+    A, K = C3_OTHERS + 1, 256
     n = C3_ROLLOUTS // K
     res = {}
 
@@ -489,13 +490,11 @@ def _c3_variants(engine, stream, mp, A, K, steps):
             ego = torch.zeros(n, dtype=torch.float64, device=dev)
             oth = torch.zeros((A - 1, n), dtype=torch.float64, device=dev)
             tot = torch.zeros(1, dtype=torch.int64, device=dev)
-            mom = torch.zeros(2 * A + 1, dtype=torch.float64, device=dev)
         def one(i):
             engine.rollout_crossing_device(mp, cp, n, K, x_t.data_ptr(), ego.data_ptr(), oth.data_ptr(), 0, 0,
                                            tot.data_ptr(), d_flags=flags_t.data_ptr() if flags_t is not None else 0,
                                            d_depth=depth_t.data_ptr() if depth_t is not None else 0,
-                                           kind=SRC_PHILOX, d_moments=mom.data_ptr(), seed=1000,
-                                           stream_hi_base=1000 + i, stream_lo_base=0)
+                                           kind=SRC_PHILOX, seed=1000, stream_hi_base=1000 + i, stream_lo_base=0)
         for i in range(2):
             one(i)
         torch.cuda.synchronize()
@@ -895,6 +894,12 @@ def run_native(args):
     c3 = measure_rollout_c3(engine, stream, world, rank, dist=dist if world > 1 else None) if not args.no_sections else None
     if world > 1:
         engine.comm_destroy()   # every collective of the bench is done; what follows runs on rank 0 alone
+    if rank == 0 and c3 is not None:
+        # rank 0 alone: only ever after comm_destroy() above (tests/test_bench_structure_cpu.py)
+        try:
+            c3["variants"] = _c3_variants(engine, stream)
+        except Exception as ex:   # a side section must never cost the line
+            c3["variants"] = {"error": f"{type(ex).__name__}: {ex}"}
     c4 = measure_c4_hypothesis(engine, stream) if (rank == 0 and not args.no_sections) else None
     if rank == 0:
         line["leaf_batched"] = leaf_batched
