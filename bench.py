@@ -900,11 +900,18 @@ def run_native(args):
             c3["variants"] = _c3_variants(engine, stream)
         except Exception as ex:   # a side section must never cost the line
             c3["variants"] = {"error": f"{type(ex).__name__}: {ex}"}
-    c4 = measure_c4_hypothesis(engine, stream) if (rank == 0 and not args.no_sections) else None
+    c4 = None
+    if rank == 0 and not args.no_sections:
+        try:
+            c4 = measure_c4_hypothesis(engine, stream)
+        except SystemExit:
+            raise                  # its correctness check failed: that must fail the run
+        except Exception as ex:    # e.g. not enough free HBM for 8 192 hypothesis trees: a side section, not the line
+            c4 = {"error": f"{type(ex).__name__}: {ex}"}
     if rank == 0:
         line["leaf_batched"] = leaf_batched
         line["c4_hypothesis"] = c4
-        if c4 is not None and cpu_baseline and cpu_baseline.get("c4_hypothesis"):
+        if c4 is not None and "error" not in c4 and cpu_baseline and cpu_baseline.get("c4_hypothesis"):
             c4["cpu_iterations_per_s"] = cpu_baseline["c4_hypothesis"]["iterations_per_s"]
             c4["cpu_cores"] = cpu_baseline["c4_hypothesis"]["cores"]
         line["c5_strong"] = c5
